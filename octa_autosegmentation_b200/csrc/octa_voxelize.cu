@@ -1,0 +1,525 @@
+// K6: anti-aliased capsule voxelizer for sm_100a.
+//
+// Replaces vessel_graph_generation/tree2img.py:176-280 (voxelize_forest) and :151-172
+// (getCrossSlice, mode='cuboid') of the reference.  Semantics mirrored (closed form):
+//   S = max(dims); D_i = max(ceil(S/76 + 0.03 S), dims_i); c = (D - dims)/2
+//   per edge: p1 = node1*S + c, p2 = node2*S + c, R = radius*S           (tree2img.py:243-245)
+//   bbox_i = [max(0, floor(min(p1,p2)_i - R*sqrt2)), min(D_i, ceil(max(p1,p2)_i + R*sqrt2 + 1)))  (:152-166)
+//   voxel centre v+0.5; t = ((v-p2).(p1-p2)) / |p1-p2|^2                   (:259-261)
+//   0<t<1 : I1 = 1 - (|v-(p2+t(p1-p2))| - (R-sqrt3/2))/sqrt3              (:262-271)
+//   always: I2 = 1 - (min(|v-p1|,|v-p2|) - (R-sqrt3/2))/sqrt3              (:273-278)
+//   img = max(img, I);  out = uint16(255*clip(img,0,1))                    (:279-280)
+// All arithmetic is IEEE float64 with the reference's operation order and no FMA contraction
+// (this file is compiled with -fmad=false); since quantisation is monotone, max is taken on the
+// quantised value, which makes the accumulation order-independent and exact.
+//
+// Design (B200): the volume is cut into tiles [TX][TY][TZ]; one CTA owns one tile of one graph,
+// max-accumulates in shared memory (u32 per voxel, smem atomicMax across warps, one warp per
+// edge) and then streams the tile out once as u16 with 16-byte stores -- the HBM traffic is the
+// algorithmic 2 bytes/voxel, no float scratch volume and no global atomics.  Edges are binned to
+// tiles by three small kernels (prep/count, scan, fill).  Edges that overlap more than KBIG tiles
+// go to a per-graph "big" list that every tile tests, which bounds the workspace at
+// (sizeof(VoxEdge) + 4*KBIG + 4) bytes per edge for ANY input.
+#include "octa_common.h"
+#include <math.h>
+
+namespace {
+
+constexpr int KBIG = 32;          // max tiles an edge may be listed in before it becomes a "big" edge
+constexpr int TILE_Y = 32;
+constexpr int TILE_Z_MAX = 64;
+constexpr int VOX_THREADS = 256;
+
+struct VoxEdge {   // 80 bytes
+    double p1[3];
+    double p2[3];
+    double R;
+    int lo[3];     // inclusive
+    int hi[3];     // exclusive; lo == hi on any axis -> edge contributes nothing
+};
+
+struct VoxGeom {
+    int D[3];        // output volume dims (image_dim)
+    int T[3];        // tile dims
+    int nt[3];       // tiles per axis
+    int ntiles;      // nt[0]*nt[1]*nt[2]
+    double S;        // scale_factor
+    double c[3];     // pos_correction
+    double zfix;     // image_dim[2]//2 as double (ignore_z)
+    int ignore_z;
+    double min_radius, max_radius;
+};
+
+__device__ __forceinline__ int imin(int a, int b) { return a < b ? a : b; }
+__device__ __forceinline__ int imax(int a, int b) { return a > b ? a : b; }
+
+// clamp a double to int range before conversion (floor/ceil results of wild inputs)
+__device__ __forceinline__ int d2i_sat(double v) {
+    if (!(v > -2.0e9)) return -2000000000;
+    if (v > 2.0e9) return 2000000000;
+    return (int)v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// prep: one thread per edge.  mode 0 = count tiles, mode 1 = fill tile lists.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tile_range(const VoxEdge& e, const VoxGeom& g, int tlo[3], int thi[3], int& n) {
+    n = 1;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        if (e.hi[a] <= e.lo[a]) { n = 0; tlo[a] = 0; thi[a] = -1; continue; }
+        tlo[a] = e.lo[a] / g.T[a];
+        thi[a] = (e.hi[a] - 1) / g.T[a];
+        if (n) n *= (thi[a] - tlo[a] + 1);
+    }
+    if (e.hi[0] <= e.lo[0] || e.hi[1] <= e.lo[1] || e.hi[2] <= e.lo[2]) n = 0;
+}
+
+__global__ void vox_prep_kernel(const double* __restrict__ edges7, const int64_t* __restrict__ edge_offsets,
+                                int n_graphs, VoxGeom g, VoxEdge* __restrict__ prep,
+                                int* __restrict__ tile_count, int* __restrict__ big_count,
+                                int* __restrict__ big_idx) {
+    const int64_t n_edges = edge_offsets[n_graphs];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_edges) return;
+    // graph of this edge: binary search in the (small) offsets array
+    int lo = 0, hi = n_graphs;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (edge_offsets[mid] <= i) lo = mid; else hi = mid;
+    }
+    const int gr = lo;
+    const double* e7 = edges7 + i * 7;
+    VoxEdge e;
+    const double radius = e7[6];
+    const bool keep = !(radius < g.min_radius || radius > g.max_radius);   // tree2img.py:227
+    e.R = radius * g.S;                                                    // :243
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        e.p1[a] = e7[a] * g.S + g.c[a];                                    // :244 (mul, then add; -fmad=false)
+        e.p2[a] = e7[3 + a] * g.S + g.c[a];                                // :245
+    }
+    if (g.ignore_z) { e.p1[2] = g.zfix; e.p2[2] = g.zfix; }                // :247-249
+    const double off = e.R * 1.4142135623730951;                           // :152  (radius/voxel_size)*sqrt(2)
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        double s = e.p1[a], t = e.p2[a];
+        if (s > t) { double tmp = s; s = t; t = tmp; }                     // :155-160
+        int l = d2i_sat(floor(s - off));                                   // :161
+        int h = d2i_sat(ceil(t + off + 1.0));                              // :162
+        e.lo[a] = imax(0, l);
+        e.hi[a] = imin(g.D[a], h);
+        if (!keep || !(e.hi[a] > e.lo[a])) { e.lo[a] = 0; e.hi[a] = 0; }
+    }
+    if (!keep) { e.lo[0] = e.hi[0] = 0; }
+    prep[i] = e;
+    int tlo[3], thi[3], n;
+    tile_range(e, g, tlo, thi, n);
+    if (n == 0) return;
+    if (n > KBIG) {
+        int pos = atomicAdd(&big_count[gr], 1);
+        big_idx[edge_offsets[gr] + pos] = (int)(i - edge_offsets[gr]);
+        return;
+    }
+    int* tc = tile_count + (size_t)gr * g.ntiles;
+    for (int tx = tlo[0]; tx <= thi[0]; ++tx)
+        for (int ty = tlo[1]; ty <= thi[1]; ++ty)
+            for (int tz = tlo[2]; tz <= thi[2]; ++tz)
+                atomicAdd(&tc[(tx * g.nt[1] + ty) * g.nt[2] + tz], 1);
+}
+
+// one CTA per graph: exclusive scan of that graph's tile counts -> starts (+ cursor copy)
+__global__ void vox_scan_kernel(const int* __restrict__ tile_count, int* __restrict__ tile_start,
+                                int* __restrict__ tile_cursor, int ntiles) {
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    const int gr = blockIdx.x;
+    const int* cnt = tile_count + (size_t)gr * ntiles;
+    int* st = tile_start + (size_t)gr * (ntiles + 1);
+    int* cur = tile_cursor + (size_t)gr * ntiles;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int base = 0; base < ntiles; base += blockDim.x) {
+        int i = base + threadIdx.x;
+        int v = (i < ntiles) ? cnt[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_sums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int w = (lane < nw) ? warp_sums[lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            warp_sums[lane] = w;   // inclusive
+        }
+        __syncthreads();
+        int prefix = carry + (warp ? warp_sums[warp - 1] : 0) + (x - v);
+        if (i < ntiles) { st[i] = prefix; cur[i] = prefix; }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = prefix + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) st[ntiles] = carry;
+}
+
+__global__ void vox_fill_kernel(const int64_t* __restrict__ edge_offsets, int n_graphs, VoxGeom g,
+                                const VoxEdge* __restrict__ prep, int* __restrict__ tile_cursor,
+                                int* __restrict__ tile_edges) {
+    const int64_t n_edges = edge_offsets[n_graphs];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_edges) return;
+    int lo = 0, hi = n_graphs;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (edge_offsets[mid] <= i) lo = mid; else hi = mid;
+    }
+    const int gr = lo;
+    const VoxEdge e = prep[i];
+    int tlo[3], thi[3], n;
+    tile_range(e, g, tlo, thi, n);
+    if (n == 0 || n > KBIG) return;
+    int* cur = tile_cursor + (size_t)gr * g.ntiles;
+    int* lst = tile_edges + (size_t)KBIG * edge_offsets[gr];
+    const int local = (int)(i - edge_offsets[gr]);
+    for (int tx = tlo[0]; tx <= thi[0]; ++tx)
+        for (int ty = tlo[1]; ty <= thi[1]; ++ty)
+            for (int tz = tlo[2]; tz <= thi[2]; ++tz) {
+                int pos = atomicAdd(&cur[(tx * g.nt[1] + ty) * g.nt[2] + tz], 1);
+                lst[pos] = local;
+            }
+}
+
+// ---------------------------------------------------------------------------------------------
+// main kernel: one CTA = one tile of one graph
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rasterize_edge_into_tile(const VoxEdge& e, const int t0[3], const int t1[3],
+                                                         const int T[3], uint32_t* acc, int lane) {
+    // bbox of the edge clipped to this tile
+    int b0[3], n[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        b0[a] = imax(e.lo[a], t0[a]);
+        n[a] = imin(e.hi[a], t1[a]) - b0[a];
+        if (n[a] <= 0) return;
+    }
+    const int nyz = n[1] * n[2];
+    const int total = n[0] * nyz;
+    const float inv_nyz = 1.0f / (float)nyz, inv_nz = 1.0f / (float)n[2];
+
+    // exact fp64 per-edge constants (tree2img.py:259-261,269)
+    const double s0 = e.p1[0] - e.p2[0], s1 = e.p1[1] - e.p2[1], s2 = e.p1[2] - e.p2[2];
+    const double ss = (s0 * s0 + s1 * s1) + s2 * s2;
+    const double SQRT3 = 1.7320508075688772;          // np.linalg.norm([1,1,1]) (:214)
+    const double rr = e.R - SQRT3 / 2;                // (radius - voxel_diag/2)
+
+    // fp32 broad phase in box-local coordinates (conservative: only rejects voxels whose exact
+    // contribution is <= 0, which never changes a max that starts at 0)
+    const float a0 = (float)(e.p2[0] - (double)b0[0] - 0.5), a1 = (float)(e.p2[1] - (double)b0[1] - 0.5),
+                a2 = (float)(e.p2[2] - (double)b0[2] - 0.5);
+    const float f0 = (float)s0, f1 = (float)s1, f2 = (float)s2;
+    const float fss = (float)ss;
+    const float inv_ss = fss > 0.f ? 1.0f / fss : 0.f;
+    const float ext = fabsf(a0) + fabsf(a1) + fabsf(a2) + fabsf(f0) + fabsf(f1) + fabsf(f2) + (float)(n[0] + n[1] + n[2]);
+    const float reach = (float)e.R + 0.8660254f + 0.02f + 8e-6f * ext;
+    const float thr = reach * reach;
+
+    for (int i = lane; i < total; i += 32) {
+        int ix = (int)((float)i * inv_nyz);
+        int r = i - ix * nyz;
+        if (r < 0) { --ix; r += nyz; } else if (r >= nyz) { ++ix; r -= nyz; }
+        int iy = (int)((float)r * inv_nz);
+        int iz = r - iy * n[2];
+        if (iz < 0) { --iy; iz += n[2]; } else if (iz >= n[2]) { ++iy; iz -= n[2]; }
+
+        const float w0 = (float)ix - a0, w1 = (float)iy - a1, w2 = (float)iz - a2;
+        float tf = (w0 * f0 + w1 * f1 + w2 * f2) * inv_ss;
+        tf = fminf(fmaxf(tf, 0.f), 1.f);
+        const float d0 = w0 - tf * f0, d1 = w1 - tf * f1, d2 = w2 - tf * f2;
+        if (d0 * d0 + d1 * d1 + d2 * d2 > thr) continue;
+
+        // exact path
+        const double vx = (double)(b0[0] + ix) + 0.5, vy = (double)(b0[1] + iy) + 0.5, vz = (double)(b0[2] + iz) + 0.5;
+        const double u0 = vx - e.p2[0], u1 = vy - e.p2[1], u2 = vz - e.p2[2];
+        const double t = ((u0 * s0 + u1 * s1) + u2 * s2) / ss;
+        const double q0 = vx - e.p1[0], q1 = vy - e.p1[1], q2 = vz - e.p1[2];
+        const double dcap = fmin(sqrt((q0 * q0 + q1 * q1) + q2 * q2), sqrt((u0 * u0 + u1 * u1) + u2 * u2));
+        double I = 1.0 - ((dcap - rr) / SQRT3);
+        if (t > 0.0 && t < 1.0) {
+            const double e0 = vx - (e.p2[0] + t * s0), e1 = vy - (e.p2[1] + t * s1), e2 = vz - (e.p2[2] + t * s2);
+            const double dl = sqrt((e0 * e0 + e1 * e1) + e2 * e2);
+            const double I1 = 1.0 - ((dl - rr) / SQRT3);
+            I = fmax(I, I1);
+        }
+        if (!(I > 0.0)) continue;
+        const double cl = I < 1.0 ? I : 1.0;
+        const uint32_t q = (uint32_t)(255.0 * cl);
+        if (q == 0) continue;
+        const int lx = b0[0] + ix - t0[0], ly = b0[1] + iy - t0[1], lz = b0[2] + iz - t0[2];
+        atomicMax(&acc[(lx * T[1] + ly) * T[2] + lz], q);
+    }
+}
+
+__global__ void __launch_bounds__(VOX_THREADS)
+vox_tile_kernel(const VoxEdge* __restrict__ prep, const int64_t* __restrict__ edge_offsets, VoxGeom g,
+                const int* __restrict__ tile_start, const int* __restrict__ tile_edges,
+                const int* __restrict__ big_count, const int* __restrict__ big_idx,
+                uint16_t* __restrict__ out) {
+    extern __shared__ __align__(16) uint32_t acc[];
+    const int gr = blockIdx.y;
+    const int tile = blockIdx.x;
+    const int tz_i = tile % g.nt[2], ty_i = (tile / g.nt[2]) % g.nt[1], tx_i = tile / (g.nt[2] * g.nt[1]);
+    const int T[3] = {g.T[0], g.T[1], g.T[2]};
+    const int t0[3] = {tx_i * T[0], ty_i * T[1], tz_i * T[2]};
+    const int t1[3] = {imin(t0[0] + T[0], g.D[0]), imin(t0[1] + T[1], g.D[1]), imin(t0[2] + T[2], g.D[2])};
+    const int tile_elems = T[0] * T[1] * T[2];
+    const int64_t e_base = edge_offsets[gr];
+    const VoxEdge* ge = prep + e_base;
+
+    const int* st = tile_start + (size_t)gr * (g.ntiles + 1);
+    const int beg = st[tile], end = st[tile + 1];
+    const int nbig = big_count[gr];
+
+    if (end > beg || nbig > 0) {
+        uint4* acc4 = reinterpret_cast<uint4*>(acc);
+        for (int i = threadIdx.x; i < tile_elems / 4; i += blockDim.x) acc4[i] = make_uint4(0, 0, 0, 0);
+        for (int i = (tile_elems / 4) * 4 + threadIdx.x; i < tile_elems; i += blockDim.x) acc[i] = 0;
+        __syncthreads();
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        const int* lst = tile_edges + (size_t)KBIG * e_base;
+        for (int k = beg + warp; k < end; k += nw) {
+            const VoxEdge e = ge[lst[k]];
+            rasterize_edge_into_tile(e, t0, t1, T, acc, lane);
+        }
+        const int* bl = big_idx + e_base;
+        for (int k = warp; k < nbig; k += nw) {
+            const VoxEdge e = ge[bl[k]];
+            rasterize_edge_into_tile(e, t0, t1, T, acc, lane);
+        }
+        __syncthreads();
+    } else {
+        // empty tile: stream zeros without touching shared memory
+        uint16_t* vol = out + (size_t)gr * g.D[0] * g.D[1] * g.D[2];
+        const int ny = t1[1] - t0[1], nz = t1[2] - t0[2];
+        for (int x = t0[0]; x < t1[0]; ++x) {
+            if (nz == g.D[2]) {
+                const size_t base = ((size_t)x * g.D[1] + t0[1]) * g.D[2];
+                const int len = ny * nz;
+                if (((base | (size_t)len) & 7) == 0) {
+                    uint4* p = reinterpret_cast<uint4*>(vol + base);
+                    for (int i = threadIdx.x; i < len / 8; i += blockDim.x) p[i] = make_uint4(0, 0, 0, 0);
+                } else {
+                    for (int i = threadIdx.x; i < len; i += blockDim.x) vol[base + i] = 0;
+                }
+            } else {
+                for (int i = threadIdx.x; i < ny * nz; i += blockDim.x) {
+                    const int y = i / nz, z = i - y * nz;
+                    vol[((size_t)x * g.D[1] + t0[1] + y) * g.D[2] + t0[2] + z] = 0;
+                }
+            }
+        }
+        return;
+    }
+
+    // stream the tile out: u32 accumulators -> u16, 2 algorithmic bytes per voxel
+    uint16_t* vol = out + (size_t)gr * g.D[0] * g.D[1] * g.D[2];
+    const int ny = t1[1] - t0[1], nz = t1[2] - t0[2];
+    for (int x = t0[0]; x < t1[0]; ++x) {
+        const uint32_t* slab = acc + (size_t)(x - t0[0]) * T[1] * T[2];
+        if (nz == g.D[2] && T[2] == g.D[2]) {
+            // (y,z) plane of this x is contiguous both in smem and in the volume
+            const size_t base = ((size_t)x * g.D[1] + t0[1]) * g.D[2];
+            const int len = ny * nz;
+            if (((base | (size_t)len) & 7) == 0) {
+                uint4* p = reinterpret_cast<uint4*>(vol + base);
+                const uint4* s4 = reinterpret_cast<const uint4*>(slab);
+                for (int i = threadIdx.x; i < len / 8; i += blockDim.x) {
+                    const uint4 a = s4[2 * i], b = s4[2 * i + 1];
+                    uint4 o;
+                    o.x = a.x | (a.y << 16); o.y = a.z | (a.w << 16);
+                    o.z = b.x | (b.y << 16); o.w = b.z | (b.w << 16);
+                    p[i] = o;
+                }
+            } else {
+                for (int i = threadIdx.x; i < len; i += blockDim.x) vol[base + i] = (uint16_t)slab[i];
+            }
+        } else {
+            for (int i = threadIdx.x; i < ny * nz; i += blockDim.x) {
+                const int y = i / nz, z = i - y * nz;
+                vol[((size_t)x * g.D[1] + t0[1] + y) * g.D[2] + t0[2] + z] = (uint16_t)slab[y * T[2] + z];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+int make_geom(const int dims[3], const OctaVoxOpts* opts, VoxGeom* g) {
+    OCTA_ARG_CHECK(dims && dims[0] > 0 && dims[1] > 0 && dims[2] > 0, "volume dimensions must be positive");
+    int S = dims[0] > dims[1] ? dims[0] : dims[1];
+    if (dims[2] > S) S = dims[2];
+    OCTA_ARG_CHECK(S <= 16384, "volume dimension too large");
+    // tree2img.py:206-211
+    const double MAX_RADIUS = 0.015;
+    const double sf = (double)S;
+    const int min_dim = (int)ceil((1.0 / 76) * sf + 2 * MAX_RADIUS * sf);
+    g->S = sf;
+    for (int a = 0; a < 3; ++a) {
+        g->D[a] = dims[a] > min_dim ? dims[a] : min_dim;
+        g->c[a] = (double)(g->D[a] - dims[a]) / 2;
+    }
+    g->zfix = (double)(g->D[2] / 2);
+    g->ignore_z = opts ? opts->ignore_z : 0;
+    g->min_radius = opts ? opts->min_radius : 0.0;
+    g->max_radius = opts ? opts->max_radius : 1.0;
+    g->T[1] = TILE_Y;
+    g->T[2] = g->D[2] < TILE_Z_MAX ? g->D[2] : TILE_Z_MAX;
+    g->T[0] = 16;
+    while (g->T[0] > 1 && (size_t)g->T[0] * g->T[1] * g->T[2] * 4 > 110 * 1024) g->T[0] >>= 1;
+    for (int a = 0; a < 3; ++a) g->nt[a] = (g->D[a] + g->T[a] - 1) / g->T[a];
+    g->ntiles = g->nt[0] * g->nt[1] * g->nt[2];
+    return OCTA_OK;
+}
+
+struct VoxWorkspace {
+    VoxEdge* prep;
+    int64_t* edge_offsets;
+    int* tile_count;
+    int* tile_start;
+    int* tile_cursor;
+    int* big_count;
+    int* big_idx;
+    int* tile_edges;
+    size_t bytes;
+};
+
+VoxWorkspace carve(void* base, int n_graphs, int64_t n_edges, int ntiles) {
+    VoxWorkspace w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = octa::align_up(off + bytes, 256); return (char*)base + o; };
+    w.prep = (VoxEdge*)take(sizeof(VoxEdge) * (size_t)(n_edges > 0 ? n_edges : 1));
+    w.edge_offsets = (int64_t*)take(sizeof(int64_t) * (size_t)(n_graphs + 1));
+    w.tile_count = (int*)take(sizeof(int) * (size_t)n_graphs * ntiles);
+    w.big_count = (int*)take(sizeof(int) * (size_t)n_graphs);   // directly after tile_count: one memset
+    w.tile_start = (int*)take(sizeof(int) * (size_t)n_graphs * (ntiles + 1));
+    w.tile_cursor = (int*)take(sizeof(int) * (size_t)n_graphs * ntiles);
+    w.big_idx = (int*)take(sizeof(int) * (size_t)(n_edges > 0 ? n_edges : 1));
+    w.tile_edges = (int*)take(sizeof(int) * (size_t)KBIG * (size_t)(n_edges > 0 ? n_edges : 1));
+    w.bytes = off;
+    return w;
+}
+
+}  // namespace
+
+extern "C" int octa_voxelize_out_dims(const int dims[3], int out_dims[3]) {
+    VoxGeom g;
+    int rc = make_geom(dims, nullptr, &g);
+    if (rc) return rc;
+    OCTA_ARG_CHECK(out_dims, "out_dims is null");
+    for (int a = 0; a < 3; ++a) out_dims[a] = g.D[a];
+    return OCTA_OK;
+}
+
+extern "C" size_t octa_voxelize_workspace_bytes(int n_graphs, int64_t n_edges, const int dims[3]) {
+    VoxGeom g;
+    if (n_graphs <= 0 || n_edges < 0 || make_geom(dims, nullptr, &g)) return 0;
+    return carve(nullptr, n_graphs, n_edges, g.ntiles).bytes;
+}
+
+extern "C" int octa_voxelize_batch_dev(const double* edges7_dev, const int64_t* edge_offsets_host, int n_graphs,
+                                       const int dims[3], const OctaVoxOpts* opts, uint16_t* out_dev,
+                                       void* workspace_dev, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    OCTA_ARG_CHECK(n_graphs > 0 && n_graphs <= 65535, "n_graphs must be in [1, 65535]");
+    OCTA_ARG_CHECK(edge_offsets_host && out_dev && workspace_dev, "null pointer");
+    OCTA_ARG_CHECK(edge_offsets_host[0] == 0, "edge_offsets[0] must be 0");
+    for (int i = 0; i < n_graphs; ++i)
+        OCTA_ARG_CHECK(edge_offsets_host[i + 1] >= edge_offsets_host[i], "edge_offsets must be non-decreasing");
+    const int64_t n_edges = edge_offsets_host[n_graphs];
+    OCTA_ARG_CHECK(n_edges == 0 || edges7_dev, "edges pointer is null");
+    OCTA_ARG_CHECK(n_edges < (int64_t)1 << 31, "too many edges");
+    VoxGeom g;
+    int rc = make_geom(dims, opts, &g);
+    if (rc) return rc;
+    VoxWorkspace w = carve(workspace_dev, n_graphs, n_edges, g.ntiles);
+    if (w.bytes > workspace_bytes) {
+        octa::set_error("octa_voxelize_batch_dev: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+        return OCTA_E_NOMEM;
+    }
+    OCTA_CUDA_CHECK(cudaMemcpyAsync(w.edge_offsets, edge_offsets_host, sizeof(int64_t) * (n_graphs + 1),
+                                    cudaMemcpyHostToDevice, stream));
+    // tile_count and big_count are adjacent (256-byte aligned carve) -> clear both
+    OCTA_CUDA_CHECK(cudaMemsetAsync(w.tile_count, 0, (char*)w.tile_start - (char*)w.tile_count, stream));
+    if (n_edges > 0) {
+        const int threads = 128;
+        const int blocks = (int)((n_edges + threads - 1) / threads);
+        vox_prep_kernel<<<blocks, threads, 0, stream>>>(edges7_dev, w.edge_offsets, n_graphs, g, w.prep,
+                                                        w.tile_count, w.big_count, w.big_idx);
+        octa::count_launch();
+    }
+    vox_scan_kernel<<<n_graphs, 1024, 0, stream>>>(w.tile_count, w.tile_start, w.tile_cursor, g.ntiles);
+    octa::count_launch();
+    if (n_edges > 0) {
+        const int threads = 128;
+        const int blocks = (int)((n_edges + threads - 1) / threads);
+        vox_fill_kernel<<<blocks, threads, 0, stream>>>(w.edge_offsets, n_graphs, g, w.prep, w.tile_cursor,
+                                                        w.tile_edges);
+        octa::count_launch();
+    }
+    const size_t smem = (size_t)g.T[0] * g.T[1] * g.T[2] * sizeof(uint32_t);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        OCTA_CUDA_CHECK(cudaFuncSetAttribute(vox_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    dim3 grid((unsigned)g.ntiles, (unsigned)n_graphs);
+    vox_tile_kernel<<<grid, VOX_THREADS, smem, stream>>>(w.prep, w.edge_offsets, g, w.tile_start, w.tile_edges,
+                                                         w.big_count, w.big_idx, out_dev);
+    octa::count_launch();
+    OCTA_CUDA_CHECK(cudaGetLastError());
+    return OCTA_OK;
+}
+
+extern "C" int octa_voxelize_host(const double* edges7, int64_t n_edges, const int dims[3], const OctaVoxOpts* opts,
+                                  uint16_t* out) {
+    OCTA_ARG_CHECK(n_edges >= 0 && out, "bad arguments");
+    OCTA_ARG_CHECK(n_edges == 0 || edges7, "edges pointer is null");
+    if (octa_device_count() <= 0) {
+        octa::set_error("octa_voxelize_host: no CUDA device (there is no CPU fallback)");
+        return OCTA_E_CUDA;
+    }
+    VoxGeom g;
+    int rc = make_geom(dims, opts, &g);
+    if (rc) return rc;
+    const size_t vol_bytes = (size_t)g.D[0] * g.D[1] * g.D[2] * sizeof(uint16_t);
+    const size_t ws_bytes = octa_voxelize_workspace_bytes(1, n_edges, dims);
+    double* d_edges = nullptr;
+    uint16_t* d_out = nullptr;
+    void* d_ws = nullptr;
+    auto cleanup = [&]() { cudaFree(d_edges); cudaFree(d_out); cudaFree(d_ws); };
+    cudaError_t ce;
+    if ((ce = cudaMalloc(&d_edges, sizeof(double) * 7 * (size_t)(n_edges ? n_edges : 1))) != cudaSuccess ||
+        (ce = cudaMalloc(&d_out, vol_bytes)) != cudaSuccess || (ce = cudaMalloc(&d_ws, ws_bytes)) != cudaSuccess) {
+        octa::set_error("octa_voxelize_host: cudaMalloc failed: %s", cudaGetErrorString(ce));
+        cleanup();
+        return OCTA_E_NOMEM;
+    }
+    if (n_edges) ce = cudaMemcpy(d_edges, edges7, sizeof(double) * 7 * (size_t)n_edges, cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) { octa::set_error("H2D failed: %s", cudaGetErrorString(ce)); cleanup(); return OCTA_E_CUDA; }
+    const int64_t offs[2] = {0, n_edges};
+    rc = octa_voxelize_batch_dev(d_edges, offs, 1, dims, opts, d_out, d_ws, ws_bytes, nullptr);
+    if (rc == OCTA_OK) {
+        ce = cudaMemcpy(out, d_out, vol_bytes, cudaMemcpyDeviceToHost);
+        if (ce != cudaSuccess) { octa::set_error("D2H failed: %s", cudaGetErrorString(ce)); rc = OCTA_E_CUDA; }
+    }
+    cleanup();
+    return rc;
+}

@@ -1,0 +1,66 @@
+"""Generates the fixtures under tests/golden/ from the UNMODIFIED reference (build container only).
+
+    python oracle/make_golden.py [--full]
+
+  graph_small_s{0,1}.csv      seeded growth, docker config cut to I=(12,12), N=400     (ref_harness.run_growth)
+  graph_docker_s0.csv.gz      seeded growth, docker config verbatim, seed 0  (needs --full, ~100 s)
+  vox_small_s0_*.npz          tree2img.voxelize_forest of graph_small_s0.csv for several requests
+  vox_docker_s0.json          sha256 / non-zero count of voxelize_forest(graph_docker_s0, [304,304,4]) and,
+                              with --full, of the [1216,1216,16] request (77 s in the reference)
+"""
+import argparse
+import gzip
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ref_harness as rh  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def digest(a: np.ndarray) -> dict:
+    return {"shape": list(a.shape), "dtype": str(a.dtype), "nonzero": int((a > 0).sum()), "sum": int(a.astype(np.int64).sum()),
+            "sha256": hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--full", action="store_true")
+    a = ap.parse_args()
+    os.makedirs(GOLD, exist_ok=True)
+    for seed in (0, 1):
+        art, ven, _ = rh.run_growth(rh.small_config(), seed)
+        with open(os.path.join(GOLD, "graph_small_s%d.csv" % seed), "wb") as f:
+            f.write(rh.csv_bytes(art, ven))
+    rows = rh.read_csv_rows(os.path.join(GOLD, "graph_small_s0.csv"))
+    cases = {"304x304x4": ([304, 304, 4], {}), "304x304x4_ignz": ([304, 304, 4], {"ignore_z": True}),
+             "100x80x30_minr": ([100, 80, 30], {"min_radius": 0.001}), "64x64x64": ([64, 64, 64], {}),
+             "96x96x130": ([96, 96, 130], {})}
+    for name, (dims, kw) in cases.items():
+        vol, _ = rh.voxelize(rows, dims, **kw)
+        np.savez_compressed(os.path.join(GOLD, "vox_small_s0_%s.npz" % name), vol=vol, dims=np.array(dims),
+                            kw=json.dumps(kw))
+    if a.full:
+        p = os.path.join(GOLD, "graph_docker_s0.csv.gz")
+        if not os.path.exists(p):
+            art, ven, _ = rh.run_growth(rh.load_config(), 0)
+            with gzip.GzipFile(p, "wb", mtime=0) as f:
+                f.write(rh.csv_bytes(art, ven))
+        import csv, io
+        rows = list(csv.DictReader(io.StringIO(gzip.open(p, "rt", newline="").read(), newline="")))
+        out = {}
+        for dims in ([304, 304, 4], [1216, 1216, 16]):
+            vol, _ = rh.voxelize(rows, dims)
+            out["x".join(map(str, dims))] = digest(vol)
+            print(dims, out["x".join(map(str, dims))])
+        with open(os.path.join(GOLD, "vox_docker_s0.json"), "w") as f:
+            json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
