@@ -1,0 +1,117 @@
+"""CPU: pins oracle/growth_oracle.cpp to the real reference.
+
+The graph_*.csv fixtures were written by oracle/ref_harness.py from the UNMODIFIED reference modules
+(seeded random / np.random); the oracle must reproduce them byte for byte.  The emulated pieces
+(two MT19937 streams, CPython set order, cKDTree index permutation) are additionally checked
+against the real CPython / numpy / scipy in this interpreter."""
+import gzip
+import hashlib
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import growth_oracle as go
+
+
+def docker_config():
+    from octa_autosegmentation_b200.config import default_config
+    return default_config()
+
+
+def small_config():
+    cfg = docker_config()
+    for m, i in zip(cfg["Greenhouse"]["modes"], (12, 12)):
+        m["I"], m["N"] = i, 400
+    return cfg
+
+
+def oracle_csv(cfg, seed, **kw):
+    art, ven, st = go.run(cfg, seed, **kw)
+    return go.csv_bytes(np.concatenate([art, ven])), st
+
+
+def test_python_random_stream():
+    for seed in (0, 1, 12345, 2**31 + 7, 2**40 + 3):
+        out = np.empty(50)
+        go.lib().og_py_random(seed, 50, out.ctypes.data)
+        random.seed(seed)
+        assert [random.random() for _ in range(50)] == list(out)
+        ch = (np.zeros(64, dtype=np.int32))
+        go.lib().og_py_choice(seed, 4, 64, ch.ctypes.data)
+        random.seed(seed)
+        assert [random.choice([0, 1, 2, 3]) for _ in range(64)] == list(ch)
+
+
+def test_numpy_legacy_stream():
+    import ctypes
+    for seed in (0, 7, 4242):
+        nrm = ctypes.c_double()
+        ints = np.zeros(3000, dtype=np.uint32)
+        dbl = np.zeros(999)
+        go.lib().og_np_stream(seed, ctypes.byref(nrm), 3000, 5663, ints.ctypes.data, 999, dbl.ctypes.data)
+        np.random.seed(seed)
+        assert np.random.normal(0.25, 0.5) == nrm.value
+        assert np.array_equal(np.random.randint(0, 5663, 3000), ints)
+        assert np.array_equal(np.random.uniform(0, 1, (333, 3)).ravel(), dbl)
+
+
+def test_cpython_tuple_hash_and_set_order():
+    rng = np.random.RandomState(0)
+    for trial in range(200):
+        n = int(rng.randint(1, 400))
+        pts = rng.uniform(-0.01, 1.01, (n, 3))
+        dup = rng.randint(0, n, n // 5)
+        pts = np.concatenate([pts, pts[dup]])          # duplicates, as when two new nodes hit one sink
+        pts = pts[rng.permutation(len(pts))]
+        tuples = [tuple(np.float64(v) for v in p) for p in pts]
+        assert go.lib().og_hash_tuple3(np.ascontiguousarray(pts[0]).ctypes.data) == hash(tuples[0])
+        s = set()
+        for t in tuples:
+            s.add(t)
+        order = np.zeros(len(pts), dtype=np.int64)
+        k = go.lib().og_set_order(np.ascontiguousarray(pts).ctypes.data, len(pts), order.ctypes.data)
+        assert [tuples[i] for i in order[:k]] == list(s)
+
+
+def test_ckdtree_index_permutation():
+    from scipy.spatial import cKDTree
+    rng = np.random.RandomState(1)
+    for trial in range(60):
+        n = int(rng.randint(1, 3000))
+        pts = rng.uniform(0, 1, (n, 3)) * np.array([1, 1, 0.0131])
+        if trial % 7 == 0:
+            pts[:, 2] = 0.005                      # zero extent along one axis
+        idx = np.zeros(n, dtype=np.int64)
+        go.lib().og_kd_indices(np.ascontiguousarray(pts).ctypes.data, n, idx.ctypes.data)
+        tree = cKDTree(pts)
+        assert np.array_equal(tree.indices, idx)
+        # ball results come back in ascending position of tree.indices
+        rank = np.empty(n, dtype=np.int64)
+        rank[idx] = np.arange(n)
+        q = pts[rng.randint(n)]
+        hits = tree.query_ball_point(q, 0.08)
+        assert list(hits) == sorted(hits, key=lambda i: rank[i])
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_small_config_byte_exact(seed):
+    got, _ = oracle_csv(small_config(), seed)
+    assert got == open(os.path.join(GOLDEN, "graph_small_s%d.csv" % seed), "rb").read()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_docker_config_byte_exact(seed):
+    """BASELINE config #1: docker/vessel_graph_gen_docker_config.yml, fixed seed."""
+    got, st = oracle_csv(docker_config(), seed)
+    dig = json.load(open(os.path.join(GOLDEN, "graph_docker_digests.json")))["docker_s%d" % seed]
+    assert len(got) == dig["bytes"] and hashlib.sha256(got).hexdigest() == dig["sha256"]
+    p = os.path.join(GOLDEN, "graph_docker_s%d.csv.gz" % seed)
+    if os.path.exists(p):
+        assert got == gzip.open(p, "rb").read()
+    if seed == 0:   # counts measured on the reference itself
+        assert st["py_draws"] == 14778 and st["nn_queries"] == 1820486 and st["bifurcations"] == 41
+        assert st["n_art_nodes"] == 9033 and st["n_ven_nodes"] == 3965 and st["n_oxy_left"] == 12127 and st["n_co2_left"] == 3567
