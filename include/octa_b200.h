@@ -76,6 +76,18 @@ int octa_voxelize_batch_dev(const double* edges7_dev, const int64_t* edge_offset
 int octa_voxelize_host(const double* edges7, int64_t n_edges, const int dims[3], const OctaVoxOpts* opts,
                        uint16_t* out);
 
+/* ------------------------------------------------------------------------------------------------
+ * Test hooks (host-only code paths of host/device-shared building blocks; used by the CPU tests).
+ * ---------------------------------------------------------------------------------------------- */
+/* 3x3 symmetric eigenproblem with LAPACK dgeev's ordering and sign (greenhouse.py:229). cov9/v9 row-major;
+ * column k of v9 is the unit eigenvector of w3[k].  Returns 0 ok, 1 complex/equal pair left, 2 no convergence. */
+int octa_test_eig3(const double* cov9, double* w3, double* v9);
+int octa_test_eig3_debug(const double* cov9, double* w3, double* v9, double* dbg48);
+/* d_l of greenhouse.py:230-233: real part of the eigenvector of argmax(w); 0 ok, 2 no convergence, 3 complex principal pair */
+int octa_test_principal_axis(const double* cov9, double* dl3);
+/* CPython hash((np.float64 x, y, z)) (greenhouse.py:100-111 set ordering) */
+int64_t octa_test_hash_tuple3(const double* xyz);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,7 +70,7 @@ typedef void (*og_trace_hook)(int t, long n_art, long n_oxy, long n_ven, long n_
 struct OGStats {
     long n_art_nodes, n_ven_nodes, n_oxy_left, n_co2_left, py_draws, np_u32, nn_queries, ball_queries,
         bifurcations, sprouts, elongations, walk_steps, sum_A, sum_M, sum_P, sum_S,
-        multi_balls, reordered_balls, interacting_groups, kd_builds;
+        multi_balls, reordered_balls, interacting_groups, kd_builds, inter_evals, inter_r1_changed, max_dict, max_list;
 };
 }
 
@@ -724,6 +724,10 @@ struct Sim {
         }
         std::vector<char> deactivate(fo.nodes.size(), 0);
         bool any_deact = false;
+        std::vector<double> radius_at_start(fo.nodes.size());
+        for (size_t i = 0; i < fo.nodes.size(); ++i) radius_at_start[i] = fo.nodes[i].radius;
+        if ((long)order.size() > st.max_dict) st.max_dict = (long)order.size();
+        for (auto& l : lists) if ((long)l.size() > st.max_list) st.max_list = (long)l.size();
         std::vector<double> ang, angp, unit, sel;
         for (size_t oi = 0; oi < order.size(); ++oi) {
             const int nid = order[oi];
@@ -863,6 +867,8 @@ struct Sim {
                 const Node& ch = fo.nodes[nd.child[0]];
                 const Node& par = fo.nodes[nd.parent];
                 const double r1 = ch.radius, r2 = r;
+                ++st.inter_evals;
+                if (r1 != radius_at_start[nd.child[0]]) ++st.inter_r1_changed;
                 const double rp = pow(pow(r1, kappa) + pow(r2, kappa), 1 / kappa);
                 const double phi1 = RAD2DEG * acos((pow(rp, 4.0) + pow(r1, 4.0) - pow(r2, 4.0)) / (2 * pow(rp, 2.0) * pow(r1, 2.0)));
                 const double phi2 = RAD2DEG * acos((pow(rp, 4.0) + pow(r2, 4.0) - pow(r1, 4.0)) / (2 * pow(rp, 2.0) * pow(r2, 2.0)));

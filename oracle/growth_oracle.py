@@ -35,7 +35,8 @@ class OGStats(ctypes.Structure):
     _fields_ = [(k, ctypes.c_long) for k in ("n_art_nodes", "n_ven_nodes", "n_oxy_left", "n_co2_left", "py_draws",
                                              "np_u32", "nn_queries", "ball_queries", "bifurcations", "sprouts",
                                              "elongations", "walk_steps", "sum_A", "sum_M", "sum_P", "sum_S",
-                                             "multi_balls", "reordered_balls", "interacting_groups", "kd_builds")]
+                                             "multi_balls", "reordered_balls", "interacting_groups", "kd_builds",
+                                             "inter_evals", "inter_r1_changed", "max_dict", "max_list")]
 
 
 EIG_HOOK = ctypes.CFUNCTYPE(None, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
