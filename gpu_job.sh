@@ -1,10 +1,3 @@
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
-nproc >> gpurun_out/gpu.txt
-python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
-python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2>&1
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --batch 8 --no-cpu-baseline > gpurun_out/ncu_b.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:vox_tile -s 2 -c 2 -o gpurun_out/prof_vox python bench.py --steps 1 --warmup 3 --batch 8 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
-tail -3 gpurun_out/pytest_gpu.log; cat gpurun_out/smoke.log; cat gpurun_out/bench.log | tail -2; tail -1 gpurun_out/bench_ref.log
+timeout 900 python -m pytest tests/test_growth_gpu.py -x -q > gpurun_out/pytest_growth.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_growth.log
+tail -40 gpurun_out/pytest_growth.log

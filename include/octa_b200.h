@@ -77,6 +77,61 @@ int octa_voxelize_host(const double* edges7, int64_t n_edges, const int dims[3],
                        uint16_t* out);
 
 /* ------------------------------------------------------------------------------------------------
+ * Growth -- replaces generate_vessel_graph.py:24-56 (`main` up to the edge lists):
+ *   Greenhouse(config['Greenhouse'])                      greenhouse.py:17-51
+ *   Forest(config['Forest'], ...) x2 (arterial, venous)   forest.py:15-181
+ *   greenhouse.develop_forest()                           greenhouse.py:57-137
+ *   edge lists in LevelOrderIter order, root excluded     generate_vessel_graph.py:45-56
+ * for a BATCH of independent samples.  Sample i is seeded the way the oracle harness seeds the reference:
+ * random.seed(seeds[i]); np.random.seed(seeds[i]) immediately before Greenhouse(...).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct OctaGrowMode {        /* one entry of config['Greenhouse']['modes'] (raw YAML values) */
+    int32_t I, N;
+    double eps_n, eps_s, eps_k, delta_art, delta_ven, gamma_art, gamma_ven, phi, omega, kappa, delta_sigma;
+    int32_t reinit;      /* mode['name'] != modes[0]['name']   greenhouse.py:84 */
+    int32_t first_mode;  /* mode == modes[0]                   greenhouse.py:95 */
+} OctaGrowMode;
+
+typedef struct OctaGrowConfig {
+    double d, r, faz_radius_bound[2], rotation_radius, faz_center[2], nerve_center[2], nerve_radius, param_scale;
+    double size[3];                  /* SimulationSpace no_voxel_x/y/z */
+    int32_t n_modes;
+    OctaGrowMode modes[8];
+    int32_t forest_type;             /* 0 = 'stumps', 1 = 'nerve' */
+    int32_t n_trees;
+    int32_t n_walls;
+    int32_t walls[6];                /* enabled source walls in config order: 0=x0 1=x1 2=y0 3=y1 */
+    int32_t cap_nodes, cap_sinks;    /* per-graph capacities; 0 = automatic */
+} OctaGrowConfig;
+
+typedef struct OctaGrowStats {
+    int64_t n_art_nodes, n_ven_nodes, n_oxy_left, n_co2_left, py_draws;
+    int64_t sum_A, sum_M, sum_P, sum_S;   /* byte-accounting counters of SURVEY.md 8(d) */
+    int32_t err;                     /* 0 ok; 1 node capacity, 2 sink capacity, 3 rng buffer, 4 recheck queue, 5 set table, 1x eig */
+    int32_t n_iters;
+} OctaGrowStats;
+
+/* Host-buffer entry point.  edges7_out: n_graphs * cap_edges_per_graph * 7 doubles; graph g's rows start at
+ * edges7_out + g*cap_edges_per_graph*7, arterial rows first (n_art_edges[g]) then venous (n_ven_edges[g]).
+ * trace (optional): n_graphs * 4096 * 4 int32, per iteration (art nodes, O2 sinks, venous nodes, CO2 sources).
+ * device_ms (optional): device time of the growth loop measured with CUDA events. */
+int octa_grow_batch_host(const OctaGrowConfig* cfg, const uint64_t* seeds, int n_graphs, double* edges7_out,
+                         int64_t cap_edges_per_graph, int64_t* n_art_edges, int64_t* n_ven_edges,
+                         OctaGrowStats* stats, int32_t* trace, double* device_ms);
+
+/* ------------------------------------------------------------------------------------------------
+ * Graph CSV -- replaces the writer of generate_vessel_graph.py:59-66 (csv.writer rows of
+ * [str(ndarray), str(ndarray), float]: numpy array2string + repr(float), "\r\n") and the row parser every
+ * consumer uses (tree2img.py:73-76 / :233-236, visualize_vessel_graphs.py:72-75, data_transforms.py:377-381).
+ * ---------------------------------------------------------------------------------------------- */
+/* Formats header + n_edges rows into buf (cap bytes).  *len receives the byte count (also when buf is NULL or
+ * too small, in which case OCTA_E_NOMEM is returned). */
+int octa_format_csv(const double* edges7, int64_t n_edges, char* buf, size_t cap, size_t* len);
+/* Parses CSV text; returns the number of data rows (>= 0) or a negative OCTA_E_* code.  Rows beyond cap_edges
+ * are counted but not stored. */
+int64_t octa_parse_csv(const char* text, size_t len, double* edges7_out, int64_t cap_edges);
+
+/* ------------------------------------------------------------------------------------------------
  * Test hooks (host-only code paths of host/device-shared building blocks; used by the CPU tests).
  * ---------------------------------------------------------------------------------------------- */
 /* 3x3 symmetric eigenproblem with LAPACK dgeev's ordering and sign (greenhouse.py:229). cov9/v9 row-major;

@@ -1,0 +1,238 @@
+// Byte-exact writer (and parser) of the reference's graph CSV (host code).
+//
+// generate_vessel_graph.py:59-66 writes, through csv.writer (default dialect -> "\r\n"):
+//     node1,node2,radius
+//     str(ndarray float64[3]),str(ndarray float64[3]),repr(float)
+// The two array cells follow numpy's array2string defaults (numpy/_core/arrayprint.py FloatingFormat,
+// precision=8, floatmode='maxprec'): exponential notation iff max >= 1e8 or min < 1e-4 or
+// max/min > 1000 over the non-zero |x|; positional mode prints every element as the shortest
+// round-trip digit string cut to <= 8 fractional digits, trailing zeros trimmed but the '.' kept,
+// right-aligned on the integer part and space-padded to the longest fraction; exponential mode
+// prints every element with as many fractional digits as the longest one needs (zero padded), a sign
+// and >= 2 exponent digits, non-negative numbers getting a blank where a '-' would be.  The radius
+// cell is Python's repr(float): shortest round-trip digits, fixed notation for 1e-4 <= |x| < 1e16.
+// Every consumer of the file (visualize_vessel_graphs.py:72-75, data_transforms.py:377-381,
+// tree2img.py:73-76) reads the cells back with  s[1:-1].split(" ")  /  float(s); octa_parse_csv
+// does the same.
+#include <charconv>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include "octa_common.h"
+
+namespace {
+
+struct Sci {            // value = (-1)^neg * d[0].d[1..] * 10^e10
+    bool neg;
+    std::string d;      // decimal digits, no leading zeros (except the value 0 -> "0")
+    int e10;
+};
+
+Sci shortest(double x) {
+    Sci s;
+    s.neg = signbit(x);
+    if (x == 0.0) { s.d = "0"; s.e10 = 0; return s; }
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof(buf), fabs(x), std::chars_format::scientific);
+    *r.ptr = 0;
+    // d[.ddd]e[+-]XX
+    const char* e = strchr(buf, 'e');
+    s.d.assign(1, buf[0]);
+    if (buf[1] == '.') s.d.append(buf + 2, (size_t)(e - (buf + 2)));
+    s.e10 = atoi(e + 1);
+    return s;
+}
+
+// positional digits with at most `prec` fractional digits, trailing zeros trimmed; returns int / frac parts
+void positional(double x, int prec, std::string* ip, std::string* fp) {
+    const Sci s = shortest(x);
+    const int n = (int)s.d.size();
+    const int nfrac = n - 1 - s.e10;
+    ip->clear(); fp->clear();
+    if (nfrac <= prec) {
+        if (s.e10 >= 0) {
+            ip->assign(s.d, 0, std::min(n, s.e10 + 1));
+            if (s.e10 + 1 > n) ip->append(s.e10 + 1 - n, '0');
+            if (n > s.e10 + 1) fp->assign(s.d, s.e10 + 1, std::string::npos);
+        } else {
+            *ip = "0";
+            fp->assign(-s.e10 - 1, '0');
+            fp->append(s.d);
+        }
+    } else {
+        char buf[512];
+        snprintf(buf, sizeof(buf), "%.*f", prec, fabs(x));   // exact, round-half-even on the binary value (as Dragon4's cutoff)
+        const char* dot = strchr(buf, '.');
+        ip->assign(buf, (size_t)(dot - buf));
+        fp->assign(dot + 1);
+    }
+    while (!fp->empty() && fp->back() == '0') fp->pop_back();
+    if (s.neg) ip->insert(ip->begin(), '-');
+}
+
+// scientific digits d.ddd with at most `prec` fractional digits (trimmed); exponent returned separately
+void scientific(double x, int prec, std::string* ip, std::string* fp, int* e10) {
+    const Sci s = shortest(x);
+    ip->clear(); fp->clear();
+    if ((int)s.d.size() - 1 <= prec) {
+        ip->assign(1, s.d[0]);
+        fp->assign(s.d, 1, std::string::npos);
+        *e10 = s.e10;
+    } else {
+        char buf[64];
+        snprintf(buf, sizeof(buf), "%.*e", prec, fabs(x));
+        const char* e = strchr(buf, 'e');
+        ip->assign(1, buf[0]);
+        fp->assign(buf + 2, (size_t)(e - (buf + 2)));
+        *e10 = atoi(e + 1);
+    }
+    while (!fp->empty() && fp->back() == '0') fp->pop_back();
+    if (s.neg) ip->insert(ip->begin(), '-');
+}
+
+void append_array3(std::string& out, const double* v) {
+    // FloatingFormat.fillFormat
+    double mx = 0, mn = 0;
+    bool any = false;
+    for (int i = 0; i < 3; ++i) {
+        const double a = fabs(v[i]);
+        if (a != 0.0) { if (!any) { mx = mn = a; any = true; } else { if (a > mx) mx = a; if (a < mn) mn = a; } }
+    }
+    const bool exp_format = any && (mx >= 1.e8 || mn < 0.0001 || mx / mn > 1000.);
+    std::string ip[3], fp[3];
+    out.push_back('[');
+    if (!exp_format) {
+        size_t pl = 0, pr = 0;
+        for (int i = 0; i < 3; ++i) { positional(v[i], 8, &ip[i], &fp[i]); pl = std::max(pl, ip[i].size()); pr = std::max(pr, fp[i].size()); }
+        for (int i = 0; i < 3; ++i) {
+            if (i) out.push_back(' ');
+            out.append(pl - ip[i].size(), ' ');
+            out += ip[i];
+            out.push_back('.');
+            out += fp[i];
+            out.append(pr - fp[i].size(), ' ');
+        }
+    } else {
+        int ex[3];
+        size_t pl = 0, prec = 0;
+        int exp_size = 2;
+        for (int i = 0; i < 3; ++i) {
+            scientific(v[i], 8, &ip[i], &fp[i], &ex[i]);
+            pl = std::max(pl, ip[i].size());
+            prec = std::max(prec, fp[i].size());
+            int a = abs(ex[i]), nd = 1;
+            while (a >= 10) { a /= 10; ++nd; }
+            exp_size = std::max(exp_size, nd);
+        }
+        char eb[16];
+        for (int i = 0; i < 3; ++i) {
+            if (i) out.push_back(' ');
+            out.append(pl - ip[i].size(), ' ');
+            out += ip[i];
+            out.push_back('.');
+            out += fp[i];
+            out.append(prec - fp[i].size(), '0');
+            snprintf(eb, sizeof(eb), "e%c%0*d", ex[i] < 0 ? '-' : '+', exp_size, abs(ex[i]));
+            out += eb;
+        }
+    }
+    out.push_back(']');
+}
+
+// Python repr(float)
+void append_repr(std::string& out, double x) {
+    if (x != x) { out += "nan"; return; }
+    if (isinf(x)) { out += x < 0 ? "-inf" : "inf"; return; }
+    const Sci s = shortest(x);
+    if (s.neg) out.push_back('-');
+    const int n = (int)s.d.size();
+    const int decpt = s.e10 + 1;          // digits before the decimal point
+    if (x == 0.0) { out += "0.0"; return; }
+    if (decpt > -4 && decpt <= 16) {      // float_repr_style 'short', format code 'r'
+        if (decpt <= 0) { out += "0."; out.append(-decpt, '0'); out += s.d; }
+        else if (decpt >= n) { out += s.d; out.append(decpt - n, '0'); out += ".0"; }
+        else { out.append(s.d, 0, decpt); out.push_back('.'); out.append(s.d, decpt, std::string::npos); }
+    } else {
+        out.push_back(s.d[0]);
+        if (n > 1) { out.push_back('.'); out.append(s.d, 1, std::string::npos); }
+        char eb[16];
+        snprintf(eb, sizeof(eb), "e%c%02d", s.e10 < 0 ? '-' : '+', abs(s.e10));
+        out += eb;
+    }
+}
+
+}  // namespace
+
+extern "C" int octa_format_csv(const double* edges7, int64_t n_edges, char* buf, size_t cap, size_t* len) {
+    OCTA_ARG_CHECK(n_edges >= 0 && len && (n_edges == 0 || edges7), "bad arguments");
+    std::string out;
+    out.reserve(32 + (size_t)n_edges * 100);
+    out += "node1,node2,radius\r\n";
+    for (int64_t i = 0; i < n_edges; ++i) {
+        const double* e = edges7 + 7 * i;
+        for (int k = 0; k < 7; ++k)
+            if (!(e[k] == e[k]) || isinf(e[k])) { octa::set_error("octa_format_csv: non-finite value in edge %lld", (long long)i); return OCTA_E_ARG; }
+        append_array3(out, e);
+        out.push_back(',');
+        append_array3(out, e + 3);
+        out.push_back(',');
+        append_repr(out, e[6]);
+        out += "\r\n";
+    }
+    *len = out.size();
+    if (!buf || cap < out.size()) {
+        octa::set_error("octa_format_csv: buffer too small (%zu needed)", out.size());
+        return OCTA_E_NOMEM;
+    }
+    memcpy(buf, out.data(), out.size());
+    return OCTA_OK;
+}
+
+// Reads a graph CSV the way the reference's consumers do: header line, then rows whose first two cells are
+// "[x y z]" (split on blanks, empty tokens dropped) and whose third is a float.  Returns the number of rows
+// (also when edges7_out is too small / NULL, so callers can size the buffer), or a negative error code.
+extern "C" int64_t octa_parse_csv(const char* text, size_t len, double* edges7_out, int64_t cap_edges) {
+    if (!text) { octa::set_error("octa_parse_csv: null text"); return OCTA_E_ARG; }
+    const char* p = text;
+    const char* end = text + len;
+    auto next_line = [&](const char** b, const char** e) {
+        if (p >= end) return false;
+        *b = p;
+        while (p < end && *p != '\n') ++p;
+        *e = p;
+        if (p < end) ++p;
+        while (*e > *b && ((*e)[-1] == '\r')) --*e;
+        return true;
+    };
+    const char *b, *e;
+    if (!next_line(&b, &e)) return 0;   // header
+    int64_t n = 0;
+    while (next_line(&b, &e)) {
+        if (b == e) continue;
+        double v[7];
+        const char* q = b;
+        int k = 0;
+        for (int cell = 0; cell < 2; ++cell) {
+            while (q < e && *q != '[') ++q;
+            if (q >= e) { octa::set_error("octa_parse_csv: malformed row %lld", (long long)n); return OCTA_E_ARG; }
+            ++q;
+            for (int c = 0; c < 3; ++c) {
+                while (q < e && *q == ' ') ++q;
+                char* stop = nullptr;
+                v[k++] = strtod(q, &stop);
+                if (stop == q) { octa::set_error("octa_parse_csv: malformed number in row %lld", (long long)n); return OCTA_E_ARG; }
+                q = stop;
+            }
+            while (q < e && *q != ']') ++q;
+            if (q < e) ++q;
+        }
+        while (q < e && *q != ',') ++q;
+        if (q >= e) { octa::set_error("octa_parse_csv: missing radius in row %lld", (long long)n); return OCTA_E_ARG; }
+        ++q;
+        v[6] = strtod(q, nullptr);
+        if (edges7_out && n < cap_edges) memcpy(edges7_out + 7 * n, v, sizeof(v));
+        ++n;
+    }
+    return n;
+}

@@ -1,0 +1,80 @@
+// Shared declarations of the growth kernels (octa_grow_kernels.cu) and their host driver
+// (octa_grow_host.cu).  Layout in HBM: structure-of-arrays, one slab of `cap` entries per graph, so a
+// warp walking consecutive nodes / sinks of one graph issues fully coalesced 8-byte loads and the
+// whole working set of a 64-graph batch (~100 MB) stays resident in the 126 MB L2.
+#pragma once
+#include <stdint.h>
+#include "octa_rng.h"
+
+namespace octa {
+
+constexpr int GEOMETRY_SIZE = 76;                 // simulation_space.py:8
+constexpr int MAX_VALID = GEOMETRY_SIZE * GEOMETRY_SIZE;
+constexpr int SET_TBL = 16384;                    // slots per CPython-set emulation table (x2: resize target)
+constexpr int PEND_MAX = 128;
+
+// per-iteration parameters (identical for every graph of the batch; computed on the host exactly
+// like greenhouse.py:34-51 / :139-147 evolve them)
+struct IterP {
+    double eps_n_eff, eps_s, eps_k, delta[2], gamma[2], phi, omega, kappa, d, r, rotation_radius;
+    double faz_cx, faz_cy, param_scale, shape[3];
+    int N, t, first_mode, mode_idx, iter;
+};
+
+enum PropType : int { P_NONE = 0, P_LEAF_ELONG = 1, P_LEAF_DRAW = 2, P_LEAF_BIF = 3, P_INTER_DRAW = 4, P_INTER_EMPTY = 5 };
+
+struct Proposal {
+    int type;
+    int cond;          // leaf: angle(vtc, avg) > 90 ; inter: angle(vtc, avg) <= 90
+    double ratio5;     // (dist_to_center / (2 FAZ_radius)) ** 5
+    double r1_used;    // inter-node: child radius the evaluation was made with
+    double p[3];       // elongation / sprout position
+    double b1[3], b2[3];  // bifurcation children
+};
+
+struct GrowShape {
+    int G, capN, capS, Nmax, pycap;
+};
+
+struct GrowDev {
+    // vessel nodes, [f][g*capN + i]
+    double *nx[2], *ny[2], *nz[2], *nrad[2], *nkap[2];
+    int *npar[2], *nch0[2], *nch1[2];
+    unsigned char *nnch[2], *nmeta[2], *deact[2];
+    int *n_nodes[2], *n_prev[2];
+    // active node lists (list order = element_mesh.py list order), with compacted positions
+    int *act[2], *n_act[2];
+    double *ax[2], *ay[2], *az[2];
+    // sinks: [0] oxygen sinks, [1] CO2 sources
+    double *sx[2], *sy[2], *sz[2];
+    int *n_s[2];
+    // RNG streams
+    MTState *np_mt, *py_mt;
+    unsigned int* py_buf;
+    int *py_n, *py_pos;
+    long long* py_draws;
+    // per-graph constants
+    double* faz_radius;
+    int* n_valid;
+    unsigned char* valid_ij;
+    // scratch
+    unsigned int *vi, *ubuf;
+    double *cx, *cy, *cz;
+    int* n_cand;
+    unsigned char *cpass, *cstate;
+    int* plist;
+    int *assign, *first, *cnt, *slot, *slot_call, *cur;
+    int *dict_node, *n_dict, *list_off, *list, *sc_idx;
+    double *sc_ang;
+    Proposal* prop;
+    int *alist, *n_alist;
+    int *hitj, *hl, *ta, *seq;
+    unsigned char* veto;
+    long long* set_hash;
+    int* set_key;
+    int* err;
+    int* trace;     // [g][iter][4]
+    long long* counters;  // [g][8] byte-accounting counters (sum_A, sum_M, sum_P, sum_S, ...)
+};
+
+}  // namespace octa

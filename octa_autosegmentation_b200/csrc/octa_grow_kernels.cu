@@ -1,0 +1,992 @@
+// K1-K5: space-colonization growth kernels for sm_100a (one launch = one phase for the whole batch).
+//
+// Replaces, per iteration of Greenhouse.develop_forest (greenhouse.py:90-125):
+//   k_sample        simulation_space.py:57-67 get_candidate_sinks (legacy numpy MT19937 stream on device)
+//   k_sink_tests    greenhouse.py:337-338   static rejection tests (i) arterial oxygen range, (ii) sink spacing
+//   k_sink_greedy   greenhouse.py:339-341   order-dependent spacing among new sinks (lexicographically-first MIS)
+//   k_assign        greenhouse.py:343-366   nearest ACTIVE node of every attractor (<= delta)
+//   k_group         greenhouse.py:357-365   dict order (= first-attractor order) and per-node attractor lists
+//   k_eval          greenhouse.py:174-306   per-node growth proposal (all float64 math, parallel)
+//   k_commit        greenhouse.py:191,235-239,289,303-306 + arterial_tree.py:174-184
+//                   sequential replay in dict order: Python-RNG draws, node creation, Murray walk
+//   k_kill          greenhouse.py:99-123    kill-radius prune, O2 -> CO2 through a CPython-set emulation
+// Bit-level conventions are documented in octa_grow_math.cuh.  This TU is compiled with -fmad=false.
+#include "octa_common.h"
+#include "octa_eig3.h"
+#include "octa_grow.cuh"
+#include "octa_grow_math.cuh"
+
+namespace octa {
+
+// ------------------------------------------------------------------------------------------
+// block-wide helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int block_scan_incl(int v, int* total) {
+    __shared__ int ws[33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) ws[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < nw ? ws[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += y;
+        }
+        ws[lane] = w;
+        if (lane == 31) ws[32] = w;
+    }
+    __syncthreads();
+    if (warp > 0) x += ws[warp - 1];
+    *total = ws[32];
+    __syncthreads();
+    return x;
+}
+
+// MT19937 state regeneration by a whole block (>= 256 threads); mt in shared memory
+__device__ void mt_regen_block(uint32_t* mt) {
+    const uint32_t UP = 0x80000000u, LOW = 0x7fffffffu, MAG = 0x9908b0dfu;
+    const int tid = threadIdx.x;
+    for (int phase = 0; phase < 3; ++phase) {
+        const int base = phase * 227;
+        const int cnt = phase == 2 ? 170 : 227;   // 454..623
+        uint32_t v[3];
+        int nk = 0;
+        for (int q = tid; q < cnt; q += blockDim.x) {
+            const int k = base + q;
+            const uint32_t nxt = (k == 623) ? mt[0] : mt[k + 1];
+            const uint32_t y = (mt[k] & UP) | (nxt & LOW);
+            const uint32_t src = (k < 227) ? mt[k + 397] : mt[k - 227];
+            if (nk < 3) v[nk] = src ^ (y >> 1) ^ ((y & 1u) ? MAG : 0u);
+            ++nk;
+        }
+        __syncthreads();
+        nk = 0;
+        for (int q = tid; q < cnt; q += blockDim.x) { mt[base + q] = v[nk < 3 ? nk : 2]; ++nk; }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ double dist2(double ax, double ay, double az, double bx, double by, double bz) {
+    const double dx = ax - bx, dy = ay - by, dz = az - bz;
+    return (dx * dx + dy * dy) + dz * dz;   // cKDTree / np.linalg.norm(axis=1) association
+}
+
+// sqrt(d2) <= r, avoiding the square root outside a narrow band around the threshold
+__device__ __forceinline__ bool within_sqrt(double d2, double r, double r2) {
+    if (d2 < r2 * (1.0 - 1e-12)) return true;
+    if (d2 > r2 * (1.0 + 1e-12)) return false;
+    return sqrt(d2) <= r;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_sample: one CTA per graph
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_sample(GrowDev D, GrowShape S, IterP P) {
+    __shared__ uint32_t mt[624];
+    __shared__ int s_idx, s_p;
+    const int g = blockIdx.x, tid = threadIdx.x;
+    if (D.err[g]) return;
+    MTState* st = D.np_mt + g;
+    for (int i = tid; i < 624; i += blockDim.x) mt[i] = st->mt[i];
+    if (tid == 0) s_idx = st->idx;
+    __syncthreads();
+    const int N = P.N;
+    const uint32_t L = (uint32_t)D.n_valid[g];
+    const uint32_t rng = L - 1;
+    uint32_t mask = rng;
+    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    unsigned int* vi = D.vi + (size_t)g * S.Nmax;
+    unsigned int* ub = D.ubuf + (size_t)g * 6 * S.Nmax;
+    // 1. randint(0, L, N): masked rejection over the 32-bit stream
+    int count = 0;
+    while (count < N) {
+        if (s_idx >= 624) { mt_regen_block(mt); if (tid == 0) s_idx = 0; __syncthreads(); }
+        const int idx = s_idx;
+        const int avail = 624 - idx;
+        uint32_t x = 0;
+        int flag = 0;
+        if (tid < avail) {
+            x = (rng == 0) ? 0u : (mt_temper(mt[idx + tid]) & mask);
+            flag = (rng == 0) ? 1 : (x <= rng);
+        }
+        int total;
+        const int incl = block_scan_incl(flag, &total);
+        const int need = N - count;
+        if (flag && incl <= need) vi[count + incl - 1] = x;
+        if (flag && incl == need) s_p = tid;
+        __syncthreads();
+        int consumed;
+        if (total >= need) { consumed = s_p + 1; count = N; } else { consumed = avail; count += total; }
+        __syncthreads();
+        if (tid == 0) s_idx = idx + ((rng == 0) ? 0 : consumed);   // rng == 0 draws nothing (numpy)
+        __syncthreads();
+    }
+    // 2. uniform(0,1,(N,3)): 6N stream words
+    int written = 0;
+    while (written < 6 * N) {
+        if (s_idx >= 624) { mt_regen_block(mt); if (tid == 0) s_idx = 0; __syncthreads(); }
+        const int idx = s_idx;
+        const int avail = 624 - idx;
+        const int take = avail < 6 * N - written ? avail : 6 * N - written;
+        if (tid < take) ub[written + tid] = mt_temper(mt[idx + tid]);
+        written += take;
+        __syncthreads();
+        if (tid == 0) s_idx = idx + take;
+        __syncthreads();
+    }
+    for (int i = tid; i < 624; i += blockDim.x) st->mt[i] = mt[i];
+    if (tid == 0) st->idx = s_idx;
+    // 3. candidates, filtered by is_valid_position (simulation_space.py:89-98), stable order
+    const unsigned char* vij = D.valid_ij + (size_t)g * MAX_VALID * 2;
+    double* cx = D.cx + (size_t)g * S.Nmax; double* cy = D.cy + (size_t)g * S.Nmax; double* cz = D.cz + (size_t)g * S.Nmax;
+    const double fzc0 = P.faz_cx * GEOMETRY_SIZE, fzc1 = P.faz_cy * GEOMETRY_SIZE;
+    const double fzr = D.faz_radius[g] * GEOMETRY_SIZE * 0.5;
+    int ncand = 0;
+    for (int base = 0; base < N; base += blockDim.x) {
+        const int i = base + tid;
+        int valid = 0;
+        double px = 0, py = 0, pz = 0;
+        if (i < N) {
+            const uint32_t v = vi[i];
+            const double u0 = mt_double(ub[6 * i], ub[6 * i + 1]), u1 = mt_double(ub[6 * i + 2], ub[6 * i + 3]),
+                         u2 = mt_double(ub[6 * i + 4], ub[6 * i + 5]);
+            px = ((double)vij[2 * v] + u0) / (double)GEOMETRY_SIZE;
+            py = ((double)vij[2 * v + 1] + u1) / (double)GEOMETRY_SIZE;
+            pz = (0.0 + u2) / (double)GEOMETRY_SIZE;
+            valid = !(px >= P.shape[0] || py >= P.shape[1] || pz >= P.shape[2] || px < 0 || py < 0 || pz < 0);
+            if (valid) {   // zip-truncated eukledian_dist(pos, FAZ_center[voxel units]) > FAZ_radius[voxel units]
+                const double a = px - fzc0, b = py - fzc1;
+                valid = sqrt(a * a + b * b) > fzr;
+            }
+        }
+        int total;
+        const int incl = block_scan_incl(valid, &total);
+        if (valid) { const int o = ncand + incl - 1; cx[o] = px; cy[o] = py; cz[o] = pz; }
+        ncand += total;
+    }
+    if (tid == 0) {
+        D.n_cand[g] = ncand;
+        D.counters[g * 8 + 2] += D.n_nodes[0][g];   // sum_P
+        D.counters[g * 8 + 3] += D.n_s[0][g];       // sum_S
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_sink_tests: thread per candidate, tiles of nodes / sinks staged through shared memory
+// ------------------------------------------------------------------------------------------
+constexpr int TILE = 128;
+
+__global__ void __launch_bounds__(TILE) k_sink_tests(GrowDev D, GrowShape S, IterP P) {
+    __shared__ double tx[TILE], ty[TILE], tz[TILE], tr[TILE];
+    const int tiles = (S.Nmax + TILE - 1) / TILE;
+    const double epsn2 = P.eps_n_eff * P.eps_n_eff, epss2 = P.eps_s * P.eps_s;
+    for (int w = blockIdx.x; w < S.G * tiles; w += gridDim.x) {
+        const int g = w / tiles, tile = w - g * tiles;
+        if (D.err[g]) continue;
+        const int nc = D.n_cand[g];
+        if (tile * TILE >= nc) continue;
+        const int c = tile * TILE + threadIdx.x;
+        const bool live = c < nc;
+        double px = 0, py = 0, pz = 0;
+        if (live) { px = D.cx[(size_t)g * S.Nmax + c]; py = D.cy[(size_t)g * S.Nmax + c]; pz = D.cz[(size_t)g * S.Nmax + c]; }
+        bool pass = live;
+        // (i) every arterial node within eps must be farther than its oxygen range (greenhouse.py:337)
+        const int Pn = D.n_nodes[0][g];
+        const size_t nb = (size_t)g * S.capN;
+        for (int base = 0; base < Pn; base += TILE) {
+            const int j = base + threadIdx.x;
+            __syncthreads();
+            if (j < Pn) { tx[threadIdx.x] = D.nx[0][nb + j]; ty[threadIdx.x] = D.ny[0][nb + j]; tz[threadIdx.x] = D.nz[0][nb + j]; tr[threadIdx.x] = D.nrad[0][nb + j]; }
+            __syncthreads();
+            if (!__syncthreads_or(pass)) break;
+            if (pass) {
+                const int lim = Pn - base < TILE ? Pn - base : TILE;
+                for (int q = 0; q < lim; ++q) {
+                    const double d2 = dist2(px, py, pz, tx[q], ty[q], tz[q]);
+                    if (d2 <= epsn2) {
+                        if (!(sqrt(d2) > oxygen_distance(tr[q], P.param_scale))) { pass = false; break; }
+                    }
+                }
+            }
+        }
+        // (ii) no existing sink within eps_s (greenhouse.py:338)
+        const int Sn = D.n_s[0][g];
+        const size_t sb = (size_t)g * S.capS;
+        for (int base = 0; base < Sn; base += TILE) {
+            const int j = base + threadIdx.x;
+            __syncthreads();
+            if (j < Sn) { tx[threadIdx.x] = D.sx[0][sb + j]; ty[threadIdx.x] = D.sy[0][sb + j]; tz[threadIdx.x] = D.sz[0][sb + j]; }
+            __syncthreads();
+            if (!__syncthreads_or(pass)) break;
+            if (pass) {
+                const int lim = Sn - base < TILE ? Sn - base : TILE;
+                for (int q = 0; q < lim; ++q) {
+                    const double d2 = dist2(px, py, pz, tx[q], ty[q], tz[q]);
+                    if (within_sqrt(d2, P.eps_s, epss2)) { pass = false; break; }
+                }
+            }
+        }
+        __syncthreads();
+        if (live) D.cpass[(size_t)g * S.Nmax + c] = pass ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_sink_greedy: one CTA per graph; lexicographically-first maximal independent set in rounds
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_sink_greedy(GrowDev D, GrowShape S, IterP P) {
+    const int g = blockIdx.x, tid = threadIdx.x;
+    if (D.err[g]) return;
+    const int nc = D.n_cand[g];
+    const double* cx = D.cx + (size_t)g * S.Nmax; const double* cy = D.cy + (size_t)g * S.Nmax; const double* cz = D.cz + (size_t)g * S.Nmax;
+    const unsigned char* cp = D.cpass + (size_t)g * S.Nmax;
+    int* pl = D.plist + (size_t)g * S.Nmax;
+    volatile unsigned char* state = D.cstate + (size_t)g * S.Nmax;
+    int np_ = 0;
+    for (int base = 0; base < nc; base += blockDim.x) {
+        const int i = base + tid;
+        const int f = (i < nc) ? cp[i] : 0;
+        int total;
+        const int incl = block_scan_incl(f, &total);
+        if (f) { pl[np_ + incl - 1] = i; state[np_ + incl - 1] = 0; }
+        np_ += total;
+    }
+    __syncthreads();
+    const double eps2 = P.eps_s * P.eps_s;
+    // state: 0 undecided, 1 accepted, 2 rejected.  Candidate k is rejected as soon as an earlier ACCEPTED
+    // candidate lies within eps_s, accepted once every earlier candidate within eps_s is rejected.
+    for (int round = 0; round < nc + 2; ++round) {
+        int undecided = 0;
+        for (int k = tid; k < np_; k += blockDim.x) {
+            if (state[k] != 0) continue;
+            const int ik = pl[k];
+            const double px = cx[ik], py = cy[ik], pz = cz[ik];
+            bool acc = false, und = false;
+            for (int j = 0; j < k; ++j) {
+                const unsigned char sj = state[j];
+                if (sj == 2) continue;
+                const int ij = pl[j];
+                const double d2 = dist2(px, py, pz, cx[ij], cy[ij], cz[ij]);
+                if (within_sqrt(d2, P.eps_s, eps2)) {   // not (norm > eps_s)
+                    if (sj == 1) { acc = true; break; }
+                    und = true;
+                }
+            }
+            if (acc) state[k] = 2;
+            else if (!und) state[k] = 1;
+            else undecided = 1;
+        }
+        __threadfence_block();
+        if (!__syncthreads_or(undecided)) break;
+    }
+    __syncthreads();
+    // append the accepted candidates, in candidate order, to the oxygen sink list
+    int n0 = D.n_s[0][g];
+    const size_t sb = (size_t)g * S.capS;
+    for (int base = 0; base < np_; base += blockDim.x) {
+        const int k = base + tid;
+        const int f = (k < np_) ? (state[k] == 1) : 0;
+        int total;
+        const int incl = block_scan_incl(f, &total);
+        if (f) {
+            const int o = n0 + incl - 1;
+            if (o < S.capS) { const int ik = pl[k]; D.sx[0][sb + o] = cx[ik]; D.sy[0][sb + o] = cy[ik]; D.sz[0][sb + o] = cz[ik]; }
+        }
+        n0 += total;
+    }
+    if (tid == 0) {
+        if (n0 > S.capS) { D.err[g] = 2; n0 = S.capS; }
+        D.n_s[0][g] = n0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_assign: thread per attractor, active-node positions staged through shared memory
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TILE) k_assign(GrowDev D, GrowShape S, IterP P, int f) {
+    __shared__ double tx[TILE], ty[TILE], tz[TILE];
+    const int tiles = (S.capS + TILE - 1) / TILE;
+    const double delta = P.delta[f];
+    for (int w = blockIdx.x; w < S.G * tiles; w += gridDim.x) {
+        const int g = w / tiles, tile = w - g * tiles;
+        if (D.err[g]) continue;
+        const int A = D.n_s[f][g];
+        if (tile * TILE >= A) continue;
+        const int a = tile * TILE + threadIdx.x;
+        const bool live = a < A;
+        const size_t sb = (size_t)g * S.capS, nb = (size_t)g * S.capN;
+        double px = 0, py = 0, pz = 0;
+        if (live) { px = D.sx[f][sb + a]; py = D.sy[f][sb + a]; pz = D.sz[f][sb + a]; }
+        const int M = D.n_act[f][g];
+        double best = INFINITY;
+        int bi = -1;
+        for (int base = 0; base < M; base += TILE) {
+            const int j = base + threadIdx.x;
+            __syncthreads();
+            if (j < M) { tx[threadIdx.x] = D.ax[f][nb + j]; ty[threadIdx.x] = D.ay[f][nb + j]; tz[threadIdx.x] = D.az[f][nb + j]; }
+            __syncthreads();
+            const int lim = M - base < TILE ? M - base : TILE;
+            for (int q = 0; q < lim; ++q) {
+                const double d2 = dist2(tx[q], ty[q], tz[q], px, py, pz);
+                if (d2 < best) { best = d2; bi = base + q; }
+            }
+        }
+        __syncthreads();
+        if (live) D.assign[sb + a] = (bi >= 0 && sqrt(best) <= delta) ? D.act[f][nb + bi] : -1;
+        if (tile == 0 && threadIdx.x == 0) { D.counters[g * 8 + 0] += A; D.counters[g * 8 + 1] += M; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_group: one CTA per graph
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_group(GrowDev D, GrowShape S, IterP P, int f) {
+    __shared__ uint32_t mt[624];
+    __shared__ int s_idx;
+    const int g = blockIdx.x, tid = threadIdx.x;
+    if (D.err[g]) return;
+    const int call_id = 2 * P.iter + f + 1;
+    const int A = D.n_s[f][g];
+    const size_t sb = (size_t)g * S.capS, nb = (size_t)g * S.capN;
+    const int* asg = D.assign + sb;
+    int* first = D.first + nb; int* cnt = D.cnt + nb; int* slot = D.slot + nb; int* slot_call = D.slot_call + nb; int* cur = D.cur + nb;
+    int* dict = D.dict_node + nb; int* loff = D.list_off + (size_t)g * (S.capN + 1); int* lst = D.list + sb;
+    for (int a = tid; a < A; a += blockDim.x) {
+        const int nd = asg[a];
+        if (nd >= 0) { atomicMin(&first[nd], a); atomicAdd(&cnt[nd], 1); }
+    }
+    __syncthreads();
+    int nd_ = 0;
+    for (int base = 0; base < A; base += blockDim.x) {
+        const int a = base + tid;
+        int isf = 0, nd = -1;
+        if (a < A) { nd = asg[a]; isf = (nd >= 0 && first[nd] == a); }
+        int total;
+        const int incl = block_scan_incl(isf, &total);
+        if (isf) { const int rk = nd_ + incl - 1; dict[rk] = nd; slot[nd] = rk; slot_call[nd] = call_id; }
+        nd_ += total;
+    }
+    __syncthreads();
+    int off = 0;
+    for (int base = 0; base < nd_; base += blockDim.x) {
+        const int e = base + tid;
+        const int c = (e < nd_) ? cnt[dict[e]] : 0;
+        int total;
+        const int incl = block_scan_incl(c, &total);
+        if (e < nd_) { loff[e] = off + incl - c; cur[e] = 0; }
+        off += total;
+    }
+    if (tid == 0) { loff[nd_] = off; D.n_dict[g] = nd_; }
+    __syncthreads();
+    for (int a = tid; a < A; a += blockDim.x) {
+        const int nd = asg[a];
+        if (nd >= 0) { const int e = slot[nd]; const int pos = atomicAdd(&cur[e], 1); lst[loff[e] + pos] = a; }
+    }
+    __syncthreads();
+    for (int e = tid; e < nd_; e += blockDim.x) {
+        int* l = lst + loff[e];
+        const int n = loff[e + 1] - loff[e];
+        for (int i = 1; i < n; ++i) {       // lists are short (mean 2, max ~150): insertion sort
+            const int v = l[i];
+            int j = i - 1;
+            while (j >= 0 && l[j] > v) { l[j + 1] = l[j]; --j; }
+            l[j + 1] = v;
+        }
+        const int nd = dict[e];
+        first[nd] = 0x7fffffff;
+        cnt[nd] = 0;
+    }
+    // top up the Python-`random` word buffer: k_commit may consume one double per dict entry
+    unsigned int* pb = D.py_buf + (size_t)g * S.pycap;
+    int pos = D.py_pos[g], n = D.py_n[g];
+    const int need = 2 * nd_ + 2;
+    __syncthreads();
+    if (n - pos < need) {
+        const int rem = n - pos;
+        for (int base = 0; base < rem; base += blockDim.x) {   // move the unread tail to the front
+            const int i = base + tid;
+            unsigned int v = 0;
+            if (i < rem) v = pb[pos + i];
+            __syncthreads();
+            if (i < rem) pb[i] = v;
+            __syncthreads();
+        }
+        MTState* st = D.py_mt + g;
+        for (int i = tid; i < 624; i += blockDim.x) mt[i] = st->mt[i];
+        if (tid == 0) s_idx = st->idx;
+        __syncthreads();
+        int have = rem;
+        while (have < need && have + 624 <= S.pycap) {
+            if (s_idx >= 624) { mt_regen_block(mt); if (tid == 0) s_idx = 0; __syncthreads(); }
+            const int idx = s_idx, avail = 624 - idx;
+            if (tid < avail) pb[have + tid] = mt_temper(mt[idx + tid]);
+            have += avail;
+            __syncthreads();
+            if (tid == 0) s_idx = 624;
+            __syncthreads();
+        }
+        for (int i = tid; i < 624; i += blockDim.x) st->mt[i] = mt[i];
+        if (tid == 0) { st->idx = s_idx; D.py_pos[g] = 0; D.py_n[g] = have; if (have < need) D.err[g] = 3; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// per-node growth proposals
+// ------------------------------------------------------------------------------------------
+struct NodeCtx {
+    double pos[3], par[3], ch[3];
+    double vtc[2], dist_to_center;
+    int nch, parent;
+};
+
+// utilities.py:42-45: angle (degrees) between u and every (att - pos); n = list length (selects the BLAS path)
+__device__ __forceinline__ double angle_to(const double* u, double nu, const double* v, int n) {
+    const double dt = (n == 1) ? ddot3(u, v) : gemv3(u, v);
+    const double C = dt / nu / norm3_axis(v);
+    return RAD2DEG * acos(clamp11(C));
+}
+
+// leaf branch, greenhouse.py:177-258
+__device__ void eval_leaf(const GrowDev& D, const GrowShape& S, const IterP& P, int g, int f, int e, const NodeCtx& nc,
+                          const int* lst, int n, Proposal* pr) {
+    const size_t sb = (size_t)g * S.capS;
+    const double* sx = D.sx[f] + sb; const double* sy = D.sy[f] + sb; const double* sz = D.sz[f] + sb;
+    double* sang = D.sc_ang + sb + (lst - (D.list + sb));
+    int* sidx = D.sc_idx + sb + (lst - (D.list + sb));
+    const double v[3] = {nc.pos[0] - nc.par[0], nc.pos[1] - nc.par[1], nc.pos[2] - nc.par[2]};
+    const double nv = norm3(v);
+    const double lim = P.gamma[f] / 2 > 0 ? P.gamma[f] / 2 : 0;
+    int m = 0;
+    double avg[3] = {0, 0, 0};
+    for (int i = 0; i < n; ++i) {
+        const int a = lst[i];
+        const double w[3] = {sx[a] - nc.pos[0], sy[a] - nc.pos[1], sz[a] - nc.pos[2]};
+        const double ang = angle_to(v, nv, w, n);
+        if (ang <= lim) {
+            const double nw = norm3(w);
+            if (m == 0) { avg[0] = w[0] / nw; avg[1] = w[1] / nw; avg[2] = w[2] / nw; }
+            else { avg[0] += w[0] / nw; avg[1] += w[1] / nw; avg[2] += w[2] / nw; }
+            sang[m] = ang;
+            sidx[m] = a;
+            ++m;
+        }
+    }
+    pr->type = P_NONE;
+    if (m == 0) return;
+    // np.std(angles): population std via numpy's pairwise sums
+    const double mean = pairwise_sum([&](long i) { return sang[i]; }, 0, m) / (double)m;
+    const double var = pairwise_sum([&](long i) { const double x = sang[i] - mean; return x * x; }, 0, m) / (double)m;
+    const double sd = sqrt(var);
+    const double faz = D.faz_radius[g];
+    // elongation, greenhouse.py:242-258 (always prepared: it is the fall-back of a failed bifurcation test)
+    {
+        const double na = norm3(avg);
+        double gv[3];
+        for (int k = 0; k < 3; ++k) gv[k] = P.omega * (v[k] / nv) + (1 - P.omega) * (avg[k] / na);
+        if (P.rotation_radius > 0 && P.t > 15) {
+            const double ng = norm3(gv);
+            for (int k = 0; k < 3; ++k) gv[k] /= ng;
+            double cv[2] = {P.faz_cx - nc.pos[0], P.faz_cy - nc.pos[1]};
+            const double ncv = norm2(cv);
+            cv[0] /= ncv; cv[1] /= ncv;
+            const double np2[2] = {P.faz_cx - (nc.pos[0] + P.d * gv[0]), P.faz_cy - (nc.pos[1] + P.d * gv[1])};
+            const double dist_new = norm2(np2);
+            const double floorw = P.first_mode ? 0.0 : 0.01;
+            const double cand = P.rotation_radius - dist_new;
+            double weight = cand > floorw ? cand : floorw;
+            weight = sqrt(weight);
+            double ort[3] = {-cv[1], cv[0], 0};
+            if (angle_between_two(gv, ort) > 90) { ort[0] = -1 * ort[0]; ort[1] = -1 * ort[1]; ort[2] = -1 * ort[2]; }
+            const double outv[3] = {-cv[0], -cv[1], 0};
+            for (int k = 0; k < 3; ++k) gv[k] = ((1 - weight) * gv[k] + 0.7 * weight * ort[k]) + 0.3 * weight * outv[k];
+        }
+        const double ng = norm3(gv);
+        for (int k = 0; k < 3; ++k) pr->p[k] = nc.pos[k] + P.d * (gv[k] / ng);
+    }
+    pr->type = P_LEAF_ELONG;
+    if (!(sd > P.phi)) return;
+    // bifurcation candidate, greenhouse.py:191-239
+    pr->type = (faz == 0) ? P_LEAF_BIF : P_LEAF_DRAW;
+    if (faz != 0) {
+        pr->ratio5 = pow(nc.dist_to_center / (2 * faz), 5.0);
+        pr->cond = angle_between_two(nc.vtc, avg) > 90;
+    }
+    double phi1, phi2;
+    murray_angles(P.r, P.r, P.kappa, &phi1, &phi2);
+    double c[3] = {0, 0, 0};
+    for (int q = 0; q < m; ++q) {
+        const int a = sidx[q];
+        if (q == 0) { c[0] = sx[a]; c[1] = sy[a]; c[2] = sz[a]; }
+        else { c[0] += sx[a]; c[1] += sy[a]; c[2] += sz[a]; }
+    }
+    for (int k = 0; k < 3; ++k) c[k] /= (double)m;
+    double dpc[3] = {c[0] - nc.pos[0], c[1] - nc.pos[1], c[2] - nc.pos[2]};
+    if (norm3(dpc) != 0.0) { const double n2 = norm3(dpc); for (int k = 0; k < 3; ++k) dpc[k] /= n2; }
+    // np.cov((atts - c).T): row means (sequential), centred rows, syrk-style running-fma products, * 1/(m-1)
+    double av[3] = {0, 0, 0};
+    for (int q = 0; q < m; ++q) {
+        const int a = sidx[q];
+        const double x[3] = {sx[a] - c[0], sy[a] - c[1], sz[a] - c[2]};
+        if (q == 0) { av[0] = x[0]; av[1] = x[1]; av[2] = x[2]; } else { av[0] += x[0]; av[1] += x[1]; av[2] += x[2]; }
+    }
+    for (int k = 0; k < 3; ++k) av[k] /= (double)m;
+    double cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int q = 0; q < m; ++q) {
+        const int a = sidx[q];
+        const double x[3] = {(sx[a] - c[0]) - av[0], (sy[a] - c[1]) - av[1], (sz[a] - c[2]) - av[2]};
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) cov[3 * i + j] = fma(x[i], x[j], cov[3 * i + j]);
+    }
+    const double fact = 1.0 / (double)(m - 1);
+    for (int i = 0; i < 9; ++i) cov[i] *= fact;
+    double dl[3];
+    const int est = eig3::principal_axis(cov, dl);
+    if (est != 0) D.err[g] = 10 + est;
+    const double c1 = cos(DEG2RAD * phi1), s1 = sin(DEG2RAD * phi1), c2 = cos(DEG2RAD * phi2), s2 = sin(DEG2RAD * phi2);
+    double g1[3], g2[3];
+    for (int k = 0; k < 3; ++k) { g1[k] = c1 * dpc[k] + s1 * dl[k]; g2[k] = c2 * dpc[k] - s2 * dl[k]; }
+    const double n1 = norm3(g1), n2 = norm3(g2);
+    for (int k = 0; k < 3; ++k) { pr->b1[k] = nc.pos[k] + g1[k] / n1 * P.d; pr->b2[k] = nc.pos[k] + g2[k] / n2 * P.d; }
+}
+
+// inter-node branch, greenhouse.py:259-306, for a given distal radius r1
+__device__ void eval_inter(const GrowDev& D, const GrowShape& S, const IterP& P, int g, int f, const NodeCtx& nc,
+                           const int* lst, int n, double r1, Proposal* pr) {
+    const size_t sb = (size_t)g * S.capS;
+    const double* sx = D.sx[f] + sb; const double* sy = D.sy[f] + sb; const double* sz = D.sz[f] + sb;
+    pr->type = P_INTER_EMPTY;
+    pr->r1_used = r1;
+    double phi1, phi2;
+    murray_angles(r1, P.r, P.kappa, &phi1, &phi2);
+    const double dseg[3] = {nc.ch[0] - nc.pos[0], nc.ch[1] - nc.pos[1], nc.ch[2] - nc.pos[2]};
+    const double pseg[3] = {nc.pos[0] - nc.par[0], nc.pos[1] - nc.par[1], nc.pos[2] - nc.par[2]};
+    const double nd_ = norm3(dseg), np_ = norm3(pseg);
+    const double g2 = P.gamma[f] / 2;
+    int m = 0;
+    double avg[3] = {0, 0, 0};
+    for (int i = 0; i < n; ++i) {
+        const int a = lst[i];
+        const double w[3] = {sx[a] - nc.pos[0], sy[a] - nc.pos[1], sz[a] - nc.pos[2]};
+        const double ad = angle_to(dseg, nd_, w, n);
+        const double ap = angle_to(pseg, np_, w, n);
+        if ((phi1 + phi2 - g2 <= ad) && (ad <= (phi1 + phi2 + g2)) && (ap <= phi2 + g2)) {
+            const double nw = norm3(w);
+            if (m == 0) { avg[0] = w[0] / nw; avg[1] = w[1] / nw; avg[2] = w[2] / nw; }
+            else { avg[0] += w[0] / nw; avg[1] += w[1] / nw; avg[2] += w[2] / nw; }
+            ++m;
+        }
+    }
+    if (m == 0) return;
+    const double dv[3] = {dseg[0] / nd_, dseg[1] / nd_, dseg[2] / nd_};
+    const double cr[3] = {dv[1] * avg[2] - dv[2] * avg[1], dv[2] * avg[0] - dv[0] * avg[2], dv[0] * avg[1] - dv[1] * avg[0]};
+    if (cr[0] == 0 && cr[1] == 0 && cr[2] == 0) return;
+    pr->type = P_INTER_DRAW;
+    pr->ratio5 = pow(nc.dist_to_center / (2 * D.faz_radius[g]), 5.0);
+    pr->cond = angle_between_two(nc.vtc, avg) <= 90;
+    const double ncr = norm3(cr);
+    const double ax[3] = {cr[0] / ncr, cr[1] / ncr, cr[2] / ncr};
+    const double ct = cos(DEG2RAD * phi2), sth = sin(DEG2RAD * phi2);
+    const double kxv[3] = {ax[1] * dv[2] - ax[2] * dv[1], ax[2] * dv[0] - ax[0] * dv[2], ax[0] * dv[1] - ax[1] * dv[0]};
+    const double kdv = ddot3(ax, dv);
+    double vv[3];
+    for (int k = 0; k < 3; ++k) vv[k] = (dv[k] * ct + kxv[k] * sth) + ax[k] * kdv * (1 - ct);
+    const double nvv = norm3(vv), na = norm3(avg);
+    double gv[3];
+    for (int k = 0; k < 3; ++k) gv[k] = P.omega * (vv[k] / nvv) + (1 - P.omega) * (avg[k] / na);
+    const double ng = norm3(gv);
+    for (int k = 0; k < 3; ++k) pr->p[k] = nc.pos[k] + P.d * (gv[k] / ng);
+}
+
+__device__ __forceinline__ void load_ctx(const GrowDev& D, const GrowShape& S, const IterP& P, int g, int f, int nd, NodeCtx* nc) {
+    const size_t nb = (size_t)g * S.capN;
+    nc->pos[0] = D.nx[f][nb + nd]; nc->pos[1] = D.ny[f][nb + nd]; nc->pos[2] = D.nz[f][nb + nd];
+    nc->parent = D.npar[f][nb + nd];
+    nc->nch = D.nnch[f][nb + nd];
+    if (nc->parent >= 0) { const int p = nc->parent; nc->par[0] = D.nx[f][nb + p]; nc->par[1] = D.ny[f][nb + p]; nc->par[2] = D.nz[f][nb + p]; }
+    if (nc->nch >= 1) { const int c = D.nch0[f][nb + nd]; nc->ch[0] = D.nx[f][nb + c]; nc->ch[1] = D.ny[f][nb + c]; nc->ch[2] = D.nz[f][nb + c]; }
+    nc->vtc[0] = P.faz_cx - nc->pos[0]; nc->vtc[1] = P.faz_cy - nc->pos[1];
+    nc->dist_to_center = norm2(nc->vtc);
+}
+
+__global__ void __launch_bounds__(128) k_eval(GrowDev D, GrowShape S, IterP P, int f) {
+    const int g = blockIdx.y;
+    if (D.err[g]) return;
+    const int nd_ = D.n_dict[g];
+    const size_t sb = (size_t)g * S.capS, nb = (size_t)g * S.capN;
+    const int* loff = D.list_off + (size_t)g * (S.capN + 1);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nd_; e += gridDim.x * blockDim.x) {
+        const int nd = D.dict_node[nb + e];
+        Proposal pr;
+        pr.type = P_NONE; pr.cond = 0; pr.ratio5 = 0; pr.r1_used = 0;
+        NodeCtx nc;
+        load_ctx(D, S, P, g, f, nd, &nc);
+        const int* lst = D.list + sb + loff[e];
+        const int n = loff[e + 1] - loff[e];
+        if (nc.nch == 0) eval_leaf(D, S, P, g, f, e, nc, lst, n, &pr);
+        else if (nc.parent >= 0 && nc.nch == 1) eval_inter(D, S, P, g, f, nc, lst, n, D.nrad[f][nb + D.nch0[f][nb + nd]], &pr);
+        D.prop[nb + e] = pr;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_commit: one CTA per graph; thread 0 replays the dict order sequentially
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P, int f) {
+    __shared__ int s_pend[PEND_MAX];
+    __shared__ int s_npend, s_overflow;
+    const int g = blockIdx.x, tid = threadIdx.x;
+    if (D.err[g]) return;
+    const int call_id = 2 * P.iter + f + 1;
+    const size_t sb = (size_t)g * S.capS, nb = (size_t)g * S.capN;
+    const int nd_ = D.n_dict[g];
+    Proposal* prop = D.prop + nb;
+    int* alist = D.alist + nb;
+    // compact the entries that act without any recheck: leaves that grow, inter-nodes that draw
+    int na = 0;
+    for (int base = 0; base < nd_; base += blockDim.x) {
+        const int e = base + tid;
+        int fl = 0;
+        if (e < nd_) { const int t = prop[e].type; fl = (t == P_LEAF_ELONG || t == P_LEAF_DRAW || t == P_LEAF_BIF || t == P_INTER_DRAW); }
+        int total;
+        const int incl = block_scan_incl(fl, &total);
+        if (fl) alist[na + incl - 1] = e;
+        na += total;
+    }
+    __syncthreads();
+    const int n_before = D.n_nodes[f][g];
+    if (tid == 0) {
+        s_npend = 0; s_overflow = 0;
+        double* X = D.nx[f] + nb; double* Y = D.ny[f] + nb; double* Z = D.nz[f] + nb;
+        double* R = D.nrad[f] + nb; double* K = D.nkap[f] + nb;
+        int* PAR = D.npar[f] + nb; int* C0 = D.nch0[f] + nb; int* C1 = D.nch1[f] + nb;
+        unsigned char* NCH = D.nnch[f] + nb; unsigned char* META = D.nmeta[f] + nb; unsigned char* DEACT = D.deact[f] + nb;
+        const int* slot = D.slot + nb; const int* slot_call = D.slot_call + nb;
+        const int* dict = D.dict_node + nb;
+        const int* loff = D.list_off + (size_t)g * (S.capN + 1);
+        unsigned int* pb = D.py_buf + (size_t)g * S.pycap;
+        int ppos = D.py_pos[g];
+        int n_nodes = n_before;
+        long long draws = 0;
+        int cur_rank = -1;
+        auto next_uniform = [&]() { const double u = mt_double(pb[ppos], pb[ppos + 1]); ppos += 2; ++draws; return u; };
+        auto add_node = [&](const double* p, int parent, int walk_after) -> int {
+            if (n_nodes >= S.capN) { D.err[g] = 1; return -1; }
+            const int id = n_nodes++;
+            X[id] = p[0]; Y[id] = p[1]; Z[id] = p[2]; R[id] = P.r; K[id] = P.kappa;
+            PAR[id] = parent; C0[id] = -1; C1[id] = -1; NCH[id] = 0; DEACT[id] = 0;
+            META[id] = (unsigned char)((P.mode_idx << 1) | (walk_after ? 1 : 0));
+            if (NCH[parent] == 0) C0[parent] = id; else C1[parent] = id;
+            NCH[parent] = NCH[parent] + 1;
+            return id;
+        };
+        // arterial_tree.py:174-184 with the device's pow (exact radii are recomputed on the host with libm,
+        // see octa_grow_host.cu); marks later inter-node dict entries whose distal radius just changed
+        auto walk = [&](int n) {
+            while (true) {
+                const int par = PAR[n];
+                const int nch = NCH[n];
+                if (par < 0 || nch == 0) return;
+                const double kap = K[n];
+                double s = 0 + pow(R[C0[n]], kap);
+                if (nch > 1) s = s + pow(R[C1[n]], kap);
+                const double rp = pow(s, 1 / kap);
+                if (R[n] == rp) return;
+                R[n] = rp;
+                if (slot_call[par] == call_id && NCH[par] == 1 && PAR[par] >= 0) {
+                    const int rk = slot[par];
+                    if (rk > cur_rank) {
+                        bool dup = false;
+                        for (int q = 0; q < s_npend; ++q) if (s_pend[q] == rk) { dup = true; break; }
+                        if (!dup) { if (s_npend < PEND_MAX) s_pend[s_npend++] = rk; else s_overflow = 1; }
+                    }
+                }
+                n = par;
+            }
+        };
+        int ai = 0;
+        while (true) {
+            // next entry in dict order: the smaller of the next action entry and the pending rechecks
+            const int ea = (ai < na) ? alist[ai] : 0x7fffffff;
+            int pq = -1, ep = 0x7fffffff;
+            for (int q = 0; q < s_npend; ++q) if (s_pend[q] < ep) { ep = s_pend[q]; pq = q; }
+            if (ea == 0x7fffffff && pq < 0) break;
+            int e;
+            bool from_pending;
+            if (ep <= ea) {
+                e = ep; from_pending = true;
+                s_pend[pq] = s_pend[--s_npend];
+                if (ep == ea) ++ai;             // also an action entry: handle once
+            } else {
+                e = ea; from_pending = false; ++ai;
+            }
+            if (D.err[g]) break;
+            cur_rank = e;
+            Proposal pr = prop[e];
+            const int nd = dict[e];
+            if (pr.type == P_INTER_DRAW || pr.type == P_INTER_EMPTY) {
+                const double r1 = R[C0[nd]];
+                if (from_pending || r1 != pr.r1_used) {
+                    // distal radius changed since k_eval (an earlier entry of this call branched below it)
+                    NodeCtx nc;
+                    load_ctx(D, S, P, g, f, nd, &nc);
+                    eval_inter(D, S, P, g, f, nc, D.list + sb + loff[e], loff[e + 1] - loff[e], r1, &pr);
+                }
+                if (pr.type != P_INTER_DRAW) continue;
+                const double u = next_uniform();
+                if (pr.ratio5 <= u && pr.cond) continue;
+                if (add_node(pr.p, nd, 1) < 0) break;
+                walk(nd);
+                DEACT[nd] = 1;
+            } else if (pr.type == P_LEAF_ELONG) {
+                if (add_node(pr.p, nd, 0) < 0) break;
+            } else if (pr.type == P_LEAF_DRAW || pr.type == P_LEAF_BIF) {
+                bool bif = true;
+                if (pr.type == P_LEAF_DRAW) { const double u = next_uniform(); bif = (pr.ratio5 > u) && pr.cond; }
+                if (bif) {
+                    if (add_node(pr.b1, nd, 0) < 0) break;
+                    if (add_node(pr.b2, nd, 1) < 0) break;
+                    walk(nd);
+                    DEACT[nd] = 1;
+                } else {
+                    if (add_node(pr.p, nd, 0) < 0) break;
+                }
+            }
+        }
+        if (s_overflow) D.err[g] = 4;
+        D.py_pos[g] = ppos;
+        D.py_draws[g] += draws;
+        D.n_prev[f][g] = n_before;
+        D.n_nodes[f][g] = n_nodes;
+    }
+    __syncthreads();
+    if (D.err[g]) return;
+    // active list: drop the nodes that branched (stable), append the new nodes (element_mesh.py:103-111,180-193)
+    const int n_after = D.n_nodes[f][g];
+    int* act = D.act[f] + nb;
+    double* ax = D.ax[f] + nb; double* ay = D.ay[f] + nb; double* az = D.az[f] + nb;
+    unsigned char* deact = D.deact[f] + nb;
+    const int M = D.n_act[f][g];
+    int w = 0;
+    for (int base = 0; base < M; base += blockDim.x) {
+        const int i = base + tid;
+        int keep = 0, id = -1;
+        double px = 0, py = 0, pz = 0;
+        if (i < M) { id = act[i]; keep = !deact[id]; px = ax[i]; py = ay[i]; pz = az[i]; }
+        int total;
+        const int incl = block_scan_incl(keep, &total);   // (contains the barriers that order reads before writes)
+        if (keep) { const int o = w + incl - 1; act[o] = id; ax[o] = px; ay[o] = py; az[o] = pz; }
+        w += total;
+        __syncthreads();
+    }
+    for (int i = n_before + tid; i < n_after; i += blockDim.x) {
+        const int o = w + (i - n_before);
+        act[o] = i; ax[o] = D.nx[f][nb + i]; ay[o] = D.ny[f][nb + i]; az[o] = D.nz[f][nb + i];
+    }
+    if (tid == 0) D.n_act[f][g] = w + (n_after - n_before);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_kill: one CTA per graph.  f = 0: satisfied O2 sinks -> CO2 sources (set order); f = 1: CO2 removal
+// ------------------------------------------------------------------------------------------
+__device__ void pyset_insert_clean(long long* th, int* tk, size_t mask, int key, long long hash) {
+    size_t perturb = (size_t)hash, i = (size_t)hash & mask;
+    while (true) {
+        size_t e = i;
+        if (tk[e] < 0) { tk[e] = key; th[e] = hash; return; }
+        if (i + 9 <= mask) {
+            for (int j = 0; j < 9; ++j) { ++e; if (tk[e] < 0) { tk[e] = key; th[e] = hash; return; } }
+        }
+        perturb >>= 5;
+        i = (i * 5 + 1 + perturb) & mask;
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_kill(GrowDev D, GrowShape S, IterP P, int f) {
+    __shared__ double nxs[512], nys[512], nzs[512];
+    const int g = blockIdx.x, tid = threadIdx.x;
+    if (D.err[g]) return;
+    const size_t sb = (size_t)g * S.capS, nb = (size_t)g * S.capN;
+    const int n0 = D.n_prev[f][g], n1 = D.n_nodes[f][g];
+    const int nn = n1 - n0;
+    const int Sn = D.n_s[f][g];
+    double* sx = D.sx[f] + sb; double* sy = D.sy[f] + sb; double* sz = D.sz[f] + sb;
+    int* hitj = D.hitj + sb;
+    const double epsk2 = P.eps_k * P.eps_k;
+    if (nn > 0) {
+        for (int i = tid; i < Sn; i += blockDim.x) hitj[i] = -1;
+        for (int base = 0; base < nn; base += 512) {
+            const int cntn = nn - base < 512 ? nn - base : 512;
+            __syncthreads();
+            for (int j = tid; j < cntn; j += blockDim.x) { nxs[j] = D.nx[f][nb + n0 + base + j]; nys[j] = D.ny[f][nb + n0 + base + j]; nzs[j] = D.nz[f][nb + n0 + base + j]; }
+            __syncthreads();
+            for (int i = tid; i < Sn; i += blockDim.x) {
+                if (hitj[i] >= 0) continue;
+                const double px = sx[i], py = sy[i], pz = sz[i];
+                for (int j = 0; j < cntn; ++j)
+                    if (dist2(px, py, pz, nxs[j], nys[j], nzs[j]) <= epsk2) { hitj[i] = base + j; break; }   // cKDTree ball: d^2 <= r^2
+            }
+        }
+        __syncthreads();
+        if (f == 0) {
+            // hits in list order
+            int* hl = D.hl + sb;
+            int H = 0;
+            for (int base = 0; base < Sn; base += blockDim.x) {
+                const int i = base + tid;
+                const int fl = (i < Sn) ? (hitj[i] >= 0) : 0;
+                int total;
+                const int incl = block_scan_incl(fl, &total);
+                if (fl) hl[H + incl - 1] = i;
+                H += total;
+            }
+            __syncthreads();
+            // veto: a venous node within eps_k (greenhouse.py:106-109), warp per hit
+            unsigned char* veto = D.veto + sb;
+            const int Vn = D.n_nodes[1][g];
+            const int lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+            for (int h = warp; h < H; h += nw) {
+                const int i = hl[h];
+                const double px = sx[i], py = sy[i], pz = sz[i];
+                bool any = false;
+                for (int j = lane; j < Vn && !any; j += 32) {
+                    const double d2 = dist2(D.nx[1][nb + j], D.ny[1][nb + j], D.nz[1][nb + j], px, py, pz);
+                    if (within_sqrt(d2, P.eps_k, epsk2)) any = true;
+                }
+                any = __any_sync(0xffffffffu, any);
+                if (lane == 0) veto[h] = any ? 1 : 0;
+            }
+            __syncthreads();
+            // insertion sequence: by (first new node that hits it, list index) -- the order of
+            // `for node in new_nodes: for oxy in ball(node)` with index-ordered ball results
+            int* seq = D.seq + sb;
+            int T = 0;
+            for (int base = 0; base < H; base += blockDim.x) {
+                const int h = base + tid;
+                const int fl = (h < H) ? !veto[h] : 0;
+                int total;
+                const int incl = block_scan_incl(fl, &total);
+                if (fl) D.ta[sb + T + incl - 1] = hl[h];
+                T += total;
+            }
+            __syncthreads();
+            const int* ta = D.ta + sb;
+            for (int q = tid; q < T; q += blockDim.x) {
+                const int i = ta[q];
+                const int ji = hitj[i];
+                int rank = 0;
+                for (int q2 = 0; q2 < T; ++q2) {
+                    const int i2 = ta[q2];
+                    const int j2 = hitj[i2];
+                    rank += (j2 < ji) || (j2 == ji && i2 < i);
+                }
+                seq[rank] = i;
+            }
+            __syncthreads();
+            // CPython set emulation (Objects/setobject.c, 3.12) -> iteration order = slot order
+            long long* th = D.set_hash + (size_t)g * 2 * SET_TBL;
+            int* tk = D.set_key + (size_t)g * 2 * SET_TBL;
+            for (int i = tid; i < 8; i += blockDim.x) { tk[i] = -1; th[i] = 0; }
+            __syncthreads();
+            if (tid == 0 && T > 0) {
+                size_t mask = 7, fill = 0, used = 0;
+                long long* curh = th; int* curk = tk;
+                long long* alth = th + SET_TBL; int* altk = tk + SET_TBL;
+                for (int q = 0; q < T; ++q) {
+                    const int key = seq[q];
+                    const long long hash = py_hash_tuple3(sx[key], sy[key], sz[key]);
+                    size_t perturb = (size_t)hash, i = (size_t)hash & mask;
+                    bool done = false;
+                    while (!done) {
+                        size_t e = i;
+                        int probes = (i + 9 <= mask) ? 9 : 0;
+                        do {
+                            if (curk[e] < 0) {
+                                curk[e] = key; curh[e] = hash;
+                                ++fill; ++used;
+                                if (fill * 5 >= mask * 3) {
+                                    const size_t minused = used > 50000 ? used * 2 : used * 4;
+                                    size_t newsize = 8;
+                                    while (newsize <= minused) newsize <<= 1;
+                                    if (newsize > (size_t)SET_TBL) { D.err[g] = 5; done = true; break; }
+                                    for (size_t z = 0; z < newsize; ++z) { altk[z] = -1; alth[z] = 0; }
+                                    for (size_t z = 0; z <= mask; ++z)
+                                        if (curk[z] >= 0) pyset_insert_clean(alth, altk, newsize - 1, curk[z], curh[z]);
+                                    long long* t1 = curh; curh = alth; alth = t1;
+                                    int* t2 = curk; curk = altk; altk = t2;
+                                    mask = newsize - 1;
+                                    fill = used;
+                                }
+                                done = true;
+                                break;
+                            }
+                            if (curh[e] == hash && curk[e] == key) { done = true; break; }
+                            ++e;
+                        } while (probes--);
+                        if (done) break;
+                        perturb >>= 5;
+                        i = (i * 5 + 1 + perturb) & mask;
+                    }
+                    if (D.err[g]) break;
+                }
+                // append to the CO2 list in slot order
+                int nco2 = D.n_s[1][g];
+                const size_t cb = (size_t)g * S.capS;
+                for (size_t z = 0; z <= mask; ++z)
+                    if (curk[z] >= 0) {
+                        if (nco2 >= S.capS) { D.err[g] = 2; break; }
+                        const int key = curk[z];
+                        D.sx[1][cb + nco2] = sx[key]; D.sy[1][cb + nco2] = sy[key]; D.sz[1][cb + nco2] = sz[key];
+                        ++nco2;
+                    }
+                D.n_s[1][g] = nco2;
+            }
+            __syncthreads();
+        }
+        // stable removal of every hit from this sink list (element_mesh.py:195-211)
+        int w = 0;
+        for (int base = 0; base < Sn; base += blockDim.x) {
+            const int i = base + tid;
+            int keep = 0;
+            double px = 0, py = 0, pz = 0;
+            if (i < Sn) { keep = hitj[i] < 0; px = sx[i]; py = sy[i]; pz = sz[i]; }
+            int total;
+            const int incl = block_scan_incl(keep, &total);
+            if (keep) { const int o = w + incl - 1; sx[o] = px; sy[o] = py; sz[o] = pz; }
+            w += total;
+            __syncthreads();
+        }
+        if (tid == 0) D.n_s[f][g] = w;
+    }
+    __syncthreads();
+    if (f == 1 && tid == 0 && D.trace) {
+        int* tr = D.trace + ((size_t)g * 4096 + P.iter) * 4;
+        if (P.iter < 4096) { tr[0] = D.n_nodes[0][g]; tr[1] = D.n_s[0][g]; tr[2] = D.n_nodes[1][g]; tr[3] = D.n_s[1][g]; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// launch wrappers (called from octa_grow_host.cu)
+// ------------------------------------------------------------------------------------------
+void launch_iteration(const GrowDev& D, const GrowShape& S, const IterP& P, int n_sm, cudaStream_t st) {
+    k_sample<<<S.G, 1024, 0, st>>>(D, S, P);
+    k_sink_tests<<<n_sm * 8, TILE, 0, st>>>(D, S, P);
+    k_sink_greedy<<<S.G, 1024, 0, st>>>(D, S, P);
+    count_launch(3);
+    for (int f = 0; f < 2; ++f) {
+        k_assign<<<n_sm * 8, TILE, 0, st>>>(D, S, P, f);
+        k_group<<<S.G, 1024, 0, st>>>(D, S, P, f);
+        k_eval<<<dim3(16, S.G), 128, 0, st>>>(D, S, P, f);
+        k_commit<<<S.G, 256, 0, st>>>(D, S, P, f);
+        k_kill<<<S.G, 1024, 0, st>>>(D, S, P, f);
+        count_launch(5);
+    }
+}
+
+}  // namespace octa

@@ -1,0 +1,58 @@
+"""Graph CSV surface (byte-compatible with the reference's files), over the C ABI.
+
+write: generate_vessel_graph.py:59-66;  read: the `[x y z]` string cells every consumer parses
+(tree2img.py:73-76, visualize_vessel_graphs.py:72-75, data_transforms.py:377-381)."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+
+def _bind():
+    L = _lib.lib()
+    L.octa_format_csv.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_size_t,
+                                  ctypes.POINTER(ctypes.c_size_t)]
+    L.octa_parse_csv.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int64]
+    L.octa_parse_csv.restype = ctypes.c_int64
+    return L
+
+
+def csv_bytes(edges7: np.ndarray) -> bytes:
+    """Header + one row per edge, exactly as the reference writes them."""
+    L = _bind()
+    e = np.ascontiguousarray(edges7, dtype=np.float64).reshape(-1, 7)
+    cap = 64 + 110 * len(e)
+    buf = ctypes.create_string_buffer(cap)
+    n = ctypes.c_size_t(0)
+    rc = L.octa_format_csv(e.ctypes.data, len(e), buf, cap, ctypes.byref(n))
+    if rc == _lib.OCTA_E_NOMEM:
+        cap = n.value
+        buf = ctypes.create_string_buffer(cap)
+        rc = L.octa_format_csv(e.ctypes.data, len(e), buf, cap, ctypes.byref(n))
+    _lib.check(rc)
+    return buf.raw[:n.value]
+
+
+def write_csv(path: str, edges7: np.ndarray) -> None:
+    with open(path, "wb") as f:
+        f.write(csv_bytes(edges7))
+
+
+def parse_csv_bytes(data: bytes) -> np.ndarray:
+    L = _bind()
+    n = L.octa_parse_csv(data, len(data), None, 0)
+    if n < 0:
+        _lib.check(int(n))
+    out = np.empty((n, 7), dtype=np.float64)
+    n2 = L.octa_parse_csv(data, len(data), out.ctypes.data, n)
+    if n2 < 0:
+        _lib.check(int(n2))
+    return out
+
+
+def read_csv(path: str) -> np.ndarray:
+    with open(path, "rb") as f:
+        return parse_csv_bytes(f.read())

@@ -1,0 +1,114 @@
+"""Host-side mirror of the reference's growth entry (generate_vessel_graph.py:24-56) over the C ABI:
+YAML-style config dict + per-sample seeds in, arterial / venous edge tables out.
+
+Seeding contract: sample i behaves exactly like the unmodified reference run with
+`random.seed(seeds[i]); np.random.seed(seeds[i])` issued right before `Greenhouse(...)`."""
+from __future__ import annotations
+
+import ctypes
+from typing import Sequence
+
+import numpy as np
+
+from . import _lib
+
+WALLS = {"x0": 0, "x1": 1, "y0": 2, "y1": 3, "z0": 4, "z1": 5}
+
+
+class OctaGrowMode(ctypes.Structure):
+    _fields_ = [("I", ctypes.c_int32), ("N", ctypes.c_int32)] + \
+        [(k, ctypes.c_double) for k in ("eps_n", "eps_s", "eps_k", "delta_art", "delta_ven", "gamma_art", "gamma_ven",
+                                        "phi", "omega", "kappa", "delta_sigma")] + \
+        [("reinit", ctypes.c_int32), ("first_mode", ctypes.c_int32)]
+
+
+class OctaGrowConfig(ctypes.Structure):
+    _fields_ = [("d", ctypes.c_double), ("r", ctypes.c_double), ("faz_radius_bound", ctypes.c_double * 2),
+                ("rotation_radius", ctypes.c_double), ("faz_center", ctypes.c_double * 2),
+                ("nerve_center", ctypes.c_double * 2), ("nerve_radius", ctypes.c_double),
+                ("param_scale", ctypes.c_double), ("size", ctypes.c_double * 3), ("n_modes", ctypes.c_int32),
+                ("modes", OctaGrowMode * 8), ("forest_type", ctypes.c_int32), ("n_trees", ctypes.c_int32),
+                ("n_walls", ctypes.c_int32), ("walls", ctypes.c_int32 * 6), ("cap_nodes", ctypes.c_int32),
+                ("cap_sinks", ctypes.c_int32)]
+
+
+class OctaGrowStats(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_int64) for k in ("n_art_nodes", "n_ven_nodes", "n_oxy_left", "n_co2_left", "py_draws",
+                                              "sum_A", "sum_M", "sum_P", "sum_S")] + \
+        [("err", ctypes.c_int32), ("n_iters", ctypes.c_int32)]
+
+
+def make_config(config: dict, cap_nodes: int = 0, cap_sinks: int = 0) -> OctaGrowConfig:
+    g, f = config["Greenhouse"], config["Forest"]
+    ss = g["SimulationSpace"]
+    if ss.get("oxygen_sample_geometry_path") is not None:
+        raise NotImplementedError("SimulationSpace.oxygen_sample_geometry_path (fixed .npy geometry) is not supported yet")
+    modes = g["modes"]
+    if not 1 <= len(modes) <= 8:
+        raise ValueError("between 1 and 8 growth modes are supported")
+    c = OctaGrowConfig()
+    c.d, c.r = float(g["d"]), float(g["r"])
+    c.faz_radius_bound[0], c.faz_radius_bound[1] = [float(x) for x in g["FAZ_radius_bound"]]
+    c.rotation_radius = float(g["rotation_radius"])
+    c.faz_center[0], c.faz_center[1] = [float(x) for x in g["FAZ_center"]]
+    c.nerve_center[0], c.nerve_center[1] = [float(x) for x in g["nerve_center"]]
+    c.nerve_radius = float(g["nerve_radius"])
+    c.param_scale = float(g["param_scale"])
+    c.size[0], c.size[1], c.size[2] = float(ss["no_voxel_x"]), float(ss["no_voxel_y"]), float(ss["no_voxel_z"])
+    c.n_modes = len(modes)
+    for i, m in enumerate(modes):
+        om = c.modes[i]
+        om.I, om.N = int(m["I"]), int(m["N"])
+        for k in ("eps_n", "eps_s", "eps_k", "delta_art", "delta_ven", "gamma_art", "gamma_ven", "phi", "omega",
+                  "kappa", "delta_sigma"):
+            setattr(om, k, float(m[k]))
+        om.reinit = int(m["name"] != modes[0]["name"])
+        om.first_mode = int(m == modes[0])
+    if f["type"] not in ("stumps", "nerve"):
+        # forest.py:36
+        raise NotImplementedError("The Forest initialization type '%s' is not implemented. Try 'stump' or 'nerve' instead." % f["type"])
+    c.forest_type = 0 if f["type"] == "stumps" else 1
+    c.n_trees = int(f["N_trees"])
+    walls = [WALLS[k] for k, v in f.get("source_walls", {}).items() if v]
+    c.n_walls = len(walls)
+    for i, w in enumerate(walls):
+        c.walls[i] = w
+    c.cap_nodes, c.cap_sinks = int(cap_nodes), int(cap_sinks)
+    return c
+
+
+def _bind():
+    L = _lib.lib()
+    L.octa_grow_batch_host.argtypes = [ctypes.POINTER(OctaGrowConfig), ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                       ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
+    return L
+
+
+def grow_batch(config: dict, seeds: Sequence[int], cap_edges: int = 40000, trace: bool = False, cap_nodes: int = 0,
+               cap_sinks: int = 0):
+    """Grow len(seeds) independent samples on the GPU.
+
+    Returns (graphs, stats, extra): graphs[i] = (art_edges7, ven_edges7) float64 arrays in the reference's row order;
+    stats[i] = dict of per-sample counters; extra = {"device_ms": ..., "trace": int32 [n, iters, 4] or None}."""
+    L = _bind()
+    c = make_config(config, cap_nodes, cap_sinks)
+    n = len(seeds)
+    sd = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint64))
+    out = np.empty((n, cap_edges, 7), dtype=np.float64)
+    na = np.zeros(n, dtype=np.int64)
+    nv = np.zeros(n, dtype=np.int64)
+    st = (OctaGrowStats * n)()
+    tr = np.zeros((n, 4096, 4), dtype=np.int32) if trace else None
+    ms = ctypes.c_double(0)
+    rc = L.octa_grow_batch_host(ctypes.byref(c), sd.ctypes.data, n, out.ctypes.data, cap_edges, na.ctypes.data,
+                                nv.ctypes.data, ctypes.cast(st, ctypes.c_void_p), tr.ctypes.data if trace else None,
+                                ctypes.byref(ms))
+    stats = [{k: getattr(st[i], k) for k, _ in OctaGrowStats._fields_} for i in range(n)]
+    if rc != 0:
+        err = _lib.OctaError(rc, L.octa_last_error().decode(errors="replace"))
+        err.stats = stats
+        raise err
+    graphs = [(out[i, :na[i]].copy(), out[i, na[i]:na[i] + nv[i]].copy()) for i in range(n)]
+    n_it = stats[0]["n_iters"] if n else 0
+    return graphs, stats, {"device_ms": ms.value, "trace": tr[:, :n_it] if trace else None}
