@@ -1,17 +1,21 @@
 #!/usr/bin/env python
 """Benchmark of the vessel-graph hot path (BASELINE.json metric: synthetic graphs/sec incl. the
-1216^2 x 16 raster; achieved HBM GB/s).
+1216^2 raster; achieved HBM GB/s).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
 
-One "step" = one pass of the hot path over one batch of B graphs per GPU (config #2: B = 64,
-raster request [1216,1216,16] -> volume 1216x1216x53 uint16).  N > 1 is launched by torchrun, one
-rank per GPU; graphs are independent, so ranks shard the batch with no data-path collective
-(weak scaling: per-GPU work fixed).  Prints ONE JSON line on rank 0.
+One "step" = one pass of the hot path over one batch of B fresh samples per GPU (BASELINE config #2:
+B = 64, docker / default 3x3 mm^2 config): seeded growth (250 iterations) -> exact radii + edge rows
+-> voxel volume for the request [1216,1216,16] (1216x1216x53 uint16) -> 1216^2 label raster and
+304^2 gray image.  Every step uses NEW seeds (nothing can be cached).  N > 1 is launched by torchrun,
+one rank per GPU; samples are independent, so ranks own disjoint seeds and there is no data-path
+collective (weak scaling: per-GPU batch fixed).  Rank 0 prints ONE JSON line.
 
-STATUS (round 1, interim): the growth kernels are not wired into the step yet -- the step
-rasterizes B pre-grown graphs (the seed-0 docker-config golden graph, jittered per graph so the
-volumes differ).  `config.workload` says so; see DESIGN.md.
+  value : whole-job graphs/s with results left in HBM (CUDA events around the timed steps; the step
+          contains host work -- D2H of the tree topology, libm radius replay, H2D of edge rows --
+          which the events bracket too).
+  e2e   : the same through host buffers: + byte-exact CSV text of every graph, + D2H of the 1216^2 label
+          and the 304^2 image into pinned memory (the 157 MB volumes stay in HBM unless --d2h-volume).
 """
 from __future__ import annotations
 
@@ -27,25 +31,24 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 DIMS = [1216, 1216, 16]
+WORKLOAD = ("BASELINE config #2: batch of %d seeded samples per GPU, default 3x3 mm^2 macular config "
+            "(= docker/vessel_graph_gen_docker_config.yml), growth -> edge rows -> voxelize [1216,1216,16] "
+            "(1216x1216x53 u16) -> 1216^2 label + 304^2 image")
 
 
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle sampler running during the timed region."""
-
     def __init__(self, index=0):
-        self.samples, self.reasons, self.proc = [], set(), None
-        self.index = index
+        self.samples, self.reasons, self.proc, self.index = [], set(), None, index
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -57,8 +60,7 @@ class ClockSampler:
         except OSError:
             self.proc = None
             return
-        self.thread = threading.Thread(target=self._read, daemon=True)
-        self.thread.start()
+        threading.Thread(target=self._read, daemon=True).start()
 
     def _read(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -81,67 +83,61 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm = sorted(s[0] for s in self.samples)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
-                "sm_max_mhz": self.samples[0][1] if self.samples else None,
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.samples[0][1] if self.samples else None,
                 "samples": len(sm), "reasons": sorted(self.reasons)}
 
 
-def golden_edges():
-    from conftest import load_graph_rows, rows_to_edges7
-    return rows_to_edges7(load_graph_rows("graph_docker_s0.csv.gz"))
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the reference's own algorithm on the host cores.  The reference is pure Python and cannot
+# travel to the GPU box (no /root/reference there), so this is the oracle PORT (oracle/growth_oracle.cpp +
+# oracle/voxelize_oracle.c, byte-identical to the reference on the committed goldens), one process per
+# core like generate_vessel_graph.py:112-126.
+# ----------------------------------------------------------------------------------------------
+def _cpu_one(seed):
+    from oracle import growth_oracle as go, vox_oracle
+    from octa_autosegmentation_b200.config import default_config
+    t0 = time.perf_counter()
+    art, ven, _ = go.run(default_config(), seed)
+    t1 = time.perf_counter()
+    vox_oracle.voxelize_edges(np.concatenate([art, ven]), DIMS)
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1
 
 
-def make_batch(e7: np.ndarray, batch: int, rank: int):
-    """B graphs: the golden graph with a per-graph sub-voxel jitter (synthetic, deterministic)."""
-    graphs = []
-    for i in range(batch):
-        rng = np.random.RandomState(1000 * rank + i)
-        g = e7.copy()
-        shift = rng.uniform(-2e-3, 2e-3, 3) * np.array([1, 1, 0.0])
-        g[:, 0:3] += shift
-        g[:, 3:6] += shift
-        graphs.append(g)
-    offs = np.cumsum([0] + [len(g) for g in graphs]).astype(np.int64)
-    return np.concatenate(graphs), offs
+def cpu_arm(n_graphs, workers, base_seed):
+    import concurrent.futures as cf
+    from oracle import growth_oracle as go, vox_oracle
+    go.build()
+    vox_oracle.build()
+    t0 = time.perf_counter()
+    with cf.ProcessPoolExecutor(max_workers=workers) as ex:
+        parts = list(ex.map(_cpu_one, [base_seed + i for i in range(n_graphs)]))
+    dt = time.perf_counter() - t0
+    return n_graphs / dt, dt, float(np.mean([p[0] for p in parts])), float(np.mean([p[1] for p in parts]))
 
 
 def run_reference(args):
-    """Reference arm: the reference's own CPU algorithm for the path on the host cores.  The
-    reference is pure Python and cannot travel to the GPU box, so this is the C oracle port
-    (oracle/voxelize_oracle.c, bit-exact to tree2img.voxelize_forest), one process per core."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    import concurrent.futures as cf
-    from oracle import vox_oracle
-    vox_oracle.build()
-    e7 = golden_edges()
-    cores = max(1, (os.cpu_count() or 2) - 1)
-    sample = min(cores, 8)   # graphs per step (bounded sample of the 64-graph workload)
-
-    def one(i):
-        vox_oracle.voxelize_edges(e7, DIMS)   # ctypes call releases the GIL
-        return i
-
-    def step():
-        with cf.ThreadPoolExecutor(max_workers=cores) as ex:
-            list(ex.map(one, range(sample)))
-
-    for _ in range(args.warmup):
-        step()
+    cores = os.cpu_count() or 2
+    workers = max(1, cores - 1)
+    sample = workers * 2
+    for w in range(args.warmup):
+        cpu_arm(workers, workers, 10_000 + w * 100)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
+    for s in range(args.steps):
+        val, dt, tg, tv = cpu_arm(sample, workers, 20_000 + s * 1000)
     dt = (time.perf_counter() - t0) / args.steps
     val = sample / dt
     print(json.dumps({
         "impl": "reference", "metric": "graphs_per_sec", "value": val, "unit": "graphs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "voxelize-only [1216,1216,16] of pre-grown docker-config graphs (interim, see DESIGN.md)",
-                   "batch_per_gpu": sample},
-        "cpu_baseline": {"value": val, "unit": "graphs/s", "cores": cores, "kind": "port",
-                         "sample": "%d graphs/step (of the 64-graph batch), C port of tree2img.voxelize_forest" % sample},
+        "config": {"workload": WORKLOAD % 64 + " [CPU arm: growth + CSV rows + voxelize; the matplotlib 2-D stage is "
+                   "excluded: matplotlib is not installed]", "sample_graphs_per_step": sample},
+        "cpu_baseline": {"value": val, "unit": "graphs/s", "cores": workers, "kind": "port",
+                         "sample": "%d graphs/step of the 64-graph batch; C++/C port of the reference "
+                                   "(growth %.2f s + voxelize %.2f s per graph per core)" % (sample, tg, tv)},
         "e2e": {"value": val, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -149,11 +145,12 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--d2h-volume", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -161,6 +158,8 @@ def main():
     import torch
     import torch.distributed as dist
     from octa_autosegmentation_b200 import _lib, tree2img
+    from octa_autosegmentation_b200.config import default_config
+    from octa_autosegmentation_b200.pipeline import Pipeline
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -172,27 +171,34 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     B = args.batch
+    W = max(args.warmup, 3)
+    pipe = Pipeline(default_config(), device=dev, volume_dims=DIMS, host_threads=max(1, (os.cpu_count() or 2) // max(world, 1)))
+    counter = [0]
 
-    e7 = golden_edges()
-    batch_np, offs = make_batch(e7, B, rank)
-    edges_dev = torch.from_numpy(batch_np).to(dev)
-    shape = tree2img.voxel_volume_shape(DIMS)
-    out = torch.empty((B, *shape), dtype=torch.uint16, device=dev)
-    ws = torch.empty(int(_lib.lib().octa_voxelize_workspace_bytes(B, int(offs[-1]), _lib.int3(DIMS))),
-                     dtype=torch.uint8, device=dev)
-    host_edges = torch.from_numpy(batch_np).pin_memory()
-    host_label = torch.empty((B, shape[0], shape[1]), dtype=torch.uint8).pin_memory()
+    def seeds():
+        # fresh seeds every step, disjoint across ranks
+        s0 = 1_000_000 + counter[0] * B * world + rank * B
+        counter[0] += 1
+        return [s0 + i for i in range(B)]
 
-    def step_device():
-        tree2img.voxelize_batch_device(edges_dev, offs, DIMS, out=out, workspace=ws)
+    phase = {"grow_ms": 0.0, "vox_ms": 0.0, "n": 0, "sumA": 0, "sumM": 0, "sumP": 0, "sumS": 0, "V": 0, "E": 0}
+    vol_host = None
+    if args.d2h_volume:
+        shape = tree2img.voxel_volume_shape(DIMS)
+        vol_host = torch.empty((B, *shape), dtype=torch.uint16).pin_memory()
 
-    def step_e2e():
-        edges_dev.copy_(host_edges, non_blocking=True)
-        tree2img.voxelize_batch_device(edges_dev, offs, DIMS, out=out, workspace=ws)
-        # result read-back: the en-face maximum-intensity projection of every volume (1216^2 u8 / graph)
-        mip = out.view(torch.int16).amax(dim=3).to(torch.uint8)
-        host_label.copy_(mip, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    def step(d2h):
+        out = pipe.run(seeds(), d2h=d2h, csv=d2h)
+        if d2h and vol_host is not None:
+            vol_host.copy_(out["volume"], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        phase["grow_ms"] += out["grow_device_ms"]
+        phase["n"] += 1
+        for st in out["stats"]:
+            phase["sumA"] += st["sum_A"]; phase["sumM"] += st["sum_M"]; phase["sumP"] += st["sum_P"]; phase["sumS"] += st["sum_S"]
+            phase["V"] += st["n_art_nodes"] + st["n_ven_nodes"]
+        phase["E"] += int(out["offsets"][-1])
+        return out
 
     def barrier():
         if world > 1:
@@ -200,69 +206,92 @@ def main():
         torch.cuda.synchronize()
 
     def timed(fn, steps):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
-        ev[0].record()
+        e0.record()
+        last = None
         for _ in range(steps):
-            fn()
-        ev[1].record()
+            last = fn()
+        e1.record()
         barrier()
-        ms = ev[0].elapsed_time(ev[1])
+        ms = e0.elapsed_time(e1)
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms / steps
+        return ms / steps, last
 
-    for _ in range(max(args.warmup, 3)):
-        step_device()
+    for _ in range(W):
+        step(False)
+    for k in phase:
+        phase[k] = 0
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     n0 = _lib.launch_count()
-    ms = timed(step_device, args.steps)
+    ms, _ = timed(lambda: step(False), args.steps)
     launches = _lib.launch_count() - n0
-    for _ in range(2):
-        step_e2e()
-    ms_e2e = timed(step_e2e, max(2, args.steps // 2))
+    ph = dict(phase)
+    # voxelizer alone, on its stream, over the last batch's edges (the HBM-bound kernel of the path)
+    out = step(False)
+    offs = out["offsets"]
+    edges_dev = pipe._buf["edges_dev"]
+    vol = out["volume"]
+    torch.cuda.synchronize()
+    ve = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    nrep = 5
+    ve[0].record()
+    for _ in range(nrep):
+        tree2img.voxelize_batch_device(edges_dev, offs, DIMS, out=vol, workspace=pipe._buf.get("vox_ws"))
+    ve[1].record()
+    torch.cuda.synchronize()
+    vox_ms = ve[0].elapsed_time(ve[1]) / nrep
+    step(True)
+    ms_e2e, last = timed(lambda: step(True), max(2, args.steps // 2))
     clocks = sampler.stop() if rank == 0 else None
 
-    # roofline of the dominant kernel (vox_tile_kernel): time it alone with events on its stream
-    E_total = int(offs[-1])
-    vol_bytes = int(np.prod(shape)) * 2
-    alg_bytes = 56 * E_total + vol_bytes * B            # B_vox = 56 E + 2 X Y Z' per graph
-    peak, peak_src = load_peaks()
-    achieved = alg_bytes / (ms * 1e-3) / 1e9            # whole step ~ dominant kernel + 3 binning kernels
-
     if rank == 0:
+        peak, peak_src = load_peaks()
+        shape = tree2img.voxel_volume_shape(DIMS)
+        vol_bytes = int(np.prod(shape)) * 2
+        E_last = int(offs[-1])
+        vox_alg = 56 * E_last + vol_bytes * B                         # B_vox = 56 E + 2 X Y Z' per graph
+        n = max(ph["n"], 1)
+        b_grow = (28 * ph["sumA"] + 24 * ph["sumM"] + 24 * 2000 * 250 * B * n + 32 * ph["sumP"] + 24 * ph["sumS"] + 40 * ph["V"]) / n
+        grow_ms = ph["grow_ms"] / n
+        vox_ach = vox_alg / (vox_ms * 1e-3) / 1e9
+        grow_ach = b_grow / (grow_ms * 1e-3) / 1e9
         line = {
             "metric": "graphs_per_sec", "value": B * world / (ms * 1e-3), "unit": "graphs/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "voxelize-only [1216,1216,16]->1216x1216x53 u16 of %d pre-grown docker-config graphs per GPU "
-                                   "(interim: growth kernels not yet in the step)" % B,
-                       "batch_per_gpu": B, "edges_per_graph": int(len(e7)),
-                       "l2": "outputs %.1f GB per step >> 126 MB L2 (no flush needed)" % (vol_bytes * B / 1e9)},
+            "steps": args.steps, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD % B, "batch_per_gpu": B, "edges_per_graph_mean": ph["E"] / n / B,
+                       "seeds": "fresh every step (1000000 + step*B*world + rank*B + i)",
+                       "l2": "per step %.1f GB of volumes + ~1.6 GB of growth state >> 126 MB L2 (no flush needed)" % (vol_bytes * B / 1e9),
+                       "phase_ms": {"growth_loop_device": grow_ms, "voxelize_4_kernels": vox_ms, "step": ms}},
             "gpu_launches": int(launches),
-            "e2e": {"value": B * world / (ms_e2e * 1e-3), "unit": "graphs/s",
-                    "h2d_bytes_per_step": int(host_edges.numel() * 8), "d2h_bytes_per_step": int(host_label.numel()),
-                    "note": "H2D edges + D2H en-face MIP label per graph; the 157 MB volumes stay in HBM"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
-                         "kernel": "vox_tile_kernel (+3 binning kernels, whole step)"},
+            "e2e": {"value": B * world / (ms_e2e * 1e-3), "unit": "graphs/s", "h2d_bytes_per_step": int(last["h2d_bytes"]),
+                    "d2h_bytes_per_step": int(last["d2h_bytes"] + (vol_host.numel() * 2 if vol_host is not None else 0)),
+                    "note": "host API: + CSV text of every graph (byte-exact), + D2H of label (1216^2 u8) and image (304^2 u8) "
+                            "into pinned memory; growth topology D2H and edge-row H2D are inside both numbers"},
+            "roofline": {"bound": "hbm", "achieved": vox_ach, "peak": peak, "unit": "GB/s", "frac": vox_ach / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "vox_tile_kernel (+prep/scan/fill, <1 %)",
+                         "algorithmic_bytes_per_launch": vox_alg, "ms_per_launch": vox_ms,
+                         "note": "the HBM-bound kernel of the path; see roofline_growth for the phase that dominates step time"},
+            "roofline_growth": {"bound": "hbm", "achieved": grow_ach, "peak": peak, "unit": "GB/s", "frac": grow_ach / peak,
+                                "traffic": None, "kernel": "growth loop, 13 kernels x 250 iterations (latency / pair-scan bound; "
+                                                           "state is L2-resident)", "algorithmic_bytes_per_step": b_grow,
+                                "ms_per_step": grow_ms},
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:
-            from oracle import vox_oracle
-            vox_oracle.build()
-            t0 = time.perf_counter()
-            nrep = 0
-            while time.perf_counter() - t0 < 10.0:
-                vox_oracle.voxelize_edges(e7, DIMS)
-                nrep += 1
-            dt = (time.perf_counter() - t0) / nrep
-            line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "graphs/s", "cores": 1, "kind": "port",
-                                    "sample": "%d x one graph, C port of tree2img.voxelize_forest, 1 thread" % nrep}
+            cores = os.cpu_count() or 2
+            workers = max(1, cores - 1)
+            val, dt, tg, tv = cpu_arm(workers, workers, 30_000)
+            line["cpu_baseline"] = {"value": val, "unit": "graphs/s", "cores": workers, "kind": "port",
+                                    "sample": "%d graphs (one per worker) of the 64-graph batch; C++/C port of the reference, "
+                                              "growth %.2f s + voxelize %.2f s per graph per core; 2-D matplotlib stage "
+                                              "excluded (not installed)" % (workers, tg, tv)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

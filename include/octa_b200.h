@@ -77,6 +77,21 @@ int octa_voxelize_host(const double* edges7, int64_t n_edges, const int dims[3],
                        uint16_t* out);
 
 /* ------------------------------------------------------------------------------------------------
+ * 2-D label rasterizer -- replaces vessel_graph_generation/tree2img.py:12-114 `rasterize_forest` (matplotlib Agg
+ * LineCollection, round caps, anti-aliased), called from generate_vessel_graph.py:79-86,
+ * visualize_vessel_graphs.py:95 and data/data_transforms.py:384.  Output: uint8 gray [H][W] per graph
+ * (H = image_resolution[1], W = image_resolution[0]); pixel row = pos[ax0]*H, col = pos[ax1]*W with
+ * ax = {0,1,2} minus mip_axis.  Uses OctaVoxOpts.min_radius / max_radius (tree2img.py:66-68); `ignore_z` is unused.
+ * Parity with Agg is statistical (no matplotlib in this image).
+ * ---------------------------------------------------------------------------------------------- */
+size_t octa_raster2d_workspace_bytes(int n_graphs, int64_t n_edges, int H, int W);
+int octa_raster2d_batch_dev(const double* edges7_dev, const int64_t* edge_offsets_host, int n_graphs, int H, int W,
+                            int mip_axis, const OctaVoxOpts* opts, uint8_t* out_dev, void* workspace_dev,
+                            size_t workspace_bytes, void* stream);
+int octa_raster2d_host(const double* edges7, int64_t n_edges, int H, int W, int mip_axis, const OctaVoxOpts* opts,
+                       uint8_t* out);
+
+/* ------------------------------------------------------------------------------------------------
  * Growth -- replaces generate_vessel_graph.py:24-56 (`main` up to the edge lists):
  *   Greenhouse(config['Greenhouse'])                      greenhouse.py:17-51
  *   Forest(config['Forest'], ...) x2 (arterial, venous)   forest.py:15-181

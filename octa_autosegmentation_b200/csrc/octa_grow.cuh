@@ -11,7 +11,6 @@ namespace octa {
 constexpr int GEOMETRY_SIZE = 76;                 // simulation_space.py:8
 constexpr int MAX_VALID = GEOMETRY_SIZE * GEOMETRY_SIZE;
 constexpr int SET_TBL = 16384;                    // slots per CPython-set emulation table (x2: resize target)
-constexpr int PEND_MAX = 128;
 
 // per-iteration parameters (identical for every graph of the batch; computed on the host exactly
 // like greenhouse.py:34-51 / :139-147 evolve them)
@@ -40,7 +39,7 @@ struct GrowDev {
     // vessel nodes, [f][g*capN + i]
     double *nx[2], *ny[2], *nz[2], *nrad[2], *nkap[2];
     int *npar[2], *nch0[2], *nch1[2];
-    unsigned char *nnch[2], *nmeta[2], *deact[2];
+    unsigned char *nnch[2], *nmeta[2], *deact[2], *dirty[2];
     int *n_nodes[2], *n_prev[2];
     // active node lists (list order = element_mesh.py list order), with compacted positions
     int *act[2], *n_act[2];
@@ -63,7 +62,7 @@ struct GrowDev {
     int* n_cand;
     unsigned char *cpass, *cstate;
     int* plist;
-    int *assign, *first, *cnt, *slot, *slot_call, *cur;
+    int *assign, *first, *cnt, *slot, *slot_call, *cur, *rtag;
     int *dict_node, *n_dict, *list_off, *list, *sc_idx;
     double *sc_ang;
     Proposal* prop;

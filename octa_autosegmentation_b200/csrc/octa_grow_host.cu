@@ -192,7 +192,7 @@ void carve(Carver& c, const GrowShape& S, GrowDev* D) {
         D->nx[f] = c.take<double>(GN); D->ny[f] = c.take<double>(GN); D->nz[f] = c.take<double>(GN);
         D->nrad[f] = c.take<double>(GN); D->nkap[f] = c.take<double>(GN);
         D->npar[f] = c.take<int>(GN); D->nch0[f] = c.take<int>(GN); D->nch1[f] = c.take<int>(GN);
-        D->nnch[f] = c.take<unsigned char>(GN); D->nmeta[f] = c.take<unsigned char>(GN); D->deact[f] = c.take<unsigned char>(GN);
+        D->nnch[f] = c.take<unsigned char>(GN); D->nmeta[f] = c.take<unsigned char>(GN); D->deact[f] = c.take<unsigned char>(GN); D->dirty[f] = c.take<unsigned char>(GN);
         D->n_nodes[f] = c.take<int>(G); D->n_prev[f] = c.take<int>(G);
         D->act[f] = c.take<int>(GN); D->n_act[f] = c.take<int>(G);
         D->ax[f] = c.take<double>(GN); D->ay[f] = c.take<double>(GN); D->az[f] = c.take<double>(GN);
@@ -208,7 +208,7 @@ void carve(Carver& c, const GrowShape& S, GrowDev* D) {
     D->n_cand = c.take<int>(G); D->cpass = c.take<unsigned char>(GC); D->cstate = c.take<unsigned char>(GC);
     D->plist = c.take<int>(GC);
     D->assign = c.take<int>(GS);
-    D->first = c.take<int>(GN); D->cnt = c.take<int>(GN); D->slot = c.take<int>(GN); D->slot_call = c.take<int>(GN); D->cur = c.take<int>(GN);
+    D->first = c.take<int>(GN); D->cnt = c.take<int>(GN); D->slot = c.take<int>(GN); D->slot_call = c.take<int>(GN); D->cur = c.take<int>(GN); D->rtag = c.take<int>(GN);
     D->dict_node = c.take<int>(GN); D->n_dict = c.take<int>(G); D->list_off = c.take<int>(G * (S.capN + 1));
     D->list = c.take<int>(GS); D->sc_idx = c.take<int>(GS); D->sc_ang = c.take<double>(GS);
     D->prop = c.take<Proposal>(GN); D->alist = c.take<int>(GN); D->n_alist = c.take<int>(G);

@@ -78,6 +78,9 @@ __device__ __forceinline__ double dist2(double ax, double ay, double az, double 
     return (dx * dx + dy * dy) + dz * dz;   // cKDTree / np.linalg.norm(axis=1) association
 }
 
+// x**y for x > 0 through exp/log: ~1e-15*|y ln x| relative error, used only for the in-loop (steering) radii
+__device__ __forceinline__ double fast_pow(double x, double y) { return exp(y * log(x)); }
+
 // sqrt(d2) <= r, avoiding the square root outside a narrow band around the threshold
 __device__ __forceinline__ bool within_sqrt(double d2, double r, double r2) {
     if (d2 < r2 * (1.0 - 1e-12)) return true;
@@ -639,8 +642,6 @@ __global__ void __launch_bounds__(128) k_eval(GrowDev D, GrowShape S, IterP P, i
 // k_commit: one CTA per graph; thread 0 replays the dict order sequentially
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P, int f) {
-    __shared__ int s_pend[PEND_MAX];
-    __shared__ int s_npend, s_overflow;
     const int g = blockIdx.x, tid = threadIdx.x;
     if (D.err[g]) return;
     const int call_id = 2 * P.iter + f + 1;
@@ -662,7 +663,6 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
     __syncthreads();
     const int n_before = D.n_nodes[f][g];
     if (tid == 0) {
-        s_npend = 0; s_overflow = 0;
         double* X = D.nx[f] + nb; double* Y = D.ny[f] + nb; double* Z = D.nz[f] + nb;
         double* R = D.nrad[f] + nb; double* K = D.nkap[f] + nb;
         int* PAR = D.npar[f] + nb; int* C0 = D.nch0[f] + nb; int* C1 = D.nch1[f] + nb;
@@ -674,7 +674,8 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
         int ppos = D.py_pos[g];
         int n_nodes = n_before;
         long long draws = 0;
-        int cur_rank = -1;
+        int cur_rank = -1, outstanding = 0;
+        int* rtag = D.rtag + nb;
         auto next_uniform = [&]() { const double u = mt_double(pb[ppos], pb[ppos + 1]); ppos += 2; ++draws; return u; };
         auto add_node = [&](const double* p, int parent, int walk_after) -> int {
             if (n_nodes >= S.capN) { D.err[g] = 1; return -1; }
@@ -686,53 +687,74 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
             NCH[parent] = NCH[parent] + 1;
             return id;
         };
-        // arterial_tree.py:174-184 with the device's pow (exact radii are recomputed on the host with libm,
-        // see octa_grow_host.cu); marks later inter-node dict entries whose distal radius just changed
-        auto walk = [&](int n) {
+        // Murray radii (arterial_tree.py:174-184) are kept LAZILY inside a call: a branch event only marks its
+        // ancestor chain dirty (one dependent load per step, stopping at the first already-dirty node) and flags later
+        // inter-node dict entries whose distal radius may have changed; a flagged entry refreshes the dirty part of
+        // its distal subtree on demand, and everything still dirty is refreshed bottom-up by the whole CTA after the
+        // replay.  (The radii that get PRINTED are recomputed on the host with libm pow, see octa_grow_host.cu.)
+        unsigned char* DIRTY = D.dirty[f] + nb;
+        auto mark_walk = [&](int n) {
             while (true) {
                 const int par = PAR[n];
-                const int nch = NCH[n];
-                if (par < 0 || nch == 0) return;
-                const double kap = K[n];
-                double s = 0 + pow(R[C0[n]], kap);
-                if (nch > 1) s = s + pow(R[C1[n]], kap);
-                const double rp = pow(s, 1 / kap);
-                if (R[n] == rp) return;
-                R[n] = rp;
+                if (par < 0 || DIRTY[n]) return;
+                DIRTY[n] = 1;
                 if (slot_call[par] == call_id && NCH[par] == 1 && PAR[par] >= 0) {
                     const int rk = slot[par];
-                    if (rk > cur_rank) {
-                        bool dup = false;
-                        for (int q = 0; q < s_npend; ++q) if (s_pend[q] == rk) { dup = true; break; }
-                        if (!dup) { if (s_npend < PEND_MAX) s_pend[s_npend++] = rk; else s_overflow = 1; }
-                    }
+                    if (rk > cur_rank && rtag[rk] != call_id) { rtag[rk] = call_id; ++outstanding; }
                 }
                 n = par;
             }
         };
-        int ai = 0;
+        auto refresh_subtree = [&](int top) {     // post-order over the dirty part of subtree(top), no stack needed
+            int n = top;
+            while (true) {
+                const int nch = NCH[n];
+                const int c0 = C0[n], c1 = C1[n];
+                if (nch >= 1 && DIRTY[c0]) { n = c0; continue; }
+                if (nch >= 2 && DIRTY[c1]) { n = c1; continue; }
+                if (nch > 0) {
+                    const double kap = K[n];
+                    double sm = fast_pow(R[c0], kap);
+                    if (nch > 1) sm = sm + fast_pow(R[c1], kap);
+                    R[n] = fast_pow(sm, 1 / kap);
+                }
+                DIRTY[n] = 0;
+                if (n == top) return;
+                n = PAR[n];
+            }
+        };
+        int ai = 0, scan = 0;
         while (true) {
-            // next entry in dict order: the smaller of the next action entry and the pending rechecks
+            // next entry in dict order: the next action entry, unless an entry flagged for a recheck (its distal
+            // radius was changed by a walk of this call) comes first.  Flags always point past cur_rank, and `scan`
+            // moves monotonically, so every dict slot is inspected at most once per call.
             const int ea = (ai < na) ? alist[ai] : 0x7fffffff;
-            int pq = -1, ep = 0x7fffffff;
-            for (int q = 0; q < s_npend; ++q) if (s_pend[q] < ep) { ep = s_pend[q]; pq = q; }
-            if (ea == 0x7fffffff && pq < 0) break;
-            int e;
+            int e = -1;
+            if (outstanding > 0) {
+                if (scan <= cur_rank) scan = cur_rank + 1;
+                const int lim = ea < nd_ ? ea : nd_;
+                for (; scan < lim; ++scan) if (rtag[scan] == call_id) { e = scan; break; }
+            }
             bool from_pending;
-            if (ep <= ea) {
-                e = ep; from_pending = true;
-                s_pend[pq] = s_pend[--s_npend];
-                if (ep == ea) ++ai;             // also an action entry: handle once
+            if (e >= 0) {
+                from_pending = true; --outstanding; rtag[e] = 0; scan = e + 1;
+            } else if (ea != 0x7fffffff) {
+                e = ea; ++ai;
+                from_pending = (rtag[e] == call_id);
+                if (from_pending) { --outstanding; rtag[e] = 0; }
             } else {
-                e = ea; from_pending = false; ++ai;
+                break;
             }
             if (D.err[g]) break;
             cur_rank = e;
             Proposal pr = prop[e];
             const int nd = dict[e];
             if (pr.type == P_INTER_DRAW || pr.type == P_INTER_EMPTY) {
-                const double r1 = R[C0[nd]];
-                if (from_pending || r1 != pr.r1_used) {
+                const int cd = C0[nd];
+                if (DIRTY[cd]) refresh_subtree(cd);
+                const double r1 = R[cd];
+                (void)from_pending;
+                if (r1 != pr.r1_used) {
                     // distal radius changed since k_eval (an earlier entry of this call branched below it)
                     NodeCtx nc;
                     load_ctx(D, S, P, g, f, nd, &nc);
@@ -742,7 +764,7 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
                 const double u = next_uniform();
                 if (pr.ratio5 <= u && pr.cond) continue;
                 if (add_node(pr.p, nd, 1) < 0) break;
-                walk(nd);
+                mark_walk(nd);
                 DEACT[nd] = 1;
             } else if (pr.type == P_LEAF_ELONG) {
                 if (add_node(pr.p, nd, 0) < 0) break;
@@ -752,14 +774,13 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
                 if (bif) {
                     if (add_node(pr.b1, nd, 0) < 0) break;
                     if (add_node(pr.b2, nd, 1) < 0) break;
-                    walk(nd);
+                    mark_walk(nd);
                     DEACT[nd] = 1;
                 } else {
                     if (add_node(pr.p, nd, 0) < 0) break;
                 }
             }
         }
-        if (s_overflow) D.err[g] = 4;
         D.py_pos[g] = ppos;
         D.py_draws[g] += draws;
         D.n_prev[f][g] = n_before;
@@ -767,8 +788,49 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
     }
     __syncthreads();
     if (D.err[g]) return;
-    // active list: drop the nodes that branched (stable), append the new nodes (element_mesh.py:103-111,180-193)
     const int n_after = D.n_nodes[f][g];
+    {
+        // bottom-up refresh of every node still dirty: a node is computed by the thread that completes its last
+        // dirty child (atomic countdown), so the critical path is one root chain, not the sum over events
+        unsigned char* DIRTY = D.dirty[f] + nb;
+        int* pend = D.cnt + nb;                      // all zero outside k_group
+        volatile double* R = D.nrad[f] + nb;
+        const double* K = D.nkap[f] + nb;
+        const int* PAR = D.npar[f] + nb; const int* C0 = D.nch0[f] + nb; const int* C1 = D.nch1[f] + nb;
+        const unsigned char* NCH = D.nnch[f] + nb;
+        for (int n = tid; n < n_after; n += blockDim.x)
+            if (DIRTY[n]) {
+                const int nch = NCH[n];
+                const int c = ((nch >= 1 && DIRTY[C0[n]]) ? 1 : 0) + ((nch >= 2 && DIRTY[C1[n]]) ? 1 : 0);
+                pend[n] = c ? c : -1;                // -1: ready now
+            }
+        __syncthreads();
+        for (int n0 = tid; n0 < n_after; n0 += blockDim.x) {
+            if (!DIRTY[n0] || pend[n0] != -1) continue;
+            int n = n0;
+            while (true) {
+                const int nch = NCH[n];
+                if (nch > 0) {
+                    const double kap = K[n];
+                    double sm = fast_pow(R[C0[n]], kap);
+                    if (nch > 1) sm = sm + fast_pow(R[C1[n]], kap);
+                    R[n] = fast_pow(sm, 1 / kap);
+                }
+                pend[n] = 0;
+                __threadfence_block();
+                const int p = PAR[n];
+                if (p < 0 || !DIRTY[p]) break;          // (the root is never marked)
+                const int old = atomicSub(&pend[p], 1);
+                if (old != 1) break;
+                __threadfence_block();
+                n = p;
+            }
+        }
+        __syncthreads();
+        for (int n = tid; n < n_after; n += blockDim.x) DIRTY[n] = 0;
+        __syncthreads();
+    }
+    // active list: drop the nodes that branched (stable), append the new nodes (element_mesh.py:103-111,180-193)
     int* act = D.act[f] + nb;
     double* ax = D.ax[f] + nb; double* ay = D.ay[f] + nb; double* az = D.az[f] + nb;
     unsigned char* deact = D.deact[f] + nb;

@@ -1,0 +1,95 @@
+"""Batched hot path: seeds -> vessel graphs (CSV rows) -> 3-D voxel volume -> 2-D label / gray image.
+
+This is the device-side composition of the C-ABI entry points that `generate_vessel_graph.py`
+(growth, CSV, 304^2 gray image, optional 3-D volume) and `visualize_vessel_graphs.py --resolution
+1216,1216,16 [--binarize]` (1216^2 image / label, optional 3-D volume) drive per sample in the
+reference.  torch is used for device memory, pinned host buffers and streams only."""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import os
+from typing import Sequence
+
+import numpy as np
+
+from . import graph_io, growth, tree2img
+
+
+class Pipeline:
+    def __init__(self, config: dict, device=None, volume_dims: Sequence[int] = (1216, 1216, 16),
+                 label_res: Sequence[int] = (1216, 1216), image_res: Sequence[int] = (304, 304), mip_axis: int = 2,
+                 voxelize: bool = True, host_threads: int = 0):
+        import torch
+
+        self.torch = torch
+        self.config = config
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.volume_dims = [int(d) for d in volume_dims]
+        self.label_res = [int(d) for d in label_res]
+        self.image_res = [int(d) for d in image_res]
+        self.mip_axis = int(mip_axis)
+        self.voxelize = bool(voxelize)
+        self.host_threads = host_threads or max(1, (os.cpu_count() or 2) - 1)
+        self._buf = {}
+
+    def _tensor(self, key, shape, dtype, pinned=False):
+        t = self._buf.get(key)
+        n = int(np.prod(shape))
+        if t is None or t.numel() < n:
+            if pinned:
+                t = self.torch.empty(n, dtype=dtype).pin_memory()
+            else:
+                t = self.torch.empty(n, dtype=dtype, device=self.device)
+            self._buf[key] = t
+        return t[:n].view(*shape)
+
+    def run(self, seeds: Sequence[int], d2h: bool = True, csv: bool = True) -> dict:
+        """One step over len(seeds) samples.  Results: edges (host), offsets, volume / label / image (device
+        tensors), and with d2h: label_host / image_host (pinned uint8) and csv (list of bytes)."""
+        torch = self.torch
+        with torch.cuda.device(self.device):
+            graphs, stats, extra = growth.grow_batch(self.config, seeds)
+            n = len(seeds)
+            sizes = [len(a) + len(v) for a, v in graphs]
+            offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+            E = int(offs[-1])
+            host_edges = self._tensor("edges_host", (max(E, 1), 7), torch.float64, pinned=True)
+            he = host_edges.numpy()
+            for i, (a, v) in enumerate(graphs):
+                he[offs[i]:offs[i] + len(a)] = a
+                he[offs[i] + len(a):offs[i + 1]] = v
+            edges_dev = self._tensor("edges_dev", (max(E, 1), 7), torch.float64)
+            edges_dev.copy_(host_edges, non_blocking=True)
+            out = {"graphs": graphs, "stats": stats, "offsets": offs, "grow_device_ms": extra["device_ms"],
+                   "edges_host": he[:E]}
+            if self.voxelize:
+                shape = tree2img.voxel_volume_shape(self.volume_dims)
+                vol = self._tensor("vol", (n, *shape), torch.uint16)
+                from . import _lib
+                need = int(_lib.lib().octa_voxelize_workspace_bytes(n, E, _lib.int3(self.volume_dims)))
+                ws = self._tensor("vox_ws", (need,), torch.uint8)
+                vol = tree2img.voxelize_batch_device(edges_dev[:max(E, 1)], offs, self.volume_dims, out=vol, workspace=ws)
+                out["volume"] = vol
+            lab = self._tensor("label", (n, self.label_res[1], self.label_res[0]), torch.uint8)
+            tree2img.raster_batch_device(edges_dev, offs, self.label_res, self.mip_axis, out=lab)
+            img = self._tensor("image", (n, self.image_res[1], self.image_res[0]), torch.uint8)
+            tree2img.raster_batch_device(edges_dev, offs, self.image_res, self.mip_axis, out=img)
+            out["label"], out["image"] = lab, img
+            if d2h:
+                lab_h = self._tensor("label_host", tuple(lab.shape), torch.uint8, pinned=True)
+                img_h = self._tensor("image_host", tuple(img.shape), torch.uint8, pinned=True)
+                lab_h.copy_(lab, non_blocking=True)
+                img_h.copy_(img, non_blocking=True)
+                if csv:
+                    with cf.ThreadPoolExecutor(max_workers=self.host_threads) as ex:   # ctypes releases the GIL
+                        out["csv"] = list(ex.map(lambda i: graph_io.csv_bytes(he[offs[i]:offs[i + 1]]), range(n)))
+                torch.cuda.current_stream().synchronize()
+                out["label_host"], out["image_host"] = lab_h.numpy(), img_h.numpy()
+                out["d2h_bytes"] = int(lab_h.numel() + img_h.numel())
+                out["h2d_bytes"] = int(E * 56)
+            return out
+
+
+def shard_seeds(base_seed: int, num_samples: int, rank: int, world: int):
+    """Sample i (seed base+i) belongs to rank i mod world; the result of a sample depends on its seed only."""
+    return [base_seed + i for i in range(num_samples) if i % world == rank]

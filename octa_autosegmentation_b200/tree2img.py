@@ -110,3 +110,70 @@ def voxelize_batch_device(edges7, edge_offsets, volume_dimensions: Sequence[int]
                                                       ctypes.byref(opts), out.data_ptr(), workspace.data_ptr(),
                                                       workspace.numel(), ctypes.c_void_p(stream.cuda_stream)))
     return out
+
+
+def raster_edges(edges7: np.ndarray, image_resolution: Sequence[int], MIP_axis: int = 2, min_radius: float = 0.0,
+                 max_radius: float = 1.0) -> np.ndarray:
+    """Host-buffer call through the C ABI (octa_raster2d_host).  Returns uint8 [H, W]."""
+    edges7 = np.ascontiguousarray(edges7, dtype=np.float64).reshape(-1, 7)
+    W, H = int(image_resolution[0]), int(image_resolution[1])
+    out = np.empty((H, W), dtype=np.uint8)
+    opts = _lib.OctaVoxOpts(float(min_radius), float(max_radius), 0, 0)
+    L = _lib.lib()
+    L.octa_raster2d_host.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                     ctypes.POINTER(_lib.OctaVoxOpts), ctypes.c_void_p]
+    _lib.check(L.octa_raster2d_host(edges7.ctypes.data, edges7.shape[0], H, W, int(MIP_axis), ctypes.byref(opts),
+                                    out.ctypes.data))
+    return out
+
+
+def rasterize_forest(forest, image_resolution: Sequence[float], MIP_axis: int = 2, radius_list: list = None,
+                     min_radius: float = 0, max_radius: float = 1, max_dropout_prob=0, blackdict: dict = None,
+                     colorize: str = None):
+    """Reference: tree2img.py:12-114.  Same signature and return value ((H, W) uint16 gray 0..255, blackdict);
+    same host-side semantics for the radius filter, the legacy string rows and the subtree dropout (one
+    `random()` draw for p unless a blackdict is given, one per surviving edge).  `radius_list` receives
+    1.3 * radius like the reference (:82-83).  `colorize` (RGB plasma rendering for figures) is not
+    provided by the GPU path."""
+    if colorize is not None:
+        raise NotImplementedError("colorize is a matplotlib colormap feature of the reference and is not part of the GPU path")
+    axes_ok = MIP_axis in (0, 1, 2)
+    if not axes_ok:
+        raise ValueError("MIP_axis must be 0, 1 or 2")
+    rl = []
+    e7, blackdict = forest_to_edges7(forest, rl, min_radius, max_radius, max_dropout_prob, blackdict)
+    if radius_list is not None:
+        radius_list.extend([r * 1.3 for r in rl])
+    res = [int(image_resolution[0]), int(image_resolution[1])]
+    return raster_edges(e7, res, MIP_axis).astype(np.uint16), blackdict
+
+
+def raster_batch_device(edges7, edge_offsets, image_resolution: Sequence[int], MIP_axis: int = 2, min_radius: float = 0.0,
+                        max_radius: float = 1.0, out=None, workspace=None, stream=None):
+    """Batched device-resident 2-D rasterization (octa_raster2d_batch_dev): CUDA uint8 tensor [n_graphs, H, W]."""
+    import torch
+
+    if not (edges7.is_cuda and edges7.dtype == torch.float64 and edges7.is_contiguous()):
+        raise ValueError("edges7 must be a contiguous CUDA float64 tensor")
+    offs = np.ascontiguousarray(np.asarray(edge_offsets, dtype=np.int64))
+    n_graphs = offs.shape[0] - 1
+    W, H = int(image_resolution[0]), int(image_resolution[1])
+    L = _lib.lib()
+    L.octa_raster2d_workspace_bytes.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int]
+    L.octa_raster2d_workspace_bytes.restype = ctypes.c_size_t
+    L.octa_raster2d_batch_dev.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_int, ctypes.POINTER(_lib.OctaVoxOpts), ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    if out is None:
+        out = torch.empty((n_graphs, H, W), dtype=torch.uint8, device=edges7.device)
+    ws_bytes = int(L.octa_raster2d_workspace_bytes(n_graphs, int(offs[-1]), H, W))
+    if workspace is None or workspace.numel() < ws_bytes:
+        workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=edges7.device)
+    if stream is None:
+        stream = torch.cuda.current_stream(edges7.device)
+    opts = _lib.OctaVoxOpts(float(min_radius), float(max_radius), 0, 0)
+    with torch.cuda.device(edges7.device):
+        _lib.check(L.octa_raster2d_batch_dev(edges7.data_ptr(), offs.ctypes.data, n_graphs, H, W, int(MIP_axis),
+                                             ctypes.byref(opts), out.data_ptr(), workspace.data_ptr(),
+                                             workspace.numel(), ctypes.c_void_p(stream.cuda_stream)))
+    return out

@@ -64,3 +64,14 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def shipped_pair(name="20230216_232653"):
+    """One of the 500 (graph csv -> 1216^2 1-bit label) pairs the reference ships under datasets/ -- the only pin
+    available for the matplotlib/Agg 2-D path.  Stored as csv.gz + bit-packed label."""
+    from PIL import Image
+    raw = open(os.path.join(rh.REFERENCE_ROOT, "datasets", "vessel_graphs", name + ".csv"), "rb").read()
+    with gzip.GzipFile(os.path.join(GOLD, "shipped_%s.csv.gz" % name), "wb", mtime=0) as f:
+        f.write(raw)
+    lab = np.array(Image.open(os.path.join(rh.REFERENCE_ROOT, "datasets", "labels", name + ".png")))
+    np.savez_compressed(os.path.join(GOLD, "shipped_%s_label.npz" % name), packed=np.packbits(lab), shape=np.array(lab.shape))

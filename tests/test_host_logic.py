@@ -1,0 +1,56 @@
+"""CPU: host-side logic of the package (config surface, CLI overrides, sharding, multi-process gather)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import yaml
+
+from conftest import ROOT
+from octa_autosegmentation_b200 import config as cfgmod
+from octa_autosegmentation_b200 import growth, pipeline
+
+
+def test_default_config_shape_and_overrides():
+    c = cfgmod.default_config()
+    assert set(c) == {"Greenhouse", "output", "Forest"} and len(c["Greenhouse"]["modes"]) == 2
+    cfgmod.apply_cli_overrides_from_unknown_args(c, ["--output.directory", "/tmp/x", "--Greenhouse.param_scale=6",
+                                                     "--output.save_stats", "--threads", "3", "--Forest.N_trees", "16"])
+    assert c["output"]["directory"] == "/tmp/x" and c["Greenhouse"]["param_scale"] == 6
+    assert c["output"]["save_stats"] is True and c["Forest"]["N_trees"] == 16 and "threads" not in c
+
+
+def test_read_config_roundtrip(tmp_path):
+    p = tmp_path / "c.yml"
+    p.write_text(yaml.dump(cfgmod.default_config()))
+    assert cfgmod.read_config(str(p)) == cfgmod.default_config()
+
+
+def test_make_config_mirrors_reference_flags():
+    c = cfgmod.default_config()
+    g = growth.make_config(c)
+    assert g.n_modes == 2 and g.modes[0].first_mode == 1 and g.modes[1].first_mode == 0
+    assert g.modes[0].reinit == 0 and g.modes[1].reinit == 1
+    assert [g.walls[i] for i in range(g.n_walls)] == [0, 1, 2, 3]
+    c["Forest"]["type"] = "grid"
+    with pytest.raises(NotImplementedError):
+        growth.make_config(c)
+
+
+def test_round_robin_sharding_covers_every_sample_once():
+    for world in (1, 2, 4, 8):
+        allseeds = sorted(s for r in range(world) for s in pipeline.shard_seeds(100, 37, r, world))
+        assert allseeds == list(range(100, 137))
+    assert pipeline.shard_seeds(0, 10, 1, 4) == [1, 5, 9]
+
+
+def test_two_rank_gloo_gather_of_edge_tables():
+    """N > 1 host path: ranks own disjoint samples and rank 0 gathers the packed edge tables (gloo, CPU)."""
+    script = os.path.join(ROOT, "tests", "_gloo_gather_worker.py")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29731")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29731", script],
+                       env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "GATHER_OK" in r.stdout
