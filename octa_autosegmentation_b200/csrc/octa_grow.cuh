@@ -10,6 +10,7 @@ namespace octa {
 
 constexpr int GEOMETRY_SIZE = 76;                 // simulation_space.py:8
 constexpr int MAX_VALID = GEOMETRY_SIZE * GEOMETRY_SIZE;
+constexpr int GRID = 64;                          // bucket grid cells per axis over the unit square
 constexpr int SET_TBL = 16384;                    // slots per CPython-set emulation table (x2: resize target)
 
 // per-iteration parameters (identical for every graph of the batch; computed on the host exactly
@@ -47,6 +48,9 @@ struct GrowDev {
     // sinks: [0] oxygen sinks, [1] CO2 sources
     double *sx[2], *sy[2], *sz[2];
     int *n_s[2];
+    // bucket grids: [0] arterial nodes (+radius), [1] O2 sinks, [2]/[3] active arterial / venous nodes
+    double *gx[4], *gy[4], *gz[4], *gr[4];
+    int *gi[4], *gcell[4];
     // RNG streams
     MTState *np_mt, *py_mt;
     unsigned int* py_buf;

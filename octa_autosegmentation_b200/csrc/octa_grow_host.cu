@@ -199,6 +199,11 @@ void carve(Carver& c, const GrowShape& S, GrowDev* D) {
         D->sx[f] = c.take<double>(GS); D->sy[f] = c.take<double>(GS); D->sz[f] = c.take<double>(GS);
         D->n_s[f] = c.take<int>(G);
     }
+    const size_t GG = (size_t)S.G * (S.capN > S.capS ? S.capN : S.capS);
+    for (int w = 0; w < 4; ++w) {
+        D->gx[w] = c.take<double>(GG); D->gy[w] = c.take<double>(GG); D->gz[w] = c.take<double>(GG); D->gr[w] = c.take<double>(GG);
+        D->gi[w] = c.take<int>(GG); D->gcell[w] = c.take<int>(G * (GRID * GRID + 1));
+    }
     D->np_mt = c.take<MTState>(G); D->py_mt = c.take<MTState>(G);
     D->py_buf = c.take<unsigned int>(G * S.pycap); D->py_n = c.take<int>(G); D->py_pos = c.take<int>(G);
     D->py_draws = c.take<long long>(G);

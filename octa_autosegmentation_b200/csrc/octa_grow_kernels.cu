@@ -2,6 +2,7 @@
 //
 // Replaces, per iteration of Greenhouse.develop_forest (greenhouse.py:90-125):
 //   k_sample        simulation_space.py:57-67 get_candidate_sinks (legacy numpy MT19937 stream on device)
+//   k_grid_build    (ours) bucket grids over nodes / sinks / active nodes; replaces the cKDTree rebuilds (element_mesh.py:97-101)
 //   k_sink_tests    greenhouse.py:337-338   static rejection tests (i) arterial oxygen range, (ii) sink spacing
 //   k_sink_greedy   greenhouse.py:339-341   order-dependent spacing among new sinks (lexicographically-first MIS)
 //   k_assign        greenhouse.py:343-366   nearest ACTIVE node of every attractor (<= delta)
@@ -182,62 +183,103 @@ __global__ void __launch_bounds__(1024) k_sample(GrowDev D, GrowShape S, IterP P
 }
 
 // ------------------------------------------------------------------------------------------
-// k_sink_tests: thread per candidate, tiles of nodes / sinks staged through shared memory
+// uniform bucket grid (GRID x GRID cells over the unit square, points outside clamp to the border cells):
+// prunes the pair scans of k_sink_tests / k_assign; every reported distance is still the exact float64
+// expression, so results are identical to a brute-force scan (= cKDTree's exact queries).
+// Points are counting-sorted by cell with their coordinates copied next to each other, so one row of
+// cells is one contiguous range of the sorted arrays.
 // ------------------------------------------------------------------------------------------
 constexpr int TILE = 128;
 
+__device__ __forceinline__ int grid_cell(double v) {
+    int c = (int)floor(v * (double)GRID);
+    return c < 0 ? 0 : (c >= GRID ? GRID - 1 : c);
+}
+
+// which: 0 = all arterial nodes (+radius), 1 = O2 sinks, 2 / 3 = active arterial / venous nodes
+__global__ void __launch_bounds__(1024) k_grid_build(GrowDev D, GrowShape S, int which) {
+    __shared__ int hist[GRID * GRID];
+    __shared__ int cursor[GRID * GRID];
+    const int g = blockIdx.x, tid = threadIdx.x;
+    if (D.err[g]) return;
+    const double *px, *py, *pz, *pr = nullptr;
+    int n;
+    size_t cap;
+    if (which == 0) { cap = S.capN; px = D.nx[0] + g * cap; py = D.ny[0] + g * cap; pz = D.nz[0] + g * cap; pr = D.nrad[0] + g * cap; n = D.n_nodes[0][g]; }
+    else if (which == 1) { cap = S.capS; px = D.sx[0] + g * cap; py = D.sy[0] + g * cap; pz = D.sz[0] + g * cap; n = D.n_s[0][g]; }
+    else { const int f = which - 2; cap = S.capN; px = D.ax[f] + g * cap; py = D.ay[f] + g * cap; pz = D.az[f] + g * cap; n = D.n_act[f][g]; }
+    const size_t gcap = S.capN > S.capS ? S.capN : S.capS;
+    double* gx = D.gx[which] + g * gcap; double* gy = D.gy[which] + g * gcap; double* gz = D.gz[which] + g * gcap;
+    double* grd = D.gr[which] + g * gcap;
+    int* gi = D.gi[which] + g * gcap;
+    int* cs = D.gcell[which] + (size_t)g * (GRID * GRID + 1);
+    for (int c = tid; c < GRID * GRID; c += blockDim.x) hist[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) atomicAdd(&hist[grid_cell(py[i]) * GRID + grid_cell(px[i])], 1);
+    __syncthreads();
+    int run = 0;
+    for (int base = 0; base < GRID * GRID; base += blockDim.x) {
+        const int c = base + tid;
+        const int v = hist[c];
+        int total;
+        const int incl = block_scan_incl(v, &total);
+        cs[c] = run + incl - v;
+        cursor[c] = run + incl - v;
+        run += total;
+    }
+    if (tid == 0) cs[GRID * GRID] = run;
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) {
+        const double x = px[i], y = py[i];
+        const int pos = atomicAdd(&cursor[grid_cell(y) * GRID + grid_cell(x)], 1);
+        gx[pos] = x; gy[pos] = y; gz[pos] = pz[i]; gi[pos] = i;
+        if (pr) grd[pos] = pr[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_sink_tests: thread per candidate over the bucket grids of the arterial nodes and the O2 sinks
+// ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TILE) k_sink_tests(GrowDev D, GrowShape S, IterP P) {
-    __shared__ double tx[TILE], ty[TILE], tz[TILE], tr[TILE];
     const int tiles = (S.Nmax + TILE - 1) / TILE;
     const double epsn2 = P.eps_n_eff * P.eps_n_eff, epss2 = P.eps_s * P.eps_s;
+    const size_t gcap = S.capN > S.capS ? S.capN : S.capS;
     for (int w = blockIdx.x; w < S.G * tiles; w += gridDim.x) {
         const int g = w / tiles, tile = w - g * tiles;
         if (D.err[g]) continue;
         const int nc = D.n_cand[g];
-        if (tile * TILE >= nc) continue;
         const int c = tile * TILE + threadIdx.x;
-        const bool live = c < nc;
-        double px = 0, py = 0, pz = 0;
-        if (live) { px = D.cx[(size_t)g * S.Nmax + c]; py = D.cy[(size_t)g * S.Nmax + c]; pz = D.cz[(size_t)g * S.Nmax + c]; }
-        bool pass = live;
+        if (c >= nc) continue;
+        const double px = D.cx[(size_t)g * S.Nmax + c], py = D.cy[(size_t)g * S.Nmax + c], pz = D.cz[(size_t)g * S.Nmax + c];
+        bool pass = true;
         // (i) every arterial node within eps must be farther than its oxygen range (greenhouse.py:337)
-        const int Pn = D.n_nodes[0][g];
-        const size_t nb = (size_t)g * S.capN;
-        for (int base = 0; base < Pn; base += TILE) {
-            const int j = base + threadIdx.x;
-            __syncthreads();
-            if (j < Pn) { tx[threadIdx.x] = D.nx[0][nb + j]; ty[threadIdx.x] = D.ny[0][nb + j]; tz[threadIdx.x] = D.nz[0][nb + j]; tr[threadIdx.x] = D.nrad[0][nb + j]; }
-            __syncthreads();
-            if (!__syncthreads_or(pass)) break;
-            if (pass) {
-                const int lim = Pn - base < TILE ? Pn - base : TILE;
-                for (int q = 0; q < lim; ++q) {
-                    const double d2 = dist2(px, py, pz, tx[q], ty[q], tz[q]);
-                    if (d2 <= epsn2) {
-                        if (!(sqrt(d2) > oxygen_distance(tr[q], P.param_scale))) { pass = false; break; }
-                    }
+        {
+            const double* gx = D.gx[0] + g * gcap; const double* gy = D.gy[0] + g * gcap; const double* gz = D.gz[0] + g * gcap;
+            const double* gr = D.gr[0] + g * gcap;
+            const int* cs = D.gcell[0] + (size_t)g * (GRID * GRID + 1);
+            const int x0 = grid_cell(px - P.eps_n_eff), x1 = grid_cell(px + P.eps_n_eff);
+            const int y0 = grid_cell(py - P.eps_n_eff), y1 = grid_cell(py + P.eps_n_eff);
+            for (int cy = y0; cy <= y1 && pass; ++cy) {
+                const int beg = cs[cy * GRID + x0], end = cs[cy * GRID + x1 + 1];
+                for (int q = beg; q < end; ++q) {
+                    const double d2 = dist2(px, py, pz, gx[q], gy[q], gz[q]);
+                    if (d2 <= epsn2 && !(sqrt(d2) > oxygen_distance(gr[q], P.param_scale))) { pass = false; break; }
                 }
             }
         }
         // (ii) no existing sink within eps_s (greenhouse.py:338)
-        const int Sn = D.n_s[0][g];
-        const size_t sb = (size_t)g * S.capS;
-        for (int base = 0; base < Sn; base += TILE) {
-            const int j = base + threadIdx.x;
-            __syncthreads();
-            if (j < Sn) { tx[threadIdx.x] = D.sx[0][sb + j]; ty[threadIdx.x] = D.sy[0][sb + j]; tz[threadIdx.x] = D.sz[0][sb + j]; }
-            __syncthreads();
-            if (!__syncthreads_or(pass)) break;
-            if (pass) {
-                const int lim = Sn - base < TILE ? Sn - base : TILE;
-                for (int q = 0; q < lim; ++q) {
-                    const double d2 = dist2(px, py, pz, tx[q], ty[q], tz[q]);
-                    if (within_sqrt(d2, P.eps_s, epss2)) { pass = false; break; }
-                }
+        if (pass) {
+            const double* gx = D.gx[1] + g * gcap; const double* gy = D.gy[1] + g * gcap; const double* gz = D.gz[1] + g * gcap;
+            const int* cs = D.gcell[1] + (size_t)g * (GRID * GRID + 1);
+            const int x0 = grid_cell(px - P.eps_s), x1 = grid_cell(px + P.eps_s);
+            const int y0 = grid_cell(py - P.eps_s), y1 = grid_cell(py + P.eps_s);
+            for (int cy = y0; cy <= y1 && pass; ++cy) {
+                const int beg = cs[cy * GRID + x0], end = cs[cy * GRID + x1 + 1];
+                for (int q = beg; q < end; ++q)
+                    if (within_sqrt(dist2(px, py, pz, gx[q], gy[q], gz[q]), P.eps_s, epss2)) { pass = false; break; }
             }
         }
-        __syncthreads();
-        if (live) D.cpass[(size_t)g * S.Nmax + c] = pass ? 1 : 0;
+        D.cpass[(size_t)g * S.Nmax + c] = pass ? 1 : 0;
     }
 }
 
@@ -311,39 +353,37 @@ __global__ void __launch_bounds__(1024) k_sink_greedy(GrowDev D, GrowShape S, It
 }
 
 // ------------------------------------------------------------------------------------------
-// k_assign: thread per attractor, active-node positions staged through shared memory
+// k_assign: thread per attractor; exact nearest ACTIVE node within delta through the bucket grid
+// (ties -> lowest list position, as a scan in list order would give)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TILE) k_assign(GrowDev D, GrowShape S, IterP P, int f) {
-    __shared__ double tx[TILE], ty[TILE], tz[TILE];
     const int tiles = (S.capS + TILE - 1) / TILE;
     const double delta = P.delta[f];
+    const size_t gcap = S.capN > S.capS ? S.capN : S.capS;
     for (int w = blockIdx.x; w < S.G * tiles; w += gridDim.x) {
         const int g = w / tiles, tile = w - g * tiles;
         if (D.err[g]) continue;
         const int A = D.n_s[f][g];
-        if (tile * TILE >= A) continue;
+        if (tile == 0 && threadIdx.x == 0) { D.counters[g * 8 + 0] += A; D.counters[g * 8 + 1] += D.n_act[f][g]; }
         const int a = tile * TILE + threadIdx.x;
-        const bool live = a < A;
+        if (a >= A) continue;
         const size_t sb = (size_t)g * S.capS, nb = (size_t)g * S.capN;
-        double px = 0, py = 0, pz = 0;
-        if (live) { px = D.sx[f][sb + a]; py = D.sy[f][sb + a]; pz = D.sz[f][sb + a]; }
-        const int M = D.n_act[f][g];
+        const double px = D.sx[f][sb + a], py = D.sy[f][sb + a], pz = D.sz[f][sb + a];
+        const double* gx = D.gx[2 + f] + g * gcap; const double* gy = D.gy[2 + f] + g * gcap; const double* gz = D.gz[2 + f] + g * gcap;
+        const int* gi = D.gi[2 + f] + g * gcap;
+        const int* cs = D.gcell[2 + f] + (size_t)g * (GRID * GRID + 1);
+        const int x0 = grid_cell(px - delta), x1 = grid_cell(px + delta), y0 = grid_cell(py - delta), y1 = grid_cell(py + delta);
         double best = INFINITY;
         int bi = -1;
-        for (int base = 0; base < M; base += TILE) {
-            const int j = base + threadIdx.x;
-            __syncthreads();
-            if (j < M) { tx[threadIdx.x] = D.ax[f][nb + j]; ty[threadIdx.x] = D.ay[f][nb + j]; tz[threadIdx.x] = D.az[f][nb + j]; }
-            __syncthreads();
-            const int lim = M - base < TILE ? M - base : TILE;
-            for (int q = 0; q < lim; ++q) {
-                const double d2 = dist2(tx[q], ty[q], tz[q], px, py, pz);
-                if (d2 < best) { best = d2; bi = base + q; }
+        for (int cy = y0; cy <= y1; ++cy) {
+            const int beg = cs[cy * GRID + x0], end = cs[cy * GRID + x1 + 1];
+            for (int q = beg; q < end; ++q) {
+                const double d2 = dist2(gx[q], gy[q], gz[q], px, py, pz);
+                const int li = gi[q];
+                if (d2 < best || (d2 == best && li < bi)) { best = d2; bi = li; }
             }
         }
-        __syncthreads();
-        if (live) D.assign[sb + a] = (bi >= 0 && sqrt(best) <= delta) ? D.act[f][nb + bi] : -1;
-        if (tile == 0 && threadIdx.x == 0) { D.counters[g * 8 + 0] += A; D.counters[g * 8 + 1] += M; }
+        D.assign[sb + a] = (bi >= 0 && sqrt(best) <= delta) ? D.act[f][nb + bi] : -1;
     }
 }
 
@@ -1038,10 +1078,14 @@ __global__ void __launch_bounds__(1024) k_kill(GrowDev D, GrowShape S, IterP P, 
 // ------------------------------------------------------------------------------------------
 void launch_iteration(const GrowDev& D, const GrowShape& S, const IterP& P, int n_sm, cudaStream_t st) {
     k_sample<<<S.G, 1024, 0, st>>>(D, S, P);
+    k_grid_build<<<S.G, 1024, 0, st>>>(D, S, 0);
+    k_grid_build<<<S.G, 1024, 0, st>>>(D, S, 1);
     k_sink_tests<<<n_sm * 8, TILE, 0, st>>>(D, S, P);
     k_sink_greedy<<<S.G, 1024, 0, st>>>(D, S, P);
-    count_launch(3);
+    count_launch(5);
     for (int f = 0; f < 2; ++f) {
+        k_grid_build<<<S.G, 1024, 0, st>>>(D, S, 2 + f);
+        count_launch(1);
         k_assign<<<n_sm * 8, TILE, 0, st>>>(D, S, P, f);
         k_group<<<S.G, 1024, 0, st>>>(D, S, P, f);
         k_eval<<<dim3(16, S.G), 128, 0, st>>>(D, S, P, f);

@@ -200,9 +200,36 @@ __global__ void vox_fill_kernel(const int64_t* __restrict__ edge_offsets, int n_
 // ---------------------------------------------------------------------------------------------
 // main kernel: one CTA = one tile of one graph
 // ---------------------------------------------------------------------------------------------
+// exact reference chain for one voxel (tree2img.py:259-280); used only inside the guard bands of the fast path
+__device__ __noinline__ uint32_t exact_voxel_q(const VoxEdge& e, double vx, double vy, double vz) {
+    const double s0 = e.p1[0] - e.p2[0], s1 = e.p1[1] - e.p2[1], s2 = e.p1[2] - e.p2[2];
+    const double ss = (s0 * s0 + s1 * s1) + s2 * s2;
+    const double SQRT3 = 1.7320508075688772;          // np.linalg.norm([1,1,1]) (:214)
+    const double rr = e.R - SQRT3 / 2;                // (radius - voxel_diag/2)
+    const double u0 = vx - e.p2[0], u1 = vy - e.p2[1], u2 = vz - e.p2[2];
+    const double t = ((u0 * s0 + u1 * s1) + u2 * s2) / ss;
+    const double q0 = vx - e.p1[0], q1 = vy - e.p1[1], q2 = vz - e.p1[2];
+    const double dcap = fmin(sqrt((q0 * q0 + q1 * q1) + q2 * q2), sqrt((u0 * u0 + u1 * u1) + u2 * u2));
+    double I = 1.0 - ((dcap - rr) / SQRT3);
+    if (t > 0.0 && t < 1.0) {
+        const double e0 = vx - (e.p2[0] + t * s0), e1 = vy - (e.p2[1] + t * s1), e2 = vz - (e.p2[2] + t * s2);
+        const double dl = sqrt((e0 * e0 + e1 * e1) + e2 * e2);
+        const double I1 = 1.0 - ((dl - rr) / SQRT3);
+        I = fmax(I, I1);
+    }
+    if (!(I > 0.0)) return 0;
+    const double cl = I < 1.0 ? I : 1.0;
+    return (uint32_t)(255.0 * cl);
+}
+
+// One warp rasterizes one edge into the shared-memory tile.  Lanes own (y,z) rows of the clipped bounding box
+// and walk along x.  Three tiers per voxel:
+//   1. fp32 broad phase in box-local coordinates -- rejects voxels whose exact contribution is <= 0 (88 %);
+//   2. fast float64 evaluation (fma, reciprocal instead of division): 255*I is accurate to ~1e-11, so its floor
+//      equals the reference's unless 255*I lies within 1e-7 of an integer or t within 1e-9 of {0,1};
+//   3. inside those guard bands (probability ~1e-7) the reference's exact operation chain decides.
 __device__ __forceinline__ void rasterize_edge_into_tile(const VoxEdge& e, const int t0[3], const int t1[3],
                                                          const int T[3], uint32_t* acc, int lane) {
-    // bbox of the edge clipped to this tile
     int b0[3], n[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -210,60 +237,64 @@ __device__ __forceinline__ void rasterize_edge_into_tile(const VoxEdge& e, const
         n[a] = imin(e.hi[a], t1[a]) - b0[a];
         if (n[a] <= 0) return;
     }
-    const int nyz = n[1] * n[2];
-    const int total = n[0] * nyz;
-    const float inv_nyz = 1.0f / (float)nyz, inv_nz = 1.0f / (float)n[2];
-
-    // exact fp64 per-edge constants (tree2img.py:259-261,269)
+    const int nrows = n[1] * n[2];
+    const float inv_nz = 1.0f / (float)n[2];
     const double s0 = e.p1[0] - e.p2[0], s1 = e.p1[1] - e.p2[1], s2 = e.p1[2] - e.p2[2];
     const double ss = (s0 * s0 + s1 * s1) + s2 * s2;
-    const double SQRT3 = 1.7320508075688772;          // np.linalg.norm([1,1,1]) (:214)
-    const double rr = e.R - SQRT3 / 2;                // (radius - voxel_diag/2)
-
-    // fp32 broad phase in box-local coordinates (conservative: only rejects voxels whose exact
-    // contribution is <= 0, which never changes a max that starts at 0)
+    const double inv_ss = ss > 0.0 ? 1.0 / ss : 0.0;
+    const double SQRT3 = 1.7320508075688772, INV_SQRT3 = 0.57735026918962576;
+    const double c0 = 1.0 + (e.R - SQRT3 / 2) * INV_SQRT3;      // I = c0 - d/sqrt3
+    const double tguard = 1e-9 * ss;
+    // fp32 broad phase, coordinates relative to p2 shifted into the clipped box
     const float a0 = (float)(e.p2[0] - (double)b0[0] - 0.5), a1 = (float)(e.p2[1] - (double)b0[1] - 0.5),
                 a2 = (float)(e.p2[2] - (double)b0[2] - 0.5);
     const float f0 = (float)s0, f1 = (float)s1, f2 = (float)s2;
     const float fss = (float)ss;
-    const float inv_ss = fss > 0.f ? 1.0f / fss : 0.f;
+    const float finv = fss > 0.f ? 1.0f / fss : 0.f;
     const float ext = fabsf(a0) + fabsf(a1) + fabsf(a2) + fabsf(f0) + fabsf(f1) + fabsf(f2) + (float)(n[0] + n[1] + n[2]);
     const float reach = (float)e.R + 0.8660254f + 0.02f + 8e-6f * ext;
     const float thr = reach * reach;
-
-    for (int i = lane; i < total; i += 32) {
-        int ix = (int)((float)i * inv_nyz);
-        int r = i - ix * nyz;
-        if (r < 0) { --ix; r += nyz; } else if (r >= nyz) { ++ix; r -= nyz; }
-        int iy = (int)((float)r * inv_nz);
-        int iz = r - iy * n[2];
+    for (int row = lane; row < nrows; row += 32) {
+        int iy = (int)((float)row * inv_nz);
+        int iz = row - iy * n[2];
         if (iz < 0) { --iy; iz += n[2]; } else if (iz >= n[2]) { ++iy; iz -= n[2]; }
-
-        const float w0 = (float)ix - a0, w1 = (float)iy - a1, w2 = (float)iz - a2;
-        float tf = (w0 * f0 + w1 * f1 + w2 * f2) * inv_ss;
-        tf = fminf(fmaxf(tf, 0.f), 1.f);
-        const float d0 = w0 - tf * f0, d1 = w1 - tf * f1, d2 = w2 - tf * f2;
-        if (d0 * d0 + d1 * d1 + d2 * d2 > thr) continue;
-
-        // exact path
-        const double vx = (double)(b0[0] + ix) + 0.5, vy = (double)(b0[1] + iy) + 0.5, vz = (double)(b0[2] + iz) + 0.5;
-        const double u0 = vx - e.p2[0], u1 = vy - e.p2[1], u2 = vz - e.p2[2];
-        const double t = ((u0 * s0 + u1 * s1) + u2 * s2) / ss;
-        const double q0 = vx - e.p1[0], q1 = vy - e.p1[1], q2 = vz - e.p1[2];
-        const double dcap = fmin(sqrt((q0 * q0 + q1 * q1) + q2 * q2), sqrt((u0 * u0 + u1 * u1) + u2 * u2));
-        double I = 1.0 - ((dcap - rr) / SQRT3);
-        if (t > 0.0 && t < 1.0) {
-            const double e0 = vx - (e.p2[0] + t * s0), e1 = vy - (e.p2[1] + t * s1), e2 = vz - (e.p2[2] + t * s2);
-            const double dl = sqrt((e0 * e0 + e1 * e1) + e2 * e2);
-            const double I1 = 1.0 - ((dl - rr) / SQRT3);
-            I = fmax(I, I1);
+        const float w1 = (float)iy - a1, w2 = (float)iz - a2;
+        const float dot12 = w1 * f1 + w2 * f2;
+        const double vy = (double)(b0[1] + iy) + 0.5, vz = (double)(b0[2] + iz) + 0.5;
+        uint32_t* arow = acc + ((b0[0] - t0[0]) * T[1] + (b0[1] + iy - t0[1])) * T[2] + (b0[2] + iz - t0[2]);
+        const int xstride = T[1] * T[2];
+        for (int ix = 0; ix < n[0]; ++ix) {
+            const float w0 = (float)ix - a0;
+            float tf = fmaf(w0, f0, dot12) * finv;
+            tf = fminf(fmaxf(tf, 0.f), 1.f);
+            const float d0 = fmaf(-tf, f0, w0), d1 = fmaf(-tf, f1, w1), d2 = fmaf(-tf, f2, w2);
+            if (fmaf(d0, d0, fmaf(d1, d1, d2 * d2)) > thr) continue;
+            // fast float64 evaluation
+            const double vx = (double)(b0[0] + ix) + 0.5;
+            const double u0 = vx - e.p2[0], u1 = vy - e.p2[1], u2 = vz - e.p2[2];
+            const double dot = fma(u2, s2, fma(u1, s1, u0 * s0));
+            uint32_t q;
+            if (fabs(dot) < tguard || fabs(dot - ss) < tguard) {
+                q = exact_voxel_q(e, vx, vy, vz);
+            } else {
+                double dd;
+                if (dot > 0.0 && dot < ss) {
+                    const double t = dot * inv_ss;
+                    const double e0 = fma(-t, s0, u0), e1 = fma(-t, s1, u1), e2 = fma(-t, s2, u2);
+                    dd = fma(e2, e2, fma(e1, e1, e0 * e0));
+                } else {
+                    const double q0 = vx - e.p1[0], q1 = vy - e.p1[1], q2 = vz - e.p1[2];
+                    dd = fmin(fma(u2, u2, fma(u1, u1, u0 * u0)), fma(q2, q2, fma(q1, q1, q0 * q0)));
+                }
+                const double val = 255.0 * fma(-sqrt(dd), INV_SQRT3, c0);
+                if (val < -1e-7) continue;
+                const double fl = floor(val);
+                const double fr = val - fl;
+                if (fr < 1e-7 || fr > 1.0 - 1e-7 || !(val == val)) q = exact_voxel_q(e, vx, vy, vz);
+                else q = val >= 255.0 ? 255u : (uint32_t)fl;
+            }
+            if (q) atomicMax(arow + ix * xstride, q);
         }
-        if (!(I > 0.0)) continue;
-        const double cl = I < 1.0 ? I : 1.0;
-        const uint32_t q = (uint32_t)(255.0 * cl);
-        if (q == 0) continue;
-        const int lx = b0[0] + ix - t0[0], ly = b0[1] + iy - t0[1], lz = b0[2] + iz - t0[2];
-        atomicMax(&acc[(lx * T[1] + ly) * T[2] + lz], q);
     }
 }
 
