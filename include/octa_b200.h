@@ -122,6 +122,7 @@ typedef struct OctaGrowConfig {
 typedef struct OctaGrowStats {
     int64_t n_art_nodes, n_ven_nodes, n_oxy_left, n_co2_left, py_draws;
     int64_t sum_A, sum_M, sum_P, sum_S;   /* byte-accounting counters of SURVEY.md 8(d) */
+    int64_t commit_cycles[4];        /* SM cycles of k_commit's prologue / sequential replay / refresh / active-list phases */
     int32_t err;                     /* 0 ok; 1 node capacity, 2 sink capacity, 3 rng buffer, 4 recheck queue, 5 set table, 1x eig */
     int32_t n_iters;
 } OctaGrowStats;
@@ -133,6 +134,14 @@ typedef struct OctaGrowStats {
 int octa_grow_batch_host(const OctaGrowConfig* cfg, const uint64_t* seeds, int n_graphs, double* edges7_out,
                          int64_t cap_edges_per_graph, int64_t* n_art_edges, int64_t* n_ven_edges,
                          OctaGrowStats* stats, int32_t* trace, double* device_ms);
+
+/* Persistent variant: device state for up to max_graphs samples of one configuration is allocated once
+ * (octa_grow_create) and reused by every octa_grow_run (same arguments as octa_grow_batch_host, n_graphs <= max_graphs);
+ * the context belongs to the CUDA device that was current at creation and to one host thread at a time. */
+int octa_grow_create(const OctaGrowConfig* cfg, int max_graphs, void** handle);
+int octa_grow_run(void* handle, const uint64_t* seeds, int n_graphs, double* edges7_out, int64_t cap_edges_per_graph,
+                  int64_t* n_art_edges, int64_t* n_ven_edges, OctaGrowStats* stats, int32_t* trace, double* device_ms);
+void octa_grow_destroy(void* handle);
 
 /* ------------------------------------------------------------------------------------------------
  * Graph CSV -- replaces the writer of generate_vessel_graph.py:59-66 (csv.writer rows of

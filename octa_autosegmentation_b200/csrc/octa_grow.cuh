@@ -19,6 +19,7 @@ struct IterP {
     double eps_n_eff, eps_s, eps_k, delta[2], gamma[2], phi, omega, kappa, d, r, rotation_radius;
     double faz_cx, faz_cy, param_scale, shape[3];
     int N, t, first_mode, mode_idx, iter;
+    double kap_tab[9];   // kappa of the node's creation mode (arterial_tree.py:32); [8] = 4, the add_node default of the stumps
 };
 
 enum PropType : int { P_NONE = 0, P_LEAF_ELONG = 1, P_LEAF_DRAW = 2, P_LEAF_BIF = 3, P_INTER_DRAW = 4, P_INTER_EMPTY = 5 };
@@ -30,6 +31,19 @@ struct Proposal {
     double r1_used;    // inter-node: child radius the evaluation was made with
     double p[3];       // elongation / sprout position
     double b1[3], b2[3];  // bifurcation children
+};
+
+// packed per-node record of everything the sequential replay touches (one 32-byte load per tree step)
+struct __align__(32) TreeRec {
+    double R;                  // in-loop (steering) radius, mirrors nrad
+    int par, c0, c1;
+    int slot, slot_call;       // dict rank of this node in grow call `slot_call`
+    unsigned char nch, kmode, dirty, pad;
+};
+
+struct __align__(16) ActDec {  // decision record of one acting dict entry
+    int e, nd, type, cond;
+    double ratio5, pad;
 };
 
 struct GrowShape {
@@ -70,6 +84,9 @@ struct GrowDev {
     int *dict_node, *n_dict, *list_off, *list, *sc_idx;
     double *sc_ang;
     Proposal* prop;
+    ActDec* adec;
+    int4* newl;
+    TreeRec* rec[2];
     int *alist, *n_alist;
     int *hitj, *hl, *ta, *seq;
     unsigned char* veto;

@@ -164,6 +164,8 @@ void build_schedule(const OctaGrowConfig& c, std::vector<IterP>* out) {
             P.param_scale = ps;
             for (int k = 0; k < 3; ++k) P.shape[k] = c.size[k];
             P.N = N; P.t = t; P.first_mode = m.first_mode; P.mode_idx = mi; P.iter = iter++;
+            for (int q = 0; q < 8; ++q) P.kap_tab[q] = q < c.n_modes ? c.modes[q].kappa : 4.0;
+            P.kap_tab[8] = 4.0;
             out->push_back(P);
             sigma_t = sigma_t + delta_sigma;
             eps_k = orig[0] / sigma_t; eps_n = orig[1] / sigma_t; eps_s = orig[2] / sigma_t;
@@ -216,28 +218,22 @@ void carve(Carver& c, const GrowShape& S, GrowDev* D) {
     D->first = c.take<int>(GN); D->cnt = c.take<int>(GN); D->slot = c.take<int>(GN); D->slot_call = c.take<int>(GN); D->cur = c.take<int>(GN); D->rtag = c.take<int>(GN);
     D->dict_node = c.take<int>(GN); D->n_dict = c.take<int>(G); D->list_off = c.take<int>(G * (S.capN + 1));
     D->list = c.take<int>(GS); D->sc_idx = c.take<int>(GS); D->sc_ang = c.take<double>(GS);
-    D->prop = c.take<Proposal>(GN); D->alist = c.take<int>(GN); D->n_alist = c.take<int>(G);
+    D->prop = c.take<Proposal>(GN); D->adec = c.take<ActDec>(GN); D->newl = c.take<int4>(GN);
+    D->rec[0] = c.take<TreeRec>(GN); D->rec[1] = c.take<TreeRec>(GN); D->alist = c.take<int>(GN); D->n_alist = c.take<int>(G);
     D->hitj = c.take<int>(GS); D->hl = c.take<int>(GS); D->ta = c.take<int>(GS); D->seq = c.take<int>(GS);
     D->veto = c.take<unsigned char>(GS);
     D->set_hash = c.take<long long>(G * 2 * SET_TBL); D->set_key = c.take<int>(G * 2 * SET_TBL);
     D->err = c.take<int>(G); D->trace = c.take<int>(G * 4096 * 4); D->counters = c.take<long long>(G * 8);
 }
 
-// exact radii + export of one graph (host)
-struct GraphExport {
-    std::vector<double> pos[2];
-    std::vector<int> parent[2];
-    std::vector<unsigned char> meta[2];
-};
-
-void finalize_forest(const OctaGrowConfig& c, const std::vector<double>& pos, const std::vector<int>& parent,
-                     const std::vector<unsigned char>& meta, double* out7, int64_t cap, int64_t* n_out) {
-    const int n = (int)parent.size();
+// exact radii + export of one forest (host).  Inputs are strided views into the pinned D2H staging buffers.
+void finalize_forest(const OctaGrowConfig& c, int n, const double* px, const double* py, const double* pz,
+                     const int* parent, const unsigned char* meta, double* out7, int64_t cap, int64_t* n_out) {
     const double r = c.r / c.param_scale;
     std::vector<double> rad(n, r), kap(n);
     std::vector<int> c0(n, -1), c1(n, -1);
     std::vector<unsigned char> nch(n, 0);
-    for (int i = 0; i < n; ++i) { const int m = meta[i] >> 1; kap[i] = (m >= 0 && m < c.n_modes && meta[i] != 0xff) ? c.modes[m].kappa : 4.0; }
+    for (int i = 0; i < n; ++i) { const int m = meta[i] >> 1; kap[i] = (meta[i] != 0xff && m < c.n_modes) ? c.modes[m].kappa : 4.0; }
     // replay in creation order (arterial_tree.py:174-184 with libm pow, exactly CPython's float.__pow__)
     for (int i = 0; i < n; ++i) {
         const int p = parent[i];
@@ -270,8 +266,8 @@ void finalize_forest(const OctaGrowConfig& c, const std::vector<double>& pos, co
                     if (k < cap) {
                         double* o = out7 + 7 * k;
                         const int pa = parent[id];
-                        o[0] = pos[3 * id]; o[1] = pos[3 * id + 1]; o[2] = pos[3 * id + 2];
-                        o[3] = pos[3 * pa]; o[4] = pos[3 * pa + 1]; o[5] = pos[3 * pa + 2];
+                        o[0] = px[id]; o[1] = py[id]; o[2] = pz[id];
+                        o[3] = px[pa]; o[4] = py[pa]; o[5] = pz[pa];
                         o[6] = rad[id];
                     }
                     ++k;
@@ -285,152 +281,251 @@ void finalize_forest(const OctaGrowConfig& c, const std::vector<double>& pos, co
     *n_out = k;
 }
 
+// persistent growth context: device state for up to G graphs of one configuration
+struct GrowCtx {
+    OctaGrowConfig cfg;
+    GrowShape S;
+    GrowDev D;
+    char* dbase = nullptr;
+    size_t dbytes = 0;
+    std::vector<IterP> sched;
+    int n_sm = 148;
+    char* stage = nullptr;      // pinned host staging
+    size_t stage_bytes = 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~GrowCtx() {
+        if (dbase) cudaFree(dbase);
+        if (stage) cudaFreeHost(stage);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    }
+    int ensure_stage(size_t bytes) {
+        if (bytes <= stage_bytes) return OCTA_OK;
+        if (stage) cudaFreeHost(stage);
+        stage = nullptr; stage_bytes = 0;
+        OCTA_CUDA_CHECK(cudaMallocHost(&stage, bytes));
+        stage_bytes = bytes;
+        return OCTA_OK;
+    }
+};
+
+int check_config(const OctaGrowConfig* cfg) {
+    OCTA_ARG_CHECK(cfg, "config is null");
+    OCTA_ARG_CHECK(cfg->n_modes >= 1 && cfg->n_modes <= 8, "n_modes must be in [1, 8]");
+    OCTA_ARG_CHECK(cfg->n_trees >= 1 && cfg->n_trees <= 64, "N_trees must be in [1, 64]");
+    OCTA_ARG_CHECK(cfg->param_scale > 0, "param_scale must be positive");
+    return OCTA_OK;
+}
+
 }  // namespace
 }  // namespace octa
 
 using namespace octa;
 
-extern "C" int octa_grow_batch_host(const OctaGrowConfig* cfg, const uint64_t* seeds, int n_graphs, double* edges7_out,
-                                    int64_t cap_edges, int64_t* n_art_edges, int64_t* n_ven_edges,
-                                    OctaGrowStats* stats, int32_t* trace, double* device_ms) {
-    OCTA_ARG_CHECK(cfg && seeds && n_graphs > 0 && n_graphs <= 4096, "bad arguments");
-    OCTA_ARG_CHECK(cfg->n_modes >= 1 && cfg->n_modes <= 8, "n_modes must be in [1, 8]");
-    OCTA_ARG_CHECK(cfg->n_trees >= 1 && cfg->n_trees <= 64, "N_trees must be in [1, 64]");
-    OCTA_ARG_CHECK(cfg->param_scale > 0, "param_scale must be positive");
-    OCTA_ARG_CHECK(edges7_out && cap_edges > 0 && n_art_edges && n_ven_edges, "output buffers missing");
-    for (int i = 0; i < n_graphs; ++i) OCTA_ARG_CHECK(seeds[i] <= 0xffffffffull, "seeds must fit 32 bits (np.random.seed)");
-    if (octa_device_count() <= 0) { set_error("octa_grow_batch_host: no CUDA device (there is no CPU fallback)"); return OCTA_E_CUDA; }
-    std::vector<IterP> sched;
-    build_schedule(*cfg, &sched);
-    OCTA_ARG_CHECK(sched.size() <= 4096, "too many iterations (max 4096)");
+extern "C" int octa_grow_create(const OctaGrowConfig* cfg, int max_graphs, void** handle) {
+    int rc = check_config(cfg);
+    if (rc) return rc;
+    OCTA_ARG_CHECK(handle && max_graphs > 0 && max_graphs <= 4096, "bad arguments");
+    if (octa_device_count() <= 0) { set_error("octa_grow_create: no CUDA device (there is no CPU fallback)"); return OCTA_E_CUDA; }
+    GrowCtx* ctx = new GrowCtx();
+    ctx->cfg = *cfg;
+    build_schedule(*cfg, &ctx->sched);
+    if (ctx->sched.size() > 4096) { delete ctx; set_error("too many iterations (max 4096)"); return OCTA_E_ARG; }
     int Nmax = 1;
-    for (const IterP& p : sched) Nmax = std::max(Nmax, p.N);
-    GrowShape S;
-    S.G = n_graphs;
-    S.Nmax = Nmax;
     long total_try = 0;
-    for (const IterP& p : sched) total_try += p.N;
+    for (const IterP& p : ctx->sched) { Nmax = std::max(Nmax, p.N); total_try += p.N; }
+    GrowShape& S = ctx->S;
+    S.G = max_graphs;
+    S.Nmax = Nmax;
     S.capN = cfg->cap_nodes > 0 ? cfg->cap_nodes : (int)std::min<long>(1 << 20, std::max<long>(4096, align_up((size_t)(total_try / 16 + 4096), 1024)));
     S.capS = cfg->cap_sinks > 0 ? cfg->cap_sinks : (int)std::min<long>(1 << 20, std::max<long>(4096, align_up((size_t)(total_try / 12 + 4096), 1024)));
     S.pycap = 2 * S.capN + 4 * 624;
-    // host initialisation
+    if (2 * cfg->n_trees > S.capN) { delete ctx; set_error("cap_nodes too small"); return OCTA_E_ARG; }
+    Carver sizing(nullptr);
+    carve(sizing, S, &ctx->D);
+    cudaError_t ce = cudaMalloc(&ctx->dbase, sizing.off);
+    if (ce != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", sizing.off, cudaGetErrorString(ce)); delete ctx; return OCTA_E_NOMEM; }
+    ctx->dbytes = sizing.off;
+    Carver real(ctx->dbase);
+    carve(real, S, &ctx->D);
+    if (cudaMemset(ctx->dbase, 0, ctx->dbytes) != cudaSuccess ||
+        cudaMemset(ctx->D.first, 0x7f, sizeof(int) * (size_t)S.G * S.capN) != cudaSuccess) {
+        set_error("cudaMemset failed"); delete ctx; return OCTA_E_CUDA;
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, dev);
+    cudaEventCreate(&ctx->e0);
+    cudaEventCreate(&ctx->e1);
+    *handle = ctx;
+    return OCTA_OK;
+}
+
+extern "C" void octa_grow_destroy(void* handle) { delete (GrowCtx*)handle; }
+
+extern "C" int octa_grow_run(void* handle, const uint64_t* seeds, int n_graphs, double* edges7_out, int64_t cap_edges,
+                             int64_t* n_art_edges, int64_t* n_ven_edges, OctaGrowStats* stats, int32_t* trace,
+                             double* device_ms) {
+    GrowCtx* ctx = (GrowCtx*)handle;
+    OCTA_ARG_CHECK(ctx && seeds && n_graphs > 0 && n_graphs <= ctx->S.G, "bad arguments (n_graphs must not exceed the context size)");
+    OCTA_ARG_CHECK(edges7_out && cap_edges > 0 && n_art_edges && n_ven_edges, "output buffers missing");
+    for (int i = 0; i < n_graphs; ++i) OCTA_ARG_CHECK(seeds[i] <= 0xffffffffull, "seeds must fit 32 bits (np.random.seed)");
+    const OctaGrowConfig& cfg = ctx->cfg;
+    GrowShape S = ctx->S;
+    S.G = n_graphs;                                   // slabs are graph-major: a smaller batch uses the leading slabs
+    GrowDev D = ctx->D;
+    cudaStream_t st = nullptr;
+    // ---- host initialisation (Greenhouse.__init__ + Forest x2), staged and uploaded with strided copies
     std::vector<HostGraphInit> init(n_graphs);
     for (int g = 0; g < n_graphs; ++g) {
-        int rc = init_graph(*cfg, seeds[g], &init[g]);
+        int rc = init_graph(cfg, seeds[g], &init[g]);
         if (rc) return rc;
-        if ((int)init[g].parent[0].size() > S.capN) { set_error("cap_nodes too small"); return OCTA_E_ARG; }
     }
-    GrowDev D;
-    Carver sizing(nullptr);
-    carve(sizing, S, &D);
-    char* dbase = nullptr;
-    cudaError_t ce = cudaMalloc(&dbase, sizing.off);
-    if (ce != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", sizing.off, cudaGetErrorString(ce)); return OCTA_E_NOMEM; }
-    struct Guard { char* p; ~Guard() { cudaFree(p); } } guard{dbase};
-    Carver real(dbase);
-    carve(real, S, &D);
-    cudaStream_t st = nullptr;
-    OCTA_CUDA_CHECK(cudaMemsetAsync(dbase, 0, sizing.off, st));
-    OCTA_CUDA_CHECK(cudaMemsetAsync(D.first, 0x7f, sizeof(int) * (size_t)S.G * S.capN, st));
-    const double r0 = cfg->r / cfg->param_scale;
+    const int n0 = 2 * cfg.n_trees;
+    const double r0 = cfg.r / cfg.param_scale;
+    const size_t G = n_graphs;
     {
-        std::vector<double> hx, hy, hz, hr, hk;
-        std::vector<int> hp, hc0, hact;
-        std::vector<unsigned char> hn, hm;
+        // staging layout: per array a dense [G][n0] block
+        size_t off = 0;
+        auto blk = [&](size_t elem) { size_t o = off; off = align_up(off + elem * G * n0, 256); return o; };
+        size_t o_x[2], o_y[2], o_z[2], o_r[2], o_k[2], o_p[2], o_c0[2], o_c1[2], o_act[2], o_n[2], o_m[2], o_rec[2];
+        for (int f = 0; f < 2; ++f) {
+            o_x[f] = blk(8); o_y[f] = blk(8); o_z[f] = blk(8); o_r[f] = blk(8); o_k[f] = blk(8);
+            o_p[f] = blk(4); o_c0[f] = blk(4); o_c1[f] = blk(4); o_act[f] = blk(4); o_n[f] = blk(1); o_m[f] = blk(1);
+            o_rec[f] = blk(sizeof(TreeRec));
+        }
+        const size_t o_mt_np = off; off = align_up(off + sizeof(MTState) * G, 256);
+        const size_t o_mt_py = off; off = align_up(off + sizeof(MTState) * G, 256);
+        const size_t o_faz = off; off = align_up(off + 8 * G, 256);
+        const size_t o_nv = off; off = align_up(off + 4 * G, 256);
+        const size_t o_cnt = off; off = align_up(off + 4 * G, 256);
+        const size_t o_valid = off; off = align_up(off + (size_t)MAX_VALID * 2 * G, 256);
+        int rc = ctx->ensure_stage(off);
+        if (rc) return rc;
+        char* sg = ctx->stage;
         for (int g = 0; g < n_graphs; ++g) {
             const HostGraphInit& h = init[g];
-            const size_t nb = (size_t)g * S.capN;
             for (int f = 0; f < 2; ++f) {
-                const int n = (int)h.parent[f].size();
-                hx.assign(n, 0); hy.assign(n, 0); hz.assign(n, 0); hr.assign(n, r0); hk.assign(n, 4.0);
-                hp.assign(n, -1); hc0.assign(n, -1); hact.assign(n, 0); hn.assign(n, 0); hm.assign(n, 0xff);
-                for (int i = 0; i < n; ++i) {
+                double* hx = (double*)(sg + o_x[f]) + (size_t)g * n0; double* hy = (double*)(sg + o_y[f]) + (size_t)g * n0;
+                double* hz = (double*)(sg + o_z[f]) + (size_t)g * n0; double* hr = (double*)(sg + o_r[f]) + (size_t)g * n0;
+                double* hk = (double*)(sg + o_k[f]) + (size_t)g * n0;
+                int* hp = (int*)(sg + o_p[f]) + (size_t)g * n0; int* hc0 = (int*)(sg + o_c0[f]) + (size_t)g * n0;
+                int* hc1 = (int*)(sg + o_c1[f]) + (size_t)g * n0; int* hact = (int*)(sg + o_act[f]) + (size_t)g * n0;
+                unsigned char* hn = (unsigned char*)(sg + o_n[f]) + (size_t)g * n0; unsigned char* hm = (unsigned char*)(sg + o_m[f]) + (size_t)g * n0;
+                TreeRec* hrec = (TreeRec*)(sg + o_rec[f]) + (size_t)g * n0;
+                for (int i = 0; i < n0; ++i) { hc0[i] = -1; hc1[i] = -1; hn[i] = 0; }
+                for (int i = 0; i < n0; ++i) {
                     hx[i] = h.pos[f][3 * i]; hy[i] = h.pos[f][3 * i + 1]; hz[i] = h.pos[f][3 * i + 2];
-                    hp[i] = h.parent[f][i];
+                    hr[i] = r0; hk[i] = 4.0; hp[i] = h.parent[f][i]; hact[i] = i; hm[i] = 0xff;
                     if (hp[i] >= 0) { hc0[hp[i]] = i; hn[hp[i]] = 1; }
-                    hact[i] = i;
                 }
-                auto up = [&](void* dst, const void* src, size_t bytes) { return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st); };
-                OCTA_CUDA_CHECK(up(D.nx[f] + nb, hx.data(), 8 * n)); OCTA_CUDA_CHECK(up(D.ny[f] + nb, hy.data(), 8 * n));
-                OCTA_CUDA_CHECK(up(D.nz[f] + nb, hz.data(), 8 * n)); OCTA_CUDA_CHECK(up(D.nrad[f] + nb, hr.data(), 8 * n));
-                OCTA_CUDA_CHECK(up(D.nkap[f] + nb, hk.data(), 8 * n)); OCTA_CUDA_CHECK(up(D.npar[f] + nb, hp.data(), 4 * n));
-                OCTA_CUDA_CHECK(up(D.nch0[f] + nb, hc0.data(), 4 * n)); OCTA_CUDA_CHECK(up(D.nnch[f] + nb, hn.data(), n));
-                OCTA_CUDA_CHECK(up(D.nmeta[f] + nb, hm.data(), n));
-                OCTA_CUDA_CHECK(up(D.act[f] + nb, hact.data(), 4 * n));
-                OCTA_CUDA_CHECK(up(D.ax[f] + nb, hx.data(), 8 * n)); OCTA_CUDA_CHECK(up(D.ay[f] + nb, hy.data(), 8 * n));
-                OCTA_CUDA_CHECK(up(D.az[f] + nb, hz.data(), 8 * n));
-                OCTA_CUDA_CHECK(up(D.n_nodes[f] + g, &n, 4)); OCTA_CUDA_CHECK(up(D.n_act[f] + g, &n, 4));
-                OCTA_CUDA_CHECK(up(D.n_prev[f] + g, &n, 4));
-                OCTA_CUDA_CHECK(cudaStreamSynchronize(st));   // staging vectors are reused
+                for (int i = 0; i < n0; ++i) {
+                    TreeRec r;
+                    r.R = r0; r.par = hp[i]; r.c0 = hc0[i]; r.c1 = -1; r.slot = 0; r.slot_call = 0;
+                    r.nch = hn[i]; r.kmode = 8; r.dirty = 0; r.pad = 0;
+                    hrec[i] = r;
+                }
             }
-            OCTA_CUDA_CHECK(cudaMemcpyAsync(D.np_mt + g, &h.np_mt, sizeof(MTState), cudaMemcpyHostToDevice, st));
-            OCTA_CUDA_CHECK(cudaMemcpyAsync(D.py_mt + g, &h.py_mt, sizeof(MTState), cudaMemcpyHostToDevice, st));
-            OCTA_CUDA_CHECK(cudaMemcpyAsync(D.faz_radius + g, &h.faz_radius, 8, cudaMemcpyHostToDevice, st));
-            OCTA_CUDA_CHECK(cudaMemcpyAsync(D.n_valid + g, &h.n_valid, 4, cudaMemcpyHostToDevice, st));
-            OCTA_CUDA_CHECK(cudaMemcpyAsync(D.valid_ij + (size_t)g * MAX_VALID * 2, h.valid_ij.data(), h.valid_ij.size(),
-                                            cudaMemcpyHostToDevice, st));
+            ((MTState*)(sg + o_mt_np))[g] = h.np_mt;
+            ((MTState*)(sg + o_mt_py))[g] = h.py_mt;
+            ((double*)(sg + o_faz))[g] = h.faz_radius;
+            ((int*)(sg + o_nv))[g] = h.n_valid;
+            ((int*)(sg + o_cnt))[g] = n0;
+            memset(sg + o_valid + (size_t)g * MAX_VALID * 2, 0, (size_t)MAX_VALID * 2);
+            memcpy(sg + o_valid + (size_t)g * MAX_VALID * 2, h.valid_ij.data(), h.valid_ij.size());
         }
-        OCTA_CUDA_CHECK(cudaStreamSynchronize(st));
+        auto up2d = [&](void* dst, size_t dpitch, const void* src, size_t elem) {
+            return cudaMemcpy2DAsync(dst, dpitch, src, elem * n0, elem * n0, G, cudaMemcpyHostToDevice, st);
+        };
+        for (int f = 0; f < 2; ++f) {
+            const size_t cn = S.capN;
+            OCTA_CUDA_CHECK(up2d(D.nx[f], 8 * cn, sg + o_x[f], 8)); OCTA_CUDA_CHECK(up2d(D.ny[f], 8 * cn, sg + o_y[f], 8));
+            OCTA_CUDA_CHECK(up2d(D.nz[f], 8 * cn, sg + o_z[f], 8)); OCTA_CUDA_CHECK(up2d(D.nrad[f], 8 * cn, sg + o_r[f], 8));
+            OCTA_CUDA_CHECK(up2d(D.nkap[f], 8 * cn, sg + o_k[f], 8)); OCTA_CUDA_CHECK(up2d(D.npar[f], 4 * cn, sg + o_p[f], 4));
+            OCTA_CUDA_CHECK(up2d(D.nch0[f], 4 * cn, sg + o_c0[f], 4)); OCTA_CUDA_CHECK(up2d(D.nch1[f], 4 * cn, sg + o_c1[f], 4));
+            OCTA_CUDA_CHECK(up2d(D.act[f], 4 * cn, sg + o_act[f], 4));
+            OCTA_CUDA_CHECK(up2d(D.nnch[f], cn, sg + o_n[f], 1)); OCTA_CUDA_CHECK(up2d(D.nmeta[f], cn, sg + o_m[f], 1));
+            OCTA_CUDA_CHECK(up2d(D.ax[f], 8 * cn, sg + o_x[f], 8)); OCTA_CUDA_CHECK(up2d(D.ay[f], 8 * cn, sg + o_y[f], 8));
+            OCTA_CUDA_CHECK(up2d(D.az[f], 8 * cn, sg + o_z[f], 8));
+            OCTA_CUDA_CHECK(up2d(D.rec[f], sizeof(TreeRec) * cn, sg + o_rec[f], sizeof(TreeRec)));
+            OCTA_CUDA_CHECK(cudaMemsetAsync(D.deact[f], 0, G * cn, st));
+            OCTA_CUDA_CHECK(cudaMemcpyAsync(D.n_nodes[f], sg + o_cnt, 4 * G, cudaMemcpyHostToDevice, st));
+            OCTA_CUDA_CHECK(cudaMemcpyAsync(D.n_act[f], sg + o_cnt, 4 * G, cudaMemcpyHostToDevice, st));
+            OCTA_CUDA_CHECK(cudaMemcpyAsync(D.n_prev[f], sg + o_cnt, 4 * G, cudaMemcpyHostToDevice, st));
+            OCTA_CUDA_CHECK(cudaMemsetAsync(D.n_s[f], 0, 4 * G, st));
+        }
+        OCTA_CUDA_CHECK(cudaMemcpyAsync(D.np_mt, sg + o_mt_np, sizeof(MTState) * G, cudaMemcpyHostToDevice, st));
+        OCTA_CUDA_CHECK(cudaMemcpyAsync(D.py_mt, sg + o_mt_py, sizeof(MTState) * G, cudaMemcpyHostToDevice, st));
+        OCTA_CUDA_CHECK(cudaMemcpyAsync(D.faz_radius, sg + o_faz, 8 * G, cudaMemcpyHostToDevice, st));
+        OCTA_CUDA_CHECK(cudaMemcpyAsync(D.n_valid, sg + o_nv, 4 * G, cudaMemcpyHostToDevice, st));
+        OCTA_CUDA_CHECK(cudaMemcpyAsync(D.valid_ij, sg + o_valid, (size_t)MAX_VALID * 2 * G, cudaMemcpyHostToDevice, st));
+        OCTA_CUDA_CHECK(cudaMemsetAsync(D.py_n, 0, 4 * G, st)); OCTA_CUDA_CHECK(cudaMemsetAsync(D.py_pos, 0, 4 * G, st));
+        OCTA_CUDA_CHECK(cudaMemsetAsync(D.py_draws, 0, 8 * G, st)); OCTA_CUDA_CHECK(cudaMemsetAsync(D.counters, 0, 64 * G, st));
+        OCTA_CUDA_CHECK(cudaMemsetAsync(D.err, 0, 4 * G, st));
+        OCTA_CUDA_CHECK(cudaMemsetAsync(D.rtag, 0, 4 * G * S.capN, st));
+        if (trace) OCTA_CUDA_CHECK(cudaMemsetAsync(D.trace, 0, sizeof(int) * G * 4096 * 4, st));
+        OCTA_CUDA_CHECK(cudaStreamSynchronize(st));      // the staging buffer is reused for the read-back
     }
     if (!trace) D.trace = nullptr;
-    int dev = 0, n_sm = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaEvent_t e0, e1;
-    OCTA_CUDA_CHECK(cudaEventCreate(&e0));
-    OCTA_CUDA_CHECK(cudaEventCreate(&e1));
-    OCTA_CUDA_CHECK(cudaEventRecord(e0, st));
-    for (const IterP& P : sched) launch_iteration(D, S, P, n_sm, st);
-    OCTA_CUDA_CHECK(cudaEventRecord(e1, st));
-    OCTA_CUDA_CHECK(cudaStreamSynchronize(st));
-    OCTA_CUDA_CHECK(cudaGetLastError());
-    float ms = 0;
-    cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    if (device_ms) *device_ms = ms;
-    // read back
+    OCTA_CUDA_CHECK(cudaEventRecord(ctx->e0, st));
+    for (const IterP& P : ctx->sched) launch_iteration(D, S, P, ctx->n_sm, st);
+    OCTA_CUDA_CHECK(cudaEventRecord(ctx->e1, st));
+    // ---- read back: counts first, then strided copies of the live prefix of every node array
     std::vector<int> err(n_graphs), nn[2], ns[2];
     std::vector<long long> draws(n_graphs), counters((size_t)n_graphs * 8);
     for (int f = 0; f < 2; ++f) {
         nn[f].resize(n_graphs); ns[f].resize(n_graphs);
-        OCTA_CUDA_CHECK(cudaMemcpy(nn[f].data(), D.n_nodes[f], 4 * n_graphs, cudaMemcpyDeviceToHost));
-        OCTA_CUDA_CHECK(cudaMemcpy(ns[f].data(), D.n_s[f], 4 * n_graphs, cudaMemcpyDeviceToHost));
+        OCTA_CUDA_CHECK(cudaMemcpyAsync(nn[f].data(), D.n_nodes[f], 4 * G, cudaMemcpyDeviceToHost, st));
+        OCTA_CUDA_CHECK(cudaMemcpyAsync(ns[f].data(), D.n_s[f], 4 * G, cudaMemcpyDeviceToHost, st));
     }
-    OCTA_CUDA_CHECK(cudaMemcpy(err.data(), D.err, 4 * n_graphs, cudaMemcpyDeviceToHost));
-    OCTA_CUDA_CHECK(cudaMemcpy(draws.data(), D.py_draws, 8 * n_graphs, cudaMemcpyDeviceToHost));
-    OCTA_CUDA_CHECK(cudaMemcpy(counters.data(), D.counters, 8 * 8 * n_graphs, cudaMemcpyDeviceToHost));
-    if (trace) OCTA_CUDA_CHECK(cudaMemcpy(trace, D.trace, sizeof(int) * (size_t)n_graphs * 4096 * 4, cudaMemcpyDeviceToHost));
-    std::vector<GraphExport> ex(n_graphs);
-    std::vector<double> tmp;
-    for (int g = 0; g < n_graphs; ++g) {
-        const size_t nb = (size_t)g * S.capN;
-        for (int f = 0; f < 2; ++f) {
-            const int n = nn[f][g];
-            ex[g].pos[f].resize(3 * (size_t)n); ex[g].parent[f].resize(n); ex[g].meta[f].resize(n);
-            tmp.resize(3 * (size_t)n);
-            OCTA_CUDA_CHECK(cudaMemcpy(tmp.data(), D.nx[f] + nb, 8 * n, cudaMemcpyDeviceToHost));
-            OCTA_CUDA_CHECK(cudaMemcpy(tmp.data() + n, D.ny[f] + nb, 8 * n, cudaMemcpyDeviceToHost));
-            OCTA_CUDA_CHECK(cudaMemcpy(tmp.data() + 2 * (size_t)n, D.nz[f] + nb, 8 * n, cudaMemcpyDeviceToHost));
-            for (int i = 0; i < n; ++i) { ex[g].pos[f][3 * i] = tmp[i]; ex[g].pos[f][3 * i + 1] = tmp[n + i]; ex[g].pos[f][3 * i + 2] = tmp[2 * (size_t)n + i]; }
-            OCTA_CUDA_CHECK(cudaMemcpy(ex[g].parent[f].data(), D.npar[f] + nb, 4 * n, cudaMemcpyDeviceToHost));
-            OCTA_CUDA_CHECK(cudaMemcpy(ex[g].meta[f].data(), D.nmeta[f] + nb, n, cudaMemcpyDeviceToHost));
-        }
+    OCTA_CUDA_CHECK(cudaMemcpyAsync(err.data(), D.err, 4 * G, cudaMemcpyDeviceToHost, st));
+    OCTA_CUDA_CHECK(cudaMemcpyAsync(draws.data(), D.py_draws, 8 * G, cudaMemcpyDeviceToHost, st));
+    OCTA_CUDA_CHECK(cudaMemcpyAsync(counters.data(), D.counters, 64 * G, cudaMemcpyDeviceToHost, st));
+    OCTA_CUDA_CHECK(cudaStreamSynchronize(st));
+    OCTA_CUDA_CHECK(cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->e0, ctx->e1);
+    if (device_ms) *device_ms = ms;
+    if (trace) OCTA_CUDA_CHECK(cudaMemcpy(trace, D.trace, sizeof(int) * G * 4096 * 4, cudaMemcpyDeviceToHost));
+    size_t mx[2] = {1, 1};
+    for (int f = 0; f < 2; ++f) for (int g = 0; g < n_graphs; ++g) mx[f] = std::max<size_t>(mx[f], (size_t)nn[f][g]);
+    size_t so[2][5], off = 0;
+    for (int f = 0; f < 2; ++f) {
+        const size_t elem[5] = {8, 8, 8, 4, 1};
+        for (int a = 0; a < 5; ++a) { so[f][a] = off; off = align_up(off + elem[a] * mx[f] * G, 256); }
     }
-    // exact radii + edge export, multi-threaded over graphs
-    const OctaGrowConfig c = *cfg;
+    {
+        int rc = ctx->ensure_stage(off);
+        if (rc) return rc;
+    }
+    char* sg = ctx->stage;
+    for (int f = 0; f < 2; ++f) {
+        const size_t cn = S.capN, w = mx[f];
+        auto dn2d = [&](size_t o, const void* src, size_t elem) {
+            return cudaMemcpy2DAsync(sg + o, elem * w, src, elem * cn, elem * w, G, cudaMemcpyDeviceToHost, st);
+        };
+        OCTA_CUDA_CHECK(dn2d(so[f][0], D.nx[f], 8)); OCTA_CUDA_CHECK(dn2d(so[f][1], D.ny[f], 8)); OCTA_CUDA_CHECK(dn2d(so[f][2], D.nz[f], 8));
+        OCTA_CUDA_CHECK(dn2d(so[f][3], D.npar[f], 4)); OCTA_CUDA_CHECK(dn2d(so[f][4], D.nmeta[f], 1));
+    }
+    OCTA_CUDA_CHECK(cudaStreamSynchronize(st));
+    // ---- exact radii + edge rows, multi-threaded over graphs
     unsigned nthreads = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)n_graphs));
     std::vector<std::thread> pool;
-    for (unsigned w = 0; w < nthreads; ++w)
-        pool.emplace_back([&, w]() {
-            for (int g = (int)w; g < n_graphs; g += (int)nthreads) {
+    for (unsigned wk = 0; wk < nthreads; ++wk)
+        pool.emplace_back([&, wk]() {
+            for (int g = (int)wk; g < n_graphs; g += (int)nthreads) {
                 double* out = edges7_out + (size_t)g * cap_edges * 7;
-                int64_t na = 0, nv = 0;
-                finalize_forest(c, ex[g].pos[0], ex[g].parent[0], ex[g].meta[0], out, cap_edges, &na);
-                const int64_t used = na < cap_edges ? na : cap_edges;
-                finalize_forest(c, ex[g].pos[1], ex[g].parent[1], ex[g].meta[1], out + 7 * used, cap_edges - used, &nv);
-                n_art_edges[g] = na;
-                n_ven_edges[g] = nv;
+                int64_t cnt[2] = {0, 0};
+                int64_t used = 0;
+                for (int f = 0; f < 2; ++f) {
+                    const size_t w = mx[f];
+                    finalize_forest(cfg, nn[f][g], (const double*)(sg + so[f][0]) + g * w, (const double*)(sg + so[f][1]) + g * w,
+                                    (const double*)(sg + so[f][2]) + g * w, (const int*)(sg + so[f][3]) + g * w,
+                                    (const unsigned char*)(sg + so[f][4]) + g * w, out + 7 * used, cap_edges - used, &cnt[f]);
+                    used = std::min<int64_t>(cap_edges, used + cnt[f]);
+                }
+                n_art_edges[g] = cnt[0];
+                n_ven_edges[g] = cnt[1];
             }
         });
     for (auto& t : pool) t.join();
@@ -442,15 +537,27 @@ extern "C" int octa_grow_batch_host(const OctaGrowConfig* cfg, const uint64_t* s
             s.py_draws = draws[g];
             s.sum_A = counters[(size_t)g * 8 + 0]; s.sum_M = counters[(size_t)g * 8 + 1];
             s.sum_P = counters[(size_t)g * 8 + 2]; s.sum_S = counters[(size_t)g * 8 + 3];
-            s.err = err[g]; s.n_iters = (int)sched.size();
+            for (int q = 0; q < 4; ++q) s.commit_cycles[q] = counters[(size_t)g * 8 + 4 + q];
+            s.err = err[g]; s.n_iters = (int)ctx->sched.size();
         }
         if (err[g] && !worst) worst = err[g];
         if (n_art_edges[g] + n_ven_edges[g] > cap_edges && !worst) worst = 100;
     }
     if (worst) {
-        set_error("octa_grow_batch_host: simulation error code %d (1 node capacity, 2 sink capacity, 3 rng buffer, "
-                  "4 recheck queue, 5 set table, 12/13 eigen solver, 100 edge buffer too small)", worst);
+        set_error("octa_grow_run: simulation error code %d (1 node capacity, 2 sink capacity, 3 rng buffer, "
+                  "5 set table, 12/13 eigen solver, 100 edge buffer too small)", worst);
         return OCTA_E_STATE;
     }
     return OCTA_OK;
+}
+
+extern "C" int octa_grow_batch_host(const OctaGrowConfig* cfg, const uint64_t* seeds, int n_graphs, double* edges7_out,
+                                    int64_t cap_edges, int64_t* n_art_edges, int64_t* n_ven_edges,
+                                    OctaGrowStats* stats, int32_t* trace, double* device_ms) {
+    void* h = nullptr;
+    int rc = octa_grow_create(cfg, n_graphs, &h);
+    if (rc) return rc;
+    rc = octa_grow_run(h, seeds, n_graphs, edges7_out, cap_edges, n_art_edges, n_ven_edges, stats, trace, device_ms);
+    octa_grow_destroy(h);
+    return rc;
 }

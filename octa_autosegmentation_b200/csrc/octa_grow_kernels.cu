@@ -401,6 +401,7 @@ __global__ void __launch_bounds__(1024) k_group(GrowDev D, GrowShape S, IterP P,
     const int* asg = D.assign + sb;
     int* first = D.first + nb; int* cnt = D.cnt + nb; int* slot = D.slot + nb; int* slot_call = D.slot_call + nb; int* cur = D.cur + nb;
     int* dict = D.dict_node + nb; int* loff = D.list_off + (size_t)g * (S.capN + 1); int* lst = D.list + sb;
+    TreeRec* rec = D.rec[f] + nb;
     for (int a = tid; a < A; a += blockDim.x) {
         const int nd = asg[a];
         if (nd >= 0) { atomicMin(&first[nd], a); atomicAdd(&cnt[nd], 1); }
@@ -413,7 +414,7 @@ __global__ void __launch_bounds__(1024) k_group(GrowDev D, GrowShape S, IterP P,
         if (a < A) { nd = asg[a]; isf = (nd >= 0 && first[nd] == a); }
         int total;
         const int incl = block_scan_incl(isf, &total);
-        if (isf) { const int rk = nd_ + incl - 1; dict[rk] = nd; slot[nd] = rk; slot_call[nd] = call_id; }
+        if (isf) { const int rk = nd_ + incl - 1; dict[rk] = nd; slot[nd] = rk; slot_call[nd] = call_id; rec[nd].slot = rk; rec[nd].slot_call = call_id; }
         nd_ += total;
     }
     __syncthreads();
@@ -679,8 +680,25 @@ __global__ void __launch_bounds__(128) k_eval(GrowDev D, GrowShape S, IterP P, i
 }
 
 // ------------------------------------------------------------------------------------------
-// k_commit: one CTA per graph; thread 0 replays the dict order sequentially
+// k_commit: one CTA per graph.
+//   prologue (all threads)  compacts the dict entries that can act into 32-byte decision records;
+//   replay   (thread 0)     walks them in dict order: Python-RNG draws, branch decisions, node ids, tree links.
+//                           It touches only L1-resident decision records and the packed 32-byte tree records
+//                           (one load per step of a dirty-marking walk) -- no positions, no pow;
+//   epilogue (all threads)  writes the new nodes' SoA fields, refreshes the dirty Murray radii bottom-up
+//                           (a node is computed by whichever thread completes its last dirty child), and
+//                           updates the active list by a stable compaction.
+// Radii inside a call are LAZY (arterial_tree.py:174-184 is order-insensitive up to rounding): a branch event only
+// marks its ancestor chain dirty, stopping at the first already-dirty node, and tags later inter-node dict
+// entries whose distal radius it changes; only a tagged entry refreshes (the dirty part of) its distal subtree and
+// is re-evaluated.  Single-child nodes carry their child's radius ((x^k)^(1/k) = x).  The radii that get
+// PRINTED are recomputed on the host with libm pow (octa_grow_host.cu).
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double murray_parent(const IterP& P, int kmode, double ra, double rb) {
+    const double kap = P.kap_tab[kmode];
+    return fast_pow(fast_pow(ra, kap) + fast_pow(rb, kap), 1 / kap);
+}
+
 __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P, int f) {
     const int g = blockIdx.x, tid = threadIdx.x;
     if (D.err[g]) return;
@@ -688,189 +706,217 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
     const size_t sb = (size_t)g * S.capS, nb = (size_t)g * S.capN;
     const int nd_ = D.n_dict[g];
     Proposal* prop = D.prop + nb;
-    int* alist = D.alist + nb;
-    // compact the entries that act without any recheck: leaves that grow, inter-nodes that draw
+    ActDec* adec = D.adec + nb;
+    int4* newl = D.newl + nb;
+    TreeRec* rec = D.rec[f] + nb;
+    const int* dict = D.dict_node + nb;
+    __shared__ int s_nnew, s_err;
+    const long long t_start = clock64();
+    // ---- prologue: decision records of the entries that act without a recheck
     int na = 0;
     for (int base = 0; base < nd_; base += blockDim.x) {
         const int e = base + tid;
-        int fl = 0;
-        if (e < nd_) { const int t = prop[e].type; fl = (t == P_LEAF_ELONG || t == P_LEAF_DRAW || t == P_LEAF_BIF || t == P_INTER_DRAW); }
+        int fl = 0, t = 0;
+        if (e < nd_) { t = prop[e].type; fl = (t == P_LEAF_ELONG || t == P_LEAF_DRAW || t == P_LEAF_BIF || t == P_INTER_DRAW); }
         int total;
         const int incl = block_scan_incl(fl, &total);
-        if (fl) alist[na + incl - 1] = e;
+        if (fl) { ActDec a; a.e = e; a.nd = dict[e]; a.type = t; a.cond = prop[e].cond; a.ratio5 = prop[e].ratio5; a.pad = 0; adec[na + incl - 1] = a; }
         na += total;
     }
     __syncthreads();
     const int n_before = D.n_nodes[f][g];
+    const long long t_replay = clock64();
+    // ---- replay
     if (tid == 0) {
-        double* X = D.nx[f] + nb; double* Y = D.ny[f] + nb; double* Z = D.nz[f] + nb;
-        double* R = D.nrad[f] + nb; double* K = D.nkap[f] + nb;
-        int* PAR = D.npar[f] + nb; int* C0 = D.nch0[f] + nb; int* C1 = D.nch1[f] + nb;
-        unsigned char* NCH = D.nnch[f] + nb; unsigned char* META = D.nmeta[f] + nb; unsigned char* DEACT = D.deact[f] + nb;
-        const int* slot = D.slot + nb; const int* slot_call = D.slot_call + nb;
-        const int* dict = D.dict_node + nb;
+        unsigned char* DEACT = D.deact[f] + nb;
         const int* loff = D.list_off + (size_t)g * (S.capN + 1);
-        unsigned int* pb = D.py_buf + (size_t)g * S.pycap;
+        const unsigned int* pb = D.py_buf + (size_t)g * S.pycap;
+        int* rtag = D.rtag + nb;
         int ppos = D.py_pos[g];
-        int n_nodes = n_before;
+        int n_nodes = n_before, nnew = 0, err = 0;
         long long draws = 0;
         int cur_rank = -1, outstanding = 0;
-        int* rtag = D.rtag + nb;
         auto next_uniform = [&]() { const double u = mt_double(pb[ppos], pb[ppos + 1]); ppos += 2; ++draws; return u; };
-        auto add_node = [&](const double* p, int parent, int walk_after) -> int {
-            if (n_nodes >= S.capN) { D.err[g] = 1; return -1; }
+        auto add_node = [&](int e, int which, int parent, int parent_nch, int walk_after) -> bool {
+            if (n_nodes >= S.capN) { err = 1; return false; }
             const int id = n_nodes++;
-            X[id] = p[0]; Y[id] = p[1]; Z[id] = p[2]; R[id] = P.r; K[id] = P.kappa;
-            PAR[id] = parent; C0[id] = -1; C1[id] = -1; NCH[id] = 0; DEACT[id] = 0;
-            META[id] = (unsigned char)((P.mode_idx << 1) | (walk_after ? 1 : 0));
-            if (NCH[parent] == 0) C0[parent] = id; else C1[parent] = id;
-            NCH[parent] = NCH[parent] + 1;
-            return id;
+            TreeRec r;
+            r.R = P.r; r.par = parent; r.c0 = -1; r.c1 = -1; r.slot = 0; r.slot_call = 0;
+            r.nch = 0; r.kmode = (unsigned char)P.mode_idx; r.dirty = 0; r.pad = 0;
+            rec[id] = r;
+            if (parent_nch == 0) rec[parent].c0 = id; else rec[parent].c1 = id;
+            rec[parent].nch = (unsigned char)(parent_nch + 1);
+            newl[nnew++] = make_int4(e, which | (walk_after << 2), parent, id);
+            return true;
         };
-        // Murray radii (arterial_tree.py:174-184) are kept LAZILY inside a call: a branch event only marks its
-        // ancestor chain dirty (one dependent load per step, stopping at the first already-dirty node) and flags later
-        // inter-node dict entries whose distal radius may have changed; a flagged entry refreshes the dirty part of
-        // its distal subtree on demand, and everything still dirty is refreshed bottom-up by the whole CTA after the
-        // replay.  (The radii that get PRINTED are recomputed on the host with libm pow, see octa_grow_host.cu.)
-        unsigned char* DIRTY = D.dirty[f] + nb;
         auto mark_walk = [&](int n) {
-            while (true) {
-                const int par = PAR[n];
-                if (par < 0 || DIRTY[n]) return;
-                DIRTY[n] = 1;
-                if (slot_call[par] == call_id && NCH[par] == 1 && PAR[par] >= 0) {
-                    const int rk = slot[par];
-                    if (rk > cur_rank && rtag[rk] != call_id) { rtag[rk] = call_id; ++outstanding; }
+            TreeRec cur = rec[n];
+            while (cur.par >= 0 && !cur.dirty) {
+                rec[n].dirty = 1;
+                const int p = cur.par;
+                const TreeRec rp = rec[p];
+                if (rp.slot_call == call_id && rp.nch == 1 && rp.par >= 0 && rp.slot > cur_rank && rtag[rp.slot] != call_id) {
+                    rtag[rp.slot] = call_id;
+                    ++outstanding;
                 }
-                n = par;
+                n = p;
+                cur = rp;
             }
         };
-        auto refresh_subtree = [&](int top) {     // post-order over the dirty part of subtree(top), no stack needed
+        auto refresh_subtree = [&](int top) {     // post-order over the dirty part of subtree(top); no stack needed
             int n = top;
             while (true) {
-                const int nch = NCH[n];
-                const int c0 = C0[n], c1 = C1[n];
-                if (nch >= 1 && DIRTY[c0]) { n = c0; continue; }
-                if (nch >= 2 && DIRTY[c1]) { n = c1; continue; }
-                if (nch > 0) {
-                    const double kap = K[n];
-                    double sm = fast_pow(R[c0], kap);
-                    if (nch > 1) sm = sm + fast_pow(R[c1], kap);
-                    R[n] = fast_pow(sm, 1 / kap);
-                }
-                DIRTY[n] = 0;
+                const TreeRec r = rec[n];
+                if (r.nch >= 1 && rec[r.c0].dirty) { n = r.c0; continue; }
+                if (r.nch >= 2 && rec[r.c1].dirty) { n = r.c1; continue; }
+                if (r.nch == 1) rec[n].R = rec[r.c0].R;
+                else if (r.nch == 2) rec[n].R = murray_parent(P, r.kmode, rec[r.c0].R, rec[r.c1].R);
+                rec[n].dirty = 0;
+                D.nrad[f][nb + n] = rec[n].R;
                 if (n == top) return;
-                n = PAR[n];
+                n = r.par;
             }
         };
         int ai = 0, scan = 0;
-        while (true) {
-            // next entry in dict order: the next action entry, unless an entry flagged for a recheck (its distal
-            // radius was changed by a walk of this call) comes first.  Flags always point past cur_rank, and `scan`
-            // moves monotonically, so every dict slot is inspected at most once per call.
-            const int ea = (ai < na) ? alist[ai] : 0x7fffffff;
+        while (!err) {
+            // next entry in dict order: the next decision record, unless an entry tagged for a recheck comes first.
+            // Tags always point past cur_rank and `scan` moves monotonically: each dict slot is inspected at most once.
+            const int ea = (ai < na) ? adec[ai].e : 0x7fffffff;
             int e = -1;
             if (outstanding > 0) {
                 if (scan <= cur_rank) scan = cur_rank + 1;
                 const int lim = ea < nd_ ? ea : nd_;
                 for (; scan < lim; ++scan) if (rtag[scan] == call_id) { e = scan; break; }
             }
-            bool from_pending;
-            if (e >= 0) {
-                from_pending = true; --outstanding; rtag[e] = 0; scan = e + 1;
+            ActDec a;
+            bool tagged;
+            if (e >= 0) {                       // tagged entry that is not (or not yet) a decision record
+                tagged = true; --outstanding; rtag[e] = 0; scan = e + 1;
+                a.e = e; a.nd = dict[e]; a.type = prop[e].type; a.cond = prop[e].cond; a.ratio5 = prop[e].ratio5;
             } else if (ea != 0x7fffffff) {
-                e = ea; ++ai;
-                from_pending = (rtag[e] == call_id);
-                if (from_pending) { --outstanding; rtag[e] = 0; }
+                a = adec[ai++];
+                e = a.e;
+                tagged = outstanding > 0 && rtag[e] == call_id;
+                if (tagged) { --outstanding; rtag[e] = 0; }
             } else {
                 break;
             }
-            if (D.err[g]) break;
             cur_rank = e;
-            Proposal pr = prop[e];
-            const int nd = dict[e];
-            if (pr.type == P_INTER_DRAW || pr.type == P_INTER_EMPTY) {
-                const int cd = C0[nd];
-                if (DIRTY[cd]) refresh_subtree(cd);
-                const double r1 = R[cd];
-                (void)from_pending;
-                if (r1 != pr.r1_used) {
-                    // distal radius changed since k_eval (an earlier entry of this call branched below it)
-                    NodeCtx nc;
-                    load_ctx(D, S, P, g, f, nd, &nc);
-                    eval_inter(D, S, P, g, f, nc, D.list + sb + loff[e], loff[e + 1] - loff[e], r1, &pr);
+            const int nd = a.nd;
+            if (a.type == P_INTER_DRAW || a.type == P_INTER_EMPTY) {
+                if (tagged) {
+                    // an earlier entry of this call branched below this node: its distal radius may have changed
+                    const int cd = rec[nd].c0;
+                    if (rec[cd].dirty) refresh_subtree(cd);
+                    const double r1 = rec[cd].R;
+                    if (r1 != prop[e].r1_used) {
+                        NodeCtx nc;
+                        load_ctx(D, S, P, g, f, nd, &nc);
+                        Proposal pr;
+                        pr.cond = 0; pr.ratio5 = 0;
+                        eval_inter(D, S, P, g, f, nc, D.list + sb + loff[e], loff[e + 1] - loff[e], r1, &pr);
+                        prop[e] = pr;
+                        a.type = pr.type; a.cond = pr.cond; a.ratio5 = pr.ratio5;
+                    }
                 }
-                if (pr.type != P_INTER_DRAW) continue;
+                if (a.type != P_INTER_DRAW) continue;
                 const double u = next_uniform();
-                if (pr.ratio5 <= u && pr.cond) continue;
-                if (add_node(pr.p, nd, 1) < 0) break;
+                if (a.ratio5 <= u && a.cond) continue;
+                if (!add_node(e, 0, nd, 1, 1)) break;
                 mark_walk(nd);
                 DEACT[nd] = 1;
-            } else if (pr.type == P_LEAF_ELONG) {
-                if (add_node(pr.p, nd, 0) < 0) break;
-            } else if (pr.type == P_LEAF_DRAW || pr.type == P_LEAF_BIF) {
+            } else if (a.type == P_LEAF_ELONG) {
+                if (!add_node(e, 0, nd, 0, 0)) break;
+            } else if (a.type == P_LEAF_DRAW || a.type == P_LEAF_BIF) {
                 bool bif = true;
-                if (pr.type == P_LEAF_DRAW) { const double u = next_uniform(); bif = (pr.ratio5 > u) && pr.cond; }
+                if (a.type == P_LEAF_DRAW) { const double u = next_uniform(); bif = (a.ratio5 > u) && a.cond; }
                 if (bif) {
-                    if (add_node(pr.b1, nd, 0) < 0) break;
-                    if (add_node(pr.b2, nd, 1) < 0) break;
+                    if (!add_node(e, 1, nd, 0, 0)) break;
+                    if (!add_node(e, 2, nd, 1, 1)) break;
                     mark_walk(nd);
                     DEACT[nd] = 1;
                 } else {
-                    if (add_node(pr.p, nd, 0) < 0) break;
+                    if (!add_node(e, 0, nd, 0, 0)) break;
                 }
             }
         }
+        if (err) D.err[g] = err;
         D.py_pos[g] = ppos;
         D.py_draws[g] += draws;
         D.n_prev[f][g] = n_before;
         D.n_nodes[f][g] = n_nodes;
+        s_nnew = nnew;
+        s_err = err;
     }
     __syncthreads();
-    if (D.err[g]) return;
-    const int n_after = D.n_nodes[f][g];
+    if (s_err) return;
+    const long long t_epi = clock64();
+    const int n_after = n_before + s_nnew;
+    // ---- epilogue 1: SoA fields of the new nodes and of their parents' links
+    for (int k = tid; k < s_nnew; k += blockDim.x) {
+        const int4 nn = newl[k];
+        const int e = nn.x, which = nn.y & 3, walk = nn.y >> 2, parent = nn.z, id = nn.w;
+        const Proposal& pr = prop[e];
+        const double* p = which == 0 ? pr.p : (which == 1 ? pr.b1 : pr.b2);
+        D.nx[f][nb + id] = p[0]; D.ny[f][nb + id] = p[1]; D.nz[f][nb + id] = p[2];
+        D.nrad[f][nb + id] = P.r; D.nkap[f][nb + id] = P.kappa;
+        D.npar[f][nb + id] = parent; D.nch0[f][nb + id] = -1; D.nch1[f][nb + id] = -1; D.nnch[f][nb + id] = 0;
+        D.deact[f][nb + id] = 0;
+        D.nmeta[f][nb + id] = (unsigned char)((P.mode_idx << 1) | walk);
+        const TreeRec rp = rec[parent];
+        D.nch0[f][nb + parent] = rp.c0; D.nch1[f][nb + parent] = rp.c1; D.nnch[f][nb + parent] = rp.nch;
+    }
+    // ---- epilogue 2: bottom-up refresh of every node still dirty
     {
-        // bottom-up refresh of every node still dirty: a node is computed by the thread that completes its last
-        // dirty child (atomic countdown), so the critical path is one root chain, not the sum over events
-        unsigned char* DIRTY = D.dirty[f] + nb;
         int* pend = D.cnt + nb;                      // all zero outside k_group
-        volatile double* R = D.nrad[f] + nb;
-        const double* K = D.nkap[f] + nb;
-        const int* PAR = D.npar[f] + nb; const int* C0 = D.nch0[f] + nb; const int* C1 = D.nch1[f] + nb;
-        const unsigned char* NCH = D.nnch[f] + nb;
-        for (int n = tid; n < n_after; n += blockDim.x)
-            if (DIRTY[n]) {
-                const int nch = NCH[n];
-                const int c = ((nch >= 1 && DIRTY[C0[n]]) ? 1 : 0) + ((nch >= 2 && DIRTY[C1[n]]) ? 1 : 0);
+        for (int n = tid; n < n_after; n += blockDim.x) {
+            const TreeRec r = rec[n];
+            if (r.dirty) {
+                const int c = ((r.nch >= 1 && rec[r.c0].dirty) ? 1 : 0) + ((r.nch >= 2 && rec[r.c1].dirty) ? 1 : 0);
                 pend[n] = c ? c : -1;                // -1: ready now
-            }
-        __syncthreads();
-        for (int n0 = tid; n0 < n_after; n0 += blockDim.x) {
-            if (!DIRTY[n0] || pend[n0] != -1) continue;
-            int n = n0;
-            while (true) {
-                const int nch = NCH[n];
-                if (nch > 0) {
-                    const double kap = K[n];
-                    double sm = fast_pow(R[C0[n]], kap);
-                    if (nch > 1) sm = sm + fast_pow(R[C1[n]], kap);
-                    R[n] = fast_pow(sm, 1 / kap);
-                }
-                pend[n] = 0;
-                __threadfence_block();
-                const int p = PAR[n];
-                if (p < 0 || !DIRTY[p]) break;          // (the root is never marked)
-                const int old = atomicSub(&pend[p], 1);
-                if (old != 1) break;
-                __threadfence_block();
-                n = p;
             }
         }
         __syncthreads();
-        for (int n = tid; n < n_after; n += blockDim.x) DIRTY[n] = 0;
+        volatile TreeRec* vrec = rec;
+        for (int n0 = tid; n0 < n_after; n0 += blockDim.x) {
+            if (!rec[n0].dirty || pend[n0] != -1) continue;
+            int n = n0;
+            TreeRec r = rec[n];
+            double rn = 0;
+            bool have_child_r = false;               // rn holds the radius of the child we just came from
+            int from = -1;
+            while (true) {
+                double val = r.R;
+                if (r.nch == 1) val = have_child_r ? rn : vrec[r.c0].R;
+                else if (r.nch == 2) {
+                    const double ra = (have_child_r && from == r.c0) ? rn : vrec[r.c0].R;
+                    const double rb = (have_child_r && from == r.c1) ? rn : vrec[r.c1].R;
+                    val = murray_parent(P, r.kmode, ra, rb);
+                }
+                vrec[n].R = val;
+                D.nrad[f][nb + n] = val;
+                rec[n].dirty = 0;
+                pend[n] = 0;
+                const int p = r.par;
+                if (p < 0) break;
+                const TreeRec rp = rec[p];
+                if (!rp.dirty) break;                // (the root is never marked)
+                if (rp.nch >= 2) {
+                    __threadfence_block();
+                    if (atomicSub(&pend[p], 1) != 1) break;
+                    __threadfence_block();
+                } else {
+                    pend[p] = 0;
+                }
+                from = n; rn = val; have_child_r = true;
+                n = p; r = rp;
+            }
+        }
         __syncthreads();
     }
-    // active list: drop the nodes that branched (stable), append the new nodes (element_mesh.py:103-111,180-193)
+    const long long t_act = clock64();
+    // ---- epilogue 3: active list: drop the nodes that branched (stable), append the new nodes
+    // (element_mesh.py:103-111,180-193)
     int* act = D.act[f] + nb;
     double* ax = D.ax[f] + nb; double* ay = D.ay[f] + nb; double* az = D.az[f] + nb;
     unsigned char* deact = D.deact[f] + nb;
@@ -891,7 +937,12 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
         const int o = w + (i - n_before);
         act[o] = i; ax[o] = D.nx[f][nb + i]; ay[o] = D.ny[f][nb + i]; az[o] = D.nz[f][nb + i];
     }
-    if (tid == 0) D.n_act[f][g] = w + (n_after - n_before);
+    if (tid == 0) {
+        D.n_act[f][g] = w + (n_after - n_before);
+        const long long t_end = clock64();          // per-phase cycle counters (reported through OctaGrowStats)
+        D.counters[g * 8 + 4] += t_replay - t_start; D.counters[g * 8 + 5] += t_epi - t_replay;
+        D.counters[g * 8 + 6] += t_act - t_epi; D.counters[g * 8 + 7] += t_end - t_act;
+    }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -35,7 +35,7 @@ class OctaGrowConfig(ctypes.Structure):
 class OctaGrowStats(ctypes.Structure):
     _fields_ = [(k, ctypes.c_int64) for k in ("n_art_nodes", "n_ven_nodes", "n_oxy_left", "n_co2_left", "py_draws",
                                               "sum_A", "sum_M", "sum_P", "sum_S")] + \
-        [("err", ctypes.c_int32), ("n_iters", ctypes.c_int32)]
+        [("commit_cycles", ctypes.c_int64 * 4), ("err", ctypes.c_int32), ("n_iters", ctypes.c_int32)]
 
 
 def make_config(config: dict, cap_nodes: int = 0, cap_sinks: int = 0) -> OctaGrowConfig:
@@ -79,36 +79,74 @@ def make_config(config: dict, cap_nodes: int = 0, cap_sinks: int = 0) -> OctaGro
 
 def _bind():
     L = _lib.lib()
-    L.octa_grow_batch_host.argtypes = [ctypes.POINTER(OctaGrowConfig), ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
-                                       ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                       ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
+    run_args = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
+    L.octa_grow_batch_host.argtypes = [ctypes.POINTER(OctaGrowConfig)] + run_args
+    L.octa_grow_create.argtypes = [ctypes.POINTER(OctaGrowConfig), ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+    L.octa_grow_run.argtypes = [ctypes.c_void_p] + run_args
+    L.octa_grow_destroy.argtypes = [ctypes.c_void_p]
+    L.octa_grow_destroy.restype = None
     return L
+
+
+class GrowContext:
+    """Persistent device state for batches of up to `max_graphs` samples of one config (octa_grow_create/run/destroy)."""
+
+    def __init__(self, config: dict, max_graphs: int, cap_edges: int = 40000, cap_nodes: int = 0, cap_sinks: int = 0):
+        self.L = _bind()
+        self.max_graphs = int(max_graphs)
+        self.cap_edges = int(cap_edges)
+        self._cfg = make_config(config, cap_nodes, cap_sinks)
+        self._h = ctypes.c_void_p()
+        _lib.check(self.L.octa_grow_create(ctypes.byref(self._cfg), self.max_graphs, ctypes.byref(self._h)))
+        self._out = np.empty((self.max_graphs, self.cap_edges, 7), dtype=np.float64)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.L.octa_grow_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run(self, seeds: Sequence[int], trace: bool = False, copy: bool = True):
+        n = len(seeds)
+        if n > self.max_graphs:
+            raise ValueError("batch larger than the context")
+        sd = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint64))
+        na = np.zeros(n, dtype=np.int64)
+        nv = np.zeros(n, dtype=np.int64)
+        st = (OctaGrowStats * n)()
+        tr = np.zeros((n, 4096, 4), dtype=np.int32) if trace else None
+        ms = ctypes.c_double(0)
+        rc = self.L.octa_grow_run(self._h, sd.ctypes.data, n, self._out.ctypes.data, self.cap_edges, na.ctypes.data,
+                                  nv.ctypes.data, ctypes.cast(st, ctypes.c_void_p), tr.ctypes.data if trace else None,
+                                  ctypes.byref(ms))
+        stats = [{k: (list(getattr(st[i], k)) if k == 'commit_cycles' else getattr(st[i], k)) for k, _ in OctaGrowStats._fields_} for i in range(n)]
+        if rc != 0:
+            err = _lib.OctaError(rc, self.L.octa_last_error().decode(errors="replace"))
+            err.stats = stats
+            raise err
+        out = self._out
+        if copy:
+            graphs = [(out[i, :na[i]].copy(), out[i, na[i]:na[i] + nv[i]].copy()) for i in range(n)]
+        else:   # views into the context's buffer, valid until the next run
+            graphs = [(out[i, :na[i]], out[i, na[i]:na[i] + nv[i]]) for i in range(n)]
+        n_it = stats[0]["n_iters"] if n else 0
+        return graphs, stats, {"device_ms": ms.value, "trace": tr[:, :n_it] if trace else None}
 
 
 def grow_batch(config: dict, seeds: Sequence[int], cap_edges: int = 40000, trace: bool = False, cap_nodes: int = 0,
                cap_sinks: int = 0):
-    """Grow len(seeds) independent samples on the GPU.
+    """Grow len(seeds) independent samples on the GPU (one-shot context).
 
     Returns (graphs, stats, extra): graphs[i] = (art_edges7, ven_edges7) float64 arrays in the reference's row order;
     stats[i] = dict of per-sample counters; extra = {"device_ms": ..., "trace": int32 [n, iters, 4] or None}."""
-    L = _bind()
-    c = make_config(config, cap_nodes, cap_sinks)
-    n = len(seeds)
-    sd = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint64))
-    out = np.empty((n, cap_edges, 7), dtype=np.float64)
-    na = np.zeros(n, dtype=np.int64)
-    nv = np.zeros(n, dtype=np.int64)
-    st = (OctaGrowStats * n)()
-    tr = np.zeros((n, 4096, 4), dtype=np.int32) if trace else None
-    ms = ctypes.c_double(0)
-    rc = L.octa_grow_batch_host(ctypes.byref(c), sd.ctypes.data, n, out.ctypes.data, cap_edges, na.ctypes.data,
-                                nv.ctypes.data, ctypes.cast(st, ctypes.c_void_p), tr.ctypes.data if trace else None,
-                                ctypes.byref(ms))
-    stats = [{k: getattr(st[i], k) for k, _ in OctaGrowStats._fields_} for i in range(n)]
-    if rc != 0:
-        err = _lib.OctaError(rc, L.octa_last_error().decode(errors="replace"))
-        err.stats = stats
-        raise err
-    graphs = [(out[i, :na[i]].copy(), out[i, na[i]:na[i] + nv[i]].copy()) for i in range(n)]
-    n_it = stats[0]["n_iters"] if n else 0
-    return graphs, stats, {"device_ms": ms.value, "trace": tr[:, :n_it] if trace else None}
+    ctx = GrowContext(config, len(seeds), cap_edges, cap_nodes, cap_sinks)
+    try:
+        return ctx.run(seeds, trace=trace)
+    finally:
+        ctx.close()

@@ -31,6 +31,7 @@ class Pipeline:
         self.voxelize = bool(voxelize)
         self.host_threads = host_threads or max(1, (os.cpu_count() or 2) - 1)
         self._buf = {}
+        self._grow = None
 
     def _tensor(self, key, shape, dtype, pinned=False):
         t = self._buf.get(key)
@@ -48,7 +49,11 @@ class Pipeline:
         tensors), and with d2h: label_host / image_host (pinned uint8) and csv (list of bytes)."""
         torch = self.torch
         with torch.cuda.device(self.device):
-            graphs, stats, extra = growth.grow_batch(self.config, seeds)
+            if self._grow is None or self._grow.max_graphs < len(seeds):
+                if self._grow is not None:
+                    self._grow.close()
+                self._grow = growth.GrowContext(self.config, len(seeds))
+            graphs, stats, extra = self._grow.run(seeds, copy=False)
             n = len(seeds)
             sizes = [len(a) + len(v) for a, v in graphs]
             offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)

@@ -30,6 +30,9 @@ for rep in range(a.reps):
     ne = [len(g[0]) + len(g[1]) for g in graphs]
     print("rep %d: batch %d  device %.1f ms  wall %.2f s  -> %.1f graphs/s (device), edges mean %.0f min %d max %d" %
           (rep, a.batch, extra["device_ms"], dt, a.batch / (extra["device_ms"] * 1e-3), np.mean(ne), min(ne), max(ne)), flush=True)
+    cyc = np.array([s["commit_cycles"] for s in stats], dtype=np.float64)
+    print("   k_commit cycles per graph (mean | max over graphs) prologue/replay/refresh/active: %s | %s  [ms at 1.9 GHz: %s]" %
+          (np.round(cyc.mean(0) / 1e6, 1), np.round(cyc.max(0) / 1e6, 1), np.round(cyc.max(0) / 1.9e6, 1)), flush=True)
 if a.check:
     from oracle import growth_oracle as go
     exact = idx = 0
