@@ -123,6 +123,7 @@ typedef struct OctaGrowStats {
     int64_t n_art_nodes, n_ven_nodes, n_oxy_left, n_co2_left, py_draws;
     int64_t sum_A, sum_M, sum_P, sum_S;   /* byte-accounting counters of SURVEY.md 8(d) */
     int64_t commit_cycles[4];        /* SM cycles of k_commit's prologue / sequential replay / refresh / active-list phases */
+    int64_t replay_detail[8];        /* replay breakdown: cycles in tag scans, walks, rechecks; counts of entries, events, walk steps, tags, decision records */
     int32_t err;                     /* 0 ok; 1 node capacity, 2 sink capacity, 3 rng buffer, 4 recheck queue, 5 set table, 1x eig */
     int32_t n_iters;
 } OctaGrowStats;

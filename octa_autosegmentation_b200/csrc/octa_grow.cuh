@@ -48,6 +48,7 @@ struct __align__(16) ActDec {  // decision record of one acting dict entry
 
 struct GrowShape {
     int G, capN, capS, Nmax, pycap;
+    int capN_smem;   // nodes per forest mirrored in k_commit's shared memory (larger forests fall back to the global path)
 };
 
 struct GrowDev {
@@ -94,6 +95,7 @@ struct GrowDev {
     int* set_key;
     int* err;
     int* trace;     // [g][iter][4]
+    long long* dbg;       // [g][8] k_commit replay breakdown (cycles: tag scan, walks, rechecks; counts: entries, events, walk steps, tags, records)
     long long* counters;  // [g][8] byte-accounting counters (sum_A, sum_M, sum_P, sum_S, ...)
 };
 

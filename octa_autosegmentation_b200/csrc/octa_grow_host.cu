@@ -18,6 +18,7 @@
 namespace octa {
 
 void launch_iteration(const GrowDev& D, const GrowShape& S, const IterP& P, int n_sm, cudaStream_t st);
+int prepare_kernels(const GrowShape& S);
 
 namespace {
 
@@ -223,7 +224,7 @@ void carve(Carver& c, const GrowShape& S, GrowDev* D) {
     D->hitj = c.take<int>(GS); D->hl = c.take<int>(GS); D->ta = c.take<int>(GS); D->seq = c.take<int>(GS);
     D->veto = c.take<unsigned char>(GS);
     D->set_hash = c.take<long long>(G * 2 * SET_TBL); D->set_key = c.take<int>(G * 2 * SET_TBL);
-    D->err = c.take<int>(G); D->trace = c.take<int>(G * 4096 * 4); D->counters = c.take<long long>(G * 8);
+    D->err = c.take<int>(G); D->trace = c.take<int>(G * 4096 * 4); D->counters = c.take<long long>(G * 8); D->dbg = c.take<long long>(G * 8);
 }
 
 // exact radii + export of one forest (host).  Inputs are strided views into the pinned D2H staging buffers.
@@ -340,6 +341,7 @@ extern "C" int octa_grow_create(const OctaGrowConfig* cfg, int max_graphs, void*
     S.capN = cfg->cap_nodes > 0 ? cfg->cap_nodes : (int)std::min<long>(1 << 20, std::max<long>(4096, align_up((size_t)(total_try / 16 + 4096), 1024)));
     S.capS = cfg->cap_sinks > 0 ? cfg->cap_sinks : (int)std::min<long>(1 << 20, std::max<long>(4096, align_up((size_t)(total_try / 12 + 4096), 1024)));
     S.pycap = 2 * S.capN + 4 * 624;
+    S.capN_smem = std::min(S.capN, 46000);            // 46000 * (4 + 3/8) B = 197 KB of the 227 KB per CTA
     if (2 * cfg->n_trees > S.capN) { delete ctx; set_error("cap_nodes too small"); return OCTA_E_ARG; }
     Carver sizing(nullptr);
     carve(sizing, S, &ctx->D);
@@ -355,6 +357,7 @@ extern "C" int octa_grow_create(const OctaGrowConfig* cfg, int max_graphs, void*
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (prepare_kernels(S) != 0) { cudaGetLastError(); set_error("cudaFuncSetAttribute(k_commit) failed"); delete ctx; return OCTA_E_CUDA; }
     cudaEventCreate(&ctx->e0);
     cudaEventCreate(&ctx->e1);
     *handle = ctx;
@@ -460,7 +463,7 @@ extern "C" int octa_grow_run(void* handle, const uint64_t* seeds, int n_graphs, 
         OCTA_CUDA_CHECK(cudaMemcpyAsync(D.n_valid, sg + o_nv, 4 * G, cudaMemcpyHostToDevice, st));
         OCTA_CUDA_CHECK(cudaMemcpyAsync(D.valid_ij, sg + o_valid, (size_t)MAX_VALID * 2 * G, cudaMemcpyHostToDevice, st));
         OCTA_CUDA_CHECK(cudaMemsetAsync(D.py_n, 0, 4 * G, st)); OCTA_CUDA_CHECK(cudaMemsetAsync(D.py_pos, 0, 4 * G, st));
-        OCTA_CUDA_CHECK(cudaMemsetAsync(D.py_draws, 0, 8 * G, st)); OCTA_CUDA_CHECK(cudaMemsetAsync(D.counters, 0, 64 * G, st));
+        OCTA_CUDA_CHECK(cudaMemsetAsync(D.py_draws, 0, 8 * G, st)); OCTA_CUDA_CHECK(cudaMemsetAsync(D.counters, 0, 64 * G, st)); OCTA_CUDA_CHECK(cudaMemsetAsync(D.dbg, 0, 64 * G, st));
         OCTA_CUDA_CHECK(cudaMemsetAsync(D.err, 0, 4 * G, st));
         OCTA_CUDA_CHECK(cudaMemsetAsync(D.rtag, 0, 4 * G * S.capN, st));
         if (trace) OCTA_CUDA_CHECK(cudaMemsetAsync(D.trace, 0, sizeof(int) * G * 4096 * 4, st));
@@ -472,7 +475,7 @@ extern "C" int octa_grow_run(void* handle, const uint64_t* seeds, int n_graphs, 
     OCTA_CUDA_CHECK(cudaEventRecord(ctx->e1, st));
     // ---- read back: counts first, then strided copies of the live prefix of every node array
     std::vector<int> err(n_graphs), nn[2], ns[2];
-    std::vector<long long> draws(n_graphs), counters((size_t)n_graphs * 8);
+    std::vector<long long> draws(n_graphs), counters((size_t)n_graphs * 8), dbg((size_t)n_graphs * 8);
     for (int f = 0; f < 2; ++f) {
         nn[f].resize(n_graphs); ns[f].resize(n_graphs);
         OCTA_CUDA_CHECK(cudaMemcpyAsync(nn[f].data(), D.n_nodes[f], 4 * G, cudaMemcpyDeviceToHost, st));
@@ -481,6 +484,7 @@ extern "C" int octa_grow_run(void* handle, const uint64_t* seeds, int n_graphs, 
     OCTA_CUDA_CHECK(cudaMemcpyAsync(err.data(), D.err, 4 * G, cudaMemcpyDeviceToHost, st));
     OCTA_CUDA_CHECK(cudaMemcpyAsync(draws.data(), D.py_draws, 8 * G, cudaMemcpyDeviceToHost, st));
     OCTA_CUDA_CHECK(cudaMemcpyAsync(counters.data(), D.counters, 64 * G, cudaMemcpyDeviceToHost, st));
+    OCTA_CUDA_CHECK(cudaMemcpyAsync(dbg.data(), D.dbg, 64 * G, cudaMemcpyDeviceToHost, st));
     OCTA_CUDA_CHECK(cudaStreamSynchronize(st));
     OCTA_CUDA_CHECK(cudaGetLastError());
     float ms = 0;
@@ -538,6 +542,7 @@ extern "C" int octa_grow_run(void* handle, const uint64_t* seeds, int n_graphs, 
             s.sum_A = counters[(size_t)g * 8 + 0]; s.sum_M = counters[(size_t)g * 8 + 1];
             s.sum_P = counters[(size_t)g * 8 + 2]; s.sum_S = counters[(size_t)g * 8 + 3];
             for (int q = 0; q < 4; ++q) s.commit_cycles[q] = counters[(size_t)g * 8 + 4 + q];
+            for (int q = 0; q < 8; ++q) s.replay_detail[q] = dbg[(size_t)g * 8 + q];
             s.err = err[g]; s.n_iters = (int)ctx->sched.size();
         }
         if (err[g] && !worst) worst = err[g];

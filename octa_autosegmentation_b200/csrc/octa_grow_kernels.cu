@@ -202,12 +202,16 @@ __global__ void __launch_bounds__(1024) k_grid_build(GrowDev D, GrowShape S, int
     __shared__ int cursor[GRID * GRID];
     const int g = blockIdx.x, tid = threadIdx.x;
     if (D.err[g]) return;
+    // The ACTIVE node set (element_mesh.py NodeKdTree of active nodes) is the node array minus the nodes that
+    // branched: list order = creation order with deletions, so node ids preserve the list's relative order and
+    // no separate list has to be maintained.
     const double *px, *py, *pz, *pr = nullptr;
+    const unsigned char* skip = nullptr;
     int n;
     size_t cap;
     if (which == 0) { cap = S.capN; px = D.nx[0] + g * cap; py = D.ny[0] + g * cap; pz = D.nz[0] + g * cap; pr = D.nrad[0] + g * cap; n = D.n_nodes[0][g]; }
     else if (which == 1) { cap = S.capS; px = D.sx[0] + g * cap; py = D.sy[0] + g * cap; pz = D.sz[0] + g * cap; n = D.n_s[0][g]; }
-    else { const int f = which - 2; cap = S.capN; px = D.ax[f] + g * cap; py = D.ay[f] + g * cap; pz = D.az[f] + g * cap; n = D.n_act[f][g]; }
+    else { const int f = which - 2; cap = S.capN; px = D.nx[f] + g * cap; py = D.ny[f] + g * cap; pz = D.nz[f] + g * cap; n = D.n_nodes[f][g]; skip = D.deact[f] + g * cap; }
     const size_t gcap = S.capN > S.capS ? S.capN : S.capS;
     double* gx = D.gx[which] + g * gcap; double* gy = D.gy[which] + g * gcap; double* gz = D.gz[which] + g * gcap;
     double* grd = D.gr[which] + g * gcap;
@@ -215,7 +219,13 @@ __global__ void __launch_bounds__(1024) k_grid_build(GrowDev D, GrowShape S, int
     int* cs = D.gcell[which] + (size_t)g * (GRID * GRID + 1);
     for (int c = tid; c < GRID * GRID; c += blockDim.x) hist[c] = 0;
     __syncthreads();
-    for (int i = tid; i < n; i += blockDim.x) atomicAdd(&hist[grid_cell(py[i]) * GRID + grid_cell(px[i])], 1);
+    int live = 0;
+    for (int i = tid; i < n; i += blockDim.x) {
+        if (skip && skip[i]) continue;
+        ++live;
+        atomicAdd(&hist[grid_cell(py[i]) * GRID + grid_cell(px[i])], 1);
+    }
+    (void)live;
     __syncthreads();
     int run = 0;
     for (int base = 0; base < GRID * GRID; base += blockDim.x) {
@@ -227,9 +237,10 @@ __global__ void __launch_bounds__(1024) k_grid_build(GrowDev D, GrowShape S, int
         cursor[c] = run + incl - v;
         run += total;
     }
-    if (tid == 0) cs[GRID * GRID] = run;
+    if (tid == 0) { cs[GRID * GRID] = run; if (which >= 2) D.n_act[which - 2][g] = run; }
     __syncthreads();
     for (int i = tid; i < n; i += blockDim.x) {
+        if (skip && skip[i]) continue;
         const double x = px[i], y = py[i];
         const int pos = atomicAdd(&cursor[grid_cell(y) * GRID + grid_cell(x)], 1);
         gx[pos] = x; gy[pos] = y; gz[pos] = pz[i]; gi[pos] = i;
@@ -383,7 +394,7 @@ __global__ void __launch_bounds__(TILE) k_assign(GrowDev D, GrowShape S, IterP P
                 if (d2 < best || (d2 == best && li < bi)) { best = d2; bi = li; }
             }
         }
-        D.assign[sb + a] = (bi >= 0 && sqrt(best) <= delta) ? D.act[f][nb + bi] : -1;
+        D.assign[sb + a] = (bi >= 0 && sqrt(best) <= delta) ? bi : -1;
     }
 }
 
@@ -711,7 +722,26 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
     TreeRec* rec = D.rec[f] + nb;
     const int* dict = D.dict_node + nb;
     __shared__ int s_nnew, s_err;
+    // shared-memory mirror of what the dirty-marking walks touch: parent pointers, dirty bits, "is an inter-node
+    // dict entry of this call" bits -- a walk step costs a shared-memory load instead of an L2 round trip
+    extern __shared__ int s_dyn[];
+    const int n_before = D.n_nodes[f][g];
+    const int nwords = (n_before + 31) >> 5;
+    int* s_par = s_dyn;
+    unsigned int* s_dirty = (unsigned int*)(s_dyn + S.capN_smem);
+    unsigned int* s_inter = s_dirty + ((S.capN_smem + 31) >> 5);
+    unsigned int* s_tag = s_inter + ((S.capN_smem + 31) >> 5);     // recheck tags, indexed by dict rank
+    const bool use_smem = n_before <= S.capN_smem;
     const long long t_start = clock64();
+    if (use_smem) {
+        for (int i = tid; i < n_before; i += blockDim.x) s_par[i] = D.npar[f][nb + i];
+        for (int i = tid; i < nwords; i += blockDim.x) { s_dirty[i] = 0; s_inter[i] = 0; s_tag[i] = 0; }
+        __syncthreads();
+        for (int e = tid; e < nd_; e += blockDim.x) {
+            const int t = prop[e].type;
+            if (t == P_INTER_DRAW || t == P_INTER_EMPTY) { const int nd = dict[e]; atomicOr(&s_inter[nd >> 5], 1u << (nd & 31)); }
+        }
+    }
     // ---- prologue: decision records of the entries that act without a recheck
     int na = 0;
     for (int base = 0; base < nd_; base += blockDim.x) {
@@ -724,7 +754,6 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
         na += total;
     }
     __syncthreads();
-    const int n_before = D.n_nodes[f][g];
     const long long t_replay = clock64();
     // ---- replay
     if (tid == 0) {
@@ -736,6 +765,7 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
         int n_nodes = n_before, nnew = 0, err = 0;
         long long draws = 0;
         int cur_rank = -1, outstanding = 0;
+        long long dbg_scan = 0, dbg_walk = 0, dbg_recheck = 0, dbg_entries = 0, dbg_events = 0, dbg_steps = 0, dbg_tags = 0;
         auto next_uniform = [&]() { const double u = mt_double(pb[ppos], pb[ppos + 1]); ppos += 2; ++draws; return u; };
         auto add_node = [&](int e, int which, int parent, int parent_nch, int walk_after) -> bool {
             if (n_nodes >= S.capN) { err = 1; return false; }
@@ -749,29 +779,63 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
             newl[nnew++] = make_int4(e, which | (walk_after << 2), parent, id);
             return true;
         };
+        const int* slot = D.slot + nb;
+        auto is_tagged = [&](int rk) -> bool { return use_smem ? ((s_tag[rk >> 5] >> (rk & 31)) & 1u) != 0 : rtag[rk] == call_id; };
+        auto set_tag = [&](int rk) { if (use_smem) s_tag[rk >> 5] |= 1u << (rk & 31); else rtag[rk] = call_id; };
+        auto clear_tag = [&](int rk) { if (use_smem) s_tag[rk >> 5] &= ~(1u << (rk & 31)); else rtag[rk] = 0; };
+        auto next_tag = [&](int from, int lim) -> int {      // first tagged rank in [from, lim), or -1
+            if (!use_smem) { for (int q = from; q < lim; ++q) if (rtag[q] == call_id) return q; return -1; }
+            int q = from;
+            while (q < lim) {
+                unsigned int wv = s_tag[q >> 5] >> (q & 31);
+                if (wv) { const int r = q + __ffs(wv) - 1; return r < lim ? r : -1; }
+                q = (q | 31) + 1;
+            }
+            return -1;
+        };
         auto mark_walk = [&](int n) {
+            ++dbg_events;
+            if (use_smem) {
+                while (true) {
+                    ++dbg_steps;
+                    const int p = s_par[n];
+                    const unsigned int bit = 1u << (n & 31);
+                    if (p < 0 || (s_dirty[n >> 5] & bit)) return;
+                    s_dirty[n >> 5] |= bit;
+                    if (s_inter[p >> 5] & (1u << (p & 31))) {
+                        const int rk = slot[p];
+                        if (rk > cur_rank && !is_tagged(rk)) { set_tag(rk); ++outstanding; ++dbg_tags; }
+                    }
+                    n = p;
+                }
+            }
             TreeRec cur = rec[n];
             while (cur.par >= 0 && !cur.dirty) {
                 rec[n].dirty = 1;
                 const int p = cur.par;
                 const TreeRec rp = rec[p];
-                if (rp.slot_call == call_id && rp.nch == 1 && rp.par >= 0 && rp.slot > cur_rank && rtag[rp.slot] != call_id) {
-                    rtag[rp.slot] = call_id;
+                if (rp.slot_call == call_id && rp.nch == 1 && rp.par >= 0 && rp.slot > cur_rank && !is_tagged(rp.slot)) {
+                    set_tag(rp.slot);
                     ++outstanding;
                 }
                 n = p;
                 cur = rp;
             }
         };
+        auto is_dirty = [&](int n) -> bool {
+            // (nodes created in this call are never dirty and lie beyond the mirrored range)
+            if (use_smem) return n < n_before && ((s_dirty[n >> 5] >> (n & 31)) & 1u);
+            return rec[n].dirty != 0;
+        };
         auto refresh_subtree = [&](int top) {     // post-order over the dirty part of subtree(top); no stack needed
             int n = top;
             while (true) {
                 const TreeRec r = rec[n];
-                if (r.nch >= 1 && rec[r.c0].dirty) { n = r.c0; continue; }
-                if (r.nch >= 2 && rec[r.c1].dirty) { n = r.c1; continue; }
+                if (r.nch >= 1 && is_dirty(r.c0)) { n = r.c0; continue; }
+                if (r.nch >= 2 && is_dirty(r.c1)) { n = r.c1; continue; }
                 if (r.nch == 1) rec[n].R = rec[r.c0].R;
                 else if (r.nch == 2) rec[n].R = murray_parent(P, r.kmode, rec[r.c0].R, rec[r.c1].R);
-                rec[n].dirty = 0;
+                if (use_smem) s_dirty[n >> 5] &= ~(1u << (n & 31)); else rec[n].dirty = 0;
                 D.nrad[f][nb + n] = rec[n].R;
                 if (n == top) return;
                 n = r.par;
@@ -784,20 +848,24 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
             const int ea = (ai < na) ? adec[ai].e : 0x7fffffff;
             int e = -1;
             if (outstanding > 0) {
+                const long long t0 = clock64();
                 if (scan <= cur_rank) scan = cur_rank + 1;
                 const int lim = ea < nd_ ? ea : nd_;
-                for (; scan < lim; ++scan) if (rtag[scan] == call_id) { e = scan; break; }
+                e = next_tag(scan, lim);
+                if (e < 0) scan = lim;
+                dbg_scan += clock64() - t0;
             }
+            ++dbg_entries;
             ActDec a;
             bool tagged;
             if (e >= 0) {                       // tagged entry that is not (or not yet) a decision record
-                tagged = true; --outstanding; rtag[e] = 0; scan = e + 1;
+                tagged = true; --outstanding; clear_tag(e); scan = e + 1;
                 a.e = e; a.nd = dict[e]; a.type = prop[e].type; a.cond = prop[e].cond; a.ratio5 = prop[e].ratio5;
             } else if (ea != 0x7fffffff) {
                 a = adec[ai++];
                 e = a.e;
-                tagged = outstanding > 0 && rtag[e] == call_id;
-                if (tagged) { --outstanding; rtag[e] = 0; }
+                tagged = outstanding > 0 && is_tagged(e);
+                if (tagged) { --outstanding; clear_tag(e); }
             } else {
                 break;
             }
@@ -805,9 +873,10 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
             const int nd = a.nd;
             if (a.type == P_INTER_DRAW || a.type == P_INTER_EMPTY) {
                 if (tagged) {
+                    const long long t0 = clock64();
                     // an earlier entry of this call branched below this node: its distal radius may have changed
                     const int cd = rec[nd].c0;
-                    if (rec[cd].dirty) refresh_subtree(cd);
+                    if (is_dirty(cd)) refresh_subtree(cd);
                     const double r1 = rec[cd].R;
                     if (r1 != prop[e].r1_used) {
                         NodeCtx nc;
@@ -818,12 +887,13 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
                         prop[e] = pr;
                         a.type = pr.type; a.cond = pr.cond; a.ratio5 = pr.ratio5;
                     }
+                    dbg_recheck += clock64() - t0;
                 }
                 if (a.type != P_INTER_DRAW) continue;
                 const double u = next_uniform();
                 if (a.ratio5 <= u && a.cond) continue;
                 if (!add_node(e, 0, nd, 1, 1)) break;
-                mark_walk(nd);
+                { const long long t0 = clock64(); mark_walk(nd); dbg_walk += clock64() - t0; }
                 DEACT[nd] = 1;
             } else if (a.type == P_LEAF_ELONG) {
                 if (!add_node(e, 0, nd, 0, 0)) break;
@@ -833,13 +903,14 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
                 if (bif) {
                     if (!add_node(e, 1, nd, 0, 0)) break;
                     if (!add_node(e, 2, nd, 1, 1)) break;
-                    mark_walk(nd);
+                    { const long long t0 = clock64(); mark_walk(nd); dbg_walk += clock64() - t0; }
                     DEACT[nd] = 1;
                 } else {
                     if (!add_node(e, 0, nd, 0, 0)) break;
                 }
             }
         }
+        if (D.dbg) { long long* q = D.dbg + g * 8; q[0] += dbg_scan; q[1] += dbg_walk; q[2] += dbg_recheck; q[3] += dbg_entries; q[4] += dbg_events; q[5] += dbg_steps; q[6] += dbg_tags; q[7] += na; }
         if (err) D.err[g] = err;
         D.py_pos[g] = ppos;
         D.py_draws[g] += draws;
@@ -852,6 +923,11 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
     if (s_err) return;
     const long long t_epi = clock64();
     const int n_after = n_before + s_nnew;
+    if (use_smem) {
+        for (int n = tid; n < n_before; n += blockDim.x)
+            if ((s_dirty[n >> 5] >> (n & 31)) & 1u) rec[n].dirty = 1;
+        __syncthreads();
+    }
     // ---- epilogue 1: SoA fields of the new nodes and of their parents' links
     for (int k = tid; k < s_nnew; k += blockDim.x) {
         const int4 nn = newl[k];
@@ -915,30 +991,8 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
         __syncthreads();
     }
     const long long t_act = clock64();
-    // ---- epilogue 3: active list: drop the nodes that branched (stable), append the new nodes
-    // (element_mesh.py:103-111,180-193)
-    int* act = D.act[f] + nb;
-    double* ax = D.ax[f] + nb; double* ay = D.ay[f] + nb; double* az = D.az[f] + nb;
-    unsigned char* deact = D.deact[f] + nb;
-    const int M = D.n_act[f][g];
-    int w = 0;
-    for (int base = 0; base < M; base += blockDim.x) {
-        const int i = base + tid;
-        int keep = 0, id = -1;
-        double px = 0, py = 0, pz = 0;
-        if (i < M) { id = act[i]; keep = !deact[id]; px = ax[i]; py = ay[i]; pz = az[i]; }
-        int total;
-        const int incl = block_scan_incl(keep, &total);   // (contains the barriers that order reads before writes)
-        if (keep) { const int o = w + incl - 1; act[o] = id; ax[o] = px; ay[o] = py; az[o] = pz; }
-        w += total;
-        __syncthreads();
-    }
-    for (int i = n_before + tid; i < n_after; i += blockDim.x) {
-        const int o = w + (i - n_before);
-        act[o] = i; ax[o] = D.nx[f][nb + i]; ay[o] = D.ny[f][nb + i]; az[o] = D.nz[f][nb + i];
-    }
+    // (no active list to maintain: the active set is the node array minus the DEACT marks, see k_grid_build)
     if (tid == 0) {
-        D.n_act[f][g] = w + (n_after - n_before);
         const long long t_end = clock64();          // per-phase cycle counters (reported through OctaGrowStats)
         D.counters[g * 8 + 4] += t_replay - t_start; D.counters[g * 8 + 5] += t_epi - t_replay;
         D.counters[g * 8 + 6] += t_act - t_epi; D.counters[g * 8 + 7] += t_end - t_act;
@@ -1127,6 +1181,12 @@ __global__ void __launch_bounds__(1024) k_kill(GrowDev D, GrowShape S, IterP P, 
 // ------------------------------------------------------------------------------------------
 // launch wrappers (called from octa_grow_host.cu)
 // ------------------------------------------------------------------------------------------
+size_t commit_smem_bytes(const GrowShape& S) { return sizeof(int) * ((size_t)S.capN_smem + 3 * (((size_t)S.capN_smem + 31) >> 5)); }
+
+int prepare_kernels(const GrowShape& S) {
+    return (int)cudaFuncSetAttribute(k_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)commit_smem_bytes(S));
+}
+
 void launch_iteration(const GrowDev& D, const GrowShape& S, const IterP& P, int n_sm, cudaStream_t st) {
     k_sample<<<S.G, 1024, 0, st>>>(D, S, P);
     k_grid_build<<<S.G, 1024, 0, st>>>(D, S, 0);
@@ -1140,7 +1200,7 @@ void launch_iteration(const GrowDev& D, const GrowShape& S, const IterP& P, int 
         k_assign<<<n_sm * 8, TILE, 0, st>>>(D, S, P, f);
         k_group<<<S.G, 1024, 0, st>>>(D, S, P, f);
         k_eval<<<dim3(16, S.G), 128, 0, st>>>(D, S, P, f);
-        k_commit<<<S.G, 256, 0, st>>>(D, S, P, f);
+        k_commit<<<S.G, 256, commit_smem_bytes(S), st>>>(D, S, P, f);
         k_kill<<<S.G, 1024, 0, st>>>(D, S, P, f);
         count_launch(5);
     }

@@ -68,11 +68,12 @@ OCTA_HDI double oxygen_distance(double radius, double param_scale) {
     return c1 * 6 / param_scale;
 }
 
-// Murray angles, greenhouse.py:206,214-215 / :264-266 (x**4 and x**2 are libm pow in CPython)
+// Murray angles, greenhouse.py:206,214-215 / :264-266.  CPython evaluates x**4 and x**2 through libm pow; here they
+// are products (<= 1 ULP from the correctly rounded power, like glibc's pow) -- the angles only steer directions.
 OCTA_HDI void murray_angles(double r1, double r2, double kappa, double* phi1, double* phi2) {
     const double rp = pow(pow(r1, kappa) + pow(r2, kappa), 1 / kappa);
-    const double rp4 = pow(rp, 4.0), r14 = pow(r1, 4.0), r24 = pow(r2, 4.0);
-    const double rp2 = pow(rp, 2.0), r12 = pow(r1, 2.0), r22 = pow(r2, 2.0);
+    const double rp2 = rp * rp, r12 = r1 * r1, r22 = r2 * r2;
+    const double rp4 = rp2 * rp2, r14 = r12 * r12, r24 = r22 * r22;
     *phi1 = RAD2DEG * acos((rp4 + r14 - r24) / (2 * rp2 * r12));
     *phi2 = RAD2DEG * acos((rp4 + r24 - r14) / (2 * rp2 * r22));
 }

@@ -222,79 +222,106 @@ __device__ __noinline__ uint32_t exact_voxel_q(const VoxEdge& e, double vx, doub
     return (uint32_t)(255.0 * cl);
 }
 
-// One warp rasterizes one edge into the shared-memory tile.  Lanes own (y,z) rows of the clipped bounding box
-// and walk along x.  Three tiers per voxel:
+// Per-edge constants staged in shared memory for one pass of EPASS edges of a tile.
+constexpr int EPASS = 32;
+struct EdgeSm {
+    double p1[3], p2[3], s[3];
+    double R, ss, inv_ss, c0, tguard;
+    float a[3], f[3], finv, thr;
+    int b0[3], n[3];
+    int rowbase;            // exclusive prefix of (y,z) rows over the pass
+};
+
+// Work distribution: the (y,z) rows of all clipped edge boxes of a pass are numbered consecutively and dealt out
+// to the threads of the CTA round-robin, so every warp gets the same amount of work whatever the number and size
+// of the edges in the tile (a warp-per-edge split left most warps waiting at the tile barrier).  A thread walks
+// its row along x.  Three tiers per voxel:
 //   1. fp32 broad phase in box-local coordinates -- rejects voxels whose exact contribution is <= 0 (88 %);
 //   2. fast float64 evaluation (fma, reciprocal instead of division): 255*I is accurate to ~1e-11, so its floor
 //      equals the reference's unless 255*I lies within 1e-7 of an integer or t within 1e-9 of {0,1};
 //   3. inside those guard bands (probability ~1e-7) the reference's exact operation chain decides.
-__device__ __forceinline__ void rasterize_edge_into_tile(const VoxEdge& e, const int t0[3], const int t1[3],
-                                                         const int T[3], uint32_t* acc, int lane) {
-    int b0[3], n[3];
+__device__ __forceinline__ void setup_edge(const VoxEdge& e, const int t0[3], const int t1[3], EdgeSm* o) {
+    int rows = 1;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        b0[a] = imax(e.lo[a], t0[a]);
-        n[a] = imin(e.hi[a], t1[a]) - b0[a];
-        if (n[a] <= 0) return;
+        o->b0[a] = imax(e.lo[a], t0[a]);
+        o->n[a] = imin(e.hi[a], t1[a]) - o->b0[a];
+        if (o->n[a] <= 0) rows = 0;
+        o->p1[a] = e.p1[a]; o->p2[a] = e.p2[a];
+        o->s[a] = e.p1[a] - e.p2[a];
     }
-    const int nrows = n[1] * n[2];
-    const float inv_nz = 1.0f / (float)n[2];
-    const double s0 = e.p1[0] - e.p2[0], s1 = e.p1[1] - e.p2[1], s2 = e.p1[2] - e.p2[2];
-    const double ss = (s0 * s0 + s1 * s1) + s2 * s2;
-    const double inv_ss = ss > 0.0 ? 1.0 / ss : 0.0;
+    o->rowbase = rows ? o->n[1] * o->n[2] : 0;
+    o->R = e.R;
+    const double ss = (o->s[0] * o->s[0] + o->s[1] * o->s[1]) + o->s[2] * o->s[2];
+    o->ss = ss;
+    o->inv_ss = ss > 0.0 ? 1.0 / ss : 0.0;
     const double SQRT3 = 1.7320508075688772, INV_SQRT3 = 0.57735026918962576;
-    const double c0 = 1.0 + (e.R - SQRT3 / 2) * INV_SQRT3;      // I = c0 - d/sqrt3
-    const double tguard = 1e-9 * ss;
-    // fp32 broad phase, coordinates relative to p2 shifted into the clipped box
-    const float a0 = (float)(e.p2[0] - (double)b0[0] - 0.5), a1 = (float)(e.p2[1] - (double)b0[1] - 0.5),
-                a2 = (float)(e.p2[2] - (double)b0[2] - 0.5);
-    const float f0 = (float)s0, f1 = (float)s1, f2 = (float)s2;
+    o->c0 = 1.0 + (e.R - SQRT3 / 2) * INV_SQRT3;      // I = c0 - d/sqrt3
+    o->tguard = 1e-9 * ss;
+    float ext = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        o->a[a] = (float)(e.p2[a] - (double)o->b0[a] - 0.5);
+        o->f[a] = (float)o->s[a];
+        ext += fabsf(o->a[a]) + fabsf(o->f[a]) + (float)(o->n[a] > 0 ? o->n[a] : 0);
+    }
     const float fss = (float)ss;
-    const float finv = fss > 0.f ? 1.0f / fss : 0.f;
-    const float ext = fabsf(a0) + fabsf(a1) + fabsf(a2) + fabsf(f0) + fabsf(f1) + fabsf(f2) + (float)(n[0] + n[1] + n[2]);
+    o->finv = fss > 0.f ? 1.0f / fss : 0.f;
     const float reach = (float)e.R + 0.8660254f + 0.02f + 8e-6f * ext;
-    const float thr = reach * reach;
-    for (int row = lane; row < nrows; row += 32) {
-        int iy = (int)((float)row * inv_nz);
-        int iz = row - iy * n[2];
-        if (iz < 0) { --iy; iz += n[2]; } else if (iz >= n[2]) { ++iy; iz -= n[2]; }
-        const float w1 = (float)iy - a1, w2 = (float)iz - a2;
-        const float dot12 = w1 * f1 + w2 * f2;
-        const double vy = (double)(b0[1] + iy) + 0.5, vz = (double)(b0[2] + iz) + 0.5;
-        uint32_t* arow = acc + ((b0[0] - t0[0]) * T[1] + (b0[1] + iy - t0[1])) * T[2] + (b0[2] + iz - t0[2]);
-        const int xstride = T[1] * T[2];
-        for (int ix = 0; ix < n[0]; ++ix) {
-            const float w0 = (float)ix - a0;
-            float tf = fmaf(w0, f0, dot12) * finv;
-            tf = fminf(fmaxf(tf, 0.f), 1.f);
-            const float d0 = fmaf(-tf, f0, w0), d1 = fmaf(-tf, f1, w1), d2 = fmaf(-tf, f2, w2);
-            if (fmaf(d0, d0, fmaf(d1, d1, d2 * d2)) > thr) continue;
-            // fast float64 evaluation
-            const double vx = (double)(b0[0] + ix) + 0.5;
-            const double u0 = vx - e.p2[0], u1 = vy - e.p2[1], u2 = vz - e.p2[2];
-            const double dot = fma(u2, s2, fma(u1, s1, u0 * s0));
-            uint32_t q;
-            if (fabs(dot) < tguard || fabs(dot - ss) < tguard) {
-                q = exact_voxel_q(e, vx, vy, vz);
+    o->thr = reach * reach;
+}
+
+__device__ __forceinline__ void rasterize_row(const EdgeSm& E, int row, const int t0[3], const int T[3], uint32_t* acc) {
+    const int nz = E.n[2];
+    int iy = (int)((float)row * (1.0f / (float)nz));
+    int iz = row - iy * nz;
+    if (iz < 0) { --iy; iz += nz; } else if (iz >= nz) { ++iy; iz -= nz; }
+    const float f0 = E.f[0], f1 = E.f[1], f2 = E.f[2], a0 = E.a[0], finv = E.finv, thr = E.thr;
+    const float w1 = (float)iy - E.a[1], w2 = (float)iz - E.a[2];
+    const float dot12 = w1 * f1 + w2 * f2;
+    const int bx = E.b0[0];
+    const double vy = (double)(E.b0[1] + iy) + 0.5, vz = (double)(E.b0[2] + iz) + 0.5;
+    uint32_t* arow = acc + ((bx - t0[0]) * T[1] + (E.b0[1] + iy - t0[1])) * T[2] + (E.b0[2] + iz - t0[2]);
+    const int xstride = T[1] * T[2];
+    const int nx = E.n[0];
+    for (int ix = 0; ix < nx; ++ix) {
+        const float w0 = (float)ix - a0;
+        float tf = fmaf(w0, f0, dot12) * finv;
+        tf = fminf(fmaxf(tf, 0.f), 1.f);
+        const float d0 = fmaf(-tf, f0, w0), d1 = fmaf(-tf, f1, w1), d2 = fmaf(-tf, f2, w2);
+        if (fmaf(d0, d0, fmaf(d1, d1, d2 * d2)) > thr) continue;
+        // fast float64 evaluation
+        const double vx = (double)(bx + ix) + 0.5;
+        const double s0 = E.s[0], s1 = E.s[1], s2 = E.s[2], ss = E.ss;
+        const double u0 = vx - E.p2[0], u1 = vy - E.p2[1], u2 = vz - E.p2[2];
+        const double dot = fma(u2, s2, fma(u1, s1, u0 * s0));
+        uint32_t q;
+        bool exact = fabs(dot) < E.tguard || fabs(dot - ss) < E.tguard;
+        if (!exact) {
+            double dd;
+            if (dot > 0.0 && dot < ss) {
+                const double t = dot * E.inv_ss;
+                const double e0 = fma(-t, s0, u0), e1 = fma(-t, s1, u1), e2 = fma(-t, s2, u2);
+                dd = fma(e2, e2, fma(e1, e1, e0 * e0));
             } else {
-                double dd;
-                if (dot > 0.0 && dot < ss) {
-                    const double t = dot * inv_ss;
-                    const double e0 = fma(-t, s0, u0), e1 = fma(-t, s1, u1), e2 = fma(-t, s2, u2);
-                    dd = fma(e2, e2, fma(e1, e1, e0 * e0));
-                } else {
-                    const double q0 = vx - e.p1[0], q1 = vy - e.p1[1], q2 = vz - e.p1[2];
-                    dd = fmin(fma(u2, u2, fma(u1, u1, u0 * u0)), fma(q2, q2, fma(q1, q1, q0 * q0)));
-                }
-                const double val = 255.0 * fma(-sqrt(dd), INV_SQRT3, c0);
-                if (val < -1e-7) continue;
-                const double fl = floor(val);
-                const double fr = val - fl;
-                if (fr < 1e-7 || fr > 1.0 - 1e-7 || !(val == val)) q = exact_voxel_q(e, vx, vy, vz);
-                else q = val >= 255.0 ? 255u : (uint32_t)fl;
+                const double q0 = vx - E.p1[0], q1 = vy - E.p1[1], q2 = vz - E.p1[2];
+                dd = fmin(fma(u2, u2, fma(u1, u1, u0 * u0)), fma(q2, q2, fma(q1, q1, q0 * q0)));
             }
-            if (q) atomicMax(arow + ix * xstride, q);
+            const double val = 255.0 * fma(-sqrt(dd), 0.57735026918962576, E.c0);
+            if (val < -1e-7) continue;
+            const double fl = floor(val);
+            const double fr = val - fl;
+            exact = fr < 1e-7 || fr > 1.0 - 1e-7 || !(val == val);
+            q = val >= 255.0 ? 255u : (uint32_t)fl;
         }
+        if (exact) {
+            VoxEdge e;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { e.p1[a] = E.p1[a]; e.p2[a] = E.p2[a]; }
+            e.R = E.R;
+            q = exact_voxel_q(e, vx, vy, vz);
+        }
+        if (q) atomicMax(arow + ix * xstride, q);
     }
 }
 
@@ -323,18 +350,36 @@ vox_tile_kernel(const VoxEdge* __restrict__ prep, const int64_t* __restrict__ ed
         for (int i = threadIdx.x; i < tile_elems / 4; i += blockDim.x) acc4[i] = make_uint4(0, 0, 0, 0);
         for (int i = (tile_elems / 4) * 4 + threadIdx.x; i < tile_elems; i += blockDim.x) acc[i] = 0;
         __syncthreads();
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        __shared__ EdgeSm es[EPASS];
+        __shared__ int s_total;
         const int* lst = tile_edges + (size_t)KBIG * e_base;
-        for (int k = beg + warp; k < end; k += nw) {
-            const VoxEdge e = ge[lst[k]];
-            rasterize_edge_into_tile(e, t0, t1, T, acc, lane);
-        }
         const int* bl = big_idx + e_base;
-        for (int k = warp; k < nbig; k += nw) {
-            const VoxEdge e = ge[bl[k]];
-            rasterize_edge_into_tile(e, t0, t1, T, acc, lane);
+        const int nlist = end - beg, nall = nlist + nbig;
+        for (int pass = 0; pass < nall; pass += EPASS) {
+            const int cnt = imin(EPASS, nall - pass);
+            if (threadIdx.x < cnt) {
+                const int k = pass + threadIdx.x;
+                const VoxEdge e = ge[k < nlist ? lst[beg + k] : bl[k - nlist]];
+                setup_edge(e, t0, t1, &es[threadIdx.x]);
+            }
+            __syncthreads();
+            if (threadIdx.x < 32) {           // exclusive prefix of the row counts of this pass
+                const int v = threadIdx.x < cnt ? es[threadIdx.x].rowbase : 0;
+                int x = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if ((int)threadIdx.x >= o) x += y; }
+                if (threadIdx.x < cnt) es[threadIdx.x].rowbase = x - v;
+                if (threadIdx.x == 31) s_total = x;
+            }
+            __syncthreads();
+            const int total = s_total;
+            for (int item = threadIdx.x; item < total; item += blockDim.x) {
+                int lo = 0, hi = cnt;             // last edge with rowbase <= item
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (es[mid].rowbase <= item) lo = mid; else hi = mid; }
+                rasterize_row(es[lo], item - es[lo].rowbase, t0, T, acc);
+            }
+            __syncthreads();
         }
-        __syncthreads();
     } else {
         // empty tile: stream zeros without touching shared memory
         uint16_t* vol = out + (size_t)gr * g.D[0] * g.D[1] * g.D[2];

@@ -35,7 +35,7 @@ class OctaGrowConfig(ctypes.Structure):
 class OctaGrowStats(ctypes.Structure):
     _fields_ = [(k, ctypes.c_int64) for k in ("n_art_nodes", "n_ven_nodes", "n_oxy_left", "n_co2_left", "py_draws",
                                               "sum_A", "sum_M", "sum_P", "sum_S")] + \
-        [("commit_cycles", ctypes.c_int64 * 4), ("err", ctypes.c_int32), ("n_iters", ctypes.c_int32)]
+        [("commit_cycles", ctypes.c_int64 * 4), ("replay_detail", ctypes.c_int64 * 8), ("err", ctypes.c_int32), ("n_iters", ctypes.c_int32)]
 
 
 def make_config(config: dict, cap_nodes: int = 0, cap_sinks: int = 0) -> OctaGrowConfig:
@@ -125,7 +125,7 @@ class GrowContext:
         rc = self.L.octa_grow_run(self._h, sd.ctypes.data, n, self._out.ctypes.data, self.cap_edges, na.ctypes.data,
                                   nv.ctypes.data, ctypes.cast(st, ctypes.c_void_p), tr.ctypes.data if trace else None,
                                   ctypes.byref(ms))
-        stats = [{k: (list(getattr(st[i], k)) if k == 'commit_cycles' else getattr(st[i], k)) for k, _ in OctaGrowStats._fields_} for i in range(n)]
+        stats = [{k: (list(getattr(st[i], k)) if k in ('commit_cycles', 'replay_detail') else getattr(st[i], k)) for k, _ in OctaGrowStats._fields_} for i in range(n)]
         if rc != 0:
             err = _lib.OctaError(rc, self.L.octa_last_error().decode(errors="replace"))
             err.stats = stats
