@@ -165,6 +165,8 @@ int octa_test_eig3(const double* cov9, double* w3, double* v9);
 int octa_test_eig3_debug(const double* cov9, double* w3, double* v9, double* dbg48);
 /* d_l of greenhouse.py:230-233: real part of the eigenvector of argmax(w); 0 ok, 2 no convergence, 3 complex principal pair */
 int octa_test_principal_axis(const double* cov9, double* dl3);
+/* cKDTree `tree.indices` permutation of n points given as SoA (element_mesh.py:97-101,136-137: ball-result order) */
+void octa_test_kd_indices(const double* x, const double* y, const double* z, int n, int* idx_out);
 /* CPython hash((np.float64 x, y, z)) (greenhouse.py:100-111 set ordering) */
 int64_t octa_test_hash_tuple3(const double* xyz);
 

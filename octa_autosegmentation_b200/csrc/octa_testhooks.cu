@@ -15,3 +15,8 @@ extern "C" int octa_test_eig3_debug(const double* cov9, double* w3, double* v9, 
 }
 
 extern "C" int octa_test_principal_axis(const double* cov9, double* dl3) { return octa::eig3::principal_axis(cov9, dl3); }
+
+#include "octa_kdorder.h"
+extern "C" void octa_test_kd_indices(const double* x, const double* y, const double* z, int n, int* idx_out) {
+    octa::kd::build_indices_seq(x, y, z, n, idx_out);
+}

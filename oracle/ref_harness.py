@@ -147,3 +147,18 @@ if __name__ == "__main__":
     if a.out:
         with open(a.out, "wb") as f:
             f.write(data)
+
+
+def nerve_config(I=(12, 12), N=600) -> dict:
+    """The 12x12 mm^2 'nerve' variant of example_custom_vessel_simulation.ipynb (cell at :137-160), shortened."""
+    cfg = load_config()
+    g = cfg["Greenhouse"]
+    g["param_scale"] = 12
+    cfg["Forest"]["type"] = "nerve"
+    cfg["output"]["image_scale_factor"] = 1216
+    g["SimulationSpace"]["no_voxel_z"] = 0.0033
+    g["d"] = 0.15
+    for m, i in zip(g["modes"], I):
+        m["I"], m["N"], m["delta_sigma"] = i, N, 0.002222
+    cfg["Forest"]["N_trees"] = 16
+    return cfg

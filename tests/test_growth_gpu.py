@@ -90,3 +90,53 @@ def test_batch_is_order_independent(growth):
     b, _, _ = growth.grow_batch(cfg, [9, 5])
     assert np.array_equal(a[0][0], b[1][0]) and np.array_equal(a[0][1], b[1][1])
     assert np.array_equal(a[2][0], b[0][0]) and np.array_equal(a[2][1], b[0][1])
+
+
+def test_nerve_forest_12x12_variant_vs_reference_csv(growth):
+    """Forest.type 'nerve', param_scale 12, 16 trees (example_custom_vessel_simulation.ipynb :137-160, shortened to
+    I = 70 + 50, N = 1500): the nerve disk is carved out of the sampling mask and the stumps start at the optic nerve."""
+    from octa_autosegmentation_b200.config import default_config
+    cfg = default_config()
+    g = cfg["Greenhouse"]
+    g["param_scale"] = 12
+    cfg["Forest"]["type"] = "nerve"
+    cfg["output"]["image_scale_factor"] = 1216
+    g["SimulationSpace"]["no_voxel_z"] = 0.0033
+    g["d"] = 0.15
+    for m, i in zip(g["modes"], (70, 50)):
+        m["I"], m["N"], m["delta_sigma"] = i, 1500, 0.002222
+    cfg["Forest"]["N_trees"] = 16
+    graphs, _ = compare_with_oracle(growth, cfg, [0, 1, 2])
+    assert numpy_csv(np.concatenate(graphs[0])) == open(os.path.join(GOLDEN, "graph_nerve_s0.csv"), "rb").read()
+
+
+def test_stress_config_vs_oracle(growth):
+    """BASELINE config #4 growth part: 4x attraction points (N = 8000 in both modes).  The reference needs ~4 min per
+    sample for this, so the pin is the oracle (byte-identical to the reference on every committed golden)."""
+    from octa_autosegmentation_b200.config import default_config
+    from oracle import growth_oracle as go
+    cfg = default_config()
+    for m in cfg["Greenhouse"]["modes"]:
+        m["N"] = 8000
+    graphs, stats, _ = growth.grow_batch(cfg, [0, 1], cap_edges=60000)
+    for seed, (art, ven) in zip((0, 1), graphs):
+        oa, ov, _ = go.run(cfg, seed, ball_order=1)
+        e, o = np.concatenate([art, ven]), np.concatenate([oa, ov])
+        assert e.shape == o.shape and np.array_equal(e[:, 6], o[:, 6]) and np.abs(e[:, :6] - o[:, :6]).max() < 1e-11
+    assert len(graphs[0][0]) + len(graphs[0][1]) == 16351      # edge count measured on the reference (SURVEY 8d, config #4)
+
+
+def test_round_robin_sharding_gives_identical_files(growth):
+    """BASELINE config #3 contract: sample i -> rank i mod world; outputs must be byte-identical to the 1-GPU run."""
+    from octa_autosegmentation_b200 import graph_io
+    from octa_autosegmentation_b200.pipeline import shard_seeds
+    cfg = small_config()
+    base, n = 40, 10
+    single, _, _ = growth.grow_batch(cfg, [base + i for i in range(n)])
+    ref = {base + i: graph_io.csv_bytes(np.concatenate(single[i])) for i in range(n)}
+    for world in (2, 4):
+        for rank in range(world):
+            seeds = shard_seeds(base, n, rank, world)
+            got, _, _ = growth.grow_batch(cfg, seeds)
+            for s, g in zip(seeds, got):
+                assert graph_io.csv_bytes(np.concatenate(g)) == ref[s]
