@@ -1,4 +1,5 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests/test_growth_gpu.py -x -q > gpurun_out/pytest_growth.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_growth.log
-tail -12 gpurun_out/pytest_growth.log
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 2 --warmup 3 > gpurun_out/bench2.log 2>&1; tail -1 gpurun_out/bench2.log | cut -c1-700
+timeout 600 python -m pytest tests/test_kdorder_gpu.py -x -q > gpurun_out/pytest_kd.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_kd.log
+tail -12 gpurun_out/pytest_kd.log
+timeout 900 python tools/grow_probe.py --batch 64 --check 24 --reps 2 > gpurun_out/grow_probe.log 2>&1
+head -4 gpurun_out/grow_probe.log; tail -1 gpurun_out/grow_probe.log

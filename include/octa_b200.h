@@ -167,6 +167,8 @@ int octa_test_eig3_debug(const double* cov9, double* w3, double* v9, double* dbg
 int octa_test_principal_axis(const double* cov9, double* dl3);
 /* cKDTree `tree.indices` permutation of n points given as SoA (element_mesh.py:97-101,136-137: ball-result order) */
 void octa_test_kd_indices(const double* x, const double* y, const double* z, int n, int* idx_out);
+/* the same permutation built by one CTA on the GPU (the block-parallel code path of the growth kernels) */
+int octa_test_kd_indices_gpu(const double* x, const double* y, const double* z, int n, int* idx_out);
 /* CPython hash((np.float64 x, y, z)) (greenhouse.py:100-111 set ordering) */
 int64_t octa_test_hash_tuple3(const double* xyz);
 

@@ -48,6 +48,7 @@ struct __align__(16) ActDec {  // decision record of one acting dict entry
 
 struct GrowShape {
     int G, capN, capS, Nmax, pycap;
+    int exact_ball_order;   // 1: rebuild cKDTree's index permutation for the O2->CO2 insertion order (exact); 0: list-index order
     int capN_smem;   // nodes per forest mirrored in k_commit's shared memory (larger forests fall back to the global path)
 };
 
@@ -90,6 +91,7 @@ struct GrowDev {
     TreeRec* rec[2];
     int *alist, *n_alist;
     int *hitj, *hl, *ta, *seq;
+    int *kd_idx, *kd_posL, *kd_posR, *kd_rank, *kd_nodes;
     unsigned char* veto;
     long long* set_hash;
     int* set_key;

@@ -8,6 +8,7 @@
 //   * edge rows in the reference's order (per tree, level order, children in attach order,
 //     generate_vessel_graph.py:45-56).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <thread>
@@ -223,6 +224,8 @@ void carve(Carver& c, const GrowShape& S, GrowDev* D) {
     D->rec[0] = c.take<TreeRec>(GN); D->rec[1] = c.take<TreeRec>(GN); D->alist = c.take<int>(GN); D->n_alist = c.take<int>(G);
     D->hitj = c.take<int>(GS); D->hl = c.take<int>(GS); D->ta = c.take<int>(GS); D->seq = c.take<int>(GS);
     D->veto = c.take<unsigned char>(GS);
+    D->kd_idx = c.take<int>(GS); D->kd_posL = c.take<int>(GS); D->kd_posR = c.take<int>(GS); D->kd_rank = c.take<int>(GS);
+    D->kd_nodes = c.take<int>(GS);
     D->set_hash = c.take<long long>(G * 2 * SET_TBL); D->set_key = c.take<int>(G * 2 * SET_TBL);
     D->err = c.take<int>(G); D->trace = c.take<int>(G * 4096 * 4); D->counters = c.take<long long>(G * 8); D->dbg = c.take<long long>(G * 8);
 }
@@ -341,6 +344,10 @@ extern "C" int octa_grow_create(const OctaGrowConfig* cfg, int max_graphs, void*
     S.capN = cfg->cap_nodes > 0 ? cfg->cap_nodes : (int)std::min<long>(1 << 20, std::max<long>(4096, align_up((size_t)(total_try / 16 + 4096), 1024)));
     S.capS = cfg->cap_sinks > 0 ? cfg->cap_sinks : (int)std::min<long>(1 << 20, std::max<long>(4096, align_up((size_t)(total_try / 12 + 4096), 1024)));
     S.pycap = 2 * S.capN + 4 * 624;
+    {
+        const char* bo = getenv("OCTA_BALL_ORDER");      // "index" = list-index order (diagnostics); default exact
+        S.exact_ball_order = (bo && strcmp(bo, "index") == 0) ? 0 : 1;
+    }
     S.capN_smem = std::min(S.capN, 46000);            // 46000 * (4 + 3/8) B = 197 KB of the 227 KB per CTA
     if (2 * cfg->n_trees > S.capN) { delete ctx; set_error("cap_nodes too small"); return OCTA_E_ARG; }
     Carver sizing(nullptr);

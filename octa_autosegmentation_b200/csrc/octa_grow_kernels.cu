@@ -16,6 +16,7 @@
 #include "octa_eig3.h"
 #include "octa_grow.cuh"
 #include "octa_grow_math.cuh"
+#include "octa_kdorder_par.cuh"
 
 namespace octa {
 
@@ -1084,14 +1085,30 @@ __global__ void __launch_bounds__(1024) k_kill(GrowDev D, GrowShape S, IterP P, 
             }
             __syncthreads();
             const int* ta = D.ta + sb;
+            // Within one ball the reference receives the hits in cKDTree order (ascending position in tree.indices,
+            // element_mesh.py:136-137).  The permutation is rebuilt exactly (octa_kdorder_par.cuh) whenever the
+            // order can matter, i.e. when at least two sinks are inserted.
+            const int* kdrank = nullptr;
+            if (S.exact_ball_order && T >= 2) {
+                int* kidx = D.kd_idx + sb;
+                kdpar::build_indices_block(sx, sy, sz, Sn, kidx, D.kd_posL + sb, D.kd_posR + sb, D.kd_nodes + sb,
+                                           D.kd_nodes + sb + S.capS / 2);
+                __syncthreads();
+                int* rk = D.kd_rank + sb;
+                for (int i = tid; i < Sn; i += blockDim.x) rk[kidx[i]] = i;
+                __syncthreads();
+                kdrank = rk;
+            }
             for (int q = tid; q < T; q += blockDim.x) {
                 const int i = ta[q];
                 const int ji = hitj[i];
+                const int ki = kdrank ? kdrank[i] : i;
                 int rank = 0;
                 for (int q2 = 0; q2 < T; ++q2) {
                     const int i2 = ta[q2];
                     const int j2 = hitj[i2];
-                    rank += (j2 < ji) || (j2 == ji && i2 < i);
+                    const int k2 = kdrank ? kdrank[i2] : i2;
+                    rank += (j2 < ji) || (j2 == ji && k2 < ki);
                 }
                 seq[rank] = i;
             }

@@ -20,3 +20,33 @@ extern "C" int octa_test_principal_axis(const double* cov9, double* dl3) { retur
 extern "C" void octa_test_kd_indices(const double* x, const double* y, const double* z, int n, int* idx_out) {
     octa::kd::build_indices_seq(x, y, z, n, idx_out);
 }
+
+#include "octa_kdorder_par.cuh"
+namespace {
+__global__ void __launch_bounds__(1024) kd_test_kernel(const double* x, const double* y, const double* z, int n, int* idx,
+                                                       int* posL, int* posR, int* nodes) {
+    octa::kdpar::build_indices_block(x, y, z, n, idx, posL, posR, nodes, nodes + n / 2 + 8);
+}
+}  // namespace
+
+// GPU build of the same permutation by one CTA (the code path k_kill uses); host buffers in/out.
+extern "C" int octa_test_kd_indices_gpu(const double* x, const double* y, const double* z, int n, int* idx_out) {
+    OCTA_ARG_CHECK(n >= 0 && idx_out, "bad arguments");
+    if (octa_device_count() <= 0) { octa::set_error("no CUDA device"); return OCTA_E_CUDA; }
+    if (n == 0) return OCTA_OK;
+    double* d = nullptr;
+    int* w = nullptr;
+    OCTA_CUDA_CHECK(cudaMalloc(&d, sizeof(double) * 3 * (size_t)n));
+    OCTA_CUDA_CHECK(cudaMalloc(&w, sizeof(int) * (4 * (size_t)n + 64)));
+    cudaMemcpy(d, x, 8 * (size_t)n, cudaMemcpyHostToDevice);
+    cudaMemcpy(d + n, y, 8 * (size_t)n, cudaMemcpyHostToDevice);
+    cudaMemcpy(d + 2 * (size_t)n, z, 8 * (size_t)n, cudaMemcpyHostToDevice);
+    kd_test_kernel<<<1, 1024>>>(d, d + n, d + 2 * (size_t)n, n, w, w + n, w + 2 * (size_t)n, w + 3 * (size_t)n);
+    octa::count_launch();
+    cudaError_t ce = cudaDeviceSynchronize();
+    if (ce == cudaSuccess) ce = cudaMemcpy(idx_out, w, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    cudaFree(w);
+    if (ce != cudaSuccess) { octa::set_error("kd_test_kernel: %s", cudaGetErrorString(ce)); return OCTA_E_CUDA; }
+    return OCTA_OK;
+}

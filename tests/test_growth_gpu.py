@@ -46,11 +46,11 @@ def compare_with_oracle(growth, cfg, seeds):
     graphs, stats, extra = growth.grow_batch(cfg, seeds, trace=True)
     for i, s in enumerate(seeds):
         art, ven = graphs[i]
-        oa, ov, ost = go.run(cfg, s, ball_order=1)       # list-index ball order (see DESIGN.md "ordering")
+        oa, ov, ost = go.run(cfg, s)                     # exact oracle: cKDTree ball-result order
         if len(art) != len(oa) or len(ven) != len(ov):
             # locate the first diverging iteration for the failure message
             tr = []
-            go.run(cfg, s, ball_order=1, trace=lambda t, a, o, v, c, pd, nd: tr.append((a, o, v, c)))
+            go.run(cfg, s, trace=lambda t, a, o, v, c, pd, nd: tr.append((a, o, v, c)))
             mine = extra["trace"][i]
             first = next((k for k in range(len(tr)) if tuple(mine[k]) != tr[k]), None)
             raise AssertionError("seed %d: edge counts differ (%d,%d) vs oracle (%d,%d); first diverging iteration %s: %s vs %s"
@@ -120,7 +120,7 @@ def test_stress_config_vs_oracle(growth):
         m["N"] = 8000
     graphs, stats, _ = growth.grow_batch(cfg, [0, 1], cap_edges=60000)
     for seed, (art, ven) in zip((0, 1), graphs):
-        oa, ov, _ = go.run(cfg, seed, ball_order=1)
+        oa, ov, _ = go.run(cfg, seed)
         e, o = np.concatenate([art, ven]), np.concatenate([oa, ov])
         assert e.shape == o.shape and np.array_equal(e[:, 6], o[:, 6]) and np.abs(e[:, :6] - o[:, :6]).max() < 1e-11
     assert len(graphs[0][0]) + len(graphs[0][1]) == 16351      # edge count measured on the reference
