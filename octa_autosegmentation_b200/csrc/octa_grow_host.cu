@@ -18,7 +18,8 @@
 
 namespace octa {
 
-void launch_iteration(const GrowDev& D, const GrowShape& S, const IterP& P, int n_sm, cudaStream_t st);
+void launch_iteration(const GrowDev& D, const GrowShape& S, const IterP& P, int n_sm, cudaStream_t st, cudaStream_t side,
+                      cudaEvent_t ev_sinks, cudaEvent_t ev_kd);
 int prepare_kernels(const GrowShape& S);
 
 namespace {
@@ -296,8 +297,12 @@ struct GrowCtx {
     int n_sm = 148;
     char* stage = nullptr;      // pinned host staging
     size_t stage_bytes = 0;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, ev_sinks = nullptr, ev_kd = nullptr;
+    cudaStream_t side = nullptr;
     ~GrowCtx() {
+        if (side) cudaStreamDestroy(side);
+        if (ev_sinks) cudaEventDestroy(ev_sinks);
+        if (ev_kd) cudaEventDestroy(ev_kd);
         if (dbase) cudaFree(dbase);
         if (stage) cudaFreeHost(stage);
         if (e0) cudaEventDestroy(e0);
@@ -365,6 +370,9 @@ extern "C" int octa_grow_create(const OctaGrowConfig* cfg, int max_graphs, void*
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, dev);
     if (prepare_kernels(S) != 0) { cudaGetLastError(); set_error("cudaFuncSetAttribute(k_commit) failed"); delete ctx; return OCTA_E_CUDA; }
+    cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_sinks, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_kd, cudaEventDisableTiming);
     cudaEventCreate(&ctx->e0);
     cudaEventCreate(&ctx->e1);
     *handle = ctx;
@@ -478,7 +486,7 @@ extern "C" int octa_grow_run(void* handle, const uint64_t* seeds, int n_graphs, 
     }
     if (!trace) D.trace = nullptr;
     OCTA_CUDA_CHECK(cudaEventRecord(ctx->e0, st));
-    for (const IterP& P : ctx->sched) launch_iteration(D, S, P, ctx->n_sm, st);
+    for (const IterP& P : ctx->sched) launch_iteration(D, S, P, ctx->n_sm, st, ctx->side, ctx->ev_sinks, ctx->ev_kd);
     OCTA_CUDA_CHECK(cudaEventRecord(ctx->e1, st));
     // ---- read back: counts first, then strided copies of the live prefix of every node array
     std::vector<int> err(n_graphs), nn[2], ns[2];

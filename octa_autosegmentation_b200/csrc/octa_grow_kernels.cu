@@ -1087,18 +1087,8 @@ __global__ void __launch_bounds__(1024) k_kill(GrowDev D, GrowShape S, IterP P, 
             const int* ta = D.ta + sb;
             // Within one ball the reference receives the hits in cKDTree order (ascending position in tree.indices,
             // element_mesh.py:136-137).  The permutation is rebuilt exactly (octa_kdorder_par.cuh) whenever the
-            // order can matter, i.e. when at least two sinks are inserted.
-            const int* kdrank = nullptr;
-            if (S.exact_ball_order && T >= 2) {
-                int* kidx = D.kd_idx + sb;
-                kdpar::build_indices_block(sx, sy, sz, Sn, kidx, D.kd_posL + sb, D.kd_posR + sb, D.kd_nodes + sb,
-                                           D.kd_nodes + sb + S.capS / 2);
-                __syncthreads();
-                int* rk = D.kd_rank + sb;
-                for (int i = tid; i < Sn; i += blockDim.x) rk[kidx[i]] = i;
-                __syncthreads();
-                kdrank = rk;
-            }
+            // sink list changes (k_kdbuild, overlapped with the arterial growth kernels on a second stream).
+            const int* kdrank = S.exact_ball_order ? D.kd_rank + sb : nullptr;   // built by k_kdbuild on the side stream
             for (int q = tid; q < T; q += blockDim.x) {
                 const int i = ta[q];
                 const int ji = hitj[i];
@@ -1196,6 +1186,24 @@ __global__ void __launch_bounds__(1024) k_kill(GrowDev D, GrowShape S, IterP P, 
 }
 
 // ------------------------------------------------------------------------------------------
+// k_kdbuild: one CTA per graph; cKDTree index permutation of the O2 sink list as it stands after sampling
+// (= the tree the reference queries in step 3, greenhouse.py:101-102).  Runs on a side stream, concurrently with
+// the arterial growth kernels, which do not modify the sink list.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_kdbuild(GrowDev D, GrowShape S) {
+    const int g = blockIdx.x, tid = threadIdx.x;
+    if (D.err[g]) return;
+    const size_t sb = (size_t)g * S.capS;
+    const int Sn = D.n_s[0][g];
+    int* kidx = D.kd_idx + sb;
+    kdpar::build_indices_block(D.sx[0] + sb, D.sy[0] + sb, D.sz[0] + sb, Sn, kidx, D.kd_posL + sb, D.kd_posR + sb,
+                               D.kd_nodes + sb, D.kd_nodes + sb + S.capS / 2);
+    __syncthreads();
+    int* rk = D.kd_rank + sb;
+    for (int i = tid; i < Sn; i += blockDim.x) rk[kidx[i]] = i;
+}
+
+// ------------------------------------------------------------------------------------------
 // launch wrappers (called from octa_grow_host.cu)
 // ------------------------------------------------------------------------------------------
 size_t commit_smem_bytes(const GrowShape& S) { return sizeof(int) * ((size_t)S.capN_smem + 3 * (((size_t)S.capN_smem + 31) >> 5)); }
@@ -1204,13 +1212,21 @@ int prepare_kernels(const GrowShape& S) {
     return (int)cudaFuncSetAttribute(k_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)commit_smem_bytes(S));
 }
 
-void launch_iteration(const GrowDev& D, const GrowShape& S, const IterP& P, int n_sm, cudaStream_t st) {
+void launch_iteration(const GrowDev& D, const GrowShape& S, const IterP& P, int n_sm, cudaStream_t st, cudaStream_t side,
+                      cudaEvent_t ev_sinks, cudaEvent_t ev_kd) {
     k_sample<<<S.G, 1024, 0, st>>>(D, S, P);
     k_grid_build<<<S.G, 1024, 0, st>>>(D, S, 0);
     k_grid_build<<<S.G, 1024, 0, st>>>(D, S, 1);
     k_sink_tests<<<n_sm * 8, TILE, 0, st>>>(D, S, P);
     k_sink_greedy<<<S.G, 1024, 0, st>>>(D, S, P);
     count_launch(5);
+    if (S.exact_ball_order) {
+        cudaEventRecord(ev_sinks, st);
+        cudaStreamWaitEvent(side, ev_sinks, 0);
+        k_kdbuild<<<S.G, 1024, 0, side>>>(D, S);
+        cudaEventRecord(ev_kd, side);
+        count_launch(1);
+    }
     for (int f = 0; f < 2; ++f) {
         k_grid_build<<<S.G, 1024, 0, st>>>(D, S, 2 + f);
         count_launch(1);
@@ -1218,6 +1234,7 @@ void launch_iteration(const GrowDev& D, const GrowShape& S, const IterP& P, int 
         k_group<<<S.G, 1024, 0, st>>>(D, S, P, f);
         k_eval<<<dim3(16, S.G), 128, 0, st>>>(D, S, P, f);
         k_commit<<<S.G, 256, commit_smem_bytes(S), st>>>(D, S, P, f);
+        if (f == 0 && S.exact_ball_order) cudaStreamWaitEvent(st, ev_kd, 0);
         k_kill<<<S.G, 1024, 0, st>>>(D, S, P, f);
         count_launch(5);
     }
