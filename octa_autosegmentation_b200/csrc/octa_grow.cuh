@@ -93,6 +93,7 @@ struct GrowDev {
     int *hitj, *hl, *ta, *seq;
     int *kd_idx, *kd_posL, *kd_posR, *kd_rank, *kd_nodes;
     unsigned char* veto;
+    long long* seqhash;
     long long* set_hash;
     int* set_key;
     int* err;

@@ -305,7 +305,9 @@ __global__ void __launch_bounds__(1024) k_sink_greedy(GrowDev D, GrowShape S, It
     const double* cx = D.cx + (size_t)g * S.Nmax; const double* cy = D.cy + (size_t)g * S.Nmax; const double* cz = D.cz + (size_t)g * S.Nmax;
     const unsigned char* cp = D.cpass + (size_t)g * S.Nmax;
     int* pl = D.plist + (size_t)g * S.Nmax;
-    volatile unsigned char* state = D.cstate + (size_t)g * S.Nmax;
+    // decision state per passing candidate: shared memory (read by every other candidate every round)
+    __shared__ unsigned char s_state[8192];
+    volatile unsigned char* state = (S.Nmax <= 8192) ? (volatile unsigned char*)s_state : (volatile unsigned char*)(D.cstate + (size_t)g * S.Nmax);
     int np_ = 0;
     for (int base = 0; base < nc; base += blockDim.x) {
         const int i = base + tid;
@@ -1101,20 +1103,30 @@ __global__ void __launch_bounds__(1024) k_kill(GrowDev D, GrowShape S, IterP P, 
                     rank += (j2 < ji) || (j2 == ji && k2 < ki);
                 }
                 seq[rank] = i;
+                D.seqhash[sb + rank] = py_hash_tuple3(sx[i], sy[i], sz[i]);   // CPython hash of the sink tuple, in parallel
             }
             __syncthreads();
-            // CPython set emulation (Objects/setobject.c, 3.12) -> iteration order = slot order
-            long long* th = D.set_hash + (size_t)g * 2 * SET_TBL;
-            int* tk = D.set_key + (size_t)g * 2 * SET_TBL;
-            for (int i = tid; i < 8; i += blockDim.x) { tk[i] = -1; th[i] = 0; }
+            // CPython set emulation (Objects/setobject.c, 3.12) -> iteration order = slot order.  Tables of up to
+            // SM_TBL slots live in shared memory (the usual case: tens of insertions); larger ones spill to global.
+            constexpr int SM_TBL = 1024;
+            __shared__ long long s_th[2][SM_TBL];
+            __shared__ int s_tk[2][SM_TBL];
+            __shared__ int s_tabinfo[3];                 // which table holds the result (0/1 smem, 2/3 global), mask, err
+            long long* gth = D.set_hash + (size_t)g * 2 * SET_TBL;
+            int* gtk = D.set_key + (size_t)g * 2 * SET_TBL;
+            for (int i = tid; i < 8; i += blockDim.x) { s_tk[0][i] = -1; s_th[0][i] = 0; }
             __syncthreads();
-            if (tid == 0 && T > 0) {
+            if (tid == 0) {
                 size_t mask = 7, fill = 0, used = 0;
-                long long* curh = th; int* curk = tk;
-                long long* alth = th + SET_TBL; int* altk = tk + SET_TBL;
-                for (int q = 0; q < T; ++q) {
+                int cur = 0;                             // 0/1: shared tables, 2/3: global tables
+                auto tabh = [&](int t) -> long long* { return t < 2 ? s_th[t] : gth + (size_t)(t - 2) * SET_TBL; };
+                auto tabk = [&](int t) -> int* { return t < 2 ? s_tk[t] : gtk + (size_t)(t - 2) * SET_TBL; };
+                long long* curh = tabh(0); int* curk = tabk(0);
+                int err = 0;
+                const long long* sh = D.seqhash + sb;
+                for (int q = 0; q < T && !err; ++q) {
                     const int key = seq[q];
-                    const long long hash = py_hash_tuple3(sx[key], sy[key], sz[key]);
+                    const long long hash = sh[q];
                     size_t perturb = (size_t)hash, i = (size_t)hash & mask;
                     bool done = false;
                     while (!done) {
@@ -1128,12 +1140,13 @@ __global__ void __launch_bounds__(1024) k_kill(GrowDev D, GrowShape S, IterP P, 
                                     const size_t minused = used > 50000 ? used * 2 : used * 4;
                                     size_t newsize = 8;
                                     while (newsize <= minused) newsize <<= 1;
-                                    if (newsize > (size_t)SET_TBL) { D.err[g] = 5; done = true; break; }
+                                    if (newsize > (size_t)SET_TBL) { err = 5; done = true; break; }
+                                    const int alt = newsize <= (size_t)SM_TBL ? (cur == 0 ? 1 : 0) : (cur == 2 ? 3 : 2);
+                                    long long* alth = tabh(alt); int* altk = tabk(alt);
                                     for (size_t z = 0; z < newsize; ++z) { altk[z] = -1; alth[z] = 0; }
                                     for (size_t z = 0; z <= mask; ++z)
                                         if (curk[z] >= 0) pyset_insert_clean(alth, altk, newsize - 1, curk[z], curh[z]);
-                                    long long* t1 = curh; curh = alth; alth = t1;
-                                    int* t2 = curk; curk = altk; altk = t2;
+                                    cur = alt; curh = alth; curk = altk;
                                     mask = newsize - 1;
                                     fill = used;
                                 }
@@ -1147,19 +1160,29 @@ __global__ void __launch_bounds__(1024) k_kill(GrowDev D, GrowShape S, IterP P, 
                         perturb >>= 5;
                         i = (i * 5 + 1 + perturb) & mask;
                     }
-                    if (D.err[g]) break;
                 }
-                // append to the CO2 list in slot order
+                s_tabinfo[0] = cur; s_tabinfo[1] = (int)mask; s_tabinfo[2] = err;
+                if (err) D.err[g] = err;
+            }
+            __syncthreads();
+            // append to the CO2 list in slot order (all threads: stable compaction of the occupied slots)
+            if (!s_tabinfo[2] && T > 0) {
+                const int cur = s_tabinfo[0], nslots = s_tabinfo[1] + 1;
+                const int* curk = cur < 2 ? s_tk[cur] : gtk + (size_t)(cur - 2) * SET_TBL;
                 int nco2 = D.n_s[1][g];
                 const size_t cb = (size_t)g * S.capS;
-                for (size_t z = 0; z <= mask; ++z)
-                    if (curk[z] >= 0) {
-                        if (nco2 >= S.capS) { D.err[g] = 2; break; }
-                        const int key = curk[z];
-                        D.sx[1][cb + nco2] = sx[key]; D.sy[1][cb + nco2] = sy[key]; D.sz[1][cb + nco2] = sz[key];
-                        ++nco2;
+                for (int base = 0; base < nslots; base += blockDim.x) {
+                    const int zslot = base + tid;
+                    const int key = zslot < nslots ? curk[zslot] : -1;
+                    int total;
+                    const int incl = block_scan_incl(key >= 0, &total);
+                    if (key >= 0) {
+                        const int o = nco2 + incl - 1;
+                        if (o < S.capS) { D.sx[1][cb + o] = sx[key]; D.sy[1][cb + o] = sy[key]; D.sz[1][cb + o] = sz[key]; }
                     }
-                D.n_s[1][g] = nco2;
+                    nco2 += total;
+                }
+                if (tid == 0) { if (nco2 > S.capS) { D.err[g] = 2; nco2 = S.capS; } D.n_s[1][g] = nco2; }
             }
             __syncthreads();
         }
