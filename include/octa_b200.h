@@ -142,6 +142,11 @@ int octa_grow_batch_host(const OctaGrowConfig* cfg, const uint64_t* seeds, int n
 int octa_grow_create(const OctaGrowConfig* cfg, int max_graphs, void** handle);
 int octa_grow_run(void* handle, const uint64_t* seeds, int n_graphs, double* edges7_out, int64_t cap_edges_per_graph,
                   int64_t* n_art_edges, int64_t* n_ven_edges, OctaGrowStats* stats, int32_t* trace, double* device_ms);
+/* Same, but the rows of all graphs are packed back to back into edges7_out (capacity cap_total_edges rows, e.g. a pinned
+ * host buffer that is then copied to the device in one piece); edge_offsets[0..n_graphs] receives the row offsets. */
+int octa_grow_run_packed(void* handle, const uint64_t* seeds, int n_graphs, double* edges7_out, int64_t cap_total_edges,
+                         int64_t* edge_offsets, int64_t* n_art_edges, int64_t* n_ven_edges, OctaGrowStats* stats,
+                         int32_t* trace, double* device_ms);
 void octa_grow_destroy(void* handle);
 
 /* ------------------------------------------------------------------------------------------------

@@ -91,6 +91,95 @@ void scientific(double x, int prec, std::string* ip, std::string* fp, int* e10) 
     if (s.neg) ip->insert(ip->begin(), '-');
 }
 
+// |x| * 10^8 rounded to the nearest integer, ties to even, EXACTLY (128-bit integer arithmetic on the binary value):
+// the digits numpy's Dragon4 prints for precision=8 in positional mode.  When the shortest round-trip
+// representation has <= 8 fractional digits it is a multiple of 1e-8 closer to x than half an ulp, so it is also
+// what this rounding returns (after trimming zeros) -- no separate shortest-digits search is needed.
+// Valid for 2^-60 < |x| < 2^20 (always true for unit-cube coordinates); returns false otherwise.
+bool fixed8(double x, uint64_t* q_out) {
+    const double ax = fabs(x);
+    if (!(ax < 1048576.0)) return false;
+    if (ax == 0.0) { *q_out = 0; return true; }
+    uint64_t bits;
+    memcpy(&bits, &ax, 8);
+    const int be = (int)(bits >> 52);
+    if (be == 0) return false;                             // subnormal: leave to the generic path
+    const uint64_t m = (bits & 0xfffffffffffffull) | (1ull << 52);   // ax = m * 2^(be-1075)
+    const int s = 1075 - be;                               // ax = m / 2^s
+    if (s <= 0 || s > 113) return false;
+    const unsigned __int128 N = (unsigned __int128)m * 100000000u;
+    const unsigned __int128 one = 1;
+    unsigned __int128 q = N >> s;
+    const unsigned __int128 rem = N & ((one << s) - 1), half = one << (s - 1);
+    if (rem > half || (rem == half && (q & 1))) ++q;
+    *q_out = (uint64_t)q;
+    return true;
+}
+
+static const char DIG2[201] =
+    "00010203040506070809101112131415161718192021222324252627282930313233343536373839404142434445464748495051525354555657585960616263646566676869707172737475767778798081828384858687888990919293949596979899";
+
+// writes the integer / fraction digit strings of q = round(|x| * 1e8); fraction trimmed of trailing zeros
+inline void fixed8_digits(uint64_t q, bool neg, char* ip, int* ilen, char* fp, int* flen) {
+    uint64_t ipart = q / 100000000u;
+    uint32_t f = (uint32_t)(q % 100000000u);
+    int k = 0;
+    if (neg) ip[k++] = '-';
+    if (ipart < 10) ip[k++] = (char)('0' + ipart);
+    else {
+        char tmp[24];
+        int n = 0;
+        do { tmp[n++] = (char)('0' + ipart % 10); ipart /= 10; } while (ipart);
+        while (n) ip[k++] = tmp[--n];
+    }
+    *ilen = k;
+    const uint32_t hi = f / 10000u, lo = f % 10000u;
+    memcpy(fp, DIG2 + 2 * (hi / 100u), 2); memcpy(fp + 2, DIG2 + 2 * (hi % 100u), 2);
+    memcpy(fp + 4, DIG2 + 2 * (lo / 100u), 2); memcpy(fp + 6, DIG2 + 2 * (lo % 100u), 2);
+    int fl = 8;
+    while (fl > 0 && fp[fl - 1] == '0') --fl;
+    *flen = fl;
+}
+
+// 9 significant digits of |x| (d.dddddddd x 10^e10), exactly rounded on the binary value (ties to even): what
+// Dragon4 prints for dragon4_scientific(precision=8).  Valid for 1e-30 < |x| < 1e8; returns false otherwise.
+bool sci9(double x, uint64_t* q_out, int* e10_out) {
+    static const uint64_t P10[20] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull, 100000000ull,
+                                     1000000000ull, 10000000000ull, 100000000000ull, 1000000000000ull, 10000000000000ull,
+                                     100000000000000ull, 1000000000000000ull, 10000000000000000ull, 100000000000000000ull,
+                                     1000000000000000000ull, 10000000000000000000ull};
+    const double ax = fabs(x);
+    if (!(ax > 1e-11 && ax < 1e8)) return false;
+    uint64_t bits;
+    memcpy(&bits, &ax, 8);
+    const int be = (int)(bits >> 52);
+    if (be == 0) return false;
+    const uint64_t m = (bits & 0xfffffffffffffull) | (1ull << 52);
+    const int s = 1075 - be;                               // ax = m / 2^s, s in (26, 90)
+    const int e = be - 1022;                               // ax = fr * 2^e with fr in [0.5, 1)
+    int e10 = (int)floor((e - 1) * 0.30102999566398120);   // floor(log10(ax)) or one less
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        const int k = 8 - e10;                             // scale by 10^k
+        if (k < 0 || k > 19 || s <= 0 || s > 120) return false;
+        const unsigned __int128 N = (unsigned __int128)m * P10[k];
+        const unsigned __int128 one = 1;
+        unsigned __int128 q = N >> s;
+        const unsigned __int128 rem = N & ((one << s) - 1), half = one << (s - 1);
+        if (rem > half || (rem == half && (q & 1))) ++q;
+        if (q >= 1000000000u) {
+            // either e10 was one too small, or rounding carried into a 10th digit (d = 9.99999999(5+) -> 1.00000000 e+1)
+            const unsigned __int128 lo = (unsigned __int128)1000000000u << s;
+            if (N >= lo) { ++e10; continue; }              // genuinely >= 10^(e10+1)
+            *q_out = 100000000u; *e10_out = e10 + 1;
+            return true;
+        }
+        if (q < 100000000u) { --e10; continue; }
+        *q_out = (uint64_t)q; *e10_out = e10;
+        return true;
+    }
+    return false;
+}
+
 void append_array3(std::string& out, const double* v) {
     // FloatingFormat.fillFormat
     double mx = 0, mn = 0;
@@ -100,6 +189,72 @@ void append_array3(std::string& out, const double* v) {
         if (a != 0.0) { if (!any) { mx = mn = a; any = true; } else { if (a > mx) mx = a; if (a < mn) mn = a; } }
     }
     const bool exp_format = any && (mx >= 1.e8 || mn < 0.0001 || mx / mn > 1000.);
+    if (!exp_format) {
+        uint64_t q[3];
+        if (fixed8(v[0], &q[0]) && fixed8(v[1], &q[1]) && fixed8(v[2], &q[2])) {
+            char ipb[3][24], fpb[3][8];
+            int il[3], fl[3], pl = 0, pr = 0;
+            for (int i = 0; i < 3; ++i) {
+                fixed8_digits(q[i], signbit(v[i]) && q[i] != 0 ? true : signbit(v[i]), ipb[i], &il[i], fpb[i], &fl[i]);
+                if (il[i] > pl) pl = il[i];
+                if (fl[i] > pr) pr = fl[i];
+            }
+            char line[128];
+            int k = 0;
+            line[k++] = '[';
+            for (int i = 0; i < 3; ++i) {
+                if (i) line[k++] = ' ';
+                for (int p = il[i]; p < pl; ++p) line[k++] = ' ';
+                memcpy(line + k, ipb[i], il[i]); k += il[i];
+                line[k++] = '.';
+                memcpy(line + k, fpb[i], fl[i]); k += fl[i];
+                for (int p = fl[i]; p < pr; ++p) line[k++] = ' ';
+            }
+            line[k++] = ']';
+            out.append(line, k);
+            return;
+        }
+    }
+    if (exp_format) {
+        uint64_t q[3];
+        int ex[3];
+        bool ok = true;
+        for (int i = 0; i < 3 && ok; ++i) {
+            if (v[i] == 0.0) { q[i] = 0; ex[i] = 0; } else ok = sci9(v[i], &q[i], &ex[i]);
+        }
+        if (ok) {
+            char dg[3][10];
+            int fl[3], pl = 1, prec = 0, exp_size = 2;
+            for (int i = 0; i < 3; ++i) {
+                uint64_t t = q[i];
+                for (int d = 8; d >= 0; --d) { dg[i][d] = (char)('0' + t % 10); t /= 10; }
+                int f = 8;
+                while (f > 0 && dg[i][f] == '0') --f;          // trimmed fraction length (digits 1..f)
+                fl[i] = f;
+                if (f > prec) prec = f;
+                if (signbit(v[i])) pl = 2;
+                int a = abs(ex[i]), nd = 1;
+                while (a >= 10) { a /= 10; ++nd; }
+                if (nd > exp_size) exp_size = nd;
+            }
+            char line[160];
+            int k = 0;
+            line[k++] = '[';
+            for (int i = 0; i < 3; ++i) {
+                if (i) line[k++] = ' ';
+                const bool neg = signbit(v[i]);
+                if (pl == 2 && !neg) line[k++] = ' ';
+                if (neg) line[k++] = '-';
+                line[k++] = dg[i][0];
+                line[k++] = '.';
+                for (int d = 1; d <= prec; ++d) line[k++] = d <= fl[i] ? dg[i][d] : '0';
+                k += snprintf(line + k, 16, "e%c%0*d", ex[i] < 0 ? '-' : '+', exp_size, abs(ex[i]));
+            }
+            line[k++] = ']';
+            out.append(line, k);
+            return;
+        }
+    }
     std::string ip[3], fp[3];
     out.push_back('[');
     if (!exp_format) {
@@ -142,6 +297,17 @@ void append_array3(std::string& out, const double* v) {
 
 // Python repr(float)
 void append_repr(std::string& out, double x) {
+    const double axr = fabs(x);
+    if (axr >= 1e-4 && axr < 1e16) {
+        // fixed notation range of float_repr_style 'short': shortest round-trip digits, plain positional
+        char b[40];
+        auto r = std::to_chars(b, b + sizeof(b), x, std::chars_format::fixed);
+        bool dot = false;
+        for (char* c = b; c != r.ptr; ++c) if (*c == '.') { dot = true; break; }
+        out.append(b, r.ptr - b);
+        if (!dot) out += ".0";
+        return;
+    }
     if (x != x) { out += "nan"; return; }
     if (isinf(x)) { out += x < 0 ? "-inf" : "inf"; return; }
     const Sci s = shortest(x);

@@ -49,7 +49,7 @@ struct __align__(16) ActDec {  // decision record of one acting dict entry
 struct GrowShape {
     int G, capN, capS, Nmax, pycap;
     int exact_ball_order;   // 1: rebuild cKDTree's index permutation for the O2->CO2 insertion order (exact); 0: list-index order
-    int capN_smem;   // nodes per forest mirrored in k_commit's shared memory (larger forests fall back to the global path)
+    int commit_smem; // bytes of dynamic shared memory of k_commit (parent/dirty/tag mirrors + decision records)
 };
 
 struct GrowDev {

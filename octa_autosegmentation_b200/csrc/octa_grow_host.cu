@@ -359,7 +359,7 @@ extern "C" int octa_grow_create(const OctaGrowConfig* cfg, int max_graphs, void*
         const char* bo = getenv("OCTA_BALL_ORDER");      // "index" = list-index order (diagnostics); default exact
         S.exact_ball_order = (bo && strcmp(bo, "index") == 0) ? 0 : 1;
     }
-    S.capN_smem = std::min(S.capN, 46000);            // 46000 * (4 + 3/8) B = 197 KB of the 227 KB per CTA
+    S.commit_smem = 224 * 1024;                       // of the 227 KB a CTA may own on sm_100
     if (2 * cfg->n_trees > S.capN) { delete ctx; set_error("cap_nodes too small"); return OCTA_E_ARG; }
     Carver sizing(nullptr);
     carve(sizing, S, &ctx->D);
@@ -387,9 +387,11 @@ extern "C" int octa_grow_create(const OctaGrowConfig* cfg, int max_graphs, void*
 
 extern "C" void octa_grow_destroy(void* handle) { delete (GrowCtx*)handle; }
 
-extern "C" int octa_grow_run(void* handle, const uint64_t* seeds, int n_graphs, double* edges7_out, int64_t cap_edges,
-                             int64_t* n_art_edges, int64_t* n_ven_edges, OctaGrowStats* stats, int32_t* trace,
-                             double* device_ms) {
+static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, double* edges7_out, int64_t cap_edges,
+                         int64_t* n_art_edges, int64_t* n_ven_edges, OctaGrowStats* stats, int32_t* trace,
+                         double* device_ms, int64_t* packed_offsets) {
+    // packed_offsets != NULL: rows are packed back to back (cap_edges = total capacity) and packed_offsets[0..n] receives
+    // the row offsets; otherwise graph g owns the fixed slab edges7_out + g*cap_edges*7.
     GrowCtx* ctx = (GrowCtx*)handle;
     OCTA_ARG_CHECK(ctx && seeds && n_graphs > 0 && n_graphs <= ctx->S.G, "bad arguments (n_graphs must not exceed the context size)");
     OCTA_ARG_CHECK(edges7_out && cap_edges > 0 && n_art_edges && n_ven_edges, "output buffers missing");
@@ -533,21 +535,34 @@ extern "C" int octa_grow_run(void* handle, const uint64_t* seeds, int n_graphs, 
         OCTA_CUDA_CHECK(dn2d(so[f][3], D.npar[f], 4)); OCTA_CUDA_CHECK(dn2d(so[f][4], D.nmeta[f], 1));
     }
     OCTA_CUDA_CHECK(cudaStreamSynchronize(st));
+    std::vector<int64_t> row0(n_graphs + 1, 0);
+    if (packed_offsets) {
+        // every non-root node is one row; roots = N_trees per forest
+        for (int g = 0; g < n_graphs; ++g)
+            row0[g + 1] = row0[g] + std::max(0, nn[0][g] - cfg.n_trees) + std::max(0, nn[1][g] - cfg.n_trees);
+        for (int g = 0; g <= n_graphs; ++g) packed_offsets[g] = row0[g];
+        if (row0[n_graphs] > cap_edges) {
+            set_error("octa_grow_run_packed: edge buffer too small (%lld rows needed, %lld available)",
+                      (long long)row0[n_graphs], (long long)cap_edges);
+            return OCTA_E_NOMEM;
+        }
+    }
     // ---- exact radii + edge rows, multi-threaded over graphs
     unsigned nthreads = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)n_graphs));
     std::vector<std::thread> pool;
     for (unsigned wk = 0; wk < nthreads; ++wk)
         pool.emplace_back([&, wk]() {
             for (int g = (int)wk; g < n_graphs; g += (int)nthreads) {
-                double* out = edges7_out + (size_t)g * cap_edges * 7;
+                double* out = packed_offsets ? edges7_out + (size_t)row0[g] * 7 : edges7_out + (size_t)g * cap_edges * 7;
+                const int64_t cap_g = packed_offsets ? row0[g + 1] - row0[g] : cap_edges;
                 int64_t cnt[2] = {0, 0};
                 int64_t used = 0;
                 for (int f = 0; f < 2; ++f) {
                     const size_t w = mx[f];
                     finalize_forest(cfg, nn[f][g], (const double*)(sg + so[f][0]) + g * w, (const double*)(sg + so[f][1]) + g * w,
                                     (const double*)(sg + so[f][2]) + g * w, (const int*)(sg + so[f][3]) + g * w,
-                                    (const unsigned char*)(sg + so[f][4]) + g * w, out + 7 * used, cap_edges - used, &cnt[f]);
-                    used = std::min<int64_t>(cap_edges, used + cnt[f]);
+                                    (const unsigned char*)(sg + so[f][4]) + g * w, out + 7 * used, cap_g - used, &cnt[f]);
+                    used = std::min<int64_t>(cap_g, used + cnt[f]);
                 }
                 n_art_edges[g] = cnt[0];
                 n_ven_edges[g] = cnt[1];
@@ -567,7 +582,8 @@ extern "C" int octa_grow_run(void* handle, const uint64_t* seeds, int n_graphs, 
             s.err = err[g]; s.n_iters = (int)ctx->sched.size();
         }
         if (err[g] && !worst) worst = err[g];
-        if (n_art_edges[g] + n_ven_edges[g] > cap_edges && !worst) worst = 100;
+        if (!packed_offsets && n_art_edges[g] + n_ven_edges[g] > cap_edges && !worst) worst = 100;
+        if (packed_offsets && n_art_edges[g] + n_ven_edges[g] != row0[g + 1] - row0[g] && !worst) worst = 101;
     }
     if (worst) {
         set_error("octa_grow_run: simulation error code %d (1 node capacity, 2 sink capacity, 3 rng buffer, "
@@ -575,6 +591,20 @@ extern "C" int octa_grow_run(void* handle, const uint64_t* seeds, int n_graphs, 
         return OCTA_E_STATE;
     }
     return OCTA_OK;
+}
+
+extern "C" int octa_grow_run(void* handle, const uint64_t* seeds, int n_graphs, double* edges7_out, int64_t cap_edges,
+                             int64_t* n_art_edges, int64_t* n_ven_edges, OctaGrowStats* stats, int32_t* trace,
+                             double* device_ms) {
+    return grow_run_impl(handle, seeds, n_graphs, edges7_out, cap_edges, n_art_edges, n_ven_edges, stats, trace, device_ms, nullptr);
+}
+
+extern "C" int octa_grow_run_packed(void* handle, const uint64_t* seeds, int n_graphs, double* edges7_out,
+                                    int64_t cap_total_edges, int64_t* edge_offsets, int64_t* n_art_edges,
+                                    int64_t* n_ven_edges, OctaGrowStats* stats, int32_t* trace, double* device_ms) {
+    OCTA_ARG_CHECK(edge_offsets, "edge_offsets is null");
+    return grow_run_impl(handle, seeds, n_graphs, edges7_out, cap_total_edges, n_art_edges, n_ven_edges, stats, trace, device_ms,
+                         edge_offsets);
 }
 
 extern "C" int octa_grow_batch_host(const OctaGrowConfig* cfg, const uint64_t* seeds, int n_graphs, double* edges7_out,

@@ -720,21 +720,28 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
     const size_t sb = (size_t)g * S.capS, nb = (size_t)g * S.capN;
     const int nd_ = D.n_dict[g];
     Proposal* prop = D.prop + nb;
-    ActDec* adec = D.adec + nb;
+    ActDec* adec = D.adec + nb;      // (re-pointed to shared memory below when it fits)
     int4* newl = D.newl + nb;
     TreeRec* rec = D.rec[f] + nb;
     const int* dict = D.dict_node + nb;
     __shared__ int s_nnew, s_err;
     // shared-memory mirror of what the dirty-marking walks touch: parent pointers, dirty bits, "is an inter-node
     // dict entry of this call" bits -- a walk step costs a shared-memory load instead of an L2 round trip
-    extern __shared__ int s_dyn[];
+    extern __shared__ __align__(16) int s_dyn[];
     const int n_before = D.n_nodes[f][g];
     const int nwords = (n_before + 31) >> 5;
+    const int budget_words = S.commit_smem / 4;
+    const bool use_smem = n_before + 3 * nwords <= budget_words;
     int* s_par = s_dyn;
-    unsigned int* s_dirty = (unsigned int*)(s_dyn + S.capN_smem);
-    unsigned int* s_inter = s_dirty + ((S.capN_smem + 31) >> 5);
-    unsigned int* s_tag = s_inter + ((S.capN_smem + 31) >> 5);     // recheck tags, indexed by dict rank
-    const bool use_smem = n_before <= S.capN_smem;
+    unsigned int* s_dirty = (unsigned int*)(s_dyn + n_before);
+    unsigned int* s_inter = s_dirty + nwords;
+    unsigned int* s_tag = s_inter + nwords;                      // recheck tags, indexed by dict rank
+    // the decision records and the Python-stream words of this call also live in shared memory when they fit
+    const int off_words = use_smem ? ((n_before + 3 * nwords + 3) & ~3) : 0;
+    const bool dec_smem = (size_t)nd_ * sizeof(ActDec) + (size_t)(2 * nd_ + 2) * 4 + 64 <= (size_t)(budget_words - off_words) * 4;
+    ActDec* adec_s = reinterpret_cast<ActDec*>(s_dyn + off_words);
+    unsigned int* pb_s = reinterpret_cast<unsigned int*>(adec_s + nd_);
+    if (dec_smem) adec = adec_s;
     const long long t_start = clock64();
     if (use_smem) {
         for (int i = tid; i < n_before; i += blockDim.x) s_par[i] = D.npar[f][nb + i];
@@ -744,6 +751,11 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
             const int t = prop[e].type;
             if (t == P_INTER_DRAW || t == P_INTER_EMPTY) { const int nd = dict[e]; atomicOr(&s_inter[nd >> 5], 1u << (nd & 31)); }
         }
+    }
+    const int ppos0 = D.py_pos[g];
+    if (dec_smem) {
+        const unsigned int* pbg = D.py_buf + (size_t)g * S.pycap + ppos0;
+        for (int i = tid; i < 2 * nd_ + 2; i += blockDim.x) pb_s[i] = pbg[i];
     }
     // ---- prologue: decision records of the entries that act without a recheck
     int na = 0;
@@ -762,9 +774,10 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
     if (tid == 0) {
         unsigned char* DEACT = D.deact[f] + nb;
         const int* loff = D.list_off + (size_t)g * (S.capN + 1);
-        const unsigned int* pb = D.py_buf + (size_t)g * S.pycap;
+        // word stream of Python's `random`: shared-memory copy of this call's window, or the global buffer
+        const unsigned int* pb = dec_smem ? pb_s - ppos0 : D.py_buf + (size_t)g * S.pycap;
         int* rtag = D.rtag + nb;
-        int ppos = D.py_pos[g];
+        int ppos = ppos0;
         int n_nodes = n_before, nnew = 0, err = 0;
         long long draws = 0;
         int cur_rank = -1, outstanding = 0;
@@ -1229,7 +1242,7 @@ __global__ void __launch_bounds__(1024) k_kdbuild(GrowDev D, GrowShape S) {
 // ------------------------------------------------------------------------------------------
 // launch wrappers (called from octa_grow_host.cu)
 // ------------------------------------------------------------------------------------------
-size_t commit_smem_bytes(const GrowShape& S) { return sizeof(int) * ((size_t)S.capN_smem + 3 * (((size_t)S.capN_smem + 31) >> 5)); }
+size_t commit_smem_bytes(const GrowShape& S) { return (size_t)S.commit_smem; }
 
 int prepare_kernels(const GrowShape& S) {
     return (int)cudaFuncSetAttribute(k_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)commit_smem_bytes(S));

@@ -84,6 +84,9 @@ def _bind():
     L.octa_grow_batch_host.argtypes = [ctypes.POINTER(OctaGrowConfig)] + run_args
     L.octa_grow_create.argtypes = [ctypes.POINTER(OctaGrowConfig), ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
     L.octa_grow_run.argtypes = [ctypes.c_void_p] + run_args
+    L.octa_grow_run_packed.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
+                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.POINTER(ctypes.c_double)]
     L.octa_grow_destroy.argtypes = [ctypes.c_void_p]
     L.octa_grow_destroy.restype = None
     return L
@@ -99,7 +102,7 @@ class GrowContext:
         self._cfg = make_config(config, cap_nodes, cap_sinks)
         self._h = ctypes.c_void_p()
         _lib.check(self.L.octa_grow_create(ctypes.byref(self._cfg), self.max_graphs, ctypes.byref(self._h)))
-        self._out = np.empty((self.max_graphs, self.cap_edges, 7), dtype=np.float64)
+        self._out = None
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -112,6 +115,28 @@ class GrowContext:
         except Exception:
             pass
 
+    def run_packed(self, seeds: Sequence[int], out: np.ndarray):
+        """Rows of all graphs packed back to back into `out` (float64 [cap, 7], e.g. a view of pinned memory).
+        Returns (offsets int64 [n+1], n_art int64 [n], stats, device_ms)."""
+        n = len(seeds)
+        if n > self.max_graphs:
+            raise ValueError("batch larger than the context")
+        sd = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint64))
+        offs = np.zeros(n + 1, dtype=np.int64)
+        na = np.zeros(n, dtype=np.int64)
+        nv = np.zeros(n, dtype=np.int64)
+        st = (OctaGrowStats * n)()
+        ms = ctypes.c_double(0)
+        rc = self.L.octa_grow_run_packed(self._h, sd.ctypes.data, n, out.ctypes.data, out.shape[0], offs.ctypes.data,
+                                         na.ctypes.data, nv.ctypes.data, ctypes.cast(st, ctypes.c_void_p), None,
+                                         ctypes.byref(ms))
+        stats = [{k: (list(getattr(st[i], k)) if k in ('commit_cycles', 'replay_detail') else getattr(st[i], k)) for k, _ in OctaGrowStats._fields_} for i in range(n)]
+        if rc != 0:
+            err = _lib.OctaError(rc, self.L.octa_last_error().decode(errors="replace"))
+            err.stats = stats
+            raise err
+        return offs, na, stats, ms.value
+
     def run(self, seeds: Sequence[int], trace: bool = False, copy: bool = True):
         n = len(seeds)
         if n > self.max_graphs:
@@ -122,6 +147,8 @@ class GrowContext:
         st = (OctaGrowStats * n)()
         tr = np.zeros((n, 4096, 4), dtype=np.int32) if trace else None
         ms = ctypes.c_double(0)
+        if self._out is None:
+            self._out = np.empty((self.max_graphs, self.cap_edges, 7), dtype=np.float64)
         rc = self.L.octa_grow_run(self._h, sd.ctypes.data, n, self._out.ctypes.data, self.cap_edges, na.ctypes.data,
                                   nv.ctypes.data, ctypes.cast(st, ctypes.c_void_p), tr.ctypes.data if trace else None,
                                   ctypes.byref(ms))

@@ -32,6 +32,7 @@ class Pipeline:
         self.host_threads = host_threads or max(1, (os.cpu_count() or 2) - 1)
         self._buf = {}
         self._grow = None
+        self.edge_cap = 24000      # rows reserved per sample in the pinned edge buffer (docker config: ~13 k)
 
     def _tensor(self, key, shape, dtype, pinned=False):
         t = self._buf.get(key)
@@ -53,20 +54,16 @@ class Pipeline:
                 if self._grow is not None:
                     self._grow.close()
                 self._grow = growth.GrowContext(self.config, len(seeds))
-            graphs, stats, extra = self._grow.run(seeds, copy=False)
             n = len(seeds)
-            sizes = [len(a) + len(v) for a, v in graphs]
-            offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+            cap = n * self.edge_cap
+            host_edges = self._tensor("edges_host", (cap, 7), torch.float64, pinned=True)
+            offs, n_art, stats, grow_ms = self._grow.run_packed(seeds, host_edges.numpy())
             E = int(offs[-1])
-            host_edges = self._tensor("edges_host", (max(E, 1), 7), torch.float64, pinned=True)
             he = host_edges.numpy()
-            for i, (a, v) in enumerate(graphs):
-                he[offs[i]:offs[i] + len(a)] = a
-                he[offs[i] + len(a):offs[i + 1]] = v
-            edges_dev = self._tensor("edges_dev", (max(E, 1), 7), torch.float64)
-            edges_dev.copy_(host_edges, non_blocking=True)
-            out = {"graphs": graphs, "stats": stats, "offsets": offs, "grow_device_ms": extra["device_ms"],
-                   "edges_host": he[:E]}
+            edges_dev = self._tensor("edges_dev", (cap, 7), torch.float64)
+            edges_dev[:max(E, 1)].copy_(host_edges[:max(E, 1)], non_blocking=True)
+            graphs = [(he[offs[i]:offs[i] + n_art[i]], he[offs[i] + n_art[i]:offs[i + 1]]) for i in range(n)]   # views
+            out = {"graphs": graphs, "stats": stats, "offsets": offs, "grow_device_ms": grow_ms, "edges_host": he[:E]}
             if self.voxelize:
                 shape = tree2img.voxel_volume_shape(self.volume_dims)
                 vol = self._tensor("vol", (n, *shape), torch.uint16)

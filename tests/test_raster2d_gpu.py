@@ -78,3 +78,25 @@ def test_batch_device_matches_single(t2i):
     host = out.cpu().numpy()
     for i, g in enumerate(graphs):
         assert np.array_equal(host[i], t2i.raster_edges(g, [304, 304])), i
+
+
+def test_training_transform_drop_in(t2i, tmp_path):
+    """LoadGraphAndFilterByRandomRadiusd semantics (data_transforms.py:362-387) on the GPU rasterizer."""
+    import gzip
+    import shutil
+    import torch
+    from octa_autosegmentation_b200.data_transforms import LoadGraphAndFilterByRandomRadiusd
+    p = tmp_path / "g.csv"
+    shutil.copy(os.path.join(GOLDEN, "graph_small_s0.csv"), p)
+    tr = LoadGraphAndFilterByRandomRadiusd(keys=["real_A", "real_B"], image_resolutions=[[304, 304], [1216, 1216]],
+                                           min_radius=[0, 0.001], max_dropout_prob=0.02)
+    random.seed(153)
+    out = tr({"real_A": str(p), "real_B": str(p)})
+    assert isinstance(out["real_A"], torch.Tensor) and out["real_A"].dtype == torch.float32
+    assert tuple(out["real_A"].shape) == (304, 304) and tuple(out["real_B"].shape) == (1216, 1216)
+    rows = load_graph_rows("graph_small_s0.csv")
+    random.seed(153)
+    a, bd = t2i.rasterize_forest(rows, [304, 304], 2, min_radius=0, max_dropout_prob=0.02)
+    assert np.array_equal(out["real_A"].numpy(), a.astype(np.float32))
+    b, _ = t2i.rasterize_forest(rows, [1216, 1216], 2, min_radius=0.001, max_dropout_prob=0.02, blackdict=bd)
+    assert np.array_equal(out["real_B"].numpy(), b.astype(np.float32))
