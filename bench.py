@@ -38,6 +38,17 @@ WORKLOAD = ("BASELINE config #2: batch of %d seeded samples per GPU, default 3x3
             "(1216x1216x53 u16) -> 1216^2 label + 304^2 image")
 
 
+def load_traffic(batch):
+    """DRAM bytes per launch of vox_tile_kernel from the committed `ncu --set full` capture (profiles/), same batch."""
+    p = os.path.join(ROOT, "profiles", "r01_vox_tile_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            t = json.load(f)
+        if int(t.get("batch", -1)) == int(batch):
+            return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])
+    return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -275,7 +286,7 @@ def main():
                     "note": "host API: + CSV text of every graph (byte-exact), + D2H of label (1216^2 u8) and image (304^2 u8) "
                             "into pinned memory; growth topology D2H and edge-row H2D are inside both numbers"},
             "roofline": {"bound": "hbm", "achieved": vox_ach, "peak": peak, "unit": "GB/s", "frac": vox_ach / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "vox_tile_kernel (+prep/scan/fill, <1 %)",
+                         "traffic": load_traffic(B), "peak_source": peak_src, "kernel": "vox_tile_kernel (+prep/scan/fill, <1 %)",
                          "algorithmic_bytes_per_launch": vox_alg, "ms_per_launch": vox_ms,
                          "note": "the HBM-bound kernel of the path; see roofline_growth for the phase that dominates step time"},
             "roofline_growth": {"bound": "hbm", "achieved": grow_ach, "peak": peak, "unit": "GB/s", "frac": grow_ach / peak,

@@ -85,6 +85,7 @@ struct GrowDev {
     int *assign, *first, *cnt, *slot, *slot_call, *cur, *rtag;
     int *dict_node, *n_dict, *list_off, *list, *sc_idx;
     double *sc_ang;
+    double *sc_inter;     // per (inter-node, attractor): angle to distal / proximal segment and unit vector (5 doubles)
     Proposal* prop;
     ActDec* adec;
     int4* newl;

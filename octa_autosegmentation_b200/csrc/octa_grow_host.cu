@@ -220,7 +220,7 @@ void carve(Carver& c, const GrowShape& S, GrowDev* D) {
     D->assign = c.take<int>(GS);
     D->first = c.take<int>(GN); D->cnt = c.take<int>(GN); D->slot = c.take<int>(GN); D->slot_call = c.take<int>(GN); D->cur = c.take<int>(GN); D->rtag = c.take<int>(GN);
     D->dict_node = c.take<int>(GN); D->n_dict = c.take<int>(G); D->list_off = c.take<int>(G * (S.capN + 1));
-    D->list = c.take<int>(GS); D->sc_idx = c.take<int>(GS); D->sc_ang = c.take<double>(GS);
+    D->list = c.take<int>(GS); D->sc_idx = c.take<int>(GS); D->sc_ang = c.take<double>(GS); D->sc_inter = c.take<double>(5 * GS);
     D->prop = c.take<Proposal>(GN); D->adec = c.take<ActDec>(GN); D->newl = c.take<int4>(GN);
     D->rec[0] = c.take<TreeRec>(GN); D->rec[1] = c.take<TreeRec>(GN); D->alist = c.take<int>(GN); D->n_alist = c.take<int>(G);
     D->hitj = c.take<int>(GS); D->hl = c.take<int>(GS); D->ta = c.take<int>(GS); D->seq = c.take<int>(GS);

@@ -93,10 +93,10 @@ __device__ __forceinline__ bool within_sqrt(double d2, double r, double r2) {
 // ------------------------------------------------------------------------------------------
 // k_sample: one CTA per graph
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_sample(GrowDev D, GrowShape S, IterP P) {
+__device__ __forceinline__ void sample_body(const GrowDev& D, const GrowShape& S, const IterP& P, int g) {
     __shared__ uint32_t mt[624];
     __shared__ int s_idx, s_p;
-    const int g = blockIdx.x, tid = threadIdx.x;
+    const int tid = threadIdx.x;
     if (D.err[g]) return;
     MTState* st = D.np_mt + g;
     for (int i = tid; i < 624; i += blockDim.x) mt[i] = st->mt[i];
@@ -198,10 +198,10 @@ __device__ __forceinline__ int grid_cell(double v) {
 }
 
 // which: 0 = all arterial nodes (+radius), 1 = O2 sinks, 2 / 3 = active arterial / venous nodes
-__global__ void __launch_bounds__(1024) k_grid_build(GrowDev D, GrowShape S, int which) {
+__device__ __forceinline__ void grid_build_body(const GrowDev& D, const GrowShape& S, int which, int g) {
     __shared__ int hist[GRID * GRID];
     __shared__ int cursor[GRID * GRID];
-    const int g = blockIdx.x, tid = threadIdx.x;
+    const int tid = threadIdx.x;
     if (D.err[g]) return;
     // The ACTIVE node set (element_mesh.py NodeKdTree of active nodes) is the node array minus the nodes that
     // branched: list order = creation order with deletions, so node ids preserve the list's relative order and
@@ -247,6 +247,17 @@ __global__ void __launch_bounds__(1024) k_grid_build(GrowDev D, GrowShape S, int
         gx[pos] = x; gy[pos] = y; gz[pos] = pz[i]; gi[pos] = i;
         if (pr) grd[pos] = pr[i];
     }
+}
+
+__global__ void __launch_bounds__(1024) k_grid_build(GrowDev D, GrowShape S, int which) { grid_build_body(D, S, which, blockIdx.x); }
+
+// k_prepare: everything an iteration needs that depends only on the state left by the previous iteration, in ONE
+// launch: blockIdx.y = 0..3 -> the four bucket grids (arterial nodes, O2 sinks, active arterial / venous nodes; the
+// venous set does not change before the venous commit), blockIdx.y = 4 -> the candidate sampler.  5*G CTAs run
+// side by side instead of five dependent single-wave launches.
+__global__ void __launch_bounds__(1024) k_prepare(GrowDev D, GrowShape S, IterP P) {
+    if (blockIdx.y < 4) grid_build_body(D, S, (int)blockIdx.y, blockIdx.x);
+    else sample_body(D, S, P, blockIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -615,10 +626,13 @@ __device__ void eval_leaf(const GrowDev& D, const GrowShape& S, const IterP& P, 
 }
 
 // inter-node branch, greenhouse.py:259-306, for a given distal radius r1
+// `cache_mode`: 1 = store the radius-independent per-attractor terms (two angles, unit vector) for a later
+// re-evaluation, 2 = re-evaluate from that cache (k_commit, when the distal radius changed inside the call), 0 = neither.
 __device__ void eval_inter(const GrowDev& D, const GrowShape& S, const IterP& P, int g, int f, const NodeCtx& nc,
-                           const int* lst, int n, double r1, Proposal* pr) {
+                           const int* lst, int n, double r1, Proposal* pr, int cache_mode) {
     const size_t sb = (size_t)g * S.capS;
     const double* sx = D.sx[f] + sb; const double* sy = D.sy[f] + sb; const double* sz = D.sz[f] + sb;
+    double* cache = D.sc_inter + (sb + (lst - (D.list + sb))) * 5;
     pr->type = P_INTER_EMPTY;
     pr->r1_used = r1;
     double phi1, phi2;
@@ -630,14 +644,21 @@ __device__ void eval_inter(const GrowDev& D, const GrowShape& S, const IterP& P,
     int m = 0;
     double avg[3] = {0, 0, 0};
     for (int i = 0; i < n; ++i) {
-        const int a = lst[i];
-        const double w[3] = {sx[a] - nc.pos[0], sy[a] - nc.pos[1], sz[a] - nc.pos[2]};
-        const double ad = angle_to(dseg, nd_, w, n);
-        const double ap = angle_to(pseg, np_, w, n);
-        if ((phi1 + phi2 - g2 <= ad) && (ad <= (phi1 + phi2 + g2)) && (ap <= phi2 + g2)) {
+        double ad, ap, un[3];
+        if (cache_mode == 2) {
+            ad = cache[5 * i]; ap = cache[5 * i + 1]; un[0] = cache[5 * i + 2]; un[1] = cache[5 * i + 3]; un[2] = cache[5 * i + 4];
+        } else {
+            const int a = lst[i];
+            const double w[3] = {sx[a] - nc.pos[0], sy[a] - nc.pos[1], sz[a] - nc.pos[2]};
+            ad = angle_to(dseg, nd_, w, n);
+            ap = angle_to(pseg, np_, w, n);
             const double nw = norm3(w);
-            if (m == 0) { avg[0] = w[0] / nw; avg[1] = w[1] / nw; avg[2] = w[2] / nw; }
-            else { avg[0] += w[0] / nw; avg[1] += w[1] / nw; avg[2] += w[2] / nw; }
+            un[0] = w[0] / nw; un[1] = w[1] / nw; un[2] = w[2] / nw;
+            if (cache_mode == 1) { cache[5 * i] = ad; cache[5 * i + 1] = ap; cache[5 * i + 2] = un[0]; cache[5 * i + 3] = un[1]; cache[5 * i + 4] = un[2]; }
+        }
+        if ((phi1 + phi2 - g2 <= ad) && (ad <= (phi1 + phi2 + g2)) && (ap <= phi2 + g2)) {
+            if (m == 0) { avg[0] = un[0]; avg[1] = un[1]; avg[2] = un[2]; }
+            else { avg[0] += un[0]; avg[1] += un[1]; avg[2] += un[2]; }
             ++m;
         }
     }
@@ -688,7 +709,7 @@ __global__ void __launch_bounds__(128) k_eval(GrowDev D, GrowShape S, IterP P, i
         const int* lst = D.list + sb + loff[e];
         const int n = loff[e + 1] - loff[e];
         if (nc.nch == 0) eval_leaf(D, S, P, g, f, e, nc, lst, n, &pr);
-        else if (nc.parent >= 0 && nc.nch == 1) eval_inter(D, S, P, g, f, nc, lst, n, D.nrad[f][nb + D.nch0[f][nb + nd]], &pr);
+        else if (nc.parent >= 0 && nc.nch == 1) eval_inter(D, S, P, g, f, nc, lst, n, D.nrad[f][nb + D.nch0[f][nb + nd]], &pr, 1);
         D.prop[nb + e] = pr;
     }
 }
@@ -731,13 +752,15 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
     const int n_before = D.n_nodes[f][g];
     const int nwords = (n_before + 31) >> 5;
     const int budget_words = S.commit_smem / 4;
-    const bool use_smem = n_before + 3 * nwords <= budget_words;
+    const bool use_smem = n_before + 5 * nwords <= budget_words;
     int* s_par = s_dyn;
     unsigned int* s_dirty = (unsigned int*)(s_dyn + n_before);
     unsigned int* s_inter = s_dirty + nwords;
     unsigned int* s_tag = s_inter + nwords;                      // recheck tags, indexed by dict rank
+    unsigned int* s_bif = s_tag + nwords;                        // node has two children
+    unsigned int* s_arr = s_bif + nwords;                        // refresh: one child of a bifurcation has arrived
     // the decision records and the Python-stream words of this call also live in shared memory when they fit
-    const int off_words = use_smem ? ((n_before + 3 * nwords + 3) & ~3) : 0;
+    const int off_words = use_smem ? ((n_before + 5 * nwords + 3) & ~3) : 0;
     const bool dec_smem = (size_t)nd_ * sizeof(ActDec) + (size_t)(2 * nd_ + 2) * 4 + 64 <= (size_t)(budget_words - off_words) * 4;
     ActDec* adec_s = reinterpret_cast<ActDec*>(s_dyn + off_words);
     unsigned int* pb_s = reinterpret_cast<unsigned int*>(adec_s + nd_);
@@ -745,8 +768,10 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
     const long long t_start = clock64();
     if (use_smem) {
         for (int i = tid; i < n_before; i += blockDim.x) s_par[i] = D.npar[f][nb + i];
-        for (int i = tid; i < nwords; i += blockDim.x) { s_dirty[i] = 0; s_inter[i] = 0; s_tag[i] = 0; }
+        for (int i = tid; i < nwords; i += blockDim.x) { s_dirty[i] = 0; s_inter[i] = 0; s_tag[i] = 0; s_bif[i] = 0; s_arr[i] = 0; }
         __syncthreads();
+        for (int i = tid; i < n_before; i += blockDim.x)
+            if (D.nnch[f][nb + i] >= 2) atomicOr(&s_bif[i >> 5], 1u << (i & 31));
         for (int e = tid; e < nd_; e += blockDim.x) {
             const int t = prop[e].type;
             if (t == P_INTER_DRAW || t == P_INTER_EMPTY) { const int nd = dict[e]; atomicOr(&s_inter[nd >> 5], 1u << (nd & 31)); }
@@ -792,6 +817,7 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
             rec[id] = r;
             if (parent_nch == 0) rec[parent].c0 = id; else rec[parent].c1 = id;
             rec[parent].nch = (unsigned char)(parent_nch + 1);
+            if (use_smem && parent_nch == 1) s_bif[parent >> 5] |= 1u << (parent & 31);
             newl[nnew++] = make_int4(e, which | (walk_after << 2), parent, id);
             return true;
         };
@@ -899,7 +925,7 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
                         load_ctx(D, S, P, g, f, nd, &nc);
                         Proposal pr;
                         pr.cond = 0; pr.ratio5 = 0;
-                        eval_inter(D, S, P, g, f, nc, D.list + sb + loff[e], loff[e + 1] - loff[e], r1, &pr);
+                        eval_inter(D, S, P, g, f, nc, D.list + sb + loff[e], loff[e + 1] - loff[e], r1, &pr, 2);
                         prop[e] = pr;
                         a.type = pr.type; a.cond = pr.cond; a.ratio5 = pr.ratio5;
                     }
@@ -939,11 +965,7 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
     if (s_err) return;
     const long long t_epi = clock64();
     const int n_after = n_before + s_nnew;
-    if (use_smem) {
-        for (int n = tid; n < n_before; n += blockDim.x)
-            if ((s_dirty[n >> 5] >> (n & 31)) & 1u) rec[n].dirty = 1;
-        __syncthreads();
-    }
+
     // ---- epilogue 1: SoA fields of the new nodes and of their parents' links
     for (int k = tid; k < s_nnew; k += blockDim.x) {
         const int4 nn = newl[k];
@@ -959,7 +981,57 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
         D.nch0[f][nb + parent] = rp.c0; D.nch1[f][nb + parent] = rp.c1; D.nnch[f][nb + parent] = rp.nch;
     }
     // ---- epilogue 2: bottom-up refresh of every node still dirty
-    {
+    if (use_smem) {
+        // Shared-memory driven: a chain climbs through parent pointers / dirty / bifurcation bits held in shared memory;
+        // single-child ancestors just copy the radius (no load, no atomic); at a bifurcation the first child to arrive
+        // stops and the second one (or the only dirty one) combines both radii and goes on.
+        __shared__ int s_nstart;
+        if (tid == 0) s_nstart = 0;
+        __syncthreads();
+        int* starters = D.alist + nb;
+        auto dirty_bit = [&](int n) -> bool { return n < n_before && ((s_dirty[n >> 5] >> (n & 31)) & 1u); };
+        for (int w = tid; w < nwords; w += blockDim.x) {
+            unsigned int bits = s_dirty[w];
+            while (bits) {
+                const int n = (w << 5) + __ffs(bits) - 1;
+                bits &= bits - 1;
+                const TreeRec r = rec[n];
+                const bool d0 = r.nch >= 1 && dirty_bit(r.c0), d1 = r.nch >= 2 && dirty_bit(r.c1);
+                if (!d0 && !d1) starters[atomicAdd(&s_nstart, 1)] = n;
+                else if (r.nch >= 2 && (d0 != d1)) atomicOr(&s_arr[n >> 5], 1u << (n & 31));
+            }
+        }
+        __syncthreads();
+        const int nstart = s_nstart;
+        volatile double* vR = D.nrad[f] + nb;
+        for (int k = tid; k < nstart; k += blockDim.x) {
+            int n = starters[k];
+            const TreeRec r = rec[n];
+            double val = r.R;
+            if (r.nch == 1) val = vR[r.c0];
+            else if (r.nch >= 2) val = murray_parent(P, r.kmode, vR[r.c0], vR[r.c1]);
+            rec[n].R = val;
+            vR[n] = val;
+            while (true) {
+                const int p = s_par[n];
+                if (p < 0 || !dirty_bit(p)) break;                  // (the root is never marked)
+                const unsigned int pbit = 1u << (p & 31);
+                if (s_bif[p >> 5] & pbit) {
+                    __threadfence_block();
+                    if (!(atomicOr(&s_arr[p >> 5], pbit) & pbit)) break;   // first arrival: the sibling's chain continues
+                    __threadfence_block();
+                    const TreeRec rp = rec[p];
+                    const double ra = (rp.c0 == n) ? val : vR[rp.c0];
+                    const double rb = (rp.c1 == n) ? val : vR[rp.c1];
+                    val = murray_parent(P, rp.kmode, ra, rb);
+                }
+                rec[p].R = val;
+                vR[p] = val;
+                n = p;
+            }
+        }
+        __syncthreads();
+    } else {
         int* pend = D.cnt + nb;                      // all zero outside k_group
         for (int n = tid; n < n_after; n += blockDim.x) {
             const TreeRec r = rec[n];
@@ -1250,12 +1322,10 @@ int prepare_kernels(const GrowShape& S) {
 
 void launch_iteration(const GrowDev& D, const GrowShape& S, const IterP& P, int n_sm, cudaStream_t st, cudaStream_t side,
                       cudaEvent_t ev_sinks, cudaEvent_t ev_kd) {
-    k_sample<<<S.G, 1024, 0, st>>>(D, S, P);
-    k_grid_build<<<S.G, 1024, 0, st>>>(D, S, 0);
-    k_grid_build<<<S.G, 1024, 0, st>>>(D, S, 1);
+    k_prepare<<<dim3(S.G, 5), 1024, 0, st>>>(D, S, P);
     k_sink_tests<<<n_sm * 8, TILE, 0, st>>>(D, S, P);
     k_sink_greedy<<<S.G, 1024, 0, st>>>(D, S, P);
-    count_launch(5);
+    count_launch(3);
     if (S.exact_ball_order) {
         cudaEventRecord(ev_sinks, st);
         cudaStreamWaitEvent(side, ev_sinks, 0);
@@ -1264,8 +1334,6 @@ void launch_iteration(const GrowDev& D, const GrowShape& S, const IterP& P, int 
         count_launch(1);
     }
     for (int f = 0; f < 2; ++f) {
-        k_grid_build<<<S.G, 1024, 0, st>>>(D, S, 2 + f);
-        count_launch(1);
         k_assign<<<n_sm * 8, TILE, 0, st>>>(D, S, P, f);
         k_group<<<S.G, 1024, 0, st>>>(D, S, P, f);
         k_eval<<<dim3(16, S.G), 128, 0, st>>>(D, S, P, f);
