@@ -54,13 +54,12 @@ struct GrowShape {
 
 struct GrowDev {
     // vessel nodes, [f][g*capN + i]
-    double *nx[2], *ny[2], *nz[2], *nrad[2], *nkap[2];
+    double *nx[2], *ny[2], *nz[2], *nrad[2];
     int *npar[2], *nch0[2], *nch1[2];
-    unsigned char *nnch[2], *nmeta[2], *deact[2], *dirty[2];
+    unsigned char *nnch[2], *nmeta[2], *deact[2];      // deact: the node branched and left the ACTIVE set
     int *n_nodes[2], *n_prev[2];
-    // active node lists (list order = element_mesh.py list order), with compacted positions
-    int *act[2], *n_act[2];
-    double *ax[2], *ay[2], *az[2];
+    // number of ACTIVE nodes (node array minus deact marks), refreshed by k_prepare for the byte accounting
+    int *n_act[2];
     // sinks: [0] oxygen sinks, [1] CO2 sources
     double *sx[2], *sy[2], *sz[2];
     int *n_s[2];
@@ -82,15 +81,15 @@ struct GrowDev {
     int* n_cand;
     unsigned char *cpass, *cstate;
     int* plist;
-    int *assign, *first, *cnt, *slot, *slot_call, *cur, *rtag;
+    int *assign, *first, *cnt, *slot, *cur, *rtag;
     int *dict_node, *n_dict, *list_off, *list, *sc_idx;
     double *sc_ang;
     double *sc_inter;     // per (inter-node, attractor): angle to distal / proximal segment and unit vector (5 doubles)
     Proposal* prop;
-    ActDec* adec;
+    ActDec* adec;         // decision records (global fallback when they do not fit in k_commit's shared memory)
     int4* newl;
     TreeRec* rec[2];
-    int *alist, *n_alist;
+    int *alist;           // k_commit scratch: start nodes of the bottom-up radius refresh
     int *hitj, *hl, *ta, *seq;
     int *kd_idx, *kd_posL, *kd_posR, *kd_rank, *kd_nodes;
     unsigned char* veto;

@@ -195,12 +195,11 @@ void carve(Carver& c, const GrowShape& S, GrowDev* D) {
     const size_t GN = (size_t)S.G * S.capN, GS = (size_t)S.G * S.capS, GC = (size_t)S.G * S.Nmax, G = S.G;
     for (int f = 0; f < 2; ++f) {
         D->nx[f] = c.take<double>(GN); D->ny[f] = c.take<double>(GN); D->nz[f] = c.take<double>(GN);
-        D->nrad[f] = c.take<double>(GN); D->nkap[f] = c.take<double>(GN);
+        D->nrad[f] = c.take<double>(GN);
         D->npar[f] = c.take<int>(GN); D->nch0[f] = c.take<int>(GN); D->nch1[f] = c.take<int>(GN);
-        D->nnch[f] = c.take<unsigned char>(GN); D->nmeta[f] = c.take<unsigned char>(GN); D->deact[f] = c.take<unsigned char>(GN); D->dirty[f] = c.take<unsigned char>(GN);
+        D->nnch[f] = c.take<unsigned char>(GN); D->nmeta[f] = c.take<unsigned char>(GN); D->deact[f] = c.take<unsigned char>(GN);
         D->n_nodes[f] = c.take<int>(G); D->n_prev[f] = c.take<int>(G);
-        D->act[f] = c.take<int>(GN); D->n_act[f] = c.take<int>(G);
-        D->ax[f] = c.take<double>(GN); D->ay[f] = c.take<double>(GN); D->az[f] = c.take<double>(GN);
+        D->n_act[f] = c.take<int>(G);
         D->sx[f] = c.take<double>(GS); D->sy[f] = c.take<double>(GS); D->sz[f] = c.take<double>(GS);
         D->n_s[f] = c.take<int>(G);
     }
@@ -218,11 +217,11 @@ void carve(Carver& c, const GrowShape& S, GrowDev* D) {
     D->n_cand = c.take<int>(G); D->cpass = c.take<unsigned char>(GC); D->cstate = c.take<unsigned char>(GC);
     D->plist = c.take<int>(GC);
     D->assign = c.take<int>(GS);
-    D->first = c.take<int>(GN); D->cnt = c.take<int>(GN); D->slot = c.take<int>(GN); D->slot_call = c.take<int>(GN); D->cur = c.take<int>(GN); D->rtag = c.take<int>(GN);
+    D->first = c.take<int>(GN); D->cnt = c.take<int>(GN); D->slot = c.take<int>(GN); D->cur = c.take<int>(GN); D->rtag = c.take<int>(GN);
     D->dict_node = c.take<int>(GN); D->n_dict = c.take<int>(G); D->list_off = c.take<int>(G * (S.capN + 1));
     D->list = c.take<int>(GS); D->sc_idx = c.take<int>(GS); D->sc_ang = c.take<double>(GS); D->sc_inter = c.take<double>(5 * GS);
     D->prop = c.take<Proposal>(GN); D->adec = c.take<ActDec>(GN); D->newl = c.take<int4>(GN);
-    D->rec[0] = c.take<TreeRec>(GN); D->rec[1] = c.take<TreeRec>(GN); D->alist = c.take<int>(GN); D->n_alist = c.take<int>(G);
+    D->rec[0] = c.take<TreeRec>(GN); D->rec[1] = c.take<TreeRec>(GN); D->alist = c.take<int>(GN);
     D->hitj = c.take<int>(GS); D->hl = c.take<int>(GS); D->ta = c.take<int>(GS); D->seq = c.take<int>(GS);
     D->veto = c.take<unsigned char>(GS);
     D->kd_idx = c.take<int>(GS); D->kd_posL = c.take<int>(GS); D->kd_posR = c.take<int>(GS); D->kd_rank = c.take<int>(GS);
@@ -467,12 +466,9 @@ static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, doub
             const size_t cn = S.capN;
             OCTA_CUDA_CHECK(up2d(D.nx[f], 8 * cn, sg + o_x[f], 8)); OCTA_CUDA_CHECK(up2d(D.ny[f], 8 * cn, sg + o_y[f], 8));
             OCTA_CUDA_CHECK(up2d(D.nz[f], 8 * cn, sg + o_z[f], 8)); OCTA_CUDA_CHECK(up2d(D.nrad[f], 8 * cn, sg + o_r[f], 8));
-            OCTA_CUDA_CHECK(up2d(D.nkap[f], 8 * cn, sg + o_k[f], 8)); OCTA_CUDA_CHECK(up2d(D.npar[f], 4 * cn, sg + o_p[f], 4));
+            OCTA_CUDA_CHECK(up2d(D.npar[f], 4 * cn, sg + o_p[f], 4));
             OCTA_CUDA_CHECK(up2d(D.nch0[f], 4 * cn, sg + o_c0[f], 4)); OCTA_CUDA_CHECK(up2d(D.nch1[f], 4 * cn, sg + o_c1[f], 4));
-            OCTA_CUDA_CHECK(up2d(D.act[f], 4 * cn, sg + o_act[f], 4));
             OCTA_CUDA_CHECK(up2d(D.nnch[f], cn, sg + o_n[f], 1)); OCTA_CUDA_CHECK(up2d(D.nmeta[f], cn, sg + o_m[f], 1));
-            OCTA_CUDA_CHECK(up2d(D.ax[f], 8 * cn, sg + o_x[f], 8)); OCTA_CUDA_CHECK(up2d(D.ay[f], 8 * cn, sg + o_y[f], 8));
-            OCTA_CUDA_CHECK(up2d(D.az[f], 8 * cn, sg + o_z[f], 8));
             OCTA_CUDA_CHECK(up2d(D.rec[f], sizeof(TreeRec) * cn, sg + o_rec[f], sizeof(TreeRec)));
             OCTA_CUDA_CHECK(cudaMemsetAsync(D.deact[f], 0, G * cn, st));
             OCTA_CUDA_CHECK(cudaMemcpyAsync(D.n_nodes[f], sg + o_cnt, 4 * G, cudaMemcpyHostToDevice, st));

@@ -332,6 +332,9 @@ __global__ void __launch_bounds__(1024) k_sink_greedy(GrowDev D, GrowShape S, It
     const double eps2 = P.eps_s * P.eps_s;
     // state: 0 undecided, 1 accepted, 2 rejected.  Candidate k is rejected as soon as an earlier ACCEPTED
     // candidate lies within eps_s, accepted once every earlier candidate within eps_s is rejected.
+    // Threads read state[j] of other threads inside a round without a barrier (compute-sanitizer racecheck
+    // flags it): a state only ever moves 0 -> 1 or 0 -> 2, and either value seen gives a decision the
+    // sequential greedy would also reach, so the fixed point is unique; early visibility just saves rounds.
     for (int round = 0; round < nc + 2; ++round) {
         int undecided = 0;
         for (int k = tid; k < np_; k += blockDim.x) {
@@ -424,7 +427,7 @@ __global__ void __launch_bounds__(1024) k_group(GrowDev D, GrowShape S, IterP P,
     const int A = D.n_s[f][g];
     const size_t sb = (size_t)g * S.capS, nb = (size_t)g * S.capN;
     const int* asg = D.assign + sb;
-    int* first = D.first + nb; int* cnt = D.cnt + nb; int* slot = D.slot + nb; int* slot_call = D.slot_call + nb; int* cur = D.cur + nb;
+    int* first = D.first + nb; int* cnt = D.cnt + nb; int* slot = D.slot + nb; int* cur = D.cur + nb;
     int* dict = D.dict_node + nb; int* loff = D.list_off + (size_t)g * (S.capN + 1); int* lst = D.list + sb;
     TreeRec* rec = D.rec[f] + nb;
     for (int a = tid; a < A; a += blockDim.x) {
@@ -439,7 +442,7 @@ __global__ void __launch_bounds__(1024) k_group(GrowDev D, GrowShape S, IterP P,
         if (a < A) { nd = asg[a]; isf = (nd >= 0 && first[nd] == a); }
         int total;
         const int incl = block_scan_incl(isf, &total);
-        if (isf) { const int rk = nd_ + incl - 1; dict[rk] = nd; slot[nd] = rk; slot_call[nd] = call_id; rec[nd].slot = rk; rec[nd].slot_call = call_id; }
+        if (isf) { const int rk = nd_ + incl - 1; dict[rk] = nd; slot[nd] = rk; rec[nd].slot = rk; rec[nd].slot_call = call_id; }
         nd_ += total;
     }
     __syncthreads();
@@ -973,7 +976,7 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
         const Proposal& pr = prop[e];
         const double* p = which == 0 ? pr.p : (which == 1 ? pr.b1 : pr.b2);
         D.nx[f][nb + id] = p[0]; D.ny[f][nb + id] = p[1]; D.nz[f][nb + id] = p[2];
-        D.nrad[f][nb + id] = P.r; D.nkap[f][nb + id] = P.kappa;
+        D.nrad[f][nb + id] = P.r;
         D.npar[f][nb + id] = parent; D.nch0[f][nb + id] = -1; D.nch1[f][nb + id] = -1; D.nnch[f][nb + id] = 0;
         D.deact[f][nb + id] = 0;
         D.nmeta[f][nb + id] = (unsigned char)((P.mode_idx << 1) | walk);
