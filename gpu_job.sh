@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
-timeout 300 python tools/grow_probe.py --batch 64 --check 24 > gpurun_out/probe.log 2>&1; tail -8 gpurun_out/probe.log
-timeout 600 python bench.py > gpurun_out/bench.log 2>&1; tail -1 gpurun_out/bench.log
+for ty in 16 32; do
+OCTA_VOX_TILE_Y=$ty timeout 600 python bench.py --no-cpu-baseline --steps 3 > gpurun_out/bench_ty$ty.log 2>&1; tail -1 gpurun_out/bench_ty$ty.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print($ty, d['value'], d['config']['phase_ms'], d['roofline']['frac'])"
+done

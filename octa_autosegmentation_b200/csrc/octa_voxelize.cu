@@ -13,20 +13,23 @@
 // (this file is compiled with -fmad=false); since quantisation is monotone, max is taken on the
 // quantised value, which makes the accumulation order-independent and exact.
 //
-// Design (B200): the volume is cut into tiles [TX][TY][TZ]; one CTA owns one tile of one graph,
-// max-accumulates in shared memory (u32 per voxel, smem atomicMax across warps, one warp per
-// edge) and then streams the tile out once as u16 with 16-byte stores -- the HBM traffic is the
-// algorithmic 2 bytes/voxel, no float scratch volume and no global atomics.  Edges are binned to
-// tiles by three small kernels (prep/count, scan, fill).  Edges that overlap more than KBIG tiles
-// go to a per-graph "big" list that every tile tests, which bounds the workspace at
-// (sizeof(VoxEdge) + 4*KBIG + 4) bytes per edge for ANY input.
+// Design (B200): the volume is cut into tiles [TX=16][TY=16][TZ<=64]; one CTA owns one tile of one graph and
+// max-accumulates it in shared memory as u16 cells laid out exactly like the volume (27 KB for z = 53: four
+// CTAs per SM).  The (y,z) rows of the clipped edge boxes are dealt out to lanes; a lane culls its row in
+// fp32, the warp compacts the surviving voxels and evaluates them in float64 with all lanes busy (see
+// rasterize notes below).  The finished tile leaves with TMA bulk copies shared -> global
+// (cp.async.bulk, one per x plane) -- the HBM traffic is the algorithmic 2 bytes/voxel, no float scratch volume
+// and no global atomics.  Edges are binned to tiles by three small kernels (prep/count, scan, fill).  Edges
+// that overlap more than KBIG tiles go to a per-graph "big" list that every tile tests, which bounds the
+// workspace at (sizeof(VoxEdge) + 4*KBIG + 4) bytes per edge for ANY input.
 #include "octa_common.h"
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
-constexpr int KBIG = 32;          // max tiles an edge may be listed in before it becomes a "big" edge
-constexpr int TILE_Y = 32;
+constexpr int KBIG = 64;          // max tiles an edge may be listed in before it becomes a "big" edge
+constexpr int TILE_Y = 16;
 constexpr int TILE_Z_MAX = 64;
 constexpr int VOX_THREADS = 256;
 
@@ -224,6 +227,7 @@ __device__ __noinline__ uint32_t exact_voxel_q(const VoxEdge& e, double vx, doub
 
 // Per-edge constants staged in shared memory for one pass of EPASS edges of a tile.
 constexpr int EPASS = 32;
+constexpr int QCAP = 512;       // survivor queue entries per warp: 32 rows x at most 16 voxels
 struct EdgeSm {
     double p1[3], p2[3], s[3];
     double R, ss, inv_ss, c0, tguard;
@@ -233,13 +237,16 @@ struct EdgeSm {
 };
 
 // Work distribution: the (y,z) rows of all clipped edge boxes of a pass are numbered consecutively and dealt out
-// to the threads of the CTA round-robin, so every warp gets the same amount of work whatever the number and size
-// of the edges in the tile (a warp-per-edge split left most warps waiting at the tile barrier).  A thread walks
-// its row along x.  Three tiers per voxel:
-//   1. fp32 broad phase in box-local coordinates -- rejects voxels whose exact contribution is <= 0 (88 %);
-//   2. fast float64 evaluation (fma, reciprocal instead of division): 255*I is accurate to ~1e-11, so its floor
+// to the lanes of the CTA's warps, so every warp gets the same amount of work whatever the number and size of the
+// edges in the tile.  Three tiers per voxel:
+//   1. fp32 broad phase in box-local coordinates: a lane walks its row along x (<= 16 voxels) and produces a bit
+//      mask of the voxels whose exact contribution can be > 0 (12 % survive);
+//   2. the warp COMPACTS the survivors of its 32 rows into a shared-memory queue and evaluates them with all lanes
+//      busy: fast float64 (fma, reciprocal instead of division); 255*I is accurate to ~1e-11, so its floor
 //      equals the reference's unless 255*I lies within 1e-7 of an integer or t within 1e-9 of {0,1};
 //   3. inside those guard bands (probability ~1e-7) the reference's exact operation chain decides.
+// (Without the compaction the float64 tier ran at the survivors' lane density: almost every x step of a warp had
+// at least one surviving lane and paid the full float64 cost for it.)
 __device__ __forceinline__ void setup_edge(const VoxEdge& e, const int t0[3], const int t1[3], EdgeSm* o) {
     int rows = 1;
 #pragma unroll
@@ -271,131 +278,109 @@ __device__ __forceinline__ void setup_edge(const VoxEdge& e, const int t0[3], co
     o->thr = reach * reach;
 }
 
-__device__ __forceinline__ void rasterize_row(const EdgeSm& E, int row, const int t0[3], const int T[3], uint32_t* acc) {
-    const int nz = E.n[2];
-    int iy = (int)((float)row * (1.0f / (float)nz));
-    int iz = row - iy * nz;
-    if (iz < 0) { --iy; iz += nz; } else if (iz >= nz) { ++iy; iz -= nz; }
+// tier 1: bit ix of the result is set when voxel (b0x + ix, row) may receive a positive contribution
+__device__ __forceinline__ uint32_t cull_row(const EdgeSm& E, int iy, int iz) {
     const float f0 = E.f[0], f1 = E.f[1], f2 = E.f[2], a0 = E.a[0], finv = E.finv, thr = E.thr;
     const float w1 = (float)iy - E.a[1], w2 = (float)iz - E.a[2];
     const float dot12 = w1 * f1 + w2 * f2;
-    const int bx = E.b0[0];
-    const double vy = (double)(E.b0[1] + iy) + 0.5, vz = (double)(E.b0[2] + iz) + 0.5;
-    uint32_t* arow = acc + ((bx - t0[0]) * T[1] + (E.b0[1] + iy - t0[1])) * T[2] + (E.b0[2] + iz - t0[2]);
-    const int xstride = T[1] * T[2];
     const int nx = E.n[0];
+    uint32_t mask = 0;
+#pragma unroll 4
     for (int ix = 0; ix < nx; ++ix) {
         const float w0 = (float)ix - a0;
         float tf = fmaf(w0, f0, dot12) * finv;
         tf = fminf(fmaxf(tf, 0.f), 1.f);
         const float d0 = fmaf(-tf, f0, w0), d1 = fmaf(-tf, f1, w1), d2 = fmaf(-tf, f2, w2);
-        if (fmaf(d0, d0, fmaf(d1, d1, d2 * d2)) > thr) continue;
-        // fast float64 evaluation
-        const double vx = (double)(bx + ix) + 0.5;
-        const double s0 = E.s[0], s1 = E.s[1], s2 = E.s[2], ss = E.ss;
-        const double u0 = vx - E.p2[0], u1 = vy - E.p2[1], u2 = vz - E.p2[2];
-        const double dot = fma(u2, s2, fma(u1, s1, u0 * s0));
-        uint32_t q;
-        bool exact = fabs(dot) < E.tguard || fabs(dot - ss) < E.tguard;
-        if (!exact) {
-            double dd;
-            if (dot > 0.0 && dot < ss) {
-                const double t = dot * E.inv_ss;
-                const double e0 = fma(-t, s0, u0), e1 = fma(-t, s1, u1), e2 = fma(-t, s2, u2);
-                dd = fma(e2, e2, fma(e1, e1, e0 * e0));
-            } else {
-                const double q0 = vx - E.p1[0], q1 = vy - E.p1[1], q2 = vz - E.p1[2];
-                dd = fmin(fma(u2, u2, fma(u1, u1, u0 * u0)), fma(q2, q2, fma(q1, q1, q0 * q0)));
-            }
-            const double val = 255.0 * fma(-sqrt(dd), 0.57735026918962576, E.c0);
-            if (val < -1e-7) continue;
-            const double fl = floor(val);
-            const double fr = val - fl;
-            exact = fr < 1e-7 || fr > 1.0 - 1e-7 || !(val == val);
-            q = val >= 255.0 ? 255u : (uint32_t)fl;
+        if (!(fmaf(d0, d0, fmaf(d1, d1, d2 * d2)) > thr)) mask |= 1u << ix;
+    }
+    return mask;
+}
+
+// tiers 2 and 3 for one surviving voxel; returns the quantised contribution
+__device__ __forceinline__ uint32_t eval_voxel(const EdgeSm& E, int ix, int iy, int iz) {
+    const double vx = (double)(E.b0[0] + ix) + 0.5, vy = (double)(E.b0[1] + iy) + 0.5, vz = (double)(E.b0[2] + iz) + 0.5;
+    const double s0 = E.s[0], s1 = E.s[1], s2 = E.s[2], ss = E.ss;
+    const double u0 = vx - E.p2[0], u1 = vy - E.p2[1], u2 = vz - E.p2[2];
+    const double dot = fma(u2, s2, fma(u1, s1, u0 * s0));
+    uint32_t q = 0;
+    bool exact = fabs(dot) < E.tguard || fabs(dot - ss) < E.tguard;
+    if (!exact) {
+        double dd;
+        if (dot > 0.0 && dot < ss) {
+            const double t = dot * E.inv_ss;
+            const double e0 = fma(-t, s0, u0), e1 = fma(-t, s1, u1), e2 = fma(-t, s2, u2);
+            dd = fma(e2, e2, fma(e1, e1, e0 * e0));
+        } else {
+            const double q0 = vx - E.p1[0], q1 = vy - E.p1[1], q2 = vz - E.p1[2];
+            dd = fmin(fma(u2, u2, fma(u1, u1, u0 * u0)), fma(q2, q2, fma(q1, q1, q0 * q0)));
         }
-        if (exact) {
-            VoxEdge e;
+        const double val = 255.0 * fma(-sqrt(dd), 0.57735026918962576, E.c0);
+        if (val < -1e-7) return 0;
+        const double fl = floor(val);
+        const double fr = val - fl;
+        exact = fr < 1e-7 || fr > 1.0 - 1e-7 || !(val == val);
+        q = val >= 255.0 ? 255u : (uint32_t)fl;
+    }
+    if (exact) {
+        VoxEdge e;
 #pragma unroll
-            for (int a = 0; a < 3; ++a) { e.p1[a] = E.p1[a]; e.p2[a] = E.p2[a]; }
-            e.R = E.R;
-            q = exact_voxel_q(e, vx, vy, vz);
-        }
-        if (q) atomicMax(arow + ix * xstride, q);
+        for (int a = 0; a < 3; ++a) { e.p1[a] = E.p1[a]; e.p2[a] = E.p2[a]; }
+        e.R = E.R;
+        q = exact_voxel_q(e, vx, vy, vz);
+    }
+    return q;
+}
+
+// max-accumulate a 16-bit tile cell (values 0..255; contention is rare, most updates stop at the first load)
+__device__ __forceinline__ void tile_max(unsigned short* p, uint32_t q) {
+    unsigned short old = *(volatile unsigned short*)p;
+    while (old < q) {
+        const unsigned short seen = atomicCAS(p, old, (unsigned short)q);
+        if (seen == old) break;
+        old = seen;
     }
 }
 
-__global__ void __launch_bounds__(VOX_THREADS)
+__global__ void __launch_bounds__(VOX_THREADS, 4)
 vox_tile_kernel(const VoxEdge* __restrict__ prep, const int64_t* __restrict__ edge_offsets, VoxGeom g,
                 const int* __restrict__ tile_start, const int* __restrict__ tile_edges,
                 const int* __restrict__ big_count, const int* __restrict__ big_idx,
                 uint16_t* __restrict__ out) {
-    extern __shared__ __align__(16) uint32_t acc[];
-    const int gr = blockIdx.y;
-    const int tile = blockIdx.x;
-    const int tz_i = tile % g.nt[2], ty_i = (tile / g.nt[2]) % g.nt[1], tx_i = tile / (g.nt[2] * g.nt[1]);
+    // dynamic shared memory: the tile accumulators, u16 [TX][TY][TZ] in the volume's own layout
+    extern __shared__ __align__(128) unsigned short acc[];
+    // grid = (tiles along y and z, tiles along x, graphs)
+    const int gr = blockIdx.z;
+    const int tx_i = blockIdx.y, ty_i = blockIdx.x / g.nt[2], tz_i = blockIdx.x - ty_i * g.nt[2];
+    const int tile = (tx_i * g.nt[1] + ty_i) * g.nt[2] + tz_i;
     const int T[3] = {g.T[0], g.T[1], g.T[2]};
     const int t0[3] = {tx_i * T[0], ty_i * T[1], tz_i * T[2]};
     const int t1[3] = {imin(t0[0] + T[0], g.D[0]), imin(t0[1] + T[1], g.D[1]), imin(t0[2] + T[2], g.D[2])};
     const int tile_elems = T[0] * T[1] * T[2];
     const int64_t e_base = edge_offsets[gr];
     const VoxEdge* ge = prep + e_base;
+    uint16_t* vol = out + (size_t)gr * g.D[0] * g.D[1] * g.D[2];
+    const int ny = t1[1] - t0[1], nz = t1[2] - t0[2];
+    // the (y,z) plane of one x of the tile is one contiguous run both in shared memory and in the volume
+    const bool plane_contig = (nz == g.D[2] && T[2] == g.D[2]);
+    const int plane_len = ny * nz;
 
     const int* st = tile_start + (size_t)gr * (g.ntiles + 1);
     const int beg = st[tile], end = st[tile + 1];
     const int nbig = big_count[gr];
 
-    if (end > beg || nbig > 0) {
-        uint4* acc4 = reinterpret_cast<uint4*>(acc);
-        for (int i = threadIdx.x; i < tile_elems / 4; i += blockDim.x) acc4[i] = make_uint4(0, 0, 0, 0);
-        for (int i = (tile_elems / 4) * 4 + threadIdx.x; i < tile_elems; i += blockDim.x) acc[i] = 0;
-        __syncthreads();
-        __shared__ EdgeSm es[EPASS];
-        __shared__ int s_total;
-        const int* lst = tile_edges + (size_t)KBIG * e_base;
-        const int* bl = big_idx + e_base;
-        const int nlist = end - beg, nall = nlist + nbig;
-        for (int pass = 0; pass < nall; pass += EPASS) {
-            const int cnt = imin(EPASS, nall - pass);
-            if (threadIdx.x < cnt) {
-                const int k = pass + threadIdx.x;
-                const VoxEdge e = ge[k < nlist ? lst[beg + k] : bl[k - nlist]];
-                setup_edge(e, t0, t1, &es[threadIdx.x]);
-            }
-            __syncthreads();
-            if (threadIdx.x < 32) {           // exclusive prefix of the row counts of this pass
-                const int v = threadIdx.x < cnt ? es[threadIdx.x].rowbase : 0;
-                int x = v;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if ((int)threadIdx.x >= o) x += y; }
-                if (threadIdx.x < cnt) es[threadIdx.x].rowbase = x - v;
-                if (threadIdx.x == 31) s_total = x;
-            }
-            __syncthreads();
-            const int total = s_total;
-            for (int item = threadIdx.x; item < total; item += blockDim.x) {
-                int lo = 0, hi = cnt;             // last edge with rowbase <= item
-                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (es[mid].rowbase <= item) lo = mid; else hi = mid; }
-                rasterize_row(es[lo], item - es[lo].rowbase, t0, T, acc);
-            }
-            __syncthreads();
-        }
-    } else {
+    if (!(end > beg || nbig > 0)) {
         // empty tile: stream zeros without touching shared memory
-        uint16_t* vol = out + (size_t)gr * g.D[0] * g.D[1] * g.D[2];
-        const int ny = t1[1] - t0[1], nz = t1[2] - t0[2];
         for (int x = t0[0]; x < t1[0]; ++x) {
-            if (nz == g.D[2]) {
+            if (plane_contig) {
                 const size_t base = ((size_t)x * g.D[1] + t0[1]) * g.D[2];
-                const int len = ny * nz;
-                if (((base | (size_t)len) & 7) == 0) {
+                if (((base | (size_t)plane_len) & 7) == 0) {
                     uint4* p = reinterpret_cast<uint4*>(vol + base);
-                    for (int i = threadIdx.x; i < len / 8; i += blockDim.x) p[i] = make_uint4(0, 0, 0, 0);
+                    for (int i = threadIdx.x; i < plane_len / 8; i += blockDim.x) p[i] = make_uint4(0, 0, 0, 0);
                 } else {
-                    for (int i = threadIdx.x; i < len; i += blockDim.x) vol[base + i] = 0;
+                    for (int i = threadIdx.x; i < plane_len; i += blockDim.x) vol[base + i] = 0;
                 }
             } else {
-                for (int i = threadIdx.x; i < ny * nz; i += blockDim.x) {
+                for (int i = threadIdx.x; i < plane_len; i += blockDim.x) {
                     const int y = i / nz, z = i - y * nz;
                     vol[((size_t)x * g.D[1] + t0[1] + y) * g.D[2] + t0[2] + z] = 0;
                 }
@@ -404,32 +389,112 @@ vox_tile_kernel(const VoxEdge* __restrict__ prep, const int64_t* __restrict__ ed
         return;
     }
 
-    // stream the tile out: u32 accumulators -> u16, 2 algorithmic bytes per voxel
-    uint16_t* vol = out + (size_t)gr * g.D[0] * g.D[1] * g.D[2];
-    const int ny = t1[1] - t0[1], nz = t1[2] - t0[2];
-    for (int x = t0[0]; x < t1[0]; ++x) {
-        const uint32_t* slab = acc + (size_t)(x - t0[0]) * T[1] * T[2];
-        if (nz == g.D[2] && T[2] == g.D[2]) {
-            // (y,z) plane of this x is contiguous both in smem and in the volume
-            const size_t base = ((size_t)x * g.D[1] + t0[1]) * g.D[2];
-            const int len = ny * nz;
-            if (((base | (size_t)len) & 7) == 0) {
-                uint4* p = reinterpret_cast<uint4*>(vol + base);
-                const uint4* s4 = reinterpret_cast<const uint4*>(slab);
-                for (int i = threadIdx.x; i < len / 8; i += blockDim.x) {
-                    const uint4 a = s4[2 * i], b = s4[2 * i + 1];
-                    uint4 o;
-                    o.x = a.x | (a.y << 16); o.y = a.z | (a.w << 16);
-                    o.z = b.x | (b.y << 16); o.w = b.z | (b.w << 16);
-                    p[i] = o;
-                }
-            } else {
-                for (int i = threadIdx.x; i < len; i += blockDim.x) vol[base + i] = (uint16_t)slab[i];
+    {
+        uint4* acc4 = reinterpret_cast<uint4*>(acc);
+        for (int i = threadIdx.x; i < tile_elems / 8; i += blockDim.x) acc4[i] = make_uint4(0, 0, 0, 0);
+        for (int i = (tile_elems / 8) * 8 + threadIdx.x; i < tile_elems; i += blockDim.x) acc[i] = 0;
+    }
+    __shared__ EdgeSm es[EPASS];
+    __shared__ unsigned short s_queue[(VOX_THREADS / 32) * QCAP];
+    __shared__ int s_total, s_rowbase[EPASS];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned short* queue = s_queue + warp * QCAP;
+    const int* lst = tile_edges + (size_t)KBIG * e_base;
+    const int* bl = big_idx + e_base;
+    const int nlist = end - beg, nall = nlist + nbig;
+    const int ystride = T[2], xstride = T[1] * T[2];
+    for (int pass = 0; pass < nall; pass += EPASS) {
+        const int cnt = imin(EPASS, nall - pass);
+        if (threadIdx.x < cnt) {
+            const int k = pass + threadIdx.x;
+            const VoxEdge e = ge[k < nlist ? lst[beg + k] : bl[k - nlist]];
+            setup_edge(e, t0, t1, &es[threadIdx.x]);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {           // exclusive prefix of the row counts of this pass
+            const int v = threadIdx.x < cnt ? es[threadIdx.x].rowbase : 0;
+            int x = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if ((int)threadIdx.x >= o) x += y; }
+            if (threadIdx.x < cnt) es[threadIdx.x].rowbase = x - v;
+            s_rowbase[threadIdx.x] = x - v;
+            if (threadIdx.x == 31) s_total = x;
+        }
+        __syncthreads();
+        const int total = s_total;
+        int lo = 0;                        // last edge with rowbase <= item (items of a lane only move forward)
+        for (int base = warp * 32; base < total; base += VOX_THREADS) {      // warp-uniform trip count
+            const int item = base + lane;
+            uint32_t mask = 0, rowinfo = 0;
+            if (item < total) {
+                while (lo + 1 < cnt && s_rowbase[lo + 1] <= item) ++lo;
+                const EdgeSm& E = es[lo];
+                const int row = item - E.rowbase, enz = E.n[2];
+                int iy = (int)((float)row * (1.0f / (float)enz));
+                int iz = row - iy * enz;
+                if (iz < 0) { --iy; iz += enz; } else if (iz >= enz) { ++iy; iz -= enz; }
+                mask = cull_row(E, iy, iz);
+                rowinfo = ((uint32_t)lo << 16) | ((uint32_t)iy << 8) | (uint32_t)iz;
             }
+            // compaction: queue entry = (source lane << 4) | ix
+            const int c = __popc(mask);
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+            const int tot = __shfl_sync(0xffffffffu, incl, 31);
+            int w = incl - c;
+            while (mask) {
+                const int ix = __ffs(mask) - 1;
+                mask &= mask - 1;
+                queue[w++] = (unsigned short)((lane << 4) | ix);
+            }
+            __syncwarp();
+            for (int jb = 0; jb < tot; jb += 32) {
+                const int j = jb + lane;
+                const bool on = j < tot;
+                const uint32_t ent = on ? queue[j] : 0u;
+                const uint32_t ri = __shfl_sync(0xffffffffu, rowinfo, ent >> 4);
+                if (on) {
+                    const EdgeSm& E = es[ri >> 16];
+                    const int ix = ent & 15, iy = (ri >> 8) & 255, iz = ri & 255;
+                    const uint32_t q = eval_voxel(E, ix, iy, iz);
+                    if (q) tile_max(acc + (E.b0[0] + ix - t0[0]) * xstride + (E.b0[1] + iy - t0[1]) * ystride + (E.b0[2] + iz - t0[2]), q);
+                }
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+    }
+
+    // stream the tile out: the accumulators already are the volume's u16 cells, 2 algorithmic bytes per voxel
+    const size_t base0 = ((size_t)t0[0] * g.D[1] + t0[1]) * g.D[2];
+    const size_t xpitch = (size_t)g.D[1] * g.D[2];
+    if (plane_contig && (((base0 | xpitch | (size_t)plane_len | (size_t)xstride) & 7) == 0)) {
+        // TMA bulk copies shared -> global, one per x plane (16-byte aligned runs), issued by one thread
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t bytes = (uint32_t)plane_len * 2u;
+            for (int x = 0; x < t1[0] - t0[0]; ++x) {
+                const uint32_t src = (uint32_t)__cvta_generic_to_shared(acc + (size_t)x * xstride);
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             ::"l"(vol + base0 + (size_t)x * xpitch), "r"(src), "r"(bytes) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        return;
+    }
+    for (int x = t0[0]; x < t1[0]; ++x) {
+        const unsigned short* slab = acc + (size_t)(x - t0[0]) * xstride;
+        if (plane_contig) {
+            const size_t base = ((size_t)x * g.D[1] + t0[1]) * g.D[2];
+            for (int i = threadIdx.x; i < plane_len; i += blockDim.x) vol[base + i] = slab[i];
         } else {
-            for (int i = threadIdx.x; i < ny * nz; i += blockDim.x) {
+            for (int i = threadIdx.x; i < plane_len; i += blockDim.x) {
                 const int y = i / nz, z = i - y * nz;
-                vol[((size_t)x * g.D[1] + t0[1] + y) * g.D[2] + t0[2] + z] = (uint16_t)slab[y * T[2] + z];
+                vol[((size_t)x * g.D[1] + t0[1] + y) * g.D[2] + t0[2] + z] = slab[y * T[2] + z];
             }
         }
     }
@@ -457,9 +522,10 @@ int make_geom(const int dims[3], const OctaVoxOpts* opts, VoxGeom* g) {
     g->min_radius = opts ? opts->min_radius : 0.0;
     g->max_radius = opts ? opts->max_radius : 1.0;
     g->T[1] = TILE_Y;
+    if (const char* ev = getenv("OCTA_VOX_TILE_Y")) { const int v = atoi(ev); if (v == 8 || v == 16 || v == 32) g->T[1] = v; }   // tuning knob
     g->T[2] = g->D[2] < TILE_Z_MAX ? g->D[2] : TILE_Z_MAX;
-    g->T[0] = 16;
-    while (g->T[0] > 1 && (size_t)g->T[0] * g->T[1] * g->T[2] * 4 > 110 * 1024) g->T[0] >>= 1;
+    g->T[0] = 16;                  // <= 16: a row's survivors are a 16-bit mask
+    while (g->T[0] > 1 && (size_t)g->T[0] * g->T[1] * g->T[2] * sizeof(uint16_t) > 56 * 1024) g->T[0] >>= 1;
     for (int a = 0; a < 3; ++a) g->nt[a] = (g->D[a] + g->T[a] - 1) / g->T[a];
     g->ntiles = g->nt[0] * g->nt[1] * g->nt[2];
     return OCTA_OK;
@@ -550,13 +616,13 @@ extern "C" int octa_voxelize_batch_dev(const double* edges7_dev, const int64_t* 
                                                         w.tile_edges);
         octa::count_launch();
     }
-    const size_t smem = (size_t)g.T[0] * g.T[1] * g.T[2] * sizeof(uint32_t);
+    const size_t smem = octa::align_up((size_t)g.T[0] * g.T[1] * g.T[2] * sizeof(uint16_t), 16);
     static size_t smem_set = 0;
     if (smem > smem_set) {
         OCTA_CUDA_CHECK(cudaFuncSetAttribute(vox_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
-    dim3 grid((unsigned)g.ntiles, (unsigned)n_graphs);
+    dim3 grid((unsigned)(g.nt[1] * g.nt[2]), (unsigned)g.nt[0], (unsigned)n_graphs);
     vox_tile_kernel<<<grid, VOX_THREADS, smem, stream>>>(w.prep, w.edge_offsets, g, w.tile_start, w.tile_edges,
                                                          w.big_count, w.big_idx, out_dev);
     octa::count_launch();
