@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-for ty in 16 32; do
-OCTA_VOX_TILE_Y=$ty timeout 600 python bench.py --no-cpu-baseline --steps 3 > gpurun_out/bench_ty$ty.log 2>&1; tail -1 gpurun_out/bench_ty$ty.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print($ty, d['value'], d['config']['phase_ms'], d['roofline']['frac'])"
-done
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -5 gpurun_out/pytest_gpu.log
+OCTA_GROW_TIMING=1 timeout 300 python tools/grow_probe.py --batch 64 --check 24 > gpurun_out/probe.log 2>&1; grep -E "timing|rep 1|k_commit|replay|parity" gpurun_out/probe.log | tail -6
+OCTA_GROW_TIMING=1 timeout 300 python tools/grow_probe.py --batch 1 2>&1 | grep -E "timing|rep 1" | tail -2

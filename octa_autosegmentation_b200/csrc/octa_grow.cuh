@@ -20,6 +20,7 @@ struct IterP {
     double faz_cx, faz_cy, param_scale, shape[3];
     int N, t, first_mode, mode_idx, iter;
     double kap_tab[9];   // kappa of the node's creation mode (arterial_tree.py:32); [8] = 4, the add_node default of the stumps
+    double leafc_tab[9]; // r ** kap_tab[q]: what a fresh leaf contributes to a parent of creation mode q (see GrowDev::ncon)
 };
 
 enum PropType : int { P_NONE = 0, P_LEAF_ELONG = 1, P_LEAF_DRAW = 2, P_LEAF_BIF = 3, P_INTER_DRAW = 4, P_INTER_EMPTY = 5 };
@@ -28,33 +29,31 @@ struct Proposal {
     int type;
     int cond;          // leaf: angle(vtc, avg) > 90 ; inter: angle(vtc, avg) <= 90
     double ratio5;     // (dist_to_center / (2 FAZ_radius)) ** 5
-    double r1_used;    // inter-node: child radius the evaluation was made with
+    double c_used;     // inter-node: ncon value of the distal child the evaluation was made with
     double p[3];       // elongation / sprout position
     double b1[3], b2[3];  // bifurcation children
 };
 
-// packed per-node record of everything the sequential replay touches (one 32-byte load per tree step)
-struct __align__(32) TreeRec {
-    double R;                  // in-loop (steering) radius, mirrors nrad
-    int par, c0, c1;
-    int slot, slot_call;       // dict rank of this node in grow call `slot_call`
-    unsigned char nch, kmode, dirty, pad;
-};
-
-struct __align__(16) ActDec {  // decision record of one acting dict entry
+struct __align__(16) ActDec {  // decision record of one dict entry the replay has to look at
     int e, nd, type, cond;
-    double ratio5, pad;
+    double ratio5, c_used;
 };
 
 struct GrowShape {
     int G, capN, capS, Nmax, pycap;
     int exact_ball_order;   // 1: rebuild cKDTree's index permutation for the O2->CO2 insertion order (exact); 0: list-index order
-    int commit_smem; // bytes of dynamic shared memory of k_commit (parent/dirty/tag mirrors + decision records)
+    int commit_smem; // bytes of dynamic shared memory of k_commit (tree mirror + decision records)
 };
 
 struct GrowDev {
     // vessel nodes, [f][g*capN + i]
-    double *nx[2], *ny[2], *nz[2], *nrad[2];
+    double *nx[2], *ny[2], *nz[2];
+    // Steering radii are kept as Murray CONTRIBUTIONS: ncon[n] = radius(n) ** kappa(parent(n)), so that a parent's
+    // update (arterial_tree.py:174-184, r_p = (sum r_c**k)**(1/k)) is a plain sum of its children's ncon and a
+    // pow is needed only where parent and grandparent were created in modes of different kappa, and when a
+    // radius itself is wanted (k_eval / k_commit: the distal radius of an inter-node).  These values only steer
+    // directions; the radii that get PRINTED are recomputed on the host with libm pow (octa_grow_host.cu).
+    double *ncon[2];
     int *npar[2], *nch0[2], *nch1[2];
     unsigned char *nnch[2], *nmeta[2], *deact[2];      // deact: the node branched and left the ACTIVE set
     int *n_nodes[2], *n_prev[2];
@@ -81,15 +80,15 @@ struct GrowDev {
     int* n_cand;
     unsigned char *cpass, *cstate;
     int* plist;
-    int *assign, *first, *cnt, *slot, *cur, *rtag;
+    int *assign, *first, *cnt, *slot, *cur;
     int *dict_node, *n_dict, *list_off, *list, *sc_idx;
     double *sc_ang;
     double *sc_inter;     // per (inter-node, attractor): angle to distal / proximal segment and unit vector (5 doubles)
     Proposal* prop;
     ActDec* adec;         // decision records (global fallback when they do not fit in k_commit's shared memory)
     int4* newl;
-    TreeRec* rec[2];
-    int *alist;           // k_commit scratch: start nodes of the bottom-up radius refresh
+    int *alist;           // k_commit scratch: start nodes of the bottom-up refresh
+    unsigned int* cbits;  // k_commit scratch, [g][4][capN/32]: dirty / arrival / inter / tag bitmaps when the tree does not fit in shared memory
     int *hitj, *hl, *ta, *seq;
     int *kd_idx, *kd_posL, *kd_posR, *kd_rank, *kd_nodes;
     unsigned char* veto;
@@ -98,7 +97,7 @@ struct GrowDev {
     int* set_key;
     int* err;
     int* trace;     // [g][iter][4]
-    long long* dbg;       // [g][8] k_commit replay breakdown (cycles: tag scan, walks, rechecks; counts: entries, events, walk steps, tags, records)
+    long long* dbg;       // [g][8] k_commit replay breakdown (cycles: -, walks, rechecks; counts: entries, events, walk steps, re-evaluations, records)
     long long* counters;  // [g][8] byte-accounting counters (sum_A, sum_M, sum_P, sum_S, ...)
 };
 

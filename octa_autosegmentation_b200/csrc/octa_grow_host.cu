@@ -18,6 +18,8 @@
 
 namespace octa {
 
+void grow_timing_begin(cudaStream_t st);
+void grow_timing_report();
 void launch_iteration(const GrowDev& D, const GrowShape& S, const IterP& P, int n_sm, cudaStream_t st, cudaStream_t side,
                       cudaEvent_t ev_sinks, cudaEvent_t ev_kd);
 int prepare_kernels(const GrowShape& S);
@@ -169,6 +171,7 @@ void build_schedule(const OctaGrowConfig& c, std::vector<IterP>* out) {
             P.N = N; P.t = t; P.first_mode = m.first_mode; P.mode_idx = mi; P.iter = iter++;
             for (int q = 0; q < 8; ++q) P.kap_tab[q] = q < c.n_modes ? c.modes[q].kappa : 4.0;
             P.kap_tab[8] = 4.0;
+            for (int q = 0; q < 9; ++q) P.leafc_tab[q] = pow(P.r, P.kap_tab[q]);
             out->push_back(P);
             sigma_t = sigma_t + delta_sigma;
             eps_k = orig[0] / sigma_t; eps_n = orig[1] / sigma_t; eps_s = orig[2] / sigma_t;
@@ -195,7 +198,7 @@ void carve(Carver& c, const GrowShape& S, GrowDev* D) {
     const size_t GN = (size_t)S.G * S.capN, GS = (size_t)S.G * S.capS, GC = (size_t)S.G * S.Nmax, G = S.G;
     for (int f = 0; f < 2; ++f) {
         D->nx[f] = c.take<double>(GN); D->ny[f] = c.take<double>(GN); D->nz[f] = c.take<double>(GN);
-        D->nrad[f] = c.take<double>(GN);
+        D->ncon[f] = c.take<double>(GN);
         D->npar[f] = c.take<int>(GN); D->nch0[f] = c.take<int>(GN); D->nch1[f] = c.take<int>(GN);
         D->nnch[f] = c.take<unsigned char>(GN); D->nmeta[f] = c.take<unsigned char>(GN); D->deact[f] = c.take<unsigned char>(GN);
         D->n_nodes[f] = c.take<int>(G); D->n_prev[f] = c.take<int>(G);
@@ -217,11 +220,11 @@ void carve(Carver& c, const GrowShape& S, GrowDev* D) {
     D->n_cand = c.take<int>(G); D->cpass = c.take<unsigned char>(GC); D->cstate = c.take<unsigned char>(GC);
     D->plist = c.take<int>(GC);
     D->assign = c.take<int>(GS);
-    D->first = c.take<int>(GN); D->cnt = c.take<int>(GN); D->slot = c.take<int>(GN); D->cur = c.take<int>(GN); D->rtag = c.take<int>(GN);
+    D->first = c.take<int>(GN); D->cnt = c.take<int>(GN); D->slot = c.take<int>(GN); D->cur = c.take<int>(GN);
     D->dict_node = c.take<int>(GN); D->n_dict = c.take<int>(G); D->list_off = c.take<int>(G * (S.capN + 1));
     D->list = c.take<int>(GS); D->sc_idx = c.take<int>(GS); D->sc_ang = c.take<double>(GS); D->sc_inter = c.take<double>(5 * GS);
     D->prop = c.take<Proposal>(GN); D->adec = c.take<ActDec>(GN); D->newl = c.take<int4>(GN);
-    D->rec[0] = c.take<TreeRec>(GN); D->rec[1] = c.take<TreeRec>(GN); D->alist = c.take<int>(GN);
+    D->alist = c.take<int>(GN); D->cbits = c.take<unsigned int>((size_t)S.G * 4 * ((S.capN + 31) / 32));
     D->hitj = c.take<int>(GS); D->hl = c.take<int>(GS); D->ta = c.take<int>(GS); D->seq = c.take<int>(GS);
     D->veto = c.take<unsigned char>(GS);
     D->kd_idx = c.take<int>(GS); D->kd_posL = c.take<int>(GS); D->kd_posR = c.take<int>(GS); D->kd_rank = c.take<int>(GS);
@@ -413,11 +416,10 @@ static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, doub
         // staging layout: per array a dense [G][n0] block
         size_t off = 0;
         auto blk = [&](size_t elem) { size_t o = off; off = align_up(off + elem * G * n0, 256); return o; };
-        size_t o_x[2], o_y[2], o_z[2], o_r[2], o_k[2], o_p[2], o_c0[2], o_c1[2], o_act[2], o_n[2], o_m[2], o_rec[2];
+        size_t o_x[2], o_y[2], o_z[2], o_r[2], o_k[2], o_p[2], o_c0[2], o_c1[2], o_act[2], o_n[2], o_m[2];
         for (int f = 0; f < 2; ++f) {
             o_x[f] = blk(8); o_y[f] = blk(8); o_z[f] = blk(8); o_r[f] = blk(8); o_k[f] = blk(8);
             o_p[f] = blk(4); o_c0[f] = blk(4); o_c1[f] = blk(4); o_act[f] = blk(4); o_n[f] = blk(1); o_m[f] = blk(1);
-            o_rec[f] = blk(sizeof(TreeRec));
         }
         const size_t o_mt_np = off; off = align_up(off + sizeof(MTState) * G, 256);
         const size_t o_mt_py = off; off = align_up(off + sizeof(MTState) * G, 256);
@@ -437,18 +439,11 @@ static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, doub
                 int* hp = (int*)(sg + o_p[f]) + (size_t)g * n0; int* hc0 = (int*)(sg + o_c0[f]) + (size_t)g * n0;
                 int* hc1 = (int*)(sg + o_c1[f]) + (size_t)g * n0; int* hact = (int*)(sg + o_act[f]) + (size_t)g * n0;
                 unsigned char* hn = (unsigned char*)(sg + o_n[f]) + (size_t)g * n0; unsigned char* hm = (unsigned char*)(sg + o_m[f]) + (size_t)g * n0;
-                TreeRec* hrec = (TreeRec*)(sg + o_rec[f]) + (size_t)g * n0;
                 for (int i = 0; i < n0; ++i) { hc0[i] = -1; hc1[i] = -1; hn[i] = 0; }
                 for (int i = 0; i < n0; ++i) {
                     hx[i] = h.pos[f][3 * i]; hy[i] = h.pos[f][3 * i + 1]; hz[i] = h.pos[f][3 * i + 2];
-                    hr[i] = r0; hk[i] = 4.0; hp[i] = h.parent[f][i]; hact[i] = i; hm[i] = 0xff;
+                    hr[i] = pow(r0, 4.0) /* ncon: every initial node hangs below a kappa-4 node */; hk[i] = 4.0; hp[i] = h.parent[f][i]; hact[i] = i; hm[i] = 0xff;
                     if (hp[i] >= 0) { hc0[hp[i]] = i; hn[hp[i]] = 1; }
-                }
-                for (int i = 0; i < n0; ++i) {
-                    TreeRec r;
-                    r.R = r0; r.par = hp[i]; r.c0 = hc0[i]; r.c1 = -1; r.slot = 0; r.slot_call = 0;
-                    r.nch = hn[i]; r.kmode = 8; r.dirty = 0; r.pad = 0;
-                    hrec[i] = r;
                 }
             }
             ((MTState*)(sg + o_mt_np))[g] = h.np_mt;
@@ -465,11 +460,10 @@ static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, doub
         for (int f = 0; f < 2; ++f) {
             const size_t cn = S.capN;
             OCTA_CUDA_CHECK(up2d(D.nx[f], 8 * cn, sg + o_x[f], 8)); OCTA_CUDA_CHECK(up2d(D.ny[f], 8 * cn, sg + o_y[f], 8));
-            OCTA_CUDA_CHECK(up2d(D.nz[f], 8 * cn, sg + o_z[f], 8)); OCTA_CUDA_CHECK(up2d(D.nrad[f], 8 * cn, sg + o_r[f], 8));
+            OCTA_CUDA_CHECK(up2d(D.nz[f], 8 * cn, sg + o_z[f], 8)); OCTA_CUDA_CHECK(up2d(D.ncon[f], 8 * cn, sg + o_r[f], 8));
             OCTA_CUDA_CHECK(up2d(D.npar[f], 4 * cn, sg + o_p[f], 4));
             OCTA_CUDA_CHECK(up2d(D.nch0[f], 4 * cn, sg + o_c0[f], 4)); OCTA_CUDA_CHECK(up2d(D.nch1[f], 4 * cn, sg + o_c1[f], 4));
             OCTA_CUDA_CHECK(up2d(D.nnch[f], cn, sg + o_n[f], 1)); OCTA_CUDA_CHECK(up2d(D.nmeta[f], cn, sg + o_m[f], 1));
-            OCTA_CUDA_CHECK(up2d(D.rec[f], sizeof(TreeRec) * cn, sg + o_rec[f], sizeof(TreeRec)));
             OCTA_CUDA_CHECK(cudaMemsetAsync(D.deact[f], 0, G * cn, st));
             OCTA_CUDA_CHECK(cudaMemcpyAsync(D.n_nodes[f], sg + o_cnt, 4 * G, cudaMemcpyHostToDevice, st));
             OCTA_CUDA_CHECK(cudaMemcpyAsync(D.n_act[f], sg + o_cnt, 4 * G, cudaMemcpyHostToDevice, st));
@@ -484,12 +478,13 @@ static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, doub
         OCTA_CUDA_CHECK(cudaMemsetAsync(D.py_n, 0, 4 * G, st)); OCTA_CUDA_CHECK(cudaMemsetAsync(D.py_pos, 0, 4 * G, st));
         OCTA_CUDA_CHECK(cudaMemsetAsync(D.py_draws, 0, 8 * G, st)); OCTA_CUDA_CHECK(cudaMemsetAsync(D.counters, 0, 64 * G, st)); OCTA_CUDA_CHECK(cudaMemsetAsync(D.dbg, 0, 64 * G, st));
         OCTA_CUDA_CHECK(cudaMemsetAsync(D.err, 0, 4 * G, st));
-        OCTA_CUDA_CHECK(cudaMemsetAsync(D.rtag, 0, 4 * G * S.capN, st));
+        OCTA_CUDA_CHECK(cudaMemsetAsync(D.cbits, 0, sizeof(unsigned int) * G * 4 * ((S.capN + 31) / 32), st));
         if (trace) OCTA_CUDA_CHECK(cudaMemsetAsync(D.trace, 0, sizeof(int) * G * 4096 * 4, st));
         OCTA_CUDA_CHECK(cudaStreamSynchronize(st));      // the staging buffer is reused for the read-back
     }
     if (!trace) D.trace = nullptr;
     OCTA_CUDA_CHECK(cudaEventRecord(ctx->e0, st));
+    grow_timing_begin(st);
     for (const IterP& P : ctx->sched) launch_iteration(D, S, P, ctx->n_sm, st, ctx->side, ctx->ev_sinks, ctx->ev_kd);
     OCTA_CUDA_CHECK(cudaEventRecord(ctx->e1, st));
     // ---- read back: counts first, then strided copies of the live prefix of every node array
@@ -509,6 +504,7 @@ static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, doub
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->e0, ctx->e1);
     if (device_ms) *device_ms = ms;
+    grow_timing_report();
     if (trace) OCTA_CUDA_CHECK(cudaMemcpy(trace, D.trace, sizeof(int) * G * 4096 * 4, cudaMemcpyDeviceToHost));
     size_t mx[2] = {1, 1};
     for (int f = 0; f < 2; ++f) for (int g = 0; g < n_graphs; ++g) mx[f] = std::max<size_t>(mx[f], (size_t)nn[f][g]);

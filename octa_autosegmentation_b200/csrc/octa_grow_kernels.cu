@@ -13,6 +13,10 @@
 //   k_kill          greenhouse.py:99-123    kill-radius prune, O2 -> CO2 through a CPython-set emulation
 // Bit-level conventions are documented in octa_grow_math.cuh.  This TU is compiled with -fmad=false.
 #include "octa_common.h"
+#include <stdio.h>
+#include <stdlib.h>
+#include <type_traits>
+#include <vector>
 #include "octa_eig3.h"
 #include "octa_grow.cuh"
 #include "octa_grow_math.cuh"
@@ -198,7 +202,7 @@ __device__ __forceinline__ int grid_cell(double v) {
 }
 
 // which: 0 = all arterial nodes (+radius), 1 = O2 sinks, 2 / 3 = active arterial / venous nodes
-__device__ __forceinline__ void grid_build_body(const GrowDev& D, const GrowShape& S, int which, int g) {
+__device__ __forceinline__ void grid_build_body(const GrowDev& D, const GrowShape& S, const IterP& P, int which, int g) {
     __shared__ int hist[GRID * GRID];
     __shared__ int cursor[GRID * GRID];
     const int tid = threadIdx.x;
@@ -210,7 +214,7 @@ __device__ __forceinline__ void grid_build_body(const GrowDev& D, const GrowShap
     const unsigned char* skip = nullptr;
     int n;
     size_t cap;
-    if (which == 0) { cap = S.capN; px = D.nx[0] + g * cap; py = D.ny[0] + g * cap; pz = D.nz[0] + g * cap; pr = D.nrad[0] + g * cap; n = D.n_nodes[0][g]; }
+    if (which == 0) { cap = S.capN; px = D.nx[0] + g * cap; py = D.ny[0] + g * cap; pz = D.nz[0] + g * cap; pr = D.ncon[0] + g * cap; n = D.n_nodes[0][g]; }
     else if (which == 1) { cap = S.capS; px = D.sx[0] + g * cap; py = D.sy[0] + g * cap; pz = D.sz[0] + g * cap; n = D.n_s[0][g]; }
     else { const int f = which - 2; cap = S.capN; px = D.nx[f] + g * cap; py = D.ny[f] + g * cap; pz = D.nz[f] + g * cap; n = D.n_nodes[f][g]; skip = D.deact[f] + g * cap; }
     const size_t gcap = S.capN > S.capS ? S.capN : S.capS;
@@ -245,18 +249,29 @@ __device__ __forceinline__ void grid_build_body(const GrowDev& D, const GrowShap
         const double x = px[i], y = py[i];
         const int pos = atomicAdd(&cursor[grid_cell(y) * GRID + grid_cell(x)], 1);
         gx[pos] = x; gy[pos] = y; gz[pos] = pz[i]; gi[pos] = i;
-        if (pr) grd[pos] = pr[i];
+        if (pr) {
+            // radius from the Murray contribution: ncon = radius ** kappa(parent); leaves and unbranched chains carry r itself
+            const int par = D.npar[0][g * cap + i];
+            double rad = P.r;
+            if (par >= 0) {
+                const int m = D.nmeta[0][g * cap + par];
+                const int kmp = m == 0xff ? 8 : (m >> 1);
+                const double cv = pr[i];
+                if (cv != P.leafc_tab[kmp]) rad = fast_pow(cv, 1.0 / P.kap_tab[kmp]);
+            }
+            grd[pos] = rad;
+        }
     }
 }
 
-__global__ void __launch_bounds__(1024) k_grid_build(GrowDev D, GrowShape S, int which) { grid_build_body(D, S, which, blockIdx.x); }
+__global__ void __launch_bounds__(1024) k_grid_build(GrowDev D, GrowShape S, IterP P, int which) { grid_build_body(D, S, P, which, blockIdx.x); }
 
 // k_prepare: everything an iteration needs that depends only on the state left by the previous iteration, in ONE
 // launch: blockIdx.y = 0..3 -> the four bucket grids (arterial nodes, O2 sinks, active arterial / venous nodes; the
 // venous set does not change before the venous commit), blockIdx.y = 4 -> the candidate sampler.  5*G CTAs run
 // side by side instead of five dependent single-wave launches.
 __global__ void __launch_bounds__(1024) k_prepare(GrowDev D, GrowShape S, IterP P) {
-    if (blockIdx.y < 4) grid_build_body(D, S, (int)blockIdx.y, blockIdx.x);
+    if (blockIdx.y < 4) grid_build_body(D, S, P, (int)blockIdx.y, blockIdx.x);
     else sample_body(D, S, P, blockIdx.x);
 }
 
@@ -429,7 +444,6 @@ __global__ void __launch_bounds__(1024) k_group(GrowDev D, GrowShape S, IterP P,
     const int* asg = D.assign + sb;
     int* first = D.first + nb; int* cnt = D.cnt + nb; int* slot = D.slot + nb; int* cur = D.cur + nb;
     int* dict = D.dict_node + nb; int* loff = D.list_off + (size_t)g * (S.capN + 1); int* lst = D.list + sb;
-    TreeRec* rec = D.rec[f] + nb;
     for (int a = tid; a < A; a += blockDim.x) {
         const int nd = asg[a];
         if (nd >= 0) { atomicMin(&first[nd], a); atomicAdd(&cnt[nd], 1); }
@@ -442,7 +456,7 @@ __global__ void __launch_bounds__(1024) k_group(GrowDev D, GrowShape S, IterP P,
         if (a < A) { nd = asg[a]; isf = (nd >= 0 && first[nd] == a); }
         int total;
         const int incl = block_scan_incl(isf, &total);
-        if (isf) { const int rk = nd_ + incl - 1; dict[rk] = nd; slot[nd] = rk; rec[nd].slot = rk; rec[nd].slot_call = call_id; }
+        if (isf) { const int rk = nd_ + incl - 1; dict[rk] = nd; slot[nd] = rk; }
         nd_ += total;
     }
     __syncthreads();
@@ -632,12 +646,12 @@ __device__ void eval_leaf(const GrowDev& D, const GrowShape& S, const IterP& P, 
 // `cache_mode`: 1 = store the radius-independent per-attractor terms (two angles, unit vector) for a later
 // re-evaluation, 2 = re-evaluate from that cache (k_commit, when the distal radius changed inside the call), 0 = neither.
 __device__ void eval_inter(const GrowDev& D, const GrowShape& S, const IterP& P, int g, int f, const NodeCtx& nc,
-                           const int* lst, int n, double r1, Proposal* pr, int cache_mode) {
+                           const int* lst, int n, double r1, double c_used, Proposal* pr, int cache_mode) {
     const size_t sb = (size_t)g * S.capS;
     const double* sx = D.sx[f] + sb; const double* sy = D.sy[f] + sb; const double* sz = D.sz[f] + sb;
     double* cache = D.sc_inter + (sb + (lst - (D.list + sb))) * 5;
     pr->type = P_INTER_EMPTY;
-    pr->r1_used = r1;
+    pr->c_used = c_used;
     double phi1, phi2;
     murray_angles(r1, P.r, P.kappa, &phi1, &phi2);
     const double dseg[3] = {nc.ch[0] - nc.pos[0], nc.ch[1] - nc.pos[1], nc.ch[2] - nc.pos[2]};
@@ -706,78 +720,147 @@ __global__ void __launch_bounds__(128) k_eval(GrowDev D, GrowShape S, IterP P, i
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nd_; e += gridDim.x * blockDim.x) {
         const int nd = D.dict_node[nb + e];
         Proposal pr;
-        pr.type = P_NONE; pr.cond = 0; pr.ratio5 = 0; pr.r1_used = 0;
+        pr.type = P_NONE; pr.cond = 0; pr.ratio5 = 0; pr.c_used = 0;
         NodeCtx nc;
         load_ctx(D, S, P, g, f, nd, &nc);
         const int* lst = D.list + sb + loff[e];
         const int n = loff[e + 1] - loff[e];
         if (nc.nch == 0) eval_leaf(D, S, P, g, f, e, nc, lst, n, &pr);
-        else if (nc.parent >= 0 && nc.nch == 1) eval_inter(D, S, P, g, f, nc, lst, n, D.nrad[f][nb + D.nch0[f][nb + nd]], &pr, 1);
+        else if (nc.parent >= 0 && nc.nch == 1) {
+            // distal radius from the child's Murray contribution (GrowDev::ncon)
+            const double cv = D.ncon[f][nb + D.nch0[f][nb + nd]];
+            const int m = D.nmeta[f][nb + nd];
+            eval_inter(D, S, P, g, f, nc, lst, n, fast_pow(cv, 1.0 / P.kap_tab[m == 0xff ? 8 : (m >> 1)]), cv, &pr, 1);
+        }
         D.prop[nb + e] = pr;
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // k_commit: one CTA per graph.
-//   prologue (all threads)  compacts the dict entries that can act into 32-byte decision records;
-//   replay   (thread 0)     walks them in dict order: Python-RNG draws, branch decisions, node ids, tree links.
-//                           It touches only L1-resident decision records and the packed 32-byte tree records
-//                           (one load per step of a dirty-marking walk) -- no positions, no pow;
-//   epilogue (all threads)  writes the new nodes' SoA fields, refreshes the dirty Murray radii bottom-up
-//                           (a node is computed by whichever thread completes its last dirty child), and
-//                           updates the active list by a stable compaction.
+//   prologue (all threads)  mirrors the forest's topology and Murray contributions (GrowDev::ncon) in shared memory
+//                           and compacts the dict entries the replay has to look at into 32-byte decision records;
+//   replay   (thread 0)     walks them in dict order: Python-RNG draws, branch decisions, node ids, tree links --
+//                           shared-memory traffic only, except for the re-evaluation of an inter-node;
+//   epilogue (all threads)  writes the new nodes' SoA fields, refreshes the contributions still dirty bottom-up
+//                           (a node is computed by whichever chain reaches it last) and writes them back.
 // Radii inside a call are LAZY (arterial_tree.py:174-184 is order-insensitive up to rounding): a branch event only
-// marks its ancestor chain dirty, stopping at the first already-dirty node, and tags later inter-node dict
-// entries whose distal radius it changes; only a tagged entry refreshes (the dirty part of) its distal subtree and
-// is re-evaluated.  Single-child nodes carry their child's radius ((x^k)^(1/k) = x).  The radii that get
-// PRINTED are recomputed on the host with libm pow (octa_grow_host.cu).
+// marks its ancestor chain dirty, stopping at the first already-dirty node.  An inter-node entry refreshes the dirty
+// part of its distal subtree when its turn comes and is re-evaluated if the distal contribution differs from the one
+// k_eval used.  With contributions instead of radii a refresh step is an addition; pow appears only across creation
+// modes of different kappa.
+// `SM` = the tree fits the shared-memory mirror (16-bit node ids); otherwise the same code runs on the global arrays.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ double murray_parent(const IterP& P, int kmode, double ra, double rb) {
-    const double kap = P.kap_tab[kmode];
-    return fast_pow(fast_pow(ra, kap) + fast_pow(rb, kap), 1 / kap);
+template <bool SM>
+struct TreeView {
+    // SM: shared-memory mirror, 16-bit links (0xffff = none); !SM: the global SoA arrays themselves
+    typename std::conditional<SM, unsigned short, int>::type *par, *c0, *c1;
+    double* C;
+    typename std::conditional<SM, unsigned short, int>::type *slot;   // dict rank of the inter-node entries of this call
+    unsigned char* km;           // SM: creation-mode index; !SM: nmeta (decoded on access)
+    unsigned int *dirty, *arr;   // by node: contribution is stale / one child of a bifurcation has arrived (epilogue)
+    unsigned int *inter, *tag;   // by node: is an inter-node dict entry of this call; by dict rank: re-check pending
+    int n_before;
+    __device__ __forceinline__ int get_par(int n) const { if (SM) { const int v = par[n]; return v == 0xffff ? -1 : v; } return par[n]; }
+    __device__ __forceinline__ int get_c0(int n) const { if (SM) { const int v = c0[n]; return v == 0xffff ? -1 : v; } return c0[n]; }
+    __device__ __forceinline__ int get_c1(int n) const { if (SM) { const int v = c1[n]; return v == 0xffff ? -1 : v; } return c1[n]; }
+    __device__ __forceinline__ void set_c0(int n, int v) { c0[n] = v; }
+    __device__ __forceinline__ void set_c1(int n, int v) { c1[n] = v; }
+    __device__ __forceinline__ int kmode(int n) const { if (SM) return km[n]; const int m = km[n]; return m == 0xff ? 8 : (m >> 1); }
+    __device__ __forceinline__ bool is_dirty(int n) const { return n < n_before && ((dirty[n >> 5] >> (n & 31)) & 1u); }
+    __device__ __forceinline__ void set_dirty(int n) { dirty[n >> 5] |= 1u << (n & 31); }
+    __device__ __forceinline__ void clr_dirty(int n) { dirty[n >> 5] &= ~(1u << (n & 31)); }
+    __device__ __forceinline__ bool is_inter(int n) const { return (inter[n >> 5] >> (n & 31)) & 1u; }
+    __device__ __forceinline__ bool is_tagged(int rk) const { return (tag[rk >> 5] >> (rk & 31)) & 1u; }
+    __device__ __forceinline__ void set_tag(int rk) { tag[rk >> 5] |= 1u << (rk & 31); }
+    __device__ __forceinline__ void clr_tag(int rk) { tag[rk >> 5] &= ~(1u << (rk & 31)); }
+    __device__ __forceinline__ int next_tag(int from, int lim) const {      // first tagged rank in [from, lim), or -1
+        int q = from;
+        while (q < lim) {
+            const unsigned int wv = tag[q >> 5] >> (q & 31);
+            if (wv) { const int r = q + __ffs(wv) - 1; return r < lim ? r : -1; }
+            q = (q | 31) + 1;
+        }
+        return -1;
+    }
+};
+
+// contribution of node n (children c0, c1; at least one) to its parent; vol = read children through volatile loads
+template <bool SM, bool VOL>
+__device__ __forceinline__ double node_contribution(const TreeView<SM>& T, const IterP& P, int n, int c0, int c1) {
+    const int kmn = T.kmode(n);
+    auto cv = [&](int c) -> double {        // nodes created in this call are leaves of radius r
+        if (c >= T.n_before) return P.leafc_tab[kmn];
+        return VOL ? *(volatile double*)(T.C + c) : T.C[c];
+    };
+    double s = cv(c0);
+    if (c1 >= 0) s = s + cv(c1);
+    const int p = T.get_par(n);
+    const double kn = P.kap_tab[kmn], kp = P.kap_tab[T.kmode(p)];
+    return kp == kn ? s : fast_pow(s, kp / kn);
 }
 
-__global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P, int f) {
+template <bool SM>
+__device__ void commit_body(const GrowDev& D, const GrowShape& S, const IterP& P, int f, int* s_dyn) {
     const int g = blockIdx.x, tid = threadIdx.x;
-    if (D.err[g]) return;
-    const int call_id = 2 * P.iter + f + 1;
     const size_t sb = (size_t)g * S.capS, nb = (size_t)g * S.capN;
     const int nd_ = D.n_dict[g];
     Proposal* prop = D.prop + nb;
     ActDec* adec = D.adec + nb;      // (re-pointed to shared memory below when it fits)
     int4* newl = D.newl + nb;
-    TreeRec* rec = D.rec[f] + nb;
     const int* dict = D.dict_node + nb;
-    __shared__ int s_nnew, s_err;
-    // shared-memory mirror of what the dirty-marking walks touch: parent pointers, dirty bits, "is an inter-node
-    // dict entry of this call" bits -- a walk step costs a shared-memory load instead of an L2 round trip
-    extern __shared__ __align__(16) int s_dyn[];
+    __shared__ int s_nnew, s_err, s_nstart, s_marked;
     const int n_before = D.n_nodes[f][g];
     const int nwords = (n_before + 31) >> 5;
     const int budget_words = S.commit_smem / 4;
-    const bool use_smem = n_before + 5 * nwords <= budget_words;
-    int* s_par = s_dyn;
-    unsigned int* s_dirty = (unsigned int*)(s_dyn + n_before);
-    unsigned int* s_inter = s_dirty + nwords;
-    unsigned int* s_tag = s_inter + nwords;                      // recheck tags, indexed by dict rank
-    unsigned int* s_bif = s_tag + nwords;                        // node has two children
-    unsigned int* s_arr = s_bif + nwords;                        // refresh: one child of a bifurcation has arrived
+    TreeView<SM> T;
+    T.n_before = n_before;
+    int off_words = 0;
+    if (SM) {
+        // layout: C [n] f64 | par, c0, c1, slot [n] u16 | km [n] u8 | dirty, arr, inter, tag [nwords] u32
+        T.C = reinterpret_cast<double*>(s_dyn);
+        unsigned short* h = reinterpret_cast<unsigned short*>(T.C + n_before);
+        T.par = (decltype(T.par))h; T.c0 = (decltype(T.c0))(h + n_before); T.c1 = (decltype(T.c1))(h + 2 * n_before);
+        T.slot = (decltype(T.slot))(h + 3 * n_before);
+        T.km = reinterpret_cast<unsigned char*>(h + 4 * n_before);
+        const size_t bytes = (((size_t)n_before * 17 + 3) & ~(size_t)3);
+        T.dirty = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(s_dyn) + bytes);
+        T.arr = T.dirty + nwords; T.inter = T.arr + nwords; T.tag = T.inter + nwords;
+        off_words = (int)((bytes / 4 + 4 * nwords + 3) & ~(size_t)3);
+    } else {
+        T.C = D.ncon[f] + nb;
+        T.par = (decltype(T.par))(D.npar[f] + nb); T.c0 = (decltype(T.c0))(D.nch0[f] + nb); T.c1 = (decltype(T.c1))(D.nch1[f] + nb);
+        T.slot = (decltype(T.slot))(D.slot + nb);
+        T.km = D.nmeta[f] + nb;
+        const size_t cw = (S.capN + 31) / 32;
+        T.dirty = D.cbits + (size_t)g * 4 * cw;
+        T.arr = T.dirty + cw; T.inter = T.arr + cw; T.tag = T.inter + cw;
+    }
     // the decision records and the Python-stream words of this call also live in shared memory when they fit
-    const int off_words = use_smem ? ((n_before + 5 * nwords + 3) & ~3) : 0;
     const bool dec_smem = (size_t)nd_ * sizeof(ActDec) + (size_t)(2 * nd_ + 2) * 4 + 64 <= (size_t)(budget_words - off_words) * 4;
     ActDec* adec_s = reinterpret_cast<ActDec*>(s_dyn + off_words);
     unsigned int* pb_s = reinterpret_cast<unsigned int*>(adec_s + nd_);
     if (dec_smem) adec = adec_s;
     const long long t_start = clock64();
-    if (use_smem) {
-        for (int i = tid; i < n_before; i += blockDim.x) s_par[i] = D.npar[f][nb + i];
-        for (int i = tid; i < nwords; i += blockDim.x) { s_dirty[i] = 0; s_inter[i] = 0; s_tag[i] = 0; s_bif[i] = 0; s_arr[i] = 0; }
-        __syncthreads();
-        for (int i = tid; i < n_before; i += blockDim.x)
-            if (D.nnch[f][nb + i] >= 2) atomicOr(&s_bif[i >> 5], 1u << (i & 31));
-        for (int e = tid; e < nd_; e += blockDim.x) {
-            const int t = prop[e].type;
-            if (t == P_INTER_DRAW || t == P_INTER_EMPTY) { const int nd = dict[e]; atomicOr(&s_inter[nd >> 5], 1u << (nd & 31)); }
+    if (SM) {
+        const int* gpar = D.npar[f] + nb; const int* gc0 = D.nch0[f] + nb; const int* gc1 = D.nch1[f] + nb;
+        const double* gC = D.ncon[f] + nb; const unsigned char* gm = D.nmeta[f] + nb;
+        for (int i = tid; i < n_before; i += blockDim.x) {
+            T.C[i] = gC[i];
+            T.par[i] = (unsigned short)gpar[i]; T.c0[i] = (unsigned short)gc0[i]; T.c1[i] = (unsigned short)gc1[i];   // -1 -> 0xffff
+            const int m = gm[i];
+            T.km[i] = (unsigned char)(m == 0xff ? 8 : (m >> 1));
+        }
+    }
+    for (int i = tid; i < nwords; i += blockDim.x) { T.dirty[i] = 0; T.arr[i] = 0; T.inter[i] = 0; T.tag[i] = 0; }
+    if (tid == 0) { s_nstart = 0; s_marked = 0; }
+    __syncthreads();
+    for (int e = tid; e < nd_; e += blockDim.x) {
+        const int t = prop[e].type;
+        if (t == P_INTER_DRAW || t == P_INTER_EMPTY) {
+            const int nd = dict[e];
+            atomicOr(&T.inter[nd >> 5], 1u << (nd & 31));
+            if (SM) T.slot[nd] = (unsigned short)e;
         }
     }
     const int ppos0 = D.py_pos[g];
@@ -785,7 +868,7 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
         const unsigned int* pbg = D.py_buf + (size_t)g * S.pycap + ppos0;
         for (int i = tid; i < 2 * nd_ + 2; i += blockDim.x) pb_s[i] = pbg[i];
     }
-    // ---- prologue: decision records of the entries that act without a recheck
+    // ---- prologue: decision records of the entries that act without a re-evaluation
     int na = 0;
     for (int base = 0; base < nd_; base += blockDim.x) {
         const int e = base + tid;
@@ -793,7 +876,7 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
         if (e < nd_) { t = prop[e].type; fl = (t == P_LEAF_ELONG || t == P_LEAF_DRAW || t == P_LEAF_BIF || t == P_INTER_DRAW); }
         int total;
         const int incl = block_scan_incl(fl, &total);
-        if (fl) { ActDec a; a.e = e; a.nd = dict[e]; a.type = t; a.cond = prop[e].cond; a.ratio5 = prop[e].ratio5; a.pad = 0; adec[na + incl - 1] = a; }
+        if (fl) { ActDec a; a.e = e; a.nd = dict[e]; a.type = t; a.cond = prop[e].cond; a.ratio5 = prop[e].ratio5; a.c_used = prop[e].c_used; adec[na + incl - 1] = a; }
         na += total;
     }
     __syncthreads();
@@ -804,131 +887,88 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
         const int* loff = D.list_off + (size_t)g * (S.capN + 1);
         // word stream of Python's `random`: shared-memory copy of this call's window, or the global buffer
         const unsigned int* pb = dec_smem ? pb_s - ppos0 : D.py_buf + (size_t)g * S.pycap;
-        int* rtag = D.rtag + nb;
         int ppos = ppos0;
         int n_nodes = n_before, nnew = 0, err = 0;
+        const int id_limit = SM ? (S.capN < 0xfffe ? S.capN : 0xfffe) : S.capN;
         long long draws = 0;
-        int cur_rank = -1, outstanding = 0;
-        long long dbg_scan = 0, dbg_walk = 0, dbg_recheck = 0, dbg_entries = 0, dbg_events = 0, dbg_steps = 0, dbg_tags = 0;
+        long long dbg_walk = 0, dbg_recheck = 0, dbg_events = 0, dbg_steps = 0, dbg_reevals = 0, dbg_entries = 0;
         auto next_uniform = [&]() { const double u = mt_double(pb[ppos], pb[ppos + 1]); ppos += 2; ++draws; return u; };
         auto add_node = [&](int e, int which, int parent, int parent_nch, int walk_after) -> bool {
-            if (n_nodes >= S.capN) { err = 1; return false; }
+            if (n_nodes >= id_limit) { err = 1; return false; }
             const int id = n_nodes++;
-            TreeRec r;
-            r.R = P.r; r.par = parent; r.c0 = -1; r.c1 = -1; r.slot = 0; r.slot_call = 0;
-            r.nch = 0; r.kmode = (unsigned char)P.mode_idx; r.dirty = 0; r.pad = 0;
-            rec[id] = r;
-            if (parent_nch == 0) rec[parent].c0 = id; else rec[parent].c1 = id;
-            rec[parent].nch = (unsigned char)(parent_nch + 1);
-            if (use_smem && parent_nch == 1) s_bif[parent >> 5] |= 1u << (parent & 31);
+            if (parent_nch == 0) T.set_c0(parent, id); else T.set_c1(parent, id);
             newl[nnew++] = make_int4(e, which | (walk_after << 2), parent, id);
             return true;
         };
-        const int* slot = D.slot + nb;
-        auto is_tagged = [&](int rk) -> bool { return use_smem ? ((s_tag[rk >> 5] >> (rk & 31)) & 1u) != 0 : rtag[rk] == call_id; };
-        auto set_tag = [&](int rk) { if (use_smem) s_tag[rk >> 5] |= 1u << (rk & 31); else rtag[rk] = call_id; };
-        auto clear_tag = [&](int rk) { if (use_smem) s_tag[rk >> 5] &= ~(1u << (rk & 31)); else rtag[rk] = 0; };
-        auto next_tag = [&](int from, int lim) -> int {      // first tagged rank in [from, lim), or -1
-            if (!use_smem) { for (int q = from; q < lim; ++q) if (rtag[q] == call_id) return q; return -1; }
-            int q = from;
-            while (q < lim) {
-                unsigned int wv = s_tag[q >> 5] >> (q & 31);
-                if (wv) { const int r = q + __ffs(wv) - 1; return r < lim ? r : -1; }
-                q = (q | 31) + 1;
-            }
-            return -1;
-        };
+        int cur_rank = -1, outstanding = 0;
         auto mark_walk = [&](int n) {
             ++dbg_events;
-            if (use_smem) {
-                while (true) {
-                    ++dbg_steps;
-                    const int p = s_par[n];
-                    const unsigned int bit = 1u << (n & 31);
-                    if (p < 0 || (s_dirty[n >> 5] & bit)) return;
-                    s_dirty[n >> 5] |= bit;
-                    if (s_inter[p >> 5] & (1u << (p & 31))) {
-                        const int rk = slot[p];
-                        if (rk > cur_rank && !is_tagged(rk)) { set_tag(rk); ++outstanding; ++dbg_tags; }
-                    }
-                    n = p;
-                }
-            }
-            TreeRec cur = rec[n];
-            while (cur.par >= 0 && !cur.dirty) {
-                rec[n].dirty = 1;
-                const int p = cur.par;
-                const TreeRec rp = rec[p];
-                if (rp.slot_call == call_id && rp.nch == 1 && rp.par >= 0 && rp.slot > cur_rank && !is_tagged(rp.slot)) {
-                    set_tag(rp.slot);
-                    ++outstanding;
+            while (true) {
+                ++dbg_steps;
+                const int p = T.get_par(n);
+                if (p < 0 || T.is_dirty(n)) return;          // (the root is never marked)
+                T.set_dirty(n);
+                if (T.is_inter(p)) {                         // p's distal contribution changes: re-check it when its turn comes
+                    const int rk = T.slot[p];
+                    if (rk > cur_rank && !T.is_tagged(rk)) { T.set_tag(rk); ++outstanding; }
                 }
                 n = p;
-                cur = rp;
             }
-        };
-        auto is_dirty = [&](int n) -> bool {
-            // (nodes created in this call are never dirty and lie beyond the mirrored range)
-            if (use_smem) return n < n_before && ((s_dirty[n >> 5] >> (n & 31)) & 1u);
-            return rec[n].dirty != 0;
         };
         auto refresh_subtree = [&](int top) {     // post-order over the dirty part of subtree(top); no stack needed
             int n = top;
             while (true) {
-                const TreeRec r = rec[n];
-                if (r.nch >= 1 && is_dirty(r.c0)) { n = r.c0; continue; }
-                if (r.nch >= 2 && is_dirty(r.c1)) { n = r.c1; continue; }
-                if (r.nch == 1) rec[n].R = rec[r.c0].R;
-                else if (r.nch == 2) rec[n].R = murray_parent(P, r.kmode, rec[r.c0].R, rec[r.c1].R);
-                if (use_smem) s_dirty[n >> 5] &= ~(1u << (n & 31)); else rec[n].dirty = 0;
-                D.nrad[f][nb + n] = rec[n].R;
+                const int c0 = T.get_c0(n), c1 = T.get_c1(n);
+                if (c0 >= 0 && T.is_dirty(c0)) { n = c0; continue; }
+                if (c1 >= 0 && T.is_dirty(c1)) { n = c1; continue; }
+                T.C[n] = node_contribution<SM, false>(T, P, n, c0, c1);
+                T.clr_dirty(n);
                 if (n == top) return;
-                n = r.par;
+                n = T.get_par(n);
             }
         };
         int ai = 0, scan = 0;
         while (!err) {
-            // next entry in dict order: the next decision record, unless an entry tagged for a recheck comes first.
+            // next entry in dict order: the next decision record, unless an entry tagged for a re-check comes first.
             // Tags always point past cur_rank and `scan` moves monotonically: each dict slot is inspected at most once.
             const int ea = (ai < na) ? adec[ai].e : 0x7fffffff;
             int e = -1;
             if (outstanding > 0) {
-                const long long t0 = clock64();
                 if (scan <= cur_rank) scan = cur_rank + 1;
                 const int lim = ea < nd_ ? ea : nd_;
-                e = next_tag(scan, lim);
+                e = T.next_tag(scan, lim);
                 if (e < 0) scan = lim;
-                dbg_scan += clock64() - t0;
             }
-            ++dbg_entries;
             ActDec a;
             bool tagged;
             if (e >= 0) {                       // tagged entry that is not (or not yet) a decision record
-                tagged = true; --outstanding; clear_tag(e); scan = e + 1;
-                a.e = e; a.nd = dict[e]; a.type = prop[e].type; a.cond = prop[e].cond; a.ratio5 = prop[e].ratio5;
+                tagged = true; --outstanding; T.clr_tag(e); scan = e + 1;
+                a.e = e; a.nd = dict[e]; a.type = prop[e].type; a.cond = prop[e].cond; a.ratio5 = prop[e].ratio5; a.c_used = prop[e].c_used;
             } else if (ea != 0x7fffffff) {
                 a = adec[ai++];
                 e = a.e;
-                tagged = outstanding > 0 && is_tagged(e);
-                if (tagged) { --outstanding; clear_tag(e); }
+                tagged = outstanding > 0 && T.is_tagged(e);
+                if (tagged) { --outstanding; T.clr_tag(e); }
             } else {
                 break;
             }
+            ++dbg_entries;
             cur_rank = e;
             const int nd = a.nd;
             if (a.type == P_INTER_DRAW || a.type == P_INTER_EMPTY) {
                 if (tagged) {
                     const long long t0 = clock64();
-                    // an earlier entry of this call branched below this node: its distal radius may have changed
-                    const int cd = rec[nd].c0;
-                    if (is_dirty(cd)) refresh_subtree(cd);
-                    const double r1 = rec[cd].R;
-                    if (r1 != prop[e].r1_used) {
+                    // an earlier entry of this call branched below this node: bring its distal contribution up to date
+                    const int cd = T.get_c0(nd);
+                    if (T.is_dirty(cd)) refresh_subtree(cd);
+                    const double cv = T.C[cd];
+                    if (cv != a.c_used) {
+                        ++dbg_reevals;
                         NodeCtx nc;
                         load_ctx(D, S, P, g, f, nd, &nc);
                         Proposal pr;
                         pr.cond = 0; pr.ratio5 = 0;
-                        eval_inter(D, S, P, g, f, nc, D.list + sb + loff[e], loff[e + 1] - loff[e], r1, &pr, 2);
+                        eval_inter(D, S, P, g, f, nc, D.list + sb + loff[e], loff[e + 1] - loff[e], fast_pow(cv, 1.0 / P.kap_tab[T.kmode(nd)]), cv, &pr, 2);
                         prop[e] = pr;
                         a.type = pr.type; a.cond = pr.cond; a.ratio5 = pr.ratio5;
                     }
@@ -938,7 +978,7 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
                 const double u = next_uniform();
                 if (a.ratio5 <= u && a.cond) continue;
                 if (!add_node(e, 0, nd, 1, 1)) break;
-                { const long long t0 = clock64(); mark_walk(nd); dbg_walk += clock64() - t0; }
+                { const long long t1 = clock64(); mark_walk(nd); dbg_walk += clock64() - t1; }
                 DEACT[nd] = 1;
             } else if (a.type == P_LEAF_ELONG) {
                 if (!add_node(e, 0, nd, 0, 0)) break;
@@ -948,14 +988,14 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
                 if (bif) {
                     if (!add_node(e, 1, nd, 0, 0)) break;
                     if (!add_node(e, 2, nd, 1, 1)) break;
-                    { const long long t0 = clock64(); mark_walk(nd); dbg_walk += clock64() - t0; }
+                    { const long long t1 = clock64(); mark_walk(nd); dbg_walk += clock64() - t1; }
                     DEACT[nd] = 1;
                 } else {
                     if (!add_node(e, 0, nd, 0, 0)) break;
                 }
             }
         }
-        if (D.dbg) { long long* q = D.dbg + g * 8; q[0] += dbg_scan; q[1] += dbg_walk; q[2] += dbg_recheck; q[3] += dbg_entries; q[4] += dbg_events; q[5] += dbg_steps; q[6] += dbg_tags; q[7] += na; }
+        if (D.dbg) { long long* q = D.dbg + g * 8; q[1] += dbg_walk; q[2] += dbg_recheck; q[3] += dbg_entries; q[4] += dbg_events; q[5] += dbg_steps; q[6] += dbg_reevals; q[7] += na; }
         if (err) D.err[g] = err;
         D.py_pos[g] = ppos;
         D.py_draws[g] += draws;
@@ -963,11 +1003,11 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
         D.n_nodes[f][g] = n_nodes;
         s_nnew = nnew;
         s_err = err;
+        s_marked = dbg_events > 0;
     }
     __syncthreads();
     if (s_err) return;
     const long long t_epi = clock64();
-    const int n_after = n_before + s_nnew;
 
     // ---- epilogue 1: SoA fields of the new nodes and of their parents' links
     for (int k = tid; k < s_nnew; k += blockDim.x) {
@@ -976,118 +1016,73 @@ __global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P,
         const Proposal& pr = prop[e];
         const double* p = which == 0 ? pr.p : (which == 1 ? pr.b1 : pr.b2);
         D.nx[f][nb + id] = p[0]; D.ny[f][nb + id] = p[1]; D.nz[f][nb + id] = p[2];
-        D.nrad[f][nb + id] = P.r;
+        D.ncon[f][nb + id] = P.leafc_tab[T.kmode(parent)];
         D.npar[f][nb + id] = parent; D.nch0[f][nb + id] = -1; D.nch1[f][nb + id] = -1; D.nnch[f][nb + id] = 0;
         D.deact[f][nb + id] = 0;
         D.nmeta[f][nb + id] = (unsigned char)((P.mode_idx << 1) | walk);
-        const TreeRec rp = rec[parent];
-        D.nch0[f][nb + parent] = rp.c0; D.nch1[f][nb + parent] = rp.c1; D.nnch[f][nb + parent] = rp.nch;
+        const int c0 = T.get_c0(parent), c1 = T.get_c1(parent);
+        D.nch0[f][nb + parent] = c0; D.nch1[f][nb + parent] = c1; D.nnch[f][nb + parent] = (unsigned char)((c0 >= 0) + (c1 >= 0));
     }
-    // ---- epilogue 2: bottom-up refresh of every node still dirty
-    if (use_smem) {
-        // Shared-memory driven: a chain climbs through parent pointers / dirty / bifurcation bits held in shared memory;
-        // single-child ancestors just copy the radius (no load, no atomic); at a bifurcation the first child to arrive
-        // stops and the second one (or the only dirty one) combines both radii and goes on.
-        __shared__ int s_nstart;
-        if (tid == 0) s_nstart = 0;
-        __syncthreads();
+    // ---- epilogue 2: bottom-up refresh of every contribution still dirty.  A chain starts at a dirty node without
+    // dirty children and climbs; at a bifurcation the first child to arrive stops and the second one (or the only
+    // dirty one) adds both contributions and goes on.
+    if (s_marked) {
         int* starters = D.alist + nb;
-        auto dirty_bit = [&](int n) -> bool { return n < n_before && ((s_dirty[n >> 5] >> (n & 31)) & 1u); };
         for (int w = tid; w < nwords; w += blockDim.x) {
-            unsigned int bits = s_dirty[w];
+            unsigned int bits = T.dirty[w];
             while (bits) {
                 const int n = (w << 5) + __ffs(bits) - 1;
                 bits &= bits - 1;
-                const TreeRec r = rec[n];
-                const bool d0 = r.nch >= 1 && dirty_bit(r.c0), d1 = r.nch >= 2 && dirty_bit(r.c1);
+                const int c0 = T.get_c0(n), c1 = T.get_c1(n);
+                const bool d0 = c0 >= 0 && T.is_dirty(c0), d1 = c1 >= 0 && T.is_dirty(c1);
                 if (!d0 && !d1) starters[atomicAdd(&s_nstart, 1)] = n;
-                else if (r.nch >= 2 && (d0 != d1)) atomicOr(&s_arr[n >> 5], 1u << (n & 31));
+                else if (c1 >= 0 && (d0 != d1)) atomicOr(&T.arr[n >> 5], 1u << (n & 31));
             }
         }
         __syncthreads();
         const int nstart = s_nstart;
-        volatile double* vR = D.nrad[f] + nb;
+        volatile double* vC = T.C;
         for (int k = tid; k < nstart; k += blockDim.x) {
             int n = starters[k];
-            const TreeRec r = rec[n];
-            double val = r.R;
-            if (r.nch == 1) val = vR[r.c0];
-            else if (r.nch >= 2) val = murray_parent(P, r.kmode, vR[r.c0], vR[r.c1]);
-            rec[n].R = val;
-            vR[n] = val;
+            double val = node_contribution<SM, true>(T, P, n, T.get_c0(n), T.get_c1(n));
+            vC[n] = val;
             while (true) {
-                const int p = s_par[n];
-                if (p < 0 || !dirty_bit(p)) break;                  // (the root is never marked)
+                const int p = T.get_par(n);
+                if (p < 0 || !T.is_dirty(p)) break;                  // (the root is never marked)
                 const unsigned int pbit = 1u << (p & 31);
-                if (s_bif[p >> 5] & pbit) {
+                if (T.get_c1(p) >= 0) {
                     __threadfence_block();
-                    if (!(atomicOr(&s_arr[p >> 5], pbit) & pbit)) break;   // first arrival: the sibling's chain continues
+                    if (!(atomicOr(&T.arr[p >> 5], pbit) & pbit)) break;   // first arrival: the sibling's chain continues
                     __threadfence_block();
-                    const TreeRec rp = rec[p];
-                    const double ra = (rp.c0 == n) ? val : vR[rp.c0];
-                    const double rb = (rp.c1 == n) ? val : vR[rp.c1];
-                    val = murray_parent(P, rp.kmode, ra, rb);
                 }
-                rec[p].R = val;
-                vR[p] = val;
+                val = node_contribution<SM, true>(T, P, p, T.get_c0(p), T.get_c1(p));
+                vC[p] = val;
                 n = p;
             }
         }
         __syncthreads();
-    } else {
-        int* pend = D.cnt + nb;                      // all zero outside k_group
-        for (int n = tid; n < n_after; n += blockDim.x) {
-            const TreeRec r = rec[n];
-            if (r.dirty) {
-                const int c = ((r.nch >= 1 && rec[r.c0].dirty) ? 1 : 0) + ((r.nch >= 2 && rec[r.c1].dirty) ? 1 : 0);
-                pend[n] = c ? c : -1;                // -1: ready now
-            }
+        if (SM) {
+            double* gC = D.ncon[f] + nb;
+            for (int i = tid; i < n_before; i += blockDim.x) gC[i] = T.C[i];
         }
-        __syncthreads();
-        volatile TreeRec* vrec = rec;
-        for (int n0 = tid; n0 < n_after; n0 += blockDim.x) {
-            if (!rec[n0].dirty || pend[n0] != -1) continue;
-            int n = n0;
-            TreeRec r = rec[n];
-            double rn = 0;
-            bool have_child_r = false;               // rn holds the radius of the child we just came from
-            int from = -1;
-            while (true) {
-                double val = r.R;
-                if (r.nch == 1) val = have_child_r ? rn : vrec[r.c0].R;
-                else if (r.nch == 2) {
-                    const double ra = (have_child_r && from == r.c0) ? rn : vrec[r.c0].R;
-                    const double rb = (have_child_r && from == r.c1) ? rn : vrec[r.c1].R;
-                    val = murray_parent(P, r.kmode, ra, rb);
-                }
-                vrec[n].R = val;
-                D.nrad[f][nb + n] = val;
-                rec[n].dirty = 0;
-                pend[n] = 0;
-                const int p = r.par;
-                if (p < 0) break;
-                const TreeRec rp = rec[p];
-                if (!rp.dirty) break;                // (the root is never marked)
-                if (rp.nch >= 2) {
-                    __threadfence_block();
-                    if (atomicSub(&pend[p], 1) != 1) break;
-                    __threadfence_block();
-                } else {
-                    pend[p] = 0;
-                }
-                from = n; rn = val; have_child_r = true;
-                n = p; r = rp;
-            }
-        }
-        __syncthreads();
     }
     const long long t_act = clock64();
-    // (no active list to maintain: the active set is the node array minus the DEACT marks, see k_grid_build)
     if (tid == 0) {
         const long long t_end = clock64();          // per-phase cycle counters (reported through OctaGrowStats)
         D.counters[g * 8 + 4] += t_replay - t_start; D.counters[g * 8 + 5] += t_epi - t_replay;
         D.counters[g * 8 + 6] += t_act - t_epi; D.counters[g * 8 + 7] += t_end - t_act;
     }
+}
+
+__global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P, int f) {
+    extern __shared__ __align__(16) int s_dyn[];
+    const int g = blockIdx.x;
+    if (D.err[g]) return;
+    const int n_before = D.n_nodes[f][g];
+    const size_t need = (((size_t)n_before * 17 + 3) & ~(size_t)3) + 16 * (size_t)((n_before + 31) >> 5) + 64;
+    // room for every node this call can add must remain within 16-bit ids
+    if (need <= (size_t)S.commit_smem && n_before + 2 * D.n_dict[g] < 0xfffe) commit_body<true>(D, S, P, f, s_dyn);
+    else commit_body<false>(D, S, P, f, s_dyn);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1323,11 +1318,54 @@ int prepare_kernels(const GrowShape& S) {
     return (int)cudaFuncSetAttribute(k_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)commit_smem_bytes(S));
 }
 
+// Optional per-kernel timing (OCTA_GROW_TIMING=1): an event after every launch; grow_timing_report() sums the
+// intervals per kernel kind once the stream is idle.  Diagnostics only (tools/grow_probe.py).
+namespace {
+struct Timing {
+    bool on = false, init = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> kind;
+    size_t used = 0;
+    cudaEvent_t next(int k) {
+        if (used == ev.size()) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); kind.push_back(0); }
+        kind[used] = k;
+        return ev[used++];
+    }
+} g_timing;
+const char* const kTimingNames[] = {"start", "k_prepare", "k_sink_tests", "k_sink_greedy", "k_assign[a]", "k_group[a]", "k_eval[a]",
+                                    "k_commit[a]", "k_kill[a]", "k_assign[v]", "k_group[v]", "k_eval[v]", "k_commit[v]", "k_kill[v]"};
+inline void tick(cudaStream_t st, int k) { if (g_timing.on) cudaEventRecord(g_timing.next(k), st); }
+}  // namespace
+
+void grow_timing_begin(cudaStream_t st) {
+    if (!g_timing.init) { g_timing.init = true; const char* e = getenv("OCTA_GROW_TIMING"); g_timing.on = e && e[0] == '1'; }
+    g_timing.used = 0;
+    tick(st, 0);
+}
+
+void grow_timing_report() {       // call after the stream has been synchronised
+    if (!g_timing.on || g_timing.used < 2) return;
+    double sum[14] = {0};
+    for (size_t i = 1; i < g_timing.used; ++i) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, g_timing.ev[i - 1], g_timing.ev[i]);
+        sum[g_timing.kind[i]] += ms;
+    }
+    double tot = 0;
+    for (int k = 1; k < 14; ++k) tot += sum[k];
+    fprintf(stderr, "[octa grow timing] total %.1f ms:", tot);
+    for (int k = 1; k < 14; ++k) fprintf(stderr, " %s %.1f", kTimingNames[k], sum[k]);
+    fprintf(stderr, "\n");
+}
+
 void launch_iteration(const GrowDev& D, const GrowShape& S, const IterP& P, int n_sm, cudaStream_t st, cudaStream_t side,
                       cudaEvent_t ev_sinks, cudaEvent_t ev_kd) {
     k_prepare<<<dim3(S.G, 5), 1024, 0, st>>>(D, S, P);
+    tick(st, 1);
     k_sink_tests<<<n_sm * 8, TILE, 0, st>>>(D, S, P);
+    tick(st, 2);
     k_sink_greedy<<<S.G, 1024, 0, st>>>(D, S, P);
+    tick(st, 3);
     count_launch(3);
     if (S.exact_ball_order) {
         cudaEventRecord(ev_sinks, st);
@@ -1338,11 +1376,16 @@ void launch_iteration(const GrowDev& D, const GrowShape& S, const IterP& P, int 
     }
     for (int f = 0; f < 2; ++f) {
         k_assign<<<n_sm * 8, TILE, 0, st>>>(D, S, P, f);
+        tick(st, 4 + 5 * f);
         k_group<<<S.G, 1024, 0, st>>>(D, S, P, f);
+        tick(st, 5 + 5 * f);
         k_eval<<<dim3(16, S.G), 128, 0, st>>>(D, S, P, f);
+        tick(st, 6 + 5 * f);
         k_commit<<<S.G, 256, commit_smem_bytes(S), st>>>(D, S, P, f);
+        tick(st, 7 + 5 * f);
         if (f == 0 && S.exact_ball_order) cudaStreamWaitEvent(st, ev_kd, 0);
         k_kill<<<S.G, 1024, 0, st>>>(D, S, P, f);
+        tick(st, 8 + 5 * f);
         count_launch(5);
     }
 }

@@ -34,8 +34,8 @@ for rep in range(a.reps):
     print("   k_commit cycles per graph (mean | max over graphs) prologue/replay/refresh/active: %s | %s  [ms at 1.9 GHz: %s]" %
           (np.round(cyc.mean(0) / 1e6, 1), np.round(cyc.max(0) / 1e6, 1), np.round(cyc.max(0) / 1.9e6, 1)), flush=True)
     det = np.array([s["replay_detail"] for s in stats], dtype=np.float64).mean(0)
-    print("   replay detail (mean/graph): Mcycles scan %.1f walk %.1f recheck %.1f | entries %d events %d walk steps %d tags %d records %d" %
-          (det[0] / 1e6, det[1] / 1e6, det[2] / 1e6, det[3], det[4], det[5], det[6], det[7]), flush=True)
+    print("   replay detail (mean/graph): Mcycles walk %.1f recheck %.1f | entries %d events %d walk steps %d re-evaluations %d records %d" %
+          (det[1] / 1e6, det[2] / 1e6, det[3], det[4], det[5], det[6], det[7]), flush=True)
 if a.check:
     from oracle import growth_oracle as go
     exact = idx = 0
