@@ -20,8 +20,10 @@ namespace octa {
 
 void grow_timing_begin(cudaStream_t st);
 void grow_timing_report();
-void launch_iteration(const GrowDev& D, const GrowShape& S, const IterP& P, int n_sm, cudaStream_t st, cudaStream_t side,
-                      cudaEvent_t ev_sinks, cudaEvent_t ev_kd);
+struct GrowEvents { cudaEvent_t start, sinks, kd, killa; };
+void launch_begin(const GrowDev& D, const GrowShape& S, const IterP& P0, int n_sm, cudaStream_t st, cudaStream_t side, const GrowEvents& ev);
+void launch_iteration(const GrowDev& D, const GrowShape& S, const IterP& P, const IterP* Pnext, int n_sm, cudaStream_t st,
+                      cudaStream_t side, const GrowEvents& ev);
 int prepare_kernels(const GrowShape& S);
 
 namespace {
@@ -305,12 +307,12 @@ struct GrowCtx {
     int n_sm = 148;
     char* stage = nullptr;      // pinned host staging
     size_t stage_bytes = 0;
-    cudaEvent_t e0 = nullptr, e1 = nullptr, ev_sinks = nullptr, ev_kd = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    GrowEvents ev = {nullptr, nullptr, nullptr, nullptr};
     cudaStream_t side = nullptr;
     ~GrowCtx() {
         if (side) cudaStreamDestroy(side);
-        if (ev_sinks) cudaEventDestroy(ev_sinks);
-        if (ev_kd) cudaEventDestroy(ev_kd);
+        for (cudaEvent_t e : {ev.start, ev.sinks, ev.kd, ev.killa}) if (e) cudaEventDestroy(e);
         if (dbase) cudaFree(dbase);
         if (stage) cudaFreeHost(stage);
         if (e0) cudaEventDestroy(e0);
@@ -379,8 +381,7 @@ extern "C" int octa_grow_create(const OctaGrowConfig* cfg, int max_graphs, void*
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, dev);
     if (prepare_kernels(S) != 0) { cudaGetLastError(); set_error("cudaFuncSetAttribute(k_commit) failed"); delete ctx; return OCTA_E_CUDA; }
     cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking);
-    cudaEventCreateWithFlags(&ctx->ev_sinks, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ctx->ev_kd, cudaEventDisableTiming);
+    for (cudaEvent_t* e : {&ctx->ev.start, &ctx->ev.sinks, &ctx->ev.kd, &ctx->ev.killa}) cudaEventCreateWithFlags(e, cudaEventDisableTiming);
     cudaEventCreate(&ctx->e0);
     cudaEventCreate(&ctx->e1);
     *handle = ctx;
@@ -485,7 +486,9 @@ static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, doub
     if (!trace) D.trace = nullptr;
     OCTA_CUDA_CHECK(cudaEventRecord(ctx->e0, st));
     grow_timing_begin(st);
-    for (const IterP& P : ctx->sched) launch_iteration(D, S, P, ctx->n_sm, st, ctx->side, ctx->ev_sinks, ctx->ev_kd);
+    if (!ctx->sched.empty()) launch_begin(D, S, ctx->sched[0], ctx->n_sm, st, ctx->side, ctx->ev);
+    for (size_t i = 0; i < ctx->sched.size(); ++i)
+        launch_iteration(D, S, ctx->sched[i], i + 1 < ctx->sched.size() ? &ctx->sched[i + 1] : nullptr, ctx->n_sm, st, ctx->side, ctx->ev);
     OCTA_CUDA_CHECK(cudaEventRecord(ctx->e1, st));
     // ---- read back: counts first, then strided copies of the live prefix of every node array
     std::vector<int> err(n_graphs), nn[2], ns[2];

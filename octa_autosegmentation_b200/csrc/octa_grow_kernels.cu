@@ -266,12 +266,12 @@ __device__ __forceinline__ void grid_build_body(const GrowDev& D, const GrowShap
 
 __global__ void __launch_bounds__(1024) k_grid_build(GrowDev D, GrowShape S, IterP P, int which) { grid_build_body(D, S, P, which, blockIdx.x); }
 
-// k_prepare: everything an iteration needs that depends only on the state left by the previous iteration, in ONE
-// launch: blockIdx.y = 0..3 -> the four bucket grids (arterial nodes, O2 sinks, active arterial / venous nodes; the
-// venous set does not change before the venous commit), blockIdx.y = 4 -> the candidate sampler.  5*G CTAs run
-// side by side instead of five dependent single-wave launches.
+// k_prepare: everything the sampling of an iteration needs, in ONE launch: blockIdx.y = 0..2 -> the bucket grids of
+// the arterial nodes (+radius), the O2 sinks and the active arterial nodes, blockIdx.y = 3 -> the candidate sampler.
+// 4*G CTAs run side by side instead of four dependent single-wave launches.  (The grid of the active venous nodes is
+// rebuilt by k_grid_build right after the venous commit.)
 __global__ void __launch_bounds__(1024) k_prepare(GrowDev D, GrowShape S, IterP P) {
-    if (blockIdx.y < 4) grid_build_body(D, S, P, (int)blockIdx.y, blockIdx.x);
+    if (blockIdx.y < 3) grid_build_body(D, S, P, (int)blockIdx.y, blockIdx.x);
     else sample_body(D, S, P, blockIdx.x);
 }
 
@@ -1285,9 +1285,10 @@ __global__ void __launch_bounds__(1024) k_kill(GrowDev D, GrowShape S, IterP P, 
         if (tid == 0) D.n_s[f][g] = w;
     }
     __syncthreads();
-    if (f == 1 && tid == 0 && D.trace) {
+    if (tid == 0 && D.trace && P.iter < 4096) {       // (the sampler of the next iteration may already run beside the venous phase)
         int* tr = D.trace + ((size_t)g * 4096 + P.iter) * 4;
-        if (P.iter < 4096) { tr[0] = D.n_nodes[0][g]; tr[1] = D.n_s[0][g]; tr[2] = D.n_nodes[1][g]; tr[3] = D.n_s[1][g]; }
+        if (f == 0) { tr[0] = D.n_nodes[0][g]; tr[1] = D.n_s[0][g]; }
+        else { tr[2] = D.n_nodes[1][g]; tr[3] = D.n_s[1][g]; }
     }
 }
 
@@ -1358,22 +1359,39 @@ void grow_timing_report() {       // call after the stream has been synchronised
     fprintf(stderr, "\n");
 }
 
-void launch_iteration(const GrowDev& D, const GrowShape& S, const IterP& P, int n_sm, cudaStream_t st, cudaStream_t side,
-                      cudaEvent_t ev_sinks, cudaEvent_t ev_kd) {
-    k_prepare<<<dim3(S.G, 5), 1024, 0, st>>>(D, S, P);
-    tick(st, 1);
-    k_sink_tests<<<n_sm * 8, TILE, 0, st>>>(D, S, P);
-    tick(st, 2);
-    k_sink_greedy<<<S.G, 1024, 0, st>>>(D, S, P);
-    tick(st, 3);
+// Two pipelines per batch.  The sampling of iteration i+1 (bucket grids, candidate sampler, sink tests, greedy
+// acceptance, cKDTree permutation) reads the arterial forest and the O2 sink list only, both final once the arterial
+// kill of iteration i is done -- so it runs on the side stream BESIDE the venous phase of iteration i and the
+// arterial growth of iteration i+1:
+//   main: [wait sinks] assign/group/eval/commit [a]  [wait kd] kill[a]  assign/group/eval/commit [v] grid(ven) kill[v]
+//   side:                                     [wait kill[a]] prepare tests greedy (sinks) kdbuild (kd)   -> iteration i+1
+struct GrowEvents { cudaEvent_t start, sinks, kd, killa; };
+
+void launch_sampling(const GrowDev& D, const GrowShape& S, const IterP& P, int n_sm, cudaStream_t side, const GrowEvents& ev) {
+    k_prepare<<<dim3(S.G, 4), 1024, 0, side>>>(D, S, P);
+    k_sink_tests<<<n_sm * 8, TILE, 0, side>>>(D, S, P);
+    k_sink_greedy<<<S.G, 1024, 0, side>>>(D, S, P);
+    cudaEventRecord(ev.sinks, side);
     count_launch(3);
     if (S.exact_ball_order) {
-        cudaEventRecord(ev_sinks, st);
-        cudaStreamWaitEvent(side, ev_sinks, 0);
         k_kdbuild<<<S.G, 1024, 0, side>>>(D, S);
-        cudaEventRecord(ev_kd, side);
         count_launch(1);
     }
+    cudaEventRecord(ev.kd, side);
+}
+
+void launch_begin(const GrowDev& D, const GrowShape& S, const IterP& P0, int n_sm, cudaStream_t st, cudaStream_t side, const GrowEvents& ev) {
+    // uploads of the initial state were issued on `st`
+    k_grid_build<<<S.G, 1024, 0, st>>>(D, S, P0, 3);
+    count_launch(1);
+    cudaEventRecord(ev.start, st);
+    cudaStreamWaitEvent(side, ev.start, 0);
+    launch_sampling(D, S, P0, n_sm, side, ev);
+}
+
+void launch_iteration(const GrowDev& D, const GrowShape& S, const IterP& P, const IterP* Pnext, int n_sm, cudaStream_t st,
+                      cudaStream_t side, const GrowEvents& ev) {
+    cudaStreamWaitEvent(st, ev.sinks, 0);
     for (int f = 0; f < 2; ++f) {
         k_assign<<<n_sm * 8, TILE, 0, st>>>(D, S, P, f);
         tick(st, 4 + 5 * f);
@@ -1383,10 +1401,18 @@ void launch_iteration(const GrowDev& D, const GrowShape& S, const IterP& P, int 
         tick(st, 6 + 5 * f);
         k_commit<<<S.G, 256, commit_smem_bytes(S), st>>>(D, S, P, f);
         tick(st, 7 + 5 * f);
-        if (f == 0 && S.exact_ball_order) cudaStreamWaitEvent(st, ev_kd, 0);
+        if (f == 0) cudaStreamWaitEvent(st, ev.kd, 0);
+        else { k_grid_build<<<S.G, 1024, 0, st>>>(D, S, P, 3); count_launch(1); }
         k_kill<<<S.G, 1024, 0, st>>>(D, S, P, f);
         tick(st, 8 + 5 * f);
         count_launch(5);
+        if (f == 0) {
+            cudaEventRecord(ev.killa, st);
+            if (Pnext) {
+                cudaStreamWaitEvent(side, ev.killa, 0);
+                launch_sampling(D, S, *Pnext, n_sm, side, ev);
+            }
+        }
     }
 }
 
