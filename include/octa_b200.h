@@ -174,6 +174,8 @@ int octa_test_principal_axis(const double* cov9, double* dl3);
 void octa_test_kd_indices(const double* x, const double* y, const double* z, int n, int* idx_out);
 /* the same permutation built by one CTA on the GPU (the block-parallel code path of the growth kernels) */
 int octa_test_kd_indices_gpu(const double* x, const double* y, const double* z, int n, int* idx_out);
+/* the shared-memory resident build k_kdbuild prefers (n <= ~17 k): rank_out[idx_out[i]] = i; -1 everywhere if it bailed out */
+int octa_test_kd_ranks_gpu_smem(const double* x, const double* y, const double* z, int n, int* rank_out);
 /* CPython hash((np.float64 x, y, z)) (greenhouse.py:100-111 set ordering) */
 int64_t octa_test_hash_tuple3(const double* xyz);
 

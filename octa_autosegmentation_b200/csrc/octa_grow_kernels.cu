@@ -1297,16 +1297,24 @@ __global__ void __launch_bounds__(1024) k_kill(GrowDev D, GrowShape S, IterP P, 
 // (= the tree the reference queries in step 3, greenhouse.py:101-102).  Runs on a side stream, concurrently with
 // the arterial growth kernels, which do not modify the sink list.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_kdbuild(GrowDev D, GrowShape S) {
+__global__ void __launch_bounds__(1024) k_kdbuild(GrowDev D, GrowShape S, int smem_bytes) {
+    extern __shared__ __align__(16) char s_kd[];
+    __shared__ int s_ws[kdpar::WS_INTS];
+    __shared__ double s_wd[kdpar::WD_DOUBLES];
     const int g = blockIdx.x, tid = threadIdx.x;
     if (D.err[g]) return;
     const size_t sb = (size_t)g * S.capS;
     const int Sn = D.n_s[0][g];
+    int* rk = D.kd_rank + sb;
+    // shared-memory resident build (12 bytes per sink) when the list fits, else / on bail-out the global-memory one
+    if ((size_t)Sn * 12 + 64 <= (size_t)smem_bytes && Sn < 65536 &&
+        kdsm::build_ranks_block(D.sx[0] + sb, D.sy[0] + sb, D.sz[0] + sb, Sn, rk, s_kd, D.kd_nodes + sb, D.kd_nodes + sb + S.capS / 2, s_ws, s_wd))
+        return;
+    __syncthreads();
     int* kidx = D.kd_idx + sb;
     kdpar::build_indices_block(D.sx[0] + sb, D.sy[0] + sb, D.sz[0] + sb, Sn, kidx, D.kd_posL + sb, D.kd_posR + sb,
-                               D.kd_nodes + sb, D.kd_nodes + sb + S.capS / 2);
+                               D.kd_nodes + sb, D.kd_nodes + sb + S.capS / 2, s_ws, s_wd);
     __syncthreads();
-    int* rk = D.kd_rank + sb;
     for (int i = tid; i < Sn; i += blockDim.x) rk[kidx[i]] = i;
 }
 
@@ -1315,15 +1323,18 @@ __global__ void __launch_bounds__(1024) k_kdbuild(GrowDev D, GrowShape S) {
 // ------------------------------------------------------------------------------------------
 size_t commit_smem_bytes(const GrowShape& S) { return (size_t)S.commit_smem; }
 
+constexpr int KD_SMEM_BYTES = 208 * 1024;        // + ~17 KB static: scan / reduction scratch
+
 int prepare_kernels(const GrowShape& S) {
-    return (int)cudaFuncSetAttribute(k_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)commit_smem_bytes(S));
+    cudaError_t e = cudaFuncSetAttribute(k_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)commit_smem_bytes(S));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_kdbuild, cudaFuncAttributeMaxDynamicSharedMemorySize, KD_SMEM_BYTES);
+    return (int)e;
 }
 
 // Optional per-kernel timing (OCTA_GROW_TIMING=1): an event after every launch; grow_timing_report() sums the
 // intervals per kernel kind once the stream is idle.  Diagnostics only (tools/grow_probe.py).
 namespace {
 struct Timing {
-    bool on = false, init = false;
     std::vector<cudaEvent_t> ev;
     std::vector<int> kind;
     size_t used = 0;
@@ -1332,31 +1343,39 @@ struct Timing {
         kind[used] = k;
         return ev[used++];
     }
-} g_timing;
+};
+Timing g_timing[2];        // [0] main stream, [1] side stream
+bool g_timing_on = false, g_timing_init = false;
 const char* const kTimingNames[] = {"start", "k_prepare", "k_sink_tests", "k_sink_greedy", "k_assign[a]", "k_group[a]", "k_eval[a]",
-                                    "k_commit[a]", "k_kill[a]", "k_assign[v]", "k_group[v]", "k_eval[v]", "k_commit[v]", "k_kill[v]"};
-inline void tick(cudaStream_t st, int k) { if (g_timing.on) cudaEventRecord(g_timing.next(k), st); }
+                                    "k_commit[a]", "k_kill[a]", "k_assign[v]", "k_group[v]", "k_eval[v]", "k_commit[v]", "k_kill[v]",
+                                    "k_kdbuild", "(side waits)"};
+constexpr int N_KINDS = 16;
+inline void tick(cudaStream_t st, int k, int which = 0) { if (g_timing_on) cudaEventRecord(g_timing[which].next(k), st); }
 }  // namespace
 
 void grow_timing_begin(cudaStream_t st) {
-    if (!g_timing.init) { g_timing.init = true; const char* e = getenv("OCTA_GROW_TIMING"); g_timing.on = e && e[0] == '1'; }
-    g_timing.used = 0;
+    if (!g_timing_init) { g_timing_init = true; const char* e = getenv("OCTA_GROW_TIMING"); g_timing_on = e && e[0] == '1'; }
+    g_timing[0].used = g_timing[1].used = 0;
     tick(st, 0);
 }
 
-void grow_timing_report() {       // call after the stream has been synchronised
-    if (!g_timing.on || g_timing.used < 2) return;
-    double sum[14] = {0};
-    for (size_t i = 1; i < g_timing.used; ++i) {
-        float ms = 0;
-        cudaEventElapsedTime(&ms, g_timing.ev[i - 1], g_timing.ev[i]);
-        sum[g_timing.kind[i]] += ms;
+void grow_timing_report() {       // call after the streams have been synchronised
+    if (!g_timing_on) return;
+    for (int w = 0; w < 2; ++w) {
+        const Timing& T = g_timing[w];
+        if (T.used < 2) continue;
+        double sum[N_KINDS] = {0};
+        for (size_t i = 1; i < T.used; ++i) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, T.ev[i - 1], T.ev[i]);
+            sum[T.kind[i]] += ms;
+        }
+        double tot = 0;
+        for (int k = 1; k < N_KINDS; ++k) tot += sum[k];
+        fprintf(stderr, "[octa grow timing] %s stream, total %.1f ms:", w ? "side" : "main", tot);
+        for (int k = 1; k < N_KINDS; ++k) if (sum[k] > 0) fprintf(stderr, " %s %.1f", kTimingNames[k], sum[k]);
+        fprintf(stderr, "\n");
     }
-    double tot = 0;
-    for (int k = 1; k < 14; ++k) tot += sum[k];
-    fprintf(stderr, "[octa grow timing] total %.1f ms:", tot);
-    for (int k = 1; k < 14; ++k) fprintf(stderr, " %s %.1f", kTimingNames[k], sum[k]);
-    fprintf(stderr, "\n");
 }
 
 // Two pipelines per batch.  The sampling of iteration i+1 (bucket grids, candidate sampler, sink tests, greedy
@@ -1368,13 +1387,18 @@ void grow_timing_report() {       // call after the stream has been synchronised
 struct GrowEvents { cudaEvent_t start, sinks, kd, killa; };
 
 void launch_sampling(const GrowDev& D, const GrowShape& S, const IterP& P, int n_sm, cudaStream_t side, const GrowEvents& ev) {
+    tick(side, 15, 1);            // (the time since the previous side-stream event was spent waiting for the main stream)
     k_prepare<<<dim3(S.G, 4), 1024, 0, side>>>(D, S, P);
+    tick(side, 1, 1);
     k_sink_tests<<<n_sm * 8, TILE, 0, side>>>(D, S, P);
+    tick(side, 2, 1);
     k_sink_greedy<<<S.G, 1024, 0, side>>>(D, S, P);
+    tick(side, 3, 1);
     cudaEventRecord(ev.sinks, side);
     count_launch(3);
     if (S.exact_ball_order) {
-        k_kdbuild<<<S.G, 1024, 0, side>>>(D, S);
+        k_kdbuild<<<S.G, 1024, KD_SMEM_BYTES, side>>>(D, S, KD_SMEM_BYTES);
+        tick(side, 14, 1);
         count_launch(1);
     }
     cudaEventRecord(ev.kd, side);

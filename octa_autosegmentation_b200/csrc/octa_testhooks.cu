@@ -24,16 +24,31 @@ extern "C" void octa_test_kd_indices(const double* x, const double* y, const dou
 #include "octa_kdorder_par.cuh"
 namespace {
 __global__ void __launch_bounds__(1024) kd_test_kernel(const double* x, const double* y, const double* z, int n, int* idx,
-                                                       int* posL, int* posR, int* nodes) {
-    octa::kdpar::build_indices_block(x, y, z, n, idx, posL, posR, nodes, nodes + n / 2 + 8);
+                                                       int* posL, int* posR, int* nodes, int mode) {
+    __shared__ int s_ws[octa::kdpar::WS_INTS];
+    __shared__ double s_wd[octa::kdpar::WD_DOUBLES];
+    extern __shared__ __align__(16) char s_dyn[];
+    if (mode == 1) {   // shared-memory resident build; idx receives the RANK of every point (-1 everywhere on bail-out)
+        if (!octa::kdsm::build_ranks_block(x, y, z, n, idx, s_dyn, nodes, nodes + 3 * (n / 8 + 4), s_ws, s_wd))
+            for (int i = threadIdx.x; i < n; i += blockDim.x) idx[i] = -1;
+        return;
+    }
+    octa::kdpar::build_indices_block(x, y, z, n, idx, posL, posR, nodes, nodes + n / 2 + 8, s_ws, s_wd);
 }
 }  // namespace
 
-// GPU build of the same permutation by one CTA (the code path k_kill uses); host buffers in/out.
-extern "C" int octa_test_kd_indices_gpu(const double* x, const double* y, const double* z, int n, int* idx_out) {
-    OCTA_ARG_CHECK(n >= 0 && idx_out, "bad arguments");
+// GPU build of the same permutation by one CTA (the code paths k_kdbuild uses); host buffers in/out.
+// mode 0: global-memory build -> indices; mode 1: shared-memory resident build -> RANKS (rank[indices[i]] = i).
+static int kd_indices_gpu(const double* x, const double* y, const double* z, int n, int* out, int mode) {
+    OCTA_ARG_CHECK(n >= 0 && out, "bad arguments");
     if (octa_device_count() <= 0) { octa::set_error("no CUDA device"); return OCTA_E_CUDA; }
     if (n == 0) return OCTA_OK;
+    size_t smem = 0;
+    if (mode == 1) {
+        smem = (size_t)n * 12 + 64;
+        OCTA_ARG_CHECK(smem <= 208 * 1024 && n < 65536, "too many points for the shared-memory build");
+        OCTA_CUDA_CHECK(cudaFuncSetAttribute(kd_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+    }
     double* d = nullptr;
     int* w = nullptr;
     OCTA_CUDA_CHECK(cudaMalloc(&d, sizeof(double) * 3 * (size_t)n));
@@ -41,12 +56,20 @@ extern "C" int octa_test_kd_indices_gpu(const double* x, const double* y, const 
     cudaMemcpy(d, x, 8 * (size_t)n, cudaMemcpyHostToDevice);
     cudaMemcpy(d + n, y, 8 * (size_t)n, cudaMemcpyHostToDevice);
     cudaMemcpy(d + 2 * (size_t)n, z, 8 * (size_t)n, cudaMemcpyHostToDevice);
-    kd_test_kernel<<<1, 1024>>>(d, d + n, d + 2 * (size_t)n, n, w, w + n, w + 2 * (size_t)n, w + 3 * (size_t)n);
+    kd_test_kernel<<<1, 1024, smem>>>(d, d + n, d + 2 * (size_t)n, n, w, w + n, w + 2 * (size_t)n, w + 3 * (size_t)n, mode);
     octa::count_launch();
     cudaError_t ce = cudaDeviceSynchronize();
-    if (ce == cudaSuccess) ce = cudaMemcpy(idx_out, w, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost);
+    if (ce == cudaSuccess) ce = cudaMemcpy(out, w, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost);
     cudaFree(d);
     cudaFree(w);
     if (ce != cudaSuccess) { octa::set_error("kd_test_kernel: %s", cudaGetErrorString(ce)); return OCTA_E_CUDA; }
     return OCTA_OK;
+}
+
+extern "C" int octa_test_kd_indices_gpu(const double* x, const double* y, const double* z, int n, int* idx_out) {
+    return kd_indices_gpu(x, y, z, n, idx_out, 0);
+}
+
+extern "C" int octa_test_kd_ranks_gpu_smem(const double* x, const double* y, const double* z, int n, int* rank_out) {
+    return kd_indices_gpu(x, y, z, n, rank_out, 1);
 }
