@@ -845,6 +845,7 @@ __device__ void commit_body(const GrowDev& D, const GrowShape& S, const IterP& P
     if (SM) {
         const int* gpar = D.npar[f] + nb; const int* gc0 = D.nch0[f] + nb; const int* gc1 = D.nch1[f] + nb;
         const double* gC = D.ncon[f] + nb; const unsigned char* gm = D.nmeta[f] + nb;
+#pragma unroll 4
         for (int i = tid; i < n_before; i += blockDim.x) {
             T.C[i] = gC[i];
             T.par[i] = (unsigned short)gpar[i]; T.c0[i] = (unsigned short)gc0[i]; T.c1[i] = (unsigned short)gc1[i];   // -1 -> 0xffff
@@ -903,6 +904,25 @@ __device__ void commit_body(const GrowDev& D, const GrowShape& S, const IterP& P
         int cur_rank = -1, outstanding = 0;
         auto mark_walk = [&](int n) {
             ++dbg_events;
+            if (SM) {
+                // software-pipelined: the parent link and the dirty word of the node under the cursor were loaded one
+                // step ahead, so a step costs one shared-memory round trip instead of four dependent ones
+                int p = T.par[n];
+                unsigned int dw = T.dirty[n >> 5];
+                while (p != 0xffff && !((dw >> (n & 31)) & 1u)) {          // (the root is never marked)
+                    ++dbg_steps;
+                    const int pp = T.par[p];
+                    const unsigned int iw = T.inter[p >> 5];
+                    T.dirty[n >> 5] = dw | (1u << (n & 31));
+                    const unsigned int dwp = T.dirty[p >> 5];
+                    if ((iw >> (p & 31)) & 1u) {                             // p's distal contribution changes: re-check it when its turn comes
+                        const int rk = T.slot[p];
+                        if (rk > cur_rank && !T.is_tagged(rk)) { T.set_tag(rk); ++outstanding; }
+                    }
+                    n = p; p = pp; dw = dwp;
+                }
+                return;
+            }
             while (true) {
                 ++dbg_steps;
                 const int p = T.get_par(n);
@@ -1074,7 +1094,7 @@ __device__ void commit_body(const GrowDev& D, const GrowShape& S, const IterP& P
     }
 }
 
-__global__ void __launch_bounds__(256) k_commit(GrowDev D, GrowShape S, IterP P, int f) {
+__global__ void __launch_bounds__(512) k_commit(GrowDev D, GrowShape S, IterP P, int f) {
     extern __shared__ __align__(16) int s_dyn[];
     const int g = blockIdx.x;
     if (D.err[g]) return;
@@ -1423,7 +1443,7 @@ void launch_iteration(const GrowDev& D, const GrowShape& S, const IterP& P, cons
         tick(st, 5 + 5 * f);
         k_eval<<<dim3(16, S.G), 128, 0, st>>>(D, S, P, f);
         tick(st, 6 + 5 * f);
-        k_commit<<<S.G, 256, commit_smem_bytes(S), st>>>(D, S, P, f);
+        k_commit<<<S.G, 512, commit_smem_bytes(S), st>>>(D, S, P, f);
         tick(st, 7 + 5 * f);
         if (f == 0) cudaStreamWaitEvent(st, ev.kd, 0);
         else { k_grid_build<<<S.G, 1024, 0, st>>>(D, S, P, 3); count_launch(1); }
