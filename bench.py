@@ -290,7 +290,7 @@ def main():
                          "algorithmic_bytes_per_launch": vox_alg, "ms_per_launch": vox_ms,
                          "note": "the HBM-bound kernel of the path; see roofline_growth for the phase that dominates step time"},
             "roofline_growth": {"bound": "hbm", "achieved": grow_ach, "peak": peak, "unit": "GB/s", "frac": grow_ach / peak,
-                                "traffic": None, "kernel": "growth loop, 13 kernels x 250 iterations (latency / pair-scan bound; "
+                                "traffic": None, "kernel": "growth loop, 15 launches x 250 iterations on two streams (latency / pair-scan bound; "
                                                            "state is L2-resident)", "algorithmic_bytes_per_step": b_grow,
                                 "ms_per_step": grow_ms},
             "clocks": clocks,
