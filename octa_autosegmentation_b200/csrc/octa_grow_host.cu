@@ -364,6 +364,10 @@ extern "C" int octa_grow_create(const OctaGrowConfig* cfg, int max_graphs, void*
         S.exact_ball_order = (bo && strcmp(bo, "index") == 0) ? 0 : 1;
     }
     S.commit_smem = 224 * 1024;                       // of the 227 KB a CTA may own on sm_100
+    if (const char* e = getenv("OCTA_COMMIT_SMEM")) {  // tests: a small budget forces k_commit onto the global-memory tree view
+        const int v = atoi(e);
+        if (v >= 1024 && v <= 224 * 1024) S.commit_smem = v;
+    }
     if (2 * cfg->n_trees > S.capN) { delete ctx; set_error("cap_nodes too small"); return OCTA_E_ARG; }
     Carver sizing(nullptr);
     carve(sizing, S, &ctx->D);

@@ -140,3 +140,11 @@ def test_round_robin_sharding_gives_identical_files(growth):
             got, _, _ = growth.grow_batch(cfg, seeds)
             for s, g in zip(seeds, got):
                 assert graph_io.csv_bytes(np.concatenate(g)) == ref[s]
+
+
+def test_commit_global_tree_view_fallback(monkeypatch):
+    """A tree that does not fit k_commit's shared-memory mirror runs the same replay on the global arrays: force that path
+    with a 1 KB budget (decision records and RNG window go to global memory too) and compare with the oracle."""
+    monkeypatch.setenv("OCTA_COMMIT_SMEM", "1024")
+    from octa_autosegmentation_b200 import growth as gmod
+    compare_with_oracle(gmod, small_config(), [0, 1, 2])
