@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <chrono>
 #include <thread>
 #include <vector>
 #include "octa_common.h"
@@ -309,8 +310,11 @@ struct GrowCtx {
     size_t stage_bytes = 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     GrowEvents ev = {nullptr, nullptr, nullptr, nullptr};
-    cudaStream_t side = nullptr;
+    // The growth loop is a chain of short latency-bound launches: both of its streams get the highest priority, so that
+    // throughput kernels of other streams (the voxelizer of the previous batch) do not sit in front of it.
+    cudaStream_t main = nullptr, side = nullptr;
     ~GrowCtx() {
+        if (main) cudaStreamDestroy(main);
         if (side) cudaStreamDestroy(side);
         for (cudaEvent_t e : {ev.start, ev.sinks, ev.kd, ev.killa}) if (e) cudaEventDestroy(e);
         if (dbase) cudaFree(dbase);
@@ -322,6 +326,7 @@ struct GrowCtx {
         if (bytes <= stage_bytes) return OCTA_OK;
         if (stage) cudaFreeHost(stage);
         stage = nullptr; stage_bytes = 0;
+        bytes += bytes / 4;                      // headroom: batch sizes drift by a few percent, pinned reallocation costs ~17 ms
         OCTA_CUDA_CHECK(cudaMallocHost(&stage, bytes));
         stage_bytes = bytes;
         return OCTA_OK;
@@ -380,11 +385,17 @@ extern "C" int octa_grow_create(const OctaGrowConfig* cfg, int max_graphs, void*
         cudaMemset(ctx->D.first, 0x7f, sizeof(int) * (size_t)S.G * S.capN) != cudaSuccess) {
         set_error("cudaMemset failed"); delete ctx; return OCTA_E_CUDA;
     }
+    cudaDeviceSynchronize();                          // (the context's own streams do not wait for the default stream)
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, dev);
     if (prepare_kernels(S) != 0) { cudaGetLastError(); set_error("cudaFuncSetAttribute(k_commit) failed"); delete ctx; return OCTA_E_CUDA; }
-    cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking);
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);      // hi = numerically lowest = greatest priority
+        cudaStreamCreateWithPriority(&ctx->main, cudaStreamNonBlocking, hi);
+        cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, hi);
+    }
     for (cudaEvent_t* e : {&ctx->ev.start, &ctx->ev.sinks, &ctx->ev.kd, &ctx->ev.killa}) cudaEventCreateWithFlags(e, cudaEventDisableTiming);
     cudaEventCreate(&ctx->e0);
     cudaEventCreate(&ctx->e1);
@@ -407,13 +418,19 @@ static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, doub
     GrowShape S = ctx->S;
     S.G = n_graphs;                                   // slabs are graph-major: a smaller batch uses the leading slabs
     GrowDev D = ctx->D;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = ctx->main;
+    // optional host-phase wall clock (OCTA_GROW_HOST_TIMING=1, diagnostics)
+    static const bool host_timing = [] { const char* e = getenv("OCTA_GROW_HOST_TIMING"); return e && e[0] == '1'; }();
+    auto wall = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tw[8] = {0};
+    tw[0] = wall();
     // ---- host initialisation (Greenhouse.__init__ + Forest x2), staged and uploaded with strided copies
     std::vector<HostGraphInit> init(n_graphs);
     for (int g = 0; g < n_graphs; ++g) {
         int rc = init_graph(cfg, seeds[g], &init[g]);
         if (rc) return rc;
     }
+    tw[1] = wall();
     const int n0 = 2 * cfg.n_trees;
     const double r0 = cfg.r / cfg.param_scale;
     const size_t G = n_graphs;
@@ -488,12 +505,14 @@ static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, doub
         OCTA_CUDA_CHECK(cudaStreamSynchronize(st));      // the staging buffer is reused for the read-back
     }
     if (!trace) D.trace = nullptr;
+    tw[2] = wall();
     OCTA_CUDA_CHECK(cudaEventRecord(ctx->e0, st));
     grow_timing_begin(st);
     if (!ctx->sched.empty()) launch_begin(D, S, ctx->sched[0], ctx->n_sm, st, ctx->side, ctx->ev);
     for (size_t i = 0; i < ctx->sched.size(); ++i)
         launch_iteration(D, S, ctx->sched[i], i + 1 < ctx->sched.size() ? &ctx->sched[i + 1] : nullptr, ctx->n_sm, st, ctx->side, ctx->ev);
     OCTA_CUDA_CHECK(cudaEventRecord(ctx->e1, st));
+    tw[3] = wall();
     // ---- read back: counts first, then strided copies of the live prefix of every node array
     std::vector<int> err(n_graphs), nn[2], ns[2];
     std::vector<long long> draws(n_graphs), counters((size_t)n_graphs * 8), dbg((size_t)n_graphs * 8);
@@ -508,6 +527,7 @@ static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, doub
     OCTA_CUDA_CHECK(cudaMemcpyAsync(dbg.data(), D.dbg, 64 * G, cudaMemcpyDeviceToHost, st));
     OCTA_CUDA_CHECK(cudaStreamSynchronize(st));
     OCTA_CUDA_CHECK(cudaGetLastError());
+    tw[4] = wall();
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->e0, ctx->e1);
     if (device_ms) *device_ms = ms;
@@ -546,6 +566,7 @@ static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, doub
             return OCTA_E_NOMEM;
         }
     }
+    tw[5] = wall();
     // ---- exact radii + edge rows, multi-threaded over graphs
     unsigned nthreads = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)n_graphs));
     std::vector<std::thread> pool;
@@ -568,6 +589,10 @@ static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, doub
             }
         });
     for (auto& t : pool) t.join();
+    tw[6] = wall();
+    if (host_timing)
+        fprintf(stderr, "[octa grow host] init %.1f  stage+upload %.1f  launch issue %.1f  wait device %.1f  download %.1f  radii+rows (%u threads) %.1f  | total %.1f ms\n",
+                tw[1] - tw[0], tw[2] - tw[1], tw[3] - tw[2], tw[4] - tw[3], tw[5] - tw[4], nthreads, tw[6] - tw[5], tw[6] - tw[0]);
     int worst = 0;
     for (int g = 0; g < n_graphs; ++g) {
         if (stats) {

@@ -32,6 +32,7 @@ class Pipeline:
         self.host_threads = host_threads or max(1, (os.cpu_count() or 2) - 1)
         self._buf = {}
         self._grow = None
+        self._post_stream = None
         self.edge_cap = 24000      # rows reserved per sample in the pinned edge buffer (docker config: ~13 k)
 
     def _tensor(self, key, shape, dtype, pinned=False):
@@ -45,9 +46,8 @@ class Pipeline:
             self._buf[key] = t
         return t[:n].view(*shape)
 
-    def run(self, seeds: Sequence[int], d2h: bool = True, csv: bool = True) -> dict:
-        """One step over len(seeds) samples.  Results: edges (host), offsets, volume / label / image (device
-        tensors), and with d2h: label_host / image_host (pinned uint8) and csv (list of bytes)."""
+    def _grow_stage(self, seeds: Sequence[int], slot: int = 0) -> dict:
+        """Growth of one batch (blocking; the growth context owns two high-priority streams) into pinned edge rows."""
         torch = self.torch
         with torch.cuda.device(self.device):
             if self._grow is None or self._grow.max_graphs < len(seeds):
@@ -56,40 +56,77 @@ class Pipeline:
                 self._grow = growth.GrowContext(self.config, len(seeds))
             n = len(seeds)
             cap = n * self.edge_cap
-            host_edges = self._tensor("edges_host", (cap, 7), torch.float64, pinned=True)
+            host_edges = self._tensor("edges_host%d" % slot, (cap, 7), torch.float64, pinned=True)
             offs, n_art, stats, grow_ms = self._grow.run_packed(seeds, host_edges.numpy())
-            E = int(offs[-1])
-            he = host_edges.numpy()
-            edges_dev = self._tensor("edges_dev", (cap, 7), torch.float64)
-            edges_dev[:max(E, 1)].copy_(host_edges[:max(E, 1)], non_blocking=True)
-            graphs = [(he[offs[i]:offs[i] + n_art[i]], he[offs[i] + n_art[i]:offs[i + 1]]) for i in range(n)]   # views
-            out = {"graphs": graphs, "stats": stats, "offsets": offs, "grow_device_ms": grow_ms, "edges_host": he[:E]}
-            if self.voxelize:
-                shape = tree2img.voxel_volume_shape(self.volume_dims)
-                vol = self._tensor("vol", (n, *shape), torch.uint16)
-                from . import _lib
-                need = int(_lib.lib().octa_voxelize_workspace_bytes(n, E, _lib.int3(self.volume_dims)))
-                ws = self._tensor("vox_ws", (need,), torch.uint8)
-                vol = tree2img.voxelize_batch_device(edges_dev[:max(E, 1)], offs, self.volume_dims, out=vol, workspace=ws)
-                out["volume"] = vol
-            lab = self._tensor("label", (n, self.label_res[1], self.label_res[0]), torch.uint8)
-            tree2img.raster_batch_device(edges_dev, offs, self.label_res, self.mip_axis, out=lab)
-            img = self._tensor("image", (n, self.image_res[1], self.image_res[0]), torch.uint8)
-            tree2img.raster_batch_device(edges_dev, offs, self.image_res, self.mip_axis, out=img)
-            out["label"], out["image"] = lab, img
-            if d2h:
-                lab_h = self._tensor("label_host", tuple(lab.shape), torch.uint8, pinned=True)
-                img_h = self._tensor("image_host", tuple(img.shape), torch.uint8, pinned=True)
-                lab_h.copy_(lab, non_blocking=True)
-                img_h.copy_(img, non_blocking=True)
-                if csv:
-                    with cf.ThreadPoolExecutor(max_workers=self.host_threads) as ex:   # ctypes releases the GIL
-                        out["csv"] = list(ex.map(lambda i: graph_io.csv_bytes(he[offs[i]:offs[i + 1]]), range(n)))
-                torch.cuda.current_stream().synchronize()
-                out["label_host"], out["image_host"] = lab_h.numpy(), img_h.numpy()
-                out["d2h_bytes"] = int(lab_h.numel() + img_h.numel())
-                out["h2d_bytes"] = int(E * 56)
-            return out
+            return {"n": n, "cap": cap, "host_edges": host_edges, "offs": offs, "n_art": n_art, "stats": stats, "grow_ms": grow_ms}
+
+    def _post_stage(self, g: dict, slot: int, d2h: bool, csv: bool, stream=None) -> dict:
+        """Edge rows -> device, voxelize, 2-D rasters, optional D2H + CSV text, all on `stream` (default: current)."""
+        torch = self.torch
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream() if stream is None else stream
+            with torch.cuda.stream(stream):
+                n, cap, host_edges, offs, n_art = g["n"], g["cap"], g["host_edges"], g["offs"], g["n_art"]
+                sfx = str(slot)
+                E = int(offs[-1])
+                he = host_edges.numpy()
+                edges_dev = self._tensor("edges_dev" + sfx, (cap, 7), torch.float64)
+                edges_dev[:max(E, 1)].copy_(host_edges[:max(E, 1)], non_blocking=True)
+                graphs = [(he[offs[i]:offs[i] + n_art[i]], he[offs[i] + n_art[i]:offs[i + 1]]) for i in range(n)]   # views
+                out = {"graphs": graphs, "stats": g["stats"], "offsets": offs, "grow_device_ms": g["grow_ms"], "edges_host": he[:E]}
+                if self.voxelize:
+                    shape = tree2img.voxel_volume_shape(self.volume_dims)
+                    vol = self._tensor("vol" + sfx, (n, *shape), torch.uint16)
+                    from . import _lib
+                    need = int(_lib.lib().octa_voxelize_workspace_bytes(n, E, _lib.int3(self.volume_dims)))
+                    ws = self._tensor("vox_ws" + sfx, (need,), torch.uint8)
+                    vol = tree2img.voxelize_batch_device(edges_dev[:max(E, 1)], offs, self.volume_dims, out=vol, workspace=ws)
+                    out["volume"] = vol
+                lab = self._tensor("label" + sfx, (n, self.label_res[1], self.label_res[0]), torch.uint8)
+                tree2img.raster_batch_device(edges_dev, offs, self.label_res, self.mip_axis, out=lab)
+                img = self._tensor("image" + sfx, (n, self.image_res[1], self.image_res[0]), torch.uint8)
+                tree2img.raster_batch_device(edges_dev, offs, self.image_res, self.mip_axis, out=img)
+                out["label"], out["image"] = lab, img
+                if d2h:
+                    lab_h = self._tensor("label_host" + sfx, tuple(lab.shape), torch.uint8, pinned=True)
+                    img_h = self._tensor("image_host" + sfx, tuple(img.shape), torch.uint8, pinned=True)
+                    lab_h.copy_(lab, non_blocking=True)
+                    img_h.copy_(img, non_blocking=True)
+                    if csv:
+                        with cf.ThreadPoolExecutor(max_workers=self.host_threads) as ex:   # ctypes releases the GIL
+                            out["csv"] = list(ex.map(lambda i: graph_io.csv_bytes(he[offs[i]:offs[i + 1]]), range(n)))
+                    stream.synchronize()
+                    out["label_host"], out["image_host"] = lab_h.numpy(), img_h.numpy()
+                    out["d2h_bytes"] = int(lab_h.numel() + img_h.numel())
+                    out["h2d_bytes"] = int(E * 56)
+                return out
+
+    def run(self, seeds: Sequence[int], d2h: bool = True, csv: bool = True) -> dict:
+        """One step over len(seeds) samples.  Results: edges (host), offsets, volume / label / image (device
+        tensors), and with d2h: label_host / image_host (pinned uint8) and csv (list of bytes)."""
+        return self._post_stage(self._grow_stage(seeds, 0), 0, d2h, csv)
+
+    def run_pipelined(self, seed_batches, d2h: bool = True, csv: bool = True):
+        """Generator over batches, results in order, software-pipelined over two buffer sets: while the (latency-bound,
+        high-priority) growth loop of batch k runs, a worker thread voxelizes / rasterizes / formats batch k-1 on a second
+        stream.  Every result equals what run() returns for the same seeds; a yielded result stays valid until the
+        batch after the next one is started."""
+        torch = self.torch
+        if self._post_stream is None:
+            with torch.cuda.device(self.device):
+                self._post_stream = torch.cuda.Stream()
+        pending = None
+        with cf.ThreadPoolExecutor(max_workers=1) as worker:
+            for k, seeds in enumerate(seed_batches):
+                slot = k & 1
+                g = self._grow_stage(seeds, slot)
+                if pending is not None:
+                    yield pending.result()
+                pending = worker.submit(self._post_stage, g, slot, d2h, csv, self._post_stream)
+            if pending is not None:
+                yield pending.result()
+                if not d2h:
+                    self._post_stream.synchronize()
 
 
 def shard_seeds(base_seed: int, num_samples: int, rank: int, world: int):

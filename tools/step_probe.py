@@ -18,14 +18,11 @@ seeds = list(range(5000, 5000 + B))
 t = [time.perf_counter()]
 def lap(name):
     torch.cuda.synchronize(); t.append(time.perf_counter()); print("%-28s %7.1f ms" % (name, (t[-1] - t[-2]) * 1e3), flush=True)
-graphs, stats, extra = pipe._grow.run(seeds, copy=False); lap("grow.run (device %.1f)" % extra["device_ms"])
-sizes = [len(a) + len(v) for a, v in graphs]
-offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64); E = int(offs[-1])
-host_edges = torch.empty((E, 7), dtype=torch.float64).pin_memory(); he = host_edges.numpy()
-for i, (a, v) in enumerate(graphs):
-    he[offs[i]:offs[i] + len(a)] = a; he[offs[i] + len(a):offs[i + 1]] = v
-lap("pack edges (python)")
-edges_dev = torch.empty((E, 7), dtype=torch.float64, device="cuda"); edges_dev.copy_(host_edges, non_blocking=True); lap("H2D edges")
+cap = B * pipe.edge_cap
+host_edges = pipe._tensor("edges_host", (cap, 7), torch.float64, pinned=True)
+offs, n_art, stats, grow_ms = pipe._grow.run_packed(seeds, host_edges.numpy()); lap("grow.run_packed (device loop %.1f)" % grow_ms)
+E = int(offs[-1]); he = host_edges.numpy()
+edges_dev = torch.empty((E, 7), dtype=torch.float64, device="cuda"); edges_dev.copy_(host_edges[:E], non_blocking=True); lap("H2D edges")
 vol = tree2img.voxelize_batch_device(edges_dev, offs, [1216, 1216, 16], out=pipe._buf["vol"][:B * 1216 * 1216 * 53].view(B, 1216, 1216, 53)); lap("voxelize")
 lab = tree2img.raster_batch_device(edges_dev[:E], offs, [1216, 1216]); lap("raster 1216")
 img = tree2img.raster_batch_device(edges_dev[:E], offs, [304, 304]); lap("raster 304")
