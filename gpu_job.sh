@@ -1,4 +1,6 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -6 gpurun_out/pytest_gpu.log
-timeout 900 python bench.py > gpurun_out/bench.log 2>&1; tail -1 gpurun_out/bench.log > gpurun_out/bench_line.json; python -c "
-import json; d=json.load(open('gpurun_out/bench_line.json')); print(d['value'], d['e2e']['value'], d['config']['phase_ms'], d['roofline']['frac'], d['gpu_launches'], d['cpu_baseline']['value'])" || tail -20 gpurun_out/bench.log
+timeout 600 python -m pytest tests/test_pipeline_gpu.py -m gpu -x -q > gpurun_out/pytest_pipe.log 2>&1; tail -4 gpurun_out/pytest_pipe.log
+for f in 1 2 3; do
+timeout 900 python bench.py --no-cpu-baseline --steps 6 --in-flight $f > gpurun_out/bench_f$f.log 2>&1; tail -1 gpurun_out/bench_f$f.log | python -c "
+import sys,json; d=json.loads(sys.stdin.read()); print($f, d['value'], d['e2e']['value'], d['config']['phase_ms'])" || tail -5 gpurun_out/bench_f$f.log
+done

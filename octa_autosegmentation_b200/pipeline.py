@@ -6,8 +6,10 @@ This is the device-side composition of the C-ABI entry points that `generate_ves
 reference.  torch is used for device memory, pinned host buffers and streams only."""
 from __future__ import annotations
 
+import collections
 import concurrent.futures as cf
 import os
+import threading
 from typing import Sequence
 
 import numpy as np
@@ -31,7 +33,8 @@ class Pipeline:
         self.voxelize = bool(voxelize)
         self.host_threads = host_threads or max(1, (os.cpu_count() or 2) - 1)
         self._buf = {}
-        self._grow = None
+        self._grows = {}           # growth contexts by index (run_pipelined keeps several batches in flight)
+        self._grow_locks = {}
         self._post_stream = None
         self.edge_cap = 24000      # rows reserved per sample in the pinned edge buffer (docker config: ~13 k)
 
@@ -46,18 +49,24 @@ class Pipeline:
             self._buf[key] = t
         return t[:n].view(*shape)
 
-    def _grow_stage(self, seeds: Sequence[int], slot: int = 0) -> dict:
-        """Growth of one batch (blocking; the growth context owns two high-priority streams) into pinned edge rows."""
+    @property
+    def _grow(self):
+        return self._grows.get(0)
+
+    def _grow_stage(self, seeds: Sequence[int], slot: int = 0, ctx: int = 0) -> dict:
+        """Growth of one batch (blocking; a growth context owns two high-priority streams) into pinned edge rows."""
         torch = self.torch
-        with torch.cuda.device(self.device):
-            if self._grow is None or self._grow.max_graphs < len(seeds):
-                if self._grow is not None:
-                    self._grow.close()
-                self._grow = growth.GrowContext(self.config, len(seeds))
+        lock = self._grow_locks.setdefault(ctx, threading.Lock())
+        with lock, torch.cuda.device(self.device):
+            g = self._grows.get(ctx)
+            if g is None or g.max_graphs < len(seeds):
+                if g is not None:
+                    g.close()
+                g = self._grows[ctx] = growth.GrowContext(self.config, len(seeds))
             n = len(seeds)
             cap = n * self.edge_cap
             host_edges = self._tensor("edges_host%d" % slot, (cap, 7), torch.float64, pinned=True)
-            offs, n_art, stats, grow_ms = self._grow.run_packed(seeds, host_edges.numpy())
+            offs, n_art, stats, grow_ms = g.run_packed(seeds, host_edges.numpy())
             return {"n": n, "cap": cap, "host_edges": host_edges, "offs": offs, "n_art": n_art, "stats": stats, "grow_ms": grow_ms}
 
     def _post_stage(self, g: dict, slot: int, d2h: bool, csv: bool, stream=None) -> dict:
@@ -106,27 +115,34 @@ class Pipeline:
         tensors), and with d2h: label_host / image_host (pinned uint8) and csv (list of bytes)."""
         return self._post_stage(self._grow_stage(seeds, 0), 0, d2h, csv)
 
-    def run_pipelined(self, seed_batches, d2h: bool = True, csv: bool = True):
-        """Generator over batches, results in order, software-pipelined over two buffer sets: while the (latency-bound,
-        high-priority) growth loop of batch k runs, a worker thread voxelizes / rasterizes / formats batch k-1 on a second
-        stream.  Every result equals what run() returns for the same seeds; a yielded result stays valid until the
-        batch after the next one is started."""
+    def run_pipelined(self, seed_batches, d2h: bool = True, csv: bool = True, in_flight: int = 2):
+        """Generator over batches, results in order, software-pipelined.
+
+        The growth loop is a chain of short latency-bound launches that leaves most of the GPU idle, voxelize / raster
+        are throughput kernels, CSV text is host work: `in_flight` growth loops run side by side (one growth context,
+        two high-priority streams and one host thread each) while a worker thread post-processes finished batches on a
+        second stream.  Every result equals what run() returns for the same seeds (a sample depends on its seed only);
+        a yielded result stays valid until `in_flight + 1` further batches have been started."""
         torch = self.torch
+        in_flight = max(1, int(in_flight))
+        nslots = in_flight + 1
         if self._post_stream is None:
             with torch.cuda.device(self.device):
                 self._post_stream = torch.cuda.Stream()
-        pending = None
-        with cf.ThreadPoolExecutor(max_workers=1) as worker:
+        pending = collections.deque()
+        with cf.ThreadPoolExecutor(max_workers=in_flight) as growers, cf.ThreadPoolExecutor(max_workers=1) as poster:
+            def post(gf, slot):
+                return self._post_stage(gf.result(), slot, d2h, csv, self._post_stream)
+
             for k, seeds in enumerate(seed_batches):
-                slot = k & 1
-                g = self._grow_stage(seeds, slot)
-                if pending is not None:
-                    yield pending.result()
-                pending = worker.submit(self._post_stage, g, slot, d2h, csv, self._post_stream)
-            if pending is not None:
-                yield pending.result()
-                if not d2h:
-                    self._post_stream.synchronize()
+                while len(pending) >= nslots:                 # buffer set k % nslots is free once result k - nslots is out
+                    yield pending.popleft().result()
+                gf = growers.submit(self._grow_stage, seeds, k % nslots, k % in_flight)
+                pending.append(poster.submit(post, gf, k % nslots))
+            while pending:
+                yield pending.popleft().result()
+            if not d2h:
+                self._post_stream.synchronize()
 
 
 def shard_seeds(base_seed: int, num_samples: int, rank: int, world: int):

@@ -20,7 +20,7 @@ def lap(name):
     torch.cuda.synchronize(); t.append(time.perf_counter()); print("%-28s %7.1f ms" % (name, (t[-1] - t[-2]) * 1e3), flush=True)
 cap = B * pipe.edge_cap
 host_edges = pipe._tensor("edges_host", (cap, 7), torch.float64, pinned=True)
-offs, n_art, stats, grow_ms = pipe._grow.run_packed(seeds, host_edges.numpy()); lap("grow.run_packed (device loop %.1f)" % grow_ms)
+offs, n_art, stats, grow_ms = pipe._grows[0].run_packed(seeds, host_edges.numpy()); lap("grow.run_packed (device loop %.1f)" % grow_ms)
 E = int(offs[-1]); he = host_edges.numpy()
 edges_dev = torch.empty((E, 7), dtype=torch.float64, device="cuda"); edges_dev.copy_(host_edges[:E], non_blocking=True); lap("H2D edges")
 vol = tree2img.voxelize_batch_device(edges_dev, offs, [1216, 1216, 16], out=pipe._buf["vol"][:B * 1216 * 1216 * 53].view(B, 1216, 1216, 53)); lap("voxelize")
