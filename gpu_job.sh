@@ -1,6 +1,3 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_pipeline_gpu.py -m gpu -x -q > gpurun_out/pytest_pipe.log 2>&1; tail -4 gpurun_out/pytest_pipe.log
-for f in 1 2 3; do
-timeout 900 python bench.py --no-cpu-baseline --steps 6 --in-flight $f > gpurun_out/bench_f$f.log 2>&1; tail -1 gpurun_out/bench_f$f.log | python -c "
-import sys,json; d=json.loads(sys.stdin.read()); print($f, d['value'], d['e2e']['value'], d['config']['phase_ms'])" || tail -5 gpurun_out/bench_f$f.log
-done
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -6 gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3

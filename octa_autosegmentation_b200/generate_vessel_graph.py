@@ -94,17 +94,34 @@ def main(argv=None):
     base = args.seed if args.seed is not None else int.from_bytes(os.urandom(4), "little") % (2 ** 32 - args.num_samples - 1)
     seeds = shard_seeds(base, args.num_samples, rank, world)
     done, failed = 0, []
-    for k in range(0, len(seeds), args.batch):
-        chunk = seeds[k:k + args.batch]
-        try:
-            graphs, _, _ = growth.grow_batch(config, chunk)
-        except Exception as e:       # the reference swallows worker exceptions (futures never read); we report them
-            failed.append((chunk, repr(e)))
-            continue
+    ctx = None
+    pending = None          # the previous chunk's files are written by a worker thread while the next chunk grows
+
+    def write_chunk(graphs):
         for art, ven in graphs:
             write_sample(config, art, ven)
-            done += 1
-        print(f"[rank {rank}] generated {done}/{len(seeds)} vessel graphs", flush=True)
+        return len(graphs)
+
+    import concurrent.futures as cf
+    with cf.ThreadPoolExecutor(max_workers=1) as writer:
+        for k in range(0, len(seeds), args.batch):
+            chunk = seeds[k:k + args.batch]
+            try:
+                if ctx is None:
+                    ctx = growth.GrowContext(config, min(args.batch, len(seeds)))
+                graphs, _, _ = ctx.run(chunk)
+            except Exception as e:       # the reference swallows worker exceptions (futures never read); we report them
+                failed.append((chunk, repr(e)))
+                continue
+            if pending is not None:
+                done += pending.result()
+                print(f"[rank {rank}] generated {done}/{len(seeds)} vessel graphs", flush=True)
+            pending = writer.submit(write_chunk, graphs)
+        if pending is not None:
+            done += pending.result()
+            print(f"[rank {rank}] generated {done}/{len(seeds)} vessel graphs", flush=True)
+    if ctx is not None:
+        ctx.close()
     if failed:
         for chunk, msg in failed:
             print(f"[rank {rank}] FAILED seeds {chunk[0]}..{chunk[-1]}: {msg}", file=sys.stderr)
