@@ -266,7 +266,7 @@ def main():
     torch.cuda.synchronize()
     vox_ms = ve[0].elapsed_time(ve[1]) / nrep
     run_steps(args.in_flight + 1, True)
-    ms_e2e, last = timed(lambda k: run_steps(k, True), max(2, args.steps // 2))
+    ms_e2e, last = timed(lambda k: run_steps(k, True), max(2, args.steps))
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:

@@ -1,3 +1,1 @@
-mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -6 gpurun_out/pytest_gpu.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3
+OCTA_GROW_HOST_TIMING=1 timeout 600 python tools/step_probe.py 2>&1 | grep "host\]" | tail -3

@@ -12,6 +12,7 @@
 #include <string.h>
 #include <algorithm>
 #include <chrono>
+#include <mutex>
 #include <thread>
 #include <vector>
 #include "octa_common.h"
@@ -22,9 +23,11 @@ namespace octa {
 void grow_timing_begin(cudaStream_t st);
 void grow_timing_report();
 struct GrowEvents { cudaEvent_t start, sinks, kd, killa; };
-void launch_begin(const GrowDev& D, const GrowShape& S, const IterP& P0, int n_sm, cudaStream_t st, cudaStream_t side, const GrowEvents& ev);
-void launch_iteration(const GrowDev& D, const GrowShape& S, const IterP& P, const IterP* Pnext, int n_sm, cudaStream_t st,
+void launch_begin(int dslot, const GrowShape& S, const IterP& P0, int n_sm, cudaStream_t st, cudaStream_t side, const GrowEvents& ev);
+void launch_iteration(int dslot, const GrowShape& S, const IterP& P, const IterP* Pnext, int n_sm, cudaStream_t st,
                       cudaStream_t side, const GrowEvents& ev);
+int max_ctx_slots();
+int upload_dev_table(int dslot, const GrowDev& D, cudaStream_t st);
 int prepare_kernels(const GrowShape& S);
 
 namespace {
@@ -297,6 +300,21 @@ void finalize_forest(const OctaGrowConfig& c, int n, const double* px, const dou
     *n_out = k;
 }
 
+// constant-memory slots of the live contexts' pointer tables
+std::mutex g_slot_mutex;
+unsigned int g_slots_used = 0;
+int acquire_slot() {
+    std::lock_guard<std::mutex> lk(g_slot_mutex);
+    for (int i = 0; i < max_ctx_slots() && i < 32; ++i)
+        if (!(g_slots_used & (1u << i))) { g_slots_used |= 1u << i; return i; }
+    return -1;
+}
+void release_slot(int i) {
+    if (i < 0) return;
+    std::lock_guard<std::mutex> lk(g_slot_mutex);
+    g_slots_used &= ~(1u << i);
+}
+
 // persistent growth context: device state for up to G graphs of one configuration
 struct GrowCtx {
     OctaGrowConfig cfg;
@@ -313,7 +331,9 @@ struct GrowCtx {
     // The growth loop is a chain of short latency-bound launches: both of its streams get the highest priority, so that
     // throughput kernels of other streams (the voxelizer of the previous batch) do not sit in front of it.
     cudaStream_t main = nullptr, side = nullptr;
+    int dslot = -1;             // constant-memory slot of this context's pointer table
     ~GrowCtx() {
+        release_slot(dslot);
         if (main) cudaStreamDestroy(main);
         if (side) cudaStreamDestroy(side);
         for (cudaEvent_t e : {ev.start, ev.sinks, ev.kd, ev.killa}) if (e) cudaEventDestroy(e);
@@ -352,6 +372,8 @@ extern "C" int octa_grow_create(const OctaGrowConfig* cfg, int max_graphs, void*
     OCTA_ARG_CHECK(handle && max_graphs > 0 && max_graphs <= 4096, "bad arguments");
     if (octa_device_count() <= 0) { set_error("octa_grow_create: no CUDA device (there is no CPU fallback)"); return OCTA_E_CUDA; }
     GrowCtx* ctx = new GrowCtx();
+    ctx->dslot = acquire_slot();
+    if (ctx->dslot < 0) { delete ctx; set_error("octa_grow_create: too many live growth contexts (max %d)", max_ctx_slots()); return OCTA_E_NOMEM; }
     ctx->cfg = *cfg;
     build_schedule(*cfg, &ctx->sched);
     if (ctx->sched.size() > 4096) { delete ctx; set_error("too many iterations (max 4096)"); return OCTA_E_ARG; }
@@ -508,9 +530,10 @@ static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, doub
     tw[2] = wall();
     OCTA_CUDA_CHECK(cudaEventRecord(ctx->e0, st));
     grow_timing_begin(st);
-    if (!ctx->sched.empty()) launch_begin(D, S, ctx->sched[0], ctx->n_sm, st, ctx->side, ctx->ev);
+    if (upload_dev_table(ctx->dslot, D, st) != 0) { cudaGetLastError(); set_error("cudaMemcpyToSymbol(pointer table) failed"); return OCTA_E_CUDA; }
+    if (!ctx->sched.empty()) launch_begin(ctx->dslot, S, ctx->sched[0], ctx->n_sm, st, ctx->side, ctx->ev);
     for (size_t i = 0; i < ctx->sched.size(); ++i)
-        launch_iteration(D, S, ctx->sched[i], i + 1 < ctx->sched.size() ? &ctx->sched[i + 1] : nullptr, ctx->n_sm, st, ctx->side, ctx->ev);
+        launch_iteration(ctx->dslot, S, ctx->sched[i], i + 1 < ctx->sched.size() ? &ctx->sched[i + 1] : nullptr, ctx->n_sm, st, ctx->side, ctx->ev);
     OCTA_CUDA_CHECK(cudaEventRecord(ctx->e1, st));
     tw[3] = wall();
     // ---- read back: counts first, then strided copies of the live prefix of every node array

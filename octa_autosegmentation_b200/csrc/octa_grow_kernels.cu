@@ -24,6 +24,11 @@
 
 namespace octa {
 
+// The table of device pointers (GrowDev, ~0.9 KB) lives in constant memory, one slot per growth context, instead of
+// travelling with each of the ~3 750 launches of a run: kernels receive the slot index.
+constexpr int MAX_CTX_SLOTS = 16;
+__constant__ GrowDev c_dev[MAX_CTX_SLOTS];
+
 // ------------------------------------------------------------------------------------------
 // block-wide helpers
 // ------------------------------------------------------------------------------------------
@@ -264,13 +269,14 @@ __device__ __forceinline__ void grid_build_body(const GrowDev& D, const GrowShap
     }
 }
 
-__global__ void __launch_bounds__(1024) k_grid_build(GrowDev D, GrowShape S, IterP P, int which) { grid_build_body(D, S, P, which, blockIdx.x); }
+__global__ void __launch_bounds__(1024) k_grid_build(int dslot, GrowShape S, IterP P, int which) { grid_build_body(c_dev[dslot], S, P, which, blockIdx.x); }
 
 // k_prepare: everything the sampling of an iteration needs, in ONE launch: blockIdx.y = 0..2 -> the bucket grids of
 // the arterial nodes (+radius), the O2 sinks and the active arterial nodes, blockIdx.y = 3 -> the candidate sampler.
 // 4*G CTAs run side by side instead of four dependent single-wave launches.  (The grid of the active venous nodes is
 // rebuilt by k_grid_build right after the venous commit.)
-__global__ void __launch_bounds__(1024) k_prepare(GrowDev D, GrowShape S, IterP P) {
+__global__ void __launch_bounds__(1024) k_prepare(int dslot, GrowShape S, IterP P) {
+    const GrowDev& D = c_dev[dslot];
     if (blockIdx.y < 3) grid_build_body(D, S, P, (int)blockIdx.y, blockIdx.x);
     else sample_body(D, S, P, blockIdx.x);
 }
@@ -278,7 +284,8 @@ __global__ void __launch_bounds__(1024) k_prepare(GrowDev D, GrowShape S, IterP 
 // ------------------------------------------------------------------------------------------
 // k_sink_tests: thread per candidate over the bucket grids of the arterial nodes and the O2 sinks
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TILE) k_sink_tests(GrowDev D, GrowShape S, IterP P) {
+__global__ void __launch_bounds__(TILE) k_sink_tests(int dslot, GrowShape S, IterP P) {
+    const GrowDev& D = c_dev[dslot];
     const int tiles = (S.Nmax + TILE - 1) / TILE;
     const double epsn2 = P.eps_n_eff * P.eps_n_eff, epss2 = P.eps_s * P.eps_s;
     const size_t gcap = S.capN > S.capS ? S.capN : S.capS;
@@ -324,7 +331,8 @@ __global__ void __launch_bounds__(TILE) k_sink_tests(GrowDev D, GrowShape S, Ite
 // ------------------------------------------------------------------------------------------
 // k_sink_greedy: one CTA per graph; lexicographically-first maximal independent set in rounds
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_sink_greedy(GrowDev D, GrowShape S, IterP P) {
+__global__ void __launch_bounds__(1024) k_sink_greedy(int dslot, GrowShape S, IterP P) {
+    const GrowDev& D = c_dev[dslot];
     const int g = blockIdx.x, tid = threadIdx.x;
     if (D.err[g]) return;
     const int nc = D.n_cand[g];
@@ -399,7 +407,8 @@ __global__ void __launch_bounds__(1024) k_sink_greedy(GrowDev D, GrowShape S, It
 // k_assign: thread per attractor; exact nearest ACTIVE node within delta through the bucket grid
 // (ties -> lowest list position, as a scan in list order would give)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TILE) k_assign(GrowDev D, GrowShape S, IterP P, int f) {
+__global__ void __launch_bounds__(TILE) k_assign(int dslot, GrowShape S, IterP P, int f) {
+    const GrowDev& D = c_dev[dslot];
     const int tiles = (S.capS + TILE - 1) / TILE;
     const double delta = P.delta[f];
     const size_t gcap = S.capN > S.capS ? S.capN : S.capS;
@@ -433,7 +442,8 @@ __global__ void __launch_bounds__(TILE) k_assign(GrowDev D, GrowShape S, IterP P
 // ------------------------------------------------------------------------------------------
 // k_group: one CTA per graph
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_group(GrowDev D, GrowShape S, IterP P, int f) {
+__global__ void __launch_bounds__(1024) k_group(int dslot, GrowShape S, IterP P, int f) {
+    const GrowDev& D = c_dev[dslot];
     __shared__ uint32_t mt[624];
     __shared__ int s_idx;
     const int g = blockIdx.x, tid = threadIdx.x;
@@ -711,7 +721,8 @@ __device__ __forceinline__ void load_ctx(const GrowDev& D, const GrowShape& S, c
     nc->dist_to_center = norm2(nc->vtc);
 }
 
-__global__ void __launch_bounds__(128) k_eval(GrowDev D, GrowShape S, IterP P, int f) {
+__global__ void __launch_bounds__(128) k_eval(int dslot, GrowShape S, IterP P, int f) {
+    const GrowDev& D = c_dev[dslot];
     const int g = blockIdx.y;
     if (D.err[g]) return;
     const int nd_ = D.n_dict[g];
@@ -1094,7 +1105,8 @@ __device__ void commit_body(const GrowDev& D, const GrowShape& S, const IterP& P
     }
 }
 
-__global__ void __launch_bounds__(512) k_commit(GrowDev D, GrowShape S, IterP P, int f) {
+__global__ void __launch_bounds__(512) k_commit(int dslot, GrowShape S, IterP P, int f) {
+    const GrowDev& D = c_dev[dslot];
     extern __shared__ __align__(16) int s_dyn[];
     const int g = blockIdx.x;
     if (D.err[g]) return;
@@ -1121,7 +1133,8 @@ __device__ void pyset_insert_clean(long long* th, int* tk, size_t mask, int key,
     }
 }
 
-__global__ void __launch_bounds__(1024) k_kill(GrowDev D, GrowShape S, IterP P, int f) {
+__global__ void __launch_bounds__(1024) k_kill(int dslot, GrowShape S, IterP P, int f) {
+    const GrowDev& D = c_dev[dslot];
     __shared__ double nxs[512], nys[512], nzs[512];
     const int g = blockIdx.x, tid = threadIdx.x;
     if (D.err[g]) return;
@@ -1317,7 +1330,8 @@ __global__ void __launch_bounds__(1024) k_kill(GrowDev D, GrowShape S, IterP P, 
 // (= the tree the reference queries in step 3, greenhouse.py:101-102).  Runs on a side stream, concurrently with
 // the arterial growth kernels, which do not modify the sink list.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_kdbuild(GrowDev D, GrowShape S, int smem_bytes) {
+__global__ void __launch_bounds__(1024) k_kdbuild(int dslot, GrowShape S, int smem_bytes) {
+    const GrowDev& D = c_dev[dslot];
     extern __shared__ __align__(16) char s_kd[];
     __shared__ int s_ws[kdpar::WS_INTS];
     __shared__ double s_wd[kdpar::WD_DOUBLES];
@@ -1342,6 +1356,13 @@ __global__ void __launch_bounds__(1024) k_kdbuild(GrowDev D, GrowShape S, int sm
 // launch wrappers (called from octa_grow_host.cu)
 // ------------------------------------------------------------------------------------------
 size_t commit_smem_bytes(const GrowShape& S) { return (size_t)S.commit_smem; }
+
+int max_ctx_slots() { return MAX_CTX_SLOTS; }
+
+// copy a context's pointer table into its constant-memory slot (ordered on `st`; the source may be a stack variable)
+int upload_dev_table(int dslot, const GrowDev& D, cudaStream_t st) {
+    return (int)cudaMemcpyToSymbolAsync(c_dev, &D, sizeof(GrowDev), sizeof(GrowDev) * (size_t)dslot, cudaMemcpyHostToDevice, st);
+}
 
 constexpr int KD_SMEM_BYTES = 208 * 1024;        // + ~17 KB static: scan / reduction scratch
 
@@ -1406,55 +1427,56 @@ void grow_timing_report() {       // call after the streams have been synchronis
 //   side:                                     [wait kill[a]] prepare tests greedy (sinks) kdbuild (kd)   -> iteration i+1
 struct GrowEvents { cudaEvent_t start, sinks, kd, killa; };
 
-void launch_sampling(const GrowDev& D, const GrowShape& S, const IterP& P, int n_sm, cudaStream_t side, const GrowEvents& ev) {
+void launch_sampling(int dslot, const GrowShape& S, const IterP& P, int n_sm, cudaStream_t side, const GrowEvents& ev) {
     tick(side, 15, 1);            // (the time since the previous side-stream event was spent waiting for the main stream)
-    k_prepare<<<dim3(S.G, 4), 1024, 0, side>>>(D, S, P);
+    k_prepare<<<dim3(S.G, 4), 1024, 0, side>>>(dslot, S, P);
     tick(side, 1, 1);
-    k_sink_tests<<<n_sm * 8, TILE, 0, side>>>(D, S, P);
+    k_sink_tests<<<n_sm * 8, TILE, 0, side>>>(dslot, S, P);
     tick(side, 2, 1);
-    k_sink_greedy<<<S.G, 1024, 0, side>>>(D, S, P);
+    k_sink_greedy<<<S.G, 1024, 0, side>>>(dslot, S, P);
     tick(side, 3, 1);
     cudaEventRecord(ev.sinks, side);
     count_launch(3);
     if (S.exact_ball_order) {
-        k_kdbuild<<<S.G, 1024, KD_SMEM_BYTES, side>>>(D, S, KD_SMEM_BYTES);
+        k_kdbuild<<<S.G, 1024, KD_SMEM_BYTES, side>>>(dslot, S, KD_SMEM_BYTES);
         tick(side, 14, 1);
         count_launch(1);
     }
     cudaEventRecord(ev.kd, side);
 }
 
-void launch_begin(const GrowDev& D, const GrowShape& S, const IterP& P0, int n_sm, cudaStream_t st, cudaStream_t side, const GrowEvents& ev) {
+void launch_begin(int dslot, const GrowShape& S, const IterP& P0, int n_sm, cudaStream_t st, cudaStream_t side, const GrowEvents& ev) {
     // uploads of the initial state were issued on `st`
-    k_grid_build<<<S.G, 1024, 0, st>>>(D, S, P0, 3);
+    k_grid_build<<<S.G, 1024, 0, st>>>(dslot, S, P0, 3);
     count_launch(1);
     cudaEventRecord(ev.start, st);
     cudaStreamWaitEvent(side, ev.start, 0);
-    launch_sampling(D, S, P0, n_sm, side, ev);
+    launch_sampling(dslot, S, P0, n_sm, side, ev);
 }
 
-void launch_iteration(const GrowDev& D, const GrowShape& S, const IterP& P, const IterP* Pnext, int n_sm, cudaStream_t st,
+void launch_iteration(int dslot, const GrowShape& S, const IterP& P, const IterP* Pnext, int n_sm, cudaStream_t st,
                       cudaStream_t side, const GrowEvents& ev) {
     cudaStreamWaitEvent(st, ev.sinks, 0);
     for (int f = 0; f < 2; ++f) {
-        k_assign<<<n_sm * 8, TILE, 0, st>>>(D, S, P, f);
+        k_assign<<<n_sm * 8, TILE, 0, st>>>(dslot, S, P, f);
         tick(st, 4 + 5 * f);
-        k_group<<<S.G, 1024, 0, st>>>(D, S, P, f);
+        k_group<<<S.G, 1024, 0, st>>>(dslot, S, P, f);
         tick(st, 5 + 5 * f);
-        k_eval<<<dim3(16, S.G), 128, 0, st>>>(D, S, P, f);
+        k_eval<<<dim3(16, S.G), 128, 0, st>>>(dslot, S, P, f);
         tick(st, 6 + 5 * f);
-        k_commit<<<S.G, 512, commit_smem_bytes(S), st>>>(D, S, P, f);
+        static const int commit_threads = [] { const char* e = getenv("OCTA_COMMIT_THREADS"); const int v = e ? atoi(e) : 0; return (v == 128 || v == 256 || v == 512) ? v : 512; }();
+        k_commit<<<S.G, commit_threads, commit_smem_bytes(S), st>>>(dslot, S, P, f);
         tick(st, 7 + 5 * f);
         if (f == 0) cudaStreamWaitEvent(st, ev.kd, 0);
-        else { k_grid_build<<<S.G, 1024, 0, st>>>(D, S, P, 3); count_launch(1); }
-        k_kill<<<S.G, 1024, 0, st>>>(D, S, P, f);
+        else { k_grid_build<<<S.G, 1024, 0, st>>>(dslot, S, P, 3); count_launch(1); }
+        k_kill<<<S.G, 1024, 0, st>>>(dslot, S, P, f);
         tick(st, 8 + 5 * f);
         count_launch(5);
         if (f == 0) {
             cudaEventRecord(ev.killa, st);
             if (Pnext) {
                 cudaStreamWaitEvent(side, ev.killa, 0);
-                launch_sampling(D, S, *Pnext, n_sm, side, ev);
+                launch_sampling(dslot, S, *Pnext, n_sm, side, ev);
             }
         }
     }
