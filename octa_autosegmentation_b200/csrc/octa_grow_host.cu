@@ -334,6 +334,7 @@ struct GrowCtx {
     int dslot = -1;             // constant-memory slot of this context's pointer table
     ~GrowCtx() {
         release_slot(dslot);
+        if (ev_done) cudaEventDestroy(ev_done);
         if (main) cudaStreamDestroy(main);
         if (side) cudaStreamDestroy(side);
         for (cudaEvent_t e : {ev.start, ev.sinks, ev.kd, ev.killa}) if (e) cudaEventDestroy(e);
@@ -341,6 +342,16 @@ struct GrowCtx {
         if (stage) cudaFreeHost(stage);
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
+    }
+    // wait for `st` without spinning: several growth loops (and ranks) share the host cores
+    cudaEvent_t ev_done = nullptr;
+    cudaError_t wait(cudaStream_t st) {
+        if (!ev_done) {
+            cudaError_t e = cudaEventCreateWithFlags(&ev_done, cudaEventBlockingSync | cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+        }
+        cudaError_t e = cudaEventRecord(ev_done, st);
+        return e != cudaSuccess ? e : cudaEventSynchronize(ev_done);
     }
     int ensure_stage(size_t bytes) {
         if (bytes <= stage_bytes) return OCTA_OK;
@@ -524,7 +535,7 @@ static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, doub
         OCTA_CUDA_CHECK(cudaMemsetAsync(D.err, 0, 4 * G, st));
         OCTA_CUDA_CHECK(cudaMemsetAsync(D.cbits, 0, sizeof(unsigned int) * G * 4 * ((S.capN + 31) / 32), st));
         if (trace) OCTA_CUDA_CHECK(cudaMemsetAsync(D.trace, 0, sizeof(int) * G * 4096 * 4, st));
-        OCTA_CUDA_CHECK(cudaStreamSynchronize(st));      // the staging buffer is reused for the read-back
+        OCTA_CUDA_CHECK(ctx->wait(st));      // the staging buffer is reused for the read-back
     }
     if (!trace) D.trace = nullptr;
     tw[2] = wall();
@@ -548,7 +559,7 @@ static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, doub
     OCTA_CUDA_CHECK(cudaMemcpyAsync(draws.data(), D.py_draws, 8 * G, cudaMemcpyDeviceToHost, st));
     OCTA_CUDA_CHECK(cudaMemcpyAsync(counters.data(), D.counters, 64 * G, cudaMemcpyDeviceToHost, st));
     OCTA_CUDA_CHECK(cudaMemcpyAsync(dbg.data(), D.dbg, 64 * G, cudaMemcpyDeviceToHost, st));
-    OCTA_CUDA_CHECK(cudaStreamSynchronize(st));
+    OCTA_CUDA_CHECK(ctx->wait(st));
     OCTA_CUDA_CHECK(cudaGetLastError());
     tw[4] = wall();
     float ms = 0;
@@ -576,7 +587,7 @@ static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, doub
         OCTA_CUDA_CHECK(dn2d(so[f][0], D.nx[f], 8)); OCTA_CUDA_CHECK(dn2d(so[f][1], D.ny[f], 8)); OCTA_CUDA_CHECK(dn2d(so[f][2], D.nz[f], 8));
         OCTA_CUDA_CHECK(dn2d(so[f][3], D.npar[f], 4)); OCTA_CUDA_CHECK(dn2d(so[f][4], D.nmeta[f], 1));
     }
-    OCTA_CUDA_CHECK(cudaStreamSynchronize(st));
+    OCTA_CUDA_CHECK(ctx->wait(st));
     std::vector<int64_t> row0(n_graphs + 1, 0);
     if (packed_offsets) {
         // every non-root node is one row; roots = N_trees per forest

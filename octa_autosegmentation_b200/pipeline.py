@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import collections
 import concurrent.futures as cf
+import ctypes
 import os
 import threading
 from typing import Sequence
@@ -87,14 +88,22 @@ class Pipeline:
                     shape = tree2img.voxel_volume_shape(self.volume_dims)
                     vol = self._tensor("vol" + sfx, (n, *shape), torch.uint16)
                     from . import _lib
-                    need = int(_lib.lib().octa_voxelize_workspace_bytes(n, E, _lib.int3(self.volume_dims)))
+                    # sized for the edge capacity, not for this batch: a growing workspace would mean a cudaMalloc (device-wide
+                    # synchronisation) in the middle of the growth loops that are in flight
+                    need = int(_lib.lib().octa_voxelize_workspace_bytes(n, max(E, cap), _lib.int3(self.volume_dims)))
                     ws = self._tensor("vox_ws" + sfx, (need,), torch.uint8)
                     vol = tree2img.voxelize_batch_device(edges_dev[:max(E, 1)], offs, self.volume_dims, out=vol, workspace=ws)
                     out["volume"] = vol
+                from . import _lib as _l
+                L = _l.lib()
+                L.octa_raster2d_workspace_bytes.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int]
+                L.octa_raster2d_workspace_bytes.restype = ctypes.c_size_t
                 lab = self._tensor("label" + sfx, (n, self.label_res[1], self.label_res[0]), torch.uint8)
-                tree2img.raster_batch_device(edges_dev, offs, self.label_res, self.mip_axis, out=lab)
+                ws_l = self._tensor("r2d_ws_label" + sfx, (int(L.octa_raster2d_workspace_bytes(n, max(E, cap), self.label_res[1], self.label_res[0])),), torch.uint8)
+                tree2img.raster_batch_device(edges_dev, offs, self.label_res, self.mip_axis, out=lab, workspace=ws_l)
                 img = self._tensor("image" + sfx, (n, self.image_res[1], self.image_res[0]), torch.uint8)
-                tree2img.raster_batch_device(edges_dev, offs, self.image_res, self.mip_axis, out=img)
+                ws_i = self._tensor("r2d_ws_image" + sfx, (int(L.octa_raster2d_workspace_bytes(n, max(E, cap), self.image_res[1], self.image_res[0])),), torch.uint8)
+                tree2img.raster_batch_device(edges_dev, offs, self.image_res, self.mip_axis, out=img, workspace=ws_i)
                 out["label"], out["image"] = lab, img
                 if d2h:
                     lab_h = self._tensor("label_host" + sfx, tuple(lab.shape), torch.uint8, pinned=True)
