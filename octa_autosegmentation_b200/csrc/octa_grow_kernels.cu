@@ -1173,20 +1173,20 @@ __global__ void __launch_bounds__(1024) k_kill(int dslot, GrowShape S, IterP P, 
                 H += total;
             }
             __syncthreads();
-            // veto: a venous node within eps_k (greenhouse.py:106-109), warp per hit
+            // veto: a venous node within eps_k (greenhouse.py:106-109).  Thread per venous node against the hits staged in
+            // shared memory (a warp per hit walking all venous nodes was one dependent L2 round trip per 32 nodes).
             unsigned char* veto = D.veto + sb;
             const int Vn = D.n_nodes[1][g];
-            const int lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-            for (int h = warp; h < H; h += nw) {
-                const int i = hl[h];
-                const double px = sx[i], py = sy[i], pz = sz[i];
-                bool any = false;
-                for (int j = lane; j < Vn && !any; j += 32) {
-                    const double d2 = dist2(D.nx[1][nb + j], D.ny[1][nb + j], D.nz[1][nb + j], px, py, pz);
-                    if (within_sqrt(d2, P.eps_k, epsk2)) any = true;
+            for (int hb = 0; hb < H; hb += 512) {
+                const int cnth = H - hb < 512 ? H - hb : 512;
+                __syncthreads();
+                for (int k = tid; k < cnth; k += blockDim.x) { const int i = hl[hb + k]; nxs[k] = sx[i]; nys[k] = sy[i]; nzs[k] = sz[i]; veto[hb + k] = 0; }
+                __syncthreads();
+                for (int j = tid; j < Vn; j += blockDim.x) {
+                    const double vx = D.nx[1][nb + j], vy = D.ny[1][nb + j], vz = D.nz[1][nb + j];
+                    for (int k = 0; k < cnth; ++k)
+                        if (within_sqrt(dist2(vx, vy, vz, nxs[k], nys[k], nzs[k]), P.eps_k, epsk2)) veto[hb + k] = 1;
                 }
-                any = __any_sync(0xffffffffu, any);
-                if (lane == 0) veto[h] = any ? 1 : 0;
             }
             __syncthreads();
             // insertion sequence: by (first new node that hits it, list index) -- the order of
