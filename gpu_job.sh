@@ -1,2 +1,7 @@
 mkdir -p gpurun_out
-OCTA_GROW_TIMING=1 timeout 300 python tools/grow_probe.py --batch 64 --check 24 2>&1 | grep -E "timing|rep 1|parity" | tail -4
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python tools/sanitize_small.py > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?" >> gpurun_out/sanitizer_memcheck.log
+tail -4 gpurun_out/sanitizer_memcheck.log
+timeout 900 compute-sanitizer --tool initcheck --error-exitcode 7 python tools/sanitize_small.py > gpurun_out/sanitizer_initcheck.log 2>&1; echo "initcheck rc=$?" >> gpurun_out/sanitizer_initcheck.log
+tail -4 gpurun_out/sanitizer_initcheck.log
+timeout 1200 compute-sanitizer --tool racecheck --error-exitcode 7 python tools/sanitize_small.py > gpurun_out/sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?" >> gpurun_out/sanitizer_racecheck.log
+tail -4 gpurun_out/sanitizer_racecheck.log
