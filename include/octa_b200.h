@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define OCTA_ABI_VERSION 1
+#define OCTA_ABI_VERSION 2
 
 #define OCTA_OK 0
 #define OCTA_E_ARG (-1)     /* bad argument */
@@ -117,6 +117,11 @@ typedef struct OctaGrowConfig {
     int32_t n_walls;
     int32_t walls[6];                /* enabled source walls in config order: 0=x0 1=x1 2=y0 3=y1 */
     int32_t cap_nodes, cap_sinks;    /* per-graph capacities; 0 = automatic */
+    /* SimulationSpace.oxygen_sample_geometry_path (simulation_space.py:26-34,69-76,95-96): the loaded .npy as a C-order
+     * 0/1 byte mask [geom_dims[0]][geom_dims[1]][geom_dims[2]], or NULL.  With a mask, `size` is ignored (the space is
+     * geom_dims / max(geom_dims)).  Supported: 2-D square masks (geom_dims = {n, n, 1}, n <= 76).  Copied at create time. */
+    const unsigned char* geometry;
+    int32_t geom_dims[3];
 } OctaGrowConfig;
 
 typedef struct OctaGrowStats {
@@ -124,7 +129,7 @@ typedef struct OctaGrowStats {
     int64_t sum_A, sum_M, sum_P, sum_S;   /* byte-accounting counters of SURVEY.md 8(d) */
     int64_t commit_cycles[4];        /* SM cycles of k_commit's prologue / sequential replay / refresh / active-list phases */
     int64_t replay_detail[8];        /* replay breakdown: cycles in tag scans, walks, rechecks; counts of entries, events, walk steps, tags, decision records */
-    int32_t err;                     /* 0 ok; 1 node capacity, 2 sink capacity, 3 rng buffer, 4 recheck queue, 5 set table, 1x eig */
+    int32_t err;                     /* 0 ok; 1 node capacity, 2 sink capacity, 3 rng buffer, 5 set table, 6 geometry mask index, 1x eig */
     int32_t n_iters;
 } OctaGrowStats;
 

@@ -19,6 +19,7 @@ struct IterP {
     double eps_n_eff, eps_s, eps_k, delta[2], gamma[2], phi, omega, kappa, d, r, rotation_radius;
     double faz_cx, faz_cy, param_scale, shape[3];
     int N, t, first_mode, mode_idx, iter;
+    int geom_n;          // fixed sampling geometry: side of the square mask (GrowDev::geom_mask), 0 = none
     double kap_tab[9];   // kappa of the node's creation mode (arterial_tree.py:32); [8] = 4, the add_node default of the stumps
     double leafc_tab[9]; // r ** kap_tab[q]: what a fresh leaf contributes to a parent of creation mode q (see GrowDev::ncon)
 };
@@ -74,6 +75,7 @@ struct GrowDev {
     double* faz_radius;
     int* n_valid;
     unsigned char* valid_ij;
+    unsigned char* geom_mask;   // [geom_n][geom_n] bytes of SimulationSpace.oxygen_sample_geometry_path (one copy per context), or unused
     // scratch
     unsigned int *vi, *ubuf;
     double *cx, *cy, *cz;

@@ -84,6 +84,12 @@ int init_graph(const OctaGrowConfig& c, uint64_t seed, HostGraphInit* h) {
     const bool nerve = (nc[0] - nr <= 1) && (nc[1] - nr <= 1);
     const double ncv[2] = {nc[0] * GEOMETRY_SIZE, nc[1] * GEOMETRY_SIZE}, nrv = nr * GEOMETRY_SIZE;
     h->valid_ij.clear();
+    const int gn = c.geometry ? c.geom_dims[0] : 0;      // fixed geometry: valid_voxels = argwhere(mask) (simulation_space.py:34)
+    if (gn) {
+        for (int i = 0; i < gn; ++i)
+            for (int j = 0; j < gn; ++j)
+                if (c.geometry[i * gn + j]) { h->valid_ij.push_back((unsigned char)i); h->valid_ij.push_back((unsigned char)j); }
+    } else
     for (int i = 0; i < nx; ++i)
         for (int j = 0; j < ny; ++j) {
             const double a = (double)j - fc[0], b = (double)i - fc[1];
@@ -104,7 +110,37 @@ int init_graph(const OctaGrowConfig& c, uint64_t seed, HostGraphInit* h) {
                     const double lo = (p - d0 > 0) ? -1.0 : 0.0, hi = (p + d0 < size) ? 1.0 : 0.0;
                     return np_uniform(h->np_mt, lo, hi);
                 };
-                if (wall == 0 || wall == 1) {
+                // fixed geometry (simulation_space.py:69-76): random.choice over argwhere of the wall plane, then
+                // _vox_2_unit_pos (three np.random.uniform(0,1) draws).  The plane index is `0 if first else shape[axis]-1`
+                // with the NORMALISED shape, i.e. 0.0 for a full-length axis: the far walls sample plane 0 as well.
+                auto fixed_wall = [&](int axis, double* a_out, double* z_out) -> bool {
+                    std::vector<int> rows;
+                    for (int q = 0; q < gn; ++q)
+                        if (axis == 0 ? c.geometry[0 * gn + q] : c.geometry[q * gn + 0]) rows.push_back(q);
+                    if (rows.empty()) return false;
+                    const int a = rows[py_randbelow(h->py_mt, (int)rows.size())];
+                    const double idx3[3] = {axis == 0 ? 0.0 : (double)a, axis == 0 ? (double)a : 0.0, 0.0};
+                    double p3[3];
+                    for (int k = 0; k < 3; ++k) p3[k] = (idx3[k] + np_uniform(h->np_mt, 0, 1)) / (double)gn;
+                    *a_out = axis == 0 ? p3[1] : p3[0];
+                    *z_out = p3[2];
+                    return true;
+                };
+                if (gn && wall < 4) {
+                    double a, z;
+                    if (!fixed_wall(wall < 2 ? 0 : 1, &a, &z)) { set_error("geometry mask: the wall plane has no valid voxel"); return OCTA_E_ARG; }
+                    if (wall < 2) {
+                        pos[0] = wall == 0 ? 0.0 : c.size[0] - 1e-6; pos[1] = a; pos[2] = z;
+                        dir[0] = wall == 0 ? np_uniform(h->np_mt, 0.1, 1) : np_uniform(h->np_mt, -1, -0.1);
+                        dir[1] = rng_dir(a, c.size[1]);
+                        dir[2] = rng_dir(z, c.size[2]);
+                    } else {
+                        pos[0] = a; pos[1] = wall == 2 ? 0.0 : c.size[1] - 1e-6; pos[2] = z;
+                        dir[0] = rng_dir(a, c.size[0]);
+                        dir[1] = wall == 2 ? np_uniform(h->np_mt, 0.1, 1) : np_uniform(h->np_mt, -1, -0.1);
+                        dir[2] = rng_dir(z, c.size[2]);
+                    }
+                } else if (wall == 0 || wall == 1) {
                     const double y = np_uniform(h->np_mt, 0, c.size[1]), z = np_uniform(h->np_mt, 0, c.size[2]);
                     pos[0] = wall == 0 ? 0.0 : c.size[0] - 1e-6; pos[1] = y; pos[2] = z;
                     dir[0] = wall == 0 ? np_uniform(h->np_mt, 0.1, 1) : np_uniform(h->np_mt, -1, -0.1);
@@ -175,6 +211,7 @@ void build_schedule(const OctaGrowConfig& c, std::vector<IterP>* out) {
             P.param_scale = ps;
             for (int k = 0; k < 3; ++k) P.shape[k] = c.size[k];
             P.N = N; P.t = t; P.first_mode = m.first_mode; P.mode_idx = mi; P.iter = iter++;
+            P.geom_n = c.geometry ? c.geom_dims[0] : 0;
             for (int q = 0; q < 8; ++q) P.kap_tab[q] = q < c.n_modes ? c.modes[q].kappa : 4.0;
             P.kap_tab[8] = 4.0;
             for (int q = 0; q < 9; ++q) P.leafc_tab[q] = pow(P.r, P.kap_tab[q]);
@@ -221,6 +258,7 @@ void carve(Carver& c, const GrowShape& S, GrowDev* D) {
     D->py_buf = c.take<unsigned int>(G * S.pycap); D->py_n = c.take<int>(G); D->py_pos = c.take<int>(G);
     D->py_draws = c.take<long long>(G);
     D->faz_radius = c.take<double>(G); D->n_valid = c.take<int>(G); D->valid_ij = c.take<unsigned char>(G * MAX_VALID * 2);
+    D->geom_mask = c.take<unsigned char>(MAX_VALID);
     D->vi = c.take<unsigned int>(GC); D->ubuf = c.take<unsigned int>(6 * GC);
     D->cx = c.take<double>(GC); D->cy = c.take<double>(GC); D->cz = c.take<double>(GC);
     D->n_cand = c.take<int>(G); D->cpass = c.take<unsigned char>(GC); D->cstate = c.take<unsigned char>(GC);
@@ -332,6 +370,7 @@ struct GrowCtx {
     // throughput kernels of other streams (the voxelizer of the previous batch) do not sit in front of it.
     cudaStream_t main = nullptr, side = nullptr;
     int dslot = -1;             // constant-memory slot of this context's pointer table
+    std::vector<unsigned char> geom;   // copy of the fixed sampling geometry (cfg.geometry points here)
     ~GrowCtx() {
         release_slot(dslot);
         if (ev_done) cudaEventDestroy(ev_done);
@@ -382,11 +421,22 @@ extern "C" int octa_grow_create(const OctaGrowConfig* cfg, int max_graphs, void*
     if (rc) return rc;
     OCTA_ARG_CHECK(handle && max_graphs > 0 && max_graphs <= 4096, "bad arguments");
     if (octa_device_count() <= 0) { set_error("octa_grow_create: no CUDA device (there is no CPU fallback)"); return OCTA_E_CUDA; }
+    if (cfg->geometry) {
+        const int n = cfg->geom_dims[0];
+        OCTA_ARG_CHECK(cfg->geom_dims[2] == 1 && cfg->geom_dims[1] == n && n >= 1 && n <= GEOMETRY_SIZE,
+                       "geometry mask must be [n, n, 1] with n <= 76");
+    }
     GrowCtx* ctx = new GrowCtx();
     ctx->dslot = acquire_slot();
     if (ctx->dslot < 0) { delete ctx; set_error("octa_grow_create: too many live growth contexts (max %d)", max_ctx_slots()); return OCTA_E_NOMEM; }
     ctx->cfg = *cfg;
-    build_schedule(*cfg, &ctx->sched);
+    if (cfg->geometry) {      // own copy of the mask; the space becomes geom_dims / max(geom_dims) (simulation_space.py:31-33)
+        const int n = cfg->geom_dims[0];
+        ctx->geom.assign(cfg->geometry, cfg->geometry + (size_t)n * n);
+        ctx->cfg.geometry = ctx->geom.data();
+        for (int k = 0; k < 3; ++k) ctx->cfg.size[k] = (double)cfg->geom_dims[k] / (double)n;
+    }
+    build_schedule(ctx->cfg, &ctx->sched);
     if (ctx->sched.size() > 4096) { delete ctx; set_error("too many iterations (max 4096)"); return OCTA_E_ARG; }
     int Nmax = 1;
     long total_try = 0;
@@ -422,6 +472,9 @@ extern "C" int octa_grow_create(const OctaGrowConfig* cfg, int max_graphs, void*
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (!ctx->geom.empty() && cudaMemcpy(ctx->D.geom_mask, ctx->geom.data(), ctx->geom.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("upload of the geometry mask failed"); delete ctx; return OCTA_E_CUDA;
+    }
     if (prepare_kernels(S) != 0) { cudaGetLastError(); set_error("cudaFuncSetAttribute(k_commit) failed"); delete ctx; return OCTA_E_CUDA; }
     {
         int lo = 0, hi = 0;
@@ -645,7 +698,7 @@ static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, doub
     }
     if (worst) {
         set_error("octa_grow_run: simulation error code %d (1 node capacity, 2 sink capacity, 3 rng buffer, "
-                  "5 set table, 12/13 eigen solver, 100 edge buffer too small)", worst);
+                  "5 set table, 6 sample outside the geometry mask array, 12/13 eigen solver, 100 edge buffer too small)", worst);
         return OCTA_E_STATE;
     }
     return OCTA_OK;

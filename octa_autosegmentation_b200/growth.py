@@ -29,7 +29,7 @@ class OctaGrowConfig(ctypes.Structure):
                 ("param_scale", ctypes.c_double), ("size", ctypes.c_double * 3), ("n_modes", ctypes.c_int32),
                 ("modes", OctaGrowMode * 8), ("forest_type", ctypes.c_int32), ("n_trees", ctypes.c_int32),
                 ("n_walls", ctypes.c_int32), ("walls", ctypes.c_int32 * 6), ("cap_nodes", ctypes.c_int32),
-                ("cap_sinks", ctypes.c_int32)]
+                ("cap_sinks", ctypes.c_int32), ("geometry", ctypes.c_void_p), ("geom_dims", ctypes.c_int32 * 3)]
 
 
 class OctaGrowStats(ctypes.Structure):
@@ -41,8 +41,6 @@ class OctaGrowStats(ctypes.Structure):
 def make_config(config: dict, cap_nodes: int = 0, cap_sinks: int = 0) -> OctaGrowConfig:
     g, f = config["Greenhouse"], config["Forest"]
     ss = g["SimulationSpace"]
-    if ss.get("oxygen_sample_geometry_path") is not None:
-        raise NotImplementedError("SimulationSpace.oxygen_sample_geometry_path (fixed .npy geometry) is not supported yet")
     modes = g["modes"]
     if not 1 <= len(modes) <= 8:
         raise ValueError("between 1 and 8 growth modes are supported")
@@ -54,7 +52,18 @@ def make_config(config: dict, cap_nodes: int = 0, cap_sinks: int = 0) -> OctaGro
     c.nerve_center[0], c.nerve_center[1] = [float(x) for x in g["nerve_center"]]
     c.nerve_radius = float(g["nerve_radius"])
     c.param_scale = float(g["param_scale"])
-    c.size[0], c.size[1], c.size[2] = float(ss["no_voxel_x"]), float(ss["no_voxel_y"]), float(ss["no_voxel_z"])
+    if ss.get("oxygen_sample_geometry_path") is not None:
+        # simulation_space.py:29-34: the mask replaces no_voxel_x/y/z (the library copies it at octa_grow_create)
+        geo = np.ascontiguousarray(np.load(ss["oxygen_sample_geometry_path"]).astype(bool).astype(np.uint8))
+        if geo.ndim != 3 or geo.shape[2] != 1 or geo.shape[0] != geo.shape[1] or geo.shape[0] > 76:
+            raise NotImplementedError("oxygen_sample_geometry_path: only square 2-D masks of shape [n, n, 1], n <= 76, are supported")
+        c._geometry_keepalive = geo
+        c.geometry = geo.ctypes.data
+        for k in range(3):
+            c.geom_dims[k] = geo.shape[k]
+            c.size[k] = geo.shape[k] / max(geo.shape)
+    else:
+        c.size[0], c.size[1], c.size[2] = float(ss["no_voxel_x"]), float(ss["no_voxel_y"]), float(ss["no_voxel_z"])
     c.n_modes = len(modes)
     for i, m in enumerate(modes):
         om = c.modes[i]

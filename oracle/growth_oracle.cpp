@@ -62,6 +62,9 @@ struct OGConfig {
     int walls[6];    /* enabled source walls in config order: 0=x0 1=x1 2=y0 3=y1 4=z0 5=z1 */
     int ball_order;  /* 0 = cKDTree order (exact), 1 = list-index order (sensitivity experiments) */
     int venous;      /* 1 = grow a venous forest as well (generate_vessel_graph.py:34) */
+    /* SimulationSpace.oxygen_sample_geometry_path (simulation_space.py:26-34): C-order bool mask, or NULL */
+    const unsigned char* geometry;
+    int geom_dims[3];
 };
 
 typedef void (*og_eig_hook)(const double* cov9, double* w3, double* v9);
@@ -518,6 +521,7 @@ struct Sim {
     double orig_scale[6];
     /* simulation space */
     double shape[3];
+    int GSZ = 76; /* geometry_size */
     std::vector<int> valid_voxels; /* pairs (i, j) */
     double ss_FAZ_center[2], ss_FAZ_radius;
     Forest F[2]; /* 0 arterial, 1 venous */
@@ -547,6 +551,18 @@ struct Sim {
         FAZ_center[0] = cfg.faz_center[0]; FAZ_center[1] = cfg.faz_center[1];
         const double nc[2] = {cfg.nerve_center[0] / param_scale, cfg.nerve_center[1] / param_scale};
         const double nr = cfg.nerve_radius / param_scale;
+        if (cfg.geometry) { /* simulation_space.py:29-34: shape = geometry.shape / max(geometry.shape); valid = argwhere(geometry) */
+            GSZ = std::max(cfg.geom_dims[0], std::max(cfg.geom_dims[1], cfg.geom_dims[2]));
+            for (int k = 0; k < 3; ++k) shape[k] = (double)cfg.geom_dims[k] / (double)GSZ;
+            if (cfg.geom_dims[2] != 1) abort(); /* only 2-D masks are restated (valid_voxels holds (i, j) pairs) */
+            valid_voxels.clear();
+            for (int i = 0; i < cfg.geom_dims[0]; ++i)
+                for (int j = 0; j < cfg.geom_dims[1]; ++j)
+                    if (cfg.geometry[(size_t)i * cfg.geom_dims[1] + j]) { valid_voxels.push_back(i); valid_voxels.push_back(j); }
+            init_params(cfg.modes[0]);
+            return;
+        }
+        GSZ = 76;
         for (int k = 0; k < 3; ++k) shape[k] = cfg.size[k];
         const int GS = 76;
         ss_FAZ_center[0] = FAZ_center[0] * GS; ss_FAZ_center[1] = FAZ_center[1] * GS;
@@ -568,10 +584,15 @@ struct Sim {
         init_params(cfg.modes[0]);
     }
 
-    /* simulation_space.py:89-98 (non-fixed geometry) */
+    /* simulation_space.py:89-98 */
     bool is_valid_position(const double* p) const {
         for (int k = 0; k < 3; ++k)
             if (p[k] >= shape[k] || p[k] < 0) return false;
+        if (cfg.geometry) { /* geometry[(pos * geometry_size).astype(uint16)] > 0 */
+            const int vi = (int)(uint16_t)(p[0] * (double)GSZ), vj = (int)(uint16_t)(p[1] * (double)GSZ), vk = (int)(uint16_t)(p[2] * (double)GSZ);
+            if (vi >= cfg.geom_dims[0] || vj >= cfg.geom_dims[1] || vk >= cfg.geom_dims[2]) abort(); /* numpy IndexError */
+            return cfg.geometry[((size_t)vi * cfg.geom_dims[1] + vj) * cfg.geom_dims[2] + vk] != 0;
+        }
         double a = p[0] - ss_FAZ_center[0], b = p[1] - ss_FAZ_center[1]; /* zip-truncated eukledian_dist */
         double s = 0 + pow(a, 2.0);
         s = s + pow(b, 2.0);
@@ -588,14 +609,32 @@ struct Sim {
                 double lo = (p - d0 > 0) ? -1.0 : 0.0, hi = (p + d0 < size) ? 1.0 : 0.0;
                 return np.uniform(lo, hi);
             };
+            /* simulation_space.py:69-76, fixed geometry: random.choice over argwhere of the wall plane.  ax_index is
+               `0 if first else self.shape[axis]-1` with the NORMALISED shape, i.e. 0.0 for a full-length axis: the far
+               walls sample plane 0 as well. */
+            auto fixed_wall = [&](int axis, double* a_out, double* z_out) {
+                std::vector<int> rows;
+                if (axis == 0) { for (int y = 0; y < cfg.geom_dims[1]; ++y) if (cfg.geometry[(size_t)0 * cfg.geom_dims[1] + y]) rows.push_back(y); }
+                else { for (int x = 0; x < cfg.geom_dims[0]; ++x) if (cfg.geometry[(size_t)x * cfg.geom_dims[1] + 0]) rows.push_back(x); }
+                const int a = rows[py.randbelow((int)rows.size())];
+                const double idx3[3] = {axis == 0 ? 0.0 : (double)a, axis == 0 ? (double)a : 0.0, 0.0};
+                double p3[3];
+                for (int k = 0; k < 3; ++k) p3[k] = (idx3[k] + (0.0 + 1.0 * np.dbl())) / (double)GSZ; /* _vox_2_unit_pos */
+                *a_out = axis == 0 ? p3[1] : p3[0];
+                *z_out = p3[2];
+            };
             if (wall == 0 || wall == 1) {
-                double y = np.uniform(0, shape[1]), z = np.uniform(0, shape[2]);
+                double y, z;
+                if (cfg.geometry) fixed_wall(0, &y, &z);
+                else { y = np.uniform(0, shape[1]); z = np.uniform(0, shape[2]); }
                 pos[0] = wall == 0 ? 0.0 : shape[0] - 1e-6; pos[1] = y; pos[2] = z;
                 dir[0] = wall == 0 ? np.uniform(0.1, 1) : np.uniform(-1, -0.1);
                 dir[1] = rng_dir(y, shape[1]);
                 dir[2] = rng_dir(z, shape[2]);
             } else if (wall == 2 || wall == 3) {
-                double x = np.uniform(0, shape[0]), z = np.uniform(0, shape[2]);
+                double x, z;
+                if (cfg.geometry) fixed_wall(1, &x, &z);
+                else { x = np.uniform(0, shape[0]); z = np.uniform(0, shape[2]); }
                 pos[0] = x; pos[1] = wall == 2 ? 0.0 : shape[1] - 1e-6; pos[2] = z;
                 dir[0] = rng_dir(x, shape[0]);
                 dir[1] = wall == 2 ? np.uniform(0.1, 1) : np.uniform(-1, -0.1);
@@ -667,8 +706,8 @@ struct Sim {
         cand.reserve(3 * n_try);
         for (int i = 0; i < n_try; ++i) {
             double u0 = np.dbl(), u1 = np.dbl(), u2 = np.dbl(); /* uniform(0,1) = 0 + (1-0)*x */
-            double p[3] = {((double)valid_voxels[2 * vi[i]] + (0.0 + 1.0 * u0)) / 76.0,
-                           ((double)valid_voxels[2 * vi[i] + 1] + (0.0 + 1.0 * u1)) / 76.0, (0.0 + (0.0 + 1.0 * u2)) / 76.0};
+            double p[3] = {((double)valid_voxels[2 * vi[i]] + (0.0 + 1.0 * u0)) / (double)GSZ,
+                           ((double)valid_voxels[2 * vi[i] + 1] + (0.0 + 1.0 * u1)) / (double)GSZ, (0.0 + (0.0 + 1.0 * u2)) / (double)GSZ};
             if (is_valid_position(p)) cand.insert(cand.end(), p, p + 3);
         }
         std::vector<double> added;

@@ -28,7 +28,8 @@ class OGConfig(ctypes.Structure):
                 ("nerve_radius", ctypes.c_double), ("param_scale", ctypes.c_double), ("size", ctypes.c_double * 3),
                 ("n_modes", ctypes.c_int), ("modes", OGMode * 8), ("forest_type", ctypes.c_int),
                 ("n_trees", ctypes.c_int), ("n_walls", ctypes.c_int), ("walls", ctypes.c_int * 6),
-                ("ball_order", ctypes.c_int), ("venous", ctypes.c_int)]
+                ("ball_order", ctypes.c_int), ("venous", ctypes.c_int),
+                ("geometry", ctypes.c_void_p), ("geom_dims", ctypes.c_int * 3)]
 
 
 class OGStats(ctypes.Structure):
@@ -87,8 +88,16 @@ def make_config(config: dict, ball_order: int = 0, venous: bool = True) -> OGCon
     c.param_scale = float(g["param_scale"])
     ss = g["SimulationSpace"]
     if ss.get("oxygen_sample_geometry_path") is not None:
-        raise NotImplementedError("fixed geometry sampling is not restated in the oracle")
-    c.size[0], c.size[1], c.size[2] = float(ss["no_voxel_x"]), float(ss["no_voxel_y"]), float(ss["no_voxel_z"])
+        geo = np.ascontiguousarray(np.load(ss["oxygen_sample_geometry_path"]).astype(bool).astype(np.uint8))
+        if geo.ndim != 3 or geo.shape[2] != 1:
+            raise NotImplementedError("only 2-D geometry masks (shape [X, Y, 1]) are restated in the oracle")
+        c._geometry_keepalive = geo
+        c.geometry = geo.ctypes.data
+        for k in range(3):
+            c.geom_dims[k] = geo.shape[k]
+            c.size[k] = geo.shape[k] / max(geo.shape)
+    else:
+        c.size[0], c.size[1], c.size[2] = float(ss["no_voxel_x"]), float(ss["no_voxel_y"]), float(ss["no_voxel_z"])
     modes = g["modes"]
     c.n_modes = len(modes)
     for i, m in enumerate(modes):

@@ -4,6 +4,9 @@
 
   graph_small_s{0,1}.csv      seeded growth, docker config cut to I=(12,12), N=400     (ref_harness.run_growth)
   graph_docker_s0.csv.gz      seeded growth, docker config verbatim, seed 0  (needs --full, ~100 s)
+  graph_geom_s{0,1}.csv       the same with SimulationSpace.oxygen_sample_geometry_path = tests/golden/geometry_mask.npy
+                              (a synthetic 76x76x1 mask written by geometry_mask(); fixed-geometry branch of
+                              simulation_space.py:26-34,69-76,95-96)
   vox_small_s0_*.npz          tree2img.voxelize_forest of graph_small_s0.csv for several requests
   vox_docker_s0.json          sha256 / non-zero count of voxelize_forest(graph_docker_s0, [304,304,4]) and,
                               with --full, of the [1216,1216,16] request (77 s in the reference)
@@ -28,6 +31,17 @@ def digest(a: np.ndarray) -> dict:
             "sha256": hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()}
 
 
+def geometry_mask() -> np.ndarray:
+    """Synthetic oxygen-sample geometry (bool [76, 76, 1]): a hole, a blocked bar and partly blocked wall planes."""
+    g = np.ones((76, 76, 1), dtype=bool)
+    yy, xx = np.ogrid[:76, :76]
+    g[:, :, 0] &= (xx - 38) ** 2 + (yy - 37) ** 2 > 6.5 ** 2
+    g[10:13, 58:71, 0] = False
+    g[0, :7, 0] = False          # wall plane used by x0 / x1
+    g[:5, 0, 0] = False          # wall plane used by y0 / y1
+    return g
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
@@ -36,6 +50,14 @@ def main():
     for seed in (0, 1):
         art, ven, _ = rh.run_growth(rh.small_config(), seed)
         with open(os.path.join(GOLD, "graph_small_s%d.csv" % seed), "wb") as f:
+            f.write(rh.csv_bytes(art, ven))
+    mask_path = os.path.join(GOLD, "geometry_mask.npy")
+    np.save(mask_path, geometry_mask())
+    for seed in (0, 1):
+        cfg = rh.small_config()
+        cfg["Greenhouse"]["SimulationSpace"]["oxygen_sample_geometry_path"] = mask_path
+        art, ven, _ = rh.run_growth(cfg, seed)
+        with open(os.path.join(GOLD, "graph_geom_s%d.csv" % seed), "wb") as f:
             f.write(rh.csv_bytes(art, ven))
     rows = rh.read_csv_rows(os.path.join(GOLD, "graph_small_s0.csv"))
     cases = {"304x304x4": ([304, 304, 4], {}), "304x304x4_ignz": ([304, 304, 4], {"ignore_z": True}),

@@ -148,3 +148,14 @@ def test_commit_global_tree_view_fallback(monkeypatch):
     monkeypatch.setenv("OCTA_COMMIT_SMEM", "1024")
     from octa_autosegmentation_b200 import growth as gmod
     compare_with_oracle(gmod, small_config(), [0, 1, 2])
+
+
+def test_fixed_geometry_vs_reference_csv(growth):
+    """f-4: SimulationSpace.oxygen_sample_geometry_path.  Goldens written by the unmodified reference with the synthetic mask
+    tests/golden/geometry_mask.npy (oracle/make_golden.py)."""
+    cfg = small_config()
+    cfg["Greenhouse"]["SimulationSpace"]["oxygen_sample_geometry_path"] = os.path.join(GOLDEN, "geometry_mask.npy")
+    graphs, _ = compare_with_oracle(growth, cfg, [0, 1, 2, 3])
+    for seed in (0, 1):
+        got = numpy_csv(np.concatenate(graphs[seed]))
+        assert got == open(os.path.join(GOLDEN, "graph_geom_s%d.csv" % seed), "rb").read()

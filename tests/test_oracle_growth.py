@@ -103,6 +103,16 @@ def test_small_config_byte_exact(seed):
     assert got == open(os.path.join(GOLDEN, "graph_small_s%d.csv" % seed), "rb").read()
 
 
+@pytest.mark.parametrize("seed", [0, 1])
+def test_fixed_geometry_byte_exact(seed):
+    """SimulationSpace.oxygen_sample_geometry_path (simulation_space.py:26-34,69-76,95-96): wall positions through
+    random.choice over the mask's wall plane, sampling from argwhere(mask), mask lookup in is_valid_position."""
+    cfg = small_config()
+    cfg["Greenhouse"]["SimulationSpace"]["oxygen_sample_geometry_path"] = os.path.join(GOLDEN, "geometry_mask.npy")
+    got, _ = oracle_csv(cfg, seed)
+    assert got == open(os.path.join(GOLDEN, "graph_geom_s%d.csv" % seed), "rb").read()
+
+
 @pytest.mark.parametrize("seed", [0, 1, 2, 3])
 def test_docker_config_byte_exact(seed):
     """BASELINE config #1: docker/vessel_graph_gen_docker_config.yml, fixed seed."""
