@@ -524,10 +524,10 @@ static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, doub
         // staging layout: per array a dense [G][n0] block
         size_t off = 0;
         auto blk = [&](size_t elem) { size_t o = off; off = align_up(off + elem * G * n0, 256); return o; };
-        size_t o_x[2], o_y[2], o_z[2], o_r[2], o_k[2], o_p[2], o_c0[2], o_c1[2], o_act[2], o_n[2], o_m[2];
+        size_t o_x[2], o_y[2], o_z[2], o_r[2], o_p[2], o_c0[2], o_c1[2], o_n[2], o_m[2];
         for (int f = 0; f < 2; ++f) {
-            o_x[f] = blk(8); o_y[f] = blk(8); o_z[f] = blk(8); o_r[f] = blk(8); o_k[f] = blk(8);
-            o_p[f] = blk(4); o_c0[f] = blk(4); o_c1[f] = blk(4); o_act[f] = blk(4); o_n[f] = blk(1); o_m[f] = blk(1);
+            o_x[f] = blk(8); o_y[f] = blk(8); o_z[f] = blk(8); o_r[f] = blk(8);
+            o_p[f] = blk(4); o_c0[f] = blk(4); o_c1[f] = blk(4); o_n[f] = blk(1); o_m[f] = blk(1);
         }
         const size_t o_mt_np = off; off = align_up(off + sizeof(MTState) * G, 256);
         const size_t o_mt_py = off; off = align_up(off + sizeof(MTState) * G, 256);
@@ -543,14 +543,14 @@ static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, doub
             for (int f = 0; f < 2; ++f) {
                 double* hx = (double*)(sg + o_x[f]) + (size_t)g * n0; double* hy = (double*)(sg + o_y[f]) + (size_t)g * n0;
                 double* hz = (double*)(sg + o_z[f]) + (size_t)g * n0; double* hr = (double*)(sg + o_r[f]) + (size_t)g * n0;
-                double* hk = (double*)(sg + o_k[f]) + (size_t)g * n0;
                 int* hp = (int*)(sg + o_p[f]) + (size_t)g * n0; int* hc0 = (int*)(sg + o_c0[f]) + (size_t)g * n0;
-                int* hc1 = (int*)(sg + o_c1[f]) + (size_t)g * n0; int* hact = (int*)(sg + o_act[f]) + (size_t)g * n0;
+                int* hc1 = (int*)(sg + o_c1[f]) + (size_t)g * n0;
                 unsigned char* hn = (unsigned char*)(sg + o_n[f]) + (size_t)g * n0; unsigned char* hm = (unsigned char*)(sg + o_m[f]) + (size_t)g * n0;
                 for (int i = 0; i < n0; ++i) { hc0[i] = -1; hc1[i] = -1; hn[i] = 0; }
                 for (int i = 0; i < n0; ++i) {
                     hx[i] = h.pos[f][3 * i]; hy[i] = h.pos[f][3 * i + 1]; hz[i] = h.pos[f][3 * i + 2];
-                    hr[i] = pow(r0, 4.0) /* ncon: every initial node hangs below a kappa-4 node */; hk[i] = 4.0; hp[i] = h.parent[f][i]; hact[i] = i; hm[i] = 0xff;
+                    hr[i] = pow(r0, 4.0);   // ncon: every initial node hangs below a kappa-4 node
+                    hp[i] = h.parent[f][i]; hm[i] = 0xff;
                     if (hp[i] >= 0) { hc0[hp[i]] = i; hn[hp[i]] = 1; }
                 }
             }
