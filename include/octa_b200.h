@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define OCTA_ABI_VERSION 2
+#define OCTA_ABI_VERSION 3
 
 #define OCTA_OK 0
 #define OCTA_E_ARG (-1)     /* bad argument */
@@ -167,6 +167,36 @@ int octa_format_csv(const double* edges7, int64_t n_edges, char* buf, size_t cap
 int64_t octa_parse_csv(const char* text, size_t len, double* edges7_out, int64_t cap_edges);
 
 /* ------------------------------------------------------------------------------------------------
+ * GAN contrast adaptation (BASELINE config #5) -- replaces the generator forward behind
+ * test.py:58-90 (GanSegModel.inference, models/gan_seg_model.py:65-79 -> ResnetGenerator.forward,
+ * models/networks.py:350-443; resnetGenerator9 :502-503) and the pixel transforms of
+ * docker/trained_models/GAN/config.yml:49-92 (ScaleIntensityd, background Rotate90d+Flipd,
+ * AddRandomBackgroundNoised data/data_transforms.py:498-516, CastToTyped) plus the uint8 writer
+ * utils/visualizer.py:338.  The 3x3 convolutions run on tcgen05 tensor cores (bf16 x bf16 -> fp32).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct OctaGanWeights {      /* HOST pointers, float32, the reference state-dict layouts [Cout][Cin][kh][kw] */
+    const float* stem_w;             /* model.1.weight  [64][1][7][7]                                          */
+    const float* conv_w[22];         /* model.4, model.8, model.12..20 .conv_block.1 / .5 (interleaved), model.22, model.26 */
+    const float* head_w;             /* model.30.weight [1][64][7][7]                                          */
+    float head_b;                    /* model.30.bias; the other biases cancel in InstanceNorm2d(affine=False)  */
+    int reserved;
+} OctaGanWeights;
+/* Uploads the weights (3x3 kernels as bf16 [Cout][tap][Cin]) and allocates activations for up to max_images images of
+ * H x W (multiples of 4) per call: about 145 MB per 304 x 304 image. */
+int octa_gan_create(const OctaGanWeights* w, int max_images, int H, int W, void** handle);
+/* x_dev float32 [n][H][W] in [0,1] -> y_dev float32 [n][H][W] (sigmoid output) and/or y_u8_dev = uint8(y * 255);
+ * either output may be NULL.  Asynchronous on `stream`. */
+int octa_gan_forward_dev(void* handle, const float* x_dev, int n_images, float* y_dev, uint8_t* y_u8_dev, void* stream);
+void octa_gan_destroy(void* handle);
+/* speckle_dev[i] = the float64 array of `np.random.seed(seeds[i]); np.random.uniform(0, 1, (H, W))` (data_transforms.py:510) */
+int octa_gan_speckle_dev(const uint32_t* seeds_dev, int n_images, int H, int W, double* speckle_dev, void* stream);
+/* x = float32(max(scale(raster), scale(background)^T * speckle)) per image (scale = ScaleIntensity to [0,1]; the
+ * transpose is Rotate90d(k=1) followed by Flipd(0)).  background_dev and speckle_dev may both be NULL (no noise).
+ * minmax_ws_dev: 4 ints per image of scratch. */
+int octa_gan_input_dev(const uint8_t* raster_dev, const uint8_t* background_dev, const double* speckle_dev, int n_images, int H, int W,
+                       int* minmax_ws_dev, float* x_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Test hooks (host-only code paths of host/device-shared building blocks; used by the CPU tests).
  * ---------------------------------------------------------------------------------------------- */
 /* 3x3 symmetric eigenproblem with LAPACK dgeev's ordering and sign (greenhouse.py:229). cov9/v9 row-major;
@@ -181,6 +211,9 @@ void octa_test_kd_indices(const double* x, const double* y, const double* z, int
 int octa_test_kd_indices_gpu(const double* x, const double* y, const double* z, int n, int* idx_out);
 /* the shared-memory resident build k_kdbuild prefers (n <= ~17 k): rank_out[idx_out[i]] = i; -1 everywhere if it bailed out */
 int octa_test_kd_ranks_gpu_smem(const double* x, const double* y, const double* z, int n, int* rank_out);
+/* one 3x3 convolution (padding 1, zero or reflect) through the tcgen05 kernel of the GAN path, HOST tensors in torch layouts:
+ * x [n][Cin][H][W], w [Cout][Cin][3][3] -> y [n][Cout][H][W] (inputs rounded to bf16, fp32 accumulation, bf16 result) */
+int octa_test_gan_conv3_host(const float* x, const float* w, int n, int H, int W, int cin, int cout, int reflect, float* y);
 /* CPython hash((np.float64 x, y, z)) (greenhouse.py:100-111 set ordering) */
 int64_t octa_test_hash_tuple3(const double* xyz);
 

@@ -64,7 +64,10 @@ def build_library(force: bool = False, verbose: bool = True) -> str:
                         for h in glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh"))
                         + glob.glob(os.path.join(PKG_DIR, "..", "include", "*.h")))):
             continue
-        cmd = [_nvcc(), *NVCC_FLAGS, "-x", "cu", "-c", src, "-o", obj]
+        flags = list(NVCC_FLAGS)
+        if os.path.basename(src) == "octa_gan.cu":        # float32 / bf16 network math: contraction is welcome there
+            flags.remove("-fmad=false")
+        cmd = [_nvcc(), *flags, "-x", "cu", "-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, p in procs:

@@ -35,7 +35,7 @@ def test_exports_every_declared_symbol(libpath):
 
 def test_version_and_no_device_behaviour(libpath):
     from octa_autosegmentation_b200 import _lib, tree2img
-    assert _lib.lib().octa_abi_version() == 2
+    assert _lib.lib().octa_abi_version() == 3
     assert tree2img.voxel_volume_shape([1216, 1216, 16]) == (1216, 1216, 53)
     assert _lib.lib().octa_voxelize_workspace_bytes(1, 1000, _lib.int3([304, 304, 4])) > 0
     if _lib.lib().octa_device_count() == 0:

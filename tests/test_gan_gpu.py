@@ -1,0 +1,118 @@
+"""GPU parity tests of the GAN contrast-adaptation path (BASELINE config #5) through the C ABI.
+
+Oracle: oracle/gan_oracle.py (plain PyTorch fp32 restatement, pinned bit-exactly to the reference's classes with the
+shipped checkpoint by tests/test_oracle_gan.py).  Bars:
+  * speckle stream and input transform: bit-exact;
+  * one tcgen05 3x3 convolution: bf16 inputs, fp32 accumulation, bf16 result -> |err| <= 2^-8 * |ref| + 2e-3 * scale;
+  * whole generator (bf16 activations between layers): max |err| <= 0.06, mean |err| <= 0.008 on the sigmoid output
+    (a CPU emulation of the bf16 rounding points gives max 0.025 / mean 0.004), i.e. a few grey levels of the uint8 PNG.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf16_round(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(torch.bfloat16).to(torch.float32)
+
+
+@pytest.mark.parametrize("cin,cout,reflect,shape", [(64, 128, False, (2, 20, 24)), (256, 256, True, (1, 19, 19)),
+                                                    (128, 64, False, (1, 37, 22)), (128, 256, False, (3, 12, 50))])
+def test_conv3_tcgen05_matches_torch(cin, cout, reflect, shape):
+    import torch
+    import torch.nn.functional as F
+    from octa_autosegmentation_b200 import gan
+
+    n, H, W = shape
+    rs = np.random.RandomState(cin + cout + H)
+    x = rs.standard_normal((n, cin, H, W)).astype(np.float32)
+    w = (rs.standard_normal((cout, cin, 3, 3)) * (2.0 / (9 * cin)) ** 0.5).astype(np.float32)
+    y = gan.conv3_test(x, w, reflect)
+    xt, wt = _bf16_round(x), _bf16_round(w)
+    xp = F.pad(xt, (1, 1, 1, 1), mode="reflect" if reflect else "constant")
+    ref = F.conv2d(xp.double(), wt.double()).float().numpy()
+    err = np.abs(y - ref)
+    tol = np.abs(ref) * 2.0 ** -8 + 2e-3 * ref.std()
+    assert np.isfinite(y).all()
+    assert (err <= tol).all(), "max err %g at %s (ref std %g)" % (err.max(), np.unravel_index(err.argmax(), err.shape), ref.std())
+
+
+def test_speckle_stream_is_numpy_legacy_stream():
+    from octa_autosegmentation_b200 import gan
+
+    seeds = [0, 1, 675570, 2 ** 32 - 1]
+    got = gan.speckle_device(seeds, 52, 36).cpu().numpy()
+    for i, s in enumerate(seeds):
+        np.random.seed(s)
+        assert np.array_equal(got[i], np.random.uniform(0, 1, (52, 36)))
+    got = gan.speckle_device([7], 304, 304).cpu().numpy()
+    np.random.seed(7)
+    assert np.array_equal(got[0], np.random.uniform(0, 1, (304, 304)))
+
+
+def test_prepare_input_bit_exact():
+    import torch
+    from octa_autosegmentation_b200 import gan
+    from oracle import gan_oracle as go
+
+    rs = np.random.RandomState(3)
+    n, H = 3, 48
+    raster = (rs.rand(n, H, H) * 255 * (rs.rand(n, H, H) > 0.6)).astype(np.uint8)
+    raster[2] = 17                                    # constant image -> zeros (ScaleIntensity with max == min)
+    bg = rs.randint(3, 250, (n, H, H)).astype(np.uint8)
+    seeds = [11, 12, 13]
+    sp = gan.speckle_device(seeds, H, H)
+    x = gan.prepare_input(torch.from_numpy(raster).cuda(), torch.from_numpy(bg).cuda(), sp).cpu().numpy()
+    for i in range(n):
+        ref = go.prepare_input(raster[i], bg[i], go.speckle(seeds[i], (H, H)))
+        assert np.array_equal(x[i, 0], ref)
+    x0 = gan.prepare_input(torch.from_numpy(raster).cuda()).cpu().numpy()
+    for i in range(n):
+        assert np.array_equal(x0[i, 0], go.scale_intensity(raster[i]))
+
+
+@pytest.mark.parametrize("seed,n,size", [(1, 3, 64), (2, 2, 100)])
+def test_generator_matches_oracle(seed, n, size):
+    import torch
+    from octa_autosegmentation_b200 import gan
+    from oracle import gan_oracle as go
+
+    sd = go.random_state_dict(seed)
+    g = torch.Generator().manual_seed(100 + seed)
+    x = torch.rand(n, 1, size, size, generator=g)
+    x = x * (x > 0.6)
+    with torch.no_grad():
+        ref = go.generator_forward(sd, x).numpy()
+    G = gan.ResnetGenerator9(sd, image_size=(size, size), max_images=2)      # n > max_images: exercises the chunk loop
+    out8 = torch.empty((n, size, size), dtype=torch.uint8, device="cuda")
+    y = G.forward(x.cuda(), out_u8=out8).cpu().numpy()
+    G.close()
+    err = np.abs(y - ref)
+    print("generator seed %d: max err %.4f mean err %.5f" % (seed, err.max(), err.mean()))
+    assert np.isfinite(y).all()
+    assert err.max() <= 0.06 and err.mean() <= 0.008
+    assert np.array_equal(out8.cpu().numpy(), (y[:, 0] * np.float32(255)).astype(np.uint8))
+    d8 = np.abs(out8.cpu().numpy().astype(int) - go.to_png_u8(ref[:, 0]).astype(int))
+    assert d8.max() <= 16
+
+
+def test_contrast_adapt_full_size_runs():
+    import torch
+    from octa_autosegmentation_b200 import gan
+    from oracle import gan_oracle as go
+
+    sd = go.random_state_dict(5)
+    rs = np.random.RandomState(9)
+    raster = (rs.rand(2, 304, 304) > 0.8).astype(np.uint8) * 200
+    bg = rs.randint(0, 255, (2, 304, 304)).astype(np.uint8)
+    G = gan.ResnetGenerator9(sd, image_size=(304, 304), max_images=2)
+    out = gan.contrast_adapt(G, torch.from_numpy(raster).cuda(), torch.from_numpy(bg).cuda(), [1, 2]).cpu().numpy()
+    x = np.stack([go.prepare_input(raster[i], bg[i], go.speckle([1, 2][i], (304, 304))) for i in range(2)])[:, None]
+    with torch.no_grad():
+        ref = go.to_png_u8(go.generator_forward(sd, torch.from_numpy(x)).numpy()[:, 0])
+    G.close()
+    d = np.abs(out.astype(int) - ref.astype(int))
+    print("full size: max u8 diff %d, mean %.3f" % (d.max(), d.mean()))
+    assert d.max() <= 16 and d.mean() <= 2.0
