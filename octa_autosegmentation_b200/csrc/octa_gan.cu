@@ -113,10 +113,12 @@ template <int BLOCK_N> struct ConvCfg {
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024;
 };
 
-template <int BLOCK_N>
+// EPI 0: bf16 rows raw[q][cout] (the conv layers).  EPI 1: fp32 planes out[c][q], c < cout (the 7x7 head: one GEMM gives the
+// response of every input pixel to every tap, k_gan_head_sum then adds 49 shifted planes -- all loads coalesced).
+template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(CONV_THREADS)
-k_gan_conv3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, bf16* __restrict__ raw,
-            int m_total, int wp, int cin_blocks, int cout) {
+k_gan_conv3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, void* __restrict__ out,
+            int m_total, int wp, int cin_blocks, int cout, int taps, int kwn) {
     using Cfg = ConvCfg<BLOCK_N>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_dyn[];
@@ -125,7 +127,7 @@ k_gan_conv3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     __shared__ uint32_t tmem_base_s;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BLOCK_N;
-    const int num_kb = 9 * cin_blocks;
+    const int num_kb = taps * cin_blocks;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -149,7 +151,7 @@ k_gan_conv3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 mbar_wait(&empty_bar[s], ph ^ 1u);
                 mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
                 const int tap = kb / cin_blocks, cb = kb - tap * cin_blocks;
-                const int kh = tap / 3, kw = tap - kh * 3;
+                const int kh = tap / kwn, kw = tap - kh * kwn;
                 uint8_t* a = tiles + (size_t)s * Cfg::STAGE_BYTES;
                 tma_load_2d(a, &tmA, &full_bar[s], cb * 64, m0 + kh * wp + kw);
                 tma_load_2d(a + Cfg::A_BYTES, &tmB, &full_bar[s], kb * 64, n0);
@@ -178,19 +180,27 @@ k_gan_conv3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tc_fence_after();
         const int quarter = warp & 3;                      // TMEM lanes this warp may read
         const int q = m0 + quarter * 32 + lane;
-        bf16* dst = raw + (size_t)q * cout + n0;
 #pragma unroll 1
         for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
             uint32_t v[32];
             tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-            if (q < m_total) {
-                uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
+            if (EPI == 0) {
+                if (q < m_total) {
+                    uint4* d4 = reinterpret_cast<uint4*>(static_cast<bf16*>(out) + (size_t)q * cout + n0 + c0);
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    d4[j] = make_uint4(pack_bf16(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
-                                       pack_bf16(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
-                                       pack_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
-                                       pack_bf16(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+                    for (int j = 0; j < 4; ++j)
+                        d4[j] = make_uint4(pack_bf16(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
+                                           pack_bf16(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
+                                           pack_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+                                           pack_bf16(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+                }
+            } else {
+                if (q < m_total) {
+                    float* o = static_cast<float*>(out) + (size_t)(n0 + c0) * m_total + q;   // a warp writes 32 consecutive q per plane
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (n0 + c0 + j < cout) o[(size_t)j * m_total] = __uint_as_float(v[j]);
+                }
             }
         }
     }
@@ -281,7 +291,7 @@ __global__ void k_gan_input(const uint8_t* __restrict__ raster, const uint8_t* _
 }
 
 // ------------------------------------------------------------------------------------------
-// 7x7 stem (1 -> 64, reflect pad 3) and head (64 -> 1, reflect pad 3 materialised, bias, sigmoid)
+// 7x7 stem (1 -> 64, reflect pad 3) and the tap sum of the head (64 -> 1 over the materialised reflect pad 3, bias, sigmoid)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_gan_stem(const float* __restrict__ x, const float* __restrict__ wt /*[49][64]*/, int n, int H, int W,
                                                   bf16* __restrict__ raw /*[n][(H+2)][(W+2)][64]*/) {
@@ -317,35 +327,22 @@ __global__ void __launch_bounds__(128) k_gan_stem(const float* __restrict__ x, c
     }
 }
 
-__global__ void __launch_bounds__(128) k_gan_head(const bf16* __restrict__ act /*[n][H+6][W+6][64]*/, const float* __restrict__ wt /*[49][64]*/, float bias,
-                                                  int n, int H, int W, float* __restrict__ y, uint8_t* __restrict__ y8) {
-    __shared__ __align__(16) float sw[49 * 64];
-    for (int i = threadIdx.x; i < 49 * 64; i += blockDim.x) sw[i] = wt[i];
-    __syncthreads();
+// out(h,w) = sigmoid(bias + sum_{a,b} planes[a*7+b][(h+a, w+b)]) over the [H+6][W+6] grid of the padded head input
+__global__ void __launch_bounds__(256) k_gan_head_sum(const float* __restrict__ planes, size_t plane_stride, float bias, int n, int H, int W,
+                                                      float* __restrict__ y, uint8_t* __restrict__ y8) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t hw = (size_t)H * W;
     if (i >= (size_t)n * hw) return;
     const int b = (int)(i / hw);
     const int p = (int)(i - (size_t)b * hw), h = p / W, w = p - h * W;
     const int Wp = W + 6;
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-#pragma unroll 1
-    for (int a = 0; a < 7; ++a) {
-        const uint4* row = reinterpret_cast<const uint4*>(act + ((size_t)(b * (H + 6) + h + a) * Wp + w) * 64);
-#pragma unroll 1
-        for (int c = 0; c < 7; ++c) {
-            const float* wv = &sw[(a * 7 + c) * 64];
+    const float* base = planes + ((size_t)(b * (H + 6) + h) * Wp + w);
+    float acc[7] = {0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                float f[8];
-                unpack8(__ldg(row + c * 8 + g), f);
-                const float4 w0 = *reinterpret_cast<const float4*>(wv + g * 8), w1 = *reinterpret_cast<const float4*>(wv + g * 8 + 4);
-                acc0 = fmaf(f[0], w0.x, acc0); acc1 = fmaf(f[1], w0.y, acc1); acc2 = fmaf(f[2], w0.z, acc2); acc3 = fmaf(f[3], w0.w, acc3);
-                acc0 = fmaf(f[4], w1.x, acc0); acc1 = fmaf(f[5], w1.y, acc1); acc2 = fmaf(f[6], w1.z, acc2); acc3 = fmaf(f[7], w1.w, acc3);
-            }
-        }
-    }
-    const float z = ((acc0 + acc1) + (acc2 + acc3)) + bias;
+    for (int a = 0; a < 7; ++a)
+#pragma unroll
+        for (int c = 0; c < 7; ++c) acc[a] += __ldg(base + (size_t)(a * 7 + c) * plane_stride + (size_t)a * Wp + c);
+    const float z = (((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + acc[6])) + bias;
     const float s = 1.0f / (1.0f + expf(-z));
     if (y) y[i] = s;
     if (y8) y8[i] = (uint8_t)(s * 255.0f);                  // utils/visualizer.py:338 (float32 multiply, truncation)
@@ -525,7 +522,8 @@ struct Conv3 {            // one 3x3 layer: weights [cout][9][cin] bf16 and its 
 
 struct GanCtx {
     int max_n = 0, H = 0, W = 0;
-    float *stem_w = nullptr, *head_w = nullptr;
+    float *stem_w = nullptr, *planes = nullptr;
+    Conv3 head;           // [64 rows: tap t < 49, zero above][64 channels] bf16 -- the head as one GEMM
     float head_b = 0.f;
     Conv3 conv[22];       // 0,1 = down; 2..19 = blocks (a, b); 20,21 = up
     // activations (bf16, padded), see octa_gan_forward_dev
@@ -575,7 +573,18 @@ int upload_7x7(GanCtx* c, float** dst, const float* w /*[64][7][7] as [ch][tap]*
     return OCTA_OK;
 }
 
-int stats_chunks(int hw) { int c = hw / 2048; return c < 1 ? 1 : (c > 64 ? 64 : c); }
+int upload_head(GanCtx* c, const float* w /*[1][64][7][7]*/) {
+    c->head.cin = 64; c->head.cout = 49;
+    std::vector<uint16_t> h(64 * 64, 0);
+    for (int t = 0; t < 49; ++t)
+        for (int ch = 0; ch < 64; ++ch) h[t * 64 + ch] = f2bf(w[ch * 49 + t]);
+    int rc = dev_alloc(c, &c->head.w, h.size());
+    if (rc) return rc;
+    OCTA_CUDA_CHECK(cudaMemcpy(c->head.w, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+    return make_map(&c->head.tmB, c->head.w, 64, 64, 64);
+}
+
+int stats_chunks(int hw) { int c = hw / 256; return c < 1 ? 1 : (c > 64 ? 64 : c); }
 
 // raw = conv3x3(act) over the flat rows of act's padded grid
 int run_conv(const GanCtx* c, const Conv3& L, const bf16* act, int n, int H, int W, cudaStream_t st) {
@@ -586,9 +595,9 @@ int run_conv(const GanCtx* c, const Conv3& L, const bf16* act, int n, int H, int
     if (rc) return rc;
     const unsigned mt = (unsigned)((rows + 127) / 128);
     if (L.cout >= 128) {
-        k_gan_conv3<128><<<dim3(mt, L.cout / 128), CONV_THREADS, ConvCfg<128>::SMEM, st>>>(tmA, L.tmB, c->raw, (int)rows, Wp, L.cin / 64, L.cout);
+        k_gan_conv3<128, 0><<<dim3(mt, L.cout / 128), CONV_THREADS, ConvCfg<128>::SMEM, st>>>(tmA, L.tmB, c->raw, (int)rows, Wp, L.cin / 64, L.cout, 9, 3);
     } else {
-        k_gan_conv3<64><<<dim3(mt, 1), CONV_THREADS, ConvCfg<64>::SMEM, st>>>(tmA, L.tmB, c->raw, (int)rows, Wp, L.cin / 64, L.cout);
+        k_gan_conv3<64, 0><<<dim3(mt, 1), CONV_THREADS, ConvCfg<64>::SMEM, st>>>(tmA, L.tmB, c->raw, (int)rows, Wp, L.cin / 64, L.cout, 9, 3);
     }
     octa::count_launch();
     OCTA_CUDA_CHECK(cudaGetLastError());
@@ -629,7 +638,7 @@ extern "C" int octa_gan_create(const OctaGanWeights* w, int max_images, int H, i
     OCTA_ARG_CHECK(w && handle, "null argument");
     OCTA_ARG_CHECK(max_images > 0 && max_images <= 4096, "max_images out of range");
     OCTA_ARG_CHECK(H >= 16 && W >= 16 && H % 4 == 0 && W % 4 == 0 && H <= 4096 && W <= 4096, "H and W must be multiples of 4 in [16, 4096]");
-    OCTA_ARG_CHECK((long long)max_images * (H + 2) * (W + 2) < (1ll << 31) - 4096, "max_images * (H+2) * (W+2) must stay below 2^31");
+    OCTA_ARG_CHECK((long long)max_images * (H + 6) * (W + 6) < (1ll << 31) - 4096, "max_images * (H+6) * (W+6) must stay below 2^31");
     OCTA_ARG_CHECK(w->stem_w && w->head_w, "null weight pointer");
     for (int i = 0; i < 22; ++i) OCTA_ARG_CHECK(w->conv_w[i], "null weight pointer");
     int ndev = 0;
@@ -640,7 +649,7 @@ extern "C" int octa_gan_create(const OctaGanWeights* w, int max_images, int H, i
     int rc = OCTA_OK;
     auto fail = [&](int code) { delete c; return code; };
     if ((rc = upload_7x7(c, &c->stem_w, w->stem_w))) return fail(rc);
-    if ((rc = upload_7x7(c, &c->head_w, w->head_w))) return fail(rc);
+    if ((rc = upload_head(c, w->head_w))) return fail(rc);
     static const int cio[22][2] = {{64, 128}, {128, 256}, {256, 256}, {256, 256}, {256, 256}, {256, 256}, {256, 256}, {256, 256}, {256, 256}, {256, 256},
                                    {256, 256}, {256, 256}, {256, 256}, {256, 256}, {256, 256}, {256, 256}, {256, 256}, {256, 256}, {256, 256}, {256, 256},
                                    {256, 128}, {128, 64}};
@@ -653,11 +662,12 @@ extern "C" int octa_gan_create(const OctaGanWeights* w, int max_images, int H, i
         (rc = dev_alloc(c, &c->a2, n * p2 * 128)) || (rc = dev_alloc(c, &c->b2, n * p2 * 256)) || (rc = dev_alloc(c, &c->r0, n * p3 * 256)) ||
         (rc = dev_alloc(c, &c->r1, n * p3 * 256)) || (rc = dev_alloc(c, &c->rt, n * p3 * 256)) || (rc = dev_alloc(c, &c->u1, n * p2 * 256)) ||
         (rc = dev_alloc(c, &c->b3, n * p2 * 128)) || (rc = dev_alloc(c, &c->u2, n * p1 * 128)) ||
-        (rc = dev_alloc(c, &c->fin, n * (size_t)(H + 6) * (W + 6) * 64)) || (rc = dev_alloc(c, &c->partial, n * 64 * 256 * 2)) ||
+        (rc = dev_alloc(c, &c->fin, n * (size_t)(H + 6) * (W + 6) * 64)) || (rc = dev_alloc(c, &c->planes, n * (size_t)(H + 6) * (W + 6) * 49)) || (rc = dev_alloc(c, &c->partial, n * 64 * 256 * 2)) ||
         (rc = dev_alloc(c, &c->mr, n * 256)))
         return fail(rc);
-    if (cudaFuncSetAttribute(k_gan_conv3<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvCfg<128>::SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(k_gan_conv3<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvCfg<64>::SMEM) != cudaSuccess) {
+    if (cudaFuncSetAttribute(k_gan_conv3<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvCfg<128>::SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(k_gan_conv3<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvCfg<64>::SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(k_gan_conv3<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvCfg<64>::SMEM) != cudaSuccess) {
         octa::set_error("cudaFuncSetAttribute(k_gan_conv3): %s", cudaGetErrorString(cudaGetLastError()));
         return fail(OCTA_E_CUDA);
     }
@@ -711,9 +721,17 @@ extern "C" int octa_gan_forward_dev(void* handle, const float* x_dev, int n_imag
     GAN_TRY(run_stats(c, n, H, W, 64, st));
     GAN_TRY(run_norm(c, nullptr, n, H, W, 64, 3, 1, 1, c->fin, st));
     // head: ReflectionPad2d(3) + Conv2d(64, 1, 7) + Sigmoid                                    networks.py:415-417
-    k_gan_head<<<px_blocks, 128, 0, st>>>(c->fin, c->head_w, c->head_b, n, H, W, y_dev, y_u8_dev);
-    octa::count_launch();
-    OCTA_CUDA_CHECK(cudaGetLastError());
+    // one GEMM [pixels of the padded grid x 64 ch] x [64 ch x 49 taps] on the tensor cores, then the shifted sum of the 49 planes
+    {
+        const long long rows = (long long)n * (H + 6) * (W + 6);
+        CUtensorMap tmA;
+        GAN_TRY(make_map(&tmA, c->fin, 64, (uint64_t)rows, 128));
+        k_gan_conv3<64, 1><<<dim3((unsigned)((rows + 127) / 128), 1), CONV_THREADS, ConvCfg<64>::SMEM, st>>>(tmA, c->head.tmB, c->planes, (int)rows, W + 6, 1, 49, 1, 1);
+        const size_t total = (size_t)n * H * W;
+        k_gan_head_sum<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(c->planes, (size_t)rows, c->head_b, n, H, W, y_dev, y_u8_dev);
+        octa::count_launch(2);
+        OCTA_CUDA_CHECK(cudaGetLastError());
+    }
     return OCTA_OK;
 }
 
@@ -767,8 +785,8 @@ extern "C" int octa_test_gan_conv3_host(const float* x, const float* w, int n, i
     bf16* d_act = nullptr;
     if ((rc = dev_alloc(&c, &d_act, act.size())) || (rc = dev_alloc(&c, &c.raw, rows * cout + 128 * 256))) return rc;
     OCTA_CUDA_CHECK(cudaMemcpy(d_act, act.data(), act.size() * 2, cudaMemcpyHostToDevice));
-    OCTA_CUDA_CHECK(cudaFuncSetAttribute(k_gan_conv3<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvCfg<128>::SMEM));
-    OCTA_CUDA_CHECK(cudaFuncSetAttribute(k_gan_conv3<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvCfg<64>::SMEM));
+    OCTA_CUDA_CHECK(cudaFuncSetAttribute(k_gan_conv3<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvCfg<128>::SMEM));
+    OCTA_CUDA_CHECK(cudaFuncSetAttribute(k_gan_conv3<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvCfg<64>::SMEM));
     if ((rc = run_conv(&c, L, d_act, n, H, W, 0))) return rc;
     OCTA_CUDA_CHECK(cudaDeviceSynchronize());
     std::vector<uint16_t> raw(rows * cout);

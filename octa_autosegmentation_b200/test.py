@@ -67,7 +67,7 @@ def run(config: dict, num_samples: int = 9999999, batch_size: int = 32, device=N
             edges = []
             for p in paths:
                 with open(p, "rb") as f:
-                    edges.append(graph_io.parse_csv(f.read()))
+                    edges.append(graph_io.parse_csv_bytes(f.read()))
             offs = np.zeros(len(edges) + 1, dtype=np.int64)
             offs[1:] = np.cumsum([e.shape[0] for e in edges])
             e7 = torch.from_numpy(np.concatenate(edges, axis=0) if offs[-1] else np.zeros((1, 7))).to(device)

@@ -116,3 +116,52 @@ def test_contrast_adapt_full_size_runs():
     d = np.abs(out.astype(int) - ref.astype(int))
     print("full size: max u8 diff %d, mean %.3f" % (d.max(), d.mean()))
     assert d.max() <= 16 and d.mean() <= 2.0
+
+
+def test_cli_writes_reference_named_pngs(tmp_path):
+    """python -m octa_autosegmentation_b200.test: the GAN config of the reference (keys of docker/trained_models/GAN/config.yml)
+    with a synthetic checkpoint -> `<save_dir>/G_<csv name>.png`, equal to the oracle run on the same inputs within the bar."""
+    import gzip
+    import os
+    import random
+    import shutil
+    import torch
+    import yaml
+    from PIL import Image
+    from octa_autosegmentation_b200 import graph_io, test as gan_cli, tree2img
+    from oracle import gan_oracle as go
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    gdir, bdir, out = tmp_path / "vessel_graphs", tmp_path / "bg", tmp_path / "images"
+    gdir.mkdir(); bdir.mkdir()
+    for s in (0, 1):
+        shutil.copy(os.path.join(here, "golden", "graph_small_s%d.csv" % s), gdir / ("g%d.csv" % s))
+    with gzip.open(os.path.join(here, "golden", "graph_docker_s0.csv.gz"), "rb") as f:
+        (gdir / "g10.csv").write_bytes(f.read())
+    rs = np.random.RandomState(0)
+    for i in range(3):
+        Image.fromarray(rs.randint(0, 255, (304, 304)).astype(np.uint8)).save(bdir / ("bg%d.png" % i))
+    sd = go.random_state_dict(4)
+    torch.save({"epoch": 150, "model": sd}, tmp_path / "150_G_model.pth")
+    cfg = {"General": {"inference": "G", "seed": 675570, "task": "gan-ves-seg", "device": "cpu"},
+           "Output": {"save_dir": str(tmp_path / "o")},
+           "Test": {"batch_size": 1, "model_path": str(tmp_path / "150_G_model.pth"), "save_dir": str(out),
+                    "data": {"real_A": {"files": str(gdir / "**/*.csv")}, "background": {"files": str(bdir / "**/*.png")}},
+                    "data_augmentation": [{"name": "LoadGraphAndFilterByRandomRadiusd", "keys": ["real_A"], "image_resolutions": [[304, 304]]}]}}
+    with open(tmp_path / "config.yml", "w") as f:
+        yaml.safe_dump(cfg, f)
+    gan_cli.main(["--config_file", str(tmp_path / "config.yml"), "--batch_size", "2", "--Test.save_dir", str(out)])
+    names = ["g0", "g1", "g10"]                                # natural order, like natsorted in data/image_dataset.py:52
+    assert sorted(os.listdir(out)) == sorted("G_%s.png" % n for n in names)
+    bgs = sorted(os.listdir(bdir))
+    for i, n in enumerate(names):
+        got = np.asarray(Image.open(out / ("G_%s.png" % n)))
+        assert got.shape == (304, 304) and got.dtype == np.uint8
+        e7 = graph_io.parse_csv_bytes((gdir / (n + ".csv")).read_bytes())
+        raster = tree2img.raster_edges(e7, [304, 304], 2)
+        bg = np.asarray(Image.open(bdir / bgs[random.Random(675570 + i).randint(0, 2)]))
+        x = go.prepare_input(raster.astype(np.uint8), bg, go.speckle(675570 + i, (304, 304)))
+        with torch.no_grad():
+            ref = go.to_png_u8(go.generator_forward(sd, torch.from_numpy(x)[None, None]).numpy()[0, 0])
+        d = np.abs(got.astype(int) - ref.astype(int))
+        assert d.max() <= 16 and d.mean() <= 2.0
