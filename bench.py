@@ -162,6 +162,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--d2h-volume", action="store_true")
+    ap.add_argument("--no-gan", action="store_true", help="skip the config #5 (GAN contrast adaptation) leg")
     ap.add_argument("--in-flight", type=int, default=2, help="growth loops (batches) in flight per GPU in the pipelined API")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -268,6 +269,53 @@ def main():
     run_steps(args.in_flight + 1, True)
     ms_e2e, last = timed(lambda k: run_steps(k, True), max(2, args.steps))
     clocks = sampler.stop() if rank == 0 else None
+    gan_line = None
+    if rank == 0 and not args.no_gan:
+        # BASELINE config #5 tail: the 304^2 images of the last batch -> background noise -> resnetGenerator9
+        # (random-init weights, synthetic backgrounds) -> uint8 images; tensor-core rate of its 3x3 convolutions
+        from octa_autosegmentation_b200 import gan
+        sd = gan.random_init_state_dict(0)
+        G = gan.ResnetGenerator9(sd, image_size=(304, 304), max_images=32, device=dev)
+        img = step(False)["image"]
+        nimg = int(img.shape[0])
+        bg = torch.randint(0, 255, tuple(img.shape), device=dev, dtype=torch.uint8)
+        sp_seeds = list(range(nimg))
+        gan.contrast_adapt(G, img, bg, sp_seeds)
+        torch.cuda.synchronize()
+        ge = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        l0 = _lib.launch_count()
+        ge[0].record()
+        for _ in range(3):
+            g_out = gan.contrast_adapt(G, img, bg, sp_seeds)
+        ge[1].record()
+        torch.cuda.synchronize()
+        gan_ms = ge[0].elapsed_time(ge[1]) / 3
+        tfl = nimg * gan.conv_flops_per_image(304, 304) / (gan_ms * 1e-3) / 1e12
+        tpeak = None
+        try:
+            tpeak = float(json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")))["bf16_tflops"])
+        except Exception:
+            pass
+        gan_line = {"workload": "BASELINE config #5 tail: %d rasters 304^2 (this step's images) -> ScaleIntensity + background speckle -> "
+                                "resnetGenerator9 (random-init, bf16 tcgen05 convolutions) -> uint8 images, device resident" % nimg,
+                    "images_per_sec": nimg / (gan_ms * 1e-3), "ms_per_batch": gan_ms, "gpu_launches": int((_lib.launch_count() - l0) // 3),
+                    "roofline": {"bound": "tensor", "achieved": tfl, "peak": tpeak, "unit": "TFLOP/s", "frac": (tfl / tpeak) if tpeak else None,
+                                 "traffic": None, "kernel": "whole forward; algorithmic flops = the 22 3x3 convolutions (177.2 GF/image); "
+                                                            "k_gan_conv3 alone: see profiles/"},
+                    "mean_gray": float(g_out.float().mean().item())}
+        if not args.no_cpu_baseline and world == 1:
+            import time as _t
+            from oracle import gan_oracle as go
+            xs = torch.rand(2, 1, 304, 304)
+            with torch.no_grad():
+                go.generator_forward(sd, xs[:1])
+                t0 = _t.time()
+                go.generator_forward(sd, xs)
+                dt = _t.time() - t0
+            gan_line["cpu_baseline"] = {"value": 2 / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                                        "sample": "2 images through the fp32 PyTorch restatement of the generator (the reference runs it on CPU, "
+                                                  "docker/trained_models/GAN/config.yml General.device: cpu)"}
+        G.close()
 
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -309,6 +357,8 @@ def main():
                                 "ms_per_step": ms, "device_ms_per_batch_loop": grow_ms},
             "clocks": clocks,
         }
+        if gan_line is not None:
+            line["config5_gan"] = gan_line
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 2
             workers = max(1, cores - 1)

@@ -247,7 +247,7 @@ struct EdgeSm {
 //   3. inside those guard bands (probability ~1e-7) the reference's exact operation chain decides.
 // (Without the compaction the float64 tier ran at the survivors' lane density: almost every x step of a warp had
 // at least one surviving lane and paid the full float64 cost for it.)
-__device__ __forceinline__ void setup_edge(const VoxEdge& e, const int t0[3], const int t1[3], EdgeSm* o) {
+__device__ __forceinline__ int setup_edge(const VoxEdge& e, const int t0[3], const int t1[3], EdgeSm* o) {
     int rows = 1;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -276,6 +276,7 @@ __device__ __forceinline__ void setup_edge(const VoxEdge& e, const int t0[3], co
     o->finv = fss > 0.f ? 1.0f / fss : 0.f;
     const float reach = (float)e.R + 0.8660254f + 0.02f + 8e-6f * ext;
     o->thr = reach * reach;
+    return o->rowbase;
 }
 
 // tier 1: bit ix of the result is set when voxel (b0x + ix, row) may receive a positive contribution
@@ -285,9 +286,10 @@ __device__ __forceinline__ uint32_t cull_row(const EdgeSm& E, int iy, int iz) {
     const float dot12 = w1 * f1 + w2 * f2;
     const int nx = E.n[0];
     uint32_t mask = 0;
+    float fx = 0.f;                                   // (float)ix without a conversion per step (small integers are exact)
 #pragma unroll 4
-    for (int ix = 0; ix < nx; ++ix) {
-        const float w0 = (float)ix - a0;
+    for (int ix = 0; ix < nx; ++ix, fx += 1.0f) {
+        const float w0 = fx - a0;
         float tf = fmaf(w0, f0, dot12) * finv;
         tf = fminf(fmaxf(tf, 0.f), 1.f);
         const float d0 = fmaf(-tf, f0, w0), d1 = fmaf(-tf, f1, w1), d2 = fmaf(-tf, f2, w2);
@@ -397,7 +399,6 @@ vox_tile_kernel(const VoxEdge* __restrict__ prep, const int64_t* __restrict__ ed
     __shared__ EdgeSm es[EPASS];
     __shared__ unsigned short s_queue[(VOX_THREADS / 32) * QCAP];
     __shared__ int s_total, s_rowbase[EPASS];
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned short* queue = s_queue + warp * QCAP;
     const int* lst = tile_edges + (size_t)KBIG * e_base;
@@ -406,20 +407,19 @@ vox_tile_kernel(const VoxEdge* __restrict__ prep, const int64_t* __restrict__ ed
     const int ystride = T[2], xstride = T[1] * T[2];
     for (int pass = 0; pass < nall; pass += EPASS) {
         const int cnt = imin(EPASS, nall - pass);
-        if (threadIdx.x < cnt) {
-            const int k = pass + threadIdx.x;
-            const VoxEdge e = ge[k < nlist ? lst[beg + k] : bl[k - nlist]];
-            setup_edge(e, t0, t1, &es[threadIdx.x]);
-        }
-        __syncthreads();
-        if (threadIdx.x < 32) {           // exclusive prefix of the row counts of this pass
-            const int v = threadIdx.x < cnt ? es[threadIdx.x].rowbase : 0;
+        if (warp == 0) {                   // EPASS == 32: warp 0 sets the pass up and scans the row counts, ONE barrier per pass
+            int v = 0;                     // (the first pass shares it with the zeroing of the accumulators above)
+            if (lane < cnt) {
+                const int k = pass + lane;
+                const VoxEdge e = ge[k < nlist ? lst[beg + k] : bl[k - nlist]];
+                v = setup_edge(e, t0, t1, &es[lane]);
+            }
             int x = v;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if ((int)threadIdx.x >= o) x += y; }
-            if (threadIdx.x < cnt) es[threadIdx.x].rowbase = x - v;
-            s_rowbase[threadIdx.x] = x - v;
-            if (threadIdx.x == 31) s_total = x;
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            if (lane < cnt) es[lane].rowbase = x - v;
+            s_rowbase[lane] = x - v;
+            if (lane == 31) s_total = x;
         }
         __syncthreads();
         const int total = s_total;
@@ -430,10 +430,10 @@ vox_tile_kernel(const VoxEdge* __restrict__ prep, const int64_t* __restrict__ ed
             if (item < total) {
                 while (lo + 1 < cnt && s_rowbase[lo + 1] <= item) ++lo;
                 const EdgeSm& E = es[lo];
-                const int row = item - E.rowbase, enz = E.n[2];
-                int iy = (int)((float)row * (1.0f / (float)enz));
-                int iz = row - iy * enz;
-                if (iz < 0) { --iy; iz += enz; } else if (iz >= enz) { ++iy; iz -= enz; }
+                const int row = item - E.rowbase, eny = E.n[1];      // rows numbered y-fastest: neighbouring lanes update
+                int iz = (int)((float)row * (1.0f / (float)eny));    // different 32-bit words of the u16 accumulators
+                int iy = row - iz * eny;
+                if (iy < 0) { --iz; iy += eny; } else if (iy >= eny) { ++iz; iy -= eny; }
                 mask = cull_row(E, iy, iz);
                 rowinfo = ((uint32_t)lo << 16) | ((uint32_t)iy << 8) | (uint32_t)iz;
             }
@@ -464,6 +464,7 @@ vox_tile_kernel(const VoxEdge* __restrict__ prep, const int64_t* __restrict__ ed
             }
             __syncwarp();
         }
+        if (pass + EPASS >= nall) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // (see the bulk stores below)
         __syncthreads();
     }
 
@@ -471,9 +472,8 @@ vox_tile_kernel(const VoxEdge* __restrict__ prep, const int64_t* __restrict__ ed
     const size_t base0 = ((size_t)t0[0] * g.D[1] + t0[1]) * g.D[2];
     const size_t xpitch = (size_t)g.D[1] * g.D[2];
     if (plane_contig && (((base0 | xpitch | (size_t)plane_len | (size_t)xstride) & 7) == 0)) {
-        // TMA bulk copies shared -> global, one per x plane (16-byte aligned runs), issued by one thread
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
+        // TMA bulk copies shared -> global, one per x plane (16-byte aligned runs), issued by one thread; every thread fenced
+        // its accumulator writes for the async proxy before the closing barrier of the last pass
         if (threadIdx.x == 0) {
             const uint32_t bytes = (uint32_t)plane_len * 2u;
             for (int x = 0; x < t1[0] - t0[0]; ++x) {

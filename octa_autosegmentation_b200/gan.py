@@ -53,6 +53,28 @@ def conv_keys() -> list:
     return keys + list(UP)
 
 
+def random_init_state_dict(seed: int = 0) -> dict:
+    """Random-init weights with the reference's state-dict keys and shapes (benchmarks / smoke tests without a checkpoint)."""
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    shapes = {STEM: (64, 1, 7, 7), DOWN[0]: (128, 64, 3, 3), DOWN[1]: (256, 128, 3, 3), UP[0]: (128, 256, 3, 3),
+              UP[1]: (64, 128, 3, 3), HEAD: (1, 64, 7, 7)}
+    for b in BLOCKS:
+        shapes[b + ".conv_block.1"] = shapes[b + ".conv_block.5"] = (256, 256, 3, 3)
+    sd = {}
+    for k, s in shapes.items():
+        sd[k + ".weight"] = torch.randn(*s, generator=g) * (2.0 / (s[1] * s[2] * s[3])) ** 0.5
+        sd[k + ".bias"] = torch.zeros(s[0])
+    return sd
+
+
+def conv_flops_per_image(H: int, W: int) -> int:
+    """Algorithmic flops of the 22 3x3 convolutions of one image: 2 * 9 * sum(pixels * Cin * Cout)."""
+    return 2 * 9 * (H * W * 64 * 128 + (H // 2) * (W // 2) * 128 * 256 + 18 * (H // 4) * (W // 4) * 256 * 256
+                    + (H // 2) * (W // 2) * 256 * 128 + H * W * 128 * 64)
+
+
 class ResnetGenerator9:
     """`resnetGenerator9()` of models/networks.py:502-503 for inference: x float32 [N,1,H,W] in [0,1] -> [N,1,H,W]."""
 
