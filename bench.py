@@ -270,7 +270,7 @@ def main():
     ms_e2e, last = timed(lambda k: run_steps(k, True), max(2, args.steps))
     clocks = sampler.stop() if rank == 0 else None
     gan_line = None
-    if rank == 0 and not args.no_gan:
+    if rank == 0 and world == 1 and not args.no_gan:      # (N = 1 only, like cpu_baseline: the other ranks would idle behind it)
         # BASELINE config #5 tail: the 304^2 images of the last batch -> background noise -> resnetGenerator9
         # (random-init weights, synthetic backgrounds) -> uint8 images; tensor-core rate of its 3x3 convolutions
         from octa_autosegmentation_b200 import gan

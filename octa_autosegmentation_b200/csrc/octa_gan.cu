@@ -15,10 +15,10 @@
 // is a plain 2-D TMA box [128 pixels x 64 channels] at a shifted row coordinate; no im2col buffer exists.
 //
 // k_gan_conv3 is the tensor-core kernel: TMA (128B swizzle) -> shared-memory ring -> tcgen05.mma (cta_group::1,
-// kind::f16, bf16 x bf16 -> fp32, M=128, N=64/128, K=16) with the accumulator in TMEM -> tcgen05.ld epilogue -> bf16 rows.
+// kind::f16, bf16 x bf16 -> fp32, M=128, N=Cout=64/128/256, K=16) with the accumulator in TMEM -> tcgen05.ld epilogue -> bf16 rows.
 // Warp roles: warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane), warps 2..5 = epilogue
-// (one TMEM lane quarter each).  Two CTAs fit per SM (3 x 32 KB stages, 128 TMEM columns each), so one CTA's epilogue
-// overlaps the other's main loop.  Conv biases that are followed by InstanceNorm(affine=False) cancel exactly in the
+// (one TMEM lane quarter each).  The kernel is persistent (one CTA per SM walks the M tiles) with TWO accumulators in TMEM, so
+// the epilogue of tile i runs under the main loop of tile i+1, and the TMA ring (192 KB) runs ahead across tiles.  Conv biases that are followed by InstanceNorm(affine=False) cancel exactly in the
 // mean subtraction and are not applied.
 // The remaining layers are bandwidth-bound element kernels: instance-norm statistics, norm+ReLU(+skip) into the next
 // padded buffer (zero or reflect border), blur-pool down / bilinear up, the 7x7 stem (1 -> 64) and head (64 -> 1, sigmoid).
@@ -27,6 +27,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 #include <vector>
@@ -107,35 +108,45 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // 3x3 convolution as nine shifted GEMMs on tcgen05
 // ------------------------------------------------------------------------------------------
 constexpr int CONV_THREADS = 192;
-template <int BLOCK_N> struct ConvCfg {
-    static constexpr int STAGES = BLOCK_N == 128 ? 3 : 4;
+template <int BLOCK_N, int CTAS> struct ConvCfg {                          // CTAS = resident CTAs per SM (1 or 2)
     static constexpr uint32_t A_BYTES = 128 * 128, B_BYTES = BLOCK_N * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (192 * 1024 / CTAS) / (int)STAGE_BYTES;  // 1 CTA/SM: N = 64: 8 x 24 KB, 128: 6 x 32 KB, 256: 4 x 48 KB
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024;
+    static constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;                     // two accumulators: 128 / 256 / 512 columns
+    static_assert(TMEM_COLS * CTAS <= 512 && STAGES >= 2, "TMEM / shared memory budget");
 };
 
-// EPI 0: bf16 rows raw[q][cout] (the conv layers).  EPI 1: fp32 planes out[c][q], c < cout (the 7x7 head: one GEMM gives the
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent, warp-specialised: one CTA per SM walks the M tiles (128 flat pixels x all BLOCK_N = Cout channels).
+//   warp 0 (one lane)  TMA producer: ring of STAGES x (A 128x64 + B BLOCK_Nx64) bf16 tiles, 128B swizzle, runs ahead across tiles
+//   warp 1 (one lane)  MMA issuer: 4 x tcgen05.mma (K = 16) per stage into accumulator (tile & 1) of TMEM; tcgen05.commit frees
+//                      the stage, and after the last k-block hands the accumulator to the epilogue
+//   warps 2..5         epilogue of the PREVIOUS tile while the next one accumulates: tcgen05.ld (one TMEM lane quarter each)
+// EPI 0: bf16 rows out[q][cout] (the conv layers).  EPI 1: fp32 planes out[c][q], c < cout (the 7x7 head: one GEMM gives the
 // response of every input pixel to every tap, k_gan_head_sum then adds 49 shifted planes -- all loads coalesced).
-template <int BLOCK_N, int EPI>
-__global__ void __launch_bounds__(CONV_THREADS)
+template <int BLOCK_N, int EPI, int CTAS>
+__global__ void __launch_bounds__(CONV_THREADS, CTAS)
 k_gan_conv3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, void* __restrict__ out,
-            int m_total, int wp, int cin_blocks, int cout, int taps, int kwn) {
-    using Cfg = ConvCfg<BLOCK_N>;
+            int m_total, int wp, int cin_blocks, int cout, int taps, int kwn, int num_tiles) {
+    using Cfg = ConvCfg<BLOCK_N, CTAS>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_dyn[];
     uint8_t* tiles = reinterpret_cast<uint8_t*>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
-    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_s;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BLOCK_N;
     const int num_kb = taps * cin_blocks;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(&accum_bar, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)BLOCK_N) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(Cfg::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -145,70 +156,88 @@ k_gan_conv3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
     if (warp == 0) {
         if (lane == 0) {                                   // ---- TMA producer
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-                mbar_wait(&empty_bar[s], ph ^ 1u);
-                mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-                const int tap = kb / cin_blocks, cb = kb - tap * cin_blocks;
-                const int kh = tap / kwn, kw = tap - kh * kwn;
-                uint8_t* a = tiles + (size_t)s * Cfg::STAGE_BYTES;
-                tma_load_2d(a, &tmA, &full_bar[s], cb * 64, m0 + kh * wp + kw);
-                tma_load_2d(a + Cfg::A_BYTES, &tmB, &full_bar[s], kb * 64, n0);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = tile * 128;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+                    const int tap = kb / cin_blocks, cb = kb - tap * cin_blocks;
+                    const int kh = tap / kwn, kw = tap - kh * kwn;
+                    uint8_t* a = tiles + (size_t)s * Cfg::STAGE_BYTES;
+                    tma_load_2d(a, &tmA, &full_bar[s], cb * 64, m0 + kh * wp + kw);
+                    tma_load_2d(a + Cfg::A_BYTES, &tmB, &full_bar[s], kb * 64, 0);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {                                   // ---- MMA issuer
             // instruction descriptor: D fp32, A/B bf16, both K-major, N = BLOCK_N, M = 128
             constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-                mbar_wait(&full_bar[s], ph);
+            uint32_t it = 0, t = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+                const uint32_t as = t & 1u, aph = (t >> 1) & 1u;
+                mbar_wait(&acc_empty[as], aph ^ 1u);       // the epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t a = smem_u32(tiles + (size_t)s * Cfg::STAGE_BYTES);
-                const uint64_t adesc = umma_desc_sw128(a), bdesc = umma_desc_sw128(a + Cfg::A_BYTES);
+                const uint32_t d_tmem = tmem_base + as * (uint32_t)BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t a = smem_u32(tiles + (size_t)s * Cfg::STAGE_BYTES);
+                    const uint64_t adesc = umma_desc_sw128(a), bdesc = umma_desc_sw128(a + Cfg::A_BYTES);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)                // 4 x K=16 inside the 128-byte swizzle row: +32 B per step
-                    tc_mma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
-                tc_commit(&empty_bar[s]);                  // frees the stage once these MMAs have read it
+                    for (int k = 0; k < 4; ++k)            // 4 x K=16 inside the 128-byte swizzle row: +32 B per step
+                        tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                    tc_commit(&empty_bar[s]);              // frees the stage once these MMAs have read it
+                }
+                tc_commit(&acc_full[as]);                  // accumulator complete
             }
-            tc_commit(&accum_bar);                         // accumulator complete
         }
-    } else {                                               // ---- epilogue: TMEM -> registers -> bf16 rows
-        mbar_wait(&accum_bar, 0);
-        tc_fence_after();
+    } else {                                               // ---- epilogue: TMEM -> registers -> global
         const int quarter = warp & 3;                      // TMEM lanes this warp may read
-        const int q = m0 + quarter * 32 + lane;
+        uint32_t t = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+            const uint32_t as = t & 1u, aph = (t >> 1) & 1u;
+            mbar_wait(&acc_full[as], aph);
+            tc_fence_after();
+            const int q = tile * 128 + quarter * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * (uint32_t)BLOCK_N;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-            uint32_t v[32];
-            tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-            if (EPI == 0) {
-                if (q < m_total) {
-                    uint4* d4 = reinterpret_cast<uint4*>(static_cast<bf16*>(out) + (size_t)q * cout + n0 + c0);
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                if (EPI == 1 && c0 >= cout) break;
+                uint32_t v[32];
+                tc_ld32(taddr + (uint32_t)c0, v);
+                if (EPI == 0) {
+                    if (q < m_total) {
+                        uint4* d4 = reinterpret_cast<uint4*>(static_cast<bf16*>(out) + (size_t)q * cout + c0);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        d4[j] = make_uint4(pack_bf16(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
-                                           pack_bf16(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
-                                           pack_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
-                                           pack_bf16(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
-                }
-            } else {
-                if (q < m_total) {
-                    float* o = static_cast<float*>(out) + (size_t)(n0 + c0) * m_total + q;   // a warp writes 32 consecutive q per plane
+                        for (int j = 0; j < 4; ++j)
+                            d4[j] = make_uint4(pack_bf16(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
+                                               pack_bf16(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
+                                               pack_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+                                               pack_bf16(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+                    }
+                } else {
+                    if (q < m_total) {
+                        float* o = static_cast<float*>(out) + (size_t)c0 * m_total + q;   // a warp writes 32 consecutive q per plane
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (n0 + c0 + j < cout) o[(size_t)j * m_total] = __uint_as_float(v[j]);
+                        for (int j = 0; j < 32; ++j)
+                            if (c0 + j < cout) o[(size_t)j * m_total] = __uint_as_float(v[j]);
+                    }
                 }
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);    // 4 arrivals (one per epilogue warp) release the accumulator
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         __syncwarp();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BLOCK_N) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
     }
 }
 
@@ -521,7 +550,7 @@ struct Conv3 {            // one 3x3 layer: weights [cout][9][cin] bf16 and its 
 };
 
 struct GanCtx {
-    int max_n = 0, H = 0, W = 0;
+    int max_n = 0, H = 0, W = 0, n_sm = 148, two_ctas = -1;
     float *stem_w = nullptr, *planes = nullptr;
     Conv3 head;           // [64 rows: tap t < 49, zero above][64 channels] bf16 -- the head as one GEMM
     float head_b = 0.f;
@@ -560,7 +589,7 @@ int upload_conv(GanCtx* c, Conv3* L, const float* w /*[cout][cin][3][3]*/, int c
     int rc = dev_alloc(c, &L->w, h.size());
     if (rc) return rc;
     OCTA_CUDA_CHECK(cudaMemcpy(L->w, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
-    return make_map(&L->tmB, L->w, (uint64_t)9 * cin, (uint64_t)cout, cout >= 128 ? 128 : 64);
+    return make_map(&L->tmB, L->w, (uint64_t)9 * cin, (uint64_t)cout, (uint32_t)cout);
 }
 
 int upload_7x7(GanCtx* c, float** dst, const float* w /*[64][7][7] as [ch][tap]*/) {
@@ -593,12 +622,22 @@ int run_conv(const GanCtx* c, const Conv3& L, const bf16* act, int n, int H, int
     CUtensorMap tmA;
     int rc = make_map(&tmA, act, (uint64_t)L.cin, (uint64_t)rows, 128);
     if (rc) return rc;
-    const unsigned mt = (unsigned)((rows + 127) / 128);
-    if (L.cout >= 128) {
-        k_gan_conv3<128, 0><<<dim3(mt, L.cout / 128), CONV_THREADS, ConvCfg<128>::SMEM, st>>>(tmA, L.tmB, c->raw, (int)rows, Wp, L.cin / 64, L.cout, 9, 3);
-    } else {
-        k_gan_conv3<64, 0><<<dim3(mt, 1), CONV_THREADS, ConvCfg<64>::SMEM, st>>>(tmA, L.tmB, c->raw, (int)rows, Wp, L.cin / 64, L.cout, 9, 3);
-    }
+    const int mt = (int)((rows + 127) / 128);
+    auto grid = [&](int ctas) { const int g = c->n_sm * ctas; return (unsigned)(mt < g ? mt : g); };
+    // bit 0: the Cout = 128 layers, bit 1: the Cout = 64 layer run 2 CTAs per SM (half the ring each).  Their A tiles feed fewer
+    // MMA columns, so they are bound by L2 -> shared-memory traffic and two producers keep more of it in flight (measured per
+    // layer on B200, 1 vs 2 CTAs: 551 -> 504 us, 560 -> 385 us, 1008 -> 577 us); the Cout = 256 layers prefer one CTA with N = 256
+    const int two = c->two_ctas >= 0 ? c->two_ctas : 3;
+    if (L.cout == 256)
+        k_gan_conv3<256, 0, 1><<<grid(1), CONV_THREADS, ConvCfg<256, 1>::SMEM, st>>>(tmA, L.tmB, c->raw, (int)rows, Wp, L.cin / 64, L.cout, 9, 3, mt);
+    else if (L.cout == 128 && !(two & 1))
+        k_gan_conv3<128, 0, 1><<<grid(1), CONV_THREADS, ConvCfg<128, 1>::SMEM, st>>>(tmA, L.tmB, c->raw, (int)rows, Wp, L.cin / 64, L.cout, 9, 3, mt);
+    else if (L.cout == 128)
+        k_gan_conv3<128, 0, 2><<<grid(2), CONV_THREADS, ConvCfg<128, 2>::SMEM, st>>>(tmA, L.tmB, c->raw, (int)rows, Wp, L.cin / 64, L.cout, 9, 3, mt);
+    else if (!(two & 2))
+        k_gan_conv3<64, 0, 1><<<grid(1), CONV_THREADS, ConvCfg<64, 1>::SMEM, st>>>(tmA, L.tmB, c->raw, (int)rows, Wp, L.cin / 64, L.cout, 9, 3, mt);
+    else
+        k_gan_conv3<64, 0, 2><<<grid(2), CONV_THREADS, ConvCfg<64, 2>::SMEM, st>>>(tmA, L.tmB, c->raw, (int)rows, Wp, L.cin / 64, L.cout, 9, 3, mt);
     octa::count_launch();
     OCTA_CUDA_CHECK(cudaGetLastError());
     return OCTA_OK;
@@ -627,6 +666,22 @@ int run_resample(const bf16* src, int n, int Hs, int Ws, int C, int mode, int re
     k_gan_resample<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, n, Hs, Ws, C, mode, reflect, dst);
     octa::count_launch();
     OCTA_CUDA_CHECK(cudaGetLastError());
+    return OCTA_OK;
+}
+
+int conv_attrs(GanCtx* c) {
+    int dev = 0, sm = 0;
+    OCTA_CUDA_CHECK(cudaGetDevice(&dev));
+    OCTA_CUDA_CHECK(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev));
+    c->n_sm = sm > 0 ? sm : 148;
+    const char* e = getenv("OCTA_GAN_TWO_CTAS");             // diagnostics: which layers run 2 CTAs per SM (see run_conv)
+    if (e) c->two_ctas = atoi(e);
+    OCTA_CUDA_CHECK(cudaFuncSetAttribute(k_gan_conv3<256, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvCfg<256, 1>::SMEM));
+    OCTA_CUDA_CHECK(cudaFuncSetAttribute(k_gan_conv3<128, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvCfg<128, 1>::SMEM));
+    OCTA_CUDA_CHECK(cudaFuncSetAttribute(k_gan_conv3<128, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvCfg<128, 2>::SMEM));
+    OCTA_CUDA_CHECK(cudaFuncSetAttribute(k_gan_conv3<64, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvCfg<64, 1>::SMEM));
+    OCTA_CUDA_CHECK(cudaFuncSetAttribute(k_gan_conv3<64, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvCfg<64, 2>::SMEM));
+    OCTA_CUDA_CHECK(cudaFuncSetAttribute(k_gan_conv3<64, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvCfg<64, 1>::SMEM));
     return OCTA_OK;
 }
 
@@ -665,12 +720,7 @@ extern "C" int octa_gan_create(const OctaGanWeights* w, int max_images, int H, i
         (rc = dev_alloc(c, &c->fin, n * (size_t)(H + 6) * (W + 6) * 64)) || (rc = dev_alloc(c, &c->planes, n * (size_t)(H + 6) * (W + 6) * 49)) || (rc = dev_alloc(c, &c->partial, n * 64 * 256 * 2)) ||
         (rc = dev_alloc(c, &c->mr, n * 256)))
         return fail(rc);
-    if (cudaFuncSetAttribute(k_gan_conv3<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvCfg<128>::SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(k_gan_conv3<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvCfg<64>::SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(k_gan_conv3<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvCfg<64>::SMEM) != cudaSuccess) {
-        octa::set_error("cudaFuncSetAttribute(k_gan_conv3): %s", cudaGetErrorString(cudaGetLastError()));
-        return fail(OCTA_E_CUDA);
-    }
+    if ((rc = conv_attrs(c))) return fail(rc);
     *handle = c;
     return OCTA_OK;
 }
@@ -726,7 +776,8 @@ extern "C" int octa_gan_forward_dev(void* handle, const float* x_dev, int n_imag
         const long long rows = (long long)n * (H + 6) * (W + 6);
         CUtensorMap tmA;
         GAN_TRY(make_map(&tmA, c->fin, 64, (uint64_t)rows, 128));
-        k_gan_conv3<64, 1><<<dim3((unsigned)((rows + 127) / 128), 1), CONV_THREADS, ConvCfg<64>::SMEM, st>>>(tmA, c->head.tmB, c->planes, (int)rows, W + 6, 1, 49, 1, 1);
+        const int mt = (int)((rows + 127) / 128);
+        k_gan_conv3<64, 1, 1><<<(unsigned)(mt < c->n_sm ? mt : c->n_sm), CONV_THREADS, ConvCfg<64, 1>::SMEM, st>>>(tmA, c->head.tmB, c->planes, (int)rows, W + 6, 1, 49, 1, 1, mt);
         const size_t total = (size_t)n * H * W;
         k_gan_head_sum<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(c->planes, (size_t)rows, c->head_b, n, H, W, y_dev, y_u8_dev);
         octa::count_launch(2);
@@ -762,7 +813,7 @@ extern "C" int octa_gan_input_dev(const uint8_t* raster_dev, const uint8_t* back
 // check the tensor-core kernel alone against torch.nn.functional.conv2d.
 extern "C" int octa_test_gan_conv3_host(const float* x, const float* w, int n, int H, int W, int cin, int cout, int reflect, float* y) {
     OCTA_ARG_CHECK(x && w && y && n > 0 && H > 1 && W > 1, "bad argument");
-    OCTA_ARG_CHECK(cin % 64 == 0 && (cout == 64 || cout % 128 == 0), "Cin must be a multiple of 64, Cout 64 or a multiple of 128");
+    OCTA_ARG_CHECK(cin % 64 == 0 && (cout == 64 || cout == 128 || cout == 256), "Cin must be a multiple of 64, Cout 64, 128 or 256");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); octa::set_error("no CUDA device"); return OCTA_E_CUDA; }
     GanCtx c;
@@ -785,8 +836,7 @@ extern "C" int octa_test_gan_conv3_host(const float* x, const float* w, int n, i
     bf16* d_act = nullptr;
     if ((rc = dev_alloc(&c, &d_act, act.size())) || (rc = dev_alloc(&c, &c.raw, rows * cout + 128 * 256))) return rc;
     OCTA_CUDA_CHECK(cudaMemcpy(d_act, act.data(), act.size() * 2, cudaMemcpyHostToDevice));
-    OCTA_CUDA_CHECK(cudaFuncSetAttribute(k_gan_conv3<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvCfg<128>::SMEM));
-    OCTA_CUDA_CHECK(cudaFuncSetAttribute(k_gan_conv3<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvCfg<64>::SMEM));
+    if ((rc = conv_attrs(&c))) return rc;
     if ((rc = run_conv(&c, L, d_act, n, H, W, 0))) return rc;
     OCTA_CUDA_CHECK(cudaDeviceSynchronize());
     std::vector<uint16_t> raw(rows * cout);

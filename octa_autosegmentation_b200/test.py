@@ -14,8 +14,9 @@ Rotate90d(k=1) + Flipd(0) on the background, AddRandomBackgroundNoised).  Output
 2-D raster, input transform, speckle stream, generator.
 
 Randomness: the reference draws the background index with `random.randint` inside dataloader worker processes and the
-speckle with the workers' `np.random`, so its outputs are not reproducible run to run.  Here sample i uses
-`random.Random(seed + i).randint(0, n_bg - 1)` and the stream `np.random.seed(seed + i)` with seed = `General.seed`.
+speckle with the workers' `np.random`, so its outputs are not reproducible run to run.  Here sample i (index in the sorted
+CSV list) uses `random.Random(seed + i).randint(0, n_bg - 1)` and the stream `np.random.seed(seed + i)` with seed =
+`General.seed`.  Under `torchrun --nproc-per-node N` rank r renders samples i = r (mod N) on GPU `LOCAL_RANK`.
 """
 from __future__ import annotations
 
@@ -45,12 +46,16 @@ def run(config: dict, num_samples: int = 9999999, batch_size: int = 32, device=N
     import torch
     from PIL import Image
 
-    device = torch.device(device or "cuda")
+    # one process per GPU (torchrun): rank r renders samples i = r (mod world) and writes its own files; a sample's output
+    # depends on its global index only, so any world size writes the same set of files
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    device = torch.device(device or ("cuda:%d" % int(os.environ.get("LOCAL_RANK", "0")) if world > 1 else "cuda"))
     test = config["Test"]
     seed = int(config["General"].get("seed") or 0)
     csvs = sorted(glob(test["data"]["real_A"]["files"], recursive=True), key=natural_key)
     assert len(csvs) > 0, f"Error: Your provided file path {test['data']['real_A']['files']} for real_A does not match any files!"
     csvs = csvs[:num_samples]
+    mine = list(range(rank, len(csvs), world))
     bgs = []
     if "background" in test["data"]:
         bgs = sorted(glob(test["data"]["background"]["files"], recursive=True), key=natural_key)
@@ -62,8 +67,9 @@ def run(config: dict, num_samples: int = 9999999, batch_size: int = 32, device=N
     G = gan.ResnetGenerator9.from_checkpoint(test["model_path"], image_size=(H, W), max_images=batch_size, device=device)
     written = []
     with torch.cuda.device(device):
-        for b0 in range(0, len(csvs), batch_size):
-            paths = csvs[b0:b0 + batch_size]
+        for b0 in range(0, len(mine), batch_size):
+            gidx = mine[b0:b0 + batch_size]
+            paths = [csvs[i] for i in gidx]
             edges = []
             for p in paths:
                 with open(p, "rb") as f:
@@ -74,11 +80,11 @@ def run(config: dict, num_samples: int = 9999999, batch_size: int = 32, device=N
             raster = tree2img.raster_batch_device(e7, offs, (W, H), 2, min_radius=min_radius)
             bg_t, seeds = None, None
             if bgs:
-                idx = [random.Random(seed + b0 + i).randint(0, len(bgs) - 1) for i in range(len(paths))]
+                idx = [random.Random(seed + i).randint(0, len(bgs) - 1) for i in gidx]
                 bg = np.stack([np.asarray(Image.open(bgs[j]).convert("L").resize((W, H)) if Image.open(bgs[j]).size != (W, H)
                                           else Image.open(bgs[j]).convert("L"), dtype=np.uint8) for j in idx])
                 bg_t = torch.from_numpy(bg).to(device)
-                seeds = [(seed + b0 + i) & 0xFFFFFFFF for i in range(len(paths))]
+                seeds = [(seed + i) & 0xFFFFFFFF for i in gidx]
             out = gan.contrast_adapt(G, raster, bg_t, seeds).cpu().numpy()
             gan.save_images(save_dir, paths, out, prefix=prefix)
             written += [os.path.join(save_dir, prefix + ".".join(os.path.basename(p).split(".")[:-1]) + ".png") for p in paths]

@@ -19,7 +19,8 @@ def _bf16_round(a):
 
 
 @pytest.mark.parametrize("cin,cout,reflect,shape", [(64, 128, False, (2, 20, 24)), (256, 256, True, (1, 19, 19)),
-                                                    (128, 64, False, (1, 37, 22)), (128, 256, False, (3, 12, 50))])
+                                                    (128, 64, False, (1, 37, 22)), (128, 256, False, (3, 12, 50)),
+                                                    (64, 128, True, (4, 96, 96))])        # 300 M tiles: several per persistent CTA
 def test_conv3_tcgen05_matches_torch(cin, cout, reflect, shape):
     import torch
     import torch.nn.functional as F
