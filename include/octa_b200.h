@@ -182,7 +182,7 @@ typedef struct OctaGanWeights {      /* HOST pointers, float32, the reference st
     int reserved;
 } OctaGanWeights;
 /* Uploads the weights (3x3 kernels as bf16 [Cout][tap][Cin]) and allocates activations for up to max_images images of
- * H x W (multiples of 4) per call: about 145 MB per 304 x 304 image. */
+ * H x W (multiples of 4) per call: about 100 MB per 304 x 304 image. */
 int octa_gan_create(const OctaGanWeights* w, int max_images, int H, int W, void** handle);
 /* x_dev float32 [n][H][W] in [0,1] -> y_dev float32 [n][H][W] (sigmoid output) and/or y_u8_dev = uint8(y * 255);
  * either output may be NULL.  Asynchronous on `stream`. */
