@@ -29,6 +29,8 @@ import time
 
 import numpy as np
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before CUDA initialises: one hardware queue per stream (see _lib.py)
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -163,7 +165,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--d2h-volume", action="store_true")
     ap.add_argument("--no-gan", action="store_true", help="skip the config #5 (GAN contrast adaptation) leg")
-    ap.add_argument("--in-flight", type=int, default=2, help="growth loops (batches) in flight per GPU in the pipelined API")
+    ap.add_argument("--in-flight", type=int, default=6, help="growth loops (sub-batches) in flight per GPU in the pipelined API")
+    ap.add_argument("--sub-batch", type=int, default=32, help="samples per growth loop; a step's --batch samples are fed to the "
+                                                              "pipelined API as batch / sub-batch consecutive batches")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -184,6 +188,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     B = args.batch
+    SB = args.sub_batch if 0 < args.sub_batch < B and B % args.sub_batch == 0 else B
+    NSUB = B // SB
     W = max(args.warmup, 3)
     pipe = Pipeline(default_config(), device=dev, volume_dims=DIMS, host_threads=max(1, (os.cpu_count() or 2) // max(world, 1)))
     counter = [0]
@@ -216,10 +222,21 @@ def main():
         return account(pipe.run(seeds(), d2h=d2h, csv=d2h), d2h)
 
     def run_steps(k, d2h):
-        # the public batched API: growth of step i overlaps voxelize / raster / CSV of step i-1 (two buffer sets)
+        # the public batched API: a step's B samples go in as B / SB batches; several growth loops are in flight while
+        # voxelize / raster / CSV of finished batches run on another stream
         last = None
-        for out in pipe.run_pipelined([seeds() for _ in range(k)], d2h=d2h, csv=d2h, in_flight=args.in_flight):
+        batches = []
+        for _ in range(k):
+            s = seeds()
+            batches += [s[j:j + SB] for j in range(0, B, SB)]
+        h2d = d2h_b = 0
+        for i, out in enumerate(pipe.run_pipelined(batches, d2h=d2h, csv=d2h, in_flight=args.in_flight)):
             last = account(out, d2h)
+            if d2h:
+                h2d += int(out["h2d_bytes"]); d2h_b += int(out["d2h_bytes"])
+        if d2h and last is not None:
+            last = dict(last)
+            last["h2d_bytes"], last["d2h_bytes"] = h2d // k, d2h_b // k      # per step of B samples
         return last
 
     def barrier():
@@ -242,7 +259,7 @@ def main():
             ms = float(t.item())
         return ms / steps, last
 
-    run_steps(max(W, args.in_flight + 1), False)               # (also allocates every buffer set of the pipelined path)
+    run_steps(max(W, (args.in_flight + NSUB) // NSUB), False)  # (also allocates every buffer set of the pipelined path)
     for k in phase:
         phase[k] = 0
     sampler = ClockSampler(local)
@@ -266,7 +283,7 @@ def main():
     ve[1].record()
     torch.cuda.synchronize()
     vox_ms = ve[0].elapsed_time(ve[1]) / nrep
-    run_steps(args.in_flight + 1, True)
+    run_steps(max(1, (args.in_flight + NSUB) // NSUB), True)
     ms_e2e, last = timed(lambda k: run_steps(k, True), max(2, args.steps))
     clocks = sampler.stop() if rank == 0 else None
     gan_line = None
@@ -323,8 +340,9 @@ def main():
         vol_bytes = int(np.prod(shape)) * 2
         E_last = int(offs[-1])
         vox_alg = 56 * E_last + vol_bytes * B                         # B_vox = 56 E + 2 X Y Z' per graph
-        n = max(ph["n"], 1)
-        b_grow = (28 * ph["sumA"] + 24 * ph["sumM"] + 24 * 2000 * 250 * B * n + 32 * ph["sumP"] + 24 * ph["sumS"] + 40 * ph["V"]) / n
+        n = max(ph["n"], 1)                                          # growth loops (sub-batches of SB samples) accounted
+        nsteps = n / NSUB
+        b_grow = (28 * ph["sumA"] + 24 * ph["sumM"] + 24 * 2000 * 250 * SB * n + 32 * ph["sumP"] + 24 * ph["sumS"] + 40 * ph["V"]) / nsteps
         grow_ms = ph["grow_ms"] / n
         vox_ach = vox_alg / (vox_ms * 1e-3) / 1e9
         # growth loops of several batches overlap: bytes of one step over the step time (the loop dominates the timeline)
@@ -333,14 +351,15 @@ def main():
             "metric": "graphs_per_sec", "value": B * world / (ms * 1e-3), "unit": "graphs/s", "n_gpus": world,
             "steps": args.steps, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD % B, "batch_per_gpu": B, "edges_per_graph_mean": ph["E"] / n / B,
+            "config": {"workload": WORKLOAD % B, "batch_per_gpu": B, "edges_per_graph_mean": ph["E"] / n / SB,
                        "seeds": "fresh every step (1000000 + step*B*world + rank*B + i)",
                        "l2": "per step %.1f GB of volumes + ~1.6 GB of growth state >> 126 MB L2 (no flush needed)" % (vol_bytes * B / 1e9),
-                       "pipelining": "Pipeline.run_pipelined: %d growth loops (batches of %d) in flight per GPU, each on its own pair of "
-                                     "high-priority streams; voxelize / raster / CSV of finished batches run on another stream and a "
-                                     "worker thread; the timed region contains every step completely (K batches in, K results out)"
-                                     % (args.in_flight, B),
-                       "in_flight_batches": args.in_flight,
+                       "pipelining": "Pipeline.run_pipelined: a step's %d samples enter as %d batches of %d; %d growth loops in flight per "
+                                     "GPU, each on its own pair of high-priority streams (CUDA_DEVICE_MAX_CONNECTIONS=%s); voxelize / "
+                                     "raster / CSV of finished batches run on another stream and a worker thread; the timed region "
+                                     "contains every step completely (all batches in, all results out)"
+                                     % (B, NSUB, SB, args.in_flight, os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS")),
+                       "in_flight_batches": args.in_flight, "sub_batch": SB,
                        "phase_ms": {"growth_loop_device": grow_ms, "voxelize_4_kernels": vox_ms, "step": ms}},
             "gpu_launches": int(launches),
             "e2e": {"value": B * world / (ms_e2e * 1e-3), "unit": "graphs/s", "h2d_bytes_per_step": int(last["h2d_bytes"]),

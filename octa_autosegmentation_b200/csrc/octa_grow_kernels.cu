@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(1024) k_grid_build(int dslot, GrowShape S, Ite
 // the arterial nodes (+radius), the O2 sinks and the active arterial nodes, blockIdx.y = 3 -> the candidate sampler.
 // 4*G CTAs run side by side instead of four dependent single-wave launches.  (The grid of the active venous nodes is
 // rebuilt by k_grid_build right after the venous commit.)
-__global__ void __launch_bounds__(1024) k_prepare(int dslot, GrowShape S, IterP P) {
+__global__ void __launch_bounds__(1024, 2) k_prepare(int dslot, GrowShape S, IterP P) {
     const GrowDev& D = c_dev[dslot];
     if (blockIdx.y < 3) grid_build_body(D, S, P, (int)blockIdx.y, blockIdx.x);
     else sample_body(D, S, P, blockIdx.x);
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(TILE) k_sink_tests(int dslot, GrowShape S, Ite
 // ------------------------------------------------------------------------------------------
 // k_sink_greedy: one CTA per graph; lexicographically-first maximal independent set in rounds
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_sink_greedy(int dslot, GrowShape S, IterP P) {
+__global__ void __launch_bounds__(1024, 2) k_sink_greedy(int dslot, GrowShape S, IterP P) {
     const GrowDev& D = c_dev[dslot];
     const int g = blockIdx.x, tid = threadIdx.x;
     if (D.err[g]) return;
@@ -1475,7 +1475,8 @@ void launch_iteration(int dslot, const GrowShape& S, const IterP& P, const IterP
         tick(st, 7 + 5 * f);
         if (f == 0) cudaStreamWaitEvent(st, ev.kd, 0);
         else { k_grid_build<<<S.G, 1024, 0, st>>>(dslot, S, P, 3); count_launch(1); }
-        k_kill<<<S.G, 1024, 0, st>>>(dslot, S, P, f);
+        static const int kill_threads = [] { const char* e = getenv("OCTA_KILL_THREADS"); const int v = e ? atoi(e) : 0; return (v == 256 || v == 512 || v == 1024) ? v : 1024; }();
+        k_kill<<<S.G, kill_threads, 0, st>>>(dslot, S, P, f);
         tick(st, 8 + 5 * f);
         count_launch(5);
         if (f == 0) {
