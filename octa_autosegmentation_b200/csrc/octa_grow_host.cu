@@ -24,7 +24,7 @@ void grow_timing_begin(cudaStream_t st);
 void grow_timing_report();
 struct GrowEvents { cudaEvent_t start, sinks, kd, killa; };
 void launch_begin(int dslot, const GrowShape& S, const IterP& P0, int n_sm, cudaStream_t st, cudaStream_t side, const GrowEvents& ev);
-void launch_iteration(int dslot, const GrowShape& S, const IterP& P, const IterP* Pnext, int n_sm, cudaStream_t st,
+void launch_iteration(int dslot, const GrowShape& S, const int commit_smem[2], const IterP& P, const IterP* Pnext, int n_sm, cudaStream_t st,
                       cudaStream_t side, const GrowEvents& ev);
 int max_ctx_slots();
 int upload_dev_table(int dslot, const GrowDev& D, cudaStream_t st);
@@ -371,6 +371,11 @@ struct GrowCtx {
     cudaStream_t main = nullptr, side = nullptr;
     int dslot = -1;             // constant-memory slot of this context's pointer table
     std::vector<unsigned char> geom;   // copy of the fixed sampling geometry (cfg.geometry points here)
+    // Envelope of the node count of each forest after iteration i, over the batches this context has grown so far.  The next run
+    // sizes k_commit's shared-memory tree mirror per launch from it: most of the schedule needs a fraction of the 224 KB, and a
+    // CTA that holds less shared memory lets other graphs' kernels (other loops in flight) share its SM.  A tree that outgrows the
+    // prediction runs the same code on the global arrays (bit-identical), so this is a performance hint, never a result.
+    std::vector<int> hist_nodes[2];
     ~GrowCtx() {
         release_slot(dslot);
         if (ev_done) cudaEventDestroy(ev_done);
@@ -587,17 +592,28 @@ static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, doub
         OCTA_CUDA_CHECK(cudaMemsetAsync(D.py_draws, 0, 8 * G, st)); OCTA_CUDA_CHECK(cudaMemsetAsync(D.counters, 0, 64 * G, st)); OCTA_CUDA_CHECK(cudaMemsetAsync(D.dbg, 0, 64 * G, st));
         OCTA_CUDA_CHECK(cudaMemsetAsync(D.err, 0, 4 * G, st));
         OCTA_CUDA_CHECK(cudaMemsetAsync(D.cbits, 0, sizeof(unsigned int) * G * 4 * ((S.capN + 31) / 32), st));
-        if (trace) OCTA_CUDA_CHECK(cudaMemsetAsync(D.trace, 0, sizeof(int) * G * 4096 * 4, st));
+        OCTA_CUDA_CHECK(cudaMemsetAsync(D.trace, 0, sizeof(int) * G * 4096 * 4, st));
         OCTA_CUDA_CHECK(ctx->wait(st));      // the staging buffer is reused for the read-back
     }
-    if (!trace) D.trace = nullptr;
     tw[2] = wall();
     OCTA_CUDA_CHECK(cudaEventRecord(ctx->e0, st));
     grow_timing_begin(st);
     if (upload_dev_table(ctx->dslot, D, st) != 0) { cudaGetLastError(); set_error("cudaMemcpyToSymbol(pointer table) failed"); return OCTA_E_CUDA; }
     if (!ctx->sched.empty()) launch_begin(ctx->dslot, S, ctx->sched[0], ctx->n_sm, st, ctx->side, ctx->ev);
-    for (size_t i = 0; i < ctx->sched.size(); ++i)
-        launch_iteration(ctx->dslot, S, ctx->sched[i], i + 1 < ctx->sched.size() ? &ctx->sched[i + 1] : nullptr, ctx->n_sm, st, ctx->side, ctx->ev);
+    const size_t n_it = ctx->sched.size();
+    static const bool adapt = [] { const char* e = getenv("OCTA_COMMIT_ADAPT"); return !(e && e[0] == '0'); }();
+    for (size_t i = 0; i < n_it; ++i) {
+        int cs[2] = {S.commit_smem, S.commit_smem};
+        for (int f = 0; f < 2 && adapt; ++f) {
+            const std::vector<int>& h = ctx->hist_nodes[f];
+            if (h.size() != n_it || n_it > 4096) continue;             // no history for this schedule yet: full mirror
+            const size_t n = (size_t)h[i > 0 ? i - 1 : 0] * 9 / 8 + 256;  // nodes before this call, +12 % and 256 of margin
+            const size_t need = ((n * 17 + 3) & ~(size_t)3) + 16 * ((n + 31) >> 5) + 64;   // k_commit's own formula
+            const size_t want = (need + 1023) & ~(size_t)1023;
+            cs[f] = (int)std::min<size_t>((size_t)S.commit_smem, std::max<size_t>(want, 8 * 1024));
+        }
+        launch_iteration(ctx->dslot, S, cs, ctx->sched[i], i + 1 < n_it ? &ctx->sched[i + 1] : nullptr, ctx->n_sm, st, ctx->side, ctx->ev);
+    }
     OCTA_CUDA_CHECK(cudaEventRecord(ctx->e1, st));
     tw[3] = wall();
     // ---- read back: counts first, then strided copies of the live prefix of every node array
@@ -620,6 +636,17 @@ static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, doub
     if (device_ms) *device_ms = ms;
     grow_timing_report();
     if (trace) OCTA_CUDA_CHECK(cudaMemcpy(trace, D.trace, sizeof(int) * G * 4096 * 4, cudaMemcpyDeviceToHost));
+    if (n_it > 0 && n_it <= 4096) {      // node counts per iteration of this batch -> envelope for the next run's mirror sizes
+        std::vector<int> tr((size_t)G * n_it * 4);
+        OCTA_CUDA_CHECK(cudaMemcpy2D(tr.data(), n_it * 16, D.trace, (size_t)4096 * 16, n_it * 16, G, cudaMemcpyDeviceToHost));
+        for (int f = 0; f < 2; ++f) {
+            std::vector<int>& h = ctx->hist_nodes[f];
+            if (h.size() != n_it) h.assign(n_it, 0);
+            for (int g = 0; g < n_graphs; ++g)
+                for (size_t i = 0; i < n_it; ++i) h[i] = std::max(h[i], tr[((size_t)g * n_it + i) * 4 + 2 * f]);
+            for (size_t i = 1; i < n_it; ++i) h[i] = std::max(h[i], h[i - 1]);
+        }
+    }
     size_t mx[2] = {1, 1};
     for (int f = 0; f < 2; ++f) for (int g = 0; g < n_graphs; ++g) mx[f] = std::max<size_t>(mx[f], (size_t)nn[f][g]);
     size_t so[2][5], off = 0;

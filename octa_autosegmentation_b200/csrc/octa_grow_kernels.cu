@@ -1375,6 +1375,17 @@ constexpr int KD_SMEM_BYTES = 208 * 1024;        // + ~17 KB static: scan / redu
 int prepare_kernels(const GrowShape& S) {
     cudaError_t e = cudaFuncSetAttribute(k_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)commit_smem_bytes(S));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_kdbuild, cudaFuncAttributeMaxDynamicSharedMemorySize, KD_SMEM_BYTES);
+    // Diagnostics (OCTA_CARVEOUT=1): every growth kernel asks for the largest shared-memory carve-out, so that CTAs of different
+    // kernels never wait for an SM to change its L1 / shared split.  Measured SLOWER (462 -> 443 graphs/s): the gather kernels
+    // (k_assign, k_sink_tests, k_kill) lose their L1, which costs more than the extra co-residency gains.  Off by default.
+    static const bool max_carve = [] { const char* v = getenv("OCTA_CARVEOUT"); return v && v[0] == '1'; }();
+    if (max_carve) {
+        const void* ks[] = {(const void*)k_grid_build, (const void*)k_prepare, (const void*)k_sink_tests, (const void*)k_sink_greedy,
+                            (const void*)k_assign, (const void*)k_group, (const void*)k_eval, (const void*)k_commit, (const void*)k_kill,
+                            (const void*)k_kdbuild};
+        for (const void* k : ks)
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    }
     return (int)e;
 }
 
@@ -1460,7 +1471,7 @@ void launch_begin(int dslot, const GrowShape& S, const IterP& P0, int n_sm, cuda
     launch_sampling(dslot, S, P0, n_sm, side, ev);
 }
 
-void launch_iteration(int dslot, const GrowShape& S, const IterP& P, const IterP* Pnext, int n_sm, cudaStream_t st,
+void launch_iteration(int dslot, const GrowShape& S, const int commit_smem[2], const IterP& P, const IterP* Pnext, int n_sm, cudaStream_t st,
                       cudaStream_t side, const GrowEvents& ev) {
     cudaStreamWaitEvent(st, ev.sinks, 0);
     for (int f = 0; f < 2; ++f) {
@@ -1470,12 +1481,18 @@ void launch_iteration(int dslot, const GrowShape& S, const IterP& P, const IterP
         tick(st, 5 + 5 * f);
         k_eval<<<dim3(16, S.G), 128, 0, st>>>(dslot, S, P, f);
         tick(st, 6 + 5 * f);
-        static const int commit_threads = [] { const char* e = getenv("OCTA_COMMIT_THREADS"); const int v = e ? atoi(e) : 0; return (v == 128 || v == 256 || v == 512) ? v : 512; }();
-        k_commit<<<S.G, commit_threads, commit_smem_bytes(S), st>>>(dslot, S, P, f);
+        // 256 threads x 128 registers = half the register file, and a mirror sized for this iteration (octa_grow_host.cu): two
+        // k_commit CTAs, or k_commit and another loop's kernels, share an SM -- the replay itself is one thread
+        static const int commit_threads = [] { const char* e = getenv("OCTA_COMMIT_THREADS"); const int v = e ? atoi(e) : 0; return (v == 128 || v == 256 || v == 512) ? v : 256; }();
+        GrowShape Sc = S;
+        Sc.commit_smem = commit_smem[f];
+        k_commit<<<S.G, commit_threads, (size_t)commit_smem[f], st>>>(dslot, Sc, P, f);
         tick(st, 7 + 5 * f);
         if (f == 0) cudaStreamWaitEvent(st, ev.kd, 0);
         else { k_grid_build<<<S.G, 1024, 0, st>>>(dslot, S, P, 3); count_launch(1); }
-        static const int kill_threads = [] { const char* e = getenv("OCTA_KILL_THREADS"); const int v = e ? atoi(e) : 0; return (v == 256 || v == 512 || v == 1024) ? v : 1024; }();
+        // 512 threads x 63 registers: two k_kill CTAs (or k_kill + another loop's kernel) share an SM; the pipeline is bound by SM
+        // slots held by one-CTA-per-graph kernels, not by their parallel phases (measured: 444 -> 453 graphs/s vs 1024 threads)
+        static const int kill_threads = [] { const char* e = getenv("OCTA_KILL_THREADS"); const int v = e ? atoi(e) : 0; return (v == 256 || v == 512 || v == 1024) ? v : 512; }();
         k_kill<<<S.G, kill_threads, 0, st>>>(dslot, S, P, f);
         tick(st, 8 + 5 * f);
         count_launch(5);

@@ -144,9 +144,24 @@ r2d_tile_kernel(const REdge* __restrict__ prep, const int64_t* __restrict__ offs
     int* lst = tile_edges + (size_t)RKBIG * eb;
     const int* bl = big_idx + eb;
     const int nbig = big_count[gr];
-    // restore list order (atomics filled the lists in arbitrary order): odd-even transposition by the CTA
-    {
-        const int n = end - beg;
+    // restore list order (atomics filled the lists in arbitrary order; the float product below is applied in edge order).
+    // Lists of up to one entry per thread are ranked in shared memory (edge ids are distinct: rank = number of smaller ids,
+    // two barriers); longer ones fall back to an odd-even transposition in place (one barrier and one global round trip per pass,
+    // which dominated this kernel when it was the only path).
+    __shared__ int s_in[RT * RT], s_sorted[RT * RT];
+    const int n = end - beg;
+    const bool in_smem = n <= RT * RT;
+    if (in_smem) {
+        int v = 0;
+        if ((int)threadIdx.x < n) { v = lst[beg + threadIdx.x]; s_in[threadIdx.x] = v; }
+        __syncthreads();
+        if ((int)threadIdx.x < n) {
+            int rank = 0;
+            for (int j = 0; j < n; ++j) rank += s_in[j] < v;
+            s_sorted[rank] = v;
+        }
+        __syncthreads();
+    } else {
         for (int pass = 0; pass < n; ++pass) {
             for (int i = (pass & 1) + 2 * threadIdx.x; i + 1 < n; i += 2 * blockDim.x) {
                 const int a = lst[beg + i], b = lst[beg + i + 1];
@@ -159,7 +174,8 @@ r2d_tile_kernel(const REdge* __restrict__ prep, const int64_t* __restrict__ offs
     if (px >= g.W || py >= g.H) return;
     const float cx = (float)px + 0.5f, cy = (float)py + 0.5f;
     float T = 1.f;
-    for (int k = beg; k < end; ++k) T *= 1.f - capsule_cover(ge[lst[k]], cx, cy);
+    if (in_smem) { for (int k = 0; k < n; ++k) T *= 1.f - capsule_cover(ge[s_sorted[k]], cx, cy); }
+    else { for (int k = beg; k < end; ++k) T *= 1.f - capsule_cover(ge[lst[k]], cx, cy); }
     // edges spanning more than RKBIG tiles (rare): the product commutes, so they are applied after the tile
     // list, in ascending edge order (selection over the unsorted, tiny list keeps the result deterministic)
     int prev = -1;
