@@ -158,14 +158,15 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=16, help="timed steps of --batch samples; the pipeline fills and drains inside the timed "
+                                                            "region (a growth loop has ~0.35 s of latency), so few steps measure mostly that")
+    ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--d2h-volume", action="store_true")
     ap.add_argument("--no-gan", action="store_true", help="skip the config #5 (GAN contrast adaptation) leg")
-    ap.add_argument("--in-flight", type=int, default=6, help="growth loops (sub-batches) in flight per GPU in the pipelined API")
+    ap.add_argument("--in-flight", type=int, default=8, help="growth loops (sub-batches) in flight per GPU in the pipelined API")
     ap.add_argument("--sub-batch", type=int, default=32, help="samples per growth loop; a step's --batch samples are fed to the "
                                                               "pipelined API as batch / sub-batch consecutive batches")
     args = ap.parse_args()
