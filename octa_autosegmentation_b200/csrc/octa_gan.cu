@@ -121,6 +121,31 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// a[j] of lane l = value of row l, column j  ->  returns the sum over the warp's 32 rows of column `lane`.  Five butterfly
+// steps; each halves the columns a lane still carries (31 shuffles, fixed summation order: deterministic).
+__device__ __forceinline__ float warp_colsum(float (&a)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = up ? a[i] : a[i + off];
+            const float keep = up ? a[i + off] : a[i];
+            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return a[0];
+}
+
+// Instance-norm statistics fused into the conv epilogue (EPI 0, st.part != nullptr): every M tile leaves the per-channel sum and
+// sum of squares of its valid rows (h < H, w < W of the padded grid) in part[tile][channel]; rows of a tile that already belong
+// to the next image go to carry[image][quarter][channel].  k_gan_stats_final adds a fixed sequence of partials per image.
+struct ConvStats {
+    float2* part;       // [num_tiles][cout]
+    float2* carry;      // [n_images][4][cout]
+    int hpwp, H, W;     // rows per image of the padded grid, valid extent
+};
+
 // Persistent, warp-specialised: one CTA per SM walks the M tiles (128 flat pixels x all BLOCK_N = Cout channels).
 //   warp 0 (one lane)  TMA producer: ring of STAGES x (A 128x64 + B BLOCK_Nx64) bf16 tiles, 128B swizzle, runs ahead across tiles
 //   warp 1 (one lane)  MMA issuer: 4 x tcgen05.mma (K = 16) per stage into accumulator (tile & 1) of TMEM; tcgen05.commit frees
@@ -131,13 +156,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 template <int BLOCK_N, int EPI, int CTAS>
 __global__ void __launch_bounds__(CONV_THREADS, CTAS)
 k_gan_conv3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, void* __restrict__ out,
-            int m_total, int wp, int cin_blocks, int cout, int taps, int kwn, int num_tiles) {
+            int m_total, int wp, int cin_blocks, int cout, int taps, int kwn, int num_tiles, ConvStats st) {
     using Cfg = ConvCfg<BLOCK_N, CTAS>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_dyn[];
     uint8_t* tiles = reinterpret_cast<uint8_t*>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_s;
+    __shared__ float2 s_part[2][4][EPI == 0 ? BLOCK_N : 1];   // per accumulator, per epilogue warp: column sums of its 32 rows
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = taps * cin_blocks;
 
@@ -205,6 +231,21 @@ k_gan_conv3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tc_fence_after();
             const int q = tile * 128 + quarter * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * (uint32_t)BLOCK_N;
+            const bool stats = EPI == 0 && st.part != nullptr;
+            bool mine0 = false, mine1 = false, cross = false;      // this row counts for the tile's first / second image
+            int img0 = 0;
+            if (stats) {
+                const int m0 = tile * 128;
+                img0 = m0 / st.hpwp;
+                const int r = q - img0 * st.hpwp;
+                const bool second = r >= st.hpwp;
+                const int rr = second ? r - st.hpwp : r;
+                const int hh = rr / wp, ww = rr - hh * wp;
+                const bool valid = q < m_total && hh < st.H && ww < st.W;
+                mine0 = valid && !second;
+                mine1 = valid && second;
+                cross = m0 + 127 - img0 * st.hpwp >= st.hpwp;       // (uniform over the tile)
+            }
 #pragma unroll 1
             for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
                 if (EPI == 1 && c0 >= cout) break;
@@ -220,6 +261,19 @@ k_gan_conv3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                                pack_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
                                                pack_bf16(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
                     }
+                    if (stats) {
+                        float a[32], b[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) { const float x = mine0 ? __uint_as_float(v[j]) : 0.f; a[j] = x; b[j] = x * x; }
+                        const float s0 = warp_colsum(a, lane), s1 = warp_colsum(b, lane);
+                        s_part[as][quarter][c0 + lane] = make_float2(s0, s1);
+                        if (cross) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) { const float x = mine1 ? __uint_as_float(v[j]) : 0.f; a[j] = x; b[j] = x * x; }
+                            const float c0s = warp_colsum(a, lane), c1s = warp_colsum(b, lane);
+                            st.carry[((size_t)(img0 + 1) * 4 + quarter) * cout + c0 + lane] = make_float2(c0s, c1s);
+                        }
+                    }
                 } else {
                     if (q < m_total) {
                         float* o = static_cast<float*>(out) + (size_t)c0 * m_total + q;   // a warp writes 32 consecutive q per plane
@@ -232,6 +286,15 @@ k_gan_conv3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[as]);    // 4 arrivals (one per epilogue warp) release the accumulator
+            if (EPI == 0 && st.part != nullptr) {
+                // the four warps' column sums -> one partial per tile, added in a fixed order (s_part is double buffered by
+                // accumulator, so the next tile's sums never overwrite what a slower warp still reads)
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int col = quarter * 32 + lane; col < BLOCK_N; col += 128) {
+                    const float2 p0 = s_part[as][0][col], p1 = s_part[as][1][col], p2 = s_part[as][2][col], p3 = s_part[as][3][col];
+                    st.part[(size_t)tile * cout + col] = make_float2((p0.x + p1.x) + (p2.x + p3.x), (p0.y + p1.y) + (p2.y + p3.y));
+                }
+            }
         }
     }
     tc_fence_before();
@@ -395,6 +458,26 @@ __global__ void __launch_bounds__(256) k_gan_stats(const bf16* __restrict__ raw,
         float* o = partial + (((size_t)b * chunks + ch) * C + cg * 8) * 2;
 #pragma unroll
         for (int k = 0; k < 8; ++k) { o[2 * k] = red[cg][k]; o[2 * k + 1] = red[cg][8 + k]; }
+    }
+}
+
+// mean / rstd per (image, channel) from the per-tile partials of the conv epilogue: tiles whose first row lies in image b, in
+// order, plus the four warp partials of the tile that straddles the previous image's end.  fp64 accumulation, biased variance.
+__global__ void __launch_bounds__(256) k_gan_stats_tiles(const float2* __restrict__ part, const float2* __restrict__ carry, int C, int hpwp, int hw,
+                                                         float2* __restrict__ mr /*[n][C] mean, rstd*/) {
+    const int b = blockIdx.x;
+    const long long r0 = (long long)b * hpwp, r1 = r0 + hpwp;
+    const int t0 = (int)((r0 + 127) / 128), t1 = (int)((r1 + 127) / 128);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        double s = 0, ss = 0;
+        if (r0 % 128 != 0)
+            for (int w = 0; w < 4; ++w) { const float2 p = carry[((size_t)b * 4 + w) * C + c]; s += p.x; ss += p.y; }
+#pragma unroll 8
+        for (int t = t0; t < t1; ++t) { const float2 p = __ldg(part + (size_t)t * C + c); s += p.x; ss += p.y; }
+        const double mean = s / hw;
+        double var = ss / hw - mean * mean;
+        if (var < 0) var = 0;
+        mr[(size_t)b * C + c] = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-5)));
     }
 }
 
