@@ -1,5 +1,3 @@
 mkdir -p gpurun_out
-timeout 900 python bench.py > gpurun_out/bench_r01_v9.json 2> gpurun_out/bench_err.log; python -c "
-import json; d=json.load(open('gpurun_out/bench_r01_v9.json')); print(d['value'], d['e2e']['value'], d['ms_per_step'], d['roofline']['frac'], d['gpu_launches'], d['cpu_baseline']['value'], d['config5_gan']['images_per_sec'], d['clocks'])"; tail -2 gpurun_out/bench_err.log
-timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | tail -1 > gpurun_out/bench_ref_v9.json; python -c "
-import json; d=json.load(open('gpurun_out/bench_ref_v9.json')); print('reference arm', d['value'], d['cpu_baseline']['cores'])"
+timeout 300 python -m pytest tests/test_gan_gpu.py -q -x -s > gpurun_out/pytest_gan.log 2>&1; tail -7 gpurun_out/pytest_gan.log
+timeout 200 python tools/gan_probe.py --batch 32 --reps 5 2>&1 | tail -2

@@ -20,7 +20,8 @@
 // (one TMEM lane quarter each).  The kernel is persistent (one CTA per SM walks the M tiles) with TWO accumulators in TMEM, so
 // the epilogue of tile i runs under the main loop of tile i+1, and the TMA ring (192 KB) runs ahead across tiles.  Conv biases that are followed by InstanceNorm(affine=False) cancel exactly in the
 // mean subtraction and are not applied.
-// The remaining layers are bandwidth-bound element kernels: instance-norm statistics, norm+ReLU(+skip) into the next
+// Instance-norm statistics are taken in the conv epilogue (per-tile partial sums from the fp32 accumulators, finalised by a tiny
+// kernel, deterministic).  The remaining layers are bandwidth-bound element kernels: norm+ReLU(+skip) into the next
 // padded buffer (zero or reflect border), blur-pool down / bilinear up (with the norm applied per tap).  The 7x7 stem (1 -> 64)
 // and head (64 -> 1) are GEMMs on the same kernel: im2col rows of 49 taps, resp. per-pixel tap responses summed afterwards.
 #include "octa_common.h"
@@ -139,7 +140,7 @@ __device__ __forceinline__ float warp_colsum(float (&a)[32], int lane) {
 
 // Instance-norm statistics fused into the conv epilogue (EPI 0, st.part != nullptr): every M tile leaves the per-channel sum and
 // sum of squares of its valid rows (h < H, w < W of the padded grid) in part[tile][channel]; rows of a tile that already belong
-// to the next image go to carry[image][quarter][channel].  k_gan_stats_final adds a fixed sequence of partials per image.
+// to the next image go to carry[image][quarter][channel].  k_gan_stats_tiles adds a fixed sequence of partials per image.
 struct ConvStats {
     float2* part;       // [num_tiles][cout]
     float2* carry;      // [n_images][4][cout]
@@ -431,36 +432,8 @@ __global__ void __launch_bounds__(256) k_gan_head_sum(const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------
-// instance-norm statistics of a raw conv output (valid pixels only), two deterministic stages
+// instance-norm statistics: finalisation of the per-tile partials the conv epilogue leaves (ConvStats)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_gan_stats(const bf16* __restrict__ raw, int H, int W, int C, int chunks, float* __restrict__ partial /*[n][chunks][C][2]*/) {
-    const int b = blockIdx.y, ch = blockIdx.x;
-    const int groups = C >> 3, lanes = 256 / groups;
-    const int cg = threadIdx.x % groups, pl = threadIdx.x / groups;
-    const int hw = H * W, per = (hw + chunks - 1) / chunks;
-    const int p0 = ch * per, p1 = min(hw, p0 + per);
-    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ss[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int p = p0 + pl; p < p1; p += lanes) {
-        const int h = p / W, w = p - h * W;
-        float f[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(raw + ((size_t)(b * (H + 2) + h) * (W + 2) + w) * C) + cg), f);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { s[k] += f[k]; ss[k] = fmaf(f[k], f[k], ss[k]); }
-    }
-    __shared__ float red[256][17];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { red[threadIdx.x][k] = s[k]; red[threadIdx.x][8 + k] = ss[k]; }
-    __syncthreads();
-    if (pl == 0) {
-        for (int l = 1; l < lanes; ++l)
-#pragma unroll
-            for (int k = 0; k < 16; ++k) red[cg][k] += red[l * groups + cg][k];
-        float* o = partial + (((size_t)b * chunks + ch) * C + cg * 8) * 2;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { o[2 * k] = red[cg][k]; o[2 * k + 1] = red[cg][8 + k]; }
-    }
-}
-
 // mean / rstd per (image, channel) from the per-tile partials of the conv epilogue: tiles whose first row lies in image b, in
 // order, plus the four warp partials of the tile that straddles the previous image's end.  fp64 accumulation, biased variance.
 __global__ void __launch_bounds__(256) k_gan_stats_tiles(const float2* __restrict__ part, const float2* __restrict__ carry, int C, int hpwp, int hw,
@@ -479,18 +452,6 @@ __global__ void __launch_bounds__(256) k_gan_stats_tiles(const float2* __restric
         if (var < 0) var = 0;
         mr[(size_t)b * C + c] = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-5)));
     }
-}
-
-__global__ void k_gan_stats_final(const float* __restrict__ partial, int n, int C, int chunks, int hw, float2* __restrict__ mr /*[n][C] mean, rstd*/) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n * C) return;
-    const int b = i / C, c = i - b * C;
-    double s = 0, ss = 0;
-    for (int k = 0; k < chunks; ++k) { const float* p = partial + (((size_t)b * chunks + k) * C + c) * 2; s += p[0]; ss += p[1]; }
-    const double mean = s / hw;
-    double var = ss / hw - mean * mean;                     // biased variance (InstanceNorm2d)
-    if (var < 0) var = 0;
-    mr[i] = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-5)));
 }
 
 // raw (flat rows of the [H+2][W+2] grid) -> (x - mean) * rstd [ReLU] [+ skip]  -> destination buffer with padding P
@@ -644,8 +605,7 @@ struct GanCtx {
     Conv3 conv[22];       // 0,1 = down; 2..19 = blocks (a, b); 20,21 = up
     // activations (bf16, padded), see octa_gan_forward_dev
     bf16 *raw = nullptr, *a1 = nullptr, *a2 = nullptr, *r0 = nullptr, *r1 = nullptr, *rt = nullptr, *u1 = nullptr, *b3 = nullptr, *u2 = nullptr, *fin = nullptr;
-    float* partial = nullptr;
-    float2* mr = nullptr;
+    float2 *mr = nullptr, *part = nullptr, *carry = nullptr;
     std::vector<void*> allocs;
     ~GanCtx() { for (void* p : allocs) cudaFree(p); }
 };
@@ -700,41 +660,36 @@ int upload_head(GanCtx* c, const float* w /*[1][64][7][7]*/) {
     return make_map(&c->head.tmB, c->head.w, 64, 64, 64);
 }
 
-int stats_chunks(int hw) { int c = hw / 256; return c < 1 ? 1 : (c > 64 ? 64 : c); }
 
 // raw = conv3x3(act) over the flat rows of act's padded grid
-int run_conv(const GanCtx* c, const Conv3& L, const bf16* act, int n, int H, int W, cudaStream_t st) {
+int run_conv(const GanCtx* c, const Conv3& L, const bf16* act, int n, int H, int W, cudaStream_t st, bool with_stats = true) {
     const int Wp = W + 2;
     const long long rows = (long long)n * (H + 2) * Wp;
     CUtensorMap tmA;
     int rc = make_map(&tmA, act, (uint64_t)L.cin, (uint64_t)rows, 128);
     if (rc) return rc;
     const int mt = (int)((rows + 127) / 128);
+    const ConvStats cs = {with_stats ? c->part : nullptr, c->carry, (H + 2) * Wp, H, W};
     auto grid = [&](int ctas) { const int g = c->n_sm * ctas; return (unsigned)(mt < g ? mt : g); };
     // bit 0: the Cout = 128 layers, bit 1: the Cout = 64 layer run 2 CTAs per SM (half the ring each).  Their A tiles feed fewer
     // MMA columns, so they are bound by L2 -> shared-memory traffic and two producers keep more of it in flight (measured per
     // layer on B200, 1 vs 2 CTAs: 551 -> 504 us, 560 -> 385 us, 1008 -> 577 us); the Cout = 256 layers prefer one CTA with N = 256
     const int two = c->two_ctas >= 0 ? c->two_ctas : 3;
     if (L.cout == 256)
-        k_gan_conv3<256, 0, 1><<<grid(1), CONV_THREADS, ConvCfg<256, 1>::SMEM, st>>>(tmA, L.tmB, c->raw, (int)rows, Wp, L.cin / 64, L.cout, 9, 3, mt);
+        k_gan_conv3<256, 0, 1><<<grid(1), CONV_THREADS, ConvCfg<256, 1>::SMEM, st>>>(tmA, L.tmB, c->raw, (int)rows, Wp, L.cin / 64, L.cout, 9, 3, mt, cs);
     else if (L.cout == 128 && !(two & 1))
-        k_gan_conv3<128, 0, 1><<<grid(1), CONV_THREADS, ConvCfg<128, 1>::SMEM, st>>>(tmA, L.tmB, c->raw, (int)rows, Wp, L.cin / 64, L.cout, 9, 3, mt);
+        k_gan_conv3<128, 0, 1><<<grid(1), CONV_THREADS, ConvCfg<128, 1>::SMEM, st>>>(tmA, L.tmB, c->raw, (int)rows, Wp, L.cin / 64, L.cout, 9, 3, mt, cs);
     else if (L.cout == 128)
-        k_gan_conv3<128, 0, 2><<<grid(2), CONV_THREADS, ConvCfg<128, 2>::SMEM, st>>>(tmA, L.tmB, c->raw, (int)rows, Wp, L.cin / 64, L.cout, 9, 3, mt);
+        k_gan_conv3<128, 0, 2><<<grid(2), CONV_THREADS, ConvCfg<128, 2>::SMEM, st>>>(tmA, L.tmB, c->raw, (int)rows, Wp, L.cin / 64, L.cout, 9, 3, mt, cs);
     else if (!(two & 2))
-        k_gan_conv3<64, 0, 1><<<grid(1), CONV_THREADS, ConvCfg<64, 1>::SMEM, st>>>(tmA, L.tmB, c->raw, (int)rows, Wp, L.cin / 64, L.cout, 9, 3, mt);
+        k_gan_conv3<64, 0, 1><<<grid(1), CONV_THREADS, ConvCfg<64, 1>::SMEM, st>>>(tmA, L.tmB, c->raw, (int)rows, Wp, L.cin / 64, L.cout, 9, 3, mt, cs);
     else
-        k_gan_conv3<64, 0, 2><<<grid(2), CONV_THREADS, ConvCfg<64, 2>::SMEM, st>>>(tmA, L.tmB, c->raw, (int)rows, Wp, L.cin / 64, L.cout, 9, 3, mt);
+        k_gan_conv3<64, 0, 2><<<grid(2), CONV_THREADS, ConvCfg<64, 2>::SMEM, st>>>(tmA, L.tmB, c->raw, (int)rows, Wp, L.cin / 64, L.cout, 9, 3, mt, cs);
     octa::count_launch();
-    OCTA_CUDA_CHECK(cudaGetLastError());
-    return OCTA_OK;
-}
-
-int run_stats(const GanCtx* c, int n, int H, int W, int C, cudaStream_t st) {
-    const int chunks = stats_chunks(H * W);
-    k_gan_stats<<<dim3(chunks, n), 256, 0, st>>>(c->raw, H, W, C, chunks, c->partial);
-    k_gan_stats_final<<<(n * C + 255) / 256, 256, 0, st>>>(c->partial, n, C, chunks, H * W, c->mr);
-    octa::count_launch(2);
+    if (with_stats) {
+        k_gan_stats_tiles<<<n, 256, 0, st>>>(c->part, c->carry, L.cout, (H + 2) * Wp, H * W, c->mr);
+        octa::count_launch();
+    }
     OCTA_CUDA_CHECK(cudaGetLastError());
     return OCTA_OK;
 }
@@ -804,8 +759,8 @@ extern "C" int octa_gan_create(const OctaGanWeights* w, int max_images, int H, i
         (rc = dev_alloc(c, &c->a2, n * p2 * 128)) || (rc = dev_alloc(c, &c->r0, n * p3 * 256)) ||
         (rc = dev_alloc(c, &c->r1, n * p3 * 256)) || (rc = dev_alloc(c, &c->rt, n * p3 * 256)) || (rc = dev_alloc(c, &c->u1, n * p2 * 256)) ||
         (rc = dev_alloc(c, &c->b3, n * p2 * 128)) || (rc = dev_alloc(c, &c->u2, n * p1 * 128)) ||
-        (rc = dev_alloc(c, &c->fin, n * (size_t)(H + 6) * (W + 6) * 64)) || (rc = dev_alloc(c, &c->planes, n * (size_t)(H + 6) * (W + 6) * 49)) || (rc = dev_alloc(c, &c->partial, n * 64 * 256 * 2)) ||
-        (rc = dev_alloc(c, &c->mr, n * 256)))
+        (rc = dev_alloc(c, &c->fin, n * (size_t)(H + 6) * (W + 6) * 64)) || (rc = dev_alloc(c, &c->planes, n * (size_t)(H + 6) * (W + 6) * 49)) || (rc = dev_alloc(c, &c->part, (n * p1 / 128 + 2) * 128)) ||
+        (rc = dev_alloc(c, &c->carry, (n + 1) * 4 * 256)) || (rc = dev_alloc(c, &c->mr, n * 256)))
         return fail(rc);
     if ((rc = conv_attrs(c))) return fail(rc);
     *handle = c;
@@ -829,40 +784,35 @@ extern "C" int octa_gan_forward_dev(void* handle, const float* x_dev, int n_imag
         GAN_TRY(make_map(&tmA, c->u2, 64, (uint64_t)rows, 128));
         const int mt = (int)((rows + 127) / 128);
         const int g = 2 * c->n_sm;
-        k_gan_conv3<64, 0, 2><<<(unsigned)(mt < g ? mt : g), CONV_THREADS, ConvCfg<64, 2>::SMEM, st>>>(tmA, c->stem.tmB, c->raw, (int)rows, W + 2, 1, 64, 1, 1, mt);
-        octa::count_launch(2);
+        k_gan_conv3<64, 0, 2><<<(unsigned)(mt < g ? mt : g), CONV_THREADS, ConvCfg<64, 2>::SMEM, st>>>(tmA, c->stem.tmB, c->raw, (int)rows, W + 2, 1, 64, 1, 1, mt,
+                                                                                                              ConvStats{c->part, c->carry, (H + 2) * (W + 2), H, W});
+        k_gan_stats_tiles<<<n, 256, 0, st>>>(c->part, c->carry, 64, (H + 2) * (W + 2), H * W, c->mr);
+        octa::count_launch(3);
         OCTA_CUDA_CHECK(cudaGetLastError());
     }
-    GAN_TRY(run_stats(c, n, H, W, 64, st));
     GAN_TRY(run_norm(c, nullptr, n, H, W, 64, 1, 0, 1, c->a1, st));
     // down 1: Conv2d(64, 128, 3, padding=1) + IN + ReLU + Downsample                          networks.py:384-387
     GAN_TRY(run_conv(c, c->conv[0], c->a1, n, H, W, st));
-    GAN_TRY(run_stats(c, n, H, W, 128, st));
     GAN_TRY(run_resample(c->raw, c->mr, n, H, W, 128, 0, 0, c->a2, st));        // IN + ReLU applied per tap
     // down 2
     GAN_TRY(run_conv(c, c->conv[1], c->a2, n, H2, W2, st));
-    GAN_TRY(run_stats(c, n, H2, W2, 256, st));
     GAN_TRY(run_resample(c->raw, c->mr, n, H2, W2, 256, 0, 1, c->r0, st));
     // 9 x ResnetBlock: x + IN(conv(pad(ReLU(IN(conv(pad(x)))))))                               networks.py:291-348
     bf16 *cur = c->r0, *nxt = c->r1;
     for (int blk = 0; blk < 9; ++blk) {
         GAN_TRY(run_conv(c, c->conv[2 + 2 * blk], cur, n, H3, W3, st));
-        GAN_TRY(run_stats(c, n, H3, W3, 256, st));
         GAN_TRY(run_norm(c, nullptr, n, H3, W3, 256, 1, 1, 1, c->rt, st));
         GAN_TRY(run_conv(c, c->conv[3 + 2 * blk], c->rt, n, H3, W3, st));
-        GAN_TRY(run_stats(c, n, H3, W3, 256, st));
         GAN_TRY(run_norm(c, cur, n, H3, W3, 256, 1, 1, 0, nxt, st));
         bf16* t = cur; cur = nxt; nxt = t;
     }
     // up 1 / up 2: Upsample + Conv2d(3, padding=1) + IN + ReLU                                networks.py:408-414
     GAN_TRY(run_resample(cur, nullptr, n, H3, W3, 256, 1, 0, c->u1, st));
     GAN_TRY(run_conv(c, c->conv[20], c->u1, n, H2, W2, st));
-    GAN_TRY(run_stats(c, n, H2, W2, 128, st));
     // (up-sampling makes 4 outputs per input: normalising once into b3 is cheaper than per tap -- 650 vs 840 us per 32 images)
     GAN_TRY(run_norm(c, nullptr, n, H2, W2, 128, 1, 0, 1, c->b3, st));
     GAN_TRY(run_resample(c->b3, nullptr, n, H2, W2, 128, 1, 0, c->u2, st));
     GAN_TRY(run_conv(c, c->conv[21], c->u2, n, H, W, st));
-    GAN_TRY(run_stats(c, n, H, W, 64, st));
     GAN_TRY(run_norm(c, nullptr, n, H, W, 64, 3, 1, 1, c->fin, st));
     // head: ReflectionPad2d(3) + Conv2d(64, 1, 7) + Sigmoid                                    networks.py:415-417
     // one GEMM [pixels of the padded grid x 64 ch] x [64 ch x 49 taps] on the tensor cores, then the shifted sum of the 49 planes
@@ -871,7 +821,7 @@ extern "C" int octa_gan_forward_dev(void* handle, const float* x_dev, int n_imag
         CUtensorMap tmA;
         GAN_TRY(make_map(&tmA, c->fin, 64, (uint64_t)rows, 128));
         const int mt = (int)((rows + 127) / 128);
-        k_gan_conv3<64, 1, 1><<<(unsigned)(mt < c->n_sm ? mt : c->n_sm), CONV_THREADS, ConvCfg<64, 1>::SMEM, st>>>(tmA, c->head.tmB, c->planes, (int)rows, W + 6, 1, 49, 1, 1, mt);
+        k_gan_conv3<64, 1, 1><<<(unsigned)(mt < c->n_sm ? mt : c->n_sm), CONV_THREADS, ConvCfg<64, 1>::SMEM, st>>>(tmA, c->head.tmB, c->planes, (int)rows, W + 6, 1, 49, 1, 1, mt, ConvStats{nullptr, nullptr, 1, 0, 0});
         const size_t total = (size_t)n * H * W;
         k_gan_head_sum<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(c->planes, (size_t)rows, c->head_b, n, H, W, y_dev, y_u8_dev);
         octa::count_launch(2);
@@ -931,7 +881,7 @@ extern "C" int octa_test_gan_conv3_host(const float* x, const float* w, int n, i
     if ((rc = dev_alloc(&c, &d_act, act.size())) || (rc = dev_alloc(&c, &c.raw, rows * cout + 128 * 256))) return rc;
     OCTA_CUDA_CHECK(cudaMemcpy(d_act, act.data(), act.size() * 2, cudaMemcpyHostToDevice));
     if ((rc = conv_attrs(&c))) return rc;
-    if ((rc = run_conv(&c, L, d_act, n, H, W, 0))) return rc;
+    if ((rc = run_conv(&c, L, d_act, n, H, W, 0, false))) return rc;
     OCTA_CUDA_CHECK(cudaDeviceSynchronize());
     std::vector<uint16_t> raw(rows * cout);
     OCTA_CUDA_CHECK(cudaMemcpy(raw.data(), c.raw, raw.size() * 2, cudaMemcpyDeviceToHost));
