@@ -100,6 +100,15 @@ bool fixed8(double x, uint64_t* q_out) {
     const double ax = fabs(x);
     if (!(ax < 1048576.0)) return false;
     if (ax == 0.0) { *q_out = 0; return true; }
+    {
+        // Fast path.  p = fl(ax * 1e8) differs from the exact product T by at most ulp(p)/2 <= p * 2^-53, and p - floor(p) is exact
+        // (p < 2^47).  round-half-even(T) can differ from rounding p only if p lies within that error of a half-integer; an
+        // integer boundary between T and p does not matter (both sides round to that integer).
+        const double p = ax * 1e8;
+        const double fl = floor(p);
+        const double fr = p - fl;
+        if (fabs(fr - 0.5) > p * 1.2e-16 + 1e-300) { *q_out = (uint64_t)fl + (fr > 0.5 ? 1u : 0u); return true; }
+    }
     uint64_t bits;
     memcpy(&bits, &ax, 8);
     const int be = (int)(bits >> 52);
@@ -121,8 +130,9 @@ static const char DIG2[201] =
 
 // writes the integer / fraction digit strings of q = round(|x| * 1e8); fraction trimmed of trailing zeros
 inline void fixed8_digits(uint64_t q, bool neg, char* ip, int* ilen, char* fp, int* flen) {
-    uint64_t ipart = q / 100000000u;
-    uint32_t f = (uint32_t)(q % 100000000u);
+    uint64_t ipart = 0;
+    uint32_t f = (uint32_t)q;
+    if (q >= 100000000u) { ipart = q / 100000000u; f = (uint32_t)(q - ipart * 100000000u); }   // (|x| < 1 is the common case)
     int k = 0;
     if (neg) ip[k++] = '-';
     if (ipart < 10) ip[k++] = (char)('0' + ipart);
@@ -178,6 +188,50 @@ bool sci9(double x, uint64_t* q_out, int* e10_out) {
         return true;
     }
     return false;
+}
+
+// Positional [a b c] cell written straight into `p` (>= 64 bytes free); nullptr when the generic formatter is needed
+// (exponential notation, |x| >= 2^20).  Same layout rules as append_array3 below.
+inline char* fast_array3(char* p, const double* v) {
+    double mx = 0, mn = 0;
+    bool any = false;
+    for (int i = 0; i < 3; ++i) {
+        const double a = fabs(v[i]);
+        if (a != 0.0) { if (!any) { mx = mn = a; any = true; } else { if (a > mx) mx = a; if (a < mn) mn = a; } }
+    }
+    if (any && (mx >= 1.e8 || mn < 0.0001 || mx / mn > 1000.)) return nullptr;
+    uint64_t q[3];
+    if (!(fixed8(v[0], &q[0]) && fixed8(v[1], &q[1]) && fixed8(v[2], &q[2]))) return nullptr;
+    char ipb[3][24], fpb[3][8];
+    int il[3], fl[3], pl = 0, pr = 0;
+    for (int i = 0; i < 3; ++i) {
+        fixed8_digits(q[i], signbit(v[i]), ipb[i], &il[i], fpb[i], &fl[i]);
+        if (il[i] > pl) pl = il[i];
+        if (fl[i] > pr) pr = fl[i];
+    }
+    *p++ = '[';
+    for (int i = 0; i < 3; ++i) {
+        if (i) *p++ = ' ';
+        for (int k = il[i]; k < pl; ++k) *p++ = ' ';
+        memcpy(p, ipb[i], (size_t)il[i]); p += il[i];
+        *p++ = '.';
+        memcpy(p, fpb[i], 8); p += fl[i];                 // (8 bytes copied, fl[i] kept: the tail is overwritten next)
+        for (int k = fl[i]; k < pr; ++k) *p++ = ' ';
+    }
+    *p++ = ']';
+    return p;
+}
+
+// Python repr(float) for the fixed-notation range, straight into `p` (>= 40 bytes free); nullptr outside it
+inline char* fast_repr(char* p, double x) {
+    const double a = fabs(x);
+    if (!(a >= 1e-4 && a < 1e16)) return nullptr;
+    auto r = std::to_chars(p, p + 40, x, std::chars_format::fixed);
+    bool dot = false;
+    for (char* c = p; c != r.ptr; ++c) if (*c == '.') { dot = true; break; }
+    p = r.ptr;
+    if (!dot) { *p++ = '.'; *p++ = '0'; }
+    return p;
 }
 
 void append_array3(std::string& out, const double* v) {
@@ -248,7 +302,15 @@ void append_array3(std::string& out, const double* v) {
                 line[k++] = dg[i][0];
                 line[k++] = '.';
                 for (int d = 1; d <= prec; ++d) line[k++] = d <= fl[i] ? dg[i][d] : '0';
-                k += snprintf(line + k, 16, "e%c%0*d", ex[i] < 0 ? '-' : '+', exp_size, abs(ex[i]));
+                line[k++] = 'e';                                // "e%c%0*d" by hand (snprintf dominated this path)
+                line[k++] = ex[i] < 0 ? '-' : '+';
+                {
+                    char eb[12];
+                    int a = abs(ex[i]), nd = 0;
+                    do { eb[nd++] = (char)('0' + a % 10); a /= 10; } while (a);
+                    for (int z = nd; z < exp_size; ++z) line[k++] = '0';
+                    while (nd) line[k++] = eb[--nd];
+                }
             }
             line[k++] = ']';
             out.append(line, k);
@@ -332,26 +394,48 @@ void append_repr(std::string& out, double x) {
 
 extern "C" int octa_format_csv(const double* edges7, int64_t n_edges, char* buf, size_t cap, size_t* len) {
     OCTA_ARG_CHECK(n_edges >= 0 && len && (n_edges == 0 || edges7), "bad arguments");
-    std::string out;
-    out.reserve(32 + (size_t)n_edges * 100);
-    out += "node1,node2,radius\r\n";
+    // Rows are written straight into the caller's buffer while it has room for a worst-case row; the (rare) cells the fast
+    // writers decline -- exponential notation, huge values -- and the case of a too small / missing buffer go through strings.
+    static const char header[] = "node1,node2,radius\r\n";
+    constexpr size_t ROW_MAX = 320;
+    std::string spill;                                      // rows that did not fit the caller's buffer
+    char* p = buf;
+    char* const end = buf ? buf + cap : nullptr;
+    bool direct = buf && cap >= sizeof(header) - 1 + ROW_MAX;
+    if (direct) { memcpy(p, header, sizeof(header) - 1); p += sizeof(header) - 1; }
+    else spill.assign(header, sizeof(header) - 1);
+    std::string tmp;
     for (int64_t i = 0; i < n_edges; ++i) {
         const double* e = edges7 + 7 * i;
         for (int k = 0; k < 7; ++k)
             if (!(e[k] == e[k]) || isinf(e[k])) { octa::set_error("octa_format_csv: non-finite value in edge %lld", (long long)i); return OCTA_E_ARG; }
-        append_array3(out, e);
-        out.push_back(',');
-        append_array3(out, e + 3);
-        out.push_back(',');
-        append_repr(out, e[6]);
-        out += "\r\n";
+        if (direct && (size_t)(end - p) < ROW_MAX) { direct = false; spill.reserve((size_t)(n_edges - i) * 100); }
+        if (direct) {
+            char* r = fast_array3(p, e);
+            if (!r) { tmp.clear(); append_array3(tmp, e); memcpy(p, tmp.data(), tmp.size()); r = p + tmp.size(); }
+            p = r; *p++ = ',';
+            r = fast_array3(p, e + 3);
+            if (!r) { tmp.clear(); append_array3(tmp, e + 3); memcpy(p, tmp.data(), tmp.size()); r = p + tmp.size(); }
+            p = r; *p++ = ',';
+            r = fast_repr(p, e[6]);
+            if (!r) { tmp.clear(); append_repr(tmp, e[6]); memcpy(p, tmp.data(), tmp.size()); r = p + tmp.size(); }
+            p = r; *p++ = '\r'; *p++ = '\n';
+        } else {
+            append_array3(spill, e);
+            spill.push_back(',');
+            append_array3(spill, e + 3);
+            spill.push_back(',');
+            append_repr(spill, e[6]);
+            spill += "\r\n";
+        }
     }
-    *len = out.size();
-    if (!buf || cap < out.size()) {
-        octa::set_error("octa_format_csv: buffer too small (%zu needed)", out.size());
+    const size_t written = buf ? (size_t)(p - buf) : 0;
+    *len = written + spill.size();
+    if (!buf || !spill.empty()) {
+        if (buf && cap >= *len) { memcpy(buf + written, spill.data(), spill.size()); return OCTA_OK; }
+        octa::set_error("octa_format_csv: buffer too small (%zu needed)", *len);
         return OCTA_E_NOMEM;
     }
-    memcpy(buf, out.data(), out.size());
     return OCTA_OK;
 }
 
