@@ -37,6 +37,7 @@ class Pipeline:
         self._grows = {}           # growth contexts by index (run_pipelined keeps several batches in flight)
         self._grow_locks = {}
         self._post_stream = None
+        self._h2d_done = {}
         self.edge_cap = 24000      # rows reserved per sample in the pinned edge buffer (docker config: ~13 k)
 
     def _tensor(self, key, shape, dtype, pinned=False):
@@ -67,6 +68,9 @@ class Pipeline:
             n = len(seeds)
             cap = n * self.edge_cap
             host_edges = self._tensor("edges_host%d" % slot, (cap, 7), torch.float64, pinned=True)
+            ev = self._h2d_done.get(slot)          # the previous user of this slot's pinned rows: its upload must have been executed
+            if ev is not None:                     # (device-resident results are handed out before the post stream has run)
+                ev.synchronize()
             offs, n_art, stats, grow_ms = g.run_packed(seeds, host_edges.numpy())
             return {"n": n, "cap": cap, "host_edges": host_edges, "offs": offs, "n_art": n_art, "stats": stats, "grow_ms": grow_ms}
 
@@ -82,6 +86,9 @@ class Pipeline:
                 he = host_edges.numpy()
                 edges_dev = self._tensor("edges_dev" + sfx, (cap, 7), torch.float64)
                 edges_dev[:max(E, 1)].copy_(host_edges[:max(E, 1)], non_blocking=True)
+                h2d = torch.cuda.Event()
+                h2d.record(stream)
+                self._h2d_done[slot] = h2d
                 graphs = [(he[offs[i]:offs[i] + n_art[i]], he[offs[i] + n_art[i]:offs[i + 1]]) for i in range(n)]   # views
                 out = {"graphs": graphs, "stats": g["stats"], "offsets": offs, "grow_device_ms": g["grow_ms"], "edges_host": he[:E]}
                 if self.voxelize:
