@@ -1,3 +1,3 @@
-mkdir -p gpurun_out
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
+timeout 300 python -m pytest tests/test_pipeline_gpu.py -x -q 2>&1 | tail -1
+K=10 OCTA_EXTRA_SLOTS=0 timeout 300 python tools/e2e_probe.py 2>&1 | tail -4 | sed 's/^/slots+0 /'
+K=10 OCTA_EXTRA_SLOTS=3 timeout 300 python tools/e2e_probe.py 2>&1 | tail -4 | sed 's/^/slots+3 /'

@@ -138,10 +138,12 @@ class Pipeline:
         are throughput kernels, CSV text is host work: `in_flight` growth loops run side by side (one growth context,
         two high-priority streams and one host thread each) while a worker thread post-processes finished batches on a
         second stream.  Every result equals what run() returns for the same seeds (a sample depends on its seed only);
-        a yielded result stays valid until `in_flight + 1` further batches have been started."""
+        a yielded result stays valid until `in_flight + 4` further batches have been started."""
         torch = self.torch
         in_flight = max(1, int(in_flight))
-        nslots = in_flight + 1
+        # buffer sets: one per loop in flight, one being post-processed, and three of slack -- a grower may only reuse a slot's pinned
+        # edge rows once their upload has executed on the (default-priority, possibly lagging) post stream (_h2d_done)
+        nslots = in_flight + 1 + max(0, int(os.environ.get("OCTA_EXTRA_SLOTS", "3")))
         if self._post_stream is None:
             with torch.cuda.device(self.device):
                 self._post_stream = torch.cuda.Stream()
