@@ -260,7 +260,8 @@ def main():
             ms = float(t.item())
         return ms / steps, last
 
-    run_steps(max(W, (args.in_flight + NSUB) // NSUB), False)  # (also allocates every buffer set of the pipelined path)
+    NSETS = Pipeline.buffer_sets(args.in_flight)
+    run_steps(max(W, (NSETS + NSUB - 1) // NSUB), False)       # (also allocates every buffer set of the pipelined path)
     for k in phase:
         phase[k] = 0
     sampler = ClockSampler(local)
@@ -284,7 +285,7 @@ def main():
     ve[1].record()
     torch.cuda.synchronize()
     vox_ms = ve[0].elapsed_time(ve[1]) / nrep
-    run_steps(max(1, (args.in_flight + NSUB) // NSUB), True)
+    run_steps(max(1, (NSETS + NSUB - 1) // NSUB), True)        # (pinned result buffers of every set)
     ms_e2e, last = timed(lambda k: run_steps(k, True), max(2, args.steps))
     clocks = sampler.stop() if rank == 0 else None
     gan_line = None

@@ -131,6 +131,13 @@ class Pipeline:
         tensors), and with d2h: label_host / image_host (pinned uint8) and csv (list of bytes)."""
         return self._post_stage(self._grow_stage(seeds, 0), 0, d2h, csv)
 
+    @staticmethod
+    def buffer_sets(in_flight: int) -> int:
+        """Buffer sets run_pipelined cycles through: one per loop in flight, one being post-processed, and three of slack -- a
+        grower may only reuse a slot's pinned edge rows once their upload has executed on the (default-priority, possibly
+        lagging) post stream (_h2d_done).  Each set is allocated on first use: warm up with at least this many batches."""
+        return max(1, int(in_flight)) + 1 + max(0, int(os.environ.get("OCTA_EXTRA_SLOTS", "3")))
+
     def run_pipelined(self, seed_batches, d2h: bool = True, csv: bool = True, in_flight: int = 2):
         """Generator over batches, results in order, software-pipelined.
 
@@ -141,9 +148,7 @@ class Pipeline:
         a yielded result stays valid until `in_flight + 4` further batches have been started."""
         torch = self.torch
         in_flight = max(1, int(in_flight))
-        # buffer sets: one per loop in flight, one being post-processed, and three of slack -- a grower may only reuse a slot's pinned
-        # edge rows once their upload has executed on the (default-priority, possibly lagging) post stream (_h2d_done)
-        nslots = in_flight + 1 + max(0, int(os.environ.get("OCTA_EXTRA_SLOTS", "3")))
+        nslots = self.buffer_sets(in_flight)
         if self._post_stream is None:
             with torch.cuda.device(self.device):
                 self._post_stream = torch.cuda.Stream()

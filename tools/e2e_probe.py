@@ -19,7 +19,7 @@ def run(k, d2h, csv):
     for _ in pipe.run_pipelined(batches(k), d2h=d2h, csv=csv, in_flight=L):
         pass
     torch.cuda.synchronize()
-run(5, False, False); run(5, True, True)
+run(7, False, False); run(7, True, True)
 for name, d2h, csv in (("device resident", False, False), ("+ D2H label/image", True, False), ("+ CSV text", True, True), ("device resident", False, False)):
     torch.cuda.synchronize(); t = time.time(); run(K, d2h, csv); dt = time.time() - t
     print("%-22s %.1f graphs/s (%.1f ms per 64)" % (name, K * 64 / dt, dt / K * 1e3))
