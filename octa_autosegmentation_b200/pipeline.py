@@ -68,10 +68,17 @@ class Pipeline:
             n = len(seeds)
             cap = n * self.edge_cap
             host_edges = self._tensor("edges_host%d" % slot, (cap, 7), torch.float64, pinned=True)
-            ev = self._h2d_done.get(slot)          # the previous user of this slot's pinned rows: its upload must have been executed
-            if ev is not None:                     # (device-resident results are handed out before the post stream has run)
+            # The loop writes its rows into a buffer private to this growth context; they move into the slot's pinned rows only
+            # after the slot's previous upload has executed on the (default-priority, possibly lagging) post stream -- device-
+            # resident results are handed out before that stream has run.  Waiting here, after ~0.4 s of growth, never blocks in
+            # practice; the same wait before the loop delayed every start by the post stream's lag (482 -> 450 graphs/s).
+            ctx_edges = self._tensor("edges_ctx%d" % ctx, (cap, 7), torch.float64, pinned=True)
+            offs, n_art, stats, grow_ms = g.run_packed(seeds, ctx_edges.numpy())
+            ev = self._h2d_done.get(slot)
+            if ev is not None:
                 ev.synchronize()
-            offs, n_art, stats, grow_ms = g.run_packed(seeds, host_edges.numpy())
+            E = int(offs[-1])
+            host_edges[:E].copy_(ctx_edges[:E])
             return {"n": n, "cap": cap, "host_edges": host_edges, "offs": offs, "n_art": n_art, "stats": stats, "grow_ms": grow_ms}
 
     def _post_stage(self, g: dict, slot: int, d2h: bool, csv: bool, stream=None) -> dict:
@@ -133,10 +140,9 @@ class Pipeline:
 
     @staticmethod
     def buffer_sets(in_flight: int) -> int:
-        """Buffer sets run_pipelined cycles through: one per loop in flight, one being post-processed, and three of slack -- a
-        grower may only reuse a slot's pinned edge rows once their upload has executed on the (default-priority, possibly
-        lagging) post stream (_h2d_done).  Each set is allocated on first use: warm up with at least this many batches."""
-        return max(1, int(in_flight)) + 1 + max(0, int(os.environ.get("OCTA_EXTRA_SLOTS", "3")))
+        """Buffer sets run_pipelined cycles through: one per loop in flight and one being post-processed.  Each set is allocated on
+        first use: warm up with at least this many batches."""
+        return max(1, int(in_flight)) + 1 + max(0, int(os.environ.get("OCTA_EXTRA_SLOTS", "0")))
 
     def run_pipelined(self, seed_batches, d2h: bool = True, csv: bool = True, in_flight: int = 2):
         """Generator over batches, results in order, software-pipelined.
@@ -145,7 +151,7 @@ class Pipeline:
         are throughput kernels, CSV text is host work: `in_flight` growth loops run side by side (one growth context,
         two high-priority streams and one host thread each) while a worker thread post-processes finished batches on a
         second stream.  Every result equals what run() returns for the same seeds (a sample depends on its seed only);
-        a yielded result stays valid until `in_flight + 4` further batches have been started."""
+        a yielded result stays valid until `in_flight + 1` further batches have been started."""
         torch = self.torch
         in_flight = max(1, int(in_flight))
         nslots = self.buffer_sets(in_flight)
