@@ -78,7 +78,9 @@ class Pipeline:
             if ev is not None:
                 ev.synchronize()
             E = int(offs[-1])
-            host_edges[:E].copy_(ctx_edges[:E])
+            # plain memmove (ctypes releases the GIL): torch's copy_ would open a 16-thread OpenMP region per call, from every
+            # grower thread at once, next to the CSV pool
+            ctypes.memmove(host_edges.data_ptr(), ctx_edges.data_ptr(), E * 56)
             return {"n": n, "cap": cap, "host_edges": host_edges, "offs": offs, "n_art": n_art, "stats": stats, "grow_ms": grow_ms}
 
     def _post_stage(self, g: dict, slot: int, d2h: bool, csv: bool, stream=None) -> dict:
