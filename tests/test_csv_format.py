@@ -61,3 +61,42 @@ def test_empty_and_errors():
         graph_io.csv_bytes(np.array([[np.nan, 0, 0, 0, 0, 0, 1.0]]))
     with pytest.raises(OctaError):
         graph_io.parse_csv_bytes(b"node1,node2,radius\r\n[0.1 0.2,[0 0 0],1\r\n")
+
+
+def test_half_way_points_of_the_8_decimal_grid():
+    """The fast path of fixed8 (one double multiply) must hand exactly the inputs next to a rounding boundary to the exact
+    128-bit path: values at and within two ulps of (k + 0.5) * 1e-8, and dyadic fractions, against numpy."""
+    rng = np.random.RandomState(1)
+    k = rng.randint(1, 10 ** 8, 12000).astype(np.float64)
+    base = (k + 0.5) * 1e-8
+    vals = []
+    for d in (-2, -1, 0, 1, 2):
+        v = base.copy()
+        for _ in range(abs(d)):
+            v = np.nextafter(v, np.inf if d > 0 else -np.inf)
+        vals.append(v)
+    v = np.concatenate(vals + [rng.randint(1, 2 ** 20, 6000) / 2.0 ** rng.randint(1, 40, 6000)])
+    v = v[(v >= 1e-4) & (v < 1)]
+    n = len(v) // 6 * 6
+    e7 = np.zeros((n // 6, 7))
+    e7[:, :6] = v[:n].reshape(-1, 6)
+    e7[:, 6] = rng.rand(n // 6)
+    assert graph_io.csv_bytes(e7) == python_csv(e7)
+
+
+def test_small_caller_buffer_is_reported_not_overrun():
+    import ctypes
+    from octa_autosegmentation_b200 import _lib
+    L = _lib.lib()
+    L.octa_format_csv.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+    e7 = np.random.RandomState(2).rand(50, 7)
+    want = python_csv(e7)
+    n = ctypes.c_size_t(0)
+    for cap in (0, 10, 400, len(want) - 1):
+        buf = ctypes.create_string_buffer(cap + 16)
+        buf.raw = b"\xee" * (cap + 16)
+        rc = L.octa_format_csv(e7.ctypes.data, len(e7), buf if cap else None, cap, ctypes.byref(n))
+        assert rc == _lib.OCTA_E_NOMEM and n.value == len(want)
+        assert buf.raw[cap:] == b"\xee" * 16                       # nothing written past the capacity
+    buf = ctypes.create_string_buffer(len(want))
+    assert L.octa_format_csv(e7.ctypes.data, len(e7), buf, len(want), ctypes.byref(n)) == 0 and buf.raw[:n.value] == want

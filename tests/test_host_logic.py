@@ -54,3 +54,22 @@ def test_two_rank_gloo_gather_of_edge_tables():
                        env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "GATHER_OK" in r.stdout
+
+
+def test_gan_host_helpers():
+    """Host-side pieces of the GAN path that need no device: weight order of the C ABI, random-init shapes, flop count,
+    resolution parsing of the reference's Test.data_augmentation stanza, buffer-set count of the pipelined API."""
+    from octa_autosegmentation_b200 import gan, test as gan_cli
+    from octa_autosegmentation_b200.pipeline import Pipeline
+    from oracle import gan_oracle as go
+
+    keys = gan.conv_keys()
+    assert keys[:3] == ["model.4", "model.8", "model.12.conv_block.1"] and keys[-3:] == ["model.20.conv_block.5", "model.22", "model.26"]
+    a, b = gan.random_init_state_dict(3), go.random_state_dict(3)
+    assert set(a) == set(b) and all(tuple(a[k].shape) == tuple(b[k].shape) for k in a)
+    assert abs(gan.conv_flops_per_image(304, 304) / 1e9 - 177.2) < 0.1
+    cfg = {"Test": {"data_augmentation": [{"name": "LoadImaged"}, {"name": "LoadGraphAndFilterByRandomRadiusd", "image_resolutions": [[608, 304]],
+                                                                   "min_radius": [0.002]}]}}
+    assert gan_cli._resolution(cfg) == (608, 304, 0.002)
+    assert gan_cli._resolution({"Test": {}}) == (304, 304, 0.0)
+    assert Pipeline.buffer_sets(8) == 9 and Pipeline.buffer_sets(0) == 2
