@@ -38,6 +38,7 @@ class Pipeline:
         self._grow_locks = {}
         self._post_stream = None
         self._h2d_done = {}
+        self._csv_pool = None
         self.edge_cap = 24000      # rows reserved per sample in the pinned edge buffer (docker config: ~13 k)
 
     def _tensor(self, key, shape, dtype, pinned=False):
@@ -127,8 +128,10 @@ class Pipeline:
                     lab_h.copy_(lab, non_blocking=True)
                     img_h.copy_(img, non_blocking=True)
                     if csv:
-                        with cf.ThreadPoolExecutor(max_workers=self.host_threads) as ex:   # ctypes releases the GIL
-                            out["csv"] = list(ex.map(lambda i: graph_io.csv_bytes(he[offs[i]:offs[i + 1]]), range(n)))
+                        if self._csv_pool is None:                                          # one pool for the pipeline's lifetime
+                            self._csv_pool = cf.ThreadPoolExecutor(max_workers=self.host_threads)
+                        # ctypes releases the GIL; this worker blocks until the batch's text is complete
+                        out["csv"] = list(self._csv_pool.map(lambda i: graph_io.csv_bytes(he[offs[i]:offs[i + 1]]), range(n)))
                     stream.synchronize()
                     out["label_host"], out["image_host"] = lab_h.numpy(), img_h.numpy()
                     out["d2h_bytes"] = int(lab_h.numel() + img_h.numel())
