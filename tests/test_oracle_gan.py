@@ -41,8 +41,10 @@ def test_oracle_equals_reference_generator_with_shipped_checkpoint():
     assert not any(G.load_state_dict(ck["model"]))           # no missing / unexpected keys
     G.eval()
     x = torch.rand(2, 1, 64, 64, generator=torch.Generator().manual_seed(0))
+    xr = torch.rand(1, 1, 48, 80, generator=torch.Generator().manual_seed(1))      # non-square: pads / resampling per axis
     with torch.no_grad():
         assert torch.equal(G(x), go.generator_forward(ck["model"], x))
+        assert torch.equal(G(xr), go.generator_forward(ck["model"], xr))
         sd = go.random_state_dict(1)
         G.load_state_dict(sd, strict=False)                   # (the blur filters are buffers, not in the synthetic dict)
         assert torch.equal(G(x), go.generator_forward(sd, x))
