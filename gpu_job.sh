@@ -1,7 +1,15 @@
-# scratch script for `gpurun -- 'bash gpu_job.sh'`: full verification of the current build on one B200
+# scratch script for `gpurun -- 'bash gpu_job.sh'`
 mkdir -p gpurun_out
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
-timeout 900 python bench.py > gpurun_out/bench_line.json 2> gpurun_out/bench_err.log; tail -c 1200 gpurun_out/bench_line.json; tail -2 gpurun_out/bench_err.log
-timeout 200 python tools/gan_probe.py --batch 32 --reps 5 2>&1 | tail -2
-timeout 300 python tools/e2e_probe.py 2>&1 | tail -4
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
+nproc
+timeout 900 python -m pytest tests/test_growth_gpu.py tests/test_pipeline_gpu.py -m gpu -x -q > gpurun_out/pytest_growth.log 2>&1; tail -5 gpurun_out/pytest_growth.log
+OCTA_GROW_GRAPH=0 OCTA_BALL_ORDER=always timeout 300 python tools/pipe_probe.py 10 8 2>&1 | grep PROBE
+OCTA_GROW_GRAPH=1 OCTA_BALL_ORDER=always timeout 300 python tools/pipe_probe.py 10 8 2>&1 | grep PROBE
+OCTA_GROW_GRAPH=0 timeout 300 python tools/pipe_probe.py 10 8 2>&1 | grep PROBE
+timeout 300 python tools/pipe_probe.py 10 8 2>&1 | grep PROBE
+timeout 300 python tools/pipe_probe.py 10 12 2>&1 | grep PROBE
+timeout 300 python tools/pipe_probe.py 10 16 2>&1 | grep PROBE
+timeout 300 python tools/pipe_probe.py 10 12 16 2>&1 | grep PROBE
+timeout 300 python tools/pipe_probe.py 10 8 32 1 2>&1 | grep PROBE
+timeout 300 python tools/pipe_probe.py 10 12 32 1 2>&1 | grep PROBE
+OCTA_GROW_TIMING=1 timeout 300 python tools/grow_probe.py --batch 32 --reps 2 2>&1 | tail -8

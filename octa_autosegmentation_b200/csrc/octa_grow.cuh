@@ -42,7 +42,7 @@ struct __align__(16) ActDec {  // decision record of one dict entry the replay h
 
 struct GrowShape {
     int G, capN, capS, Nmax, pycap;
-    int exact_ball_order;   // 1: rebuild cKDTree's index permutation for the O2->CO2 insertion order (exact); 0: list-index order
+    int exact_ball_order;   // cKDTree's index permutation for the O2->CO2 insertion order: 2 = built on demand (exact, default), 1 = built every iteration (exact), 0 = list-index order instead (diagnostics)
     int commit_smem; // bytes of dynamic shared memory of k_commit (tree mirror + decision records)
 };
 
@@ -93,6 +93,9 @@ struct GrowDev {
     unsigned int* cbits;  // k_commit scratch, [g][4][capN/32]: dirty / arrival / inter / tag bitmaps when the tree does not fit in shared memory
     int *hitj, *hl, *ta, *seq;
     int *kd_idx, *kd_posL, *kd_posR, *kd_rank, *kd_nodes;
+    // on-demand exact ball order: per graph "k_kill left the arterial kill to k_kill_fix" + its T; per iteration parity the list
+    // of those graphs and its length
+    int *kd_flag, *kill_T, *kd_list, *kd_nflag;
     unsigned char* veto;
     long long* seqhash;
     long long* set_hash;

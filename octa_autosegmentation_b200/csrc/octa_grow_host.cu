@@ -22,6 +22,7 @@ namespace octa {
 
 void grow_timing_begin(cudaStream_t st);
 void grow_timing_report();
+bool grow_timing_enabled();
 struct GrowEvents { cudaEvent_t start, sinks, kd, killa; };
 void launch_begin(int dslot, const GrowShape& S, const IterP& P0, int n_sm, cudaStream_t st, cudaStream_t side, const GrowEvents& ev);
 void launch_iteration(int dslot, const GrowShape& S, const int commit_smem[2], const IterP& P, const IterP* Pnext, int n_sm, cudaStream_t st,
@@ -273,6 +274,7 @@ void carve(Carver& c, const GrowShape& S, GrowDev* D) {
     D->veto = c.take<unsigned char>(GS);
     D->kd_idx = c.take<int>(GS); D->kd_posL = c.take<int>(GS); D->kd_posR = c.take<int>(GS); D->kd_rank = c.take<int>(GS);
     D->kd_nodes = c.take<int>(GS);
+    D->kd_flag = c.take<int>(G); D->kill_T = c.take<int>(G); D->kd_list = c.take<int>(2 * G); D->kd_nflag = c.take<int>(2);
     D->seqhash = c.take<long long>(GS);
     D->set_hash = c.take<long long>(G * 2 * SET_TBL); D->set_key = c.take<int>(G * 2 * SET_TBL);
     D->err = c.take<int>(G); D->trace = c.take<int>(G * 4096 * 4); D->counters = c.take<long long>(G * 8); D->dbg = c.take<long long>(G * 8);
@@ -376,7 +378,21 @@ struct GrowCtx {
     // CTA that holds less shared memory lets other graphs' kernels (other loops in flight) share its SM.  A tree that outgrows the
     // prediction runs the same code on the global arrays (bit-identical), so this is a performance hint, never a result.
     std::vector<int> hist_nodes[2];
+    // The whole growth loop of a batch (launch_begin + every launch_iteration: ~15 kernels x 250 iterations on two streams with
+    // their event edges) captured ONCE as a CUDA graph and re-launched for every later batch of the same size: one
+    // cudaGraphLaunch instead of ~3 750 kernel launches per batch.  Iteration parameters travel by value inside the nodes (the
+    // schedule is a property of the context), the per-batch state (seeds -> stumps, RNG states) is uploaded before the launch.
+    // `cs` = k_commit's shared-memory size per (iteration, forest) baked into the nodes; the graph is re-captured when a tree
+    // of an earlier batch outgrew one of them (they are a performance hint: an outgrown mirror runs on the global arrays).
+    struct LoopGraph {
+        cudaGraphExec_t exec = nullptr;
+        int n_graphs = 0;
+        bool from_history = false;
+        std::vector<int> cs;
+        uint64_t kernels = 0;
+    } lg;
     ~GrowCtx() {
+        if (lg.exec) cudaGraphExecDestroy(lg.exec);
         release_slot(dslot);
         if (ev_done) cudaEventDestroy(ev_done);
         if (main) cudaStreamDestroy(main);
@@ -454,7 +470,7 @@ extern "C" int octa_grow_create(const OctaGrowConfig* cfg, int max_graphs, void*
     S.pycap = 2 * S.capN + 4 * 624;
     {
         const char* bo = getenv("OCTA_BALL_ORDER");      // "index" = list-index order (diagnostics); default exact
-        S.exact_ball_order = (bo && strcmp(bo, "index") == 0) ? 0 : 1;
+        S.exact_ball_order = (bo && strcmp(bo, "index") == 0) ? 0 : (bo && strcmp(bo, "always") == 0) ? 1 : 2;
     }
     S.commit_smem = 224 * 1024;                       // of the 227 KB a CTA may own on sm_100
     if (const char* e = getenv("OCTA_COMMIT_SMEM")) {  // tests: a small budget forces k_commit onto the global-memory tree view
@@ -591,6 +607,7 @@ static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, doub
         OCTA_CUDA_CHECK(cudaMemsetAsync(D.py_n, 0, 4 * G, st)); OCTA_CUDA_CHECK(cudaMemsetAsync(D.py_pos, 0, 4 * G, st));
         OCTA_CUDA_CHECK(cudaMemsetAsync(D.py_draws, 0, 8 * G, st)); OCTA_CUDA_CHECK(cudaMemsetAsync(D.counters, 0, 64 * G, st)); OCTA_CUDA_CHECK(cudaMemsetAsync(D.dbg, 0, 64 * G, st));
         OCTA_CUDA_CHECK(cudaMemsetAsync(D.err, 0, 4 * G, st));
+        OCTA_CUDA_CHECK(cudaMemsetAsync(D.kd_flag, 0, 4 * G, st)); OCTA_CUDA_CHECK(cudaMemsetAsync(D.kd_nflag, 0, 8, st));
         OCTA_CUDA_CHECK(cudaMemsetAsync(D.cbits, 0, sizeof(unsigned int) * G * 4 * ((S.capN + 31) / 32), st));
         OCTA_CUDA_CHECK(cudaMemsetAsync(D.trace, 0, sizeof(int) * G * 4096 * 4, st));
         OCTA_CUDA_CHECK(ctx->wait(st));      // the staging buffer is reused for the read-back
@@ -599,20 +616,52 @@ static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, doub
     OCTA_CUDA_CHECK(cudaEventRecord(ctx->e0, st));
     grow_timing_begin(st);
     if (upload_dev_table(ctx->dslot, D, st) != 0) { cudaGetLastError(); set_error("cudaMemcpyToSymbol(pointer table) failed"); return OCTA_E_CUDA; }
-    if (!ctx->sched.empty()) launch_begin(ctx->dslot, S, ctx->sched[0], ctx->n_sm, st, ctx->side, ctx->ev);
     const size_t n_it = ctx->sched.size();
     static const bool adapt = [] { const char* e = getenv("OCTA_COMMIT_ADAPT"); return !(e && e[0] == '0'); }();
-    for (size_t i = 0; i < n_it; ++i) {
-        int cs[2] = {S.commit_smem, S.commit_smem};
-        for (int f = 0; f < 2 && adapt; ++f) {
-            const std::vector<int>& h = ctx->hist_nodes[f];
-            if (h.size() != n_it || n_it > 4096) continue;             // no history for this schedule yet: full mirror
-            const size_t n = (size_t)h[i > 0 ? i - 1 : 0] * 9 / 8 + 256;  // nodes before this call, +12 % and 256 of margin
-            const size_t need = ((n * 17 + 3) & ~(size_t)3) + 16 * ((n + 31) >> 5) + 64;   // k_commit's own formula
-            const size_t want = (need + 1023) & ~(size_t)1023;
-            cs[f] = (int)std::min<size_t>((size_t)S.commit_smem, std::max<size_t>(want, 8 * 1024));
+    // k_commit's shared-memory size per (iteration, forest): the mirror of the tree it will see, from the envelope of the
+    // context's previous batches (+12 % and 256 nodes of margin); `raw` = the same without margin
+    auto mirror_bytes = [](size_t n) { return ((n * 17 + 3) & ~(size_t)3) + 16 * ((n + 31) >> 5) + 64; };   // k_commit's own formula
+    bool have_hist = adapt && n_it > 0 && n_it <= 4096 && ctx->hist_nodes[0].size() == n_it && ctx->hist_nodes[1].size() == n_it;
+    std::vector<int> cs_all(2 * n_it, S.commit_smem), cs_raw(2 * n_it, 0);
+    for (size_t i = 0; i < n_it && have_hist; ++i)
+        for (int f = 0; f < 2; ++f) {
+            const size_t nb = (size_t)ctx->hist_nodes[f][i > 0 ? i - 1 : 0];                  // nodes before this call
+            const size_t want = (mirror_bytes(nb * 9 / 8 + 256) + 1023) & ~(size_t)1023;
+            cs_all[2 * i + f] = (int)std::min<size_t>((size_t)S.commit_smem, std::max<size_t>(want, 8 * 1024));
+            cs_raw[2 * i + f] = (int)std::min<size_t>((size_t)S.commit_smem, mirror_bytes(nb));
         }
-        launch_iteration(ctx->dslot, S, cs, ctx->sched[i], i + 1 < n_it ? &ctx->sched[i + 1] : nullptr, ctx->n_sm, st, ctx->side, ctx->ev);
+    auto issue_loop = [&](const std::vector<int>& cs) {
+        launch_begin(ctx->dslot, S, ctx->sched[0], ctx->n_sm, st, ctx->side, ctx->ev);
+        for (size_t i = 0; i < n_it; ++i)
+            launch_iteration(ctx->dslot, S, &cs[2 * i], ctx->sched[i], i + 1 < n_it ? &ctx->sched[i + 1] : nullptr, ctx->n_sm, st, ctx->side, ctx->ev);
+    };
+    // OCTA_GROW_GRAPH: 0 = stream launches, 1 (default) = CUDA graph from the context's second batch on (the first one also
+    // establishes the mirror sizes), 2 = CUDA graph always
+    static const int graph_mode = [] { const char* e = getenv("OCTA_GROW_GRAPH"); return e ? atoi(e) : 1; }();
+    const bool use_graph = n_it > 0 && !grow_timing_enabled() && (graph_mode >= 2 || (graph_mode == 1 && have_hist));
+    if (use_graph) {
+        GrowCtx::LoopGraph& lg = ctx->lg;
+        bool stale = !lg.exec || lg.n_graphs != n_graphs || lg.cs.size() != cs_all.size() || (have_hist && !lg.from_history);
+        for (size_t q = 0; q < cs_all.size() && !stale; ++q) stale = cs_raw[q] > lg.cs[q];    // a tree outgrew its captured mirror
+        if (stale) {
+            if (lg.exec) { cudaGraphExecDestroy(lg.exec); lg.exec = nullptr; }
+            const uint64_t l0 = g_launches.load();
+            OCTA_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            issue_loop(cs_all);
+            cudaGraph_t graph = nullptr;
+            cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            const uint64_t l1 = g_launches.load();
+            g_launches.fetch_sub(l1 - l0);               // captured, not launched
+            if (ce != cudaSuccess || !graph) { cudaGetLastError(); set_error("capture of the growth loop failed: %s", cudaGetErrorString(ce)); return OCTA_E_CUDA; }
+            ce = cudaGraphInstantiate(&lg.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) { lg.exec = nullptr; cudaGetLastError(); set_error("cudaGraphInstantiate(growth loop) failed: %s", cudaGetErrorString(ce)); return OCTA_E_CUDA; }
+            lg.n_graphs = n_graphs; lg.from_history = have_hist; lg.cs = cs_all; lg.kernels = l1 - l0;
+        }
+        OCTA_CUDA_CHECK(cudaGraphLaunch(lg.exec, st));
+        count_launch((int)lg.kernels);
+    } else if (n_it > 0) {
+        issue_loop(cs_all);
     }
     OCTA_CUDA_CHECK(cudaEventRecord(ctx->e1, st));
     tw[3] = wall();

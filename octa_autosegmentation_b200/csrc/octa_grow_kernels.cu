@@ -21,6 +21,7 @@
 #include "octa_grow.cuh"
 #include "octa_grow_math.cuh"
 #include "octa_kdorder_par.cuh"
+#include "octa_pyset.cuh"
 
 namespace octa {
 
@@ -1126,22 +1127,104 @@ __global__ void __launch_bounds__(512) k_commit(int dslot, GrowShape S, IterP P,
 // ------------------------------------------------------------------------------------------
 // k_kill: one CTA per graph.  f = 0: satisfied O2 sinks -> CO2 sources (set order); f = 1: CO2 removal
 // ------------------------------------------------------------------------------------------
-__device__ void pyset_insert_clean(long long* th, int* tk, size_t mask, int key, long long hash) {
-    size_t perturb = (size_t)hash, i = (size_t)hash & mask;
-    while (true) {
-        size_t e = i;
-        if (tk[e] < 0) { tk[e] = key; th[e] = hash; return; }
-        if (i + 9 <= mask) {
-            for (int j = 0; j < 9; ++j) { ++e; if (tk[e] < 0) { tk[e] = key; th[e] = hash; return; } }
+// Stable removal of every hit from the sink list f (element_mesh.py:195-211) + per-iteration trace
+__device__ void kill_compact(const GrowDev& D, const GrowShape& S, const IterP& P, int f, int g, int Sn, bool removed) {
+    const int tid = threadIdx.x;
+    const size_t sb = (size_t)g * S.capS;
+    double* sx = D.sx[f] + sb; double* sy = D.sy[f] + sb; double* sz = D.sz[f] + sb;
+    const int* hitj = D.hitj + sb;
+    if (removed) {
+        int w = 0;
+        for (int base = 0; base < Sn; base += blockDim.x) {
+            const int i = base + tid;
+            int keep = 0;
+            double px = 0, py = 0, pz = 0;
+            if (i < Sn) { keep = hitj[i] < 0; px = sx[i]; py = sy[i]; pz = sz[i]; }
+            int total;
+            const int incl = block_scan_incl(keep, &total);
+            if (keep) { const int o = w + incl - 1; sx[o] = px; sy[o] = py; sz[o] = pz; }
+            w += total;
+            __syncthreads();
         }
-        perturb >>= 5;
-        i = (i * 5 + 1 + perturb) & mask;
+        if (tid == 0) D.n_s[f][g] = w;
+    }
+    __syncthreads();
+    if (tid == 0 && D.trace && P.iter < 4096) {       // (the sampler of the next iteration may already run beside the venous phase)
+        int* tr = D.trace + ((size_t)g * 4096 + P.iter) * 4;
+        if (f == 0) { tr[0] = D.n_nodes[0][g]; tr[1] = D.n_s[0][g]; }
+        else { tr[2] = D.n_nodes[1][g]; tr[3] = D.n_s[1][g]; }
     }
 }
 
+// O2 -> CO2 conversion of the T sinks ta[0..T) (hit, not vetoed): insertion sequence by (first new node that hits it, rank inside
+// the ball) -- the order of `for node in new_nodes: for oxy in ball(node)` --, CPython set emulation, append in slot order.
+// kdrank == nullptr: list-index order inside a ball.  Returns true (on every thread) if DETECT found the result order-sensitive;
+// nothing has been appended then.
+template <bool DETECT>
+__device__ bool kill_convert(const GrowDev& D, const GrowShape& S, int g, int T, const int* kdrank, KillShared* ks) {
+    const int tid = threadIdx.x;
+    const size_t sb = (size_t)g * S.capS;
+    const double* sx = D.sx[0] + sb; const double* sy = D.sy[0] + sb; const double* sz = D.sz[0] + sb;
+    const int* hitj = D.hitj + sb;
+    const int* ta = D.ta + sb;
+    int* seq = D.seq + sb;
+    for (int q = tid; q < T; q += blockDim.x) {
+        const int i = ta[q];
+        const int ji = hitj[i];
+        const int ki = kdrank ? kdrank[i] : i;
+        int rank = 0;
+        for (int q2 = 0; q2 < T; ++q2) {
+            const int i2 = ta[q2];
+            const int j2 = hitj[i2];
+            const int k2 = kdrank ? kdrank[i2] : i2;
+            rank += (j2 < ji) || (j2 == ji && k2 < ki);
+        }
+        seq[rank] = i;
+        D.seqhash[sb + rank] = py_hash_tuple3(sx[i], sy[i], sz[i]);   // CPython hash of the sink tuple, in parallel
+    }
+    for (int i = tid; i < 8; i += blockDim.x) { ks->tk[0][i] = -1; ks->th[0][i] = 0; }
+    __syncthreads();
+    long long* gth = D.set_hash + (size_t)g * 2 * SET_TBL;
+    int* gtk = D.set_key + (size_t)g * 2 * SET_TBL;
+    if (tid == 0) {
+        PySetDev ps;
+        ps.sh = ks; ps.gth = gth; ps.gtk = gtk;
+        ps.init();
+        const bool flagged = pyset_run<DETECT>(ps, seq, D.seqhash + sb, T, hitj, gtk);
+        ks->tabinfo[0] = ps.cur; ks->tabinfo[1] = (int)ps.mask; ks->tabinfo[2] = ps.err; ks->tabinfo[3] = flagged ? 1 : 0;
+        if (ps.err) D.err[g] = ps.err;
+    }
+    __syncthreads();
+    if (ks->tabinfo[3]) return true;
+    // append to the CO2 list in slot order (all threads: stable compaction of the occupied slots)
+    if (!ks->tabinfo[2] && T > 0) {
+        const int cur = ks->tabinfo[0], nslots = ks->tabinfo[1] + 1;
+        const int* curk = cur < 2 ? ks->tk[cur] : gtk + (size_t)(cur - 2) * SET_TBL;
+        int nco2 = D.n_s[1][g];
+        for (int base = 0; base < nslots; base += blockDim.x) {
+            const int zslot = base + tid;
+            const int key = zslot < nslots ? curk[zslot] : -1;
+            int total;
+            const int incl = block_scan_incl(key >= 0, &total);
+            if (key >= 0) {
+                const int o = nco2 + incl - 1;
+                if (o < S.capS) { D.sx[1][sb + o] = sx[key]; D.sy[1][sb + o] = sy[key]; D.sz[1][sb + o] = sz[key]; }
+            }
+            nco2 += total;
+        }
+        if (tid == 0) { if (nco2 > S.capS) { D.err[g] = 2; nco2 = S.capS; } D.n_s[1][g] = nco2; }
+    }
+    __syncthreads();
+    return false;
+}
+
+// S.exact_ball_order: 0 = list-index order inside a ball (diagnostics), 1 = cKDTree order, permutation built for every graph in
+// every iteration (k_kdbuild on the side stream), 2 = cKDTree order ON DEMAND: this kernel runs the conversion in list-index
+// order with the order-sensitivity test of pyset_run; a graph whose result could depend on the order is put on the iteration's
+// work list instead of being finished, k_kdbuild builds the permutation of the listed graphs only and k_kill_fix finishes them.
 __global__ void __launch_bounds__(1024) k_kill(int dslot, GrowShape S, IterP P, int f) {
     const GrowDev& D = c_dev[dslot];
-    __shared__ double nxs[512], nys[512], nzs[512];
+    __shared__ KillShared ks;
     const int g = blockIdx.x, tid = threadIdx.x;
     if (D.err[g]) return;
     const size_t sb = (size_t)g * S.capS, nb = (size_t)g * S.capN;
@@ -1156,13 +1239,13 @@ __global__ void __launch_bounds__(1024) k_kill(int dslot, GrowShape S, IterP P, 
         for (int base = 0; base < nn; base += 512) {
             const int cntn = nn - base < 512 ? nn - base : 512;
             __syncthreads();
-            for (int j = tid; j < cntn; j += blockDim.x) { nxs[j] = D.nx[f][nb + n0 + base + j]; nys[j] = D.ny[f][nb + n0 + base + j]; nzs[j] = D.nz[f][nb + n0 + base + j]; }
+            for (int j = tid; j < cntn; j += blockDim.x) { ks.nxs[j] = D.nx[f][nb + n0 + base + j]; ks.nys[j] = D.ny[f][nb + n0 + base + j]; ks.nzs[j] = D.nz[f][nb + n0 + base + j]; }
             __syncthreads();
             for (int i = tid; i < Sn; i += blockDim.x) {
                 if (hitj[i] >= 0) continue;
                 const double px = sx[i], py = sy[i], pz = sz[i];
                 for (int j = 0; j < cntn; ++j)
-                    if (dist2(px, py, pz, nxs[j], nys[j], nzs[j]) <= epsk2) { hitj[i] = base + j; break; }   // cKDTree ball: d^2 <= r^2
+                    if (dist2(px, py, pz, ks.nxs[j], ks.nys[j], ks.nzs[j]) <= epsk2) { hitj[i] = base + j; break; }   // cKDTree ball: d^2 <= r^2
             }
         }
         __syncthreads();
@@ -1186,18 +1269,15 @@ __global__ void __launch_bounds__(1024) k_kill(int dslot, GrowShape S, IterP P, 
             for (int hb = 0; hb < H; hb += 512) {
                 const int cnth = H - hb < 512 ? H - hb : 512;
                 __syncthreads();
-                for (int k = tid; k < cnth; k += blockDim.x) { const int i = hl[hb + k]; nxs[k] = sx[i]; nys[k] = sy[i]; nzs[k] = sz[i]; veto[hb + k] = 0; }
+                for (int k = tid; k < cnth; k += blockDim.x) { const int i = hl[hb + k]; ks.nxs[k] = sx[i]; ks.nys[k] = sy[i]; ks.nzs[k] = sz[i]; veto[hb + k] = 0; }
                 __syncthreads();
                 for (int j = tid; j < Vn; j += blockDim.x) {
                     const double vx = D.nx[1][nb + j], vy = D.ny[1][nb + j], vz = D.nz[1][nb + j];
                     for (int k = 0; k < cnth; ++k)
-                        if (within_sqrt(dist2(vx, vy, vz, nxs[k], nys[k], nzs[k]), P.eps_k, epsk2)) veto[hb + k] = 1;
+                        if (within_sqrt(dist2(vx, vy, vz, ks.nxs[k], ks.nys[k], ks.nzs[k]), P.eps_k, epsk2)) veto[hb + k] = 1;
                 }
             }
             __syncthreads();
-            // insertion sequence: by (first new node that hits it, list index) -- the order of
-            // `for node in new_nodes: for oxy in ball(node)` with index-ordered ball results
-            int* seq = D.seq + sb;
             int T = 0;
             for (int base = 0; base < H; base += blockDim.x) {
                 const int h = base + tid;
@@ -1208,127 +1288,38 @@ __global__ void __launch_bounds__(1024) k_kill(int dslot, GrowShape S, IterP P, 
                 T += total;
             }
             __syncthreads();
-            const int* ta = D.ta + sb;
             // Within one ball the reference receives the hits in cKDTree order (ascending position in tree.indices,
-            // element_mesh.py:136-137).  The permutation is rebuilt exactly (octa_kdorder_par.cuh) whenever the
-            // sink list changes (k_kdbuild, overlapped with the arterial growth kernels on a second stream).
-            const int* kdrank = S.exact_ball_order ? D.kd_rank + sb : nullptr;   // built by k_kdbuild on the side stream
-            for (int q = tid; q < T; q += blockDim.x) {
-                const int i = ta[q];
-                const int ji = hitj[i];
-                const int ki = kdrank ? kdrank[i] : i;
-                int rank = 0;
-                for (int q2 = 0; q2 < T; ++q2) {
-                    const int i2 = ta[q2];
-                    const int j2 = hitj[i2];
-                    const int k2 = kdrank ? kdrank[i2] : i2;
-                    rank += (j2 < ji) || (j2 == ji && k2 < ki);
-                }
-                seq[rank] = i;
-                D.seqhash[sb + rank] = py_hash_tuple3(sx[i], sy[i], sz[i]);   // CPython hash of the sink tuple, in parallel
-            }
-            __syncthreads();
-            // CPython set emulation (Objects/setobject.c, 3.12) -> iteration order = slot order.  Tables of up to
-            // SM_TBL slots live in shared memory (the usual case: tens of insertions); larger ones spill to global.
-            constexpr int SM_TBL = 1024;
-            __shared__ long long s_th[2][SM_TBL];
-            __shared__ int s_tk[2][SM_TBL];
-            __shared__ int s_tabinfo[3];                 // which table holds the result (0/1 smem, 2/3 global), mask, err
-            long long* gth = D.set_hash + (size_t)g * 2 * SET_TBL;
-            int* gtk = D.set_key + (size_t)g * 2 * SET_TBL;
-            for (int i = tid; i < 8; i += blockDim.x) { s_tk[0][i] = -1; s_th[0][i] = 0; }
-            __syncthreads();
-            if (tid == 0) {
-                size_t mask = 7, fill = 0, used = 0;
-                int cur = 0;                             // 0/1: shared tables, 2/3: global tables
-                auto tabh = [&](int t) -> long long* { return t < 2 ? s_th[t] : gth + (size_t)(t - 2) * SET_TBL; };
-                auto tabk = [&](int t) -> int* { return t < 2 ? s_tk[t] : gtk + (size_t)(t - 2) * SET_TBL; };
-                long long* curh = tabh(0); int* curk = tabk(0);
-                int err = 0;
-                const long long* sh = D.seqhash + sb;
-                for (int q = 0; q < T && !err; ++q) {
-                    const int key = seq[q];
-                    const long long hash = sh[q];
-                    size_t perturb = (size_t)hash, i = (size_t)hash & mask;
-                    bool done = false;
-                    while (!done) {
-                        size_t e = i;
-                        int probes = (i + 9 <= mask) ? 9 : 0;
-                        do {
-                            if (curk[e] < 0) {
-                                curk[e] = key; curh[e] = hash;
-                                ++fill; ++used;
-                                if (fill * 5 >= mask * 3) {
-                                    const size_t minused = used > 50000 ? used * 2 : used * 4;
-                                    size_t newsize = 8;
-                                    while (newsize <= minused) newsize <<= 1;
-                                    if (newsize > (size_t)SET_TBL) { err = 5; done = true; break; }
-                                    const int alt = newsize <= (size_t)SM_TBL ? (cur == 0 ? 1 : 0) : (cur == 2 ? 3 : 2);
-                                    long long* alth = tabh(alt); int* altk = tabk(alt);
-                                    for (size_t z = 0; z < newsize; ++z) { altk[z] = -1; alth[z] = 0; }
-                                    for (size_t z = 0; z <= mask; ++z)
-                                        if (curk[z] >= 0) pyset_insert_clean(alth, altk, newsize - 1, curk[z], curh[z]);
-                                    cur = alt; curh = alth; curk = altk;
-                                    mask = newsize - 1;
-                                    fill = used;
-                                }
-                                done = true;
-                                break;
-                            }
-                            if (curh[e] == hash && curk[e] == key) { done = true; break; }
-                            ++e;
-                        } while (probes--);
-                        if (done) break;
-                        perturb >>= 5;
-                        i = (i * 5 + 1 + perturb) & mask;
+            // element_mesh.py:136-137).
+            if (S.exact_ball_order == 2) {
+                if (kill_convert<true>(D, S, g, T, nullptr, &ks)) {
+                    if (tid == 0) {          // finished by k_kdbuild + k_kill_fix
+                        D.kill_T[g] = T;
+                        D.kd_flag[g] = 1;
+                        D.kd_list[(P.iter & 1) * S.G + atomicAdd(&D.kd_nflag[P.iter & 1], 1)] = g;
+                        if (D.dbg) D.dbg[g * 8 + 0] += 1;     // (diagnostics: graph-iterations that needed the exact order)
                     }
+                    return;
                 }
-                s_tabinfo[0] = cur; s_tabinfo[1] = (int)mask; s_tabinfo[2] = err;
-                if (err) D.err[g] = err;
+            } else {
+                kill_convert<false>(D, S, g, T, S.exact_ball_order ? D.kd_rank + sb : nullptr, &ks);
             }
-            __syncthreads();
-            // append to the CO2 list in slot order (all threads: stable compaction of the occupied slots)
-            if (!s_tabinfo[2] && T > 0) {
-                const int cur = s_tabinfo[0], nslots = s_tabinfo[1] + 1;
-                const int* curk = cur < 2 ? s_tk[cur] : gtk + (size_t)(cur - 2) * SET_TBL;
-                int nco2 = D.n_s[1][g];
-                const size_t cb = (size_t)g * S.capS;
-                for (int base = 0; base < nslots; base += blockDim.x) {
-                    const int zslot = base + tid;
-                    const int key = zslot < nslots ? curk[zslot] : -1;
-                    int total;
-                    const int incl = block_scan_incl(key >= 0, &total);
-                    if (key >= 0) {
-                        const int o = nco2 + incl - 1;
-                        if (o < S.capS) { D.sx[1][cb + o] = sx[key]; D.sy[1][cb + o] = sy[key]; D.sz[1][cb + o] = sz[key]; }
-                    }
-                    nco2 += total;
-                }
-                if (tid == 0) { if (nco2 > S.capS) { D.err[g] = 2; nco2 = S.capS; } D.n_s[1][g] = nco2; }
-            }
-            __syncthreads();
         }
-        // stable removal of every hit from this sink list (element_mesh.py:195-211)
-        int w = 0;
-        for (int base = 0; base < Sn; base += blockDim.x) {
-            const int i = base + tid;
-            int keep = 0;
-            double px = 0, py = 0, pz = 0;
-            if (i < Sn) { keep = hitj[i] < 0; px = sx[i]; py = sy[i]; pz = sz[i]; }
-            int total;
-            const int incl = block_scan_incl(keep, &total);
-            if (keep) { const int o = w + incl - 1; sx[o] = px; sy[o] = py; sz[o] = pz; }
-            w += total;
-            __syncthreads();
-        }
-        if (tid == 0) D.n_s[f][g] = w;
     }
+    kill_compact(D, S, P, f, g, Sn, nn > 0);
+}
+
+// finish the arterial kill of the graphs k_kill put on the work list: same conversion with the exact order inside every ball
+__global__ void __launch_bounds__(1024) k_kill_fix(int dslot, GrowShape S, IterP P) {
+    const GrowDev& D = c_dev[dslot];
+    __shared__ KillShared ks;
+    const int g = blockIdx.x;
+    if (g == 0 && threadIdx.x == 0) D.kd_nflag[(P.iter + 1) & 1] = 0;      // the next iteration's list starts empty
+    if (D.err[g] || !D.kd_flag[g]) return;
     __syncthreads();
-    if (tid == 0 && D.trace && P.iter < 4096) {       // (the sampler of the next iteration may already run beside the venous phase)
-        int* tr = D.trace + ((size_t)g * 4096 + P.iter) * 4;
-        if (f == 0) { tr[0] = D.n_nodes[0][g]; tr[1] = D.n_s[0][g]; }
-        else { tr[2] = D.n_nodes[1][g]; tr[3] = D.n_s[1][g]; }
-    }
+    if (threadIdx.x == 0) D.kd_flag[g] = 0;
+    const size_t sb = (size_t)g * S.capS;
+    kill_convert<false>(D, S, g, D.kill_T[g], D.kd_rank + sb, &ks);
+    kill_compact(D, S, P, 0, g, D.n_s[0][g], true);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1336,13 +1327,8 @@ __global__ void __launch_bounds__(1024) k_kill(int dslot, GrowShape S, IterP P, 
 // (= the tree the reference queries in step 3, greenhouse.py:101-102).  Runs on a side stream, concurrently with
 // the arterial growth kernels, which do not modify the sink list.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_kdbuild(int dslot, GrowShape S, int smem_bytes) {
-    const GrowDev& D = c_dev[dslot];
-    extern __shared__ __align__(16) char s_kd[];
-    __shared__ int s_ws[kdpar::WS_INTS];
-    __shared__ double s_wd[kdpar::WD_DOUBLES];
-    const int g = blockIdx.x, tid = threadIdx.x;
-    if (D.err[g]) return;
+__device__ void kdbuild_graph(const GrowDev& D, const GrowShape& S, int smem_bytes, int g, char* s_kd, int* s_ws, double* s_wd) {
+    const int tid = threadIdx.x;
     const size_t sb = (size_t)g * S.capS;
     const int Sn = D.n_s[0][g];
     int* rk = D.kd_rank + sb;
@@ -1356,6 +1342,29 @@ __global__ void __launch_bounds__(1024) k_kdbuild(int dslot, GrowShape S, int sm
                                D.kd_nodes + sb, D.kd_nodes + sb + S.capS / 2, s_ws, s_wd);
     __syncthreads();
     for (int i = tid; i < Sn; i += blockDim.x) rk[kidx[i]] = i;
+}
+
+__global__ void __launch_bounds__(1024) k_kdbuild(int dslot, GrowShape S, int smem_bytes) {
+    const GrowDev& D = c_dev[dslot];
+    extern __shared__ __align__(16) char s_kd[];
+    __shared__ int s_ws[kdpar::WS_INTS];
+    __shared__ double s_wd[kdpar::WD_DOUBLES];
+    const int g = blockIdx.x;
+    if (D.err[g]) return;
+    kdbuild_graph(D, S, smem_bytes, g, s_kd, s_ws, s_wd);
+}
+
+// on-demand variant (S.exact_ball_order == 2): the CTAs walk the work list k_kill filled in this iteration
+__global__ void __launch_bounds__(1024) k_kdbuild_list(int dslot, GrowShape S, int smem_bytes, int parity) {
+    const GrowDev& D = c_dev[dslot];
+    extern __shared__ __align__(16) char s_kd[];
+    __shared__ int s_ws[kdpar::WS_INTS];
+    __shared__ double s_wd[kdpar::WD_DOUBLES];
+    const int n = D.kd_nflag[parity];
+    for (int q = blockIdx.x; q < n; q += gridDim.x) {
+        kdbuild_graph(D, S, smem_bytes, D.kd_list[parity * S.G + q], s_kd, s_ws, s_wd);
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1375,6 +1384,7 @@ constexpr int KD_SMEM_BYTES = 208 * 1024;        // + ~17 KB static: scan / redu
 int prepare_kernels(const GrowShape& S) {
     cudaError_t e = cudaFuncSetAttribute(k_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)commit_smem_bytes(S));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_kdbuild, cudaFuncAttributeMaxDynamicSharedMemorySize, KD_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_kdbuild_list, cudaFuncAttributeMaxDynamicSharedMemorySize, KD_SMEM_BYTES);
     // Diagnostics (OCTA_CARVEOUT=1): every growth kernel asks for the largest shared-memory carve-out, so that CTAs of different
     // kernels never wait for an SM to change its L1 / shared split.  Measured SLOWER (462 -> 443 graphs/s): the gather kernels
     // (k_assign, k_sink_tests, k_kill) lose their L1, which costs more than the extra co-residency gains.  Off by default.
@@ -1406,13 +1416,18 @@ Timing g_timing[2];        // [0] main stream, [1] side stream
 bool g_timing_on = false, g_timing_init = false;
 const char* const kTimingNames[] = {"start", "k_prepare", "k_sink_tests", "k_sink_greedy", "k_assign[a]", "k_group[a]", "k_eval[a]",
                                     "k_commit[a]", "k_kill[a]", "k_assign[v]", "k_group[v]", "k_eval[v]", "k_commit[v]", "k_kill[v]",
-                                    "k_kdbuild", "(side waits)"};
+                                    "k_kdbuild", "(side waits) / k_kill_fix"};
 constexpr int N_KINDS = 16;
 inline void tick(cudaStream_t st, int k, int which = 0) { if (g_timing_on) cudaEventRecord(g_timing[which].next(k), st); }
 }  // namespace
 
-void grow_timing_begin(cudaStream_t st) {
+bool grow_timing_enabled() {
     if (!g_timing_init) { g_timing_init = true; const char* e = getenv("OCTA_GROW_TIMING"); g_timing_on = e && e[0] == '1'; }
+    return g_timing_on;
+}
+
+void grow_timing_begin(cudaStream_t st) {
+    grow_timing_enabled();
     g_timing[0].used = g_timing[1].used = 0;
     tick(st, 0);
 }
@@ -1454,7 +1469,7 @@ void launch_sampling(int dslot, const GrowShape& S, const IterP& P, int n_sm, cu
     tick(side, 3, 1);
     cudaEventRecord(ev.sinks, side);
     count_launch(3);
-    if (S.exact_ball_order) {
+    if (S.exact_ball_order == 1) {
         k_kdbuild<<<S.G, 1024, KD_SMEM_BYTES, side>>>(dslot, S, KD_SMEM_BYTES);
         tick(side, 14, 1);
         count_launch(1);
@@ -1496,6 +1511,16 @@ void launch_iteration(int dslot, const GrowShape& S, const int commit_smem[2], c
         k_kill<<<S.G, kill_threads, 0, st>>>(dslot, S, P, f);
         tick(st, 8 + 5 * f);
         count_launch(5);
+        if (f == 0 && S.exact_ball_order == 2) {
+            // exact cKDTree order on demand: permutation + conversion redone for the graphs k_kill listed (about a third of the
+            // graph-iterations of the docker config); the CTAs of k_kdbuild_list own a whole SM's shared memory, so the launch is
+            // half a batch wide and walks the list
+            k_kdbuild_list<<<(S.G + 1) / 2, 1024, KD_SMEM_BYTES, st>>>(dslot, S, KD_SMEM_BYTES, P.iter & 1);
+            tick(st, 14);
+            k_kill_fix<<<S.G, kill_threads, 0, st>>>(dslot, S, P);
+            tick(st, 15);
+            count_launch(2);
+        }
         if (f == 0) {
             cudaEventRecord(ev.killa, st);
             if (Pnext) {

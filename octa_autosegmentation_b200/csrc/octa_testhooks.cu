@@ -10,6 +10,32 @@ extern "C" int octa_test_eig3(const double* cov9, double* w3, double* v9) {
 
 extern "C" int64_t octa_test_hash_tuple3(const double* p) { return octa::py_hash_tuple3(p[0], p[1], p[2]); }
 
+#include <vector>
+#include "octa_pyset.cuh"
+// The set emulation + order-sensitivity test k_kill runs (host build of the same code).  xyz: T sink tuples in insertion order,
+// ball[q]: id of the ball (new node) that inserts tuple q (non-decreasing).  order_out: iteration order of the resulting set
+// (indices into xyz); returns 1 if `detect` and the result was flagged as possibly depending on the order inside a ball
+// (order_out is then not filled), 0 otherwise, < 0 on error.
+extern "C" int octa_test_pyset(const double* xyz, const int* ball, int T, int detect, int* order_out, int* n_out) {
+    static octa::KillShared ks;
+    std::vector<long long> gth((size_t)2 * octa::SET_TBL), sh(T);
+    std::vector<int> gtk((size_t)2 * octa::SET_TBL), seq(T);
+    for (int q = 0; q < T; ++q) { seq[q] = q; sh[q] = octa::py_hash_tuple3(xyz[3 * q], xyz[3 * q + 1], xyz[3 * q + 2]); }
+    for (int i = 0; i < 8; ++i) { ks.tk[0][i] = -1; ks.th[0][i] = 0; }
+    octa::PySetDev ps;
+    ps.sh = &ks; ps.gth = gth.data(); ps.gtk = gtk.data();
+    ps.init();
+    const bool flagged = detect ? octa::pyset_run<true>(ps, seq.data(), sh.data(), T, ball, gtk.data())
+                                : octa::pyset_run<false>(ps, seq.data(), sh.data(), T, ball, gtk.data());
+    if (ps.err) return -ps.err;
+    if (flagged) return 1;
+    int n = 0;
+    const int* ck = ps.tabk(ps.cur);
+    for (size_t z = 0; z <= ps.mask; ++z) if (ck[z] >= 0) order_out[n++] = ck[z];
+    *n_out = n;
+    return 0;
+}
+
 extern "C" int octa_test_eig3_debug(const double* cov9, double* w3, double* v9, double* dbg36) {
     return octa::eig3::dgeev3_sym(cov9, w3, v9, dbg36);
 }

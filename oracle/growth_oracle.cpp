@@ -73,7 +73,8 @@ typedef void (*og_trace_hook)(int t, long n_art, long n_oxy, long n_ven, long n_
 struct OGStats {
     long n_art_nodes, n_ven_nodes, n_oxy_left, n_co2_left, py_draws, np_u32, nn_queries, ball_queries,
         bifurcations, sprouts, elongations, walk_steps, sum_A, sum_M, sum_P, sum_S,
-        multi_balls, reordered_balls, interacting_groups, kd_builds, inter_evals, inter_r1_changed, max_dict, max_list;
+        multi_balls, reordered_balls, interacting_groups, kd_builds, inter_evals, inter_r1_changed, max_dict, max_list,
+        flag_iters_cons, flag_iters_perm, diff_iters, perm_groups;   /* ball-order sensitivity instrumentation */
 };
 }
 
@@ -348,6 +349,17 @@ struct PySet {
         for (const Entry& en : table) if (en.key >= 0) f(en.key);
     }
 };
+
+/* instrumentation: does the table grow before the LAST key of this group is inserted (index order)? */
+static bool trial_mid_resize(const PySet& before, const std::vector<int>& fresh, const double* xyz) {
+    PySet t = before;
+    for (size_t q = 0; q + 1 < fresh.size(); ++q) {
+        bool r = false;
+        t.add(fresh[q], py_hash_tuple3(&xyz[3 * fresh[q]]), nullptr, &r);
+        if (r) return true;
+    }
+    return false;
+}
 
 /* ------------------------------------------------------------------ cKDTree index order ----- */
 struct KdOrder {
@@ -1001,7 +1013,7 @@ struct Sim {
                 if (!new_nodes.empty()) {
                     std::vector<char> to_remove(oxy.size(), 0);
                     PySet to_add, shadow; /* shadow: list-index order, instrumentation only */
-                    bool kd_built = false;
+                    bool kd_built = false, it_cons = false, it_perm = false;
                     std::vector<int> hidx;
                     for (int nid : new_nodes) {
                         oxy.ball(F[0].nodes[nid].pos, eps_k, hits);
@@ -1027,12 +1039,14 @@ struct Sim {
                         {
                             std::vector<std::vector<size_t>> ex;
                             std::vector<long> fin;
+                            std::vector<int> fresh;
                             bool resized = false;
+                            const PySet before = shadow;
                             for (int h : hidx)
                                 if (cfg.venous && node_mesh[1].nearest_within(&oxy.xyz[3 * h], eps_k) < 0) {
                                     ex.emplace_back();
                                     long slot = shadow.add(h, py_hash_tuple3(&oxy.xyz[3 * h]), &ex.back(), &resized);
-                                    if (slot < 0) ex.pop_back(); else fin.push_back(slot);
+                                    if (slot < 0) ex.pop_back(); else { fin.push_back(slot); fresh.push_back(h); }
                                 }
                             bool inter = false;
                             if (fin.size() > 1) {
@@ -1042,8 +1056,34 @@ struct Sim {
                                         if (a != b)
                                             for (size_t sl : ex[b]) if ((long)sl == fin[a]) { inter = true; break; }
                             }
-                            if (inter) ++st.interacting_groups;
+                            if (inter) {
+                                ++st.interacting_groups;
+                                it_cons = true;
+                                /* permutation closure: does ANY order of this ball's fresh keys change the table? */
+                                bool differs = fresh.size() > 4 || (resized && trial_mid_resize(before, fresh, oxy.xyz.data()));
+                                if (!differs) {
+                                    ++st.perm_groups;
+                                    std::vector<int> perm = fresh;
+                                    std::sort(perm.begin(), perm.end());
+                                    do {
+                                        PySet trial = before;
+                                        for (int h : perm) trial.add(h, py_hash_tuple3(&oxy.xyz[3 * h]));
+                                        if (trial.table.size() != shadow.table.size()) { differs = true; break; }
+                                        for (size_t z = 0; z < trial.table.size(); ++z)
+                                            if (trial.table[z].key != shadow.table[z].key) { differs = true; break; }
+                                    } while (!differs && std::next_permutation(perm.begin(), perm.end()));
+                                }
+                                if (differs) it_perm = true;
+                            }
                         }
+                    }
+                    if (it_cons) ++st.flag_iters_cons;
+                    if (it_perm) ++st.flag_iters_perm;
+                    if (cfg.ball_order == 0) {
+                        std::vector<int> oa, ob;
+                        to_add.for_each([&](int h) { oa.push_back(h); });
+                        shadow.for_each([&](int h) { ob.push_back(h); });
+                        if (oa != ob) ++st.diff_iters;
                     }
                     to_add.for_each([&](int h) { co2.push(&oxy.xyz[3 * h], oxy.id[h]); });
                     oxy.remove_positions(to_remove);

@@ -37,7 +37,8 @@ class OGStats(ctypes.Structure):
                                              "np_u32", "nn_queries", "ball_queries", "bifurcations", "sprouts",
                                              "elongations", "walk_steps", "sum_A", "sum_M", "sum_P", "sum_S",
                                              "multi_balls", "reordered_balls", "interacting_groups", "kd_builds",
-                                             "inter_evals", "inter_r1_changed", "max_dict", "max_list")]
+                                             "inter_evals", "inter_r1_changed", "max_dict", "max_list",
+                                             "flag_iters_cons", "flag_iters_perm", "diff_iters", "perm_groups")]
 
 
 EIG_HOOK = ctypes.CFUNCTYPE(None, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),

@@ -159,3 +159,56 @@ def test_fixed_geometry_vs_reference_csv(growth):
     for seed in (0, 1):
         got = numpy_csv(np.concatenate(graphs[seed]))
         assert got == open(os.path.join(GOLDEN, "graph_geom_s%d.csv" % seed), "rb").read()
+
+
+def test_docker_config_24_seeds_vs_oracle(growth):
+    """the GPU equals the exact-order oracle on docker-config seeds 0-23 (the oracle is byte-identical to the
+    reference on the committed goldens).  Runs with the default on-demand cKDTree order (OCTA_BALL_ORDER unset)."""
+    from octa_autosegmentation_b200.config import default_config
+    graphs, stats = compare_with_oracle(growth, default_config(), list(range(4, 24)))
+    # the on-demand path must actually have been exercised: some graph-iterations needed the exact order, most did not
+    need = [s["replay_detail"][0] for s in stats]
+    assert all(0 < n < 200 for n in need), need
+
+
+def test_graph_replay_equals_stream_launches(growth):
+    """The growth loop is issued as stream launches for a context's first batch and as ONE captured CUDA graph from the
+    second batch on (octa_grow_host.cu): same seeds -> same bytes, whichever way the loop was issued."""
+    cfg = small_config()
+    ctx = growth.GrowContext(cfg, 4)
+    try:
+        first, _, _ = ctx.run([0, 1, 2, 3])          # stream launches (no node-count history yet)
+        other, _, _ = ctx.run([7, 6, 5, 4])          # captures the graph
+        again, _, _ = ctx.run([0, 1, 2, 3])          # re-launches it
+        part, _, _ = ctx.run([2, 3])                 # smaller batch: re-captured
+    finally:
+        ctx.close()
+    one_shot, _, _ = growth.grow_batch(cfg, [4, 5, 6, 7])
+    for i in range(4):
+        assert np.array_equal(first[i][0], again[i][0]) and np.array_equal(first[i][1], again[i][1])
+        assert np.array_equal(other[3 - i][0], one_shot[i][0]) and np.array_equal(other[3 - i][1], one_shot[i][1])
+    for i in range(2):
+        assert np.array_equal(part[i][0], first[2 + i][0]) and np.array_equal(part[i][1], first[2 + i][1])
+
+
+@pytest.mark.parametrize("mode", ["always", "graph2"])
+def test_ball_order_modes_agree(monkeypatch, mode):
+    """OCTA_BALL_ORDER=always builds the cKDTree permutation for every graph in every iteration (round-1 behaviour); the
+    default builds it only for the graph-iterations whose CO2 order could depend on it.  Both must give the oracle's bytes.
+    `graph2`: CUDA graph from the very first batch (OCTA_GROW_GRAPH=2)."""
+    if mode == "always":
+        monkeypatch.setenv("OCTA_BALL_ORDER", "always")
+    else:
+        monkeypatch.setenv("OCTA_GROW_GRAPH", "2")
+    import subprocess
+    import sys
+    from conftest import ROOT
+    # the switches are read once per process: run the comparison in a child
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')\n"
+            "import test_growth_gpu as t\n"
+            "from octa_autosegmentation_b200 import growth\n"
+            "from octa_autosegmentation_b200.config import default_config\n"
+            "t.compare_with_oracle(growth, default_config(), [0, 5])\n"
+            "t.compare_with_oracle(growth, t.small_config(), [0, 1, 2])\nprint('MODES_OK')\n") % (ROOT, ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=dict(os.environ))
+    assert r.returncode == 0 and "MODES_OK" in r.stdout, r.stdout + r.stderr

@@ -1,0 +1,85 @@
+"""CPU: the CPython-set emulation k_kill runs (csrc/octa_pyset.cuh, host build through octa_test_pyset) against REAL CPython
+sets, and the soundness of its order-sensitivity test: whenever it does NOT ask for the exact cKDTree ball order, every order
+of the keys inside every ball must give the same iteration order (greenhouse.py:100-111, element_mesh.py:136-137)."""
+import ctypes
+import itertools
+import random
+
+import numpy as np
+
+from octa_autosegmentation_b200 import _lib
+
+
+def _run(xyz, ball, detect):
+    L = _lib.lib()
+    L.octa_test_pyset.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    T = len(ball)
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+    b = np.ascontiguousarray(ball, dtype=np.int32)
+    out = np.zeros(max(T, 1), dtype=np.int32)
+    n = ctypes.c_int(0)
+    rc = L.octa_test_pyset(xyz.ctypes.data, b.ctypes.data, T, int(detect), out.ctypes.data, ctypes.byref(n))
+    assert rc >= 0
+    return rc, [int(v) for v in out[:n.value]]
+
+
+def _cpython_order(xyz, order):
+    s = set()
+    tup = [tuple(np.float64(v) for v in row) for row in xyz]
+    for q in order:
+        s.add(tup[q])
+    index = {t: i for i, t in enumerate(tup)}
+    return [index[t] for t in s]
+
+
+def _ball_sizes(rng, T):
+    sizes = []
+    while sum(sizes) < T:
+        sizes.append(rng.choice([1, 1, 1, 2, 2, 3, 4, 5]))
+    sizes[-1] -= sum(sizes) - T
+    return [s for s in sizes if s > 0]
+
+
+def test_plain_emulation_equals_cpython_set():
+    rng = random.Random(1)
+    for trial in range(200):
+        T = rng.randint(0, 700 if trial % 20 == 0 else 90)
+        xyz = np.random.default_rng(trial).uniform(0, 1, (T, 3))
+        ball = np.repeat(np.arange(len(_ball_sizes(rng, T)) or 1), 1)[:0]  # unused in plain mode
+        rc, order = _run(xyz, np.zeros(T, dtype=np.int32), detect=False)
+        assert rc == 0 and order == _cpython_order(xyz, range(T))
+
+
+def test_unflagged_results_do_not_depend_on_the_order_inside_a_ball():
+    rng = random.Random(2)
+    flagged = unflagged = truly_sensitive = 0
+    for trial in range(1500):
+        T = rng.randint(2, 40)
+        xyz = np.random.default_rng(10_000 + trial).uniform(0, 1, (T, 3))
+        sizes = _ball_sizes(rng, T)
+        ball = np.repeat(np.arange(len(sizes)), sizes)
+        starts = np.cumsum([0] + sizes)
+        rc, order = _run(xyz, ball, detect=True)
+        # ground truth with real sets: all combinations of orders inside the balls (bounded)
+        groups = [list(range(starts[i], starts[i + 1])) for i in range(len(sizes))]
+        n_comb = 1
+        for g in groups:
+            n_comb *= len(list(itertools.permutations(g))) if len(g) <= 5 else 10 ** 9
+        results = set()
+        if n_comb <= 3000:
+            for combo in itertools.product(*[itertools.permutations(g) for g in groups]):
+                results.add(tuple(_cpython_order(xyz, [q for grp in combo for q in grp])))
+        else:   # sample
+            for _ in range(300):
+                seq = [q for g in groups for q in rng.sample(g, len(g))]
+                results.add(tuple(_cpython_order(xyz, seq)))
+        sensitive = len(results) > 1
+        truly_sensitive += sensitive
+        if rc == 1:
+            flagged += 1
+        else:
+            unflagged += 1
+            assert not sensitive, "order-sensitive case was not flagged (trial %d)" % trial
+            assert order == _cpython_order(xyz, range(T))
+    # the test is conservative but must not be vacuous
+    assert unflagged > 300 and flagged >= truly_sensitive > 0
