@@ -5,6 +5,8 @@
 namespace octa {
 static thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
+thread_local bool t_capturing = false;
+thread_local uint64_t t_captured = 0;
 
 void set_error(const char* fmt, ...) {
     va_list ap;

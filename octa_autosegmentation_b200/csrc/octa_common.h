@@ -10,7 +10,13 @@ namespace octa {
 
 void set_error(const char* fmt, ...);
 extern std::atomic<uint64_t> g_launches;
-inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+// while a thread captures a CUDA graph its launches are recorded, not executed: they are counted per graph launch instead
+extern thread_local bool t_capturing;
+extern thread_local uint64_t t_captured;
+inline void count_launch(int n = 1) {
+    if (t_capturing) t_captured += (uint64_t)n;
+    else g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed);
+}
 
 #define OCTA_CUDA_CHECK(expr)                                                                 \
     do {                                                                                      \

@@ -635,9 +635,12 @@ static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, doub
         for (size_t i = 0; i < n_it; ++i)
             launch_iteration(ctx->dslot, S, &cs[2 * i], ctx->sched[i], i + 1 < n_it ? &ctx->sched[i + 1] : nullptr, ctx->n_sm, st, ctx->side, ctx->ev);
     };
-    // OCTA_GROW_GRAPH: 0 = stream launches, 1 (default) = CUDA graph from the context's second batch on (the first one also
-    // establishes the mirror sizes), 2 = CUDA graph always
-    static const int graph_mode = [] { const char* e = getenv("OCTA_GROW_GRAPH"); return e ? atoi(e) : 1; }();
+    // OCTA_GROW_GRAPH: 0 (default) = stream launches, 1 = CUDA graph from the context's second batch on (the first one also
+    // establishes the mirror sizes), 2 = CUDA graph always.  Measured on one B200 (profiles/README.md, round 2): the graph frees
+    // the host (cudaGraphLaunch of the 4 001 kernels: 0.03 ms instead of ~190 ms of launch calls per loop) but the device
+    // executes the same loop ~10 % SLOWER from the graph (315 vs 285 ms for 32 graphs alone), and 8 loops in flight reach
+    // 426 graphs/s instead of 498 -- so it is opt-in, for hosts with few cores per GPU.
+    static const int graph_mode = [] { const char* e = getenv("OCTA_GROW_GRAPH"); return e ? atoi(e) : 0; }();
     const bool use_graph = n_it > 0 && !grow_timing_enabled() && (graph_mode >= 2 || (graph_mode == 1 && have_hist));
     if (use_graph) {
         GrowCtx::LoopGraph& lg = ctx->lg;
@@ -645,21 +648,22 @@ static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, doub
         for (size_t q = 0; q < cs_all.size() && !stale; ++q) stale = cs_raw[q] > lg.cs[q];    // a tree outgrew its captured mirror
         if (stale) {
             if (lg.exec) { cudaGraphExecDestroy(lg.exec); lg.exec = nullptr; }
-            const uint64_t l0 = g_launches.load();
             OCTA_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            t_capturing = true; t_captured = 0;          // captured, not launched: counted per graph launch below
             issue_loop(cs_all);
+            t_capturing = false;
             cudaGraph_t graph = nullptr;
             cudaError_t ce = cudaStreamEndCapture(st, &graph);
-            const uint64_t l1 = g_launches.load();
-            g_launches.fetch_sub(l1 - l0);               // captured, not launched
             if (ce != cudaSuccess || !graph) { cudaGetLastError(); set_error("capture of the growth loop failed: %s", cudaGetErrorString(ce)); return OCTA_E_CUDA; }
             ce = cudaGraphInstantiate(&lg.exec, graph, 0);
             cudaGraphDestroy(graph);
             if (ce != cudaSuccess) { lg.exec = nullptr; cudaGetLastError(); set_error("cudaGraphInstantiate(growth loop) failed: %s", cudaGetErrorString(ce)); return OCTA_E_CUDA; }
-            lg.n_graphs = n_graphs; lg.from_history = have_hist; lg.cs = cs_all; lg.kernels = l1 - l0;
+            lg.n_graphs = n_graphs; lg.from_history = have_hist; lg.cs = cs_all; lg.kernels = t_captured;
         }
+        const double tg0 = wall();
         OCTA_CUDA_CHECK(cudaGraphLaunch(lg.exec, st));
         count_launch((int)lg.kernels);
+        if (host_timing) fprintf(stderr, "[octa grow host] %s cudaGraphLaunch of %llu kernels: %.2f ms\n", stale ? "capture + instantiate done;" : "", (unsigned long long)lg.kernels, wall() - tg0);
     } else if (n_it > 0) {
         issue_loop(cs_all);
     }

@@ -171,9 +171,19 @@ def test_docker_config_24_seeds_vs_oracle(growth):
     assert all(0 < n < 200 for n in need), need
 
 
-def test_graph_replay_equals_stream_launches(growth):
-    """The growth loop is issued as stream launches for a context's first batch and as ONE captured CUDA graph from the
-    second batch on (octa_grow_host.cu): same seeds -> same bytes, whichever way the loop was issued."""
+def test_graph_replay_equals_stream_launches(monkeypatch):
+    """OCTA_GROW_GRAPH=1: the growth loop is issued as stream launches for a context's first batch and as ONE captured CUDA
+    graph from the second batch on (octa_grow_host.cu): same seeds -> same bytes, whichever way the loop was issued."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')\n"
+            "import test_growth_gpu as t\nfrom octa_autosegmentation_b200 import growth\nt._graph_replay(growth)\nprint('GRAPH_OK')\n") % (ROOT, ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=dict(os.environ, OCTA_GROW_GRAPH="1"))
+    assert r.returncode == 0 and "GRAPH_OK" in r.stdout, r.stdout + r.stderr
+
+
+def _graph_replay(growth):
     cfg = small_config()
     ctx = growth.GrowContext(cfg, 4)
     try:
