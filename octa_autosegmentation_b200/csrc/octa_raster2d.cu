@@ -1,34 +1,39 @@
 // K7: 2-D anti-aliased label rasterizer for sm_100a.
 //
-// Replaces vessel_graph_generation/tree2img.py:12-114 (rasterize_forest), whose arithmetic lives in
-// matplotlib's Agg backend: every kept edge is a round-capped stroke of width
-//     1.3 * radius * max(W, H)  points  =  * dpi/72 = 100/72 pixels              (tree2img.py:82-86, dpi :51)
-// drawn white on black into a W x H canvas with y inverted, pixel (row, col) <-> (pos[ax0]*H, pos[ax1]*W),
-// ax = {0,1,2} \ {MIP_axis} (:46,:85), anti-aliased, composited "over" in list order, read back as 8-bit
-// gray (:104-113).  matplotlib is not part of this image and the reference pins no version, so this
-// path is "parity unpinned": the model below is validated statistically against the
-// label PNGs the reference ships (tests/test_raster2d_gpu.py, IoU / vessel fraction).
+// Replaces vessel_graph_generation/tree2img.py:12-114 (rasterize_forest), whose arithmetic lives in matplotlib's Agg backend:
+// every kept edge is a round-capped stroke of width 1.3 * radius * max(W, H) points = * 100/72 pixels (tree2img.py:82-86, dpi
+// :51) drawn white on black, pixel (row, col) <-> (pos[ax0]*H, pos[ax1]*W), ax = {0,1,2} \ {MIP_axis} (:46,:85), anti-aliased,
+// blended "over" in list order in 8 bits, read back as gray (:104-113).  csrc/octa_aggcells.cuh restates that pipeline stage
+// by stage (centre-line clip and snap, inscribed-polygon caps, the 24.8 fixed-point cover/area cells of Agg's scanline
+// rasterizer, calculate_alpha, fixed_blender_rgba_plain); the CPU restatement of the same pipeline, oracle/agg_oracle.c,
+// reproduces all 500 label PNGs the reference ships bit for bit, and this kernel equals it pixel for pixel
+// (tests/test_raster2d_gpu.py).  All pixel arithmetic is integer.
 //
-// Coverage model: box-filtered capsule -- with d the distance of the pixel centre to the segment and
-// r the half stroke width in pixels, coverage = clamp(min(d+1/2, r) - max(d-1/2, -r), 0, 1), which is the
-// exact pixel/strip overlap for axis-aligned strokes and within a few percent otherwise.  Compositing:
-// T = prod(1 - a_i) in list order, gray = round(255 (1 - T)).
-//
-// Design: same tile ownership as K6 -- one CTA owns a 32x32 pixel tile of one graph, one thread owns
-// one pixel and walks the tile's edge list (binned by prep/scan/fill kernels, each list sorted back
-// into edge order so the result is deterministic), then writes its byte once: HBM traffic is the
-// algorithmic 1 byte/pixel + 56 bytes/edge.
+// Design: tile ownership like K6.  One CTA owns a 32x32 pixel tile of one graph; its stroke list (binned by prep / scan /
+// fill, ranked back into edge order: blending does not commute) is processed in batches of SB strokes:
+//   1. outline vertices of the batch (float64 trig, one thread per vertex) -> shared memory
+//   2. one thread per outline edge: Agg's clipper -> 24.8 integer lines in shared memory
+//   3. ONE WARP PER PIXEL ROW walks the batch's strokes in order: the lanes take the stroke's lines, evaluate the piece of each
+//      line inside the row in closed form (Agg's scanline DDA is a floor division) and add its (cover, area) cell
+//      contributions with shared-memory atomics (integer sums: order-free); a warp scan of the covers gives every pixel's
+//      coverage, lane = column blends its own pixel.  Rows never interact, so there is no barrier inside a batch.
+// HBM traffic is the algorithmic 1 byte/pixel + 56 bytes/edge (+ the tile lists).
 #include "octa_common.h"
 #include <math.h>
+#include "octa_aggcells.cuh"
 
 namespace {
 
-constexpr int RT = 32;          // tile edge (pixels)
-constexpr int RKBIG = 64;
+using namespace octa;
 
-struct REdge {                  // pixel-space capsule
-    float x1, y1, x2, y2, r;
-    int lo[2], hi[2];           // tile range, inclusive; hi < lo -> skipped
+constexpr int RT = 32;          // tile edge (pixels) = warp width
+constexpr int RKBIG = 64;       // an edge listed in more tiles than this goes to the graph's "big" list, tested by every tile
+constexpr int SB = 8;           // strokes per batch
+constexpr int R2D_THREADS = RT * RT;
+
+struct REdge {                  // clipped / snapped centre line + half width (pixels), tile range
+    agg::Stroke s;
+    int lo[2], hi[2];           // tile range, inclusive; hi < lo -> nothing to draw
 };
 
 struct RGeom {
@@ -37,28 +42,35 @@ struct RGeom {
     double scale, min_radius, max_radius;
 };
 
+__device__ __forceinline__ int graph_of(const int64_t* offs, int n_graphs, int64_t i) {
+    int lo = 0, hi = n_graphs;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (offs[mid] <= i) lo = mid; else hi = mid; }
+    return lo;
+}
+
 __global__ void r2d_prep_kernel(const double* __restrict__ edges7, const int64_t* __restrict__ offs, int n_graphs, RGeom g,
                                 REdge* __restrict__ prep, int* __restrict__ tile_count, int* __restrict__ big_count,
                                 int* __restrict__ big_idx) {
     const int64_t n_edges = offs[n_graphs];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_edges) return;
-    int lo = 0, hi = n_graphs;
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (offs[mid] <= i) lo = mid; else hi = mid; }
-    const int gr = lo;
-    const double* e = edges7 + 7 * i;
+    const int gr = graph_of(offs, n_graphs, i);
     REdge q;
-    const double radius = e[6];
-    const bool keep = !(radius < g.min_radius || radius > g.max_radius);            // tree2img.py:67
-    // thickness = 1.3 * radius * scale_factor [points]; 1 pt = 100/72 px; half width in px
-    const double half = 0.5 * ((radius * 1.3) * g.scale) * (100.0 / 72.0);
-    const double x1 = e[g.ax1] * g.W, y1 = e[g.ax0] * g.H, x2 = e[3 + g.ax1] * g.W, y2 = e[3 + g.ax0] * g.H;
-    q.x1 = (float)x1; q.y1 = (float)y1; q.x2 = (float)x2; q.y2 = (float)y2; q.r = (float)half;
-    const double reach = half + 0.75;
-    const double bx0 = fmin(x1, x2) - reach, bx1 = fmax(x1, x2) + reach, by0 = fmin(y1, y2) - reach, by1 = fmax(y1, y2) + reach;
-    int px0 = (int)fmax(0.0, floor(bx0)), px1 = (int)fmin((double)g.W - 1, floor(bx1));
-    int py0 = (int)fmax(0.0, floor(by0)), py1 = (int)fmin((double)g.H - 1, floor(by1));
-    if (!keep || !(bx1 >= 0) || !(by1 >= 0) || px0 > px1 || py0 > py1 || !(half == half)) { q.lo[0] = q.lo[1] = 1; q.hi[0] = q.hi[1] = 0; prep[i] = q; return; }
+    q.lo[0] = q.lo[1] = 1; q.hi[0] = q.hi[1] = 0;
+    q.s.x0 = q.s.y0 = q.s.x1 = q.s.y1 = q.s.w = 0;
+    if (!agg::prepare_stroke(edges7 + 7 * i, g.ax0, g.ax1, g.H, g.W, g.scale, g.min_radius, g.max_radius, &q.s) || !(q.s.w == q.s.w)) {
+        prep[i] = q;
+        return;
+    }
+    // the outline is inscribed in the capsule of half width w; 1/64 px of slack covers the 1/256 vertex rounding
+    const double reach = q.s.w + 0.015625;
+    const double bx0 = fmin(q.s.x0, q.s.x1) - reach, bx1 = fmax(q.s.x0, q.s.x1) + reach;
+    const double by0 = fmin(q.s.y0, q.s.y1) - reach, by1 = fmax(q.s.y0, q.s.y1) + reach;
+    const int px0 = (int)fmax(0.0, floor(bx0)), px1 = (int)fmin((double)g.W - 1, floor(bx1));
+    const int py0 = (int)fmax(0.0, floor(by0)), py1 = (int)fmin((double)g.H - 1, floor(by1));
+    if (!(bx1 >= 0) || !(by1 >= 0) || px0 > px1 || py0 > py1) { prep[i] = q; return; }
+    // a cell's coverage depends on every outline edge to its LEFT in the row, all of which lie inside the bounding box: tiles
+    // from the box's first column on are enough
     q.lo[0] = px0 / RT; q.hi[0] = px1 / RT; q.lo[1] = py0 / RT; q.hi[1] = py1 / RT;
     prep[i] = q;
     const int n = (q.hi[0] - q.lo[0] + 1) * (q.hi[1] - q.lo[1] + 1);
@@ -105,9 +117,7 @@ __global__ void r2d_fill_kernel(const int64_t* __restrict__ offs, int n_graphs, 
     const int64_t n_edges = offs[n_graphs];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_edges) return;
-    int lo = 0, hi = n_graphs;
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (offs[mid] <= i) lo = mid; else hi = mid; }
-    const int gr = lo;
+    const int gr = graph_of(offs, n_graphs, i);
     const REdge q = prep[i];
     if (q.hi[0] < q.lo[0] || q.hi[1] < q.lo[1]) return;
     const int n = (q.hi[0] - q.lo[0] + 1) * (q.hi[1] - q.lo[1] + 1);
@@ -119,24 +129,35 @@ __global__ void r2d_fill_kernel(const int64_t* __restrict__ offs, int n_graphs, 
         for (int tx = q.lo[0]; tx <= q.hi[0]; ++tx) lst[atomicAdd(&cur[ty * g.ntx + tx], 1)] = local;
 }
 
-__device__ __forceinline__ float capsule_cover(const REdge& e, float px, float py) {
-    const float sx = e.x2 - e.x1, sy = e.y2 - e.y1;
-    const float ux = px - e.x1, uy = py - e.y1;
-    const float ss = sx * sx + sy * sy;
-    float t = ss > 0.f ? (ux * sx + uy * sy) / ss : 0.f;
-    t = fminf(fmaxf(t, 0.f), 1.f);
-    const float dx = ux - t * sx, dy = uy - t * sy;
-    const float d = sqrtf(dx * dx + dy * dy);
-    const float c = fminf(d + 0.5f, e.r) - fmaxf(d - 0.5f, -e.r);
-    return fminf(fmaxf(c, 0.f), 1.f);
-}
+// shared-memory state of one tile
+struct TileSm {
+    int list_in[R2D_THREADS], list_sorted[R2D_THREADS];     // the tile's strokes, as filled / in edge order
+    double vx[SB][agg::MAX_VERT], vy[SB][agg::MAX_VERT];
+    agg::Line lines[SB][agg::MAX_LINES];
+    int nvert[SB], ncap[SB], nlines[SB], ymin[SB], ymax[SB];
+    agg::Stroke stroke[SB];
+    int cover[RT][RT], area[RT][RT], left[RT];
+    int batch_ids[SB], batch_n;
+    int n_sorted;
+};
 
-__global__ void __launch_bounds__(RT * RT)
+struct RowAdd {     // (cover, area) contribution of a line piece to cell ex of this warp's row
+    int* cover; int* area; int* left; int tx0;
+    __device__ __forceinline__ void operator()(int ex, int c, int a) {
+        if (ex < tx0) { if (c) atomicAdd(left, c); }
+        else if (ex < tx0 + RT) { atomicAdd(cover + (ex - tx0), c); atomicAdd(area + (ex - tx0), a); }
+    }
+};
+
+__global__ void __launch_bounds__(R2D_THREADS)
 r2d_tile_kernel(const REdge* __restrict__ prep, const int64_t* __restrict__ offs, RGeom g, const int* __restrict__ tile_start,
                 int* __restrict__ tile_edges, const int* __restrict__ big_count, const int* __restrict__ big_idx,
-                uint8_t* __restrict__ out) {
+                uint8_t* __restrict__ out, int* __restrict__ err) {
+    extern __shared__ __align__(16) unsigned char r2d_smem[];
+    TileSm& T = *reinterpret_cast<TileSm*>(r2d_smem);
     const int gr = blockIdx.y, tile = blockIdx.x;
     const int tx = tile % g.ntx, ty = tile / g.ntx;
+    const int tid = threadIdx.x, lane = tid & 31, row = tid >> 5;
     const int64_t eb = offs[gr];
     const REdge* ge = prep + eb;
     const int* st = tile_start + (size_t)gr * (g.ntiles + 1);
@@ -144,54 +165,132 @@ r2d_tile_kernel(const REdge* __restrict__ prep, const int64_t* __restrict__ offs
     int* lst = tile_edges + (size_t)RKBIG * eb;
     const int* bl = big_idx + eb;
     const int nbig = big_count[gr];
-    // restore list order (atomics filled the lists in arbitrary order; the float product below is applied in edge order).
-    // Lists of up to one entry per thread are ranked in shared memory (edge ids are distinct: rank = number of smaller ids,
-    // two barriers); longer ones fall back to an odd-even transposition in place (one barrier and one global round trip per pass,
-    // which dominated this kernel when it was the only path).
-    __shared__ int s_in[RT * RT], s_sorted[RT * RT];
     const int n = end - beg;
-    const bool in_smem = n <= RT * RT;
+    // ---- the tile's strokes in edge order.  Usual case: the list (+ the big edges that overlap the tile) fits one entry per
+    // thread and is ranked in shared memory (ids are distinct: rank = number of smaller ids).
+    T.cover[row][lane] = 0; T.area[row][lane] = 0;
+    if (lane == 0) T.left[row] = 0;
+    if (tid == 0) T.n_sorted = 0;
+    __syncthreads();
+    const bool in_smem = n + nbig <= R2D_THREADS;
     if (in_smem) {
-        int v = 0;
-        if ((int)threadIdx.x < n) { v = lst[beg + threadIdx.x]; s_in[threadIdx.x] = v; }
+        int v = -1;
+        if (tid < n) v = lst[beg + tid];
+        else if (tid < n + nbig) {
+            const int b = bl[tid - n];
+            const REdge& e = ge[b];
+            if (!(tx < e.lo[0] || tx > e.hi[0] || ty < e.lo[1] || ty > e.hi[1])) v = b;
+        }
+        T.list_in[tid] = v;
         __syncthreads();
-        if ((int)threadIdx.x < n) {
+        if (v >= 0) {
             int rank = 0;
-            for (int j = 0; j < n; ++j) rank += s_in[j] < v;
-            s_sorted[rank] = v;
+            for (int j = 0; j < n + nbig; ++j) { const int u = T.list_in[j]; rank += (u >= 0 && u < v); }
+            T.list_sorted[rank] = v;
+            atomicAdd(&T.n_sorted, 1);
         }
         __syncthreads();
     } else {
+        // more than 1024 strokes in one tile: odd-even transposition of the list in place (global memory)
         for (int pass = 0; pass < n; ++pass) {
-            for (int i = (pass & 1) + 2 * threadIdx.x; i + 1 < n; i += 2 * blockDim.x) {
+            for (int i = (pass & 1) + 2 * tid; i + 1 < n; i += 2 * blockDim.x) {
                 const int a = lst[beg + i], b = lst[beg + i + 1];
                 if (a > b) { lst[beg + i] = b; lst[beg + i + 1] = a; }
             }
             __syncthreads();
         }
     }
-    const int px = tx * RT + (threadIdx.x % RT), py = ty * RT + (threadIdx.x / RT);
-    if (px >= g.W || py >= g.H) return;
-    const float cx = (float)px + 0.5f, cy = (float)py + 0.5f;
-    float T = 1.f;
-    if (in_smem) { for (int k = 0; k < n; ++k) T *= 1.f - capsule_cover(ge[s_sorted[k]], cx, cy); }
-    else { for (int k = beg; k < end; ++k) T *= 1.f - capsule_cover(ge[lst[k]], cx, cy); }
-    // edges spanning more than RKBIG tiles (rare): the product commutes, so they are applied after the tile
-    // list, in ascending edge order (selection over the unsorted, tiny list keeps the result deterministic)
-    int prev = -1;
-    for (int k = 0; k < nbig; ++k) {
-        int best = 0x7fffffff;
-        for (int j = 0; j < nbig; ++j) { const int v = bl[j]; if (v > prev && v < best) best = v; }
-        prev = best;
-        const REdge e = ge[best];
-        if (tx < e.lo[0] || tx > e.hi[0] || ty < e.lo[1] || ty > e.hi[1]) continue;
-        T *= 1.f - capsule_cover(e, cx, cy);
+    const int n_sorted = in_smem ? T.n_sorted : n;
+    unsigned char gray = 0;
+    const int py = ty * RT + row, px = tx * RT + lane;
+    const agg::Clip clip = {0.0, 0.0, (double)g.W, (double)g.H};
+    int head = 0, bprev = -1;        // (global path) next list entry / last big edge taken
+    while (true) {
+        // ---- batch assembly
+        if (in_smem) {
+            if (tid == 0) T.batch_n = min(SB, n_sorted - head);
+            if (tid < SB && head + tid < n_sorted) T.batch_ids[tid] = T.list_sorted[head + tid];
+            head += SB;
+        } else if (tid == 0) {
+            // merge of the sorted list with the (unsorted, tiny) big list, filtered by tile overlap
+            int k = 0;
+            while (k < SB) {
+                int bbest = 0x7fffffff;
+                for (int j = 0; j < nbig; ++j) {
+                    const int v = bl[j];
+                    if (v > bprev && v < bbest) {
+                        const REdge& e = ge[v];
+                        if (!(tx < e.lo[0] || tx > e.hi[0] || ty < e.lo[1] || ty > e.hi[1])) bbest = v;
+                    }
+                }
+                const int lbest = head < n ? lst[beg + head] : 0x7fffffff;
+                if (bbest == 0x7fffffff && lbest == 0x7fffffff) break;
+                if (lbest < bbest) { T.batch_ids[k++] = lbest; ++head; } else { T.batch_ids[k++] = bbest; bprev = bbest; }
+            }
+            T.batch_n = k;
+        }
+        __syncthreads();
+        const int bn = T.batch_n;
+        if (bn <= 0) break;
+        // ---- 1. stroke parameters and outline vertices
+        if (tid < bn) {
+            const agg::Stroke s = ge[T.batch_ids[tid]].s;
+            int nc = agg::cap_steps(s.w);
+            if (nc > agg::MAX_CAP_SEG) { nc = agg::MAX_CAP_SEG; atomicExch(err, 1); }     // stroke wider than ~800 px: reported
+            if (nc < 0) nc = 0;
+            T.stroke[tid] = s; T.ncap[tid] = nc; T.nvert[tid] = 2 * (nc + 2);
+            T.nlines[tid] = 0; T.ymin[tid] = 0x7fffffff; T.ymax[tid] = -0x7fffffff;
+        }
+        __syncthreads();
+        for (int it = tid; it < bn * agg::MAX_VERT; it += R2D_THREADS) {
+            const int s = it / agg::MAX_VERT, k = it - s * agg::MAX_VERT;
+            if (k < T.nvert[s]) agg::stroke_vertex(T.stroke[s], T.ncap[s], k, &T.vx[s][k], &T.vy[s][k]);
+        }
+        __syncthreads();
+        // ---- 2. outline edges through Agg's clipper -> integer lines
+        for (int it = tid; it < bn * agg::MAX_VERT; it += R2D_THREADS) {
+            const int s = it / agg::MAX_VERT, k = it - s * agg::MAX_VERT;
+            const int nv = T.nvert[s];
+            if (k >= nv) continue;
+            const int k2 = k + 1 == nv ? 0 : k + 1;
+            agg::Line tmp[3];
+            const int nl = agg::clip_edge(clip, T.vx[s][k], T.vy[s][k], T.vx[s][k2], T.vy[s][k2], tmp);
+            if (nl > 0) {
+                const int pos = atomicAdd(&T.nlines[s], nl);
+                for (int q = 0; q < nl; ++q) {
+                    if (pos + q < agg::MAX_LINES) T.lines[s][pos + q] = tmp[q];
+                    const int e1 = tmp[q].y1 >> agg::SUB_SHIFT, e2 = tmp[q].y2 >> agg::SUB_SHIFT;
+                    atomicMin(&T.ymin[s], min(e1, e2));
+                    atomicMax(&T.ymax[s], max(e1, e2));
+                }
+            }
+        }
+        __syncthreads();
+        // ---- 3. one warp per pixel row
+        for (int s = 0; s < bn; ++s) {
+            if (py < T.ymin[s] || py > T.ymax[s]) continue;
+            const int nl = min(T.nlines[s], agg::MAX_LINES);
+            RowAdd add = {T.cover[row], T.area[row], &T.left[row], tx * RT};
+            for (int li = lane; li < nl; li += 32) agg::line_row(T.lines[s][li], py, add);
+            __syncwarp();
+            const int c = T.cover[row][lane], a = T.area[row][lane], l = T.left[row];
+            __syncwarp();
+            T.cover[row][lane] = 0; T.area[row][lane] = 0;
+            if (lane == 0) T.left[row] = 0;
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+            const int alpha = agg::calc_alpha(((l + incl) << (agg::SUB_SHIFT + 1)) - a);
+            gray = agg::blend_cover(gray, alpha);
+            __syncwarp();
+        }
+        __syncthreads();
     }
-    out[((size_t)gr * g.H + py) * g.W + px] = (uint8_t)__float2int_rn(255.f * (1.f - T));
+    if (px < g.W && py < g.H) out[((size_t)gr * g.H + py) * g.W + px] = gray;
 }
 
 int make_rgeom(int H, int W, int mip_axis, const OctaVoxOpts* opts, RGeom* g) {
-    OCTA_ARG_CHECK(H > 0 && W > 0 && H <= 32768 && W <= 32768, "bad image resolution");
+    OCTA_ARG_CHECK(H > 0 && W > 0 && H <= 16384 && W <= 16384, "bad image resolution");
     OCTA_ARG_CHECK(mip_axis >= 0 && mip_axis <= 2, "MIP axis must be 0, 1 or 2");
     g->H = H; g->W = W;
     g->ntx = (W + RT - 1) / RT; g->nty = (H + RT - 1) / RT; g->ntiles = g->ntx * g->nty;
@@ -204,7 +303,7 @@ int make_rgeom(int H, int W, int mip_axis, const OctaVoxOpts* opts, RGeom* g) {
     return OCTA_OK;
 }
 
-struct RWork { REdge* prep; int64_t* offs; int *tile_count, *big_count, *tile_start, *cursor, *big_idx, *tile_edges; size_t bytes; };
+struct RWork { REdge* prep; int64_t* offs; int *tile_count, *big_count, *err, *tile_start, *cursor, *big_idx, *tile_edges; size_t bytes; };
 
 RWork rcarve(void* base, int n_graphs, int64_t n_edges, int ntiles) {
     RWork w;
@@ -215,6 +314,7 @@ RWork rcarve(void* base, int n_graphs, int64_t n_edges, int ntiles) {
     w.offs = (int64_t*)take(sizeof(int64_t) * (n_graphs + 1));
     w.tile_count = (int*)take(sizeof(int) * (size_t)n_graphs * ntiles);
     w.big_count = (int*)take(sizeof(int) * n_graphs);
+    w.err = (int*)take(sizeof(int));
     w.tile_start = (int*)take(sizeof(int) * (size_t)n_graphs * (ntiles + 1));
     w.cursor = (int*)take(sizeof(int) * (size_t)n_graphs * ntiles);
     w.big_idx = (int*)take(sizeof(int) * ne);
@@ -246,14 +346,19 @@ extern "C" int octa_raster2d_batch_dev(const double* edges7_dev, const int64_t* 
     RWork w = rcarve(workspace_dev, n_graphs, n_edges, g.ntiles);
     if (w.bytes > workspace_bytes) { octa::set_error("octa_raster2d_batch_dev: workspace too small (%zu < %zu)", workspace_bytes, w.bytes); return OCTA_E_NOMEM; }
     OCTA_CUDA_CHECK(cudaMemcpyAsync(w.offs, edge_offsets_host, sizeof(int64_t) * (n_graphs + 1), cudaMemcpyHostToDevice, stream));
-    OCTA_CUDA_CHECK(cudaMemsetAsync(w.tile_count, 0, (char*)w.tile_start - (char*)w.tile_count, stream));
+    OCTA_CUDA_CHECK(cudaMemsetAsync(w.tile_count, 0, (char*)w.tile_start - (char*)w.tile_count, stream));      // counts, big counts, error flag
     const int threads = 128, blocks = (int)((n_edges + threads - 1) / threads);
     if (n_edges > 0) { r2d_prep_kernel<<<blocks, threads, 0, stream>>>(edges7_dev, w.offs, n_graphs, g, w.prep, w.tile_count, w.big_count, w.big_idx); octa::count_launch(); }
     r2d_scan_kernel<<<n_graphs, 1024, 0, stream>>>(w.tile_count, w.tile_start, w.cursor, g.ntiles);
     octa::count_launch();
     if (n_edges > 0) { r2d_fill_kernel<<<blocks, threads, 0, stream>>>(w.offs, n_graphs, g, w.prep, w.cursor, w.tile_edges); octa::count_launch(); }
-    r2d_tile_kernel<<<dim3((unsigned)g.ntiles, (unsigned)n_graphs), RT * RT, 0, stream>>>(w.prep, w.offs, g, w.tile_start, w.tile_edges,
-                                                                                      w.big_count, w.big_idx, out_dev);
+    static bool attr_set = false;
+    if (!attr_set) {
+        OCTA_CUDA_CHECK(cudaFuncSetAttribute(r2d_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSm)));
+        attr_set = true;
+    }
+    r2d_tile_kernel<<<dim3((unsigned)g.ntiles, (unsigned)n_graphs), R2D_THREADS, sizeof(TileSm), stream>>>(
+        w.prep, w.offs, g, w.tile_start, w.tile_edges, w.big_count, w.big_idx, out_dev, w.err);
     octa::count_launch();
     OCTA_CUDA_CHECK(cudaGetLastError());
     return OCTA_OK;
@@ -280,6 +385,71 @@ extern "C" int octa_raster2d_host(const double* edges7, int64_t n_edges, int H, 
     if (rc == OCTA_OK && (ce = cudaMemcpy(out, d_o, (size_t)H * W, cudaMemcpyDeviceToHost)) != cudaSuccess) {
         octa::set_error("D2H failed: %s", cudaGetErrorString(ce)); rc = OCTA_E_CUDA;
     }
+    if (rc == OCTA_OK) {        // strokes wider than the outline buffers allow (half width > ~400 px) are reported, never silently approximated
+        const RGeom* unused = nullptr; (void)unused;
+        RGeom g; make_rgeom(H, W, mip_axis, opts, &g);
+        RWork w = rcarve(d_w, 1, n_edges, g.ntiles);
+        int flag = 0;
+        if (cudaMemcpy(&flag, w.err, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess && flag) {
+            octa::set_error("octa_raster2d_host: a stroke is wider than the rasterizer supports (half width > 400 px)"); rc = OCTA_E_ARG;
+        }
+    }
     cleanup();
     return rc;
+}
+
+// ---- CPU-callable restatement of the tile algorithm (same header code, sequential): test hook for the `-m "not gpu"` suite.
+// Rasterizes ONE graph on the host exactly the way r2d_tile_kernel does (per tile, per stroke, per row, closed-form row pieces).
+extern "C" int octa_test_raster2d_rows_host(const double* edges7, int64_t n_edges, int H, int W, int mip_axis, double min_radius,
+                                            double max_radius, uint8_t* out) {
+    OctaVoxOpts o = {min_radius, max_radius, 0, 0};
+    RGeom g;
+    int rc = make_rgeom(H, W, mip_axis, &o, &g);
+    if (rc) return rc;
+    for (size_t i = 0; i < (size_t)H * W; ++i) out[i] = 0;
+    const agg::Clip clip = {0.0, 0.0, (double)W, (double)H};
+    static double vx[agg::MAX_VERT], vy[agg::MAX_VERT];
+    static agg::Line lines[agg::MAX_LINES];
+    struct HostAdd {
+        int* cover; int* area; int* left; int x0, x1;
+        void operator()(int ex, int c, int a) {
+            if (ex < x0) *left += c;
+            else if (ex < x1) { cover[ex - x0] += c; area[ex - x0] += a; }
+        }
+    };
+    int* cover = new int[W + 1]; int* area = new int[W + 1];
+    for (int64_t e = 0; e < n_edges; ++e) {
+        agg::Stroke s;
+        if (!agg::prepare_stroke(edges7 + 7 * e, g.ax0, g.ax1, H, W, g.scale, min_radius, max_radius, &s)) continue;
+        int nc = agg::cap_steps(s.w);
+        if (nc > agg::MAX_CAP_SEG) { delete[] cover; delete[] area; return OCTA_E_ARG; }
+        const int nv = 2 * (nc + 2);
+        for (int k = 0; k < nv; ++k) agg::stroke_vertex(s, nc, k, &vx[k], &vy[k]);
+        int nl = 0, ymin = 0x7fffffff, ymax = -0x7fffffff;
+        for (int k = 0; k < nv; ++k) {
+            const int k2 = k + 1 == nv ? 0 : k + 1;
+            const int m = agg::clip_edge(clip, vx[k], vy[k], vx[k2], vy[k2], lines + nl);
+            for (int q = 0; q < m; ++q) {
+                const int e1 = lines[nl + q].y1 >> agg::SUB_SHIFT, e2 = lines[nl + q].y2 >> agg::SUB_SHIFT;
+                ymin = e1 < ymin ? e1 : ymin; ymin = e2 < ymin ? e2 : ymin; ymax = e1 > ymax ? e1 : ymax; ymax = e2 > ymax ? e2 : ymax;
+            }
+            nl += m;
+        }
+        // split the row into 32-pixel tiles like the kernel does (left = cover of everything to the left of the tile)
+        for (int py = ymin < 0 ? 0 : ymin; py <= ymax && py < H; ++py)
+            for (int tx0 = 0; tx0 < W; tx0 += RT) {
+                int left = 0;
+                for (int x = 0; x < RT; ++x) cover[x] = area[x] = 0;
+                HostAdd add = {cover, area, &left, tx0, tx0 + RT};
+                for (int li = 0; li < nl; ++li) agg::line_row(lines[li], py, add);
+                int run = left;
+                for (int x = 0; x < RT && tx0 + x < W; ++x) {
+                    run += cover[x];
+                    uint8_t* p = out + (size_t)py * W + tx0 + x;
+                    *p = agg::blend_cover(*p, agg::calc_alpha((run << (agg::SUB_SHIFT + 1)) - area[x]));
+                }
+            }
+    }
+    delete[] cover; delete[] area;
+    return OCTA_OK;
 }

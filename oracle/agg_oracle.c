@@ -284,29 +284,25 @@ static uint8_t blend_white(uint8_t v, unsigned a) {
     return (uint8_t)(((((255u << 8) - r) * a) + (r << 8)) / na);
 }
 
-/* edges7: E x 7 (node1 xyz, node2 xyz, radius).  out: H x W gray.  variant bits (exploration of details this restatement could
- * not pin): 1 = no centre-line PathClipper, 2 = no snapping, 4 = exact circle caps are NOT available here (reserved),
- * 8 = coverage rounds down instead of up (opposite polygon orientation). */
-long agg_rasterize(const double* edges7, long E, int H, int W, int ax0, int ax1, double min_radius, double max_radius,
-                   int variant, uint8_t* out) {
+/* seg: n x 4 DATA-space segments (x0, y0, x1, y1): x runs along the image width, y along the rows (y inverted by
+ * ax.invert_yaxis() and flipped back by the renderer), both scaled by the canvas size by transData; lw_points: n line widths in
+ * points (LineCollection linewidths, tree2img.py:84-86,103).  out: H x W gray.  variant bits (exploration of details this
+ * restatement could not pin a priori; 0 = what reproduces the shipped labels): 1 = no centre-line PathClipper, 2 = no snapping,
+ * 8 = coverage rounds down instead of up (opposite polygon orientation), 16 = snap parity from ceil(width) instead of round. */
+long agg_rasterize_segments(const double* seg, const double* lw_points, long n, int H, int W, int variant, uint8_t* out) {
     Ras r;
     memset(&r, 0, sizeof r);
     r.W = W; r.H = H;
     r.clip_x1 = 0; r.clip_y1 = 0; r.clip_x2 = W; r.clip_y2 = H;
     memset(out, 0, (size_t)H * W);
-    const double scale = (double)(W > H ? W : H);
     const double path_clip[4] = {-1.0, -1.0, W + 1.0, H + 1.0};
     static double vx[2 * MAX_CAP + 8], vy[2 * MAX_CAP + 8];
     int* cov = NULL; int* are = NULL; size_t cap_cells = 0;
     long drawn = 0;
-    for (long e = 0; e < E; ++e) {
-        const double* q = edges7 + 7 * e;
-        double radius = q[6];
-        if (radius < min_radius || radius > max_radius) continue;
-        radius *= 1.3;
-        const double thickness = radius * scale;                 /* points */
-        const double width_px = thickness * 100.0 / 72.0;        /* points_to_pixels, dpi = 100 */
-        double x0 = q[ax1] * W, y0 = q[ax0] * H, x1 = q[3 + ax1] * W, y1 = q[3 + ax0] * H;
+    for (long e = 0; e < n; ++e) {
+        const double* q = seg + 4 * e;
+        const double width_px = lw_points[e] * 100.0 / 72.0;     /* points_to_pixels, dpi = 100 (tree2img.py:51) */
+        double x0 = q[0] * W, y0 = q[1] * H, x1 = q[2] * W, y1 = q[3] * H;
         if (!(variant & 1)) {
             if (lb_clip_segment(&x0, &y0, &x1, &y1, path_clip) >= 4) continue;
         }
@@ -367,4 +363,25 @@ long agg_rasterize(const double* edges7, long E, int H, int W, int ax0, int ax1,
     }
     free(cov); free(are);
     return drawn;
+}
+
+/* edges7: E x 7 (node1 xyz, node2 xyz, radius): tree2img.py:66-68,82-86 for every edge, then the collection is drawn */
+long agg_rasterize(const double* edges7, long E, int H, int W, int ax0, int ax1, double min_radius, double max_radius,
+                   int variant, uint8_t* out) {
+    double* seg = (double*)malloc(sizeof(double) * 4 * (size_t)(E > 0 ? E : 1));
+    double* lw = (double*)malloc(sizeof(double) * (size_t)(E > 0 ? E : 1));
+    const double scale = (double)(W > H ? W : H);
+    long n = 0;
+    for (long e = 0; e < E; ++e) {
+        const double* q = edges7 + 7 * e;
+        double radius = q[6];
+        if (radius < min_radius || radius > max_radius) continue;
+        radius *= 1.3;
+        lw[n] = radius * scale;
+        seg[4 * n] = q[ax1]; seg[4 * n + 1] = q[ax0]; seg[4 * n + 2] = q[3 + ax1]; seg[4 * n + 3] = q[3 + ax0];
+        ++n;
+    }
+    long d = agg_rasterize_segments(seg, lw, n, H, W, variant, out);
+    free(seg); free(lw);
+    return d;
 }

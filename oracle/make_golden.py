@@ -10,6 +10,11 @@
   vox_small_s0_*.npz          tree2img.voxelize_forest of graph_small_s0.csv for several requests
   vox_docker_s0.json          sha256 / non-zero count of voxelize_forest(graph_docker_s0, [304,304,4]) and,
                               with --full, of the [1216,1216,16] request (77 s in the reference)
+  graph_nerve_s0.csv          Forest.type 'nerve', 12x12 mm^2 variant (ref_harness.nerve_config, I = 70 + 50, N = 1500)
+  graph_docker_s1.csv.gz, graph_docker_digests.json   (--full) docker config seeds 0-3: bytes + sha256 of the reference's CSV
+  shipped_<name>.csv.gz, shipped_<name>_label.npz     8 of the 500 (graph csv -> 1216^2 1-bit label) pairs the reference ships
+  r2d_small_s0.npz            tree2img.rasterize_forest of the unmodified reference (matplotlib calls served by
+                              oracle/shims/matplotlib -> oracle/agg_oracle.c) for several option sets
 """
 import argparse
 import gzip
@@ -42,6 +47,40 @@ def geometry_mask() -> np.ndarray:
     return g
 
 
+def shipped_pair(name="20230216_232653"):
+    """One of the 500 (graph csv -> 1216^2 1-bit label) pairs the reference ships under datasets/ -- the only pin
+    available for the matplotlib/Agg 2-D path (SURVEY 8c).  Stored as csv.gz + bit-packed label."""
+    from PIL import Image
+    raw = open(os.path.join(rh.REFERENCE_ROOT, "datasets", "vessel_graphs", name + ".csv"), "rb").read()
+    with gzip.GzipFile(os.path.join(GOLD, "shipped_%s.csv.gz" % name), "wb", mtime=0) as f:
+        f.write(raw)
+    lab = np.array(Image.open(os.path.join(rh.REFERENCE_ROOT, "datasets", "labels", name + ".png")))
+    np.savez_compressed(os.path.join(GOLD, "shipped_%s_label.npz" % name), packed=np.packbits(lab), shape=np.array(lab.shape))
+
+
+SHIPPED = ["20230216_232653", "20230216_235406", "20230217_010748", "20230217_015939", "20230217_031216", "20230217_043443",
+           "20230217_050150", "20230217_060539"]      # incl. every kind of near-axis-aligned (snapped) stroke found in the set
+
+
+def raster_goldens():
+    """tree2img.rasterize_forest of the UNMODIFIED reference (through oracle/shims/matplotlib -> oracle/agg_oracle.c) for
+    graph_small_s0.csv: resolutions, MIP axes, radius filter, subtree dropout with a seeded Python RNG, shared blackdict."""
+    import random
+    rows = rh.read_csv_rows(os.path.join(GOLD, "graph_small_s0.csv"))
+    out = {}
+    out["a_304x304_mip2"], _ = rh.rasterize(rows, [304, 304], 2)
+    out["b_200x120_mip0_minr"], _ = rh.rasterize(rows, [200, 120], 0, min_radius=0.001)
+    out["c_96x160_mip1_maxr"], _ = rh.rasterize(rows, [96, 160], 1, max_radius=0.002)
+    random.seed(153)
+    rl = []
+    out["d_304x304_dropout"], bd = rh.rasterize(rows, [304, 304], 2, radius_list=rl, max_dropout_prob=0.3)
+    out["d_next_random"] = np.array([random.random()])
+    out["d_radius_list"] = np.array(rl)
+    out["d_blackdict"] = np.array(sorted(bd.keys()))
+    out["e_1216x1216_blackdict"], _ = rh.rasterize(rows, [1216, 1216], 2, min_radius=0.0009, blackdict=bd)
+    np.savez_compressed(os.path.join(GOLD, "r2d_small_s0.npz"), **out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
@@ -67,12 +106,25 @@ def main():
         vol, _ = rh.voxelize(rows, dims, **kw)
         np.savez_compressed(os.path.join(GOLD, "vox_small_s0_%s.npz" % name), vol=vol, dims=np.array(dims),
                             kw=json.dumps(kw))
+    art, ven, _ = rh.run_growth(rh.nerve_config(I=(70, 50), N=1500), 0)
+    with open(os.path.join(GOLD, "graph_nerve_s0.csv"), "wb") as f:
+        f.write(rh.csv_bytes(art, ven))
+    for name in SHIPPED:
+        shipped_pair(name)
+    raster_goldens()
     if a.full:
+        # docker config verbatim: ~100 s per seed in the reference.  Seeds 0 and 1 are stored, 0-3 pinned by sha256.
+        dig = {}
+        for seed in range(4):
+            art, ven, _ = rh.run_growth(rh.load_config(), seed)
+            data = rh.csv_bytes(art, ven)
+            dig["docker_s%d" % seed] = {"bytes": len(data), "sha256": hashlib.sha256(data).hexdigest(), "rows": len(art) + len(ven)}
+            if seed < 2:
+                with gzip.GzipFile(os.path.join(GOLD, "graph_docker_s%d.csv.gz" % seed), "wb", mtime=0) as f:
+                    f.write(data)
+        with open(os.path.join(GOLD, "graph_docker_digests.json"), "w") as f:
+            json.dump(dig, f, indent=1)
         p = os.path.join(GOLD, "graph_docker_s0.csv.gz")
-        if not os.path.exists(p):
-            art, ven, _ = rh.run_growth(rh.load_config(), 0)
-            with gzip.GzipFile(p, "wb", mtime=0) as f:
-                f.write(rh.csv_bytes(art, ven))
         import csv, io
         rows = list(csv.DictReader(io.StringIO(gzip.open(p, "rt", newline="").read(), newline="")))
         out = {}
@@ -87,13 +139,3 @@ def main():
 if __name__ == "__main__":
     main()
 
-
-def shipped_pair(name="20230216_232653"):
-    """One of the 500 (graph csv -> 1216^2 1-bit label) pairs the reference ships under datasets/ -- the only pin
-    available for the matplotlib/Agg 2-D path (SURVEY 8c).  Stored as csv.gz + bit-packed label."""
-    from PIL import Image
-    raw = open(os.path.join(rh.REFERENCE_ROOT, "datasets", "vessel_graphs", name + ".csv"), "rb").read()
-    with gzip.GzipFile(os.path.join(GOLD, "shipped_%s.csv.gz" % name), "wb", mtime=0) as f:
-        f.write(raw)
-    lab = np.array(Image.open(os.path.join(rh.REFERENCE_ROOT, "datasets", "labels", name + ".png")))
-    np.savez_compressed(os.path.join(GOLD, "shipped_%s_label.npz" % name), packed=np.packbits(lab), shape=np.array(lab.shape))

@@ -130,6 +130,14 @@ def voxelize(forest, dims, **kw):
     return t2i.voxelize_forest(forest, dims, **kw)
 
 
+def rasterize(forest, image_resolution, MIP_axis=2, **kw):
+    """The UNMODIFIED tree2img.rasterize_forest (tree2img.py:12-114).  matplotlib is absent from this image: the calls it
+    makes land in oracle/shims/matplotlib, which renders the LineCollection with oracle/agg_oracle.c (the Agg restatement that
+    reproduces the reference's 500 shipped labels bit for bit)."""
+    _, _, t2i = import_reference()
+    return t2i.rasterize_forest(forest, image_resolution, MIP_axis, **kw)
+
+
 if __name__ == "__main__":
     import argparse
 
