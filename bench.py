@@ -202,15 +202,7 @@ def main():
         return [s0 + i for i in range(B)]
 
     phase = {"grow_ms": 0.0, "vox_ms": 0.0, "n": 0, "sumA": 0, "sumM": 0, "sumP": 0, "sumS": 0, "V": 0, "E": 0}
-    vol_host = None
-    if args.d2h_volume:
-        shape = tree2img.voxel_volume_shape(DIMS)
-        vol_host = torch.empty((B, *shape), dtype=torch.uint16).pin_memory()
-
     def account(out, d2h):
-        if d2h and vol_host is not None:
-            vol_host.copy_(out["volume"], non_blocking=True)
-            torch.cuda.synchronize()
         phase["grow_ms"] += out["grow_device_ms"]
         phase["n"] += 1
         for st in out["stats"]:
@@ -231,7 +223,7 @@ def main():
             s = seeds()
             batches += [s[j:j + SB] for j in range(0, B, SB)]
         h2d = d2h_b = 0
-        for i, out in enumerate(pipe.run_pipelined(batches, d2h=d2h, csv=d2h, in_flight=args.in_flight)):
+        for i, out in enumerate(pipe.run_pipelined(batches, d2h=d2h, csv=d2h, in_flight=args.in_flight, d2h_volume=d2h and args.d2h_volume)):
             last = account(out, d2h)
             if d2h:
                 h2d += int(out["h2d_bytes"]); d2h_b += int(out["d2h_bytes"])
@@ -285,7 +277,8 @@ def main():
     ve[1].record()
     torch.cuda.synchronize()
     vox_ms = ve[0].elapsed_time(ve[1]) / nrep
-    run_steps(max(1, (NSETS + NSUB - 1) // NSUB), True)        # (pinned result buffers of every set)
+    NSETS_H = Pipeline.buffer_sets(args.in_flight, True)
+    run_steps(max(1, (NSETS_H + NSUB - 1) // NSUB), True)      # (pinned result buffers of every set)
     ms_e2e, last = timed(lambda k: run_steps(k, True), max(2, args.steps))
     clocks = sampler.stop() if rank == 0 else None
     gan_line = None
@@ -365,7 +358,7 @@ def main():
                        "phase_ms": {"growth_loop_device": grow_ms, "voxelize_4_kernels": vox_ms, "step": ms}},
             "gpu_launches": int(launches),
             "e2e": {"value": B * world / (ms_e2e * 1e-3), "unit": "graphs/s", "h2d_bytes_per_step": int(last["h2d_bytes"]),
-                    "d2h_bytes_per_step": int(last["d2h_bytes"] + (vol_host.numel() * 2 if vol_host is not None else 0)),
+                    "d2h_bytes_per_step": int(last["d2h_bytes"]),
                     "note": "host API: + CSV text of every graph (byte-exact), + D2H of label (1216^2 u8) and image (304^2 u8) "
                             "into pinned memory; growth topology D2H and edge-row H2D are inside both numbers"},
             "roofline": {"bound": "hbm", "achieved": vox_ach, "peak": peak, "unit": "GB/s", "frac": vox_ach / peak,

@@ -82,12 +82,21 @@ int octa_voxelize_host(const double* edges7, int64_t n_edges, const int dims[3],
  * visualize_vessel_graphs.py:95 and data/data_transforms.py:384.  Output: uint8 gray [H][W] per graph
  * (H = image_resolution[1], W = image_resolution[0]); pixel row = pos[ax0]*H, col = pos[ax1]*W with
  * ax = {0,1,2} minus mip_axis.  Uses OctaVoxOpts.min_radius / max_radius (tree2img.py:66-68); `ignore_z` is unused.
- * Parity with Agg is statistical (no matplotlib in this image).
+ * All pixel arithmetic is the integer scanline arithmetic of Agg 2.4 (cover / area cells in 24.8 fixed point, 8-bit coverage,
+ * 8-bit "over" blending in list order): the output equals oracle/agg_oracle.c pixel for pixel, and through PIL's
+ * convert("1") the 500 label PNGs the reference ships bit for bit.
+ * octa_raster2d_batch_layers_dev: the first layer_split[g] edges of graph g and the remaining ones are rasterized on separate
+ * canvases and combined with max -- generate_vessel_graph.py:80-85 (arterial / venous forest, np.maximum).
+ * Strokes wider than ~800 px are not supported (octa_raster2d_host reports them; the batch call sets an error flag in
+ * the workspace).
  * ---------------------------------------------------------------------------------------------- */
 size_t octa_raster2d_workspace_bytes(int n_graphs, int64_t n_edges, int H, int W);
 int octa_raster2d_batch_dev(const double* edges7_dev, const int64_t* edge_offsets_host, int n_graphs, int H, int W,
                             int mip_axis, const OctaVoxOpts* opts, uint8_t* out_dev, void* workspace_dev,
                             size_t workspace_bytes, void* stream);
+int octa_raster2d_batch_layers_dev(const double* edges7_dev, const int64_t* edge_offsets_host, const int64_t* layer_split_host,
+                                   int n_graphs, int H, int W, int mip_axis, const OctaVoxOpts* opts, uint8_t* out_dev,
+                                   void* workspace_dev, size_t workspace_bytes, void* stream);
 int octa_raster2d_host(const double* edges7, int64_t n_edges, int H, int W, int mip_axis, const OctaVoxOpts* opts,
                        uint8_t* out);
 

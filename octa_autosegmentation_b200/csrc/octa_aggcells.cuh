@@ -42,6 +42,12 @@ struct Line { int x1, y1, x2, y2; };
 
 OCTA_AGG_HD int iround(double v) { return (int)((v < 0.0) ? v - 0.5 : v + 0.5); }
 OCTA_AGG_HD long long floordiv(long long a, long long b) {      // b > 0; agg: delta = p / dy; if (p % dy < 0) delta--
+    if (a > -2147483647LL && a < 2147483647LL && b < 2147483647LL) {       // the usual case: 32-bit division
+        const int ai = (int)a, bi = (int)b;
+        int q = ai / bi;
+        if (ai % bi < 0) --q;
+        return q;
+    }
     long long q = a / b;
     if (a % b < 0) --q;
     return q;
@@ -237,8 +243,10 @@ OCTA_AGG_HD void render_hline(int x1, int y1, int x2, int y2, Add& add) {
     add(ex1, delta, (fx2 + SUB_SCALE - first) * delta);
 }
 
-// ---- rasterizer_cells_aa::line restricted to scanline `ey`.  Agg's loop reaches the boundary that lies `dist` sub-pixels of y
-// away from y1 at x1 + floor(dist * dx / |dy|) (its delta / mod / lift / rem recurrence is exactly this floor division).
+// ---- rasterizer_cells_aa::line restricted to scanline `ey`.  Agg's loop reaches the scanline boundary that lies `dist`
+// sub-pixels of y away from y1 at x1 + floor(dist * dx / |dy|) (its delta / mod / lift / rem recurrence is exactly this floor
+// division), entering a scanline at fraction 0 (going down) or 256 (going up) and leaving at the opposite one.  One code path
+// for both directions (the lanes of a warp hold lines of either direction).
 template <class Add>
 OCTA_AGG_HD void line_row(const Line& L, int ey, Add& add) {
     const int x1 = L.x1, y1 = L.y1, x2 = L.x2, y2 = L.y2;
@@ -248,10 +256,11 @@ OCTA_AGG_HD void line_row(const Line& L, int ey, Add& add) {
     if (ey1 == ey2) { render_hline(x1, fy1, x2, fy2, add); return; }
     const int dx = x2 - x1;
     const int dy = y2 - y1;
+    const bool up = dy < 0;
+    const int first = up ? 0 : SUB_SCALE;              // fraction at which the line leaves a scanline
     if (dx == 0) {
         const int ex = x1 >> SUB_SHIFT;
         const int two_fx = (x1 - (ex << SUB_SHIFT)) << 1;
-        const int first = dy < 0 ? 0 : SUB_SCALE;
         int delta;
         if (ey == ey1) delta = first - fy1;
         else if (ey == ey2) delta = fy2 - SUB_SCALE + first;
@@ -259,20 +268,17 @@ OCTA_AGG_HD void line_row(const Line& L, int ey, Add& add) {
         add(ex, delta, two_fx * delta);
         return;
     }
-    if (dy > 0) {
-        const int j = ey - ey1;
-        const int xa = j == 0 ? x1 : x1 + (int)floordiv(((long long)j * SUB_SCALE - fy1) * dx, dy);
-        if (ey == ey2) { render_hline(xa, 0, x2, fy2, add); return; }
-        const int xb = x1 + (int)floordiv(((long long)(j + 1) * SUB_SCALE - fy1) * dx, dy);
-        render_hline(xa, j == 0 ? fy1 : 0, xb, SUB_SCALE, add);
-    } else {
-        const int ady = -dy;
-        const int j = ey1 - ey;
-        const int xa = j == 0 ? x1 : x1 + (int)floordiv(((long long)fy1 + (long long)(j - 1) * SUB_SCALE) * dx, ady);
-        if (ey == ey2) { render_hline(xa, SUB_SCALE, x2, fy2, add); return; }
-        const int xb = x1 + (int)floordiv(((long long)fy1 + (long long)j * SUB_SCALE) * dx, ady);
-        render_hline(xa, j == 0 ? fy1 : SUB_SCALE, xb, 0, add);
-    }
+    const int ady = up ? -dy : dy;
+    const int j = up ? ey1 - ey : ey - ey1;            // scanlines since the start
+    // distance (sub-pixels of y) from y1 to the boundary through which the line ENTERS scanline ey (j >= 1) / LEAVES it
+    const long long d_in = up ? (long long)fy1 + (long long)(j - 1) * SUB_SCALE : (long long)j * SUB_SCALE - fy1;
+    const long long d_out = d_in + SUB_SCALE;
+    const int xa = j == 0 ? x1 : x1 + (int)floordiv(d_in * dx, ady);
+    const int ya = j == 0 ? fy1 : SUB_SCALE - first;
+    const bool last = ey == ey2;
+    const int xb = last ? x2 : x1 + (int)floordiv((j == 0 ? (up ? (long long)fy1 : (long long)SUB_SCALE - fy1) : d_out) * dx, ady);
+    const int yb = last ? fy2 : first;
+    render_hline(xa, ya, xb, yb, add);
 }
 
 // rasterizer_scanline_aa::calculate_alpha (fill_non_zero, gamma = identity); v = (running cover << 9) - area of the cell
@@ -290,7 +296,12 @@ OCTA_AGG_HD unsigned char blend_cover(unsigned char v, int cover) {
     if (!alpha) return v;
     const unsigned r = (unsigned)v * 255u;
     const unsigned na = ((alpha + 255u) << 8) - alpha * 255u;
-    return (unsigned char)(((((255u << 8) - r) * alpha) + (r << 8)) / na);
+    const unsigned num = (((255u << 8) - r) * alpha) + (r << 8);
+    // num < 2^24 and na < 2^16 are exact in float; the rounded quotient is off by at most one, which the check repairs
+    unsigned q = (unsigned)((float)num / (float)na);
+    if (q * na > num) --q;
+    else if ((q + 1) * na <= num) ++q;
+    return (unsigned char)q;
 }
 
 }  // namespace agg

@@ -179,8 +179,21 @@ int init_graph(const OctaGrowConfig& c, uint64_t seed, HostGraphInit* h) {
     return OCTA_OK;
 }
 
+// Mode parameters as the reference sees them: init_params_from_config runs only for a mode whose NAME differs from the first
+// mode's (greenhouse.py:84-85), so a later mode that reuses that name keeps gamma / phi / omega / kappa (and eps / delta / I / N)
+// of whatever mode was initialised last.  eff[mi] = index of the mode whose parameters are live during mode mi.
+void effective_modes(const OctaGrowConfig& c, int eff[8]) {
+    int cur = 0;
+    for (int mi = 0; mi < c.n_modes && mi < 8; ++mi) {
+        if (c.modes[mi].reinit) cur = mi;
+        eff[mi] = cur;
+    }
+}
+
 // greenhouse.py:34-51 / :83-90 / :139-147 -> one IterP per iteration
 void build_schedule(const OctaGrowConfig& c, std::vector<IterP>* out) {
+    int eff[8] = {0};
+    effective_modes(c, eff);
     const double ps = c.param_scale;
     double d = c.d / ps;
     const double r = c.r / ps;
@@ -198,8 +211,9 @@ void build_schedule(const OctaGrowConfig& c, std::vector<IterP>* out) {
     init_params(c.modes[0]);
     int t = 0, iter = 0;
     for (int mi = 0; mi < c.n_modes; ++mi) {
-        const OctaGrowMode& m = c.modes[mi];
-        if (m.reinit) init_params(m);
+        const OctaGrowMode& m0 = c.modes[mi];
+        if (m0.reinit) init_params(m0);
+        const OctaGrowMode& m = c.modes[eff[mi]];       // gamma / phi / omega / kappa change with init_params only
         if (I <= 0) continue;
         const int t_end = t + I;
         for (; t < t_end; ++t) {
@@ -211,9 +225,9 @@ void build_schedule(const OctaGrowConfig& c, std::vector<IterP>* out) {
             P.rotation_radius = c.rotation_radius / ps; P.faz_cx = c.faz_center[0]; P.faz_cy = c.faz_center[1];
             P.param_scale = ps;
             for (int k = 0; k < 3; ++k) P.shape[k] = c.size[k];
-            P.N = N; P.t = t; P.first_mode = m.first_mode; P.mode_idx = mi; P.iter = iter++;
+            P.N = N; P.t = t; P.first_mode = m0.first_mode; P.mode_idx = mi; P.iter = iter++;
             P.geom_n = c.geometry ? c.geom_dims[0] : 0;
-            for (int q = 0; q < 8; ++q) P.kap_tab[q] = q < c.n_modes ? c.modes[q].kappa : 4.0;
+            for (int q = 0; q < 8; ++q) P.kap_tab[q] = q < c.n_modes ? c.modes[eff[q]].kappa : 4.0;
             P.kap_tab[8] = 4.0;
             for (int q = 0; q < 9; ++q) P.leafc_tab[q] = pow(P.r, P.kap_tab[q]);
             out->push_back(P);
@@ -287,7 +301,9 @@ void finalize_forest(const OctaGrowConfig& c, int n, const double* px, const dou
     std::vector<double> rad(n, r), kap(n);
     std::vector<int> c0(n, -1), c1(n, -1);
     std::vector<unsigned char> nch(n, 0);
-    for (int i = 0; i < n; ++i) { const int m = meta[i] >> 1; kap[i] = (meta[i] != 0xff && m < c.n_modes) ? c.modes[m].kappa : 4.0; }
+    int eff[8] = {0};
+    effective_modes(c, eff);
+    for (int i = 0; i < n; ++i) { const int m = meta[i] >> 1; kap[i] = (meta[i] != 0xff && m < c.n_modes) ? c.modes[eff[m]].kappa : 4.0; }
     // Final Murray radii with libm pow (exactly CPython's float.__pow__, arterial_tree.py:180).  The reference walks
     // to the root after every branch event (122 k walk steps per graph); the radius a node ENDS with is the value of
     // the last walk through it, i.e. f(children's final radii) -- the last branch event below a node updates it after

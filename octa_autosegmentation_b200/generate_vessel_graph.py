@@ -1,21 +1,24 @@
-"""Drop-in for the reference's generate_vessel_graph.py (same flags, same files on disk), with the growth,
-rasterization and voxelization running on the GPU in batches instead of one CPU process per sample.
+"""Drop-in for the reference's generate_vessel_graph.py (same flags, same files on disk), with growth, rasterization and
+voxelization running on the GPU through the batched, software-pipelined engine (`pipeline.Pipeline.run_pipelined`: several
+growth loops in flight, post-processing and CSV text of finished batches beside them) instead of one CPU process per sample.
 
     python -m octa_autosegmentation_b200.generate_vessel_graph --config_file cfg.yml --num_samples 64 \
-        [--threads T] [--debug] [--seed S] [--batch B] [--Greenhouse.param_scale 3 ...dotted overrides]
+        [--threads T] [--debug] [--seed S] [--batch B] [--in_flight L] [--gather] [--Greenhouse.param_scale 3 ...dotted overrides]
 
 Per sample, as generate_vessel_graph.py:24-89:  <output.directory>/<YYYYmmdd_HHMMSS>_<uuid4>/
     config.yml                      resolved config (yaml.dump)
     <dirname>.csv                   node1,node2,radius rows (arterial trees first), CRLF          (save_trees)
     art_ven_img_gray.npy            uint8 volume, np.maximum(arterial, venous)                    (save_3D_volumes: npy)
     art_ven_img_gray.png            uint8 gray image, np.maximum(arterial raster, venous raster)  (save_2D_image)
-New optional flags: --seed (sample i uses seed+i for BOTH generators; default: drawn from os.urandom, i.e. unseeded
-like the reference), --batch (samples per GPU launch).  Under torchrun every rank takes the samples i with
-i mod world_size == rank and writes its own files (no collective on the data path).
+New optional flags: --seed (sample i uses seed+i for BOTH generators; default: drawn from os.urandom, i.e. unseeded like the
+reference), --batch (samples per growth loop), --in_flight (growth loops in flight), --threads (file-writer threads).  Under
+torchrun every rank takes the samples i with i mod world_size == rank (no collective on the data path) and writes its own
+files; with --gather the finished edge tables travel to rank 0 in ONE NCCL gather at the end and rank 0 writes every CSV.
 """
 from __future__ import annotations
 
 import argparse
+import concurrent.futures as cf
 import os
 import sys
 import warnings
@@ -25,9 +28,9 @@ from uuid import uuid4
 import numpy as np
 import yaml
 
-from . import graph_io, growth, tree2img
+from . import graph_io, growth
 from .config import apply_cli_overrides_from_unknown_args, read_config
-from .pipeline import shard_seeds
+from .pipeline import Pipeline, shard_seeds
 
 
 def prepare_output_dir(out_cfg: dict) -> str:
@@ -37,21 +40,24 @@ def prepare_output_dir(out_cfg: dict) -> str:
     return d
 
 
-def write_sample(config: dict, art: np.ndarray, ven: np.ndarray) -> str:
-    """generate_vessel_graph.py:28-30,43-86 for one grown sample."""
+def volume_dimension(config: dict):
+    """generate_vessel_graph.py:43 -- int(d) for d in greenhouse.simspace.shape * image_scale_factor."""
+    return [int(d) for d in growth.simspace_shape(config) * config["output"]["image_scale_factor"]]
+
+
+def write_sample(config: dict, csv_bytes, image, volume) -> str:
+    """Files of one grown sample (generate_vessel_graph.py:28-30,59-86); csv_bytes / image / volume may be None."""
     from PIL import Image
 
     out_cfg = config["output"]
     out_dir = prepare_output_dir(out_cfg)
     with open(os.path.join(out_dir, "config.yml"), "w") as f:
         yaml.dump(config, f)
-    shape = np.array([config["Greenhouse"]["SimulationSpace"][k] for k in ("no_voxel_x", "no_voxel_y", "no_voxel_z")])
-    volume_dimension = [int(d) for d in shape * out_cfg["image_scale_factor"]]
-    if out_cfg["save_trees"]:
-        name = out_dir.split("/")[-1]
-        graph_io.write_csv(os.path.join(out_dir, name + ".csv"), np.concatenate([art, ven]))
-    if out_cfg.get("save_3D_volumes"):
-        vol = np.maximum(tree2img.voxelize_edges(art, volume_dimension), tree2img.voxelize_edges(ven, volume_dimension)).astype(np.uint8)
+    if csv_bytes is not None:
+        with open(os.path.join(out_dir, out_dir.split("/")[-1] + ".csv"), "wb") as f:
+            f.write(csv_bytes)
+    if volume is not None:
+        vol = volume.astype(np.uint8)
         if out_cfg["save_3D_volumes"] == "npy":
             np.save(f"{out_dir}/art_ven_img_gray.npy", vol)
         else:
@@ -60,15 +66,42 @@ def write_sample(config: dict, art: np.ndarray, ven: np.ndarray) -> str:
             except ImportError as e:
                 raise RuntimeError("save_3D_volumes: nifti needs nibabel, which is not installed; use 'npy'") from e
             nib.save(nib.Nifti1Image(vol, np.eye(4)), f"{out_dir}/art_ven_img_gray.nii.gz")
-    if out_cfg["save_2D_image"]:
-        image_res = [*volume_dimension]
-        del image_res[out_cfg["proj_axis"]]
-        a = tree2img.raster_edges(art, image_res, out_cfg["proj_axis"])
-        v = tree2img.raster_edges(ven, image_res, out_cfg["proj_axis"])
-        Image.fromarray(np.maximum(a, v).astype(np.uint8)).save(f"{out_dir}/art_ven_img_gray.png")
-    if out_cfg.get("save_stats"):
-        warnings.warn("output.save_stats (matplotlib statistic plots) is not produced by the GPU path")
+    if image is not None:
+        Image.fromarray(image.astype(np.uint8)).save(f"{out_dir}/art_ven_img_gray.png")
     return out_dir
+
+
+def generate(config: dict, seeds, batch: int = 32, in_flight: int = 8, writer_threads: int = 4, device=None, gather: bool = False,
+             on_progress=None):
+    """Grow `seeds` and write the reference's files.  Returns (output dirs in seed order, {seed: edges7} when gather else {})."""
+    out_cfg = config["output"]
+    dims = volume_dimension(config)
+    image_res = [*dims]
+    del image_res[out_cfg["proj_axis"]]
+    save3d = bool(out_cfg.get("save_3D_volumes"))
+    pipe = Pipeline(config, device=device, volume_dims=dims, label_res=None, image_res=image_res, mip_axis=out_cfg["proj_axis"],
+                    voxelize=save3d)
+    if save3d:
+        in_flight = min(in_flight, 2)               # every buffer set holds a pinned copy of the batch's volumes
+    batches = [list(seeds[k:k + batch]) for k in range(0, len(seeds), batch)]
+    dirs, tables, futs = [], {}, []
+    write_csv = bool(out_cfg["save_trees"]) and not gather
+    with cf.ThreadPoolExecutor(max_workers=max(1, writer_threads)) as writers:
+        for bi, out in enumerate(pipe.run_pipelined(batches, d2h=True, csv=write_csv, in_flight=in_flight, d2h_volume=save3d)):
+            n = len(batches[bi])
+            for i in range(n):
+                img = np.array(out["image_host"][i]) if out_cfg["save_2D_image"] else None        # copies: the pinned buffers are recycled
+                vol = np.array(out["volume_host"][i]) if save3d else None
+                futs.append(writers.submit(write_sample, config, out["csv"][i] if write_csv else None, img, vol))
+                if gather:
+                    tables[batches[bi][i]] = np.concatenate(out["graphs"][i]).copy()
+            if save3d:                                 # 157 MB per sample: let the files land before the next batch's copies
+                for f in futs:
+                    f.result()
+            if on_progress:
+                on_progress(sum(len(b) for b in batches[:bi + 1]))
+        dirs = [f.result() for f in futs]
+    return dirs, tables
 
 
 def main(argv=None):
@@ -76,9 +109,11 @@ def main(argv=None):
     parser.add_argument("--config_file", type=str, required=True)
     parser.add_argument("--num_samples", type=int, default=1)
     parser.add_argument("--debug", action="store_true")
-    parser.add_argument("--threads", help="Accepted for compatibility (host-side writer threads).", type=int, default=-1)
+    parser.add_argument("--threads", help="Number of file-writer threads. By default all available cores but one (max 8).", type=int, default=-1)
     parser.add_argument("--seed", type=int, default=None, help="base seed; sample i uses seed+i (default: unseeded)")
-    parser.add_argument("--batch", type=int, default=64, help="samples per GPU launch")
+    parser.add_argument("--batch", type=int, default=32, help="samples per growth loop")
+    parser.add_argument("--in_flight", type=int, default=8, help="growth loops in flight per GPU")
+    parser.add_argument("--gather", action="store_true", help="torchrun only: one NCCL gather of the edge tables; rank 0 writes every CSV")
     args, unknown = parser.parse_known_args(argv)
     if args.debug:
         warnings.filterwarnings("error")
@@ -87,46 +122,40 @@ def main(argv=None):
     apply_cli_overrides_from_unknown_args(config, unknown)
     assert config["output"].get("save_3D_volumes") in [None, "npy", "nifti"], \
         f"Your provided option {config['output'].get('save_3D_volumes')} for 'save_3D_volumes' does not exist. Choose one of 'null', 'npy' or 'nifti'."
+    if config["output"].get("save_stats"):
+        warnings.warn("output.save_stats (matplotlib statistic plots) is not produced by the GPU path")
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    if world > 1:
-        import torch
-        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    import torch
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    gather = args.gather and world > 1
+    if gather:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     base = args.seed if args.seed is not None else int.from_bytes(os.urandom(4), "little") % (2 ** 32 - args.num_samples - 1)
     seeds = shard_seeds(base, args.num_samples, rank, world)
-    done, failed = 0, []
-    ctx = None
-    pending = None          # the previous chunk's files are written by a worker thread while the next chunk grows
-
-    def write_chunk(graphs):
-        for art, ven in graphs:
-            write_sample(config, art, ven)
-        return len(graphs)
-
-    import concurrent.futures as cf
-    with cf.ThreadPoolExecutor(max_workers=1) as writer:
-        for k in range(0, len(seeds), args.batch):
-            chunk = seeds[k:k + args.batch]
-            try:
-                if ctx is None:
-                    ctx = growth.GrowContext(config, min(args.batch, len(seeds)))
-                graphs, _, _ = ctx.run(chunk)
-            except Exception as e:       # the reference swallows worker exceptions (futures never read); we report them
-                failed.append((chunk, repr(e)))
-                continue
-            if pending is not None:
-                done += pending.result()
-                print(f"[rank {rank}] generated {done}/{len(seeds)} vessel graphs", flush=True)
-            pending = writer.submit(write_chunk, graphs)
-        if pending is not None:
-            done += pending.result()
-            print(f"[rank {rank}] generated {done}/{len(seeds)} vessel graphs", flush=True)
-    if ctx is not None:
-        ctx.close()
-    if failed:
-        for chunk, msg in failed:
-            print(f"[rank {rank}] FAILED seeds {chunk[0]}..{chunk[-1]}: {msg}", file=sys.stderr)
-        return 1
-    return 0
+    threads = args.threads if args.threads > 0 else max(1, min(8, (os.cpu_count() or 2) - 1))
+    rc = 0
+    try:
+        dirs, tables = generate(config, seeds, batch=max(1, min(args.batch, max(len(seeds), 1))), in_flight=args.in_flight,
+                                writer_threads=threads, device=torch.device("cuda", local), gather=gather,
+                                on_progress=lambda k: print(f"[rank {rank}] generated {k}/{len(seeds)} vessel graphs", flush=True))
+        if gather:
+            from .distributed import gather_edge_tables
+            allt = gather_edge_tables(tables, dst=0)
+            if rank == 0 and config["output"]["save_trees"]:
+                # rank 0 owns the CSV files of the whole job (sample order); its own samples already have their folders
+                mine = dict(zip(seeds, dirs))
+                for sid in sorted(allt):
+                    d = mine.get(sid) or prepare_output_dir(config["output"])
+                    graph_io.write_csv(os.path.join(d, d.split("/")[-1] + ".csv"), allt[sid])
+    except Exception as e:       # the reference swallows worker exceptions (futures never read); we report them
+        print(f"[rank {rank}] FAILED: {e!r}", file=sys.stderr)
+        rc = 1
+    if gather:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return rc
 
 
 if __name__ == "__main__":

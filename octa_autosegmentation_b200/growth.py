@@ -38,6 +38,16 @@ class OctaGrowStats(ctypes.Structure):
         [("commit_cycles", ctypes.c_int64 * 4), ("replay_detail", ctypes.c_int64 * 8), ("err", ctypes.c_int32), ("n_iters", ctypes.c_int32)]
 
 
+def simspace_shape(config: dict) -> np.ndarray:
+    """greenhouse.simspace.shape (simulation_space.py:29-34): the normalised shape of the sampling geometry when
+    SimulationSpace.oxygen_sample_geometry_path is set, else (no_voxel_x, no_voxel_y, no_voxel_z)."""
+    ss = config["Greenhouse"]["SimulationSpace"]
+    if ss.get("oxygen_sample_geometry_path") is not None:
+        shape = np.array(np.load(ss["oxygen_sample_geometry_path"], mmap_mode="r").shape, dtype=np.float64)
+        return shape / shape.max()
+    return np.array([float(ss["no_voxel_x"]), float(ss["no_voxel_y"]), float(ss["no_voxel_z"])])
+
+
 def make_config(config: dict, cap_nodes: int = 0, cap_sinks: int = 0) -> OctaGrowConfig:
     g, f = config["Greenhouse"], config["Forest"]
     ss = g["SimulationSpace"]

@@ -28,7 +28,7 @@ class Pipeline:
         self.config = config
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.volume_dims = [int(d) for d in volume_dims]
-        self.label_res = [int(d) for d in label_res]
+        self.label_res = [int(d) for d in label_res] if label_res is not None else None
         self.image_res = [int(d) for d in image_res]
         self.mip_axis = int(mip_axis)
         self.voxelize = bool(voxelize)
@@ -84,8 +84,10 @@ class Pipeline:
             ctypes.memmove(host_edges.data_ptr(), ctx_edges.data_ptr(), E * 56)
             return {"n": n, "cap": cap, "host_edges": host_edges, "offs": offs, "n_art": n_art, "stats": stats, "grow_ms": grow_ms}
 
-    def _post_stage(self, g: dict, slot: int, d2h: bool, csv: bool, stream=None) -> dict:
-        """Edge rows -> device, voxelize, 2-D rasters, optional D2H + CSV text, all on `stream` (default: current)."""
+    def _post_stage(self, g: dict, slot: int, d2h: bool, csv: bool, stream=None, d2h_volume: bool = False) -> dict:
+        """Edge rows -> device, voxelize, 2-D rasters, optional D2H + CSV text, all ENQUEUED on `stream` (default: current).
+        Nothing here waits for the device: out["ready"] is recorded behind the last operation and `_finish` (or the caller)
+        waits on it; the CSV text is formatted by a thread pool meanwhile."""
         torch = self.torch
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream() if stream is None else stream
@@ -100,81 +102,111 @@ class Pipeline:
                 h2d.record(stream)
                 self._h2d_done[slot] = h2d
                 graphs = [(he[offs[i]:offs[i] + n_art[i]], he[offs[i] + n_art[i]:offs[i + 1]]) for i in range(n)]   # views
-                out = {"graphs": graphs, "stats": g["stats"], "offsets": offs, "grow_device_ms": g["grow_ms"], "edges_host": he[:E]}
+                out = {"graphs": graphs, "stats": g["stats"], "offsets": offs, "n_art": n_art, "grow_device_ms": g["grow_ms"],
+                       "edges_host": he[:E], "h2d_bytes": int(E * 56), "d2h_bytes": 0}
+                from . import _lib
+                L = _lib.lib()
                 if self.voxelize:
                     shape = tree2img.voxel_volume_shape(self.volume_dims)
                     vol = self._tensor("vol" + sfx, (n, *shape), torch.uint16)
-                    from . import _lib
                     # sized for the edge capacity, not for this batch: a growing workspace would mean a cudaMalloc (device-wide
                     # synchronisation) in the middle of the growth loops that are in flight
-                    need = int(_lib.lib().octa_voxelize_workspace_bytes(n, max(E, cap), _lib.int3(self.volume_dims)))
+                    need = int(L.octa_voxelize_workspace_bytes(n, max(E, cap), _lib.int3(self.volume_dims)))
                     ws = self._tensor("vox_ws" + sfx, (need,), torch.uint8)
                     vol = tree2img.voxelize_batch_device(edges_dev[:max(E, 1)], offs, self.volume_dims, out=vol, workspace=ws)
                     out["volume"] = vol
-                from . import _lib as _l
-                L = _l.lib()
                 L.octa_raster2d_workspace_bytes.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int]
                 L.octa_raster2d_workspace_bytes.restype = ctypes.c_size_t
-                lab = self._tensor("label" + sfx, (n, self.label_res[1], self.label_res[0]), torch.uint8)
-                ws_l = self._tensor("r2d_ws_label" + sfx, (int(L.octa_raster2d_workspace_bytes(n, max(E, cap), self.label_res[1], self.label_res[0])),), torch.uint8)
-                tree2img.raster_batch_device(edges_dev, offs, self.label_res, self.mip_axis, out=lab, workspace=ws_l)
+                # label: ONE collection over all rows of the csv, as visualize_vessel_graphs.py:95 renders it
+                lab = None
+                if self.label_res is not None:
+                    lab = self._tensor("label" + sfx, (n, self.label_res[1], self.label_res[0]), torch.uint8)
+                    ws_l = self._tensor("r2d_ws_label" + sfx, (int(L.octa_raster2d_workspace_bytes(n, max(E, cap), self.label_res[1], self.label_res[0])),), torch.uint8)
+                    tree2img.raster_batch_device(edges_dev, offs, self.label_res, self.mip_axis, out=lab, workspace=ws_l)
+                # gray image: arterial and venous forest on separate canvases, np.maximum (generate_vessel_graph.py:80-85)
                 img = self._tensor("image" + sfx, (n, self.image_res[1], self.image_res[0]), torch.uint8)
                 ws_i = self._tensor("r2d_ws_image" + sfx, (int(L.octa_raster2d_workspace_bytes(n, max(E, cap), self.image_res[1], self.image_res[0])),), torch.uint8)
-                tree2img.raster_batch_device(edges_dev, offs, self.image_res, self.mip_axis, out=img, workspace=ws_i)
+                tree2img.raster_batch_device(edges_dev, offs, self.image_res, self.mip_axis, out=img, workspace=ws_i, layer_split=n_art)
                 out["label"], out["image"] = lab, img
                 if d2h:
-                    lab_h = self._tensor("label_host" + sfx, tuple(lab.shape), torch.uint8, pinned=True)
+                    lab_h = None
+                    if lab is not None:
+                        lab_h = self._tensor("label_host" + sfx, tuple(lab.shape), torch.uint8, pinned=True)
+                        lab_h.copy_(lab, non_blocking=True)
                     img_h = self._tensor("image_host" + sfx, tuple(img.shape), torch.uint8, pinned=True)
-                    lab_h.copy_(lab, non_blocking=True)
                     img_h.copy_(img, non_blocking=True)
+                    out["_host"] = (lab_h, img_h)
+                    out["d2h_bytes"] = int((lab_h.numel() if lab_h is not None else 0) + img_h.numel())
+                    if d2h_volume and self.voxelize:
+                        vol_h = self._tensor("vol_host" + sfx, tuple(out["volume"].shape), torch.uint16, pinned=True)
+                        vol_h.copy_(out["volume"], non_blocking=True)
+                        out["_vol_host"] = vol_h
+                        out["d2h_bytes"] += int(vol_h.numel() * 2)
                     if csv:
                         if self._csv_pool is None:                                          # one pool for the pipeline's lifetime
                             self._csv_pool = cf.ThreadPoolExecutor(max_workers=self.host_threads)
-                        # ctypes releases the GIL; this worker blocks until the batch's text is complete
-                        out["csv"] = list(self._csv_pool.map(lambda i: graph_io.csv_bytes(he[offs[i]:offs[i + 1]]), range(n)))
-                    stream.synchronize()
-                    out["label_host"], out["image_host"] = lab_h.numpy(), img_h.numpy()
-                    out["d2h_bytes"] = int(lab_h.numel() + img_h.numel())
-                    out["h2d_bytes"] = int(E * 56)
+                        # ctypes releases the GIL; the text is collected in _finish
+                        out["_csv"] = [self._csv_pool.submit(graph_io.csv_bytes, he[offs[i]:offs[i + 1]]) for i in range(n)]
+                ready = torch.cuda.Event()
+                ready.record(stream)
+                out["ready"] = ready          # device results (and the pinned host copies) are complete once this event has fired
                 return out
 
-    def run(self, seeds: Sequence[int], d2h: bool = True, csv: bool = True) -> dict:
+    def _finish(self, out: dict, wait: bool = True) -> dict:
+        """Hand a result out: wait for its device work (host-buffer mode) and collect the CSV text."""
+        if "_host" in out:
+            out["ready"].synchronize()
+            lab_h, img_h = out.pop("_host")
+            out["label_host"], out["image_host"] = (lab_h.numpy() if lab_h is not None else None), img_h.numpy()
+            if "_vol_host" in out:
+                out["volume_host"] = out.pop("_vol_host").numpy()
+        elif wait:
+            out["ready"].synchronize()
+        if "_csv" in out:
+            out["csv"] = [f.result() for f in out.pop("_csv")]
+        return out
+
+    def run(self, seeds: Sequence[int], d2h: bool = True, csv: bool = True, d2h_volume: bool = False) -> dict:
         """One step over len(seeds) samples.  Results: edges (host), offsets, volume / label / image (device
-        tensors), and with d2h: label_host / image_host (pinned uint8) and csv (list of bytes)."""
-        return self._post_stage(self._grow_stage(seeds, 0), 0, d2h, csv)
+        tensors, complete), and with d2h: label_host / image_host (pinned uint8) and csv (list of bytes)."""
+        return self._finish(self._post_stage(self._grow_stage(seeds, 0), 0, d2h, csv, d2h_volume=d2h_volume))
 
     @staticmethod
-    def buffer_sets(in_flight: int) -> int:
-        """Buffer sets run_pipelined cycles through: one per loop in flight and one being post-processed.  Each set is allocated on
-        first use: warm up with at least this many batches."""
-        return max(1, int(in_flight)) + 1 + max(0, int(os.environ.get("OCTA_EXTRA_SLOTS", "0")))
+    def buffer_sets(in_flight: int, d2h: bool = False) -> int:
+        """Buffer sets run_pipelined cycles through: one per loop in flight, one being post-processed, and in host-buffer mode
+        two more whose copies / CSV text are still landing (OCTA_EXTRA_SLOTS overrides).  Each set is allocated on first use:
+        warm up with at least this many batches."""
+        extra = os.environ.get("OCTA_EXTRA_SLOTS")
+        return max(1, int(in_flight)) + 1 + (max(0, int(extra)) if extra is not None else (2 if d2h else 0))
 
-    def run_pipelined(self, seed_batches, d2h: bool = True, csv: bool = True, in_flight: int = 2):
+    def run_pipelined(self, seed_batches, d2h: bool = True, csv: bool = True, in_flight: int = 2, d2h_volume: bool = False):
         """Generator over batches, results in order, software-pipelined.
 
         The growth loop is a chain of short latency-bound launches that leaves most of the GPU idle, voxelize / raster
         are throughput kernels, CSV text is host work: `in_flight` growth loops run side by side (one growth context,
-        two high-priority streams and one host thread each) while a worker thread post-processes finished batches on a
-        second stream.  Every result equals what run() returns for the same seeds (a sample depends on its seed only);
-        a yielded result stays valid until `in_flight + 1` further batches have been started."""
+        two high-priority streams and one host thread each) while a worker thread ENQUEUES the post-processing of finished
+        batches on a second stream -- it never waits for the device.  A result is handed out once its `ready` event has fired
+        (host-buffer mode) or right away with that event attached (d2h=False: wait on out["ready"] before reading the device
+        tensors on another stream).  Every result equals what run() returns for the same seeds (a sample depends on its seed
+        only); a yielded result stays valid until buffer_sets(in_flight, d2h) further batches have been started."""
         torch = self.torch
         in_flight = max(1, int(in_flight))
-        nslots = self.buffer_sets(in_flight)
+        nslots = self.buffer_sets(in_flight, d2h)
         if self._post_stream is None:
             with torch.cuda.device(self.device):
                 self._post_stream = torch.cuda.Stream()
         pending = collections.deque()
         with cf.ThreadPoolExecutor(max_workers=in_flight) as growers, cf.ThreadPoolExecutor(max_workers=1) as poster:
             def post(gf, slot):
-                return self._post_stage(gf.result(), slot, d2h, csv, self._post_stream)
+                return self._post_stage(gf.result(), slot, d2h, csv, self._post_stream, d2h_volume)
 
             for k, seeds in enumerate(seed_batches):
                 while len(pending) >= nslots:                 # buffer set k % nslots is free once result k - nslots is out
-                    yield pending.popleft().result()
+                    yield self._finish(pending.popleft().result(), wait=False)
                 gf = growers.submit(self._grow_stage, seeds, k % nslots, k % in_flight)
                 pending.append(poster.submit(post, gf, k % nslots))
             while pending:
-                yield pending.popleft().result()
+                yield self._finish(pending.popleft().result(), wait=False)
             if not d2h:
                 self._post_stream.synchronize()
 

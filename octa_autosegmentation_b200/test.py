@@ -57,6 +57,9 @@ def run(config: dict, num_samples: int = 9999999, batch_size: int = 32, device=N
     csvs = csvs[:num_samples]
     mine = list(range(rank, len(csvs), world))
     bgs = []
+    if "background" not in test["data"]:
+        # data_transforms.py:508 falls back to torch.rand_like(img) -- an unseeded draw from torch's global generator
+        raise NotImplementedError("Test.data.background is required: the reference's fallback (torch.rand_like noise) is not reproducible")
     if "background" in test["data"]:
         bgs = sorted(glob(test["data"]["background"]["files"], recursive=True), key=natural_key)
         assert len(bgs) > 0, f"Error: Your provided file path {test['data']['background']['files']} for background does not match any files!"
@@ -81,8 +84,7 @@ def run(config: dict, num_samples: int = 9999999, batch_size: int = 32, device=N
             bg_t, seeds = None, None
             if bgs:
                 idx = [random.Random(seed + i).randint(0, len(bgs) - 1) for i in gidx]
-                bg = np.stack([np.asarray(Image.open(bgs[j]).convert("L").resize((W, H)) if Image.open(bgs[j]).size != (W, H)
-                                          else Image.open(bgs[j]).convert("L"), dtype=np.uint8) for j in idx])
+                bg = np.stack([load_background(bgs[j], W, H) for j in idx])
                 bg_t = torch.from_numpy(bg).to(device)
                 seeds = [(seed + i) & 0xFFFFFFFF for i in gidx]
             out = gan.contrast_adapt(G, raster, bg_t, seeds).cpu().numpy()
@@ -90,6 +92,17 @@ def run(config: dict, num_samples: int = 9999999, batch_size: int = 32, device=N
             written += [os.path.join(save_dir, prefix + ".".join(os.path.basename(p).split(".")[:-1]) + ".png") for p in paths]
     G.close()
     return written
+
+
+def load_background(path: str, W: int, H: int) -> np.ndarray:
+    """What MONAI's LoadImaged hands on for a PNG (docker/trained_models/GAN/config.yml:49-55): PILReader's default
+    reverse_indexing=True swaps the two spatial axes, i.e. the array arrives TRANSPOSED; the config's Rotate90d(k=1) + Flipd(0)
+    (a transpose, applied on the device by octa_gan_input_dev) then restores the image's own orientation."""
+    from PIL import Image
+    im = Image.open(path).convert("L")
+    if im.size != (W, H):
+        im = im.resize((W, H))
+    return np.ascontiguousarray(np.asarray(im, dtype=np.uint8).T)
 
 
 def main(argv=None):

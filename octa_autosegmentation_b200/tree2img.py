@@ -149,8 +149,10 @@ def rasterize_forest(forest, image_resolution: Sequence[float], MIP_axis: int = 
 
 
 def raster_batch_device(edges7, edge_offsets, image_resolution: Sequence[int], MIP_axis: int = 2, min_radius: float = 0.0,
-                        max_radius: float = 1.0, out=None, workspace=None, stream=None):
-    """Batched device-resident 2-D rasterization (octa_raster2d_batch_dev): CUDA uint8 tensor [n_graphs, H, W]."""
+                        max_radius: float = 1.0, out=None, workspace=None, stream=None, layer_split=None):
+    """Batched device-resident 2-D rasterization (octa_raster2d_batch_dev): CUDA uint8 tensor [n_graphs, H, W].
+    `layer_split` (host int64 [n_graphs]): the first layer_split[g] edges of graph g and the rest are drawn on separate canvases
+    and combined with max, as generate_vessel_graph.py:80-85 does with the arterial and the venous forest."""
     import torch
 
     if not (edges7.is_cuda and edges7.dtype == torch.float64 and edges7.is_contiguous()):
@@ -173,7 +175,18 @@ def raster_batch_device(edges7, edge_offsets, image_resolution: Sequence[int], M
         stream = torch.cuda.current_stream(edges7.device)
     opts = _lib.OctaVoxOpts(float(min_radius), float(max_radius), 0, 0)
     with torch.cuda.device(edges7.device):
-        _lib.check(L.octa_raster2d_batch_dev(edges7.data_ptr(), offs.ctypes.data, n_graphs, H, W, int(MIP_axis),
-                                             ctypes.byref(opts), out.data_ptr(), workspace.data_ptr(),
-                                             workspace.numel(), ctypes.c_void_p(stream.cuda_stream)))
+        if layer_split is None:
+            _lib.check(L.octa_raster2d_batch_dev(edges7.data_ptr(), offs.ctypes.data, n_graphs, H, W, int(MIP_axis),
+                                                 ctypes.byref(opts), out.data_ptr(), workspace.data_ptr(),
+                                                 workspace.numel(), ctypes.c_void_p(stream.cuda_stream)))
+        else:
+            sp = np.ascontiguousarray(np.asarray(layer_split, dtype=np.int64))
+            if sp.shape[0] != n_graphs:
+                raise ValueError("layer_split needs one entry per graph")
+            L.octa_raster2d_batch_layers_dev.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                                         ctypes.c_int, ctypes.c_int, ctypes.POINTER(_lib.OctaVoxOpts), ctypes.c_void_p,
+                                                         ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+            _lib.check(L.octa_raster2d_batch_layers_dev(edges7.data_ptr(), offs.ctypes.data, sp.ctypes.data, n_graphs, H, W, int(MIP_axis),
+                                                        ctypes.byref(opts), out.data_ptr(), workspace.data_ptr(),
+                                                        workspace.numel(), ctypes.c_void_p(stream.cuda_stream)))
     return out

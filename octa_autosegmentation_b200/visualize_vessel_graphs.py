@@ -1,65 +1,115 @@
-"""Drop-in for the reference's visualize_vessel_graphs.py: re-renders stored graph CSVs at any resolution on
-the GPU.  Same flags and output names (visualize_vessel_graphs.py:33-46,80-104):
+"""Drop-in for the reference's visualize_vessel_graphs.py: re-renders stored graph CSVs at any resolution on the GPU, in
+batches (one voxelize / raster launch per batch of files, file writers in a thread pool).  Same flags and output names
+(visualize_vessel_graphs.py:33-46,69-104):
 
     python -m octa_autosegmentation_b200.visualize_vessel_graphs --source_dir D --out_dir O \
         [--resolution 1216,1216,16] [--save_2d|--no_save_2d] [--save_3d] [--save_3d_as .nii.gz|.npy] [--mip_axis 2]
-        [--binarize] [--num_samples N] [--max_dropout_prob P] [--ignore_z] [--threads T]
+        [--binarize] [--num_samples N] [--max_dropout_prob P] [--ignore_z] [--threads T] [--batch B]
 
   <name>.png | <name>_label.png (1-bit, PIL Floyd-Steinberg `convert("1")` after img<0.1 -> 0)
-  <name>_3d[.nii.gz|.npy] | <name>_3d_label[...]      <name>[...]_blackdict.pkl when --max_dropout_prob > 0
-(`.npy` volumes are written as bool exactly like the reference, :94; NIfTI needs nibabel.)"""
+  <name>_3d[.nii.gz|.npy] | <name>_3d_label[...]      <name>_3d[_label]_blackdict.pkl when --max_dropout_prob > 0
+Mirrored quirks of the reference: `.npy` volumes are written as bool (:94); the 2-D image is rendered WITHOUT dropout (:95);
+with --save_3d the 2-D file names carry the 3-D suffix, because `name` is extended in place (:81-85,:99-101); the blackdict that
+is pickled next to the 2-D image is the 3-D one (:102-104; without --save_3d that line raises NameError in the reference's
+worker, which its pool swallows: no pickle is written).  NIfTI needs nibabel."""
 from __future__ import annotations
 
 import argparse
+import concurrent.futures as cf
 import csv
 import os
 import pickle
 import re
 import sys
 from glob import glob
+from random import random
 
 import numpy as np
 
-from .tree2img import rasterize_forest, voxelize_forest
+from . import graph_io, tree2img
 
 
 def natural_key(s: str):
     return [int(t) if t.isdigit() else t.lower() for t in re.split(r"(\d+)", s)]
 
 
-def render_graph(file_path: str, args, resolution, img_res):
+def _write_outputs(args, name, vol, black_dict, img):
+    """File writes of render_graph (visualize_vessel_graphs.py:79-104) for one sample; vol / img may be None."""
     from PIL import Image
 
-    name = file_path.split("/")[-1].removesuffix(".csv")
-    with open(file_path, newline="") as f:
-        rows = list(csv.DictReader(f))
-    if args.save_3d:
-        vol, black_dict = voxelize_forest(rows, resolution, max_dropout_prob=args.max_dropout_prob, ignore_z=args.ignore_z)
-        vname = name + ("_3d_label" if args.binarize else "_3d")
+    if vol is not None:
         if args.binarize:
+            name += "_3d_label"
             vol[vol < 0.1] = 0
             vol[vol >= 0.1] = 1
+        else:
+            name += "_3d"
         if args.save_3d_as == ".nii.gz":
             try:
                 import nibabel as nib
             except ImportError as e:
                 raise RuntimeError("--save_3d_as .nii.gz needs nibabel, which is not installed; use --save_3d_as .npy") from e
-            nib.save(nib.Nifti1Image(vol, np.eye(4)), os.path.join(args.out_dir, vname + ".nii.gz"))
+            nib.save(nib.Nifti1Image(vol, np.eye(4)), os.path.join(args.out_dir, name + ".nii.gz"))
         else:
-            np.save(os.path.join(args.out_dir, vname + ".npy"), vol.astype(np.bool_))
+            np.save(os.path.join(args.out_dir, name + ".npy"), vol.astype(np.bool_))
         if args.max_dropout_prob > 0:
-            with open(os.path.join(args.out_dir, vname + "_blackdict.pkl"), "wb") as f:
+            with open(os.path.join(args.out_dir, name + "_blackdict.pkl"), "wb") as f:
                 pickle.dump(black_dict, f)
-    if args.save_2d:
-        img, black_dict = rasterize_forest(rows, img_res, args.mip_axis, max_dropout_prob=args.max_dropout_prob)
+    if img is not None:
         if args.binarize:
             img[img < 0.1] = 0
             Image.fromarray(img.astype(np.uint8)).convert("1").save(os.path.join(args.out_dir, name + "_label.png"))
         else:
             Image.fromarray(img.astype(np.uint8)).save(os.path.join(args.out_dir, name + ".png"))
-        if args.max_dropout_prob > 0:
+        if args.max_dropout_prob > 0 and vol is not None:
             with open(os.path.join(args.out_dir, name + "_blackdict.pkl"), "wb") as f:
                 pickle.dump(black_dict, f)
+
+
+def render_batch(files, args, resolution, img_res, writers):
+    """One batch of csv files: parse, (3-D) host-side dropout exactly like voxelize_forest, ONE voxelize launch and ONE raster
+    launch for the whole batch, file writes handed to `writers`."""
+    import torch
+
+    names, e3, e2, bds = [], [], [], []
+    for fp in files:
+        names.append(fp.split("/")[-1].removesuffix(".csv"))
+        if args.save_3d and args.max_dropout_prob > 0:
+            # subtree dropout consumes Python's RNG row by row (tree2img.py:218-241): same host loop as voxelize_forest
+            with open(fp, newline="") as f:
+                rows = list(csv.DictReader(f))
+            kept, bd = tree2img.forest_to_edges7(rows, None, 0, 1, args.max_dropout_prob, None)
+            e3.append(kept)
+            bds.append(bd)
+            if args.save_2d:
+                # rasterize_forest(f, img_res, mip_axis) draws p, and one number per edge even though p = 0 (tree2img.py:62,78):
+                # the next file's dropout continues from there
+                for _ in range(1 + len(rows)):
+                    random()
+                e2.append(graph_io.read_csv(fp))
+            else:
+                e2.append(None)
+        else:
+            e = graph_io.read_csv(fp)            # C parser of the `[x y z]` cells (tree2img.py:73-76 semantics)
+            e3.append(e)
+            e2.append(e)
+            bds.append({})
+    dev = torch.device("cuda", torch.cuda.current_device())
+    vols = imgs = None
+    if args.save_3d:
+        offs = np.cumsum([0] + [len(e) for e in e3])
+        cat = np.concatenate(e3) if offs[-1] else np.zeros((1, 7))
+        vols = tree2img.voxelize_batch_device(torch.from_numpy(cat).to(dev), offs, [int(d) for d in resolution], ignore_z=args.ignore_z).cpu().numpy()
+    if args.save_2d:
+        offs = np.cumsum([0] + [len(e) for e in e2])
+        cat = np.concatenate(e2) if offs[-1] else np.zeros((1, 7))
+        imgs = tree2img.raster_batch_device(torch.from_numpy(cat).to(dev), offs, [int(d) for d in img_res], args.mip_axis).cpu().numpy()
+    futs = []
+    for i, name in enumerate(names):
+        vol = vols[i] if vols is not None else None
+        img = imgs[i].astype(np.uint16) if imgs is not None else None
+        futs.append(writers.submit(_write_outputs, args, name, vol, bds[i], img))
+    return futs
 
 
 def main(argv=None):
@@ -76,7 +126,8 @@ def main(argv=None):
     p.add_argument("--num_samples", type=int, default=9999999)
     p.add_argument("--max_dropout_prob", type=float, default=0)
     p.add_argument("--ignore_z", action="store_true", default=False)
-    p.add_argument("--threads", type=int, default=-1, help="accepted for compatibility")
+    p.add_argument("--threads", type=int, default=-1, help="file-writer threads (default: all cores but one, max 8)")
+    p.add_argument("--batch", type=int, default=0, help="csv files per GPU launch (default: 32 for 2-D only, 4 with --save_3d)")
     p.set_defaults(save_2d=True)
     args = p.parse_args(argv)
     resolution = np.array([int(d) for d in args.resolution.split(",")])
@@ -93,12 +144,17 @@ def main(argv=None):
     files = sorted(glob(os.path.join(args.source_dir, "**", "*.csv"), recursive=True), key=natural_key)[:args.num_samples]
     assert len(files) > 0, f"Your provided source directory {args.source_dir} does not contain any csv files."
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    if world > 1:
-        import torch
-        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-    for i, fp in enumerate(files):
-        if i % world == rank:
-            render_graph(fp, args, resolution, img_res)
+    import torch
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    mine = [fp for i, fp in enumerate(files) if i % world == rank]
+    batch = args.batch if args.batch > 0 else (4 if args.save_3d else 32)
+    threads = args.threads if args.threads > 0 else max(1, min(8, (os.cpu_count() or 2) - 1))
+    futs = []
+    with cf.ThreadPoolExecutor(max_workers=threads) as writers:
+        for k in range(0, len(mine), batch):
+            futs += render_batch(mine[k:k + batch], args, resolution, img_res, writers)
+        for f in futs:
+            f.result()
     return 0
 
 

@@ -108,6 +108,15 @@ def speckle(seed: int, shape) -> np.ndarray:
     return rs.uniform(0, 1, shape)
 
 
+def load_image_like_monai(path) -> np.ndarray:
+    """LoadImaged(image_only=True) on a PNG (config.yml:49-55): monai.data.PILReader with its default reverse_indexing=True
+    returns the pixel array with the two spatial axes swapped (third-party behaviour, restated from MONAI's documentation:
+    "reverse_indexing: whether to use a reversed spatial indexing convention for the returned data array ... default True").
+    The config's Rotate90d(k=1) + Flipd(0) in prepare_input undo exactly that."""
+    from PIL import Image
+    return np.ascontiguousarray(np.asarray(Image.open(path).convert("L"), dtype=np.uint8).T)
+
+
 def prepare_input(raster_u8: np.ndarray, background_u8: np.ndarray | None, speckle64: np.ndarray) -> np.ndarray:
     """ScaleIntensityd on both, background Rotate90d(k=1) + Flipd(axis 0) as in docker/trained_models/GAN/config.yml:60-86,
     then img = maximum(img, noise * speckle) (float32 x float64 -> float64) and CastToTyped(float32)."""

@@ -160,7 +160,7 @@ def test_cli_writes_reference_named_pngs(tmp_path):
         assert got.shape == (304, 304) and got.dtype == np.uint8
         e7 = graph_io.parse_csv_bytes((gdir / (n + ".csv")).read_bytes())
         raster = tree2img.raster_edges(e7, [304, 304], 2)
-        bg = np.asarray(Image.open(bdir / bgs[random.Random(675570 + i).randint(0, 2)]))
+        bg = go.load_image_like_monai(bdir / bgs[random.Random(675570 + i).randint(0, 2)])      # LoadImaged: axes swapped
         x = go.prepare_input(raster.astype(np.uint8), bg, go.speckle(675570 + i, (304, 304)))
         with torch.no_grad():
             ref = go.to_png_u8(go.generator_forward(sd, torch.from_numpy(x)[None, None]).numpy()[0, 0])

@@ -222,3 +222,10 @@ def test_ball_order_modes_agree(monkeypatch, mode):
             "t.compare_with_oracle(growth, t.small_config(), [0, 1, 2])\nprint('MODES_OK')\n") % (ROOT, ROOT)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=dict(os.environ))
     assert r.returncode == 0 and "MODES_OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_repeated_mode_name_vs_oracle(growth):
+    """A later mode that reuses the first mode's name keeps the parameters of the mode initialised last (greenhouse.py:84-85);
+    the oracle is pinned to the reference on this config by tests/test_oracle_growth.py."""
+    from test_oracle_growth import repeated_name_config
+    compare_with_oracle(growth, repeated_name_config(), [3, 4])

@@ -75,3 +75,21 @@ def test_generator_wrapper_rejects_bad_state_dict():
     del bad["model.15.conv_block.5.weight"]
     with pytest.raises(KeyError):
         gan.ResnetGenerator9(bad, device="cpu")
+
+
+def test_background_keeps_its_own_orientation(tmp_path):
+    """LoadImaged (PILReader, reverse_indexing=True) delivers the background transposed and the config's Rotate90d(k=1) +
+    Flipd(0) transposes it back (docker/trained_models/GAN/config.yml:49-86): the noise the generator sees has the PNG's own
+    orientation.  The product's loader (octa_autosegmentation_b200/test.py:load_background) must hand the device the same array."""
+    from PIL import Image
+    from octa_autosegmentation_b200 import test as gan_cli
+    rs = np.random.RandomState(3)
+    A = rs.randint(0, 255, (304, 304)).astype(np.uint8)
+    A[:40, :] = 255                                   # a bright band along the TOP rows: not symmetric under transposition
+    p = tmp_path / "bg.png"
+    Image.fromarray(A).save(p)
+    from oracle import gan_oracle as go
+    loaded = go.load_image_like_monai(p)
+    assert np.array_equal(loaded, A.T) and np.array_equal(gan_cli.load_background(str(p), 304, 304), loaded)
+    x = go.prepare_input(np.zeros((304, 304), np.uint8), loaded, np.ones((304, 304)))
+    assert np.array_equal(x, go.scale_intensity(A))   # effective background == the PNG as stored

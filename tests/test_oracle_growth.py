@@ -125,3 +125,31 @@ def test_docker_config_byte_exact(seed):
     if seed == 0:   # counts measured on the reference itself
         assert st["py_draws"] == 14778 and st["nn_queries"] == 1820486 and st["bifurcations"] == 41
         assert st["n_art_nodes"] == 9033 and st["n_ven_nodes"] == 3965 and st["n_oxy_left"] == 12127 and st["n_co2_left"] == 3567
+
+
+def repeated_name_config():
+    """Three modes named SVC, DVC, SVC: the reference re-initialises its parameters only for a mode whose name differs from the
+    first mode's (greenhouse.py:84-85), so the third mode runs with EVERYTHING of the second (I, N, eps, delta, gamma, phi, omega,
+    kappa) -- the values written in its own block are never read."""
+    import copy
+    cfg = small_config()
+    modes = cfg["Greenhouse"]["modes"]
+    third = copy.deepcopy(modes[0])
+    third.update(I=7, N=300, gamma_art=20, gamma_ven=20, phi=40, omega=0.9, kappa=3.7, eps_k=0.09)
+    modes.append(third)
+    modes[1]["I"] = 6
+    return cfg
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/vessel_graph_generation"), reason="needs /root/reference (build container)")
+def test_mode_with_the_first_modes_name_keeps_previous_parameters_like_the_reference():
+    from oracle import ref_harness as rh
+    cfg = repeated_name_config()
+    art, ven, _ = rh.run_growth(cfg, 3)
+    got, _ = oracle_csv(cfg, 3)
+    assert got == rh.csv_bytes(art, ven)
+    # and it is NOT what taking the third block's own values would give
+    import copy
+    other = copy.deepcopy(cfg)
+    other["Greenhouse"]["modes"][2]["name"] = "third"
+    assert oracle_csv(other, 3)[0] != got

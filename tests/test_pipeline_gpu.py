@@ -37,39 +37,3 @@ def test_pipelined_batches_equal_single_steps():
     e7 = np.concatenate([oa, ov])
     first = pipe.run(batches[0])
     assert np.array_equal(first["volume"][0].cpu().numpy(), vox_oracle.voxelize_edges(e7, list(dims)))
-
-
-def test_generate_vessel_graph_cli_writes_reference_files(tmp_path):
-    """The drop-in CLI (generate_vessel_graph.py surface: YAML in, one timestamped folder per sample with config.yml,
-    <name>.csv and art_ven_img_gray.png out): with --seed the CSVs are the reference's bytes for those seeds."""
-    import glob
-    import os
-
-    import yaml
-    from PIL import Image
-
-    from conftest import GOLDEN
-    from octa_autosegmentation_b200 import generate_vessel_graph as cli
-    from octa_autosegmentation_b200.config import default_config
-
-    cfg = default_config()
-    for m, i in zip(cfg["Greenhouse"]["modes"], (12, 12)):
-        m["I"], m["N"] = i, 400
-    cfg["output"]["directory"] = str(tmp_path / "out")
-    cfg["output"]["save_trees"] = True
-    cfg["output"]["save_2D_image"] = True
-    cfg["output"]["save_3D_volumes"] = None
-    yml = tmp_path / "cfg.yml"
-    yml.write_text(yaml.dump(cfg))
-    assert cli.main(["--config_file", str(yml), "--num_samples", "3", "--seed", "0", "--batch", "2"]) == 0
-    dirs = sorted(glob.glob(os.path.join(cfg["output"]["directory"], "*")))
-    assert len(dirs) == 3
-    csvs = set()
-    for d in dirs:
-        name = os.path.basename(d)
-        assert os.path.isfile(os.path.join(d, "config.yml"))
-        csvs.add(open(os.path.join(d, name + ".csv"), "rb").read())
-        img = np.asarray(Image.open(os.path.join(d, "art_ven_img_gray.png")))
-        assert img.ndim == 2 and img.shape[0] == img.shape[1] and img.max() > 0
-    for seed in (0, 1):
-        assert open(os.path.join(GOLDEN, "graph_small_s%d.csv" % seed), "rb").read() in csvs

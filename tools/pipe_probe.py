@@ -34,5 +34,5 @@ need.clear()
 n0 = _lib.launch_count()
 torch.cuda.synchronize(); t = time.time(); gm = run(K); dt = time.time() - t
 print("PROBE graph=%s ball=%s in_flight=%d sub_batch=%d d2h=%d: %.1f graphs/s (%.1f ms per 64), loop %.0f ms, %d launches/step, kd-needed iterations/graph %.1f"
-      % (os.environ.get("OCTA_GROW_GRAPH", "1"), os.environ.get("OCTA_BALL_ORDER", "ondemand"), L, SB, D2H, K * 64 / dt, dt / K * 1e3, gm,
+      % (os.environ.get("OCTA_GROW_GRAPH", "0"), os.environ.get("OCTA_BALL_ORDER", "ondemand"), L, SB, D2H, K * 64 / dt, dt / K * 1e3, gm,
          (_lib.launch_count() - n0) // K, float(np.mean(need)) if need else -1), flush=True)
