@@ -15,7 +15,7 @@
 //                      the cells of the row
 //   calc_alpha, blend_white   rasterizer_scanline_aa::calculate_alpha (non-zero winding, 8-bit) and
 //                      fixed_blender_rgba_plain::blend_pix for white over an opaque gray pixel
-// oracle/agg_oracle.c is the sequential CPU restatement of the same pipeline (it reproduces all 500 label PNGs the reference
+// The test tree holds a sequential CPU restatement of the same pipeline (agg_oracle.c; it reproduces all 500 label PNGs the reference
 // ships bit for bit); tests compare this code with it cell by cell and image by image.
 #pragma once
 #include <math.h>

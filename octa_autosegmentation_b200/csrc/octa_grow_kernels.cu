@@ -16,6 +16,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <type_traits>
+#include <cuda/atomic>
 #include <vector>
 #include "octa_eig3.h"
 #include "octa_grow.cuh"
@@ -809,7 +810,8 @@ __device__ __forceinline__ double node_contribution(const TreeView<SM>& T, const
     const int kmn = T.kmode(n);
     auto cv = [&](int c) -> double {        // nodes created in this call are leaves of radius r
         if (c >= T.n_before) return P.leafc_tab[kmn];
-        return VOL ? *(volatile double*)(T.C + c) : T.C[c];
+        if (VOL) return cuda::atomic_ref<double, cuda::thread_scope_block>(T.C[c]).load(cuda::memory_order_relaxed);
+        return T.C[c];
     };
     double s = cv(c0);
     if (c1 >= 0) s = s + cv(c1);
@@ -1079,22 +1081,23 @@ __device__ void commit_body(const GrowDev& D, const GrowShape& S, const IterP& P
         }
         __syncthreads();
         const int nstart = s_nstart;
-        volatile double* vC = T.C;
+        // Chains of different threads meet at bifurcations: the first child to arrive publishes its contribution and stops
+        // (release), the second one takes over both (acquire).  Contributions and the arrival bitmap are accessed through
+        // block-scope atomics, so the hand-off is ordered by the memory model itself (compute-sanitizer racecheck agrees).
         for (int k = tid; k < nstart; k += blockDim.x) {
             int n = starters[k];
             double val = node_contribution<SM, true>(T, P, n, T.get_c0(n), T.get_c1(n));
-            vC[n] = val;
+            cuda::atomic_ref<double, cuda::thread_scope_block>(T.C[n]).store(val, cuda::memory_order_relaxed);
             while (true) {
                 const int p = T.get_par(n);
                 if (p < 0 || !T.is_dirty(p)) break;                  // (the root is never marked)
                 const unsigned int pbit = 1u << (p & 31);
                 if (T.get_c1(p) >= 0) {
-                    __threadfence_block();
-                    if (!(atomicOr(&T.arr[p >> 5], pbit) & pbit)) break;   // first arrival: the sibling's chain continues
-                    __threadfence_block();
+                    cuda::atomic_ref<unsigned int, cuda::thread_scope_block> arrived(T.arr[p >> 5]);
+                    if (!(arrived.fetch_or(pbit, cuda::memory_order_acq_rel) & pbit)) break;   // first arrival: the sibling's chain continues
                 }
                 val = node_contribution<SM, true>(T, P, p, T.get_c0(p), T.get_c1(p));
-                vC[p] = val;
+                cuda::atomic_ref<double, cuda::thread_scope_block>(T.C[p]).store(val, cuda::memory_order_relaxed);
                 n = p;
             }
         }

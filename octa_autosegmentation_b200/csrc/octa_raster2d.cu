@@ -5,7 +5,7 @@
 // :51) drawn white on black, pixel (row, col) <-> (pos[ax0]*H, pos[ax1]*W), ax = {0,1,2} \ {MIP_axis} (:46,:85), anti-aliased,
 // blended "over" in list order in 8 bits, read back as gray (:104-113).  csrc/octa_aggcells.cuh restates that pipeline stage
 // by stage (centre-line clip and snap, inscribed-polygon caps, the 24.8 fixed-point cover/area cells of Agg's scanline
-// rasterizer, calculate_alpha, fixed_blender_rgba_plain); the CPU restatement of the same pipeline, oracle/agg_oracle.c,
+// rasterizer, calculate_alpha, fixed_blender_rgba_plain); the sequential CPU restatement of the same pipeline in the test tree (agg_oracle.c)
 // reproduces all 500 label PNGs the reference ships bit for bit, and this kernel equals it pixel for pixel
 // (tests/test_raster2d_gpu.py).  All pixel arithmetic is integer.
 //

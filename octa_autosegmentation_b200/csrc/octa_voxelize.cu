@@ -13,9 +13,9 @@
 // (this file is compiled with -fmad=false); since quantisation is monotone, max is taken on the
 // quantised value, which makes the accumulation order-independent and exact.
 //
-// Design (B200): the volume is cut into tiles [TX=16][TY=8][TZ<=64]; one CTA owns one tile of one graph and
-// max-accumulates it in shared memory (32-bit cells: native atomic max), then packs it to u16 cells laid out exactly like
-// the volume (27 + 13.5 KB for z = 53: four CTAs per SM).  The (y,z) rows of the clipped edge boxes are dealt out to lanes; a lane culls its row in
+// Design (B200): the volume is cut into tiles [TX=16][TY=16][TZ<=64]; one CTA owns one tile of one graph and
+// max-accumulates it in shared memory as u16 cells laid out exactly like the volume (27 KB for z = 53: four
+// CTAs per SM).  The (y,z) rows of the clipped edge boxes are dealt out to lanes; a lane culls its row in
 // fp32, the warp compacts the surviving voxels and evaluates them in float64 with all lanes busy (see
 // rasterize notes below).  The finished tile leaves with TMA bulk copies shared -> global
 // (cp.async.bulk, one per x plane) -- the HBM traffic is the algorithmic 2 bytes/voxel, no float scratch volume
@@ -25,12 +25,11 @@
 #include "octa_common.h"
 #include <math.h>
 #include <stdlib.h>
-#include <algorithm>
 
 namespace {
 
 constexpr int KBIG = 64;          // max tiles an edge may be listed in before it becomes a "big" edge
-constexpr int TILE_Y = 8;
+constexpr int TILE_Y = 16;
 constexpr int TILE_Z_MAX = 64;
 constexpr int VOX_THREADS = 256;
 
@@ -229,36 +228,25 @@ __device__ __noinline__ uint32_t exact_voxel_q(const VoxEdge& e, double vx, doub
 // Per-edge constants staged in shared memory for one pass of EPASS edges of a tile.
 constexpr int EPASS = 32;
 constexpr int QCAP = 512;       // survivor queue entries per warp: 32 rows x at most 16 voxels
-constexpr int SLOWCAP = 64;     // float64 re-evaluation queue entries per warp (flushed 32 at a time)
 struct EdgeSm {
     double p1[3], p2[3], s[3];
     double R, ss, inv_ss, c0, tguard;
     float a[3], f[3], finv, thr;
-    // analytic x interval of a (y,z) row (cull_row): infinite cylinder |perp|^2 <= thr -> A w0^2 + 2 pbx w0 + (|pb|^2 - thr) <= 0,
-    // and the slab t in [-dt, 1 + dt] the caps cannot leave (t = projection parameter, dt = reach / length)
-    float A, invA, invg, dt;
-    float c255, epsv;       // float32 evaluation: 255 * c0 and the guard band (in units of the quantised value) around integers
-    int cyl_ok, slab_ok;
     int b0[3], n[3];
     int rowbase;            // exclusive prefix of (y,z) rows over the pass
 };
 
 // Work distribution: the (y,z) rows of all clipped edge boxes of a pass are numbered consecutively and dealt out
 // to the lanes of the CTA's warps, so every warp gets the same amount of work whatever the number and size of the
-// edges in the tile.  Four tiers per voxel:
-//   1. per ROW, in closed form (fp32, box-local coordinates): the x interval in which the capsule of radius
-//      reach = R + sqrt3/2 + slack can be met -- the roots of the infinite cylinder's quadratic, cut by the slab the end
-//      caps cannot leave.  It is a superset of the voxels with a positive contribution (the slack of 0.02 voxel in
-//      `reach` exceeds the fp32 root error; rows of edges within ~13 degrees of the x axis, where the quadratic is ill
-//      conditioned, are walked voxel by voxel instead) and replaces the 16-step walk of every row (12 % of the candidate
-//      voxels survive);
+// edges in the tile.  Three tiers per voxel:
+//   1. fp32 broad phase in box-local coordinates: a lane walks its row along x (<= 16 voxels) and produces a bit
+//      mask of the voxels whose exact contribution can be > 0 (12 % survive);
 //   2. the warp COMPACTS the survivors of its 32 rows into a shared-memory queue and evaluates them with all lanes
-//      busy in FLOAT32: 255*I is accurate to `epsv` (a few 1e-3, from the coordinate magnitudes of the edge), so its floor
-//      equals the reference's unless 255*I lies within epsv of an integer;
-//   3. those voxels (a few percent) are queued again and evaluated in fast float64 (fma, reciprocal instead of division:
-//      255*I accurate to ~1e-11), again with all lanes busy;
-//   4. inside 1e-7 of an integer, or t within 1e-9 of {0,1} (probability ~1e-7), the reference's exact operation chain
-//      decides.
+//      busy: fast float64 (fma, reciprocal instead of division); 255*I is accurate to ~1e-11, so its floor
+//      equals the reference's unless 255*I lies within 1e-7 of an integer or t within 1e-9 of {0,1};
+//   3. inside those guard bands (probability ~1e-7) the reference's exact operation chain decides.
+// (Without the compaction the float64 tier ran at the survivors' lane density: almost every x step of a warp had
+// at least one surviving lane and paid the full float64 cost for it.)
 __device__ __forceinline__ int setup_edge(const VoxEdge& e, const int t0[3], const int t1[3], EdgeSm* o) {
     int rows = 1;
 #pragma unroll
@@ -288,68 +276,26 @@ __device__ __forceinline__ int setup_edge(const VoxEdge& e, const int t0[3], con
     o->finv = fss > 0.f ? 1.0f / fss : 0.f;
     const float reach = (float)e.R + 0.8660254f + 0.02f + 8e-6f * ext;
     o->thr = reach * reach;
-    const double A = ss > 0.0 ? 1.0 - o->s[0] * o->s[0] * o->inv_ss : 1.0;
-    o->A = (float)A;
-    o->cyl_ok = (ss > 0.0 && A >= 0.05) ? 1 : 0;
-    o->invA = o->cyl_ok ? (float)(1.0 / A) : 0.f;
-    const double g = o->s[0] * o->inv_ss;                       // dt/dw0
-    o->slab_ok = (ss > 0.0 && fabs(o->s[0]) >= 1e-3 * sqrt(ss)) ? 1 : 0;
-    o->invg = o->slab_ok ? (float)(1.0 / g) : 0.f;
-    o->dt = ss > 0.0 ? reach * (float)sqrt(o->inv_ss) : 3.0e38f;
-    o->c255 = (float)(255.0 * o->c0);
-    o->epsv = 2e-3f + 2e-4f * ext;
     return o->rowbase;
 }
 
-// tier 1: [*ixlo, *ixhi] = the voxels of row (iy, iz) of the edge's box that may receive a positive contribution (empty:
-// *ixhi < *ixlo).  Edges nearly parallel to x (cyl_ok == 0) get the slab interval only: tier 2 sorts the rest out.
-__device__ __forceinline__ void row_interval(const EdgeSm& E, int iy, int iz, int* ixlo, int* ixhi) {
-    const float f0 = E.f[0], f1 = E.f[1], f2 = E.f[2], a0 = E.a[0], finv = E.finv;
+// tier 1: bit ix of the result is set when voxel (b0x + ix, row) may receive a positive contribution
+__device__ __forceinline__ uint32_t cull_row(const EdgeSm& E, int iy, int iz) {
+    const float f0 = E.f[0], f1 = E.f[1], f2 = E.f[2], a0 = E.a[0], finv = E.finv, thr = E.thr;
     const float w1 = (float)iy - E.a[1], w2 = (float)iz - E.a[2];
     const float dot12 = w1 * f1 + w2 * f2;
     const int nx = E.n[0];
-    const float tb = dot12 * finv;                    // projection parameter of the row's point w0 = 0
-    float lo = 0.f, hi = (float)(nx - 1);             // interval of ix = w0 + a0
-    *ixlo = 0; *ixhi = -1;
-    if (E.cyl_ok) {
-        // perpendicular offset of that point from the axis: no cancellation at the squared level
-        const float pbx = -tb * f0, pby = fmaf(-tb, f1, w1), pbz = fmaf(-tb, f2, w2);
-        const float Cq = fmaf(pbx, pbx, fmaf(pby, pby, pbz * pbz)) - E.thr;
-        const float disc = fmaf(pbx, pbx, -E.A * Cq);
-        if (disc < 0.f) return;
-        const float sq = sqrtf(disc);
-        lo = fmaxf(lo, (-pbx - sq) * E.invA + a0 - 0.02f);
-        hi = fminf(hi, (-pbx + sq) * E.invA + a0 + 0.02f);
+    uint32_t mask = 0;
+    float fx = 0.f;                                   // (float)ix without a conversion per step (small integers are exact)
+#pragma unroll 4
+    for (int ix = 0; ix < nx; ++ix, fx += 1.0f) {
+        const float w0 = fx - a0;
+        float tf = fmaf(w0, f0, dot12) * finv;
+        tf = fminf(fmaxf(tf, 0.f), 1.f);
+        const float d0 = fmaf(-tf, f0, w0), d1 = fmaf(-tf, f1, w1), d2 = fmaf(-tf, f2, w2);
+        if (!(fmaf(d0, d0, fmaf(d1, d1, d2 * d2)) > thr)) mask |= 1u << ix;
     }
-    if (E.slab_ok) {
-        float s0 = (-E.dt - tb) * E.invg, s1 = (1.f + E.dt - tb) * E.invg;
-        if (s0 > s1) { const float t = s0; s0 = s1; s1 = t; }
-        lo = fmaxf(lo, s0 + a0 - 0.02f);
-        hi = fminf(hi, s1 + a0 + 0.02f);
-    } else if (tb < -E.dt || tb > 1.f + E.dt) {
-        return;                                       // t does not change along x and lies outside the slab
-    }
-    if (!(lo <= hi)) return;
-    *ixlo = max(0, (int)ceilf(lo));
-    *ixhi = min(nx - 1, (int)floorf(hi));
-}
-
-// tier 2: float32 evaluation of one surviving voxel.  Returns the quantised contribution, or -1 when 255*I lies within
-// the guard band of an integer (tiers 3 / 4 decide).
-__device__ __forceinline__ int eval_voxel_f32(const EdgeSm& E, int ix, int iy, int iz) {
-    const float w0 = (float)ix - E.a[0], w1 = (float)iy - E.a[1], w2 = (float)iz - E.a[2];
-    const float f0 = E.f[0], f1 = E.f[1], f2 = E.f[2];
-    float t = fmaf(w0, f0, fmaf(w1, f1, w2 * f2)) * E.finv;
-    t = fminf(fmaxf(t, 0.f), 1.f);
-    const float d0 = fmaf(-t, f0, w0), d1 = fmaf(-t, f1, w1), d2 = fmaf(-t, f2, w2);
-    const float d = sqrtf(fmaf(d0, d0, fmaf(d1, d1, d2 * d2)));
-    const float v = fmaf(-d, 147.22431864335458f, E.c255);          // 255 * (c0 - d / sqrt3)
-    const float eps = E.epsv;
-    if (v < -eps) return 0;
-    if (v >= 255.f + eps) return 255;
-    const float fl = floorf(v), fr = v - fl;
-    if (fr < eps || fr > 1.f - eps || !(v == v)) return -1;
-    return fl >= 255.f ? 255 : (int)fl;
+    return mask;
 }
 
 // tiers 2 and 3 for one surviving voxel; returns the quantised contribution
@@ -387,12 +333,14 @@ __device__ __forceinline__ uint32_t eval_voxel(const EdgeSm& E, int ix, int iy, 
     return q;
 }
 
-// max-accumulate a tile cell (values 0..255).  The cells are 32-bit words while the tile is being accumulated: shared memory has
-// a native 32-bit atomic max (one instruction, no return value needed), whereas a 16-bit compare-and-swap is emulated with a
-// 32-bit CAS loop and byte permutes -- with u16 cells that emulation was HALF of all instructions of this kernel
-// (profiles/r02_ncu_vox_*).  The tile is packed to the volume's u16 cells once, before it leaves.
-__device__ __forceinline__ void tile_max(unsigned int* p, uint32_t q) {
-    if (*(volatile unsigned int*)p < q) atomicMax(p, q);
+// max-accumulate a 16-bit tile cell (values 0..255; contention is rare, most updates stop at the first load)
+__device__ __forceinline__ void tile_max(unsigned short* p, uint32_t q) {
+    unsigned short old = *(volatile unsigned short*)p;
+    while (old < q) {
+        const unsigned short seen = atomicCAS(p, old, (unsigned short)q);
+        if (seen == old) break;
+        old = seen;
+    }
 }
 
 __global__ void __launch_bounds__(VOX_THREADS, 4)
@@ -400,8 +348,8 @@ vox_tile_kernel(const VoxEdge* __restrict__ prep, const int64_t* __restrict__ ed
                 const int* __restrict__ tile_start, const int* __restrict__ tile_edges,
                 const int* __restrict__ big_count, const int* __restrict__ big_idx,
                 uint16_t* __restrict__ out) {
-    // dynamic shared memory: the tile accumulators, u32 [TX][TY][TZ], then the packed u16 tile in the volume's own layout
-    extern __shared__ __align__(128) unsigned int acc[];
+    // dynamic shared memory: the tile accumulators, u16 [TX][TY][TZ] in the volume's own layout
+    extern __shared__ __align__(128) unsigned short acc[];
     // grid = (tiles along y and z, tiles along x, graphs)
     const int gr = blockIdx.z;
     const int tx_i = blockIdx.y, ty_i = blockIdx.x / g.nt[2], tz_i = blockIdx.x - ty_i * g.nt[2];
@@ -445,33 +393,18 @@ vox_tile_kernel(const VoxEdge* __restrict__ prep, const int64_t* __restrict__ ed
 
     {
         uint4* acc4 = reinterpret_cast<uint4*>(acc);
-        for (int i = threadIdx.x; i < tile_elems / 4; i += blockDim.x) acc4[i] = make_uint4(0, 0, 0, 0);
-        for (int i = (tile_elems / 4) * 4 + threadIdx.x; i < tile_elems; i += blockDim.x) acc[i] = 0;
+        for (int i = threadIdx.x; i < tile_elems / 8; i += blockDim.x) acc4[i] = make_uint4(0, 0, 0, 0);
+        for (int i = (tile_elems / 8) * 8 + threadIdx.x; i < tile_elems; i += blockDim.x) acc[i] = 0;
     }
-    unsigned short* packed = reinterpret_cast<unsigned short*>(acc + ((tile_elems + 3) & ~3));      // 16-byte aligned
     __shared__ EdgeSm es[EPASS];
-    // float64 re-evaluation queues of the warps: they live in the region of the packed tile, which is only written after the
-    // last pass
-    unsigned int* s_slow = reinterpret_cast<unsigned int*>(packed);
-    __shared__ int s_total, s_next, s_rowbase[EPASS];
+    __shared__ unsigned short s_queue[(VOX_THREADS / 32) * QCAP];
+    __shared__ int s_total, s_rowbase[EPASS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ystride = T[2], xstride = T[1] * T[2];
-    unsigned int* slowq = s_slow + warp * SLOWCAP;
-    int nslow = 0;                  // (warp-uniform)
-    // tiers 3 / 4 for up to 32 queued voxels, all lanes busy; entry = edge << 15 | ix << 11 | iy << 6 | iz
-    auto flush_slow = [&](int from, int cnt) {
-        const bool on = lane < cnt;
-        const unsigned int ent = on ? slowq[from + lane] : 0u;
-        if (on) {
-            const EdgeSm& E = es[ent >> 15];
-            const int ix = (ent >> 11) & 15, iy = (ent >> 6) & 31, iz = ent & 63;
-            const uint32_t q = eval_voxel(E, ix, iy, iz);
-            if (q) tile_max(acc + (E.b0[0] + ix - t0[0]) * xstride + (E.b0[1] + iy - t0[1]) * ystride + (E.b0[2] + iz - t0[2]), q);
-        }
-    };
+    unsigned short* queue = s_queue + warp * QCAP;
     const int* lst = tile_edges + (size_t)KBIG * e_base;
     const int* bl = big_idx + e_base;
     const int nlist = end - beg, nall = nlist + nbig;
+    const int ystride = T[2], xstride = T[1] * T[2];
     for (int pass = 0; pass < nall; pass += EPASS) {
         const int cnt = imin(EPASS, nall - pass);
         if (warp == 0) {                   // EPASS == 32: warp 0 sets the pass up and scans the row counts, ONE barrier per pass
@@ -486,74 +419,54 @@ vox_tile_kernel(const VoxEdge* __restrict__ prep, const int64_t* __restrict__ ed
             for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
             if (lane < cnt) es[lane].rowbase = x - v;
             s_rowbase[lane] = x - v;
-            if (lane == 31) { s_total = x; s_next = 0; }
+            if (lane == 31) s_total = x;
         }
         __syncthreads();
         const int total = s_total;
-        // the rows of the pass are handed out 32 at a time from a shared counter: a warp that drew short rows comes back
-        // sooner, so the warps reach the barrier that ends the pass together
-        while (true) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&s_next, 32);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base >= total) break;
+        int lo = 0;                        // last edge with rowbase <= item (items of a lane only move forward)
+        for (int base = warp * 32; base < total; base += VOX_THREADS) {      // warp-uniform trip count
             const int item = base + lane;
-            int ixlo = 0, len = 0, iy = 0, iz = 0, eidx = 0;
+            uint32_t mask = 0, rowinfo = 0;
             if (item < total) {
-                int lo = 0, hi = cnt;                              // last edge with rowbase <= item
-                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_rowbase[mid] <= item) lo = mid; else hi = mid; }
-                eidx = lo;
+                while (lo + 1 < cnt && s_rowbase[lo + 1] <= item) ++lo;
                 const EdgeSm& E = es[lo];
-                const int row = item - E.rowbase, eny = E.n[1];
-                iz = (int)((float)row * (1.0f / (float)eny));
-                iy = row - iz * eny;
+                const int row = item - E.rowbase, eny = E.n[1];      // rows numbered y-fastest: neighbouring lanes update
+                int iz = (int)((float)row * (1.0f / (float)eny));    // different 32-bit words of the u16 accumulators
+                int iy = row - iz * eny;
                 if (iy < 0) { --iz; iy += eny; } else if (iy >= eny) { ++iz; iy -= eny; }
-                int ixhi;
-                row_interval(E, iy, iz, &ixlo, &ixhi);
-                len = ixhi - ixlo + 1;
+                mask = cull_row(E, iy, iz);
+                rowinfo = ((uint32_t)lo << 16) | ((uint32_t)iy << 8) | (uint32_t)iz;
             }
-            const int maxlen = __reduce_max_sync(0xffffffffu, len);
-            const EdgeSm& E = es[eidx];
-            unsigned int* cell = acc + (E.b0[0] + ixlo - t0[0]) * xstride + (E.b0[1] + iy - t0[1]) * ystride + (E.b0[2] + iz - t0[2]);
-            const uint32_t sent0 = ((uint32_t)eidx << 15) | ((uint32_t)iy << 6) | (uint32_t)iz;
-            for (int k = 0; k < maxlen; ++k) {
-                int q = 0;
-                if (k < len) {
-                    q = eval_voxel_f32(E, ixlo + k, iy, iz);
-                    if (q > 0) tile_max(cell + k * xstride, (uint32_t)q);
-                }
-                // voxels in the float32 guard band: queued for the float64 tiers
-                const unsigned int need = __ballot_sync(0xffffffffu, q < 0);
-                if (need) {
-                    if (q < 0) slowq[nslow + __popc(need & ((1u << lane) - 1u))] = sent0 | ((uint32_t)(ixlo + k) << 11);
-                    nslow += __popc(need);
-                    __syncwarp();
-                    if (nslow >= 32) {
-                        flush_slow(0, 32);
-                        __syncwarp();
-                        const unsigned int mv = lane < nslow - 32 ? slowq[32 + lane] : 0u;
-                        __syncwarp();
-                        if (lane < nslow - 32) slowq[lane] = mv;
-                        nslow -= 32;
-                        __syncwarp();
-                    }
+            // compaction: queue entry = (source lane << 4) | ix
+            const int c = __popc(mask);
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+            const int tot = __shfl_sync(0xffffffffu, incl, 31);
+            int w = incl - c;
+            while (mask) {
+                const int ix = __ffs(mask) - 1;
+                mask &= mask - 1;
+                queue[w++] = (unsigned short)((lane << 4) | ix);
+            }
+            __syncwarp();
+            for (int jb = 0; jb < tot; jb += 32) {
+                const int j = jb + lane;
+                const bool on = j < tot;
+                const uint32_t ent = on ? queue[j] : 0u;
+                const uint32_t ri = __shfl_sync(0xffffffffu, rowinfo, ent >> 4);
+                if (on) {
+                    const EdgeSm& E = es[ri >> 16];
+                    const int ix = ent & 15, iy = (ri >> 8) & 255, iz = ri & 255;
+                    const uint32_t q = eval_voxel(E, ix, iy, iz);
+                    if (q) tile_max(acc + (E.b0[0] + ix - t0[0]) * xstride + (E.b0[1] + iy - t0[1]) * ystride + (E.b0[2] + iz - t0[2]), q);
                 }
             }
+            __syncwarp();
         }
-        if (nslow > 0) { flush_slow(0, nslow); nslow = 0; __syncwarp(); }      // (es[] changes with the next pass)
+        if (pass + EPASS >= nall) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // (see the bulk stores below)
         __syncthreads();
     }
-    // pack the accumulators to the volume's u16 cells (same [TX][TY][TZ] order), 8 cells per thread and step
-    for (int i = threadIdx.x * 8; i < tile_elems; i += blockDim.x * 8) {
-        if (i + 8 <= tile_elems) {
-            const uint4 a = *reinterpret_cast<const uint4*>(acc + i), b = *reinterpret_cast<const uint4*>(acc + i + 4);
-            *reinterpret_cast<uint4*>(packed + i) = make_uint4(a.x | (a.y << 16), a.z | (a.w << 16), b.x | (b.y << 16), b.z | (b.w << 16));
-        } else {
-            for (int j = i; j < tile_elems; ++j) packed[j] = (unsigned short)acc[j];
-        }
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // (the bulk stores below read `packed` through the async proxy)
-    __syncthreads();
 
     // stream the tile out: the accumulators already are the volume's u16 cells, 2 algorithmic bytes per voxel
     const size_t base0 = ((size_t)t0[0] * g.D[1] + t0[1]) * g.D[2];
@@ -564,7 +477,7 @@ vox_tile_kernel(const VoxEdge* __restrict__ prep, const int64_t* __restrict__ ed
         if (threadIdx.x == 0) {
             const uint32_t bytes = (uint32_t)plane_len * 2u;
             for (int x = 0; x < t1[0] - t0[0]; ++x) {
-                const uint32_t src = (uint32_t)__cvta_generic_to_shared(packed + (size_t)x * xstride);
+                const uint32_t src = (uint32_t)__cvta_generic_to_shared(acc + (size_t)x * xstride);
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                              ::"l"(vol + base0 + (size_t)x * xpitch), "r"(src), "r"(bytes) : "memory");
             }
@@ -574,7 +487,7 @@ vox_tile_kernel(const VoxEdge* __restrict__ prep, const int64_t* __restrict__ ed
         return;
     }
     for (int x = t0[0]; x < t1[0]; ++x) {
-        const unsigned short* slab = packed + (size_t)(x - t0[0]) * xstride;
+        const unsigned short* slab = acc + (size_t)(x - t0[0]) * xstride;
         if (plane_contig) {
             const size_t base = ((size_t)x * g.D[1] + t0[1]) * g.D[2];
             for (int i = threadIdx.x; i < plane_len; i += blockDim.x) vol[base + i] = slab[i];
@@ -609,10 +522,10 @@ int make_geom(const int dims[3], const OctaVoxOpts* opts, VoxGeom* g) {
     g->min_radius = opts ? opts->min_radius : 0.0;
     g->max_radius = opts ? opts->max_radius : 1.0;
     g->T[1] = TILE_Y;
-    if (const char* ev = getenv("OCTA_VOX_TILE_Y")) { const int v = atoi(ev); if (v == 4 || v == 8 || v == 16) g->T[1] = v; }   // tuning knob
+    if (const char* ev = getenv("OCTA_VOX_TILE_Y")) { const int v = atoi(ev); if (v == 8 || v == 16 || v == 32) g->T[1] = v; }   // tuning knob
     g->T[2] = g->D[2] < TILE_Z_MAX ? g->D[2] : TILE_Z_MAX;
     g->T[0] = 16;                  // <= 16: a row's survivors are a 16-bit mask
-    while (g->T[0] > 1 && (size_t)g->T[0] * g->T[1] * g->T[2] * 6 > 56 * 1024) g->T[0] >>= 1;      // u32 accumulators + packed u16 tile
+    while (g->T[0] > 1 && (size_t)g->T[0] * g->T[1] * g->T[2] * sizeof(uint16_t) > 56 * 1024) g->T[0] >>= 1;
     for (int a = 0; a < 3; ++a) g->nt[a] = (g->D[a] + g->T[a] - 1) / g->T[a];
     g->ntiles = g->nt[0] * g->nt[1] * g->nt[2];
     return OCTA_OK;
@@ -703,9 +616,7 @@ extern "C" int octa_voxelize_batch_dev(const double* edges7_dev, const int64_t* 
                                                         w.tile_edges);
         octa::count_launch();
     }
-    const size_t queues = (size_t)(VOX_THREADS / 32) * SLOWCAP * sizeof(unsigned int);
-    const size_t smem = octa::align_up((size_t)g.T[0] * g.T[1] * g.T[2] * 4, 16) +
-                        std::max(octa::align_up((size_t)g.T[0] * g.T[1] * g.T[2] * 2, 16), queues);
+    const size_t smem = octa::align_up((size_t)g.T[0] * g.T[1] * g.T[2] * sizeof(uint16_t), 16);
     static size_t smem_set = 0;
     if (smem > smem_set) {
         OCTA_CUDA_CHECK(cudaFuncSetAttribute(vox_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -87,7 +87,8 @@ def generate(config: dict, seeds, batch: int = 32, in_flight: int = 8, writer_th
     dirs, tables, futs = [], {}, []
     write_csv = bool(out_cfg["save_trees"]) and not gather
     with cf.ThreadPoolExecutor(max_workers=max(1, writer_threads)) as writers:
-        for bi, out in enumerate(pipe.run_pipelined(batches, d2h=True, csv=write_csv, in_flight=in_flight, d2h_volume=save3d)):
+        for bi, out in enumerate(pipe.run_pipelined(batches, d2h=True, csv=write_csv, in_flight=in_flight, d2h_volume=save3d,
+                                                    extra_slots=1 if save3d else None)):
             n = len(batches[bi])
             for i in range(n):
                 img = np.array(out["image_host"][i]) if out_cfg["save_2D_image"] else None        # copies: the pinned buffers are recycled

@@ -11,6 +11,7 @@ import concurrent.futures as cf
 import ctypes
 import os
 import threading
+import time
 from typing import Sequence
 
 import numpy as np
@@ -60,7 +61,9 @@ class Pipeline:
         """Growth of one batch (blocking; a growth context owns two high-priority streams) into pinned edge rows."""
         torch = self.torch
         lock = self._grow_locks.setdefault(ctx, threading.Lock())
+        t_sub = time.perf_counter()
         with lock, torch.cuda.device(self.device):
+            t_g0 = time.perf_counter()
             g = self._grows.get(ctx)
             if g is None or g.max_graphs < len(seeds):
                 if g is not None:
@@ -82,18 +85,25 @@ class Pipeline:
             # plain memmove (ctypes releases the GIL): torch's copy_ would open a 16-thread OpenMP region per call, from every
             # grower thread at once, next to the CSV pool
             ctypes.memmove(host_edges.data_ptr(), ctx_edges.data_ptr(), E * 56)
-            return {"n": n, "cap": cap, "host_edges": host_edges, "offs": offs, "n_art": n_art, "stats": stats, "grow_ms": grow_ms}
+            return {"n": n, "cap": cap, "host_edges": host_edges, "offs": offs, "n_art": n_art, "stats": stats, "grow_ms": grow_ms,
+                    "trace": {"ctx": ctx, "slot": slot, "t_submit": t_sub, "t_grow0": t_g0, "t_grow1": time.perf_counter()}}
 
-    def _post_stage(self, g: dict, slot: int, d2h: bool, csv: bool, stream=None, d2h_volume: bool = False) -> dict:
+    def _post_stage(self, g: dict, slot: int, d2h: bool, csv: bool, stream=None, d2h_volume: bool = False,
+                    shared_device: bool = False) -> dict:
         """Edge rows -> device, voxelize, 2-D rasters, optional D2H + CSV text, all ENQUEUED on `stream` (default: current).
         Nothing here waits for the device: out["ready"] is recorded behind the last operation and `_finish` (or the caller)
         waits on it; the CSV text is formatted by a thread pool meanwhile."""
         torch = self.torch
+        t_p0 = time.perf_counter()
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream() if stream is None else stream
             with torch.cuda.stream(stream):
                 n, cap, host_edges, offs, n_art = g["n"], g["cap"], g["host_edges"], g["offs"], g["n_art"]
-                sfx = str(slot)
+                # Host-buffer mode hands out pinned host memory only, so everything on the device is scratch of this stream
+                # (reused in stream order by the next batch): ONE shared set of device buffers, and buffer sets are cheap
+                # (73 MB of pinned memory each).  Device-resident mode hands the device tensors out: one set per slot.
+                sfx = "S" if (d2h and shared_device) else str(slot)
+                hsfx = str(slot)
                 E = int(offs[-1])
                 he = host_edges.numpy()
                 edges_dev = self._tensor("edges_dev" + sfx, (cap, 7), torch.float64)
@@ -131,14 +141,14 @@ class Pipeline:
                 if d2h:
                     lab_h = None
                     if lab is not None:
-                        lab_h = self._tensor("label_host" + sfx, tuple(lab.shape), torch.uint8, pinned=True)
+                        lab_h = self._tensor("label_host" + hsfx, tuple(lab.shape), torch.uint8, pinned=True)
                         lab_h.copy_(lab, non_blocking=True)
-                    img_h = self._tensor("image_host" + sfx, tuple(img.shape), torch.uint8, pinned=True)
+                    img_h = self._tensor("image_host" + hsfx, tuple(img.shape), torch.uint8, pinned=True)
                     img_h.copy_(img, non_blocking=True)
                     out["_host"] = (lab_h, img_h)
                     out["d2h_bytes"] = int((lab_h.numel() if lab_h is not None else 0) + img_h.numel())
                     if d2h_volume and self.voxelize:
-                        vol_h = self._tensor("vol_host" + sfx, tuple(out["volume"].shape), torch.uint16, pinned=True)
+                        vol_h = self._tensor("vol_host" + hsfx, tuple(out["volume"].shape), torch.uint16, pinned=True)
                         vol_h.copy_(out["volume"], non_blocking=True)
                         out["_vol_host"] = vol_h
                         out["d2h_bytes"] += int(vol_h.numel() * 2)
@@ -147,13 +157,18 @@ class Pipeline:
                             self._csv_pool = cf.ThreadPoolExecutor(max_workers=self.host_threads)
                         # ctypes releases the GIL; the text is collected in _finish
                         out["_csv"] = [self._csv_pool.submit(graph_io.csv_bytes, he[offs[i]:offs[i + 1]]) for i in range(n)]
+                if d2h and shared_device:             # the device tensors of this batch are recycled by the next one
+                    for k in ("volume", "label", "image"):
+                        out.pop(k, None)
                 ready = torch.cuda.Event()
                 ready.record(stream)
                 out["ready"] = ready          # device results (and the pinned host copies) are complete once this event has fired
+                out["trace"] = dict(g.get("trace", {}), t_post0=t_p0, t_post1=time.perf_counter())
                 return out
 
     def _finish(self, out: dict, wait: bool = True) -> dict:
         """Hand a result out: wait for its device work (host-buffer mode) and collect the CSV text."""
+        t_f0 = time.perf_counter()
         if "_host" in out:
             out["ready"].synchronize()
             lab_h, img_h = out.pop("_host")
@@ -162,8 +177,11 @@ class Pipeline:
                 out["volume_host"] = out.pop("_vol_host").numpy()
         elif wait:
             out["ready"].synchronize()
+        t_r = time.perf_counter()
         if "_csv" in out:
             out["csv"] = [f.result() for f in out.pop("_csv")]
+        if "trace" in out:
+            out["trace"].update(t_fin0=t_f0, t_ready=t_r, t_fin1=time.perf_counter())
         return out
 
     def run(self, seeds: Sequence[int], d2h: bool = True, csv: bool = True, d2h_volume: bool = False) -> dict:
@@ -172,14 +190,17 @@ class Pipeline:
         return self._finish(self._post_stage(self._grow_stage(seeds, 0), 0, d2h, csv, d2h_volume=d2h_volume))
 
     @staticmethod
-    def buffer_sets(in_flight: int, d2h: bool = False) -> int:
+    def buffer_sets(in_flight: int, d2h: bool = False, extra_slots=None) -> int:
         """Buffer sets run_pipelined cycles through: one per loop in flight, one being post-processed, and in host-buffer mode
-        two more whose copies / CSV text are still landing (OCTA_EXTRA_SLOTS overrides).  Each set is allocated on first use:
-        warm up with at least this many batches."""
-        extra = os.environ.get("OCTA_EXTRA_SLOTS")
-        return max(1, int(in_flight)) + 1 + (max(0, int(extra)) if extra is not None else (2 if d2h else 0))
+        twelve more (73 MB of pinned memory each) whose post-processing may lag behind: it runs at default priority in whatever
+        the high-priority growth loops leave free, and a result is only handed out once its copies have landed -- measured on
+        one B200, 8 loops in flight: 322 graphs/s with 2 spare sets, 405 with 6 (OCTA_EXTRA_SLOTS overrides).  Each set is
+        allocated on first use: warm up with at least this many batches."""
+        extra = extra_slots if extra_slots is not None else os.environ.get("OCTA_EXTRA_SLOTS")
+        return max(1, int(in_flight)) + 1 + (max(0, int(extra)) if extra is not None else (12 if d2h else 3))
 
-    def run_pipelined(self, seed_batches, d2h: bool = True, csv: bool = True, in_flight: int = 2, d2h_volume: bool = False):
+    def run_pipelined(self, seed_batches, d2h: bool = True, csv: bool = True, in_flight: int = 2, d2h_volume: bool = False,
+                      extra_slots=None):
         """Generator over batches, results in order, software-pipelined.
 
         The growth loop is a chain of short latency-bound launches that leaves most of the GPU idle, voxelize / raster
@@ -191,14 +212,14 @@ class Pipeline:
         only); a yielded result stays valid until buffer_sets(in_flight, d2h) further batches have been started."""
         torch = self.torch
         in_flight = max(1, int(in_flight))
-        nslots = self.buffer_sets(in_flight, d2h)
+        nslots = self.buffer_sets(in_flight, d2h, extra_slots)
         if self._post_stream is None:
             with torch.cuda.device(self.device):
                 self._post_stream = torch.cuda.Stream()
         pending = collections.deque()
         with cf.ThreadPoolExecutor(max_workers=in_flight) as growers, cf.ThreadPoolExecutor(max_workers=1) as poster:
             def post(gf, slot):
-                return self._post_stage(gf.result(), slot, d2h, csv, self._post_stream, d2h_volume)
+                return self._post_stage(gf.result(), slot, d2h, csv, self._post_stream, d2h_volume, shared_device=True)
 
             for k, seeds in enumerate(seed_batches):
                 while len(pending) >= nslots:                 # buffer set k % nslots is free once result k - nslots is out
