@@ -1171,6 +1171,13 @@ __device__ bool kill_convert(const GrowDev& D, const GrowShape& S, int g, int T,
     const int* hitj = D.hitj + sb;
     const int* ta = D.ta + sb;
     int* seq = D.seq + sb;
+    // order test of pyset_run_multi: hashes and ball ids of the sequence staged in the (now idle) node-coordinate arrays, its
+    // tables in the space of the hash tables
+    const bool multi = DETECT && T <= MS_MAXT;
+    long long* ms_hs = reinterpret_cast<long long*>(ks->nxs);
+    int* ms_bl = reinterpret_cast<int*>(ks->nys);
+    static_assert(sizeof(ks->nxs) >= sizeof(long long) * MS_MAXT && sizeof(ks->nys) >= sizeof(int) * MS_MAXT, "staging space");
+    static_assert(sizeof(ks->th) >= sizeof(short) * MS_TABLES * MS_TBL && SM_TBL >= MS_TBL, "table space");
     for (int q = tid; q < T; q += blockDim.x) {
         const int i = ta[q];
         const int ji = hitj[i];
@@ -1183,13 +1190,23 @@ __device__ bool kill_convert(const GrowDev& D, const GrowShape& S, int g, int T,
             rank += (j2 < ji) || (j2 == ji && k2 < ki);
         }
         seq[rank] = i;
-        D.seqhash[sb + rank] = py_hash_tuple3(sx[i], sy[i], sz[i]);   // CPython hash of the sink tuple, in parallel
+        const long long h = py_hash_tuple3(sx[i], sy[i], sz[i]);      // CPython hash of the sink tuple, in parallel
+        D.seqhash[sb + rank] = h;
+        if (multi) { ms_hs[rank] = h; ms_bl[rank] = ji; }
     }
     for (int i = tid; i < 8; i += blockDim.x) { ks->tk[0][i] = -1; ks->th[0][i] = 0; }
     __syncthreads();
     long long* gth = D.set_hash + (size_t)g * 2 * SET_TBL;
     int* gtk = D.set_key + (size_t)g * 2 * SET_TBL;
-    if (tid == 0) {
+    if (tid == 0 && multi) {
+        int mask = 7;
+        const int why = pyset_run_multi(ms_hs, ms_bl, T, reinterpret_cast<short*>(ks->th), &mask);
+        if (!why) {
+            const short* tab = reinterpret_cast<const short*>(ks->th);
+            for (int z = 0; z <= mask; ++z) ks->tk[0][z] = tab[z] >= 0 ? seq[tab[z]] : -1;
+        }
+        ks->tabinfo[0] = 0; ks->tabinfo[1] = mask; ks->tabinfo[2] = 0; ks->tabinfo[3] = why ? 1 : 0;
+    } else if (tid == 0) {
         PySetDev ps;
         ps.sh = ks; ps.gth = gth; ps.gtk = gtk;
         ps.init();

@@ -163,4 +163,148 @@ OCTA_PS_HD inline bool pyset_run(PySetDev& ps, const int* seq, const long long* 
     return false;
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Multi-state order test (T <= MS_MAXT keys, tables of up to MS_TBL slots).  pyset_run<true> above decides ball by ball and
+// gives up as soon as two orders of a ball leave different tables -- but most of those differences sit in the small early
+// tables (8 and 32 slots: the first 19 keys) and are erased by the next growth, which re-inserts the keys in slot order into a
+// table four times the size.  This test carries every table the unknown orders can have produced so far (at most MS_ALT of
+// them; all share mask and fill, growth depends on counts only), merges equal ones, and asks for the exact order only when
+//   * more than one table is alive and no growth is left (final fill = T is known), or at the end,
+//   * more than MS_ALT tables are alive, or a ball of more than 4 keys would have to be permuted.
+// Tables hold POSITIONS in the insertion sequence as 16-bit integers (key = seq[pos], hash = hs[pos], ball = bl[pos]).
+constexpr int MS_TBL = 512;
+constexpr int MS_MAXT = 306;            // the 307th key grows the table to 2048 slots
+constexpr int MS_ALT = 6;
+constexpr int MS_TABLES = 2 * MS_ALT + 2;
+
+OCTA_PS_HD inline void ms_insert(short* tab, size_t mask, int pos, long long hash, const int* bl, int ball, bool* same_ball) {
+    size_t perturb = (size_t)hash, i = (size_t)hash & mask;
+    while (true) {
+        size_t e = i;
+        int probes = (i + 9 <= mask) ? 9 : 0;
+        do {
+            const int k = tab[e];
+            if (k < 0) { tab[e] = (short)pos; return; }
+            if (bl && bl[k] == ball) *same_ball = true;
+            ++e;
+        } while (probes--);
+        perturb >>= 5;
+        i = (i * 5 + 1 + perturb) & mask;
+    }
+}
+
+// positions q + perm[0..m) into `tab` (set_add_entry + set_table_resize; `tmp` receives a grown table first)
+OCTA_PS_HD inline void ms_apply(short* tab, short* tmp, size_t* mask, size_t* fill, const long long* hs, const int* bl, int q,
+                                const int* perm, int m, bool track, bool* inter, bool* grew_inside, bool* grew) {
+    for (int k = 0; k < m; ++k) {
+        const int pos = q + (perm ? perm[k] : k);          // perm == nullptr: index order
+        ms_insert(tab, *mask, pos, hs[pos], track ? bl : nullptr, bl[q], inter);
+        ++*fill;
+        if (*fill * 5 >= *mask * 3) {
+            size_t newsize = 8;
+            while (newsize <= *fill * 4) newsize <<= 1;
+            for (size_t z = 0; z < newsize; ++z) tmp[z] = -1;
+            for (size_t z = 0; z <= *mask; ++z)
+                if (tab[z] >= 0) ms_insert(tmp, newsize - 1, tab[z], hs[tab[z]], nullptr, 0, nullptr);
+            for (size_t z = 0; z < newsize; ++z) tab[z] = tmp[z];
+            *mask = newsize - 1;
+            *grew = true;
+            if (k < m - 1) *grew_inside = true;
+        }
+    }
+}
+
+OCTA_PS_HD inline bool ms_equal(const short* a, const short* b, size_t n) {
+    for (size_t z = 0; z < n; ++z) if (a[z] != b[z]) return false;
+    return true;
+}
+
+// hs / bl: hash and ball id per sequence position (T <= MS_MAXT), tabs: MS_TABLES tables of MS_TBL shorts.  Returns 0 and the
+// final table in tabs[0 .. *mask_out] (positions, -1 = empty) when the result does not depend on the order inside any ball,
+// else a reason code > 0 (1: ball of > 4 keys, 2: too many alive tables, 3: alive tables differ with no growth left).
+OCTA_PS_HD inline int pyset_run_multi(const long long* hs, const int* bl, int T, short* tabs, int* mask_out) {
+    short* A = tabs;                               // alive tables
+    short* B = tabs + (size_t)MS_ALT * MS_TBL;     // tables after the current ball
+    short* cand = tabs + (size_t)2 * MS_ALT * MS_TBL;
+    short* tmp = cand + MS_TBL;
+    size_t mask = 7, fill = 0;
+    int alive = 1;
+    for (int z = 0; z < 8; ++z) A[z] = -1;
+    int q = 0;
+    while (q < T) {
+        const int ball = bl[q];
+        int q2 = q + 1;
+        while (q2 < T && bl[q2] == ball) ++q2;
+        const int m = q2 - q;
+        size_t mask1 = mask, fill1 = fill;
+        bool grew_any = false;
+        if (m == 1) {
+            for (int s = 0; s < alive; ++s) {
+                size_t mk = mask, fl = fill;
+                bool gi = false, gr = false;
+                ms_apply(A + (size_t)s * MS_TBL, tmp, &mk, &fl, hs, bl, q, nullptr, 1, false, nullptr, &gi, &gr);
+                mask1 = mk; fill1 = fl; grew_any = gr;
+            }
+            if (grew_any && alive > 1) {            // a growth may have erased the differences: merge equal tables
+                int keep = 0;
+                for (int s = 0; s < alive; ++s) {
+                    bool dup = false;
+                    for (int u = 0; u < keep && !dup; ++u) dup = ms_equal(A + (size_t)u * MS_TBL, A + (size_t)s * MS_TBL, mask1 + 1);
+                    if (!dup) {
+                        if (keep != s) for (size_t z = 0; z <= mask1; ++z) A[(size_t)keep * MS_TBL + z] = A[(size_t)s * MS_TBL + z];
+                        ++keep;
+                    }
+                }
+                alive = keep;
+            }
+        } else {
+            int nb = 0;
+            auto push = [&](const short* t, size_t n) -> bool {        // false: too many alive tables
+                for (int u = 0; u < nb; ++u) if (ms_equal(B + (size_t)u * MS_TBL, t, n)) return true;
+                if (nb == MS_ALT) return false;
+                for (size_t z = 0; z < n; ++z) B[(size_t)nb * MS_TBL + z] = t[z];
+                ++nb;
+                return true;
+            };
+            for (int s = 0; s < alive; ++s) {
+                const short* src = A + (size_t)s * MS_TBL;
+                // index order with tracking: no key of the ball examines a slot held by a key of the same ball and no growth
+                // before its last key -> each key lands on the first free slot of its own probe sequence, whatever the order
+                for (size_t z = 0; z <= mask; ++z) cand[z] = src[z];
+                size_t mk = mask, fl = fill;
+                bool inter = false, gi = false, gr = false;
+                ms_apply(cand, tmp, &mk, &fl, hs, bl, q, nullptr, m, true, &inter, &gi, &gr);
+                mask1 = mk; fill1 = fl;
+                if (!push(cand, mk + 1)) return 2;
+                if (!inter && !gi) continue;
+                if (m > 4) return 1;
+                int perm[4] = {0, 1, 2, 3};
+                while (true) {
+                    int i = m - 2;
+                    while (i >= 0 && perm[i] > perm[i + 1]) --i;
+                    if (i < 0) break;
+                    int j = m - 1;
+                    while (perm[j] < perm[i]) --j;
+                    { const int t = perm[i]; perm[i] = perm[j]; perm[j] = t; }
+                    for (int a = i + 1, b = m - 1; a < b; ++a, --b) { const int t = perm[a]; perm[a] = perm[b]; perm[b] = t; }
+                    for (size_t z = 0; z <= mask; ++z) cand[z] = src[z];
+                    mk = mask; fl = fill;
+                    bool i2 = false, g2 = false, g3 = false;
+                    ms_apply(cand, tmp, &mk, &fl, hs, bl, q, perm, m, false, &i2, &g2, &g3);
+                    if (!push(cand, mk + 1)) return 2;
+                }
+            }
+            { short* t = A; A = B; B = t; }
+            alive = nb;
+        }
+        mask = mask1; fill = fill1;
+        if (alive > 1 && !((size_t)T * 5 >= mask * 3)) return 3;      // no growth left that could merge them
+        q = q2;
+    }
+    if (alive > 1) return 3;
+    if (A != tabs) for (size_t z = 0; z <= mask; ++z) tabs[z] = A[z];
+    *mask_out = (int)mask;
+    return 0;
+}
+
 }  // namespace octa

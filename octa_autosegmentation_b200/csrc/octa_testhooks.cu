@@ -25,6 +25,16 @@ extern "C" int octa_test_pyset(const double* xyz, const int* ball, int T, int de
     octa::PySetDev ps;
     ps.sh = &ks; ps.gth = gth.data(); ps.gtk = gtk.data();
     ps.init();
+    if (detect == 2 && T <= octa::MS_MAXT) {          // the multi-state test k_kill runs for T <= MS_MAXT
+        std::vector<short> tabs((size_t)octa::MS_TABLES * octa::MS_TBL);
+        int mask = 0;
+        const int why = octa::pyset_run_multi(sh.data(), ball, T, tabs.data(), &mask);
+        if (why) return why;
+        int n = 0;
+        for (int z = 0; z <= mask; ++z) if (tabs[z] >= 0) order_out[n++] = seq[tabs[z]];
+        *n_out = n;
+        return 0;
+    }
     const bool flagged = detect ? octa::pyset_run<true>(ps, seq.data(), sh.data(), T, ball, gtk.data())
                                 : octa::pyset_run<false>(ps, seq.data(), sh.data(), T, ball, gtk.data());
     if (ps.err) return -ps.err;
