@@ -41,8 +41,9 @@ WORKLOAD = ("BASELINE config #2: batch of %d seeded samples per GPU, default 3x3
 
 
 def load_traffic(batch):
-    """DRAM bytes per launch of vox_tile_kernel from the committed `ncu --set full` capture (profiles/), same batch."""
-    p = os.path.join(ROOT, "profiles", "r01_vox_tile_traffic.json")
+    """DRAM bytes per launch of vox_col_kernel -- NOT measured in this run: read from the committed `ncu --set full` capture
+    of the same kernel, batch and volume (profiles/r02_vox_col_traffic.json; the line says so in roofline.traffic_source)."""
+    p = os.path.join(ROOT, "profiles", "r02_vox_col_traffic.json")
     if os.path.exists(p):
         with open(p) as f:
             t = json.load(f)
@@ -166,8 +167,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--d2h-volume", action="store_true")
     ap.add_argument("--no-gan", action="store_true", help="skip the config #5 (GAN contrast adaptation) leg")
-    ap.add_argument("--in-flight", type=int, default=8, help="growth loops (sub-batches) in flight per GPU in the pipelined API")
-    ap.add_argument("--sub-batch", type=int, default=32, help="samples per growth loop; a step's --batch samples are fed to the "
+    ap.add_argument("--in-flight", type=int, default=7, help="growth loops (sub-batches) in flight per GPU in the pipelined API")
+    ap.add_argument("--sub-batch", type=int, default=64, help="samples per growth loop; a step's --batch samples are fed to the "
                                                               "pipelined API as batch / sub-batch consecutive batches")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -362,7 +363,9 @@ def main():
                     "note": "host API: + CSV text of every graph (byte-exact), + D2H of label (1216^2 u8) and image (304^2 u8) "
                             "into pinned memory; growth topology D2H and edge-row H2D are inside both numbers"},
             "roofline": {"bound": "hbm", "achieved": vox_ach, "peak": peak, "unit": "GB/s", "frac": vox_ach / peak,
-                         "traffic": load_traffic(B), "peak_source": peak_src, "kernel": "vox_tile_kernel (+prep/scan/fill, <1 %)",
+                         "traffic": load_traffic(B), "traffic_source": "committed ncu --set full capture of the same launch shape "
+                         "(profiles/r02_vox_col_traffic.json), not measured in this run",
+                         "peak_source": peak_src, "kernel": "vox_col_kernel (+prep/scan/fill, <1 %)",
                          "algorithmic_bytes_per_launch": vox_alg, "ms_per_launch": vox_ms,
                          "note": "the HBM-bound kernel of the path; see roofline_growth for the phase that dominates step time"},
             "roofline_growth": {"bound": "hbm", "achieved": grow_ach, "peak": peak, "unit": "GB/s", "frac": grow_ach / peak,

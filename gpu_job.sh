@@ -1,12 +1,4 @@
 mkdir -p gpurun_out
-nproc; lscpu | grep "Model name"
-P="timeout 300 python tools/pipe_probe.py"
-$P 24 4 64 1 2>&1 | grep "PROBE\|Error"
-OCTA_BALL_ORDER=always $P 24 4 64 1 2>&1 | grep "PROBE\|Error"
-OCTA_BALL_ORDER=index $P 24 4 64 1 2>&1 | grep "PROBE\|Error"
-OCTA_BALL_ORDER=always $P 24 8 32 1 2>&1 | grep "PROBE\|Error"
-OCTA_GROW_GRAPH=1 $P 24 8 32 1 2>&1 | grep "PROBE\|Error"
-OCTA_GROW_GRAPH=1 $P 24 4 64 1 2>&1 | grep "PROBE\|Error"
-OCTA_GROW_GRAPH=1 OCTA_BALL_ORDER=always $P 24 8 32 1 2>&1 | grep "PROBE\|Error"
-$P 24 6 64 1 2>&1 | grep "PROBE\|Error"
-$P 24 3 128 1 2>&1 | grep "PROBE\|Error"
+timeout 600 python -m pytest tests/test_voxelize_gpu.py -m gpu -x -q 2>&1 | tail -5
+timeout 300 python tools/post_only.py 5 vox 2>&1 | tail -1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:vox_col_kernel -s 1 -c 1 -f -o gpurun_out/r02_vox_col_v3 python tools/post_only.py 1 vox > gpurun_out/ncu_vox.log 2>&1; tail -2 gpurun_out/ncu_vox.log

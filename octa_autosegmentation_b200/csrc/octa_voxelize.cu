@@ -33,12 +33,17 @@ constexpr int TILE_Y = 16;
 constexpr int TILE_Z_MAX = 64;
 constexpr int VOX_THREADS = 256;
 
-struct VoxEdge {   // 80 bytes
+struct VoxEdge {   // per edge, tile independent (vox_prep_kernel)
     double p1[3];
     double p2[3];
     double R;
     int lo[3];     // inclusive
     int hi[3];     // exclusive; lo == hi on any axis -> edge contributes nothing
+    // derived constants of the column kernel: float64 fast path ...
+    double ss, inv_ss, c0, tguard;
+    // ... and float32 tier: axis vector, 1/|s|^2, 1/|s_xy|^2, reach = R + sqrt3/2, (reach + slack)^2, guard band of 255*I
+    float f[3], finv, inv2d, reach, thr, eps;
+    int zc0, zc1;  // z range outside of which the contribution is certainly zero, cut to [lo[2], hi[2])
 };
 
 struct VoxGeom {
@@ -115,6 +120,33 @@ __global__ void vox_prep_kernel(const double* __restrict__ edges7, const int64_t
         if (!keep || !(e.hi[a] > e.lo[a])) { e.lo[a] = 0; e.hi[a] = 0; }
     }
     if (!keep) { e.lo[0] = e.hi[0] = 0; }
+    {
+        const double SQRT3 = 1.7320508075688772, INV_SQRT3 = 0.57735026918962576;
+        const double s0 = e.p1[0] - e.p2[0], s1 = e.p1[1] - e.p2[1], s2 = e.p1[2] - e.p2[2];
+        const double ss = (s0 * s0 + s1 * s1) + s2 * s2;
+        e.ss = ss;
+        e.inv_ss = ss > 0.0 ? 1.0 / ss : 0.0;
+        e.c0 = 1.0 + (e.R - SQRT3 / 2) * INV_SQRT3;      // I = c0 - d/sqrt3
+        e.tguard = 1e-9 * ss;
+        e.f[0] = (float)s0; e.f[1] = (float)s1; e.f[2] = (float)s2;
+        e.finv = (float)e.inv_ss;
+        const double s2d = s0 * s0 + s1 * s1;
+        e.inv2d = s2d > 0.0 ? (float)(1.0 / s2d) : 0.f;
+        const double reach = e.R + SQRT3 / 2;
+        e.reach = (float)reach;
+        // |voxel - p2| inside the box is at most |s| + R*sqrt2 + 2 per axis: the float32 tier works on numbers of that
+        // size with a few roundings each (the tile-relative offsets are carried as two floats), so 255*I = 147.2*(reach-d)
+        // is good to a few ulp of that magnitude; 16 ulp + 1e-3 is the guard band around the integers
+        const double ext = fabs(s0) + fabs(s1) + fabs(s2) + 3.0 * (e.R * 1.4142135623730951 + 2.0) + reach;
+        const double eps = 1e-3 + 147.3 * ext * (16.0 / 16777216.0);
+        e.eps = (float)eps;
+        const double rs = reach + eps / 100.0;
+        e.thr = (float)(rs * rs * (1.0 + 1e-6));
+        double zl = e.p1[2] < e.p2[2] ? e.p1[2] : e.p2[2], zh = e.p1[2] < e.p2[2] ? e.p2[2] : e.p1[2];
+        e.zc0 = imax(e.lo[2], d2i_sat(floor(zl - rs - 0.51)));
+        e.zc1 = imin(e.hi[2], d2i_sat(ceil(zh + rs - 0.49)) + 1);
+        if (e.zc1 < e.zc0) e.zc1 = e.zc0;
+    }
     prep[i] = e;
     int tlo[3], thi[3], n;
     tile_range(e, g, tlo, thi, n);
@@ -501,6 +533,307 @@ vox_tile_kernel(const VoxEdge* __restrict__ prep, const int64_t* __restrict__ ed
 }
 
 // ---------------------------------------------------------------------------------------------
+// main kernel, column ownership (default): one CTA = one tile of one graph, one THREAD = one (x,y) column of the tile
+// ---------------------------------------------------------------------------------------------
+// vox_tile_kernel above deals (y,z) rows of the edge boxes to lanes, so two lanes can meet in one voxel and every update is
+// a 16-bit compare-and-swap (emulated: a 32-bit CAS loop with byte permutes), and it walks every row of every box voxel
+// by voxel to find the 18 % of the candidates that contribute.  Here a thread OWNS the z column of one (x,y) of the tile:
+//   * no atomics: a column is updated by plain 16-bit loads and stores of its owner;
+//   * culling is per (column, edge), not per candidate voxel: box test, then the distance of the column from the
+//     xy projection of the capsule axis (a lower bound of the 3-D distance) -- vessels are thin (median radius one voxel
+//     at 1216^2), so a 16 x 16 box of an edge keeps ~28 of its 256 columns;
+//   * a surviving column walks the z range the capsule can reach (6 voxels on average) in float32: the offsets of the
+//     column from the edge's end point are formed from two-float tile-relative constants, 255*I = 147.2*(reach - d) is
+//     accurate to a few 1e-3 (VoxEdge::eps), so its floor equals the reference's unless it lies within eps of an integer;
+//   * those voxels (< 1 %) take the float64 fast path (fma, reciprocal: 255*I to ~1e-11), and inside 1e-7 of an integer or
+//     with t within 1e-9 of {0,1} the reference's exact operation chain decides (exact_voxel_q) -- as in the row kernel.
+// The tile is accumulated as u16 cells in the volume's own layout and leaves with TMA bulk copies, as before.
+struct ColEdge {             // per edge of a pass, tile-local
+    float ah[3], al[3];      // p2 - (tile origin + 0.5) as hi + lo
+    float f[3], finv, inv2d, reach, thr, eps;
+    short x0, nx, y0, ny, z0, nz;
+    int rcp;                 // ceil(2^20 / nz): item / nz without a division
+    int idx;
+};
+constexpr int SLOWCAP = 160; // deferred float64 evaluations per CTA (~15 per tile are usual; beyond: the cell is marked and recomputed)
+
+__device__ __noinline__ uint32_t slow_voxel_q(const VoxEdge* __restrict__ ep, int vx_i, int vy_i, int vz_i) {
+    const VoxEdge& E = *ep;
+    const double vx = (double)vx_i + 0.5, vy = (double)vy_i + 0.5, vz = (double)vz_i + 0.5;
+    const double s0 = E.p1[0] - E.p2[0], s1 = E.p1[1] - E.p2[1], s2 = E.p1[2] - E.p2[2], ss = E.ss;
+    const double u0 = vx - E.p2[0], u1 = vy - E.p2[1], u2 = vz - E.p2[2];
+    const double dot = fma(u2, s2, fma(u1, s1, u0 * s0));
+    uint32_t q = 0;
+    bool exact = fabs(dot) < E.tguard || fabs(dot - ss) < E.tguard;
+    if (!exact) {
+        double dd;
+        if (dot > 0.0 && dot < ss) {
+            const double t = dot * E.inv_ss;
+            const double e0 = fma(-t, s0, u0), e1 = fma(-t, s1, u1), e2 = fma(-t, s2, u2);
+            dd = fma(e2, e2, fma(e1, e1, e0 * e0));
+        } else {
+            const double q0 = vx - E.p1[0], q1 = vy - E.p1[1], q2 = vz - E.p1[2];
+            dd = fmin(fma(u2, u2, fma(u1, u1, u0 * u0)), fma(q2, q2, fma(q1, q1, q0 * q0)));
+        }
+        const double val = 255.0 * fma(-sqrt(dd), 0.57735026918962576, E.c0);
+        if (val < -1e-7) return 0;
+        const double fl = floor(val);
+        const double fr = val - fl;
+        exact = fr < 1e-7 || fr > 1.0 - 1e-7 || !(val == val);
+        q = val >= 255.0 ? 255u : (uint32_t)fl;
+    }
+    if (exact) q = exact_voxel_q(E, vx, vy, vz);
+    return q;
+}
+
+// cells marked 0xffff (their deferred evaluation did not fit the queue): exact maximum over every edge of the tile
+__device__ __noinline__ void resolve_marked(const VoxEdge* __restrict__ ge, const int* __restrict__ lst, int nlist,
+                                            const int* __restrict__ bl, int nbig, unsigned short* acc, int tile_elems,
+                                            int t0x, int t0y, int t0z, int xstride, int ystride) {
+    for (int c = threadIdx.x; c < tile_elems; c += blockDim.x) {
+        if (acc[c] != 0xffffu) continue;
+        const int cx = c / xstride, r = c - cx * xstride, cy = r / ystride, z = r - cy * ystride;
+        const int vx = t0x + cx, vy = t0y + cy, vz = t0z + z;
+        uint32_t best = 0;
+        for (int k = 0; k < nlist + nbig; ++k) {
+            const VoxEdge* e = ge + (k < nlist ? lst[k] : bl[k - nlist]);
+            if (vx < e->lo[0] || vx >= e->hi[0] || vy < e->lo[1] || vy >= e->hi[1] || vz < e->lo[2] || vz >= e->hi[2]) continue;
+            const uint32_t q = slow_voxel_q(e, vx, vy, vz);
+            best = q > best ? q : best;
+        }
+        acc[c] = (unsigned short)best;
+    }
+}
+
+__global__ void __launch_bounds__(VOX_THREADS, 6)
+vox_col_kernel(const VoxEdge* __restrict__ prep, const int64_t* __restrict__ edge_offsets, VoxGeom g,
+               const int* __restrict__ tile_start, const int* __restrict__ tile_edges,
+               const int* __restrict__ big_count, const int* __restrict__ big_idx,
+               uint16_t* __restrict__ out) {
+    extern __shared__ __align__(128) unsigned short acc[];
+    const int gr = blockIdx.z;
+    const int tx_i = blockIdx.y, ty_i = blockIdx.x / g.nt[2], tz_i = blockIdx.x - ty_i * g.nt[2];
+    const int tile = (tx_i * g.nt[1] + ty_i) * g.nt[2] + tz_i;
+    const int t0x = tx_i * g.T[0], t0y = ty_i * g.T[1], t0z = tz_i * g.T[2];
+    const int64_t e_base = edge_offsets[gr];
+    const VoxEdge* ge = prep + e_base;
+    uint16_t* vol = out + (size_t)gr * g.D[0] * g.D[1] * g.D[2];
+    const int* st = tile_start + (size_t)gr * (g.ntiles + 1);
+    const int beg = st[tile], end = st[tile + 1];
+    const int nbig = big_count[gr];
+
+    if (!(end > beg || nbig > 0)) {
+        // empty tile: stream zeros without touching shared memory
+        const int t1x = imin(t0x + g.T[0], g.D[0]);
+        const int ny = imin(t0y + g.T[1], g.D[1]) - t0y, nz = imin(t0z + g.T[2], g.D[2]) - t0z;
+        const bool plane_contig = (nz == g.D[2] && g.T[2] == g.D[2]);
+        const int plane_len = ny * nz;
+        for (int x = t0x; x < t1x; ++x) {
+            if (plane_contig) {
+                const size_t base = ((size_t)x * g.D[1] + t0y) * g.D[2];
+                if (((base | (size_t)plane_len) & 7) == 0) {
+                    uint4* p = reinterpret_cast<uint4*>(vol + base);
+                    for (int i = threadIdx.x; i < plane_len / 8; i += blockDim.x) p[i] = make_uint4(0, 0, 0, 0);
+                } else {
+                    for (int i = threadIdx.x; i < plane_len; i += blockDim.x) vol[base + i] = 0;
+                }
+            } else {
+                for (int i = threadIdx.x; i < plane_len; i += blockDim.x) {
+                    const int y = i / nz, z = i - y * nz;
+                    vol[((size_t)x * g.D[1] + t0y + y) * g.D[2] + t0z + z] = 0;
+                }
+            }
+        }
+        return;
+    }
+
+    const int tile_elems = g.T[0] * g.T[1] * g.T[2];
+    {
+        uint4* acc4 = reinterpret_cast<uint4*>(acc);
+        for (int i = threadIdx.x; i < tile_elems / 8; i += blockDim.x) acc4[i] = make_uint4(0, 0, 0, 0);
+        for (int i = (tile_elems / 8) * 8 + threadIdx.x; i < tile_elems; i += blockDim.x) acc[i] = 0;
+    }
+    __shared__ ColEdge ce[EPASS];
+    __shared__ float4 s_hit[VOX_THREADS / 32][32];         // per warp: (w0, w1, dxy, cell offset of the column) of the hit columns
+    __shared__ int2 s_slow[SLOWCAP];                        // deferred float64 evaluations of the CTA: (edge, cell)
+    __shared__ int s_nslow;
+    if (threadIdx.x == 0) s_nslow = 0;                      // (ordered before its first use by the barrier of the first pass)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    float4* hitw = s_hit[warp];
+    const uint32_t acc_s = (uint32_t)__cvta_generic_to_shared(acc);
+    const int* lst = tile_edges + (size_t)KBIG * e_base;
+    const int* bl = big_idx + e_base;
+    const int nlist = end - beg, nall = nlist + nbig;
+    const int ystride = g.T[2], xstride = g.T[1] * g.T[2];
+    // columns of the tile -> threads.  16 x 16 tiles: a warp owns an 8 x 4 block of columns
+    const int ncols = g.T[0] * g.T[1];
+    const bool blocked = (g.T[0] == 16 && g.T[1] == 16 && VOX_THREADS == 256);
+    for (int pass = 0; pass < nall; pass += EPASS) {
+        const int cnt = imin(EPASS, nall - pass);
+        if (pass > 0) __syncthreads();                 // the previous pass has been read by every thread
+        if (threadIdx.x < cnt) {
+            const int k = pass + threadIdx.x;
+            const int idx = k < nlist ? lst[beg + k] : bl[k - nlist];
+            const VoxEdge& e = ge[idx];
+            ColEdge c;
+            c.idx = idx;
+            const int t0[3] = {t0x, t0y, t0z};
+            int lo3[3], n3[3];
+            bool any = true;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const int elo = a == 2 ? e.zc0 : e.lo[a], ehi = a == 2 ? e.zc1 : e.hi[a];
+                lo3[a] = imax(elo, t0[a]) - t0[a];
+                n3[a] = imin(imin(ehi, t0[a] + g.T[a]), g.D[a]) - t0[a] - lo3[a];
+                if (n3[a] <= 0) any = false;
+                const double av = e.p2[a] - (double)t0[a] - 0.5;
+                c.ah[a] = (float)av;
+                c.al[a] = (float)(av - (double)c.ah[a]);
+                c.f[a] = e.f[a];
+            }
+            c.x0 = (short)lo3[0]; c.nx = (short)(any ? n3[0] : 0);
+            c.y0 = (short)lo3[1]; c.ny = (short)(any ? n3[1] : 0);
+            c.z0 = (short)lo3[2]; c.nz = (short)(any ? n3[2] : 0);
+            c.rcp = any ? ((1 << 20) + n3[2] - 1) / n3[2] : 0;
+            c.finv = e.finv; c.inv2d = e.inv2d; c.reach = e.reach; c.thr = e.thr; c.eps = e.eps;
+            ce[threadIdx.x] = c;
+        }
+        __syncthreads();                               // (also: the accumulators are cleared)
+        for (int cb = warp * 32; cb < ncols; cb += VOX_THREADS) {      // warp-uniform
+            int cx, cy, bx0, by0, bnx, bny;            // this lane's column; the box of the warp's 32 columns
+            if (blocked) {
+                bx0 = (warp & 1) << 3; by0 = (warp >> 1) << 2; bnx = 8; bny = 4;
+                cx = bx0 + (lane & 7); cy = by0 + (lane >> 3);
+            } else {
+                const int col = cb + lane;
+                cx = col / g.T[1]; cy = col - cx * g.T[1];
+                const int c1 = imin(cb + 31, ncols - 1);
+                bx0 = cb / g.T[1]; bnx = c1 / g.T[1] - bx0 + 1;
+                by0 = bnx > 1 ? 0 : cb - bx0 * g.T[1]; bny = bnx > 1 ? g.T[1] : c1 - cb + 1;
+            }
+            const float coff = __int_as_float(cx * xstride + cy * ystride);
+            const float fcx = (float)cx, fcy = (float)cy;
+            // edges of the pass whose box meets the warp's columns at all (lane k looks at edge k)
+            unsigned todo;
+            {
+                bool ov = false;
+                if (lane < cnt) {
+                    const ColEdge& E = ce[lane];
+                    ov = E.x0 < bx0 + bnx && bx0 < E.x0 + E.nx && E.y0 < by0 + bny && by0 < E.y0 + E.ny;
+                }
+                todo = __ballot_sync(0xffffffffu, ov);
+            }
+            while (todo) {
+                const int k = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const ColEdge& E = ce[k];
+                const float f0 = E.f[0], f1 = E.f[1];
+                bool hit = (unsigned)(cx - E.x0) < (unsigned)E.nx && (unsigned)(cy - E.y0) < (unsigned)E.ny;
+                float w0 = 0.f, w1 = 0.f, dxy = 0.f;
+                if (hit) {
+                    w0 = (fcx - E.ah[0]) - E.al[0]; w1 = (fcy - E.ah[1]) - E.al[1];
+                    dxy = fmaf(w1, f1, w0 * f0);
+                    const float t2 = __saturatef(dxy * E.inv2d);
+                    const float e0 = fmaf(-t2, f0, w0), e1 = fmaf(-t2, f1, w1);
+                    hit = !(fmaf(e1, e1, e0 * e0) > E.thr);              // else: the column misses the capsule's xy shadow
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (!m) continue;
+                // Within one edge all (column, z) cells are distinct and the columns belong to this warp: the cells of the hit
+                // columns are dealt to ALL lanes (plain loads and stores, no atomics), whatever the shape of the hit set.
+                if (hit) hitw[__popc(m & lt)] = make_float4(w0, w1, dxy, coff);
+                __syncwarp();
+                const int nzr = E.nz, total = __popc(m) * nzr, rcp = E.rcp, z0 = E.z0, eidx = E.idx;
+                const float f2 = E.f[2], finv = E.finv, reach = E.reach, eps = E.eps, thr = E.thr, ah2 = E.ah[2], al2 = E.al[2];
+                const float hi255 = 255.f + eps, om = 1.f - eps;
+#pragma unroll 2
+                for (int j = lane; j < total; j += 32) {
+                    const int h = (int)(((unsigned)j * (unsigned)rcp) >> 20);
+                    const int z = z0 + (j - h * nzr);
+                    const float4 hv = hitw[h];
+                    const float w2 = ((float)z - ah2) - al2;
+                    const float t = __saturatef(fmaf(w2, f2, hv.z) * finv);
+                    const float d0 = fmaf(-t, f0, hv.x), d1 = fmaf(-t, f1, hv.y), d2 = fmaf(-t, f2, w2);
+                    const float dd = fmaf(d2, d2, fmaf(d1, d1, d0 * d0));
+                    if (dd > thr) continue;
+                    float d;
+                    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(dd));
+                    const float v = (reach - d) * 147.22431864335458f;       // 255 * I
+                    const float fl = floorf(v), fr = v - fl;
+                    const int cell = __float_as_int(hv.w) + z;
+                    // certain: 255*I >= 255 + eps (clipped to 255), or at least eps away from every integer
+                    const bool top = v >= hi255;
+                    if (!top && (!(fr >= eps) || fr > om)) {               // within eps of an integer (or NaN): float64 decides
+                        if (!(v <= -eps)) {
+                            const int slot = atomicAdd(&s_nslow, 1);
+                            if (slot < SLOWCAP) s_slow[slot] = make_int2(eidx, cell);
+                            else { const unsigned short mark = 0xffffu; asm volatile("st.shared.u16 [%0], %1;" ::"r"(acc_s + 2u * cell), "h"(mark)); }
+                        }
+                        continue;
+                    }
+                    if (v < 1.f) continue;                                  // quantises to 0
+                    const unsigned short q = top ? (unsigned short)255 : (unsigned short)(int)fl;
+                    unsigned short old;
+                    const uint32_t ca = acc_s + 2u * cell;
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(old) : "r"(ca));
+                    if (q > old) asm volatile("st.shared.u16 [%0], %1;" ::"r"(ca), "h"(q));
+                }
+                __syncwarp();                                              // hitw is rewritten by the next edge
+            }
+        }
+    }
+    __syncthreads();
+    {   // the deferred cells of the CTA: float64 fast path / exact chain; two entries may name the same cell -> CAS max
+        const int ns = imin(s_nslow, SLOWCAP);
+        for (int i = threadIdx.x; i < ns; i += VOX_THREADS) {
+            const int2 ent = s_slow[i];
+            const int cx = ent.y / xstride, r = ent.y - cx * xstride, cy = r / ystride, z = r - cy * ystride;
+            const uint32_t v = slow_voxel_q(ge + ent.x, t0x + cx, t0y + cy, t0z + z);
+            if (v) tile_max(acc + ent.y, v);
+        }
+        if (s_nslow > SLOWCAP) {                      // (never seen) marked cells: recomputed from every edge of the tile
+            __syncthreads();
+            resolve_marked(ge, lst + beg, nlist, bl, nbig, acc, tile_elems, t0x, t0y, t0z, xstride, ystride);
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // (the bulk stores below read the accumulators)
+    __syncthreads();
+
+    const int t1x = imin(t0x + g.T[0], g.D[0]);
+    const int ny = imin(t0y + g.T[1], g.D[1]) - t0y, nz = imin(t0z + g.T[2], g.D[2]) - t0z;
+    const bool plane_contig = (nz == g.D[2] && g.T[2] == g.D[2]);
+    const int plane_len = ny * nz;
+    const size_t base0 = ((size_t)t0x * g.D[1] + t0y) * g.D[2];
+    const size_t xpitch = (size_t)g.D[1] * g.D[2];
+    if (plane_contig && (((base0 | xpitch | (size_t)plane_len | (size_t)xstride) & 7) == 0)) {
+        if (threadIdx.x == 0) {
+            const uint32_t bytes = (uint32_t)plane_len * 2u;
+            for (int x = 0; x < t1x - t0x; ++x) {
+                const uint32_t src = (uint32_t)__cvta_generic_to_shared(acc + (size_t)x * xstride);
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             ::"l"(vol + base0 + (size_t)x * xpitch), "r"(src), "r"(bytes) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        return;
+    }
+    for (int x = t0x; x < t1x; ++x) {
+        const unsigned short* slab = acc + (size_t)(x - t0x) * xstride;
+        if (plane_contig) {
+            const size_t base = ((size_t)x * g.D[1] + t0y) * g.D[2];
+            for (int i = threadIdx.x; i < plane_len; i += blockDim.x) vol[base + i] = slab[i];
+        } else {
+            for (int i = threadIdx.x; i < plane_len; i += blockDim.x) {
+                const int y = i / nz, z = i - y * nz;
+                vol[((size_t)x * g.D[1] + t0y + y) * g.D[2] + t0z + z] = slab[y * g.T[2] + z];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 int make_geom(const int dims[3], const OctaVoxOpts* opts, VoxGeom* g) {
@@ -620,11 +953,19 @@ extern "C" int octa_voxelize_batch_dev(const double* edges7_dev, const int64_t* 
     static size_t smem_set = 0;
     if (smem > smem_set) {
         OCTA_CUDA_CHECK(cudaFuncSetAttribute(vox_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OCTA_CUDA_CHECK(cudaFuncSetAttribute(vox_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OCTA_CUDA_CHECK(cudaFuncSetAttribute(vox_col_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));   // six tiles per SM
         smem_set = smem;
     }
+    // OCTA_VOX_KERNEL=rows selects the row-dealing kernel of round 1 (kept for A/B measurements; bit-identical results)
+    static const bool use_rows = [] { const char* e = getenv("OCTA_VOX_KERNEL"); return e && e[0] == 'r'; }();
     dim3 grid((unsigned)(g.nt[1] * g.nt[2]), (unsigned)g.nt[0], (unsigned)n_graphs);
-    vox_tile_kernel<<<grid, VOX_THREADS, smem, stream>>>(w.prep, w.edge_offsets, g, w.tile_start, w.tile_edges,
-                                                         w.big_count, w.big_idx, out_dev);
+    if (use_rows)
+        vox_tile_kernel<<<grid, VOX_THREADS, smem, stream>>>(w.prep, w.edge_offsets, g, w.tile_start, w.tile_edges,
+                                                             w.big_count, w.big_idx, out_dev);
+    else
+        vox_col_kernel<<<grid, VOX_THREADS, smem, stream>>>(w.prep, w.edge_offsets, g, w.tile_start, w.tile_edges,
+                                                            w.big_count, w.big_idx, out_dev);
     octa::count_launch();
     OCTA_CUDA_CHECK(cudaGetLastError());
     return OCTA_OK;
