@@ -278,6 +278,8 @@ def main():
     ve[1].record()
     torch.cuda.synchronize()
     vox_ms = ve[0].elapsed_time(ve[1]) / nrep
+    del out, vol, edges_dev
+    pipe.release_device_buffers()                              # 10 GB of volumes per device-resident buffer set
     NSETS_H = Pipeline.buffer_sets(args.in_flight, True)
     run_steps(max(1, (NSETS_H + NSUB - 1) // NSUB), True)      # (pinned result buffers of every set)
     ms_e2e, last = timed(lambda k: run_steps(k, True), max(2, args.steps))

@@ -1,4 +1,8 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_voxelize_gpu.py -m gpu -x -q 2>&1 | tail -5
-timeout 300 python tools/post_only.py 5 vox 2>&1 | tail -1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:vox_col_kernel -s 1 -c 1 -f -o gpurun_out/r02_vox_col_v3 python tools/post_only.py 1 vox > gpurun_out/ncu_vox.log 2>&1; tail -2 gpurun_out/ncu_vox.log
+nproc
+timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r02_b.json 2> gpurun_out/bench_r02_b.err; python -c "
+import json
+d=json.loads(open('gpurun_out/bench_r02_b.json').read().strip().splitlines()[-1])
+print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e']['value'], d['roofline']['frac'], d['roofline']['ms_per_launch'], d['cpu_baseline']['value'], d['config5_gan']['images_per_sec'])
+"; tail -3 gpurun_out/bench_r02_b.err
+timeout 300 python tools/post_only.py 5 all 2>&1 | tail -3

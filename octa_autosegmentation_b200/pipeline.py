@@ -53,6 +53,14 @@ class Pipeline:
             self._buf[key] = t
         return t[:n].view(*shape)
 
+    def release_device_buffers(self):
+        """Drop every device tensor of the buffer sets (device-resident results handed out earlier become invalid) and give
+        the memory back to the driver: a batch of 64 volumes [1216,1216,53] u16 is 10 GB per set."""
+        for k in [k for k, t in self._buf.items() if t.is_cuda]:
+            del self._buf[k]
+        self._h2d_done.clear()
+        self.torch.cuda.empty_cache()
+
     @property
     def _grow(self):
         return self._grows.get(0)
@@ -197,7 +205,7 @@ class Pipeline:
         one B200, 8 loops in flight: 322 graphs/s with 2 spare sets, 405 with 6 (OCTA_EXTRA_SLOTS overrides).  Each set is
         allocated on first use: warm up with at least this many batches."""
         extra = extra_slots if extra_slots is not None else os.environ.get("OCTA_EXTRA_SLOTS")
-        return max(1, int(in_flight)) + 1 + (max(0, int(extra)) if extra is not None else (12 if d2h else 3))
+        return max(1, int(in_flight)) + 1 + (max(0, int(extra)) if extra is not None else (12 if d2h else 1))
 
     def run_pipelined(self, seed_batches, d2h: bool = True, csv: bool = True, in_flight: int = 2, d2h_volume: bool = False,
                       extra_slots=None):

@@ -72,4 +72,4 @@ def test_gan_host_helpers():
                                                                    "min_radius": [0.002]}]}}
     assert gan_cli._resolution(cfg) == (608, 304, 0.002)
     assert gan_cli._resolution({"Test": {}}) == (304, 304, 0.0)
-    assert Pipeline.buffer_sets(8) == 12 and Pipeline.buffer_sets(0) == 5 and Pipeline.buffer_sets(8, True) == 21
+    assert Pipeline.buffer_sets(8) == 10 and Pipeline.buffer_sets(0) == 3 and Pipeline.buffer_sets(8, True) == 21
