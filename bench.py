@@ -156,6 +156,21 @@ def run_reference(args):
     }))
 
 
+def pin_rank_to_cores():
+    """One process per GPU: rank r of W keeps to its own slice of the host cores (launch-issuing grower threads, the libm radius
+    replay and the CSV pool of 8 ranks otherwise migrate over all cores of the box).  OCTA_NO_PIN=1 disables."""
+    world, local = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))), int(os.environ.get("LOCAL_RANK", "0"))
+    if world <= 1 or os.environ.get("OCTA_NO_PIN") == "1" or not hasattr(os, "sched_setaffinity"):
+        return
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = len(cores) // world
+        if per >= 2:
+            os.sched_setaffinity(0, cores[local * per:(local + 1) * per])
+    except OSError:
+        pass
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -170,9 +185,16 @@ def main():
     ap.add_argument("--in-flight", type=int, default=7, help="growth loops (sub-batches) in flight per GPU in the pipelined API")
     ap.add_argument("--sub-batch", type=int, default=64, help="samples per growth loop; a step's --batch samples are fed to the "
                                                               "pipelined API as batch / sub-batch consecutive batches")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                    help="BASELINE.json config: 2 = the headline line (default), 3 / 4 / 5 = bench_configs.py")
+    ap.add_argument("--samples", type=int, default=0, help="--config 3: samples of the regeneration job (default 500)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    pin_rank_to_cores()
+    if args.config != 2:
+        import bench_configs
+        return {3: bench_configs.run_config3, 4: bench_configs.run_config4, 5: bench_configs.run_config5}[args.config](args)
 
     import torch
     import torch.distributed as dist

@@ -18,7 +18,7 @@ from typing import Optional, Sequence
 
 import numpy as np
 
-from . import _lib
+from . import _lib, graph_io
 
 STEM, DOWN, UP, HEAD = "model.1", ("model.4", "model.8"), ("model.22", "model.26"), "model.30"
 BLOCKS = tuple("model.%d" % i for i in range(12, 21))
@@ -235,4 +235,4 @@ def save_images(out_dir: str, names: Sequence[str], images_u8: np.ndarray, prefi
     os.makedirs(out_dir, exist_ok=True)
     for name, img in zip(names, images_u8):
         stem = ".".join(os.path.basename(name).split(".")[:-1]) or os.path.basename(name)
-        Image.fromarray(np.asarray(img, dtype=np.uint8)).save(os.path.join(out_dir, prefix + stem + ".png"))
+        graph_io.save_png(os.path.join(out_dir, prefix + stem + ".png"), np.asarray(img, dtype=np.uint8))

@@ -67,7 +67,7 @@ def write_sample(config: dict, csv_bytes, image, volume) -> str:
                 raise RuntimeError("save_3D_volumes: nifti needs nibabel, which is not installed; use 'npy'") from e
             nib.save(nib.Nifti1Image(vol, np.eye(4)), f"{out_dir}/art_ven_img_gray.nii.gz")
     if image is not None:
-        Image.fromarray(image.astype(np.uint8)).save(f"{out_dir}/art_ven_img_gray.png")
+        graph_io.save_png(f"{out_dir}/art_ven_img_gray.png", image.astype(np.uint8))
     return out_dir
 
 

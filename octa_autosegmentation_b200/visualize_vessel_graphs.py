@@ -58,9 +58,9 @@ def _write_outputs(args, name, vol, black_dict, img):
     if img is not None:
         if args.binarize:
             img[img < 0.1] = 0
-            Image.fromarray(img.astype(np.uint8)).convert("1").save(os.path.join(args.out_dir, name + "_label.png"))
+            graph_io.save_png(os.path.join(args.out_dir, name + "_label.png"), np.array(Image.fromarray(img.astype(np.uint8)).convert("1")))
         else:
-            Image.fromarray(img.astype(np.uint8)).save(os.path.join(args.out_dir, name + ".png"))
+            graph_io.save_png(os.path.join(args.out_dir, name + ".png"), img.astype(np.uint8))
         if args.max_dropout_prob > 0 and vol is not None:
             with open(os.path.join(args.out_dir, name + "_blackdict.pkl"), "wb") as f:
                 pickle.dump(black_dict, f)
