@@ -63,9 +63,9 @@ struct GrowDev {
     // sinks: [0] oxygen sinks, [1] CO2 sources
     double *sx[2], *sy[2], *sz[2];
     int *n_s[2];
-    // bucket grids: [0] arterial nodes (+radius), [1] O2 sinks, [2]/[3] active arterial / venous nodes
-    double *gx[4], *gy[4], *gz[4], *gr[4];
-    int *gi[4], *gcell[4];
+    // bucket grids: [0] arterial nodes (+radius), [1] O2 sinks, [2]/[3] active arterial / venous nodes, [4] all venous nodes
+    double *gx[5], *gy[5], *gz[5], *gr[5];
+    int *gi[5], *gcell[5];
     // RNG streams
     MTState *np_mt, *py_mt;
     unsigned int* py_buf;
@@ -95,7 +95,7 @@ struct GrowDev {
     int *kd_idx, *kd_posL, *kd_posR, *kd_rank, *kd_nodes;
     // on-demand exact ball order: per graph "k_kill left the arterial kill to k_kill_fix" + its T; per iteration parity the list
     // of those graphs and its length
-    int *kd_flag, *kill_T, *kd_list, *kd_nflag;
+    int *kd_flag, *kill_T, *kill_H, *kd_list, *kd_nflag;   // kill_H: hits of the arterial kill (sorted list in `hl`), -1 = not available
     unsigned char* veto;
     long long* seqhash;
     long long* set_hash;

@@ -265,7 +265,7 @@ void carve(Carver& c, const GrowShape& S, GrowDev* D) {
         D->n_s[f] = c.take<int>(G);
     }
     const size_t GG = (size_t)S.G * (S.capN > S.capS ? S.capN : S.capS);
-    for (int w = 0; w < 4; ++w) {
+    for (int w = 0; w < 5; ++w) {
         D->gx[w] = c.take<double>(GG); D->gy[w] = c.take<double>(GG); D->gz[w] = c.take<double>(GG); D->gr[w] = c.take<double>(GG);
         D->gi[w] = c.take<int>(GG); D->gcell[w] = c.take<int>(G * (GRID * GRID + 1));
     }
@@ -288,7 +288,7 @@ void carve(Carver& c, const GrowShape& S, GrowDev* D) {
     D->veto = c.take<unsigned char>(GS);
     D->kd_idx = c.take<int>(GS); D->kd_posL = c.take<int>(GS); D->kd_posR = c.take<int>(GS); D->kd_rank = c.take<int>(GS);
     D->kd_nodes = c.take<int>(GS);
-    D->kd_flag = c.take<int>(G); D->kill_T = c.take<int>(G); D->kd_list = c.take<int>(2 * G); D->kd_nflag = c.take<int>(2);
+    D->kd_flag = c.take<int>(G); D->kill_T = c.take<int>(G); D->kill_H = c.take<int>(G); D->kd_list = c.take<int>(2 * G); D->kd_nflag = c.take<int>(2);
     D->seqhash = c.take<long long>(GS);
     D->set_hash = c.take<long long>(G * 2 * SET_TBL); D->set_key = c.take<int>(G * 2 * SET_TBL);
     D->err = c.take<int>(G); D->trace = c.take<int>(G * 4096 * 4); D->counters = c.take<long long>(G * 8); D->dbg = c.take<long long>(G * 8);

@@ -214,7 +214,7 @@ __device__ __forceinline__ int grid_cell(double v) {
     return c < 0 ? 0 : (c >= GRID ? GRID - 1 : c);
 }
 
-// which: 0 = all arterial nodes (+radius), 1 = O2 sinks, 2 / 3 = active arterial / venous nodes
+// which: 0 = all arterial nodes (+radius), 1 = O2 sinks, 2 / 3 = active arterial / venous nodes, 4 = all venous nodes (k_kill's veto)
 __device__ __forceinline__ void grid_build_body(const GrowDev& D, const GrowShape& S, const IterP& P, int which, int g) {
     __shared__ int hist[GRID * GRID];
     __shared__ int cursor[GRID * GRID];
@@ -229,6 +229,7 @@ __device__ __forceinline__ void grid_build_body(const GrowDev& D, const GrowShap
     size_t cap;
     if (which == 0) { cap = S.capN; px = D.nx[0] + g * cap; py = D.ny[0] + g * cap; pz = D.nz[0] + g * cap; pr = D.ncon[0] + g * cap; n = D.n_nodes[0][g]; }
     else if (which == 1) { cap = S.capS; px = D.sx[0] + g * cap; py = D.sy[0] + g * cap; pz = D.sz[0] + g * cap; n = D.n_s[0][g]; }
+    else if (which == 4) { cap = S.capN; px = D.nx[1] + g * cap; py = D.ny[1] + g * cap; pz = D.nz[1] + g * cap; n = D.n_nodes[1][g]; }   // every venous node
     else { const int f = which - 2; cap = S.capN; px = D.nx[f] + g * cap; py = D.ny[f] + g * cap; pz = D.nz[f] + g * cap; n = D.n_nodes[f][g]; skip = D.deact[f] + g * cap; }
     const size_t gcap = S.capN > S.capS ? S.capN : S.capS;
     double* gx = D.gx[which] + g * gcap; double* gy = D.gy[which] + g * gcap; double* gz = D.gz[which] + g * gcap;
@@ -255,7 +256,7 @@ __device__ __forceinline__ void grid_build_body(const GrowDev& D, const GrowShap
         cursor[c] = run + incl - v;
         run += total;
     }
-    if (tid == 0) { cs[GRID * GRID] = run; if (which >= 2) D.n_act[which - 2][g] = run; }
+    if (tid == 0) { cs[GRID * GRID] = run; if (which == 2 || which == 3) D.n_act[which - 2][g] = run; }
     __syncthreads();
     for (int i = tid; i < n; i += blockDim.x) {
         if (skip && skip[i]) continue;
@@ -277,7 +278,8 @@ __device__ __forceinline__ void grid_build_body(const GrowDev& D, const GrowShap
     }
 }
 
-__global__ void __launch_bounds__(1024) k_grid_build(int dslot, GrowShape S, IterP P, int which) { grid_build_body(c_dev[dslot], S, P, which, blockIdx.x); }
+// grid.y = 2 with which = 3: the grids of the active venous nodes (blockIdx.y = 0) and of all venous nodes (blockIdx.y = 1) side by side
+__global__ void __launch_bounds__(1024) k_grid_build(int dslot, GrowShape S, IterP P, int which) { grid_build_body(c_dev[dslot], S, P, which + (int)blockIdx.y, blockIdx.x); }
 
 // k_prepare: everything the sampling of an iteration needs, in ONE launch: blockIdx.y = 0..2 -> the bucket grids of
 // the arterial nodes (+radius), the O2 sinks and the active arterial nodes, blockIdx.y = 3 -> the candidate sampler.
@@ -1143,12 +1145,45 @@ __global__ void __launch_bounds__(256, 4) k_commit_r64(int dslot, GrowShape S, I
 // k_kill: one CTA per graph.  f = 0: satisfied O2 sinks -> CO2 sources (set order); f = 1: CO2 removal
 // ------------------------------------------------------------------------------------------
 // Stable removal of every hit from the sink list f (element_mesh.py:195-211) + per-iteration trace
-__device__ void kill_compact(const GrowDev& D, const GrowShape& S, const IterP& P, int f, int g, int Sn, bool removed) {
+// H >= 0: the removed positions are hl[0..H) in ascending order (H <= KILL_RCAP; staged in `rs`, shared memory): the new place of
+// an element is its position minus the number of removed positions before it (binary search), ONE barrier per 4 * blockDim
+// elements instead of a block scan (three barriers) per blockDim elements, and nothing before the first removed position moves.
+// H < 0: positions with hitj >= 0 are removed, found with block scans (fallback).
+constexpr int KILL_RCAP = 4096;
+__device__ void kill_compact(const GrowDev& D, const GrowShape& S, const IterP& P, int f, int g, int Sn, bool removed, int H = -1,
+                             const int* hl = nullptr, int* rs = nullptr) {
     const int tid = threadIdx.x;
     const size_t sb = (size_t)g * S.capS;
     double* sx = D.sx[f] + sb; double* sy = D.sy[f] + sb; double* sz = D.sz[f] + sb;
     const int* hitj = D.hitj + sb;
-    if (removed) {
+    if (removed && H >= 0) {
+        __syncthreads();
+        for (int k = tid; k < H; k += blockDim.x) rs[k] = hl[k];
+        __syncthreads();
+        if (H > 0) {
+            const int first = rs[0];
+            const int CH = 4 * blockDim.x;
+            for (int base = first; base < Sn; base += CH) {
+                double px[4], py[4], pz[4];
+                int dst[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int i = base + q * blockDim.x + tid;
+                    dst[q] = -1;
+                    if (i < Sn) {
+                        int lo = 0, hi = H;                     // removed positions < i
+                        while (lo < hi) { const int mid = (lo + hi) >> 1; if (rs[mid] < i) lo = mid + 1; else hi = mid; }
+                        if (!(lo < H && rs[lo] == i)) { dst[q] = i - lo; px[q] = sx[i]; py[q] = sy[i]; pz[q] = sz[i]; }
+                    }
+                }
+                __syncthreads();                                // every read of this chunk precedes its writes
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (dst[q] >= 0) { sx[dst[q]] = px[q]; sy[dst[q]] = py[q]; sz[dst[q]] = pz[q]; }
+            }
+            if (tid == 0) D.n_s[f][g] = Sn - H;
+        }
+    } else if (removed) {
         int w = 0;
         for (int base = 0; base < Sn; base += blockDim.x) {
             const int i = base + tid;
@@ -1266,7 +1301,58 @@ __global__ void __launch_bounds__(1024) k_kill(int dslot, GrowShape S, IterP P, 
     double* sx = D.sx[f] + sb; double* sy = D.sy[f] + sb; double* sz = D.sz[f] + sb;
     int* hitj = D.hitj + sb;
     const double epsk2 = P.eps_k * P.eps_k;
+    const size_t gcap = S.capN > S.capS ? S.capN : S.capS;
+    // positions hit by this call, in arrival order (the hash-table space is idle until kill_convert), then ranked into `hl`
+    __shared__ int s_nh;
+    int* s_hl = reinterpret_cast<int*>(ks.th);
+    static_assert(sizeof(ks.th) >= sizeof(int) * KILL_RCAP, "hit list space");
+    int* hl = D.hl + sb;
+    int H = -1;                      // hits in `hl` (sorted), -1: too many for the list, the scans decide
+    int Hc = -1;                     // what kill_compact gets: H if `hl` lists every removed position, else -1
+    if (tid == 0) s_nh = 0;
+    __syncthreads();
     if (nn > 0) {
+      if (f == 0) {
+        // Ball test through the bucket grid of the O2 sinks (built by k_prepare of this iteration BEFORE the sampler appended its
+        // accepted sinks: the list has only grown since, so the grid's indices are still list positions); the sinks appended
+        // after the build are scanned directly.  hitj = FIRST new node that hits a sink = atomicMin over the hitting nodes --
+        // the same value the sink-major scan below finds, with the same float64 distance expression.
+        for (int i = tid; i < Sn; i += blockDim.x) hitj[i] = -1;
+        __syncthreads();
+        const double* gx = D.gx[1] + g * gcap; const double* gy = D.gy[1] + g * gcap; const double* gz = D.gz[1] + g * gcap;
+        const int* gi = D.gi[1] + g * gcap;
+        const int* cs = D.gcell[1] + (size_t)g * (GRID * GRID + 1);
+        const int n_grid = cs[GRID * GRID];                       // sinks the grid knows (<= Sn)
+        const double er = P.eps_k * (1.0 + 1e-9) + 1e-12;         // the cell range may only be too wide, never too narrow
+        const int rows = 2 * ((int)ceil(er * (double)GRID) + 1) + 1;
+        unsigned int* uhit = reinterpret_cast<unsigned int*>(hitj);
+        for (int item = tid; item < nn * rows; item += blockDim.x) {
+            const int j = item / rows, r = item - j * rows;
+            const double qx = D.nx[0][nb + n0 + j], qy = D.ny[0][nb + n0 + j], qz = D.nz[0][nb + n0 + j];
+            const int y0 = grid_cell(qy - er), y1 = grid_cell(qy + er);
+            const int cy = y0 + r;
+            if (cy > y1) continue;
+            const int beg = cs[cy * GRID + grid_cell(qx - er)], end = cs[cy * GRID + grid_cell(qx + er) + 1];
+            for (int q = beg; q < end; ++q)
+                if (dist2(gx[q], gy[q], gz[q], qx, qy, qz) <= epsk2) {                                      // cKDTree ball: d^2 <= r^2
+                    const int idx = gi[q];
+                    if (atomicMin(&uhit[idx], (unsigned int)j) == 0xffffffffu) {                             // first hit of this sink
+                        const int slot = atomicAdd(&s_nh, 1);
+                        if (slot < KILL_RCAP) s_hl[slot] = idx;
+                    }
+                }
+        }
+        for (int i = n_grid + tid; i < Sn; i += blockDim.x) {     // appended after the grid was built
+            const double px = sx[i], py = sy[i], pz = sz[i];
+            for (int j = 0; j < nn; ++j)
+                if (dist2(px, py, pz, D.nx[0][nb + n0 + j], D.ny[0][nb + n0 + j], D.nz[0][nb + n0 + j]) <= epsk2) {
+                    hitj[i] = j;
+                    const int slot = atomicAdd(&s_nh, 1);
+                    if (slot < KILL_RCAP) s_hl[slot] = i;
+                    break;
+                }
+        }
+      } else {
         for (int i = tid; i < Sn; i += blockDim.x) hitj[i] = -1;
         for (int base = 0; base < nn; base += 512) {
             const int cntn = nn - base < 512 ? nn - base : 512;
@@ -1277,36 +1363,64 @@ __global__ void __launch_bounds__(1024) k_kill(int dslot, GrowShape S, IterP P, 
                 if (hitj[i] >= 0) continue;
                 const double px = sx[i], py = sy[i], pz = sz[i];
                 for (int j = 0; j < cntn; ++j)
-                    if (dist2(px, py, pz, ks.nxs[j], ks.nys[j], ks.nzs[j]) <= epsk2) { hitj[i] = base + j; break; }   // cKDTree ball: d^2 <= r^2
+                    if (dist2(px, py, pz, ks.nxs[j], ks.nys[j], ks.nzs[j]) <= epsk2) {   // cKDTree ball: d^2 <= r^2
+                        hitj[i] = base + j;
+                        const int slot = atomicAdd(&s_nh, 1);
+                        if (slot < KILL_RCAP) s_hl[slot] = i;
+                        break;
+                    }
+            }
+        }
+      }
+        __syncthreads();
+        if (s_nh <= KILL_RCAP) {     // hits in list order: rank of each position among the hit positions (tens of hits)
+            H = s_nh;
+            for (int k = tid; k < H; k += blockDim.x) {
+                const int v = s_hl[k];
+                int r = 0;
+                for (int m = 0; m < H; ++m) r += s_hl[m] < v;
+                hl[r] = v;
             }
         }
         __syncthreads();
         if (f == 0) {
-            // hits in list order
-            int* hl = D.hl + sb;
-            int H = 0;
-            for (int base = 0; base < Sn; base += blockDim.x) {
-                const int i = base + tid;
-                const int fl = (i < Sn) ? (hitj[i] >= 0) : 0;
-                int total;
-                const int incl = block_scan_incl(fl, &total);
-                if (fl) hl[H + incl - 1] = i;
-                H += total;
+            if (H < 0) {             // hits in list order by block scans
+                H = 0;
+                for (int base = 0; base < Sn; base += blockDim.x) {
+                    const int i = base + tid;
+                    const int fl = (i < Sn) ? (hitj[i] >= 0) : 0;
+                    int total;
+                    const int incl = block_scan_incl(fl, &total);
+                    if (fl) hl[H + incl - 1] = i;
+                    H += total;
+                }
+                __syncthreads();
+                if (H > KILL_RCAP) H = -H - 1;      // (compaction by scans; the veto below uses the count)
             }
-            __syncthreads();
+            const bool listed = H >= 0;
+            if (!listed) H = -H - 1;
+            Hc = listed ? H : -1;
             // veto: a venous node within eps_k (greenhouse.py:106-109).  Thread per venous node against the hits staged in
             // shared memory (a warp per hit walking all venous nodes was one dependent L2 round trip per 32 nodes).
+            // Through the bucket grid of ALL venous nodes (k_grid_build after the venous commit): item = (hit, row of cells).
             unsigned char* veto = D.veto + sb;
-            const int Vn = D.n_nodes[1][g];
-            for (int hb = 0; hb < H; hb += 512) {
-                const int cnth = H - hb < 512 ? H - hb : 512;
+            {
+                const double* vgx = D.gx[4] + g * gcap; const double* vgy = D.gy[4] + g * gcap; const double* vgz = D.gz[4] + g * gcap;
+                const int* vcs = D.gcell[4] + (size_t)g * (GRID * GRID + 1);
+                const double er = P.eps_k * (1.0 + 1e-9) + 1e-12;
+                const int rows = 2 * ((int)ceil(er * (double)GRID) + 1) + 1;
+                for (int k = tid; k < H; k += blockDim.x) veto[k] = 0;
                 __syncthreads();
-                for (int k = tid; k < cnth; k += blockDim.x) { const int i = hl[hb + k]; ks.nxs[k] = sx[i]; ks.nys[k] = sy[i]; ks.nzs[k] = sz[i]; veto[hb + k] = 0; }
-                __syncthreads();
-                for (int j = tid; j < Vn; j += blockDim.x) {
-                    const double vx = D.nx[1][nb + j], vy = D.ny[1][nb + j], vz = D.nz[1][nb + j];
-                    for (int k = 0; k < cnth; ++k)
-                        if (within_sqrt(dist2(vx, vy, vz, ks.nxs[k], ks.nys[k], ks.nzs[k]), P.eps_k, epsk2)) veto[hb + k] = 1;
+                for (int item = tid; item < H * rows; item += blockDim.x) {
+                    const int k = item / rows, r = item - k * rows;
+                    const int i = hl[k];
+                    const double px = sx[i], py = sy[i], pz = sz[i];
+                    const int y0 = grid_cell(py - er), y1 = grid_cell(py + er);
+                    const int cy = y0 + r;
+                    if (cy > y1) continue;
+                    const int beg = vcs[cy * GRID + grid_cell(px - er)], end = vcs[cy * GRID + grid_cell(px + er) + 1];
+                    for (int q = beg; q < end; ++q)
+                        if (within_sqrt(dist2(vgx[q], vgy[q], vgz[q], px, py, pz), P.eps_k, epsk2)) { veto[k] = 1; break; }
                 }
             }
             __syncthreads();
@@ -1326,6 +1440,7 @@ __global__ void __launch_bounds__(1024) k_kill(int dslot, GrowShape S, IterP P, 
                 if (kill_convert<true>(D, S, g, T, nullptr, &ks)) {
                     if (tid == 0) {          // finished by k_kdbuild + k_kill_fix
                         D.kill_T[g] = T;
+                        D.kill_H[g] = listed ? H : -1;
                         D.kd_flag[g] = 1;
                         D.kd_list[(P.iter & 1) * S.G + atomicAdd(&D.kd_nflag[P.iter & 1], 1)] = g;
                         if (D.dbg) D.dbg[g * 8 + 0] += 1;     // (diagnostics: graph-iterations that needed the exact order)
@@ -1337,7 +1452,7 @@ __global__ void __launch_bounds__(1024) k_kill(int dslot, GrowShape S, IterP P, 
             }
         }
     }
-    kill_compact(D, S, P, f, g, Sn, nn > 0);
+    kill_compact(D, S, P, f, g, Sn, nn > 0, f == 0 ? Hc : H, hl, s_hl);
 }
 
 // finish the arterial kill of the graphs k_kill put on the work list: same conversion with the exact order inside every ball
@@ -1351,7 +1466,7 @@ __global__ void __launch_bounds__(1024) k_kill_fix(int dslot, GrowShape S, IterP
     if (threadIdx.x == 0) D.kd_flag[g] = 0;
     const size_t sb = (size_t)g * S.capS;
     kill_convert<false>(D, S, g, D.kill_T[g], D.kd_rank + sb, &ks);
-    kill_compact(D, S, P, 0, g, D.n_s[0][g], true);
+    kill_compact(D, S, P, 0, g, D.n_s[0][g], true, D.kill_H[g], D.hl + sb, reinterpret_cast<int*>(ks.th));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1512,7 +1627,7 @@ void launch_sampling(int dslot, const GrowShape& S, const IterP& P, int n_sm, cu
 
 void launch_begin(int dslot, const GrowShape& S, const IterP& P0, int n_sm, cudaStream_t st, cudaStream_t side, const GrowEvents& ev) {
     // uploads of the initial state were issued on `st`
-    k_grid_build<<<S.G, 1024, 0, st>>>(dslot, S, P0, 3);
+    k_grid_build<<<dim3(S.G, 2), 1024, 0, st>>>(dslot, S, P0, 3);
     count_launch(1);
     cudaEventRecord(ev.start, st);
     cudaStreamWaitEvent(side, ev.start, 0);
@@ -1539,7 +1654,7 @@ void launch_iteration(int dslot, const GrowShape& S, const int commit_smem[2], c
         else k_commit<<<S.G, commit_threads, (size_t)commit_smem[f], st>>>(dslot, Sc, P, f);
         tick(st, 7 + 5 * f);
         if (f == 0) cudaStreamWaitEvent(st, ev.kd, 0);
-        else { k_grid_build<<<S.G, 1024, 0, st>>>(dslot, S, P, 3); count_launch(1); }
+        else { k_grid_build<<<dim3(S.G, 2), 1024, 0, st>>>(dslot, S, P, 3); count_launch(1); }
         // 512 threads x 63 registers: two k_kill CTAs (or k_kill + another loop's kernel) share an SM; the pipeline is bound by SM
         // slots held by one-CTA-per-graph kernels, not by their parallel phases (measured: 444 -> 453 graphs/s vs 1024 threads)
         static const int kill_threads = [] { const char* e = getenv("OCTA_KILL_THREADS"); const int v = e ? atoi(e) : 0; return (v == 256 || v == 512 || v == 1024) ? v : 512; }();

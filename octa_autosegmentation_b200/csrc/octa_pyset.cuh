@@ -177,36 +177,51 @@ constexpr int MS_MAXT = 306;            // the 307th key grows the table to 2048
 constexpr int MS_ALT = 6;
 constexpr int MS_TABLES = 2 * MS_ALT + 2;
 
-OCTA_PS_HD inline void ms_insert(short* tab, size_t mask, int pos, long long hash, const int* bl, int ball, bool* same_ball) {
-    size_t perturb = (size_t)hash, i = (size_t)hash & mask;
+OCTA_PS_HD inline int ms_insert(short* tab, unsigned mask, int pos, long long hash, const int* bl, int ball, bool* same_ball) {
+    unsigned long long perturb = (unsigned long long)hash;
+    unsigned i = (unsigned)perturb & mask;
     while (true) {
-        size_t e = i;
+        unsigned e = i;
         int probes = (i + 9 <= mask) ? 9 : 0;
         do {
             const int k = tab[e];
-            if (k < 0) { tab[e] = (short)pos; return; }
+            if (k < 0) { tab[e] = (short)pos; return (int)e; }
             if (bl && bl[k] == ball) *same_ball = true;
             ++e;
         } while (probes--);
         perturb >>= 5;
-        i = (i * 5 + 1 + perturb) & mask;
+        i = (i * 5u + 1u + (unsigned)perturb) & mask;       // (only the bits under the mask matter)
     }
 }
 
+// tables are 4-byte aligned and hold an even number of cells: copies and comparisons go word by word
+OCTA_PS_HD inline void ms_copy(short* dst, const short* src, unsigned n) {
+    unsigned* d = reinterpret_cast<unsigned*>(dst);
+    const unsigned* c = reinterpret_cast<const unsigned*>(src);
+    for (unsigned z = 0; z < n / 2; ++z) d[z] = c[z];
+}
+OCTA_PS_HD inline bool ms_equal(const short* a, const short* b, unsigned n) {
+    const unsigned* x = reinterpret_cast<const unsigned*>(a);
+    const unsigned* y = reinterpret_cast<const unsigned*>(b);
+    for (unsigned z = 0; z < n / 2; ++z) if (x[z] != y[z]) return false;
+    return true;
+}
+
 // positions q + perm[0..m) into `tab` (set_add_entry + set_table_resize; `tmp` receives a grown table first)
-OCTA_PS_HD inline void ms_apply(short* tab, short* tmp, size_t* mask, size_t* fill, const long long* hs, const int* bl, int q,
+OCTA_PS_HD inline void ms_apply(short* tab, short* tmp, unsigned* mask, unsigned* fill, const long long* hs, const int* bl, int q,
                                 const int* perm, int m, bool track, bool* inter, bool* grew_inside, bool* grew) {
     for (int k = 0; k < m; ++k) {
         const int pos = q + (perm ? perm[k] : k);          // perm == nullptr: index order
         ms_insert(tab, *mask, pos, hs[pos], track ? bl : nullptr, bl[q], inter);
         ++*fill;
         if (*fill * 5 >= *mask * 3) {
-            size_t newsize = 8;
+            unsigned newsize = 8;
             while (newsize <= *fill * 4) newsize <<= 1;
-            for (size_t z = 0; z < newsize; ++z) tmp[z] = -1;
-            for (size_t z = 0; z <= *mask; ++z)
+            unsigned* t32 = reinterpret_cast<unsigned*>(tmp);
+            for (unsigned z = 0; z < newsize / 2; ++z) t32[z] = 0xffffffffu;
+            for (unsigned z = 0; z <= *mask; ++z)
                 if (tab[z] >= 0) ms_insert(tmp, newsize - 1, tab[z], hs[tab[z]], nullptr, 0, nullptr);
-            for (size_t z = 0; z < newsize; ++z) tab[z] = tmp[z];
+            ms_copy(tab, tmp, newsize);
             *mask = newsize - 1;
             *grew = true;
             if (k < m - 1) *grew_inside = true;
@@ -214,20 +229,17 @@ OCTA_PS_HD inline void ms_apply(short* tab, short* tmp, size_t* mask, size_t* fi
     }
 }
 
-OCTA_PS_HD inline bool ms_equal(const short* a, const short* b, size_t n) {
-    for (size_t z = 0; z < n; ++z) if (a[z] != b[z]) return false;
-    return true;
-}
-
 // hs / bl: hash and ball id per sequence position (T <= MS_MAXT), tabs: MS_TABLES tables of MS_TBL shorts.  Returns 0 and the
 // final table in tabs[0 .. *mask_out] (positions, -1 = empty) when the result does not depend on the order inside any ball,
 // else a reason code > 0 (1: ball of > 4 keys, 2: too many alive tables, 3: alive tables differ with no growth left).
+// The usual ball (no growth inside it, no key examining a slot of a key of the same ball) is inserted IN PLACE into every alive
+// table; tables are only copied where a growth falls inside a ball or the orders of a ball have to be tried.
 OCTA_PS_HD inline int pyset_run_multi(const long long* hs, const int* bl, int T, short* tabs, int* mask_out) {
     short* A = tabs;                               // alive tables
     short* B = tabs + (size_t)MS_ALT * MS_TBL;     // tables after the current ball
     short* cand = tabs + (size_t)2 * MS_ALT * MS_TBL;
     short* tmp = cand + MS_TBL;
-    size_t mask = 7, fill = 0;
+    unsigned mask = 7, fill = 0;
     int alive = 1;
     for (int z = 0; z < 8; ++z) A[z] = -1;
     int q = 0;
@@ -236,11 +248,66 @@ OCTA_PS_HD inline int pyset_run_multi(const long long* hs, const int* bl, int T,
         int q2 = q + 1;
         while (q2 < T && bl[q2] == ball) ++q2;
         const int m = q2 - q;
-        size_t mask1 = mask, fill1 = fill;
-        bool grew_any = false;
-        if (m == 1) {
+        unsigned mask1 = mask, fill1 = fill;
+        bool expand = (fill + (unsigned)m) * 5 >= mask * 3;          // a growth falls into this ball: tables are rebuilt anyway
+        if (!expand) {
+            // in place, index order, with the log of the written slots (to take the ball back if its orders have to be tried)
+            int slots[MS_ALT][4];
+            unsigned inter_mask = 0;
             for (int s = 0; s < alive; ++s) {
-                size_t mk = mask, fl = fill;
+                short* tab = A + (size_t)s * MS_TBL;
+                bool inter = false;
+                for (int k = 0; k < m; ++k) {
+                    const int e = ms_insert(tab, mask, q + k, hs[q + k], m > 1 ? bl : nullptr, ball, &inter);
+                    if (m <= 4) slots[s][k] = e;
+                }
+                if (inter) inter_mask |= 1u << s;
+            }
+            fill1 = fill + (unsigned)m;
+            if (inter_mask) {
+                if (m > 4) return 1;
+                for (int s = 0; s < alive; ++s) {                    // take the ball back where its order may matter
+                    if (!((inter_mask >> s) & 1u)) continue;
+                    short* tab = A + (size_t)s * MS_TBL;
+                    for (int k = 0; k < m; ++k) tab[slots[s][k]] = -1;
+                }
+                expand = true;
+            }
+            if (!expand) { mask = mask1; fill = fill1; q = q2; continue; }
+            // fall through to the general path: tables without `inter` already hold the ball (marked in done_mask)
+            int nb = 0;
+            auto push = [&](const short* t, unsigned n) -> bool {
+                for (int u = 0; u < nb; ++u) if (ms_equal(B + (size_t)u * MS_TBL, t, n)) return true;
+                if (nb == MS_ALT) return false;
+                ms_copy(B + (size_t)nb * MS_TBL, t, n);
+                ++nb;
+                return true;
+            };
+            for (int s = 0; s < alive; ++s) {
+                const short* src = A + (size_t)s * MS_TBL;
+                if (!((inter_mask >> s) & 1u)) { if (!push(src, mask + 1)) return 2; continue; }
+                int perm[4] = {0, 1, 2, 3};
+                while (true) {
+                    ms_copy(cand, src, mask + 1);
+                    unsigned mk = mask, fl = fill;
+                    bool i2 = false, g2 = false, g3 = false;
+                    ms_apply(cand, tmp, &mk, &fl, hs, bl, q, perm, m, false, &i2, &g2, &g3);
+                    if (!push(cand, mk + 1)) return 2;
+                    int i = m - 2;
+                    while (i >= 0 && perm[i] > perm[i + 1]) --i;
+                    if (i < 0) break;
+                    int j = m - 1;
+                    while (perm[j] < perm[i]) --j;
+                    { const int t = perm[i]; perm[i] = perm[j]; perm[j] = t; }
+                    for (int a = i + 1, b = m - 1; a < b; ++a, --b) { const int t = perm[a]; perm[a] = perm[b]; perm[b] = t; }
+                }
+            }
+            { short* t = A; A = B; B = t; }
+            alive = nb;
+        } else if (m == 1) {
+            bool grew_any = false;
+            for (int s = 0; s < alive; ++s) {
+                unsigned mk = mask, fl = fill;
                 bool gi = false, gr = false;
                 ms_apply(A + (size_t)s * MS_TBL, tmp, &mk, &fl, hs, bl, q, nullptr, 1, false, nullptr, &gi, &gr);
                 mask1 = mk; fill1 = fl; grew_any = gr;
@@ -251,7 +318,7 @@ OCTA_PS_HD inline int pyset_run_multi(const long long* hs, const int* bl, int T,
                     bool dup = false;
                     for (int u = 0; u < keep && !dup; ++u) dup = ms_equal(A + (size_t)u * MS_TBL, A + (size_t)s * MS_TBL, mask1 + 1);
                     if (!dup) {
-                        if (keep != s) for (size_t z = 0; z <= mask1; ++z) A[(size_t)keep * MS_TBL + z] = A[(size_t)s * MS_TBL + z];
+                        if (keep != s) ms_copy(A + (size_t)keep * MS_TBL, A + (size_t)s * MS_TBL, mask1 + 1);
                         ++keep;
                     }
                 }
@@ -259,10 +326,10 @@ OCTA_PS_HD inline int pyset_run_multi(const long long* hs, const int* bl, int T,
             }
         } else {
             int nb = 0;
-            auto push = [&](const short* t, size_t n) -> bool {        // false: too many alive tables
+            auto push = [&](const short* t, unsigned n) -> bool {        // false: too many alive tables
                 for (int u = 0; u < nb; ++u) if (ms_equal(B + (size_t)u * MS_TBL, t, n)) return true;
                 if (nb == MS_ALT) return false;
-                for (size_t z = 0; z < n; ++z) B[(size_t)nb * MS_TBL + z] = t[z];
+                ms_copy(B + (size_t)nb * MS_TBL, t, n);
                 ++nb;
                 return true;
             };
@@ -270,8 +337,8 @@ OCTA_PS_HD inline int pyset_run_multi(const long long* hs, const int* bl, int T,
                 const short* src = A + (size_t)s * MS_TBL;
                 // index order with tracking: no key of the ball examines a slot held by a key of the same ball and no growth
                 // before its last key -> each key lands on the first free slot of its own probe sequence, whatever the order
-                for (size_t z = 0; z <= mask; ++z) cand[z] = src[z];
-                size_t mk = mask, fl = fill;
+                ms_copy(cand, src, mask + 1);
+                unsigned mk = mask, fl = fill;
                 bool inter = false, gi = false, gr = false;
                 ms_apply(cand, tmp, &mk, &fl, hs, bl, q, nullptr, m, true, &inter, &gi, &gr);
                 mask1 = mk; fill1 = fl;
@@ -287,7 +354,7 @@ OCTA_PS_HD inline int pyset_run_multi(const long long* hs, const int* bl, int T,
                     while (perm[j] < perm[i]) --j;
                     { const int t = perm[i]; perm[i] = perm[j]; perm[j] = t; }
                     for (int a = i + 1, b = m - 1; a < b; ++a, --b) { const int t = perm[a]; perm[a] = perm[b]; perm[b] = t; }
-                    for (size_t z = 0; z <= mask; ++z) cand[z] = src[z];
+                    ms_copy(cand, src, mask + 1);
                     mk = mask; fl = fill;
                     bool i2 = false, g2 = false, g3 = false;
                     ms_apply(cand, tmp, &mk, &fl, hs, bl, q, perm, m, false, &i2, &g2, &g3);
@@ -298,11 +365,11 @@ OCTA_PS_HD inline int pyset_run_multi(const long long* hs, const int* bl, int T,
             alive = nb;
         }
         mask = mask1; fill = fill1;
-        if (alive > 1 && !((size_t)T * 5 >= mask * 3)) return 3;      // no growth left that could merge them
+        if (alive > 1 && !((unsigned)T * 5 >= mask * 3)) return 3;      // no growth left that could merge them
         q = q2;
     }
     if (alive > 1) return 3;
-    if (A != tabs) for (size_t z = 0; z <= mask; ++z) tabs[z] = A[z];
+    if (A != tabs) ms_copy(tabs, A, mask + 1);
     *mask_out = (int)mask;
     return 0;
 }

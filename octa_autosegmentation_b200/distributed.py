@@ -21,24 +21,29 @@ def gather_edge_tables(tables: dict, dst: int = 0, device=None) -> dict:
     dist.all_gather(metas, meta)
     max_ids = int(max(m[0] for m in metas))
     max_rows = int(max(m[1] for m in metas))
-    head = torch.zeros((max(max_ids, 1), 2), dtype=torch.int64, device=dev)      # (sample id, rows)
-    body = torch.zeros((max(max_rows, 1), 7), dtype=torch.float64, device=dev)
+    # one pinned staging block per rank: (sample id, rows) heads + all rows back to back, uploaded with ONE copy; rank `dst`
+    # brings every rank's block back with one copy each and slices it on the host
+    head_h = np.zeros((max(max_ids, 1), 2), dtype=np.int64)
+    body_h = np.zeros((max(max_rows, 1), 7), dtype=np.float64)
     r = 0
     for k, i in enumerate(ids):
         t = np.ascontiguousarray(tables[i], dtype=np.float64).reshape(-1, 7)
-        head[k, 0], head[k, 1] = int(i), len(t)
-        body[r:r + len(t)] = torch.from_numpy(t).to(dev)
+        head_h[k] = (int(i), len(t))
+        body_h[r:r + len(t)] = t
         r += len(t)
+    head = torch.from_numpy(head_h).to(dev)
+    body = torch.from_numpy(body_h).to(dev)
     heads = [torch.zeros_like(head) for _ in range(world)] if rank == dst else None
     bodies = [torch.zeros_like(body) for _ in range(world)] if rank == dst else None
     dist.gather(head, heads, dst=dst)
-    dist.gather(body, bodies, dst=dst)
+    dist.gather(body, bodies, dst=dst)          # the one data exchange of the job
     out = {}
     if rank == dst:
         for w in range(world):
+            hw, bw = heads[w].cpu().numpy(), bodies[w].cpu().numpy()
             r = 0
             for k in range(int(metas[w][0])):
-                sid, rows = int(heads[w][k, 0]), int(heads[w][k, 1])
-                out[sid] = bodies[w][r:r + rows].cpu().numpy()
+                sid, rows = int(hw[k, 0]), int(hw[k, 1])
+                out[sid] = bw[r:r + rows]
                 r += rows
     return out
