@@ -215,7 +215,7 @@ def main():
     SB = args.sub_batch if 0 < args.sub_batch < B and B % args.sub_batch == 0 else B
     NSUB = B // SB
     W = max(args.warmup, 3)
-    pipe = Pipeline(default_config(), device=dev, volume_dims=DIMS, host_threads=max(1, (os.cpu_count() or 2) // max(world, 1)))
+    pipe = Pipeline(default_config(), device=dev, volume_dims=DIMS, host_threads=max(1, len(os.sched_getaffinity(0)) if world > 1 else (os.cpu_count() or 2)))
     counter = [0]
 
     def seeds():

@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <chrono>
 #include <mutex>
+#include <sched.h>
 #include <thread>
 #include <vector>
 #include "octa_common.h"
@@ -411,6 +412,7 @@ struct GrowCtx {
         if (lg.exec) cudaGraphExecDestroy(lg.exec);
         release_slot(dslot);
         if (ev_done) cudaEventDestroy(ev_done);
+        for (cudaEvent_t e : thr_ev) if (e) cudaEventDestroy(e);
         if (main) cudaStreamDestroy(main);
         if (side) cudaStreamDestroy(side);
         for (cudaEvent_t e : {ev.start, ev.sinks, ev.kd, ev.killa}) if (e) cudaEventDestroy(e);
@@ -420,6 +422,8 @@ struct GrowCtx {
         if (e1) cudaEventDestroy(e1);
     }
     // wait for `st` without spinning: several growth loops (and ranks) share the host cores
+    static constexpr int THR_RING = 64;
+    cudaEvent_t thr_ev[THR_RING] = {};       // launch throttle (grow_run_impl)
     cudaEvent_t ev_done = nullptr;
     cudaError_t wait(cudaStream_t st) {
         if (!ev_done) {
@@ -646,10 +650,26 @@ static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, doub
             cs_all[2 * i + f] = (int)std::min<size_t>((size_t)S.commit_smem, std::max<size_t>(want, 8 * 1024));
             cs_raw[2 * i + f] = (int)std::min<size_t>((size_t)S.commit_smem, mirror_bytes(nb));
         }
-    auto issue_loop = [&](const std::vector<int>& cs) {
+    // Launch throttle: the host issues an iteration in ~0.1 ms but the device needs ~1-2 ms for it, so an unthrottled thread runs
+    // up to the depth of the launch queue ahead and then SPINS inside cudaLaunchKernel (measured: 70 us per launch call, 290 ms of a
+    // core per loop, from every grower thread of every rank).  Every THROTTLE_STEP iterations an event is recorded; before going
+    // on, the thread SLEEPS (blocking-sync event) until the device is within THROTTLE_AHEAD iterations.  OCTA_GROW_THROTTLE=0: off.
+    static const int throttle = [] { const char* e = getenv("OCTA_GROW_THROTTLE"); return e ? atoi(e) : 24; }();
+    constexpr int THROTTLE_STEP = 4;
+    auto issue_loop = [&](const std::vector<int>& cs, bool capturing) {
         launch_begin(ctx->dslot, S, ctx->sched[0], ctx->n_sm, st, ctx->side, ctx->ev);
-        for (size_t i = 0; i < n_it; ++i)
+        const bool thr = throttle > 0 && !capturing;
+        const int ring = GrowCtx::THR_RING;
+        for (size_t i = 0; i < n_it; ++i) {
             launch_iteration(ctx->dslot, S, &cs[2 * i], ctx->sched[i], i + 1 < n_it ? &ctx->sched[i + 1] : nullptr, ctx->n_sm, st, ctx->side, ctx->ev);
+            if (thr && (i % THROTTLE_STEP) == THROTTLE_STEP - 1) {
+                const size_t k = i / THROTTLE_STEP;
+                if (!ctx->thr_ev[k % ring]) cudaEventCreateWithFlags(&ctx->thr_ev[k % ring], cudaEventBlockingSync | cudaEventDisableTiming);
+                cudaEventRecord(ctx->thr_ev[k % ring], st);
+                const size_t behind = (size_t)(throttle + THROTTLE_STEP - 1) / THROTTLE_STEP;
+                if (k >= behind) cudaEventSynchronize(ctx->thr_ev[(k - behind) % ring]);
+            }
+        }
     };
     // OCTA_GROW_GRAPH: 0 (default) = stream launches, 1 = CUDA graph from the context's second batch on (the first one also
     // establishes the mirror sizes), 2 = CUDA graph always.  Measured on one B200 (profiles/README.md, round 2): the graph frees
@@ -666,7 +686,7 @@ static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, doub
             if (lg.exec) { cudaGraphExecDestroy(lg.exec); lg.exec = nullptr; }
             OCTA_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
             t_capturing = true; t_captured = 0;          // captured, not launched: counted per graph launch below
-            issue_loop(cs_all);
+            issue_loop(cs_all, true);
             t_capturing = false;
             cudaGraph_t graph = nullptr;
             cudaError_t ce = cudaStreamEndCapture(st, &graph);
@@ -681,7 +701,7 @@ static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, doub
         count_launch((int)lg.kernels);
         if (host_timing) fprintf(stderr, "[octa grow host] %s cudaGraphLaunch of %llu kernels: %.2f ms\n", stale ? "capture + instantiate done;" : "", (unsigned long long)lg.kernels, wall() - tg0);
     } else if (n_it > 0) {
-        issue_loop(cs_all);
+        issue_loop(cs_all, false);
     }
     OCTA_CUDA_CHECK(cudaEventRecord(ctx->e1, st));
     tw[3] = wall();
@@ -751,7 +771,14 @@ static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, doub
     }
     tw[5] = wall();
     // ---- exact radii + edge rows, multi-threaded over graphs
-    unsigned nthreads = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)n_graphs));
+    // (the cores this process may run on: ranks of a multi-GPU job are pinned to their own slice of the box)
+    unsigned ncores = std::thread::hardware_concurrency();
+    {
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) ncores = (unsigned)CPU_COUNT(&set);
+    }
+    unsigned nthreads = std::max(1u, std::min<unsigned>(ncores, (unsigned)n_graphs));
     std::vector<std::thread> pool;
     for (unsigned wk = 0; wk < nthreads; ++wk)
         pool.emplace_back([&, wk]() {

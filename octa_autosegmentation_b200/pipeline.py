@@ -33,7 +33,8 @@ class Pipeline:
         self.image_res = [int(d) for d in image_res]
         self.mip_axis = int(mip_axis)
         self.voxelize = bool(voxelize)
-        self.host_threads = host_threads or max(1, (os.cpu_count() or 2) - 1)
+        ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 2)     # (ranks are pinned to core slices)
+        self.host_threads = host_threads or max(1, ncores - 1)
         self._buf = {}
         self._grows = {}           # growth contexts by index (run_pipelined keeps several batches in flight)
         self._grow_locks = {}
