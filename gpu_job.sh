@@ -1,7 +1,3 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
-timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r02_c.json 2> gpurun_out/bench_r02_c.err; python -c "
-import json
-d=json.loads(open('gpurun_out/bench_r02_c.json').read().strip().splitlines()[-1])
-print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e']['value'], d['roofline']['frac'], d['roofline']['ms_per_launch'], d['cpu_baseline']['value'], d['config5_gan']['images_per_sec'])
-"; tail -3 gpurun_out/bench_r02_c.err
+timeout 900 compute-sanitizer --tool memcheck python tools/sanitize_small.py > gpurun_out/r02_sanitizer_memcheck.log 2>&1; tail -3 gpurun_out/r02_sanitizer_memcheck.log
+timeout 1200 compute-sanitizer --tool racecheck python tools/sanitize_small.py > gpurun_out/r02_sanitizer_racecheck.log 2>&1; grep -c "Race reported" gpurun_out/r02_sanitizer_racecheck.log; grep "Race reported" -A3 gpurun_out/r02_sanitizer_racecheck.log | grep "at \|Race" | sort | uniq -c | sort -rn | head -12; tail -2 gpurun_out/r02_sanitizer_racecheck.log
