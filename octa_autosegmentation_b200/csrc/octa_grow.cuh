@@ -80,7 +80,8 @@ struct GrowDev {
     unsigned int *vi, *ubuf;
     double *cx, *cy, *cz;
     int* n_cand;
-    unsigned char *cpass, *cstate;
+    unsigned char *cpass;
+    unsigned int* cstate32;   // k_sink_greedy decision cells when they do not fit in shared memory
     int* plist;
     int *assign, *first, *cnt, *slot, *cur;
     int *dict_node, *n_dict, *list_off, *list, *sc_idx;

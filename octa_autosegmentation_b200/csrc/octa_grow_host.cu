@@ -277,7 +277,7 @@ void carve(Carver& c, const GrowShape& S, GrowDev* D) {
     D->geom_mask = c.take<unsigned char>(MAX_VALID);
     D->vi = c.take<unsigned int>(GC); D->ubuf = c.take<unsigned int>(6 * GC);
     D->cx = c.take<double>(GC); D->cy = c.take<double>(GC); D->cz = c.take<double>(GC);
-    D->n_cand = c.take<int>(G); D->cpass = c.take<unsigned char>(GC); D->cstate = c.take<unsigned char>(GC);
+    D->n_cand = c.take<int>(G); D->cpass = c.take<unsigned char>(GC); D->cstate32 = c.take<unsigned int>(GC);
     D->plist = c.take<int>(GC);
     D->assign = c.take<int>(GS);
     D->first = c.take<int>(GN); D->cnt = c.take<int>(GN); D->slot = c.take<int>(GN); D->cur = c.take<int>(GN);

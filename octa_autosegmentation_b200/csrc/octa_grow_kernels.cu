@@ -350,33 +350,36 @@ __global__ void __launch_bounds__(1024, 2) k_sink_greedy(int dslot, GrowShape S,
     const unsigned char* cp = D.cpass + (size_t)g * S.Nmax;
     int* pl = D.plist + (size_t)g * S.Nmax;
     // decision state per passing candidate: shared memory (read by every other candidate every round)
-    __shared__ unsigned char s_state[8192];
-    volatile unsigned char* state = (S.Nmax <= 8192) ? (volatile unsigned char*)s_state : (volatile unsigned char*)(D.cstate + (size_t)g * S.Nmax);
+    // (32-bit cells accessed through block-scope relaxed atomics: plain LDS / STS, and the memory model -- and compute-sanitizer --
+    // see the cross-thread reads inside a round as what they are)
+    __shared__ unsigned int s_state[8192];
+    unsigned int* state_p = (S.Nmax <= 8192) ? s_state : (D.cstate32 + (size_t)g * S.Nmax);
+    auto st_load = [&](int k) { return cuda::atomic_ref<unsigned int, cuda::thread_scope_block>(state_p[k]).load(cuda::memory_order_relaxed); };
+    auto st_store = [&](int k, unsigned int v) { cuda::atomic_ref<unsigned int, cuda::thread_scope_block>(state_p[k]).store(v, cuda::memory_order_relaxed); };
     int np_ = 0;
     for (int base = 0; base < nc; base += blockDim.x) {
         const int i = base + tid;
         const int f = (i < nc) ? cp[i] : 0;
         int total;
         const int incl = block_scan_incl(f, &total);
-        if (f) { pl[np_ + incl - 1] = i; state[np_ + incl - 1] = 0; }
+        if (f) { pl[np_ + incl - 1] = i; st_store(np_ + incl - 1, 0u); }
         np_ += total;
     }
     __syncthreads();
     const double eps2 = P.eps_s * P.eps_s;
     // state: 0 undecided, 1 accepted, 2 rejected.  Candidate k is rejected as soon as an earlier ACCEPTED
     // candidate lies within eps_s, accepted once every earlier candidate within eps_s is rejected.
-    // Threads read state[j] of other threads inside a round without a barrier (compute-sanitizer racecheck
-    // flags it): a state only ever moves 0 -> 1 or 0 -> 2, and either value seen gives a decision the
+    // Threads read state[j] of other threads inside a round without a barrier: a state only ever moves 0 -> 1 or 0 -> 2, and either value seen gives a decision the
     // sequential greedy would also reach, so the fixed point is unique; early visibility just saves rounds.
     for (int round = 0; round < nc + 2; ++round) {
         int undecided = 0;
         for (int k = tid; k < np_; k += blockDim.x) {
-            if (state[k] != 0) continue;
+            if (st_load(k) != 0u) continue;
             const int ik = pl[k];
             const double px = cx[ik], py = cy[ik], pz = cz[ik];
             bool acc = false, und = false;
             for (int j = 0; j < k; ++j) {
-                const unsigned char sj = state[j];
+                const unsigned int sj = st_load(j);
                 if (sj == 2) continue;
                 const int ij = pl[j];
                 const double d2 = dist2(px, py, pz, cx[ij], cy[ij], cz[ij]);
@@ -385,8 +388,8 @@ __global__ void __launch_bounds__(1024, 2) k_sink_greedy(int dslot, GrowShape S,
                     und = true;
                 }
             }
-            if (acc) state[k] = 2;
-            else if (!und) state[k] = 1;
+            if (acc) st_store(k, 2u);
+            else if (!und) st_store(k, 1u);
             else undecided = 1;
         }
         __threadfence_block();
@@ -398,7 +401,7 @@ __global__ void __launch_bounds__(1024, 2) k_sink_greedy(int dslot, GrowShape S,
     const size_t sb = (size_t)g * S.capS;
     for (int base = 0; base < np_; base += blockDim.x) {
         const int k = base + tid;
-        const int f = (k < np_) ? (state[k] == 1) : 0;
+        const int f = (k < np_) ? (st_load(k) == 1u) : 0;
         int total;
         const int incl = block_scan_incl(f, &total);
         if (f) {
