@@ -1291,7 +1291,7 @@ __device__ bool kill_convert(const GrowDev& D, const GrowShape& S, int g, int T,
 // S.exact_ball_order: 0 = list-index order inside a ball (diagnostics), 1 = cKDTree order, permutation built for every graph in
 // every iteration (k_kdbuild on the side stream), 2 = cKDTree order ON DEMAND: this kernel runs the conversion in list-index
 // order with the order-sensitivity test of pyset_run; a graph whose result could depend on the order is put on the iteration's
-// work list instead of being finished, k_kdbuild builds the permutation of the listed graphs only and k_kill_fix finishes them.
+// work list instead of being finished, k_kdbuild_list builds the permutation of the listed graphs only and finishes their kill.
 __global__ void __launch_bounds__(1024) k_kill(int dslot, GrowShape S, IterP P, int f) {
     const GrowDev& D = c_dev[dslot];
     __shared__ KillShared ks;
@@ -1441,7 +1441,7 @@ __global__ void __launch_bounds__(1024) k_kill(int dslot, GrowShape S, IterP P, 
             // element_mesh.py:136-137).
             if (S.exact_ball_order == 2) {
                 if (kill_convert<true>(D, S, g, T, nullptr, &ks)) {
-                    if (tid == 0) {          // finished by k_kdbuild + k_kill_fix
+                    if (tid == 0) {          // finished by k_kdbuild_list
                         D.kill_T[g] = T;
                         D.kill_H[g] = listed ? H : -1;
                         D.kd_flag[g] = 1;
@@ -1456,20 +1456,6 @@ __global__ void __launch_bounds__(1024) k_kill(int dslot, GrowShape S, IterP P, 
         }
     }
     kill_compact(D, S, P, f, g, Sn, nn > 0, f == 0 ? Hc : H, hl, s_hl);
-}
-
-// finish the arterial kill of the graphs k_kill put on the work list: same conversion with the exact order inside every ball
-__global__ void __launch_bounds__(1024) k_kill_fix(int dslot, GrowShape S, IterP P) {
-    const GrowDev& D = c_dev[dslot];
-    __shared__ KillShared ks;
-    const int g = blockIdx.x;
-    if (g == 0 && threadIdx.x == 0) D.kd_nflag[(P.iter + 1) & 1] = 0;      // the next iteration's list starts empty
-    if (D.err[g] || !D.kd_flag[g]) return;
-    __syncthreads();
-    if (threadIdx.x == 0) D.kd_flag[g] = 0;
-    const size_t sb = (size_t)g * S.capS;
-    kill_convert<false>(D, S, g, D.kill_T[g], D.kd_rank + sb, &ks);
-    kill_compact(D, S, P, 0, g, D.n_s[0][g], true, D.kill_H[g], D.hl + sb, reinterpret_cast<int*>(ks.th));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1505,14 +1491,31 @@ __global__ void __launch_bounds__(1024) k_kdbuild(int dslot, GrowShape S, int sm
 }
 
 // on-demand variant (S.exact_ball_order == 2): the CTAs walk the work list k_kill filled in this iteration
-__global__ void __launch_bounds__(1024) k_kdbuild_list(int dslot, GrowShape S, int smem_bytes, int parity) {
+// ... and finishes the arterial kill of each listed graph right behind its own build (the conversion with the exact order inside
+// every ball, then the compaction of the sink list): one launch instead of two, and a graph does not wait for the slowest build
+// of the batch.  The set tables of the conversion live in the build's shared memory, which is idle by then.
+__global__ void __launch_bounds__(1024) k_kdbuild_list(int dslot, GrowShape S, IterP P, int smem_bytes) {
     const GrowDev& D = c_dev[dslot];
     extern __shared__ __align__(16) char s_kd[];
     __shared__ int s_ws[kdpar::WS_INTS];
     __shared__ double s_wd[kdpar::WD_DOUBLES];
+    static_assert(sizeof(KillShared) <= 64 * 1024, "KillShared must fit the build's shared memory");
+    const int parity = P.iter & 1;
+    if (blockIdx.x == 0 && threadIdx.x == 0) D.kd_nflag[parity ^ 1] = 0;      // the next iteration's list starts empty
     const int n = D.kd_nflag[parity];
     for (int q = blockIdx.x; q < n; q += gridDim.x) {
-        kdbuild_graph(D, S, smem_bytes, D.kd_list[parity * S.G + q], s_kd, s_ws, s_wd);
+        const int g = D.kd_list[parity * S.G + q];
+        kdbuild_graph(D, S, smem_bytes, g, s_kd, s_ws, s_wd);
+        __threadfence_block();
+        __syncthreads();
+        if (!D.err[g] && D.kd_flag[g]) {
+            KillShared* ks = reinterpret_cast<KillShared*>(s_kd);
+            const size_t sb = (size_t)g * S.capS;
+            kill_convert<false>(D, S, g, D.kill_T[g], D.kd_rank + sb, ks);
+            kill_compact(D, S, P, 0, g, D.n_s[0][g], true, D.kill_H[g], D.hl + sb, reinterpret_cast<int*>(ks->th));
+            __syncthreads();
+            if (threadIdx.x == 0) D.kd_flag[g] = 0;
+        }
         __syncthreads();
     }
 }
@@ -1567,7 +1570,7 @@ Timing g_timing[2];        // [0] main stream, [1] side stream
 bool g_timing_on = false, g_timing_init = false;
 const char* const kTimingNames[] = {"start", "k_prepare", "k_sink_tests", "k_sink_greedy", "k_assign[a]", "k_group[a]", "k_eval[a]",
                                     "k_commit[a]", "k_kill[a]", "k_assign[v]", "k_group[v]", "k_eval[v]", "k_commit[v]", "k_kill[v]",
-                                    "k_kdbuild", "(side waits) / k_kill_fix"};
+                                    "k_kdbuild_list (+fix)", "(side waits)"};
 constexpr int N_KINDS = 16;
 inline void tick(cudaStream_t st, int k, int which = 0) { if (g_timing_on) cudaEventRecord(g_timing[which].next(k), st); }
 }  // namespace
@@ -1668,11 +1671,9 @@ void launch_iteration(int dslot, const GrowShape& S, const int commit_smem[2], c
             // exact cKDTree order on demand: permutation + conversion redone for the graphs k_kill listed (about a third of the
             // graph-iterations of the docker config); the CTAs of k_kdbuild_list own a whole SM's shared memory, so the launch is
             // half a batch wide and walks the list
-            k_kdbuild_list<<<(S.G + 1) / 2, 1024, KD_SMEM_BYTES, st>>>(dslot, S, KD_SMEM_BYTES, P.iter & 1);
+            k_kdbuild_list<<<(S.G + 1) / 2, 1024, KD_SMEM_BYTES, st>>>(dslot, S, P, KD_SMEM_BYTES);
             tick(st, 14);
-            k_kill_fix<<<S.G, kill_threads, 0, st>>>(dslot, S, P);
-            tick(st, 15);
-            count_launch(2);
+            count_launch(1);
         }
         if (f == 0) {
             cudaEventRecord(ev.killa, st);

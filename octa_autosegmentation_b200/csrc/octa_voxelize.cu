@@ -552,7 +552,7 @@ struct ColEdge {             // per edge of a pass, tile-local
     float ah[3], al[3];      // p2 - (tile origin + 0.5) as hi + lo
     float f[3], finv, inv2d, reach, thr, eps;
     short x0, nx, y0, ny, z0, nz;
-    int rcp;                 // ceil(2^20 / nz): item / nz without a division
+    float rfxy;              // 1 / |s_xy| (0: the edge is parallel to z)
     int idx;
 };
 constexpr int SLOWCAP = 160; // deferred float64 evaluations per CTA (~15 per tile are usual; beyond: the cell is marked and recomputed)
@@ -605,7 +605,8 @@ __device__ __noinline__ void resolve_marked(const VoxEdge* __restrict__ ge, cons
     }
 }
 
-__global__ void __launch_bounds__(VOX_THREADS, 6)
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 vox_col_kernel(const VoxEdge* __restrict__ prep, const int64_t* __restrict__ edge_offsets, VoxGeom g,
                const int* __restrict__ tile_start, const int* __restrict__ tile_edges,
                const int* __restrict__ big_count, const int* __restrict__ big_idx,
@@ -654,7 +655,7 @@ vox_col_kernel(const VoxEdge* __restrict__ prep, const int64_t* __restrict__ edg
         for (int i = (tile_elems / 8) * 8 + threadIdx.x; i < tile_elems; i += blockDim.x) acc[i] = 0;
     }
     __shared__ ColEdge ce[EPASS];
-    __shared__ float4 s_hit[VOX_THREADS / 32][32];         // per warp: (w0, w1, dxy, cell offset of the column) of the hit columns
+    __shared__ float4 s_hit[NT / 32][32];         // per warp: (w0, w1, dxy, cell offset of the column) of the hit columns
     __shared__ int2 s_slow[SLOWCAP];                        // deferred float64 evaluations of the CTA: (edge, cell)
     __shared__ int s_nslow;
     if (threadIdx.x == 0) s_nslow = 0;                      // (ordered before its first use by the barrier of the first pass)
@@ -668,7 +669,7 @@ vox_col_kernel(const VoxEdge* __restrict__ prep, const int64_t* __restrict__ edg
     const int ystride = g.T[2], xstride = g.T[1] * g.T[2];
     // columns of the tile -> threads.  16 x 16 tiles: a warp owns an 8 x 4 block of columns
     const int ncols = g.T[0] * g.T[1];
-    const bool blocked = (g.T[0] == 16 && g.T[1] == 16 && VOX_THREADS == 256);
+    const bool blocked = (g.T[0] == 16 && g.T[1] == 16 && NT == 256);
     for (int pass = 0; pass < nall; pass += EPASS) {
         const int cnt = imin(EPASS, nall - pass);
         if (pass > 0) __syncthreads();                 // the previous pass has been read by every thread
@@ -695,12 +696,12 @@ vox_col_kernel(const VoxEdge* __restrict__ prep, const int64_t* __restrict__ edg
             c.x0 = (short)lo3[0]; c.nx = (short)(any ? n3[0] : 0);
             c.y0 = (short)lo3[1]; c.ny = (short)(any ? n3[1] : 0);
             c.z0 = (short)lo3[2]; c.nz = (short)(any ? n3[2] : 0);
-            c.rcp = any ? ((1 << 20) + n3[2] - 1) / n3[2] : 0;
+            c.rfxy = sqrtf(e.inv2d);
             c.finv = e.finv; c.inv2d = e.inv2d; c.reach = e.reach; c.thr = e.thr; c.eps = e.eps;
             ce[threadIdx.x] = c;
         }
         __syncthreads();                               // (also: the accumulators are cleared)
-        for (int cb = warp * 32; cb < ncols; cb += VOX_THREADS) {      // warp-uniform
+        for (int cb = warp * 32; cb < ncols; cb += NT) {      // warp-uniform
             int cx, cy, bx0, by0, bnx, bny;            // this lane's column; the box of the warp's 32 columns
             if (blocked) {
                 bx0 = (warp & 1) << 3; by0 = (warp >> 1) << 2; bnx = 8; bny = 4;
@@ -721,6 +722,17 @@ vox_col_kernel(const VoxEdge* __restrict__ prep, const int64_t* __restrict__ edg
                 if (lane < cnt) {
                     const ColEdge& E = ce[lane];
                     ov = E.x0 < bx0 + bnx && bx0 < E.x0 + E.nx && E.y0 < by0 + bny && by0 < E.y0 + E.ny;
+                    if (ov) {
+                        // the box of a thin diagonal edge is mostly empty: also require the capsule's xy shadow to come within
+                        // the half diagonal of the warp's block of its centre (triangle inequality; 0.01 covers the float32 error)
+                        const float mx = (float)bx0 + 0.5f * (float)(bnx - 1), my = (float)by0 + 0.5f * (float)(bny - 1);
+                        const float w0 = (mx - E.ah[0]) - E.al[0], w1 = (my - E.ah[1]) - E.al[1];
+                        const float t2 = __saturatef(fmaf(w1, E.f[1], w0 * E.f[0]) * E.inv2d);
+                        const float e0 = fmaf(-t2, E.f[0], w0), e1 = fmaf(-t2, E.f[1], w1);
+                        const float hx = 0.5f * (float)(bnx - 1), hy = 0.5f * (float)(bny - 1);
+                        const float lim = sqrtf(E.thr) + sqrtf(hx * hx + hy * hy) + 0.01f;
+                        ov = !(fmaf(e1, e1, e0 * e0) > lim * lim);
+                    }
                 }
                 todo = __ballot_sync(0xffffffffu, ov);
             }
@@ -731,27 +743,49 @@ vox_col_kernel(const VoxEdge* __restrict__ prep, const int64_t* __restrict__ edg
                 const float f0 = E.f[0], f1 = E.f[1];
                 bool hit = (unsigned)(cx - E.x0) < (unsigned)E.nx && (unsigned)(cy - E.y0) < (unsigned)E.ny;
                 float w0 = 0.f, w1 = 0.f, dxy = 0.f;
+                int zl = 0, zn = 0;
                 if (hit) {
                     w0 = (fcx - E.ah[0]) - E.al[0]; w1 = (fcy - E.ah[1]) - E.al[1];
                     dxy = fmaf(w1, f1, w0 * f0);
-                    const float t2 = __saturatef(dxy * E.inv2d);
+                    const float tp = dxy * E.inv2d;
+                    const float t2 = __saturatef(tp);
                     const float e0 = fmaf(-t2, f0, w0), e1 = fmaf(-t2, f1, w1);
                     hit = !(fmaf(e1, e1, e0 * e0) > E.thr);              // else: the column misses the capsule's xy shadow
+                    if (hit) {
+                        // z cells of THIS column the capsule can reach.  A cell within r (r^2 = thr) of the point q(t*) of the
+                        // axis has |xy - q_xy(t*)| <= r, so t* lies within sqrt(r^2 - p^2) / |s_xy| of the column's projection
+                        // parameter tp (p = distance of the column from the axis LINE in xy), and |z - q_z(t*)| <= sqrt(r^2 - p^2).
+                        const float p0 = fmaf(-tp, f0, w0), p1 = fmaf(-tp, f1, w1);
+                        float hh;
+                        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(hh) : "f"(fmaxf(E.thr - fmaf(p1, p1, p0 * p0), 0.f)));
+                        hh += 0.02f;
+                        float tlo = 0.f, thi = 1.f;
+                        if (E.inv2d > 0.f) { const float dt = fmaf(hh, E.rfxy, 1e-4f); tlo = __saturatef(tp - dt); thi = __saturatef(tp + dt); }
+                        const float a2 = E.ah[2] + E.al[2], f2e = E.f[2];
+                        const float za = fmaf(f2e, tlo, a2), zb = fmaf(f2e, thi, a2);
+                        zl = max((int)ceilf(fminf(za, zb) - hh), (int)E.z0);
+                        zn = min((int)floorf(fmaxf(za, zb) + hh), (int)E.z0 + (int)E.nz - 1) - zl + 1;
+                        hit = zn > 0;
+                    }
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, hit);
                 if (!m) continue;
                 // Within one edge all (column, z) cells are distinct and the columns belong to this warp: the cells of the hit
-                // columns are dealt to ALL lanes (plain loads and stores, no atomics), whatever the shape of the hit set.
-                if (hit) hitw[__popc(m & lt)] = make_float4(w0, w1, dxy, coff);
+                // columns are dealt to ALL lanes (plain loads and stores, no atomics), whatever the shape of the hit set.  A hit
+                // column brings its own z run (zl, zn); the runs are dealt with the stride of the longest one.
+                const int nzr = (int)__reduce_max_sync(0xffffffffu, (unsigned)(hit ? zn : 0));
+                if (hit) hitw[__popc(m & lt)] = make_float4(w0, w1, dxy, __int_as_float(__float_as_int(coff) | (zl << 14) | (zn << 21)));
                 __syncwarp();
-                const int nzr = E.nz, total = __popc(m) * nzr, rcp = E.rcp, z0 = E.z0, eidx = E.idx;
+                const int total = __popc(m) * nzr, rcp = ((1 << 20) + nzr - 1) / nzr, eidx = E.idx;
                 const float f2 = E.f[2], finv = E.finv, reach = E.reach, eps = E.eps, thr = E.thr, ah2 = E.ah[2], al2 = E.al[2];
                 const float hi255 = 255.f + eps, om = 1.f - eps;
 #pragma unroll 2
                 for (int j = lane; j < total; j += 32) {
                     const int h = (int)(((unsigned)j * (unsigned)rcp) >> 20);
-                    const int z = z0 + (j - h * nzr);
                     const float4 hv = hitw[h];
+                    const int pk = __float_as_int(hv.w), dz = j - h * nzr;
+                    if (dz >= (pk >> 21)) continue;
+                    const int z = ((pk >> 14) & 127) + dz;
                     const float w2 = ((float)z - ah2) - al2;
                     const float t = __saturatef(fmaf(w2, f2, hv.z) * finv);
                     const float d0 = fmaf(-t, f0, hv.x), d1 = fmaf(-t, f1, hv.y), d2 = fmaf(-t, f2, w2);
@@ -761,7 +795,7 @@ vox_col_kernel(const VoxEdge* __restrict__ prep, const int64_t* __restrict__ edg
                     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(dd));
                     const float v = (reach - d) * 147.22431864335458f;       // 255 * I
                     const float fl = floorf(v), fr = v - fl;
-                    const int cell = __float_as_int(hv.w) + z;
+                    const int cell = (pk & 16383) + z;
                     // certain: 255*I >= 255 + eps (clipped to 255), or at least eps away from every integer
                     const bool top = v >= hi255;
                     if (!top && (!(fr >= eps) || fr > om)) {               // within eps of an integer (or NaN): float64 decides
@@ -786,7 +820,7 @@ vox_col_kernel(const VoxEdge* __restrict__ prep, const int64_t* __restrict__ edg
     __syncthreads();
     {   // the deferred cells of the CTA: float64 fast path / exact chain; two entries may name the same cell -> CAS max
         const int ns = imin(s_nslow, SLOWCAP);
-        for (int i = threadIdx.x; i < ns; i += VOX_THREADS) {
+        for (int i = threadIdx.x; i < ns; i += NT) {
             const int2 ent = s_slow[i];
             const int cx = ent.y / xstride, r = ent.y - cx * xstride, cy = r / ystride, z = r - cy * ystride;
             const uint32_t v = slow_voxel_q(ge + ent.x, t0x + cx, t0y + cy, t0z + z);
@@ -953,8 +987,10 @@ extern "C" int octa_voxelize_batch_dev(const double* edges7_dev, const int64_t* 
     static size_t smem_set = 0;
     if (smem > smem_set) {
         OCTA_CUDA_CHECK(cudaFuncSetAttribute(vox_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        OCTA_CUDA_CHECK(cudaFuncSetAttribute(vox_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        OCTA_CUDA_CHECK(cudaFuncSetAttribute(vox_col_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));   // six tiles per SM
+        OCTA_CUDA_CHECK(cudaFuncSetAttribute(vox_col_kernel<256, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OCTA_CUDA_CHECK(cudaFuncSetAttribute(vox_col_kernel<256, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));   // six tiles per SM
+        OCTA_CUDA_CHECK(cudaFuncSetAttribute(vox_col_kernel<128, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OCTA_CUDA_CHECK(cudaFuncSetAttribute(vox_col_kernel<128, 12>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         smem_set = smem;
     }
     // OCTA_VOX_KERNEL=rows selects the row-dealing kernel of round 1 (kept for A/B measurements; bit-identical results)
@@ -963,9 +999,12 @@ extern "C" int octa_voxelize_batch_dev(const double* edges7_dev, const int64_t* 
     if (use_rows)
         vox_tile_kernel<<<grid, VOX_THREADS, smem, stream>>>(w.prep, w.edge_offsets, g, w.tile_start, w.tile_edges,
                                                              w.big_count, w.big_idx, out_dev);
+    else if (g.T[0] * g.T[1] <= 128)       // half-size tiles (OCTA_VOX_TILE_Y=8): four warps per tile
+        vox_col_kernel<128, 12><<<grid, 128, smem, stream>>>(w.prep, w.edge_offsets, g, w.tile_start, w.tile_edges,
+                                                              w.big_count, w.big_idx, out_dev);
     else
-        vox_col_kernel<<<grid, VOX_THREADS, smem, stream>>>(w.prep, w.edge_offsets, g, w.tile_start, w.tile_edges,
-                                                            w.big_count, w.big_idx, out_dev);
+        vox_col_kernel<256, 6><<<grid, 256, smem, stream>>>(w.prep, w.edge_offsets, g, w.tile_start, w.tile_edges,
+                                                             w.big_count, w.big_idx, out_dev);
     octa::count_launch();
     OCTA_CUDA_CHECK(cudaGetLastError());
     return OCTA_OK;
