@@ -246,7 +246,8 @@ def main():
             s = seeds()
             batches += [s[j:j + SB] for j in range(0, B, SB)]
         h2d = d2h_b = 0
-        for i, out in enumerate(pipe.run_pipelined(batches, d2h=d2h, csv=d2h, in_flight=args.in_flight, d2h_volume=d2h and args.d2h_volume)):
+        for i, out in enumerate(pipe.run_pipelined(batches, d2h=d2h, csv=d2h, in_flight=args.in_flight, d2h_volume=d2h and args.d2h_volume,
+                                                   extra_slots=1 if (d2h and args.d2h_volume) else None)):      # (10 GB of pinned volumes per set)
             last = account(out, d2h)
             if d2h:
                 h2d += int(out["h2d_bytes"]); d2h_b += int(out["d2h_bytes"])
@@ -302,7 +303,7 @@ def main():
     vox_ms = ve[0].elapsed_time(ve[1]) / nrep
     del out, vol, edges_dev
     pipe.release_device_buffers()                              # 10 GB of volumes per device-resident buffer set
-    NSETS_H = Pipeline.buffer_sets(args.in_flight, True)
+    NSETS_H = Pipeline.buffer_sets(args.in_flight, True, 1 if args.d2h_volume else None)
     run_steps(max(1, (NSETS_H + NSUB - 1) // NSUB), True)      # (pinned result buffers of every set)
     ms_e2e, last = timed(lambda k: run_steps(k, True), max(2, args.steps))
     clocks = sampler.stop() if rank == 0 else None
