@@ -1,6 +1,5 @@
-free -g | head -2
-timeout 600 python bench.py --steps 12 --warmup 4 --in-flight 3 --d2h-volume --no-gan --no-cpu-baseline > gpurun_out/bench_r02_d2hvol.json 2> gpurun_out/bench_r02_d2hvol.err; python -c "
-import json
-d=json.loads(open('gpurun_out/bench_r02_d2hvol.json').read().strip().splitlines()[-1])
-print('d2h-volume', d['value'], d['e2e'])
-"; tail -3 gpurun_out/bench_r02_d2hvol.err
+timeout 900 python -m pytest tests/test_growth_gpu.py -m gpu -x -q 2>&1 | tail -2
+OCTA_GROW_TIMING=1 timeout 300 python tools/grow_probe.py --batch 64 --reps 2 2>&1 | grep "timing" | tail -2
+P="timeout 300 python tools/pipe_probe.py 20 7 64 1"
+$P 2>&1 | grep "PROBE\|Error"
+$P 2>&1 | grep "PROBE\|Error"

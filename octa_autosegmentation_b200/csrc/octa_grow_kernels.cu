@@ -352,8 +352,8 @@ __global__ void __launch_bounds__(1024, 2) k_sink_greedy(int dslot, GrowShape S,
     // decision state per passing candidate: shared memory (read by every other candidate every round)
     // (32-bit cells accessed through block-scope relaxed atomics: plain LDS / STS, and the memory model -- and compute-sanitizer --
     // see the cross-thread reads inside a round as what they are)
-    __shared__ unsigned int s_state[8192];
-    unsigned int* state_p = (S.Nmax <= 8192) ? s_state : (D.cstate32 + (size_t)g * S.Nmax);
+    __shared__ unsigned int s_state[4096];
+    unsigned int* state_p = (S.Nmax <= 4096) ? s_state : (D.cstate32 + (size_t)g * S.Nmax);
     auto st_load = [&](int k) { return cuda::atomic_ref<unsigned int, cuda::thread_scope_block>(state_p[k]).load(cuda::memory_order_relaxed); };
     auto st_store = [&](int k, unsigned int v) { cuda::atomic_ref<unsigned int, cuda::thread_scope_block>(state_p[k]).store(v, cuda::memory_order_relaxed); };
     int np_ = 0;
@@ -371,6 +371,35 @@ __global__ void __launch_bounds__(1024, 2) k_sink_greedy(int dslot, GrowShape S,
     // candidate lies within eps_s, accepted once every earlier candidate within eps_s is rejected.
     // Threads read state[j] of other threads inside a round without a barrier: a state only ever moves 0 -> 1 or 0 -> 2, and either value seen gives a decision the
     // sequential greedy would also reach, so the fixed point is unique; early visibility just saves rounds.
+    // The passing candidates are binned into a 32 x 32 grid (one row of cells = one contiguous range of `s_sorted`): a candidate
+    // only looks at the earlier candidates of the cells within eps_s instead of at all of them (the test itself is unchanged, and
+    // the decision depends on the SET of earlier neighbours and their states, not on the order they are visited in).
+    constexpr int G2 = 32;
+    __shared__ unsigned short s_sorted[8192];
+    __shared__ int s_cstart[G2 * G2 + 1];
+    __shared__ int s_cursor[G2 * G2];
+    const bool binned = np_ <= 8192;
+    auto cell2 = [](double v) { int c = (int)floor(v * (double)G2); return c < 0 ? 0 : (c >= G2 ? G2 - 1 : c); };
+    if (binned) {
+        for (int c = tid; c < G2 * G2; c += blockDim.x) s_cursor[c] = 0;
+        __syncthreads();
+        for (int k = tid; k < np_; k += blockDim.x) { const int ik = pl[k]; atomicAdd(&s_cursor[cell2(cy[ik]) * G2 + cell2(cx[ik])], 1); }
+        __syncthreads();
+        int run = 0;
+        for (int base = 0; base < G2 * G2; base += blockDim.x) {
+            const int c = base + tid;
+            const int v = c < G2 * G2 ? s_cursor[c] : 0;
+            int total;
+            const int incl = block_scan_incl(v, &total);
+            if (c < G2 * G2) { s_cstart[c] = run + incl - v; s_cursor[c] = run + incl - v; }
+            run += total;
+        }
+        if (tid == 0) s_cstart[G2 * G2] = run;
+        __syncthreads();
+        for (int k = tid; k < np_; k += blockDim.x) { const int ik = pl[k]; s_sorted[atomicAdd(&s_cursor[cell2(cy[ik]) * G2 + cell2(cx[ik])], 1)] = (unsigned short)k; }
+        __syncthreads();
+    }
+    const double er = P.eps_s * (1.0 + 1e-9) + 1e-12;             // the cell range may only be too wide
     for (int round = 0; round < nc + 2; ++round) {
         int undecided = 0;
         for (int k = tid; k < np_; k += blockDim.x) {
@@ -378,6 +407,24 @@ __global__ void __launch_bounds__(1024, 2) k_sink_greedy(int dslot, GrowShape S,
             const int ik = pl[k];
             const double px = cx[ik], py = cy[ik], pz = cz[ik];
             bool acc = false, und = false;
+            if (binned) {
+                const int x0 = cell2(px - er), x1 = cell2(px + er), y0 = cell2(py - er), y1 = cell2(py + er);
+                for (int yy = y0; yy <= y1 && !acc; ++yy) {
+                    const int beg = s_cstart[yy * G2 + x0], end = s_cstart[yy * G2 + x1 + 1];
+                    for (int q = beg; q < end; ++q) {
+                        const int j = s_sorted[q];
+                        if (j >= k) continue;
+                        const unsigned int sj = st_load(j);
+                        if (sj == 2) continue;
+                        const int ij = pl[j];
+                        const double d2 = dist2(px, py, pz, cx[ij], cy[ij], cz[ij]);
+                        if (within_sqrt(d2, P.eps_s, eps2)) {   // not (norm > eps_s)
+                            if (sj == 1) { acc = true; break; }
+                            und = true;
+                        }
+                    }
+                }
+            } else
             for (int j = 0; j < k; ++j) {
                 const unsigned int sj = st_load(j);
                 if (sj == 2) continue;
