@@ -455,11 +455,7 @@ __global__ void __launch_bounds__(256) k_gan_stats_tiles(const float2* __restric
 }
 
 // raw (flat rows of the [H+2][W+2] grid) -> (x - mean) * rstd [ReLU] [+ skip]  -> destination buffer with padding P
-// skip32 / out32: the residual stream of the ResnetBlocks in float32, unpadded [n][H][W][C] -- the sum x + IN(conv(...)) is formed and
-// kept in float32 (the reference's stream is float32; re-rounding x to bf16 in each of the nine blocks was the source of the
-// outliers against the reference), only the copy the next convolution reads is bf16.
 __global__ void __launch_bounds__(256) k_gan_norm(const bf16* __restrict__ raw, const float2* __restrict__ mr, const bf16* __restrict__ skip,
-                                                  const float* __restrict__ skip32, float* __restrict__ out32,
                                                   int n, int H, int W, int C, int P, int reflect, int relu, bf16* __restrict__ dst) {
     const int groups = C >> 3;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -488,20 +484,11 @@ __global__ void __launch_bounds__(256) k_gan_norm(const bf16* __restrict__ raw, 
 #pragma unroll
             for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
         }
-        if (skip32) {
-            const float4* g4 = reinterpret_cast<const float4*>(skip32 + ((size_t)(b * H + h) * W + w) * C + cg * 8);
-            const float4 g0 = __ldg(g4), g1 = __ldg(g4 + 1);
-            f[0] += g0.x; f[1] += g0.y; f[2] += g0.z; f[3] += g0.w; f[4] += g1.x; f[5] += g1.y; f[6] += g1.z; f[7] += g1.w;
-        } else if (skip) {
+        if (skip) {
             float g[8];
             unpack8(__ldg(reinterpret_cast<const uint4*>(skip + ((size_t)(b * (H + 2) + h + 1) * (W + 2) + w + 1) * C) + cg), g);
 #pragma unroll
             for (int k = 0; k < 8; ++k) f[k] += g[k];
-        }
-        if (out32 && inside) {
-            float4* o4 = reinterpret_cast<float4*>(out32 + ((size_t)(b * H + h) * W + w) * C + cg * 8);
-            o4[0] = make_float4(f[0], f[1], f[2], f[3]);
-            o4[1] = make_float4(f[4], f[5], f[6], f[7]);
         }
         out = pack8(f);
     }
@@ -612,7 +599,6 @@ struct Conv3 {            // one 3x3 layer: weights [cout][9][cin] bf16 and its 
 struct GanCtx {
     int max_n = 0, H = 0, W = 0, n_sm = 148, two_ctas = -1;
     float* planes = nullptr;
-    float *x0 = nullptr, *x1 = nullptr;     // float32 residual stream of the ResnetBlocks (ping-pong), [n][H/4][W/4][256]
     Conv3 stem;           // [64 cout][64 slots: tap t < 49, zero above] bf16 -- the stem as one GEMM over im2col rows
     Conv3 head;           // [64 rows: tap t < 49, zero above][64 channels] bf16 -- the head as one GEMM
     float head_b = 0.f;
@@ -708,10 +694,9 @@ int run_conv(const GanCtx* c, const Conv3& L, const bf16* act, int n, int H, int
     return OCTA_OK;
 }
 
-int run_norm(const GanCtx* c, const bf16* skip, int n, int H, int W, int C, int P, int reflect, int relu, bf16* dst, cudaStream_t st,
-             const float* skip32 = nullptr, float* out32 = nullptr) {
+int run_norm(const GanCtx* c, const bf16* skip, int n, int H, int W, int C, int P, int reflect, int relu, bf16* dst, cudaStream_t st) {
     const size_t total = (size_t)n * (H + 2 * P) * (W + 2 * P) * (C / 8);
-    k_gan_norm<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(c->raw, c->mr, skip, skip32, out32, n, H, W, C, P, reflect, relu, dst);
+    k_gan_norm<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(c->raw, c->mr, skip, n, H, W, C, P, reflect, relu, dst);
     octa::count_launch();
     OCTA_CUDA_CHECK(cudaGetLastError());
     return OCTA_OK;
@@ -775,8 +760,7 @@ extern "C" int octa_gan_create(const OctaGanWeights* w, int max_images, int H, i
         (rc = dev_alloc(c, &c->r1, n * p3 * 256)) || (rc = dev_alloc(c, &c->rt, n * p3 * 256)) || (rc = dev_alloc(c, &c->u1, n * p2 * 256)) ||
         (rc = dev_alloc(c, &c->b3, n * p2 * 128)) || (rc = dev_alloc(c, &c->u2, n * p1 * 128)) ||
         (rc = dev_alloc(c, &c->fin, n * (size_t)(H + 6) * (W + 6) * 64)) || (rc = dev_alloc(c, &c->planes, n * (size_t)(H + 6) * (W + 6) * 49)) || (rc = dev_alloc(c, &c->part, (n * p1 / 128 + 2) * 128)) ||
-        (rc = dev_alloc(c, &c->carry, (n + 1) * 4 * 256)) || (rc = dev_alloc(c, &c->mr, n * 256)) ||
-        (rc = dev_alloc(c, &c->x0, n * (size_t)(H / 4) * (W / 4) * 256)) || (rc = dev_alloc(c, &c->x1, n * (size_t)(H / 4) * (W / 4) * 256)))
+        (rc = dev_alloc(c, &c->carry, (n + 1) * 4 * 256)) || (rc = dev_alloc(c, &c->mr, n * 256)))
         return fail(rc);
     if ((rc = conv_attrs(c))) return fail(rc);
     *handle = c;
@@ -815,15 +799,12 @@ extern "C" int octa_gan_forward_dev(void* handle, const float* x_dev, int n_imag
     GAN_TRY(run_resample(c->raw, c->mr, n, H2, W2, 256, 0, 1, c->r0, st));
     // 9 x ResnetBlock: x + IN(conv(pad(ReLU(IN(conv(pad(x)))))))                               networks.py:291-348
     bf16 *cur = c->r0, *nxt = c->r1;
-    float *xcur = c->x0, *xnxt = c->x1;
     for (int blk = 0; blk < 9; ++blk) {
         GAN_TRY(run_conv(c, c->conv[2 + 2 * blk], cur, n, H3, W3, st));
         GAN_TRY(run_norm(c, nullptr, n, H3, W3, 256, 1, 1, 1, c->rt, st));
         GAN_TRY(run_conv(c, c->conv[3 + 2 * blk], c->rt, n, H3, W3, st));
-        // residual sum in float32: block 0 starts from the bf16 activations of the down path, later blocks from the float32 stream
-        GAN_TRY(run_norm(c, cur, n, H3, W3, 256, 1, 1, 0, nxt, st, blk == 0 ? nullptr : xcur, xnxt));
+        GAN_TRY(run_norm(c, cur, n, H3, W3, 256, 1, 1, 0, nxt, st));
         bf16* t = cur; cur = nxt; nxt = t;
-        float* tx = xcur; xcur = xnxt; xnxt = tx;
     }
     // up 1 / up 2: Upsample + Conv2d(3, padding=1) + IN + ReLU                                networks.py:408-414
     GAN_TRY(run_resample(cur, nullptr, n, H3, W3, 256, 1, 0, c->u1, st));
