@@ -1179,18 +1179,6 @@ __global__ void __launch_bounds__(512) k_commit(int dslot, GrowShape S, IterP P,
     else commit_body<false>(D, S, P, f, s_dyn);
 }
 
-// the same kernel capped at 64 registers (experiment: OCTA_COMMIT_REGS=64; four CTAs of 256 threads per SM instead of two)
-__global__ void __launch_bounds__(256, 4) k_commit_r64(int dslot, GrowShape S, IterP P, int f) {
-    const GrowDev& D = c_dev[dslot];
-    extern __shared__ __align__(16) int s_dyn[];
-    const int g = blockIdx.x;
-    if (D.err[g]) return;
-    const int n_before = D.n_nodes[f][g];
-    const size_t need = (((size_t)n_before * 17 + 3) & ~(size_t)3) + 16 * (size_t)((n_before + 31) >> 5) + 64;
-    if (need <= (size_t)S.commit_smem && n_before + 2 * D.n_dict[g] < 0xfffe) commit_body<true>(D, S, P, f, s_dyn);
-    else commit_body<false>(D, S, P, f, s_dyn);
-}
-
 // ------------------------------------------------------------------------------------------
 // k_kill: one CTA per graph.  f = 0: satisfied O2 sinks -> CO2 sources (set order); f = 1: CO2 removal
 // ------------------------------------------------------------------------------------------
@@ -1583,7 +1571,6 @@ constexpr int KD_SMEM_BYTES = 208 * 1024;        // + ~17 KB static: scan / redu
 
 int prepare_kernels(const GrowShape& S) {
     cudaError_t e = cudaFuncSetAttribute(k_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)commit_smem_bytes(S));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_commit_r64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)commit_smem_bytes(S));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_kdbuild, cudaFuncAttributeMaxDynamicSharedMemorySize, KD_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_kdbuild_list, cudaFuncAttributeMaxDynamicSharedMemorySize, KD_SMEM_BYTES);
     // Diagnostics (OCTA_CARVEOUT=1): every growth kernel asks for the largest shared-memory carve-out, so that CTAs of different
@@ -1702,9 +1689,7 @@ void launch_iteration(int dslot, const GrowShape& S, const int commit_smem[2], c
         static const int commit_threads = [] { const char* e = getenv("OCTA_COMMIT_THREADS"); const int v = e ? atoi(e) : 0; return (v == 128 || v == 256 || v == 512) ? v : 256; }();
         GrowShape Sc = S;
         Sc.commit_smem = commit_smem[f];
-        static const bool commit_r64 = [] { const char* e = getenv("OCTA_COMMIT_REGS"); return e && atoi(e) == 64; }();
-        if (commit_r64) k_commit_r64<<<S.G, commit_threads > 256 ? 256 : commit_threads, (size_t)commit_smem[f], st>>>(dslot, Sc, P, f);
-        else k_commit<<<S.G, commit_threads, (size_t)commit_smem[f], st>>>(dslot, Sc, P, f);
+        k_commit<<<S.G, commit_threads, (size_t)commit_smem[f], st>>>(dslot, Sc, P, f);
         tick(st, 7 + 5 * f);
         if (f == 0) cudaStreamWaitEvent(st, ev.kd, 0);
         else { k_grid_build<<<dim3(S.G, 2), 1024, 0, st>>>(dslot, S, P, 3); count_launch(1); }
