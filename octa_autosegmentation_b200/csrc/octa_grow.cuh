@@ -94,7 +94,7 @@ struct GrowDev {
     unsigned int* cbits;  // k_commit scratch, [g][4][capN/32]: dirty / arrival / inter / tag bitmaps when the tree does not fit in shared memory
     int *hitj, *hl, *ta, *seq;
     int *kd_idx, *kd_posL, *kd_posR, *kd_rank, *kd_nodes;
-    // on-demand exact ball order: per graph "k_kill left the arterial kill to k_kill_fix" + its T; per iteration parity the list
+    // on-demand exact ball order: per graph "k_kill left the arterial kill to k_kdbuild_list" + its T; per iteration parity the list
     // of those graphs and its length
     int *kd_flag, *kill_T, *kill_H, *kd_list, *kd_nflag;   // kill_H: hits of the arterial kill (sorted list in `hl`), -1 = not available
     unsigned char* veto;

@@ -10,7 +10,9 @@
 //   k_eval          greenhouse.py:174-306   per-node growth proposal (all float64 math, parallel)
 //   k_commit        greenhouse.py:191,235-239,289,303-306 + arterial_tree.py:174-184
 //                   sequential replay in dict order: Python-RNG draws, node creation, Murray walk
-//   k_kill          greenhouse.py:99-123    kill-radius prune, O2 -> CO2 through a CPython-set emulation
+//   k_kill          greenhouse.py:99-123    kill-radius prune (bucket grids), O2 -> CO2 through a CPython-set emulation with an
+//                   order test; k_kdbuild_list builds cKDTree's index permutation for the graphs whose result depends on the
+//                   order inside a ball (element_mesh.py:136-137) and finishes their kill
 // Bit-level conventions are documented in octa_grow_math.cuh.  This TU is compiled with -fmad=false.
 #include "octa_common.h"
 #include <stdio.h>

@@ -73,3 +73,29 @@ def test_gan_host_helpers():
     assert gan_cli._resolution(cfg) == (608, 304, 0.002)
     assert gan_cli._resolution({"Test": {}}) == (304, 304, 0.0)
     assert Pipeline.buffer_sets(8) == 10 and Pipeline.buffer_sets(0) == 3 and Pipeline.buffer_sets(8, True) == 21
+
+
+def test_png_writer_stores_the_pixels_pil_stores(tmp_path):
+    """graph_io.png_bytes (zlib level 1, filter 0) against PIL: same pixels for 8-bit gray and 1-bit images, incl. odd widths."""
+    import io
+    import numpy as np
+    from PIL import Image
+    from octa_autosegmentation_b200 import graph_io
+    rs = np.random.RandomState(0)
+    for shape in [(1216, 1216), (304, 304), (7, 13), (1, 1)]:
+        gray = (rs.rand(*shape) * 255 * (rs.rand(*shape) > 0.5)).astype(np.uint8)
+        back = np.array(Image.open(io.BytesIO(graph_io.png_bytes(gray))))
+        assert back.dtype == np.uint8 and np.array_equal(back, gray)
+        bits = np.array(Image.fromarray(gray).convert("1"))
+        im = Image.open(io.BytesIO(graph_io.png_bytes(bits)))
+        assert im.mode == "1" and np.array_equal(np.array(im), bits)
+    p = tmp_path / "x.png"
+    graph_io.save_png(str(p), gray)
+    assert np.array_equal(np.array(Image.open(p)), gray)
+
+
+def test_bench_configs_module_and_buffer_sets():
+    import bench_configs
+    from octa_autosegmentation_b200.pipeline import Pipeline
+    assert all(callable(getattr(bench_configs, "run_config%d" % k)) for k in (3, 4, 5))
+    assert Pipeline.buffer_sets(7, True, 1) == 9 and Pipeline.buffer_sets(7, False) == 9 and Pipeline.buffer_sets(7, True) == 20
