@@ -174,6 +174,17 @@ int octa_format_csv(const double* edges7, int64_t n_edges, char* buf, size_t cap
 /* Parses CSV text; returns the number of data rows (>= 0) or a negative OCTA_E_* code.  Rows beyond cap_edges
  * are counted but not stored. */
 int64_t octa_parse_csv(const char* text, size_t len, double* edges7_out, int64_t cap_edges);
+/* The same files for a whole batch, written ON THE DEVICE (the host writer costs 3.7 ms of a core per docker-config graph, more
+ * than the GPU needs to grow it): edges7_dev [E][7] with graph g owning the rows edge_offsets_host[g] .. [g+1].  text_dev
+ * (text_cap bytes; octa_format_csv_text_cap gives the bound) receives the files back to back, text_offsets_dev[0..n_graphs]
+ * their byte offsets, fallback_dev[g] != 0 marks a graph with a cell the device formatters do not cover (magnitudes outside the
+ * unit cube's, a radius outside [1e-4, 1) or a power of two): its text region is undefined and the caller formats that graph with
+ * octa_format_csv.  Everything is enqueued on `stream`; nothing is synchronised. */
+size_t octa_format_csv_workspace_bytes(int n_graphs, int64_t n_edges);
+size_t octa_format_csv_text_cap(int n_graphs, int64_t n_edges);
+int octa_format_csv_batch_dev(const double* edges7_dev, const int64_t* edge_offsets_host, int n_graphs, char* text_dev,
+                              size_t text_cap, int64_t* text_offsets_dev, int32_t* fallback_dev, void* workspace_dev,
+                              size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * GAN contrast adaptation (BASELINE config #5) -- replaces the generator forward behind

@@ -109,3 +109,16 @@ extern "C" int octa_test_kd_indices_gpu(const double* x, const double* y, const 
 extern "C" int octa_test_kd_ranks_gpu_smem(const double* x, const double* y, const double* z, int n, int* rank_out) {
     return kd_indices_gpu(x, y, z, n, rank_out, 1);
 }
+
+// The cell formatters the DEVICE CSV writer uses (host build of the same code): text into out (>= 128 bytes), returns the length
+// or -1 when the formatter declines (generic host path).
+#include "octa_csvfmt.cuh"
+extern "C" int octa_test_csvfmt_array3(const double* v3, char* out) { return octa::csvfmt::array3(out, v3); }
+extern "C" int octa_test_csvfmt_repr(double x, char* out) { return octa::csvfmt::repr_unit(out, x); }
+// batch forms for the randomized tests: n values -> lengths (or -1) and texts at stride 128
+extern "C" void octa_test_csvfmt_repr_many(const double* x, int64_t n, char* out, int* len) {
+    for (int64_t i = 0; i < n; ++i) len[i] = octa::csvfmt::repr_unit(out + 128 * i, x[i]);
+}
+extern "C" void octa_test_csvfmt_array3_many(const double* v, int64_t n, char* out, int* len) {
+    for (int64_t i = 0; i < n; ++i) len[i] = octa::csvfmt::array3(out + 128 * i, v + 3 * i);
+}

@@ -92,3 +92,28 @@ def save_png(path: str, image: np.ndarray) -> None:
         return
     with open(path, "wb") as f:
         f.write(png_bytes(image))
+
+
+def csv_batch_device(edges_dev, offsets, text_dev, text_offsets_dev, fallback_dev, workspace, stream=None):
+    """Device writer (octa_format_csv_batch_dev): the CSV files of a batch, back to back, into `text_dev` (uint8 CUDA tensor);
+    `text_offsets_dev` int64 [n+1], `fallback_dev` int32 [n] (!= 0: format that graph with csv_bytes).  Enqueued on `stream`."""
+    import torch
+    L = _lib.lib()
+    offs = np.ascontiguousarray(offsets, dtype=np.int64)
+    n = len(offs) - 1
+    L.octa_format_csv_batch_dev.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    st = torch.cuda.current_stream() if stream is None else stream
+    _lib.check(L.octa_format_csv_batch_dev(edges_dev.data_ptr(), offs.ctypes.data, n, text_dev.data_ptr(), text_dev.numel(),
+                                           text_offsets_dev.data_ptr(), fallback_dev.data_ptr(), workspace.data_ptr(), workspace.numel(),
+                                           ctypes.c_void_p(st.cuda_stream)))
+
+
+def csv_device_sizes(n_graphs: int, n_edges: int):
+    """(workspace bytes, text capacity bytes) of csv_batch_device."""
+    L = _lib.lib()
+    L.octa_format_csv_workspace_bytes.argtypes = [ctypes.c_int, ctypes.c_int64]
+    L.octa_format_csv_workspace_bytes.restype = ctypes.c_size_t
+    L.octa_format_csv_text_cap.argtypes = [ctypes.c_int, ctypes.c_int64]
+    L.octa_format_csv_text_cap.restype = ctypes.c_size_t
+    return int(L.octa_format_csv_workspace_bytes(n_graphs, n_edges)), int(L.octa_format_csv_text_cap(n_graphs, n_edges))

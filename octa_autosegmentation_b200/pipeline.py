@@ -42,6 +42,12 @@ class Pipeline:
         self._h2d_done = {}
         self._csv_pool = None
         self.edge_cap = 24000      # rows reserved per sample in the pinned edge buffer (docker config: ~13 k)
+        # Who writes the CSV text (same bytes either way, tests/test_csv_device_gpu.py): the host writer costs 3.7 ms of a core per
+        # docker-config graph -- 2.4 cores per GPU at 650 graphs/s --, the device writer ~1 ms of GPU time and 90 MB of D2H per batch
+        # of 64.  Measured on one B200: 16 cores 646 (host) vs 631 (device) graphs/s, 4 cores (the share of a rank on an 8-GPU box)
+        # 593 vs 621: the device writes when this process has fewer than 8 cores.  OCTA_CSV=host|device overrides.
+        mode = os.environ.get("OCTA_CSV", "auto")
+        self.device_csv = (mode == "device") or (mode != "host" and ncores < 8)
 
     def _tensor(self, key, shape, dtype, pinned=False):
         t = self._buf.get(key)
@@ -161,7 +167,28 @@ class Pipeline:
                         vol_h.copy_(out["volume"], non_blocking=True)
                         out["_vol_host"] = vol_h
                         out["d2h_bytes"] += int(vol_h.numel() * 2)
-                    if csv:
+                    if csv and self.device_csv:
+                        # the files of the batch are written on the device (csrc/octa_csv_dev.cu) and come back as text; the host
+                        # only slices them (graphs the device formatters decline are formatted by the host writer in _finish)
+                        rows = max(E, cap)
+                        ws_b, cap_b = graph_io.csv_device_sizes(n, rows)
+                        text_dev = self._tensor("csv_text" + sfx, (cap_b,), torch.uint8)
+                        toff_dev = self._tensor("csv_off" + sfx, (n + 1,), torch.int64)
+                        fb_dev = self._tensor("csv_fb" + sfx, (n,), torch.int32)
+                        ws_c = self._tensor("csv_ws" + sfx, (ws_b,), torch.uint8)
+                        graph_io.csv_batch_device(edges_dev, offs, text_dev, toff_dev, fb_dev, ws_c, stream)
+                        # (a row is 94 bytes; files that end beyond the copied part fall back to the host writer)
+                        host_cap = min(cap_b, 104 * E + 64 * n)
+                        self._tensor("csv_text_host" + hsfx, (min(cap_b, 104 * rows + 64 * n),), torch.uint8, pinned=True)   # sized once, for the capacity
+                        text_h = self._tensor("csv_text_host" + hsfx, (host_cap,), torch.uint8, pinned=True)
+                        toff_h = self._tensor("csv_off_host" + hsfx, (n + 1,), torch.int64, pinned=True)
+                        fb_h = self._tensor("csv_fb_host" + hsfx, (n,), torch.int32, pinned=True)
+                        text_h.copy_(text_dev[:host_cap], non_blocking=True)
+                        toff_h.copy_(toff_dev, non_blocking=True)
+                        fb_h.copy_(fb_dev, non_blocking=True)
+                        out["_csv_dev"] = (text_h, toff_h, fb_h, he, offs, n)
+                        out["d2h_bytes"] += int(host_cap)
+                    elif csv:
                         if self._csv_pool is None:                                          # one pool for the pipeline's lifetime
                             self._csv_pool = cf.ThreadPoolExecutor(max_workers=self.host_threads)
                         # ctypes releases the GIL; the text is collected in _finish
@@ -189,6 +216,13 @@ class Pipeline:
         t_r = time.perf_counter()
         if "_csv" in out:
             out["csv"] = [f.result() for f in out.pop("_csv")]
+        if "_csv_dev" in out:
+            text_h, toff_h, fb_h, he, offs, n = out.pop("_csv_dev")
+            out["ready"].synchronize()
+            t, o, fb = text_h.numpy(), toff_h.numpy(), fb_h.numpy()
+            out["csv"] = [graph_io.csv_bytes(he[offs[i]:offs[i + 1]]) if (fb[i] or o[i + 1] > len(t)) else t[o[i]:o[i + 1]].tobytes()
+                          for i in range(n)]
+            out["csv_host_fallbacks"] = int(sum(1 for i in range(n) if fb[i] or o[i + 1] > len(t)))
         if "trace" in out:
             out["trace"].update(t_fin0=t_f0, t_ready=t_r, t_fin1=time.perf_counter())
         return out

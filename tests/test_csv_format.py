@@ -100,3 +100,52 @@ def test_small_caller_buffer_is_reported_not_overrun():
         assert buf.raw[cap:] == b"\xee" * 16                       # nothing written past the capacity
     buf = ctypes.create_string_buffer(len(want))
     assert L.octa_format_csv(e7.ctypes.data, len(e7), buf, len(want), ctypes.byref(n)) == 0 and buf.raw[:n.value] == want
+
+
+# ----------------------------------------------------------------------------------------------------------------------------
+# The cell formatters of the DEVICE writer (csrc/octa_csvfmt.cuh, host build through the test hooks): same strings as numpy's
+# str(ndarray) and CPython's repr(float); what they decline (-1) goes to the host writer.
+# ----------------------------------------------------------------------------------------------------------------------------
+def _fmt_many(fn_name, values, width):
+    import ctypes
+    from octa_autosegmentation_b200 import _lib
+    L = _lib.lib()
+    v = np.ascontiguousarray(values, dtype=np.float64)
+    n = len(v) // width if v.ndim == 1 and width > 1 else len(v)
+    out = ctypes.create_string_buffer(128 * n)
+    ln = np.zeros(n, dtype=np.int32)
+    getattr(L, fn_name)(v.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(n), out, ln.ctypes.data_as(ctypes.c_void_p))
+    raw = out.raw
+    return [raw[128 * i:128 * i + ln[i]].decode() if ln[i] >= 0 else None for i in range(n)]
+
+
+def test_device_formatter_of_the_radius_equals_python_repr():
+    rs = np.random.RandomState(1)
+    xs = np.concatenate([10 ** rs.uniform(-4, 0, 150000), rs.uniform(1e-4, 1, 50000),
+                         np.round(rs.uniform(1e-4, 1, 50000), rs.randint(1, 16)),
+                         np.nextafter(np.round(rs.uniform(1e-4, 1, 20000), 6), 1), np.nextafter(np.round(rs.uniform(1e-4, 1, 20000), 5), 0),
+                         [0.0025 / 3, 0.0025, 0.1, 0.3, 0.001, 0.0001, 0.09999999999999999, 0.9999999999999999, 0.5, 0.25]])
+    xs = xs[(xs >= 1e-4) & (xs < 1)]
+    got = _fmt_many("octa_test_csvfmt_repr_many", xs, 1)
+    declined = set()
+    for x, g in zip(xs, got):
+        if g is None:
+            declined.add(float(x))
+            assert np.frexp(x)[0] == 0.5                  # only powers of two are declined inside the range
+        else:
+            assert g == repr(float(x))
+    assert len(declined) <= 14
+    assert _fmt_many("octa_test_csvfmt_repr_many", np.array([1.0, 2.5, 5e-5, 0.0, -0.01]), 1) == [None] * 5
+
+
+def test_device_formatter_of_the_position_cells_equals_numpy_str():
+    rs = np.random.RandomState(2)
+    vs = np.concatenate([rs.uniform(0, 1, (60000, 3)), rs.uniform(-1, 1, (20000, 3)) * 10 ** rs.uniform(-6, 2, (20000, 1)),
+                         rs.uniform(0, 1, (20000, 3)) * np.array([1, 1, 1e-3]), np.round(rs.uniform(0, 1, (20000, 3)), rs.randint(0, 9))])
+    vs[rs.randint(0, len(vs), 1000), rs.randint(0, 3, 1000)] = 0.0
+    got = _fmt_many("octa_test_csvfmt_array3_many", vs.reshape(-1), 3)
+    for v, g in zip(vs, got):
+        assert g is None or g == str(v)
+    assert sum(g is None for g in got) == 0
+    assert _fmt_many("octa_test_csvfmt_array3_many", np.array([3.0e9, 0.1, 0.2, np.inf, 0.0, 0.0]), 3) == [None, None]
+    assert _fmt_many("octa_test_csvfmt_array3_many", np.array([3.0e7, 0.1, 0.2]), 3) == [str(np.array([3.0e7, 0.1, 0.2]))]
