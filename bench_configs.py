@@ -94,7 +94,7 @@ def run_config3(args, pin_cores=None):
         futs = []
         for bi, out in enumerate(pipe.run_pipelined(batches, d2h=True, csv=True, in_flight=args.in_flight, extra_slots=4)):
             for i, seed in enumerate(batches[bi]):
-                futs.append((seed, writers.submit(write, seed, out["csv"][i], np.array(out["label_host"][i]), np.array(out["image_host"][i]))))
+                futs.append((seed, writers.submit(write, seed, bytes(out["csv"][i]), np.array(out["label_host"][i]), np.array(out["image_host"][i]))))
                 tables[seed] = np.concatenate(out["graphs"][i]).copy() if "graphs" in out else None
         done = [(seed, f.result()) for seed, f in futs]
     t_files = time.perf_counter() - t0

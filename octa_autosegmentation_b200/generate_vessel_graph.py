@@ -93,7 +93,7 @@ def generate(config: dict, seeds, batch: int = 32, in_flight: int = 8, writer_th
             for i in range(n):
                 img = np.array(out["image_host"][i]) if out_cfg["save_2D_image"] else None        # copies: the pinned buffers are recycled
                 vol = np.array(out["volume_host"][i]) if save3d else None
-                futs.append(writers.submit(write_sample, config, out["csv"][i] if write_csv else None, img, vol))
+                futs.append(writers.submit(write_sample, config, bytes(out["csv"][i]) if write_csv else None, img, vol))      # (copy: may be a view of a pinned buffer)
                 if gather:
                     tables[batches[bi][i]] = np.concatenate(out["graphs"][i]).copy()
             if save3d:                                 # 157 MB per sample: let the files land before the next batch's copies

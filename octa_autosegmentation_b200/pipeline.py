@@ -44,7 +44,7 @@ class Pipeline:
         self.edge_cap = 24000      # rows reserved per sample in the pinned edge buffer (docker config: ~13 k)
         # Who writes the CSV text (same bytes either way, tests/test_csv_device_gpu.py): the host writer costs 3.7 ms of a core per
         # docker-config graph -- 2.4 cores per GPU at 650 graphs/s --, the device writer ~1 ms of GPU time and 90 MB of D2H per batch
-        # of 64.  Measured on one B200: 16 cores 646 (host) vs 631 (device) graphs/s, 4 cores (the share of a rank on an 8-GPU box)
+        # of 64.  Measured on one B200: 16 cores 649 (host) vs 638 (device) graphs/s, 4 cores (the share of a rank on an 8-GPU box)
         # 593 vs 621: the device writes when this process has fewer than 8 cores.  OCTA_CSV=host|device overrides.
         mode = os.environ.get("OCTA_CSV", "auto")
         self.device_csv = (mode == "device") or (mode != "host" and ncores < 8)
@@ -220,7 +220,9 @@ class Pipeline:
             text_h, toff_h, fb_h, he, offs, n = out.pop("_csv_dev")
             out["ready"].synchronize()
             t, o, fb = text_h.numpy(), toff_h.numpy(), fb_h.numpy()
-            out["csv"] = [graph_io.csv_bytes(he[offs[i]:offs[i + 1]]) if (fb[i] or o[i + 1] > len(t)) else t[o[i]:o[i + 1]].tobytes()
+            # views of the pinned text (bytes-like: ==, len, hashlib, file.write; valid as long as label_host / image_host are --
+            # bytes(view) makes a copy that outlives the buffer set)
+            out["csv"] = [graph_io.csv_bytes(he[offs[i]:offs[i + 1]]) if (fb[i] or o[i + 1] > len(t)) else t[o[i]:o[i + 1]].data
                           for i in range(n)]
             out["csv_host_fallbacks"] = int(sum(1 for i in range(n) if fb[i] or o[i + 1] > len(t)))
         if "trace" in out:

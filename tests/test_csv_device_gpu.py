@@ -68,5 +68,5 @@ def test_pipeline_csv_is_the_same_with_both_writers(monkeypatch):
         monkeypatch.setenv("OCTA_CSV", mode)
         pipe = Pipeline(cfg, volume_dims=[152, 152, 8], label_res=(304, 304), image_res=(152, 152))
         assert pipe.device_csv == (mode == "device")
-        outs[mode] = [list(o["csv"]) for o in pipe.run_pipelined(seeds, in_flight=2)]
+        outs[mode] = [[bytes(c) for c in o["csv"]] for o in pipe.run_pipelined(seeds, in_flight=2)]
     assert outs["device"] == outs["host"] and all(len(c) > 1000 for b in outs["device"] for c in b)
