@@ -44,6 +44,7 @@ struct GrowShape {
     int G, capN, capS, Nmax, pycap;
     int exact_ball_order;   // cKDTree's index permutation for the O2->CO2 insertion order: 2 = built on demand (exact, default), 1 = built every iteration (exact), 0 = list-index order instead (diagnostics)
     int commit_smem; // bytes of dynamic shared memory of k_commit (tree mirror + decision records)
+    int kill_rcap;   // hits per call k_kill keeps as a sorted list (<= KILL_RCAP = 4096; beyond: block scans over the sink list; tests shrink it)
 };
 
 struct GrowDev {

@@ -511,6 +511,8 @@ extern "C" int octa_grow_create(const OctaGrowConfig* cfg, int max_graphs, void*
         const char* bo = getenv("OCTA_BALL_ORDER");      // "index" = list-index order (diagnostics); default exact
         S.exact_ball_order = (bo && strcmp(bo, "index") == 0) ? 0 : (bo && strcmp(bo, "always") == 0) ? 1 : 2;
     }
+    S.kill_rcap = 4096;
+    if (const char* e = getenv("OCTA_KILL_RCAP")) { const int v = atoi(e); if (v >= 0 && v <= 4096) S.kill_rcap = v; }   // tests: force the scan fallback
     S.commit_smem = 224 * 1024;                       // of the 227 KB a CTA may own on sm_100
     if (const char* e = getenv("OCTA_COMMIT_SMEM")) {  // tests: a small budget forces k_commit onto the global-memory tree view
         const int v = atoi(e);

@@ -1413,7 +1413,7 @@ __global__ void __launch_bounds__(1024) k_kill(int dslot, GrowShape S, IterP P, 
         }
       }
         __syncthreads();
-        if (s_nh <= KILL_RCAP) {     // hits in list order: rank of each position among the hit positions (tens of hits)
+        if (s_nh <= S.kill_rcap) {   // hits in list order: rank of each position among the hit positions (tens of hits)
             H = s_nh;
             for (int k = tid; k < H; k += blockDim.x) {
                 const int v = s_hl[k];
@@ -1435,7 +1435,7 @@ __global__ void __launch_bounds__(1024) k_kill(int dslot, GrowShape S, IterP P, 
                     H += total;
                 }
                 __syncthreads();
-                if (H > KILL_RCAP) H = -H - 1;      // (compaction by scans; the veto below uses the count)
+                if (H > S.kill_rcap) H = -H - 1;    // (compaction by scans; the veto below uses the count)
             }
             const bool listed = H >= 0;
             if (!listed) H = -H - 1;

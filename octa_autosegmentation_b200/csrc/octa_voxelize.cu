@@ -55,6 +55,7 @@ struct VoxGeom {
     double c[3];     // pos_correction
     double zfix;     // image_dim[2]//2 as double (ignore_z)
     int ignore_z;
+    int slowcap;     // usable entries of the column kernel's deferred-cell queue (<= SLOWCAP; tests shrink it to reach the overflow path)
     double min_radius, max_radius;
 };
 
@@ -801,7 +802,7 @@ vox_col_kernel(const VoxEdge* __restrict__ prep, const int64_t* __restrict__ edg
                     if (!top && (!(fr >= eps) || fr > om)) {               // within eps of an integer (or NaN): float64 decides
                         if (!(v <= -eps)) {
                             const int slot = atomicAdd(&s_nslow, 1);
-                            if (slot < SLOWCAP) s_slow[slot] = make_int2(eidx, cell);
+                            if (slot < g.slowcap) s_slow[slot] = make_int2(eidx, cell);
                             else { const unsigned short mark = 0xffffu; asm volatile("st.shared.u16 [%0], %1;" ::"r"(acc_s + 2u * cell), "h"(mark)); }
                         }
                         continue;
@@ -819,14 +820,14 @@ vox_col_kernel(const VoxEdge* __restrict__ prep, const int64_t* __restrict__ edg
     }
     __syncthreads();
     {   // the deferred cells of the CTA: float64 fast path / exact chain; two entries may name the same cell -> CAS max
-        const int ns = imin(s_nslow, SLOWCAP);
+        const int ns = imin(s_nslow, g.slowcap);
         for (int i = threadIdx.x; i < ns; i += NT) {
             const int2 ent = s_slow[i];
             const int cx = ent.y / xstride, r = ent.y - cx * xstride, cy = r / ystride, z = r - cy * ystride;
             const uint32_t v = slow_voxel_q(ge + ent.x, t0x + cx, t0y + cy, t0z + z);
             if (v) tile_max(acc + ent.y, v);
         }
-        if (s_nslow > SLOWCAP) {                      // (never seen) marked cells: recomputed from every edge of the tile
+        if (s_nslow > g.slowcap) {                    // (never seen in real graphs) marked cells: recomputed from every edge of the tile
             __syncthreads();
             resolve_marked(ge, lst + beg, nlist, bl, nbig, acc, tile_elems, t0x, t0y, t0z, xstride, ystride);
         }
@@ -888,6 +889,8 @@ int make_geom(const int dims[3], const OctaVoxOpts* opts, VoxGeom* g) {
     g->ignore_z = opts ? opts->ignore_z : 0;
     g->min_radius = opts ? opts->min_radius : 0.0;
     g->max_radius = opts ? opts->max_radius : 1.0;
+    g->slowcap = 160;
+    if (const char* ev = getenv("OCTA_VOX_SLOWCAP")) { const int v = atoi(ev); if (v >= 0 && v <= 160) g->slowcap = v; }   // test knob
     g->T[1] = TILE_Y;
     if (const char* ev = getenv("OCTA_VOX_TILE_Y")) { const int v = atoi(ev); if (v == 8 || v == 16 || v == 32) g->T[1] = v; }   // tuning knob
     g->T[2] = g->D[2] < TILE_Z_MAX ? g->D[2] : TILE_Z_MAX;
@@ -994,7 +997,8 @@ extern "C" int octa_voxelize_batch_dev(const double* edges7_dev, const int64_t* 
         smem_set = smem;
     }
     // OCTA_VOX_KERNEL=rows selects the row-dealing kernel of round 1 (kept for A/B measurements; bit-identical results)
-    static const bool use_rows = [] { const char* e = getenv("OCTA_VOX_KERNEL"); return e && e[0] == 'r'; }();
+    const char* vk = getenv("OCTA_VOX_KERNEL");
+    const bool use_rows = vk && vk[0] == 'r';
     dim3 grid((unsigned)(g.nt[1] * g.nt[2]), (unsigned)g.nt[0], (unsigned)n_graphs);
     if (use_rows)
         vox_tile_kernel<<<grid, VOX_THREADS, smem, stream>>>(w.prep, w.edge_offsets, g, w.tile_start, w.tile_edges,

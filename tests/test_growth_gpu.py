@@ -229,3 +229,19 @@ def test_repeated_mode_name_vs_oracle(growth):
     the oracle is pinned to the reference on this config by tests/test_oracle_growth.py."""
     from test_oracle_growth import repeated_name_config
     compare_with_oracle(growth, repeated_name_config(), [3, 4])
+
+
+def test_kill_scan_fallback_equals_hit_list_path(monkeypatch):
+    """k_kill keeps the hit positions of a call as a sorted list (<= 4096); a longer list falls back to block scans over the sink
+    list.  OCTA_KILL_RCAP=2 sends nearly every call down the fallback: same graphs, byte for byte."""
+    from octa_autosegmentation_b200 import graph_io, growth
+    from octa_autosegmentation_b200.config import default_config
+    cfg = default_config()
+    for m, i in zip(cfg["Greenhouse"]["modes"], (30, 40)):
+        m["I"] = i
+    seeds = [3, 4, 5, 6]
+    want, _, _ = growth.grow_batch(cfg, seeds)
+    monkeypatch.setenv("OCTA_KILL_RCAP", "2")
+    got, _, _ = growth.grow_batch(cfg, seeds)
+    for a, b in zip(want, got):
+        assert graph_io.csv_bytes(np.concatenate(a)) == graph_io.csv_bytes(np.concatenate(b))

@@ -117,3 +117,18 @@ def test_dropout_matches_oracle_host_logic(t2i):
     got2, _ = t2i.voxelize_forest(rows, [128, 128, 4], radius_list=rl, min_radius=0.001, blackdict=dict(bd))
     ref2, _ = vox_oracle.voxelize_forest(rows, [128, 128, 4], min_radius=0.001, blackdict=dict(bd))
     assert np.array_equal(got2, ref2) and len(rl) > 0 and min(rl) >= 0.001
+
+
+@pytest.mark.parametrize("knob", [{"OCTA_VOX_SLOWCAP": "0"}, {"OCTA_VOX_SLOWCAP": "3"}, {"OCTA_VOX_TILE_Y": "8"}, {"OCTA_VOX_KERNEL": "rows"}])
+def test_fallback_paths_give_the_same_volume(t2i, monkeypatch, knob):
+    """The paths real graphs never (or only by choice) take: a full deferred-cell queue (cells are marked and recomputed from every
+    edge of the tile), half-size tiles with four warps, and the row kernel of round 1 -- all bit-identical to the reference digest."""
+    gold = json.load(open(os.path.join(GOLDEN, "vox_docker_s0.json")))
+    e7 = rows_to_edges7(load_graph_rows("graph_docker_s0.csv.gz"))
+    for k, v in knob.items():
+        monkeypatch.setenv(k, v)
+    vol = t2i.voxelize_edges(e7, [304, 304, 4])
+    assert hashlib.sha256(vol.tobytes()).hexdigest() == gold["304x304x4"]["sha256"]
+    if "1216x1216x16" in gold:
+        vol = t2i.voxelize_edges(e7, [1216, 1216, 16])
+        assert hashlib.sha256(vol.tobytes()).hexdigest() == gold["1216x1216x16"]["sha256"]
