@@ -1528,6 +1528,91 @@ __global__ void __launch_bounds__(1024) k_kdbuild(int dslot, GrowShape S, int sm
 }
 
 // on-demand variant (S.exact_ball_order == 2): the CTAs walk the work list k_kill filled in this iteration
+// The build of one graph keeps ONE SM's issue slots 46 % busy for ~350 us and sits on the critical path of the iteration, while
+// a subtree of the kd tree is independent of its siblings: the split form runs the first KD_TOP_LEVELS levels in one CTA
+// (k_kd_top), the subtrees below them in one CTA each (k_kd_sub: 2^KD_TOP_LEVELS CTAs per graph, each with its own shared memory
+// and all 32 warps), and k_kd_fix finishes the kill (and redoes a graph by the one-CTA build if a partial build bailed out).
+// Per graph the scratch arrays double as hand-over space: kd_posL = the permutation after the top levels (16-bit), kd_posR =
+// {number of subtree roots or -1, 3 ints per root, ..., [13] = redo flag}.
+constexpr int KD_TOP_LEVELS = 2;
+constexpr int KD_SUBS = 1 << KD_TOP_LEVELS;
+
+__global__ void __launch_bounds__(1024) k_kd_top(int dslot, GrowShape S, IterP P, int smem_bytes) {
+    const GrowDev& D = c_dev[dslot];
+    extern __shared__ __align__(16) char s_kd[];
+    __shared__ int s_ws[kdpar::WS_INTS];
+    __shared__ double s_wd[kdpar::WD_DOUBLES];
+    const int parity = P.iter & 1;
+    const int n = D.kd_nflag[parity];
+    for (int q = blockIdx.x; q < n; q += gridDim.x) {
+        const int g = D.kd_list[parity * S.G + q];
+        const size_t sb = (size_t)g * S.capS;
+        const int Sn = D.n_s[0][g];
+        int* top = D.kd_posR + sb;
+        if (threadIdx.x == 0) top[13] = 0;
+        if ((size_t)Sn * 12 + 64 <= (size_t)smem_bytes && Sn < 65536)
+            kdsm::build_top_block(D.sx[0] + sb, D.sy[0] + sb, D.sz[0] + sb, Sn, KD_TOP_LEVELS, D.kd_rank + sb,
+                                  reinterpret_cast<unsigned short*>(D.kd_posL + sb), top, s_kd, D.kd_nodes + sb, D.kd_nodes + sb + S.capS / 2, s_ws, s_wd);
+        else if (threadIdx.x == 0) top[0] = -1;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_kd_sub(int dslot, GrowShape S, IterP P, int smem_bytes) {
+    const GrowDev& D = c_dev[dslot];
+    extern __shared__ __align__(16) char s_kd[];
+    __shared__ int s_ws[kdpar::WS_INTS];
+    __shared__ double s_wd[kdpar::WD_DOUBLES];
+    const int parity = P.iter & 1;
+    const int n = D.kd_nflag[parity];
+    const int sub = blockIdx.x;
+    for (int q = blockIdx.y; q < n; q += gridDim.y) {
+        const int g = D.kd_list[parity * S.G + q];
+        const size_t sb = (size_t)g * S.capS;
+        int* top = D.kd_posR + sb;
+        const int cnt = top[0];
+        if (cnt < 0 || sub >= cnt) continue;                 // (block-uniform)
+        const int s = top[1 + 3 * sub], e = top[2 + 3 * sub];
+        bool ok = (size_t)(e - s) * 12 + 64 <= (size_t)smem_bytes;
+        if (ok) ok = kdsm::build_sub_block(D.sx[0] + sb, D.sy[0] + sb, D.sz[0] + sb, s, e, D.kd_rank + sb,
+                                           reinterpret_cast<const unsigned short*>(D.kd_posL + sb), s_kd,
+                                           D.kd_nodes + sb + (size_t)sub * (S.capS / KD_SUBS), D.kd_nodes + sb + (size_t)sub * (S.capS / KD_SUBS) + S.capS / (2 * KD_SUBS),
+                                           s_ws, s_wd);
+        if (!ok && threadIdx.x == 0) top[13] = 1;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_kd_fix(int dslot, GrowShape S, IterP P, int smem_bytes) {
+    const GrowDev& D = c_dev[dslot];
+    extern __shared__ __align__(16) char s_kd[];
+    __shared__ int s_ws[kdpar::WS_INTS];
+    __shared__ double s_wd[kdpar::WD_DOUBLES];
+    const int parity = P.iter & 1;
+    if (blockIdx.x == 0 && threadIdx.x == 0) D.kd_nflag[parity ^ 1] = 0;      // the next iteration's list starts empty
+    const int n = D.kd_nflag[parity];
+    for (int q = blockIdx.x; q < n; q += gridDim.x) {
+        const int g = D.kd_list[parity * S.G + q];
+        const size_t sb = (size_t)g * S.capS;
+        const int* top = D.kd_posR + sb;
+        const bool redo = top[0] < 0 || top[13];            // (block-uniform) a partial build bailed out: the one-CTA build
+        __syncthreads();                                    // (its scratch includes `top`: every thread has read the flags)
+        if (redo) {
+            kdbuild_graph(D, S, smem_bytes, g, s_kd, s_ws, s_wd);
+            __threadfence_block();
+        }
+        __syncthreads();
+        if (!D.err[g] && D.kd_flag[g]) {
+            KillShared* ks = reinterpret_cast<KillShared*>(s_kd);
+            kill_convert<false>(D, S, g, D.kill_T[g], D.kd_rank + sb, ks);
+            kill_compact(D, S, P, 0, g, D.n_s[0][g], true, D.kill_H[g], D.hl + sb, reinterpret_cast<int*>(ks->th));
+            __syncthreads();
+            if (threadIdx.x == 0) D.kd_flag[g] = 0;
+        }
+        __syncthreads();
+    }
+}
+
 // ... and finishes the arterial kill of each listed graph right behind its own build (the conversion with the exact order inside
 // every ball, then the compaction of the sink list): one launch instead of two, and a graph does not wait for the slowest build
 // of the batch.  The set tables of the conversion live in the build's shared memory, which is idle by then.
@@ -1570,11 +1655,15 @@ int upload_dev_table(int dslot, const GrowDev& D, cudaStream_t st) {
 }
 
 constexpr int KD_SMEM_BYTES = 208 * 1024;        // + ~17 KB static: scan / reduction scratch
+constexpr int KD_SUB_SMEM_BYTES = 144 * 1024;    // a subtree below the top levels: a quarter of the list (12 000 sinks fit; larger: one-CTA build)
 
 int prepare_kernels(const GrowShape& S) {
     cudaError_t e = cudaFuncSetAttribute(k_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)commit_smem_bytes(S));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_kdbuild, cudaFuncAttributeMaxDynamicSharedMemorySize, KD_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_kdbuild_list, cudaFuncAttributeMaxDynamicSharedMemorySize, KD_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_kd_top, cudaFuncAttributeMaxDynamicSharedMemorySize, KD_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_kd_sub, cudaFuncAttributeMaxDynamicSharedMemorySize, KD_SUB_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_kd_fix, cudaFuncAttributeMaxDynamicSharedMemorySize, KD_SMEM_BYTES);
     // Diagnostics (OCTA_CARVEOUT=1): every growth kernel asks for the largest shared-memory carve-out, so that CTAs of different
     // kernels never wait for an SM to change its L1 / shared split.  Measured SLOWER (462 -> 443 graphs/s): the gather kernels
     // (k_assign, k_sink_tests, k_kill) lose their L1, which costs more than the extra co-residency gains.  Off by default.
@@ -1705,9 +1794,22 @@ void launch_iteration(int dslot, const GrowShape& S, const int commit_smem[2], c
             // exact cKDTree order on demand: permutation + conversion redone for the graphs k_kill listed (about a third of the
             // graph-iterations of the docker config); the CTAs of k_kdbuild_list own a whole SM's shared memory, so the launch is
             // half a batch wide and walks the list
-            k_kdbuild_list<<<(S.G + 1) / 2, 1024, KD_SMEM_BYTES, st>>>(dslot, S, P, KD_SMEM_BYTES);
-            tick(st, 14);
-            count_launch(1);
+            // OCTA_KD_SPLIT=1: the three-kernel form (top levels, four subtree CTAs per graph, fix).  Measured on one B200, 64 graphs:
+            // a loop ALONE takes 263 instead of 299 ms (the build leaves the critical path 36 % faster), but with 7 loops in flight
+            // -- where aggregate SM time and launches count, not the latency of one loop -- 628 instead of 645 graphs/s.  Default:
+            // the one-kernel form; the split is for latency-bound use (single batches).
+            static const bool kd_split = [] { const char* e = getenv("OCTA_KD_SPLIT"); return e && e[0] == '1'; }();
+            if (kd_split) {
+                k_kd_top<<<(S.G + 1) / 2, 1024, KD_SMEM_BYTES, st>>>(dslot, S, P, KD_SMEM_BYTES);
+                k_kd_sub<<<dim3(KD_SUBS, (S.G + 1) / 2), 1024, KD_SUB_SMEM_BYTES, st>>>(dslot, S, P, KD_SUB_SMEM_BYTES);
+                k_kd_fix<<<(S.G + 1) / 2, 1024, KD_SMEM_BYTES, st>>>(dslot, S, P, KD_SMEM_BYTES);
+                tick(st, 14);
+                count_launch(3);
+            } else {
+                k_kdbuild_list<<<(S.G + 1) / 2, 1024, KD_SMEM_BYTES, st>>>(dslot, S, P, KD_SMEM_BYTES);
+                tick(st, 14);
+                count_launch(1);
+            }
         }
         if (f == 0) {
             cudaEventRecord(ev.killa, st);

@@ -545,6 +545,54 @@ static __device__ int build_node_sm(const View& M, const double* const xyz[3], i
 // Whole build by one CTA of THREADS threads; writes rank[point] = position in cKDTree's `indices`.
 // smem: 12*n bytes (+ padding), nodes_a/nodes_b: global scratch of 3*(n/8+4) ints each.  Returns false (on every
 // thread) if the caller has to fall back.
+// Levels of the build over the node list `cur` (ncur nodes of 3 ints: start, end, dimension the key array holds), at most
+// max_levels of them: a node is handled by 32 / 16 / 8 / 4 warps on the first four levels of the call, by one warp below.
+// Returns the number of nodes left for the next level (their list is `cur` again), or -1 when the caller has to fall back.
+static __device__ int run_levels(const View& M, const double* const xyz[3], int*& cur, int*& nxt, int ncur, int max_levels,
+                                 int* s_ws, double* s_wd, int* s_cnt, int* s_fail) {
+    const int tid = threadIdx.x;
+    int phase = 0;
+    for (int level = 0; ncur > 0 && level < max_levels; ++level) {
+        int nwarps = 32 >> level;
+        if (level > 5 || nwarps < 4) nwarps = 1;     // below 4 warps per node: one warp per node
+        const int ngroups = 32 / nwarps;
+        const int grp = (tid >> 5) / nwarps;
+        const int gt = tid - grp * nwarps * 32;
+        const int bar_id = 1 + grp;                  // <= 8 multi-warp groups -> ids 1..8
+        phase = 0;                                   // (groups were re-formed: restart the scan buffers' alternation)
+        for (int base = 0; base < ncur; base += ngroups) {
+            const int k = base + grp;
+            if (k < ncur) {
+                const int s = cur[3 * k], e = cur[3 * k + 1];
+                int dim = cur[3 * k + 2];
+                const int p = build_node_sm(M, xyz, s, e, &dim, gt, nwarps, bar_id, s_ws + (grp & 7) * 64, phase, s_wd + (grp & 7) * 192);
+                if (p == -2) { if (gt == 0) *s_fail = 1; }
+                else if (p >= 0 && gt == 0) {
+                    // children that are leaves need no visit
+                    const int nl = (p - s > kd::LEAFSIZE) ? 1 : 0, nr = (e - p > kd::LEAFSIZE) ? 1 : 0;
+                    if (nl + nr) {
+                        int o = atomicAdd(s_cnt, nl + nr);
+                        if (nl) { nxt[3 * o] = s; nxt[3 * o + 1] = p; nxt[3 * o + 2] = dim; ++o; }
+                        if (nr) { nxt[3 * o] = p; nxt[3 * o + 1] = e; nxt[3 * o + 2] = dim; }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        ncur = *s_cnt;
+        const int fail = *s_fail;
+        __syncthreads();
+        if (fail) return -1;
+        if (tid == 0) *s_cnt = 0;
+        int* t = cur; cur = nxt; nxt = t;
+        __syncthreads();
+    }
+    return ncur;
+}
+
+// Whole build by one CTA of THREADS threads; writes rank[point] = position in cKDTree's `indices`.
+// smem: 12*n bytes (+ padding), nodes_a/nodes_b: global scratch of 3*(n/8+4) ints each.  Returns false (on every
+// thread) if the caller has to fall back.
 static __device__ bool build_ranks_block(const double* x, const double* y, const double* z, int n, int* rank, char* smem,
                                          int* node_a, int* node_b, int* s_ws /*kdpar::WS_INTS*/, double* s_wd /*kdpar::WD_DOUBLES*/) {
     __shared__ int s_cnt, s_fail;
@@ -559,44 +607,55 @@ static __device__ bool build_ranks_block(const double* x, const double* y, const
     int* nxt = node_b;
     if (tid == 0) { cur[0] = 0; cur[1] = n; cur[2] = -1; s_cnt = 0; s_fail = 0; }
     __syncthreads();
-    int ncur = 1;
-    int phase = 0;
-    for (int level = 0; ncur > 0; ++level) {
-        int nwarps = 32 >> level;
-        if (nwarps < 4) nwarps = 1;                  // below 4 warps per node: one warp per node
-        const int ngroups = 32 / nwarps;
-        const int grp = (tid >> 5) / nwarps;
-        const int gt = tid - grp * nwarps * 32;
-        const int bar_id = 1 + grp;                  // <= 8 multi-warp groups -> ids 1..8
-        phase = 0;                                   // (groups were re-formed: restart the scan buffers' alternation)
-        for (int base = 0; base < ncur; base += ngroups) {
-            const int k = base + grp;
-            if (k < ncur) {
-                const int s = cur[3 * k], e = cur[3 * k + 1];
-                int dim = cur[3 * k + 2];
-                const int p = build_node_sm(M, xyz, s, e, &dim, gt, nwarps, bar_id, s_ws + (grp & 7) * 64, phase, s_wd + (grp & 7) * 192);
-                if (p == -2) { if (gt == 0) s_fail = 1; }
-                else if (p >= 0 && gt == 0) {
-                    // children that are leaves need no visit
-                    const int nl = (p - s > kd::LEAFSIZE) ? 1 : 0, nr = (e - p > kd::LEAFSIZE) ? 1 : 0;
-                    if (nl + nr) {
-                        int o = atomicAdd(&s_cnt, nl + nr);
-                        if (nl) { nxt[3 * o] = s; nxt[3 * o + 1] = p; nxt[3 * o + 2] = dim; ++o; }
-                        if (nr) { nxt[3 * o] = p; nxt[3 * o + 1] = e; nxt[3 * o + 2] = dim; }
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        ncur = s_cnt;
-        const int fail = s_fail;
-        __syncthreads();
-        if (fail) return false;
-        if (tid == 0) s_cnt = 0;
-        int* t = cur; cur = nxt; nxt = t;
-        __syncthreads();
-    }
+    if (run_levels(M, xyz, cur, nxt, 1, 1 << 30, s_ws, s_wd, &s_cnt, &s_fail) < 0) return false;
     for (int i = tid; i < n; i += blockDim.x) rank[M.idx[i]] = i;
+    return true;
+}
+
+// The same build split over several CTAs (the build of one graph keeps the issue slots of its SM 46 % busy for 350 us, and it
+// sits on the critical path of the iteration): build_top_block runs the first `top_levels` levels, leaves the permutation so
+// far in idx16 (global), provisional ranks in `rank`, and the nodes of the next level in top[1..] (top[0] = their number, -1 =
+// fall back to the one-CTA build); build_sub_block finishes ONE of those nodes -- a subtree is independent of its siblings --
+// in its own shared memory and writes the final ranks of its range.
+static __device__ void build_top_block(const double* x, const double* y, const double* z, int n, int top_levels, int* rank,
+                                       unsigned short* idx16, int* top /*1 + 3 * 2^top_levels ints*/, char* smem, int* node_a, int* node_b,
+                                       int* s_ws, double* s_wd) {
+    __shared__ int s_cnt, s_fail;
+    View M;
+    M.key = reinterpret_cast<double*>(smem);
+    M.idx = reinterpret_cast<unsigned short*>(M.key + n);
+    M.posR = M.idx + n;
+    const double* const xyz[3] = {x, y, z};
+    const int tid = threadIdx.x;
+    for (int i = tid; i < n; i += blockDim.x) M.idx[i] = (unsigned short)i;
+    int* cur = node_a;
+    int* nxt = node_b;
+    if (tid == 0) { cur[0] = 0; cur[1] = n; cur[2] = -1; s_cnt = 0; s_fail = 0; }
+    __syncthreads();
+    const int left = run_levels(M, xyz, cur, nxt, 1, top_levels, s_ws, s_wd, &s_cnt, &s_fail);
+    if (left < 0) { if (tid == 0) top[0] = -1; return; }
+    for (int i = tid; i < n; i += blockDim.x) { const unsigned short a = M.idx[i]; idx16[i] = a; rank[a] = i; }
+    if (tid == 0) top[0] = left;
+    for (int i = tid; i < 3 * left; i += blockDim.x) top[1 + i] = cur[i];
+}
+
+static __device__ bool build_sub_block(const double* x, const double* y, const double* z, int start, int end, int* rank,
+                                       const unsigned short* idx16, char* smem, int* node_a, int* node_b, int* s_ws, double* s_wd) {
+    __shared__ int s_cnt, s_fail;
+    const int n = end - start;
+    View M;                                          // (positions are absolute: the arrays are addressed with their offset)
+    M.key = reinterpret_cast<double*>(smem) - start;
+    M.idx = reinterpret_cast<unsigned short*>(reinterpret_cast<double*>(smem) + n) - start;
+    M.posR = M.idx + n;
+    const double* const xyz[3] = {x, y, z};
+    const int tid = threadIdx.x;
+    for (int i = start + tid; i < end; i += blockDim.x) M.idx[i] = idx16[i];
+    int* cur = node_a;
+    int* nxt = node_b;
+    if (tid == 0) { cur[0] = start; cur[1] = end; cur[2] = -1; s_cnt = 0; s_fail = 0; }
+    __syncthreads();
+    if (run_levels(M, xyz, cur, nxt, 1, 1 << 30, s_ws, s_wd, &s_cnt, &s_fail) < 0) return false;
+    for (int i = start + tid; i < end; i += blockDim.x) rank[M.idx[i]] = i;
     return true;
 }
 

@@ -245,3 +245,30 @@ def test_kill_scan_fallback_equals_hit_list_path(monkeypatch):
     got, _, _ = growth.grow_batch(cfg, seeds)
     for a, b in zip(want, got):
         assert graph_io.csv_bytes(np.concatenate(a)) == graph_io.csv_bytes(np.concatenate(b))
+
+
+def test_split_kd_build_equals_one_kernel_build(monkeypatch):
+    """OCTA_KD_SPLIT=1: top levels of the cKDTree permutation in one CTA, the four subtrees below them in a CTA each (lower latency
+    of a single loop).  Same graphs as the one-kernel build, byte for byte (the growth contexts read the switch per process, so the
+    split runs in a child process)."""
+    import subprocess, sys, os, hashlib
+    from octa_autosegmentation_b200 import graph_io, growth
+    from octa_autosegmentation_b200.config import default_config
+    cfg = default_config()
+    for m, i in zip(cfg["Greenhouse"]["modes"], (40, 50)):
+        m["I"] = i
+    seeds = [11, 12, 13, 14, 15, 16]
+    want, stats, _ = growth.grow_batch(cfg, seeds)
+    assert sum(s["replay_detail"][0] for s in stats) > 0            # the exact order was needed somewhere
+    digest = hashlib.sha256(b"".join(graph_io.csv_bytes(np.concatenate(g)) for g in want)).hexdigest()
+    code = ("import sys, hashlib, numpy as np; sys.path.insert(0, %r)\n"
+            "from octa_autosegmentation_b200 import graph_io, growth\n"
+            "from octa_autosegmentation_b200.config import default_config\n"
+            "cfg = default_config()\n"
+            "for m, i in zip(cfg['Greenhouse']['modes'], (40, 50)): m['I'] = i\n"
+            "g, _, _ = growth.grow_batch(cfg, %r)\n"
+            "print(hashlib.sha256(b''.join(graph_io.csv_bytes(np.concatenate(x)) for x in g)).hexdigest())\n"
+            % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), seeds))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, OCTA_KD_SPLIT="1"), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.strip().splitlines()[-1] == digest
