@@ -50,7 +50,7 @@ def _max_over_ranks(x, world, dev):
     return float(t.item())
 
 
-def run_config3(args, pin_cores=None):
+def run_config3(args):
     import torch
     import torch.distributed as dist
     from PIL import Image
