@@ -119,7 +119,7 @@ def test_dropout_matches_oracle_host_logic(t2i):
     assert np.array_equal(got2, ref2) and len(rl) > 0 and min(rl) >= 0.001
 
 
-@pytest.mark.parametrize("knob", [{"OCTA_VOX_SLOWCAP": "0"}, {"OCTA_VOX_SLOWCAP": "3"}, {"OCTA_VOX_TILE_Y": "8"}, {"OCTA_VOX_KERNEL": "rows"}])
+@pytest.mark.parametrize("knob", [{"OCTA_VOX_SLOWCAP": "0"}, {"OCTA_VOX_SLOWCAP": "3"}, {"OCTA_VOX_TILE_Y": "16"}, {"OCTA_VOX_KERNEL": "rows"}])
 def test_fallback_paths_give_the_same_volume(t2i, monkeypatch, knob):
     """The paths real graphs never (or only by choice) take: a full deferred-cell queue (cells are marked and recomputed from every
     edge of the tile), half-size tiles with four warps, and the row kernel of round 1 -- all bit-identical to the reference digest."""
