@@ -790,7 +790,30 @@ __global__ void __launch_bounds__(128) k_eval(int dslot, GrowShape S, IterP P, i
     const int nd_ = D.n_dict[g];
     const size_t sb = (size_t)g * S.capS, nb = (size_t)g * S.capN;
     const int* loff = D.list_off + (size_t)g * (S.capN + 1);
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nd_; e += gridDim.x * blockDim.x) {
+    // Leaf entries (elongate / bifurcate: covariance + eigenvector) and inter-node entries (sprout) run different code of
+    // thousands of float64 instructions each; in dict order they are mixed, so every warp would run both.  The entries of a chunk
+    // of 128 are dealt to the thread slots by kind instead: leaves from slot 0, inter-nodes from the next multiple of 32 -- a warp
+    // sees one kind.  (An entry's proposal depends on the entry alone: which thread computes it does not matter.)
+    __shared__ unsigned char s_perm[256];
+    __shared__ int s_wcnt[2][4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int chunk = blockIdx.x * 128; chunk < nd_; chunk += gridDim.x * 128) {          // (block-uniform)
+        const int e0 = chunk + tid;
+        int kind = 2;                                                                      // 0 leaf, 1 inter-node, 2 none
+        if (e0 < nd_) kind = D.nnch[f][nb + D.dict_node[nb + e0]] == 0 ? 0 : 1;
+        const unsigned m0 = __ballot_sync(0xffffffffu, kind == 0), m1 = __ballot_sync(0xffffffffu, kind == 1);
+        if (lane == 0) { s_wcnt[0][warp] = __popc(m0); s_wcnt[1][warp] = __popc(m1); }
+        __syncthreads();
+        int b0 = 0, b1 = 0, n0 = 0, n1 = 0;
+        for (int w = 0; w < 4; ++w) { if (w < warp) { b0 += s_wcnt[0][w]; b1 += s_wcnt[1][w]; } n0 += s_wcnt[0][w]; n1 += s_wcnt[1][w]; }
+        const int inter0 = (n0 + 31) & ~31;
+        const unsigned lt = (1u << lane) - 1u;
+        if (kind == 0) s_perm[b0 + __popc(m0 & lt)] = (unsigned char)tid;
+        else if (kind == 1) s_perm[inter0 + b1 + __popc(m1 & lt)] = (unsigned char)tid;
+        __syncthreads();
+      for (int slot = tid; slot < inter0 + n1; slot += 128) {
+        if (slot >= n0 && slot < inter0) continue;
+        const int e = chunk + s_perm[slot];
         const int nd = D.dict_node[nb + e];
         Proposal pr;
         pr.type = P_NONE; pr.cond = 0; pr.ratio5 = 0; pr.c_used = 0;
@@ -806,6 +829,8 @@ __global__ void __launch_bounds__(128) k_eval(int dslot, GrowShape S, IterP P, i
             eval_inter(D, S, P, g, f, nc, lst, n, fast_pow(cv, 1.0 / P.kap_tab[m == 0xff ? 8 : (m >> 1)]), cv, &pr, 1);
         }
         D.prop[nb + e] = pr;
+      }
+        __syncthreads();                                                                   // s_perm / s_wcnt are reused by the next chunk
     }
 }
 
