@@ -487,9 +487,20 @@ __global__ void __launch_bounds__(TILE) k_assign(int dslot, GrowShape S, IterP P
         const int* gi = D.gi[2 + f] + g * gcap;
         const int* cs = D.gcell[2 + f] + (size_t)g * (GRID * GRID + 1);
         const int x0 = grid_cell(px - delta), x1 = grid_cell(px + delta), y0 = grid_cell(py - delta), y1 = grid_cell(py + delta);
+        // rows of cells are visited outwards from the attractor's own row, and a row whose nearest edge is already farther than the
+        // best node found so far is skipped (its points cannot win, nor tie: the bound is strict and slightly loosened) -- the
+        // argmin with ties to the lowest list position is what a scan of every row in the range finds
         double best = INFINITY;
         int bi = -1;
-        for (int cy = y0; cy <= y1; ++cy) {
+        const int cyc = grid_cell(py);
+        for (int step = 0; step <= 2 * (GRID - 1); ++step) {
+            const int cy = (step & 1) ? cyc + ((step + 1) >> 1) : cyc - (step >> 1);
+            if (cy < y0 || cy > y1) { if (cyc - ((step + 1) >> 1) < y0 && cyc + ((step + 1) >> 1) > y1) break; continue; }
+            double dyr = 0.0;                                   // distance of py from the row's band (border rows also hold the outside)
+            if (cy < cyc) dyr = py - (double)(cy + 1) / (double)GRID;
+            else if (cy > cyc) dyr = (double)cy / (double)GRID - py;
+            dyr -= 1e-12;
+            if (dyr > 0.0 && dyr * dyr > best) continue;
             const int beg = cs[cy * GRID + x0], end = cs[cy * GRID + x1 + 1];
             for (int q = beg; q < end; ++q) {
                 const double d2 = dist2(gx[q], gy[q], gz[q], px, py, pz);
