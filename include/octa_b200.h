@@ -128,7 +128,8 @@ typedef struct OctaGrowConfig {
     int32_t cap_nodes, cap_sinks;    /* per-graph capacities; 0 = automatic */
     /* SimulationSpace.oxygen_sample_geometry_path (simulation_space.py:26-34,69-76,95-96): the loaded .npy as a C-order
      * 0/1 byte mask [geom_dims[0]][geom_dims[1]][geom_dims[2]], or NULL.  With a mask, `size` is ignored (the space is
-     * geom_dims / max(geom_dims)).  Supported: 2-D square masks (geom_dims = {n, n, 1}, n <= 76).  Copied at create time. */
+     * geom_dims / max(geom_dims)) and the source walls z0 / z1 become usable (forest.py:152-176).  Any 3-D mask: every dimension
+     * 1..65535 (voxel indices pass through uint16 in the reference, simulation_space.py:108), at most 2^26 voxels.  Copied at create time. */
     const unsigned char* geometry;
     int32_t geom_dims[3];
 } OctaGrowConfig;

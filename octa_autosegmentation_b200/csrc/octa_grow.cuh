@@ -19,7 +19,8 @@ struct IterP {
     double eps_n_eff, eps_s, eps_k, delta[2], gamma[2], phi, omega, kappa, d, r, rotation_radius;
     double faz_cx, faz_cy, param_scale, shape[3];
     int N, t, first_mode, mode_idx, iter;
-    int geom_n;          // fixed sampling geometry: side of the square mask (GrowDev::geom_mask), 0 = none
+    int geom_gs;         // fixed sampling geometry: geometry_size = max(mask.shape) (simulation_space.py:30), 0 = none
+    int geom_dims[3];    // shape of the mask (GrowDev::geom_mask, C order)
     double kap_tab[9];   // kappa of the node's creation mode (arterial_tree.py:32); [8] = 4, the add_node default of the stumps
     double leafc_tab[9]; // r ** kap_tab[q]: what a fresh leaf contributes to a parent of creation mode q (see GrowDev::ncon)
 };
@@ -45,6 +46,7 @@ struct GrowShape {
     int exact_ball_order;   // cKDTree's index permutation for the O2->CO2 insertion order: 2 = built on demand (exact, default), 1 = built every iteration (exact), 0 = list-index order instead (diagnostics)
     int commit_smem; // bytes of dynamic shared memory of k_commit (tree mirror + decision records)
     int kill_rcap;   // hits per call k_kill keeps as a sorted list (<= KILL_RCAP = 4096; beyond: block scans over the sink list; tests shrink it)
+    int geom_cells, geom_nvalid;   // fixed sampling geometry: voxels of the mask and how many of them are set (0 = no mask)
 };
 
 struct GrowDev {
@@ -76,7 +78,8 @@ struct GrowDev {
     double* faz_radius;
     int* n_valid;
     unsigned char* valid_ij;
-    unsigned char* geom_mask;   // [geom_n][geom_n] bytes of SimulationSpace.oxygen_sample_geometry_path (one copy per context), or unused
+    unsigned char* geom_mask;   // bytes of SimulationSpace.oxygen_sample_geometry_path, C order [d0][d1][d2] (one copy per context), or unused
+    unsigned short* geom_valid; // np.argwhere(mask): (i, j, k) per set voxel, C order, shared by every graph of the context
     // scratch
     unsigned int *vi, *ubuf;
     double *cx, *cy, *cz;

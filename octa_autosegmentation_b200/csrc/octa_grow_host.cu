@@ -69,7 +69,7 @@ int py_randbelow(MTState& s, int n) {
 inline double hnorm3(const double* a) { return sqrt(fma(a[2], a[2], fma(a[1], a[1], a[0] * a[0]))); }   // ddot-based norm
 
 // greenhouse.py:17-32, simulation_space.py:16-54, forest.py:38-181
-int init_graph(const OctaGrowConfig& c, uint64_t seed, HostGraphInit* h) {
+int init_graph(const OctaGrowConfig& c, int geom_nvalid, uint64_t seed, HostGraphInit* h) {
     const uint32_t key[2] = {(uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32)};
     mt_init_by_array(h->py_mt, key, key[1] ? 2 : 1);
     mt_init_genrand(h->np_mt, (uint32_t)seed);
@@ -86,12 +86,10 @@ int init_graph(const OctaGrowConfig& c, uint64_t seed, HostGraphInit* h) {
     const bool nerve = (nc[0] - nr <= 1) && (nc[1] - nr <= 1);
     const double ncv[2] = {nc[0] * GEOMETRY_SIZE, nc[1] * GEOMETRY_SIZE}, nrv = nr * GEOMETRY_SIZE;
     h->valid_ij.clear();
-    const int gn = c.geometry ? c.geom_dims[0] : 0;      // fixed geometry: valid_voxels = argwhere(mask) (simulation_space.py:34)
-    if (gn) {
-        for (int i = 0; i < gn; ++i)
-            for (int j = 0; j < gn; ++j)
-                if (c.geometry[i * gn + j]) { h->valid_ij.push_back((unsigned char)i); h->valid_ij.push_back((unsigned char)j); }
-    } else
+    // fixed geometry: valid_voxels = argwhere(mask) (simulation_space.py:34) is the same for every graph -- the context holds
+    // one device copy (GrowDev::geom_valid) and only its length travels per graph
+    const int gn = c.geometry ? std::max(c.geom_dims[0], std::max(c.geom_dims[1], c.geom_dims[2])) : 0;   // geometry_size
+    if (!gn)
     for (int i = 0; i < nx; ++i)
         for (int j = 0; j < ny; ++j) {
             const double a = (double)j - fc[0], b = (double)i - fc[1];
@@ -99,7 +97,7 @@ int init_graph(const OctaGrowConfig& c, uint64_t seed, HostGraphInit* h) {
             if (nerve) { const double e = (double)j - ncv[0], f = (double)i - ncv[1]; ok = ok && (e * e + f * f > nrv * nrv); }
             if (ok) { h->valid_ij.push_back((unsigned char)i); h->valid_ij.push_back((unsigned char)j); }
         }
-    h->n_valid = (int)h->valid_ij.size() / 2;
+    h->n_valid = gn ? geom_nvalid : (int)h->valid_ij.size() / 2;
     if (h->n_valid == 0) { set_error("no valid sampling voxel"); return OCTA_E_ARG; }
     for (int f = 0; f < 2; ++f) {
         h->pos[f].clear(); h->parent[f].clear();
@@ -114,21 +112,35 @@ int init_graph(const OctaGrowConfig& c, uint64_t seed, HostGraphInit* h) {
                 };
                 // fixed geometry (simulation_space.py:69-76): random.choice over argwhere of the wall plane, then
                 // _vox_2_unit_pos (three np.random.uniform(0,1) draws).  The plane index is `0 if first else shape[axis]-1`
-                // with the NORMALISED shape, i.e. 0.0 for a full-length axis: the far walls sample plane 0 as well.
-                auto fixed_wall = [&](int axis, double* a_out, double* z_out) -> bool {
-                    std::vector<int> rows;
-                    for (int q = 0; q < gn; ++q)
-                        if (axis == 0 ? c.geometry[0 * gn + q] : c.geometry[q * gn + 0]) rows.push_back(q);
-                    if (rows.empty()) return false;
-                    const int a = rows[py_randbelow(h->py_mt, (int)rows.size())];
-                    const double idx3[3] = {axis == 0 ? 0.0 : (double)a, axis == 0 ? (double)a : 0.0, 0.0};
+                // with the NORMALISED shape, a float in (-1, 0] that np.take truncates to 0: the far walls sample plane 0
+                // as well, and the float only lands in the coordinate that `del pos_3d[along_axis]` drops.  argwhere of
+                // the 2-D plane lists the two remaining axes (u < v) in C order.
+                auto fixed_wall = [&](int axis, double* a_out, double* b_out) -> bool {
+                    const int u = axis == 0 ? 1 : 0, v = axis == 2 ? 1 : 2;
+                    const int* gd = c.geom_dims;
+                    std::vector<int> cells;
+                    for (int p = 0; p < gd[u]; ++p)
+                        for (int q = 0; q < gd[v]; ++q) {
+                            int idx[3]; idx[axis] = 0; idx[u] = p; idx[v] = q;
+                            if (c.geometry[((size_t)idx[0] * gd[1] + idx[1]) * gd[2] + idx[2]]) { cells.push_back(p); cells.push_back(q); }
+                        }
+                    if (cells.empty()) return false;
+                    const int pick = py_randbelow(h->py_mt, (int)cells.size() / 2);
+                    double idx3[3]; idx3[axis] = 0.0; idx3[u] = (double)cells[2 * pick]; idx3[v] = (double)cells[2 * pick + 1];
                     double p3[3];
                     for (int k = 0; k < 3; ++k) p3[k] = (idx3[k] + np_uniform(h->np_mt, 0, 1)) / (double)gn;
-                    *a_out = axis == 0 ? p3[1] : p3[0];
-                    *z_out = p3[2];
+                    *a_out = p3[u];
+                    *b_out = p3[v];
                     return true;
                 };
-                if (gn && wall < 4) {
+                if (gn && wall >= 4) {      // forest.py:152-176: z0 / z1 (both ask for first=True); usable only with a geometry file
+                    double x, y;
+                    if (!fixed_wall(2, &x, &y)) { set_error("geometry mask: the wall plane has no valid voxel"); return OCTA_E_ARG; }
+                    pos[0] = x; pos[1] = y; pos[2] = wall == 4 ? 0.0 : c.size[2] - 1e-6;
+                    dir[0] = rng_dir(x, c.size[0]);
+                    dir[1] = rng_dir(y, c.size[1]);
+                    dir[2] = wall == 4 ? np_uniform(h->np_mt, 0.1, 1) : np_uniform(h->np_mt, -1, -0.1);
+                } else if (gn) {
                     double a, z;
                     if (!fixed_wall(wall < 2 ? 0 : 1, &a, &z)) { set_error("geometry mask: the wall plane has no valid voxel"); return OCTA_E_ARG; }
                     if (wall < 2) {
@@ -155,8 +167,8 @@ int init_graph(const OctaGrowConfig& c, uint64_t seed, HostGraphInit* h) {
                     dir[1] = wall == 2 ? np_uniform(h->np_mt, 0.1, 1) : np_uniform(h->np_mt, -1, -0.1);
                     dir[2] = rng_dir(z, c.size[2]);
                 } else {
-                    // the reference's z0/z1 branch dereferences an attribute that does not exist (simulation_space.py:83)
-                    set_error("source walls z0/z1 are not usable in the reference either (AttributeError)");
+                    // without a geometry file the reference's z0/z1 branch dereferences an attribute that does not exist (simulation_space.py:83)
+                    set_error("source walls z0/z1 need SimulationSpace.oxygen_sample_geometry_path (the reference raises AttributeError without it)");
                     return OCTA_E_ARG;
                 }
             } else {
@@ -227,7 +239,8 @@ void build_schedule(const OctaGrowConfig& c, std::vector<IterP>* out) {
             P.param_scale = ps;
             for (int k = 0; k < 3; ++k) P.shape[k] = c.size[k];
             P.N = N; P.t = t; P.first_mode = m0.first_mode; P.mode_idx = mi; P.iter = iter++;
-            P.geom_n = c.geometry ? c.geom_dims[0] : 0;
+            P.geom_gs = c.geometry ? std::max(c.geom_dims[0], std::max(c.geom_dims[1], c.geom_dims[2])) : 0;
+            for (int k = 0; k < 3; ++k) P.geom_dims[k] = c.geometry ? c.geom_dims[k] : 0;
             for (int q = 0; q < 8; ++q) P.kap_tab[q] = q < c.n_modes ? c.modes[eff[q]].kappa : 4.0;
             P.kap_tab[8] = 4.0;
             for (int q = 0; q < 9; ++q) P.leafc_tab[q] = pow(P.r, P.kap_tab[q]);
@@ -274,7 +287,8 @@ void carve(Carver& c, const GrowShape& S, GrowDev* D) {
     D->py_buf = c.take<unsigned int>(G * S.pycap); D->py_n = c.take<int>(G); D->py_pos = c.take<int>(G);
     D->py_draws = c.take<long long>(G);
     D->faz_radius = c.take<double>(G); D->n_valid = c.take<int>(G); D->valid_ij = c.take<unsigned char>(G * MAX_VALID * 2);
-    D->geom_mask = c.take<unsigned char>(MAX_VALID);
+    D->geom_mask = c.take<unsigned char>(S.geom_cells > MAX_VALID ? (size_t)S.geom_cells : (size_t)MAX_VALID);
+    D->geom_valid = c.take<unsigned short>(3 * (size_t)(S.geom_nvalid > 0 ? S.geom_nvalid : 1));
     D->vi = c.take<unsigned int>(GC); D->ubuf = c.take<unsigned int>(6 * GC);
     D->cx = c.take<double>(GC); D->cy = c.take<double>(GC); D->cz = c.take<double>(GC);
     D->n_cand = c.take<int>(G); D->cpass = c.take<unsigned char>(GC); D->cstate32 = c.take<unsigned int>(GC);
@@ -409,6 +423,7 @@ struct GrowCtx {
     cudaStream_t main = nullptr, side = nullptr;
     int dslot = -1;             // constant-memory slot of this context's pointer table
     std::vector<unsigned char> geom;   // copy of the fixed sampling geometry (cfg.geometry points here)
+    std::vector<unsigned short> geom_valid;   // np.argwhere(geom) as (i, j, k) triples (uploaded once to GrowDev::geom_valid)
     // Envelope of the node count of each forest after iteration i, over the batches this context has grown so far.  The next run
     // sizes k_commit's shared-memory tree mirror per launch from it: most of the schedule needs a fraction of the 224 KB, and a
     // CTA that holds less shared memory lets other graphs' kernels (other loops in flight) share its SM.  A tree that outgrows the
@@ -481,20 +496,31 @@ extern "C" int octa_grow_create(const OctaGrowConfig* cfg, int max_graphs, void*
     if (rc) return rc;
     OCTA_ARG_CHECK(handle && max_graphs > 0 && max_graphs <= 4096, "bad arguments");
     if (octa_device_count() <= 0) { set_error("octa_grow_create: no CUDA device (there is no CPU fallback)"); return OCTA_E_CUDA; }
-    if (cfg->geometry) {
-        const int n = cfg->geom_dims[0];
-        OCTA_ARG_CHECK(cfg->geom_dims[2] == 1 && cfg->geom_dims[1] == n && n >= 1 && n <= GEOMETRY_SIZE,
-                       "geometry mask must be [n, n, 1] with n <= 76");
+    size_t geom_cells = 0;
+    if (cfg->geometry) {      // any 3-D mask (simulation_space.py:29-34); voxel indices pass through uint16 in the reference (:108)
+        const int* gd = cfg->geom_dims;
+        OCTA_ARG_CHECK(gd[0] >= 1 && gd[1] >= 1 && gd[2] >= 1 && gd[0] <= 65535 && gd[1] <= 65535 && gd[2] <= 65535,
+                       "geometry mask: every dimension must be between 1 and 65535");
+        geom_cells = (size_t)gd[0] * gd[1] * gd[2];
+        OCTA_ARG_CHECK(geom_cells <= ((size_t)1 << 26), "geometry mask: more than 2^26 voxels");
     }
     GrowCtx* ctx = new GrowCtx();
     ctx->dslot = acquire_slot();
     if (ctx->dslot < 0) { delete ctx; set_error("octa_grow_create: too many live growth contexts (max %d)", max_ctx_slots()); return OCTA_E_NOMEM; }
     ctx->cfg = *cfg;
     if (cfg->geometry) {      // own copy of the mask; the space becomes geom_dims / max(geom_dims) (simulation_space.py:31-33)
-        const int n = cfg->geom_dims[0];
-        ctx->geom.assign(cfg->geometry, cfg->geometry + (size_t)n * n);
+        const int* gd = cfg->geom_dims;
+        const int gs = std::max(gd[0], std::max(gd[1], gd[2]));
+        ctx->geom.assign(cfg->geometry, cfg->geometry + geom_cells);
         ctx->cfg.geometry = ctx->geom.data();
-        for (int k = 0; k < 3; ++k) ctx->cfg.size[k] = (double)cfg->geom_dims[k] / (double)n;
+        for (int k = 0; k < 3; ++k) ctx->cfg.size[k] = (double)gd[k] / (double)gs;
+        for (int i = 0; i < gd[0]; ++i)
+            for (int j = 0; j < gd[1]; ++j)
+                for (int k = 0; k < gd[2]; ++k)
+                    if (ctx->geom[((size_t)i * gd[1] + j) * gd[2] + k]) {
+                        ctx->geom_valid.push_back((unsigned short)i); ctx->geom_valid.push_back((unsigned short)j); ctx->geom_valid.push_back((unsigned short)k);
+                    }
+        if (ctx->geom_valid.empty()) { delete ctx; set_error("geometry mask: no valid sampling voxel"); return OCTA_E_ARG; }
     }
     build_schedule(ctx->cfg, &ctx->sched);
     if (ctx->sched.size() > 4096) { delete ctx; set_error("too many iterations (max 4096)"); return OCTA_E_ARG; }
@@ -504,6 +530,8 @@ extern "C" int octa_grow_create(const OctaGrowConfig* cfg, int max_graphs, void*
     GrowShape& S = ctx->S;
     S.G = max_graphs;
     S.Nmax = Nmax;
+    S.geom_cells = (int)geom_cells;
+    S.geom_nvalid = (int)(ctx->geom_valid.size() / 3);
     S.capN = cfg->cap_nodes > 0 ? cfg->cap_nodes : (int)std::min<long>(1 << 20, std::max<long>(4096, align_up((size_t)(total_try / 16 + 4096), 1024)));
     S.capS = cfg->cap_sinks > 0 ? cfg->cap_sinks : (int)std::min<long>(1 << 20, std::max<long>(4096, align_up((size_t)(total_try / 12 + 4096), 1024)));
     S.pycap = 2 * S.capN + 4 * 624;
@@ -534,7 +562,8 @@ extern "C" int octa_grow_create(const OctaGrowConfig* cfg, int max_graphs, void*
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (!ctx->geom.empty() && cudaMemcpy(ctx->D.geom_mask, ctx->geom.data(), ctx->geom.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+    if (!ctx->geom.empty() && (cudaMemcpy(ctx->D.geom_mask, ctx->geom.data(), ctx->geom.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+                               cudaMemcpy(ctx->D.geom_valid, ctx->geom_valid.data(), ctx->geom_valid.size() * sizeof(unsigned short), cudaMemcpyHostToDevice) != cudaSuccess)) {
         set_error("upload of the geometry mask failed"); delete ctx; return OCTA_E_CUDA;
     }
     if (prepare_kernels(S) != 0) { cudaGetLastError(); set_error("cudaFuncSetAttribute(k_commit) failed"); delete ctx; return OCTA_E_CUDA; }
@@ -575,7 +604,7 @@ static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, doub
     // ---- host initialisation (Greenhouse.__init__ + Forest x2), staged and uploaded with strided copies
     std::vector<HostGraphInit> init(n_graphs);
     for (int g = 0; g < n_graphs; ++g) {
-        int rc = init_graph(cfg, seeds[g], &init[g]);
+        int rc = init_graph(cfg, ctx->S.geom_nvalid, seeds[g], &init[g]);
         if (rc) return rc;
     }
     tw[1] = wall();

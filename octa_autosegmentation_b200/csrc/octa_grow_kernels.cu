@@ -175,16 +175,19 @@ __device__ __forceinline__ void sample_body(const GrowDev& D, const GrowShape& S
             const uint32_t v = vi[i];
             const double u0 = mt_double(ub[6 * i], ub[6 * i + 1]), u1 = mt_double(ub[6 * i + 2], ub[6 * i + 3]),
                          u2 = mt_double(ub[6 * i + 4], ub[6 * i + 5]);
-            const double gs = P.geom_n ? (double)P.geom_n : (double)GEOMETRY_SIZE;      // simulation_space.py:31 / :41
-            px = ((double)vij[2 * v] + u0) / gs;
-            py = ((double)vij[2 * v + 1] + u1) / gs;
-            pz = (0.0 + u2) / gs;
+            const double gs = P.geom_gs ? (double)P.geom_gs : (double)GEOMETRY_SIZE;      // simulation_space.py:30 / :41
+            double vx, vy, vz = 0.0;      // the voxel: argwhere row of the mask (3-D), or a pixel of the FAZ mask (positions miss the z dim)
+            if (P.geom_gs) { const unsigned short* t = D.geom_valid + 3 * (size_t)v; vx = (double)t[0]; vy = (double)t[1]; vz = (double)t[2]; }
+            else { vx = (double)vij[2 * v]; vy = (double)vij[2 * v + 1]; }
+            px = (vx + u0) / gs;
+            py = (vy + u1) / gs;
+            pz = (vz + u2) / gs;
             valid = !(px >= P.shape[0] || py >= P.shape[1] || pz >= P.shape[2] || px < 0 || py < 0 || pz < 0);
-            if (valid && P.geom_n) {
+            if (valid && P.geom_gs) {
                 // fixed geometry (simulation_space.py:95-96): geometry[(pos * geometry_size).astype(uint16)] > 0
                 const int vi_ = (int)(unsigned short)(px * gs), vj_ = (int)(unsigned short)(py * gs), vk_ = (int)(unsigned short)(pz * gs);
-                if (vi_ >= P.geom_n || vj_ >= P.geom_n || vk_ >= 1) { D.err[g] = 6; valid = 0; }   // numpy would raise IndexError
-                else valid = D.geom_mask[vi_ * P.geom_n + vj_] != 0;
+                if (vi_ >= P.geom_dims[0] || vj_ >= P.geom_dims[1] || vk_ >= P.geom_dims[2]) { D.err[g] = 6; valid = 0; }   // numpy would raise IndexError
+                else valid = D.geom_mask[((size_t)vi_ * P.geom_dims[1] + vj_) * P.geom_dims[2] + vk_] != 0;
             } else if (valid) {   // zip-truncated eukledian_dist(pos, FAZ_center[voxel units]) > FAZ_radius[voxel units]
                 const double a = px - fzc0, b = py - fzc1;
                 valid = sqrt(a * a + b * b) > fzr;

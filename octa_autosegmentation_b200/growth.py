@@ -65,8 +65,8 @@ def make_config(config: dict, cap_nodes: int = 0, cap_sinks: int = 0) -> OctaGro
     if ss.get("oxygen_sample_geometry_path") is not None:
         # simulation_space.py:29-34: the mask replaces no_voxel_x/y/z (the library copies it at octa_grow_create)
         geo = np.ascontiguousarray(np.load(ss["oxygen_sample_geometry_path"]).astype(bool).astype(np.uint8))
-        if geo.ndim != 3 or geo.shape[2] != 1 or geo.shape[0] != geo.shape[1] or geo.shape[0] > 76:
-            raise NotImplementedError("oxygen_sample_geometry_path: only square 2-D masks of shape [n, n, 1], n <= 76, are supported")
+        if geo.ndim != 3:
+            raise ValueError("oxygen_sample_geometry_path: the array must be 3-D (simulation_space.py:32 unpacks three sizes)")
         c._geometry_keepalive = geo
         c.geometry = geo.ctypes.data
         for k in range(3):

@@ -534,7 +534,7 @@ struct Sim {
     /* simulation space */
     double shape[3];
     int GSZ = 76; /* geometry_size */
-    std::vector<int> valid_voxels; /* pairs (i, j) */
+    std::vector<int> valid_voxels; /* triples (i, j, k); k = 0 without a geometry file (the reference's positions miss the z dim there) */
     double ss_FAZ_center[2], ss_FAZ_radius;
     Forest F[2]; /* 0 arterial, 1 venous */
     PointList node_mesh[2], active_mesh[2];
@@ -566,11 +566,13 @@ struct Sim {
         if (cfg.geometry) { /* simulation_space.py:29-34: shape = geometry.shape / max(geometry.shape); valid = argwhere(geometry) */
             GSZ = std::max(cfg.geom_dims[0], std::max(cfg.geom_dims[1], cfg.geom_dims[2]));
             for (int k = 0; k < 3; ++k) shape[k] = (double)cfg.geom_dims[k] / (double)GSZ;
-            if (cfg.geom_dims[2] != 1) abort(); /* only 2-D masks are restated (valid_voxels holds (i, j) pairs) */
-            valid_voxels.clear();
+            valid_voxels.clear(); /* argwhere of the 3-D mask, C order: triples (i, j, k) */
             for (int i = 0; i < cfg.geom_dims[0]; ++i)
                 for (int j = 0; j < cfg.geom_dims[1]; ++j)
-                    if (cfg.geometry[(size_t)i * cfg.geom_dims[1] + j]) { valid_voxels.push_back(i); valid_voxels.push_back(j); }
+                    for (int k = 0; k < cfg.geom_dims[2]; ++k)
+                        if (cfg.geometry[((size_t)i * cfg.geom_dims[1] + j) * cfg.geom_dims[2] + k]) {
+                            valid_voxels.push_back(i); valid_voxels.push_back(j); valid_voxels.push_back(k);
+                        }
             init_params(cfg.modes[0]);
             return;
         }
@@ -591,7 +593,7 @@ struct Sim {
                     double c = (double)j - ncv[0], e = (double)i - ncv[1];
                     ok = ok && (c * c + e * e > nrv * nrv);
                 }
-                if (ok) { valid_voxels.push_back(i); valid_voxels.push_back(j); }
+                if (ok) { valid_voxels.push_back(i); valid_voxels.push_back(j); valid_voxels.push_back(0); }
             }
         init_params(cfg.modes[0]);
     }
@@ -624,16 +626,24 @@ struct Sim {
             /* simulation_space.py:69-76, fixed geometry: random.choice over argwhere of the wall plane.  ax_index is
                `0 if first else self.shape[axis]-1` with the NORMALISED shape, i.e. 0.0 for a full-length axis: the far
                walls sample plane 0 as well. */
-            auto fixed_wall = [&](int axis, double* a_out, double* z_out) {
-                std::vector<int> rows;
-                if (axis == 0) { for (int y = 0; y < cfg.geom_dims[1]; ++y) if (cfg.geometry[(size_t)0 * cfg.geom_dims[1] + y]) rows.push_back(y); }
-                else { for (int x = 0; x < cfg.geom_dims[0]; ++x) if (cfg.geometry[(size_t)x * cfg.geom_dims[1] + 0]) rows.push_back(x); }
-                const int a = rows[py.randbelow((int)rows.size())];
-                const double idx3[3] = {axis == 0 ? 0.0 : (double)a, axis == 0 ? (double)a : 0.0, 0.0};
+            auto fixed_wall = [&](int axis, double* a_out, double* b_out) {
+                /* np.take(geometry, ax_index, axis) takes plane int(ax_index) = 0 (|shape[axis]-1| < 1 truncates to 0); argwhere of
+                   that 2-D plane lists the two remaining axes in C order; the float ax_index only lands in the coordinate
+                   that `del pos_3d[along_axis]` drops, but _vox_2_unit_pos still draws three uniforms. */
+                const int u = axis == 0 ? 1 : 0, v = axis == 2 ? 1 : 2; /* remaining axes, in order */
+                std::vector<int> cells;
+                for (int p = 0; p < cfg.geom_dims[u]; ++p)
+                    for (int q = 0; q < cfg.geom_dims[v]; ++q) {
+                        int idx[3]; idx[axis] = 0; idx[u] = p; idx[v] = q;
+                        if (cfg.geometry[((size_t)idx[0] * cfg.geom_dims[1] + idx[1]) * cfg.geom_dims[2] + idx[2]]) { cells.push_back(p); cells.push_back(q); }
+                    }
+                if (cells.empty()) abort(); /* random.choice of an empty sequence raises IndexError */
+                const int c = py.randbelow((int)cells.size() / 2);
+                double idx3[3]; idx3[axis] = 0.0; idx3[u] = (double)cells[2 * c]; idx3[v] = (double)cells[2 * c + 1];
                 double p3[3];
                 for (int k = 0; k < 3; ++k) p3[k] = (idx3[k] + (0.0 + 1.0 * np.dbl())) / (double)GSZ; /* _vox_2_unit_pos */
-                *a_out = axis == 0 ? p3[1] : p3[0];
-                *z_out = p3[2];
+                *a_out = p3[u];
+                *b_out = p3[v];
             };
             if (wall == 0 || wall == 1) {
                 double y, z;
@@ -651,8 +661,15 @@ struct Sim {
                 dir[0] = rng_dir(x, shape[0]);
                 dir[1] = wall == 2 ? np.uniform(0.1, 1) : np.uniform(-1, -0.1);
                 dir[2] = rng_dir(z, shape[2]);
+            } else if (cfg.geometry) { /* forest.py:152-176: z0 / z1, both with first=True */
+                double x, y;
+                fixed_wall(2, &x, &y);
+                pos[0] = x; pos[1] = y; pos[2] = wall == 4 ? 0.0 : shape[2] - 1e-6;
+                dir[0] = rng_dir(x, shape[0]);
+                dir[1] = rng_dir(y, shape[1]);
+                dir[2] = wall == 4 ? np.uniform(0.1, 1) : np.uniform(-1, -0.1);
             } else {
-                /* z0/z1 walls reference self.valid_pixels, which does not exist (simulation_space.py:83) */
+                /* without a geometry file z0/z1 walls reference self.valid_pixels, which does not exist (simulation_space.py:83) */
                 abort();
             }
             double nrm = norm3(dir);
@@ -711,15 +728,16 @@ struct Sim {
 
     /* simulation_space.py:57-67 + greenhouse.py:319-341 */
     void sample_oxygen_sinks(int n_try, double eps_n_eff, double eps_s_) {
-        const uint32_t L = (uint32_t)(valid_voxels.size() / 2);
+        const uint32_t L = (uint32_t)(valid_voxels.size() / 3);
         std::vector<uint32_t> vi(n_try);
         for (int i = 0; i < n_try; ++i) vi[i] = np.randint(L);
         std::vector<double> cand;
         cand.reserve(3 * n_try);
         for (int i = 0; i < n_try; ++i) {
             double u0 = np.dbl(), u1 = np.dbl(), u2 = np.dbl(); /* uniform(0,1) = 0 + (1-0)*x */
-            double p[3] = {((double)valid_voxels[2 * vi[i]] + (0.0 + 1.0 * u0)) / (double)GSZ,
-                           ((double)valid_voxels[2 * vi[i] + 1] + (0.0 + 1.0 * u1)) / (double)GSZ, (0.0 + (0.0 + 1.0 * u2)) / (double)GSZ};
+            double p[3] = {((double)valid_voxels[3 * vi[i]] + (0.0 + 1.0 * u0)) / (double)GSZ,
+                           ((double)valid_voxels[3 * vi[i] + 1] + (0.0 + 1.0 * u1)) / (double)GSZ,
+                           ((double)valid_voxels[3 * vi[i] + 2] + (0.0 + 1.0 * u2)) / (double)GSZ};
             if (is_valid_position(p)) cand.insert(cand.end(), p, p + 3);
         }
         std::vector<double> added;

@@ -90,8 +90,8 @@ def make_config(config: dict, ball_order: int = 0, venous: bool = True) -> OGCon
     ss = g["SimulationSpace"]
     if ss.get("oxygen_sample_geometry_path") is not None:
         geo = np.ascontiguousarray(np.load(ss["oxygen_sample_geometry_path"]).astype(bool).astype(np.uint8))
-        if geo.ndim != 3 or geo.shape[2] != 1:
-            raise NotImplementedError("only 2-D geometry masks (shape [X, Y, 1]) are restated in the oracle")
+        if geo.ndim != 3:
+            raise ValueError("the sampling geometry must be a 3-D array (simulation_space.py:32 unpacks three sizes)")
         c._geometry_keepalive = geo
         c.geometry = geo.ctypes.data
         for k in range(3):

@@ -7,6 +7,8 @@
   graph_geom_s{0,1}.csv       the same with SimulationSpace.oxygen_sample_geometry_path = tests/golden/geometry_mask.npy
                               (a synthetic 76x76x1 mask written by geometry_mask(); fixed-geometry branch of
                               simulation_space.py:26-34,69-76,95-96)
+  graph_geom3d_s{0,1}.csv     a 3-D mask (tests/golden/geometry_mask_3d.npy, [40, 84, 8]) with source walls x0, y0, y1, z0, z1
+                              (geometry_mask_3d(), geom3d_config(): 3-D argwhere sampling, z walls of forest.py:152-176)
   vox_small_s0_*.npz          tree2img.voxelize_forest of graph_small_s0.csv for several requests
   vox_docker_s0.json          sha256 / non-zero count of voxelize_forest(graph_docker_s0, [304,304,4]) and,
                               with --full, of the [1216,1216,16] request (77 s in the reference)
@@ -45,6 +47,28 @@ def geometry_mask() -> np.ndarray:
     g[0, :7, 0] = False          # wall plane used by x0 / x1
     g[:5, 0, 0] = False          # wall plane used by y0 / y1
     return g
+
+
+def geometry_mask_3d() -> np.ndarray:
+    """Synthetic 3-D sampling geometry (bool [40, 84, 8], geometry_size 84 > the default 76, x and z shorter than y): an
+    ellipsoidal hole, a blocked slab and partly blocked x / y / z wall planes."""
+    g = np.ones((40, 84, 8), dtype=bool)
+    ii, jj, kk = np.ogrid[:40, :84, :8]
+    g &= (ii - 20) ** 2 + (jj - 45) ** 2 + 4 * (kk - 4) ** 2 > 6.0 ** 2
+    g[30:34, 10:30, 2:] = False
+    g[0, :9, :] = False          # wall plane used by x0 / x1
+    g[:6, 0, :3] = False         # wall plane used by y0 / y1
+    g[:10, :12, 0] = False       # wall plane used by z0 / z1
+    return g
+
+
+def geom3d_config(mask_path: str) -> dict:
+    """small_config grown inside the 3-D mask, trees rooted on x0, y0, y1, z0 and z1 (the z walls only work with a geometry file)."""
+    cfg = rh.small_config(I=(25, 15), N=500)
+    cfg["Greenhouse"]["SimulationSpace"]["oxygen_sample_geometry_path"] = mask_path
+    cfg["Forest"]["source_walls"] = {"x0": True, "x1": False, "y0": True, "y1": True, "z0": True, "z1": True}
+    cfg["Forest"]["N_trees"] = 6
+    return cfg
 
 
 def shipped_pair(name="20230216_232653"):
@@ -97,6 +121,12 @@ def main():
         cfg["Greenhouse"]["SimulationSpace"]["oxygen_sample_geometry_path"] = mask_path
         art, ven, _ = rh.run_growth(cfg, seed)
         with open(os.path.join(GOLD, "graph_geom_s%d.csv" % seed), "wb") as f:
+            f.write(rh.csv_bytes(art, ven))
+    mask3_path = os.path.join(GOLD, "geometry_mask_3d.npy")
+    np.save(mask3_path, geometry_mask_3d())
+    for seed in (0, 1):
+        art, ven, _ = rh.run_growth(geom3d_config(mask3_path), seed)
+        with open(os.path.join(GOLD, "graph_geom3d_s%d.csv" % seed), "wb") as f:
             f.write(rh.csv_bytes(art, ven))
     rows = rh.read_csv_rows(os.path.join(GOLD, "graph_small_s0.csv"))
     cases = {"304x304x4": ([304, 304, 4], {}), "304x304x4_ignz": ([304, 304, 4], {"ignore_z": True}),

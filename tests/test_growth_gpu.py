@@ -161,6 +161,27 @@ def test_fixed_geometry_vs_reference_csv(growth):
         assert got == open(os.path.join(GOLDEN, "graph_geom_s%d.csv" % seed), "rb").read()
 
 
+def test_3d_geometry_and_z_walls_vs_reference_csv(growth, tmp_path):
+    """f-4: a 3-D sampling mask ([40, 84, 8], geometry_size 84) with trees rooted on x0, y0, y1, z0 and z1 -- goldens written by
+    the unmodified reference (oracle/make_golden.py geom3d_config) -- and, against the oracle, a thick slab with trees on all six walls in which the
+    ball queries and the cKDTree order are genuinely three-dimensional."""
+    from test_oracle_growth import geom3d_config
+    graphs, _ = compare_with_oracle(growth, geom3d_config(), [0, 1, 2, 3])
+    for seed in (0, 1):
+        got = numpy_csv(np.concatenate(graphs[seed]))
+        assert got == open(os.path.join(GOLDEN, "graph_geom3d_s%d.csv" % seed), "rb").read()
+    g = np.ones((30, 30, 5), dtype=bool)      # a slab 1/6 as thick as it is wide (the default space: 1/76)
+    ii, jj, kk = np.ogrid[:30, :30, :5]
+    g &= (ii - 15) ** 2 + (jj - 14) ** 2 + (kk - 2) ** 2 > (30 / 7) ** 2
+    np.save(tmp_path / "cube.npy", g)
+    cfg = small_config()
+    for m, i in zip(cfg["Greenhouse"]["modes"], (30, 20)):
+        m["I"], m["N"] = i, 300
+    cfg["Greenhouse"]["SimulationSpace"]["oxygen_sample_geometry_path"] = str(tmp_path / "cube.npy")
+    cfg["Forest"]["source_walls"] = {"x0": True, "x1": True, "y0": True, "y1": True, "z0": True, "z1": True}
+    compare_with_oracle(growth, cfg, [0, 1, 2])
+
+
 def test_docker_config_24_seeds_vs_oracle(growth):
     """the GPU equals the exact-order oracle on docker-config seeds 0-23 (the oracle is byte-identical to the
     reference on the committed goldens).  Runs with the default on-demand cKDTree order (OCTA_BALL_ORDER unset)."""

@@ -113,6 +113,25 @@ def test_fixed_geometry_byte_exact(seed):
     assert got == open(os.path.join(GOLDEN, "graph_geom_s%d.csv" % seed), "rb").read()
 
 
+def geom3d_config():
+    """oracle/make_golden.py geom3d_config(): 3-D mask [40, 84, 8], trees rooted on x0, y0, y1, z0, z1."""
+    cfg = docker_config()
+    for m, i in zip(cfg["Greenhouse"]["modes"], (25, 15)):
+        m["I"], m["N"] = i, 500
+    cfg["Greenhouse"]["SimulationSpace"]["oxygen_sample_geometry_path"] = os.path.join(GOLDEN, "geometry_mask_3d.npy")
+    cfg["Forest"]["source_walls"] = {"x0": True, "x1": False, "y0": True, "y1": True, "z0": True, "z1": True}
+    cfg["Forest"]["N_trees"] = 6
+    return cfg
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_3d_geometry_and_z_walls_byte_exact(seed):
+    """A 3-D sampling mask (simulation_space.py:29-34: any .npy; geometry_size 84, argwhere triples, 3-D mask lookup) and
+    the z0 / z1 source walls that only work with a geometry file (forest.py:152-176, simulation_space.py:69-76)."""
+    got, _ = oracle_csv(geom3d_config(), seed)
+    assert got == open(os.path.join(GOLDEN, "graph_geom3d_s%d.csv" % seed), "rb").read()
+
+
 @pytest.mark.parametrize("seed", [0, 1, 2, 3])
 def test_docker_config_byte_exact(seed):
     """BASELINE config #1: docker/vessel_graph_gen_docker_config.yml, fixed seed."""
