@@ -162,6 +162,11 @@ int octa_grow_run(void* handle, const uint64_t* seeds, int n_graphs, double* edg
 int octa_grow_run_packed(void* handle, const uint64_t* seeds, int n_graphs, double* edges7_out, int64_t cap_total_edges,
                          int64_t* edge_offsets, int64_t* n_art_edges, int64_t* n_ven_edges, OctaGrowStats* stats,
                          int32_t* trace, double* device_ms);
+/* Final sink lists of graph `graph` (0 <= graph < n_graphs) of the context's LAST successful run -- what Greenhouse.save_stats
+ * plots (greenhouse.py:401-418: oxy_mesh / co2_mesh .get_all_elements()).  which: 0 = oxygen sinks, 1 = CO2 sources; rows
+ * (x, y, z) in list order.  *n receives the count, also when xyz_out is NULL or cap rows are too few (OCTA_E_NOMEM then).
+ * The per-iteration node / sink counts of the same plot set are the `trace` argument of the run calls. */
+int octa_grow_sinks(void* handle, int graph, int which, double* xyz_out, int64_t cap, int64_t* n);
 void octa_grow_destroy(void* handle);
 
 /* ------------------------------------------------------------------------------------------------

@@ -424,6 +424,7 @@ struct GrowCtx {
     int dslot = -1;             // constant-memory slot of this context's pointer table
     std::vector<unsigned char> geom;   // copy of the fixed sampling geometry (cfg.geometry points here)
     std::vector<unsigned short> geom_valid;   // np.argwhere(geom) as (i, j, k) triples (uploaded once to GrowDev::geom_valid)
+    int last_n = 0;             // graphs of the last finished run (octa_grow_sinks reads their final sink lists)
     // Envelope of the node count of each forest after iteration i, over the batches this context has grown so far.  The next run
     // sizes k_commit's shared-memory tree mirror per launch from it: most of the schedule needs a fraction of the 224 KB, and a
     // CTA that holds less shared memory lets other graphs' kernels (other loops in flight) share its SM.  A tree that outgrows the
@@ -869,6 +870,7 @@ static int grow_run_impl(void* handle, const uint64_t* seeds, int n_graphs, doub
         if (!packed_offsets && n_art_edges[g] + n_ven_edges[g] > cap_edges && !worst) worst = 100;
         if (packed_offsets && n_art_edges[g] + n_ven_edges[g] != row0[g + 1] - row0[g] && !worst) worst = 101;
     }
+    ctx->last_n = worst ? 0 : n_graphs;
     if (worst) {
         set_error("octa_grow_run: simulation error code %d (1 node capacity, 2 sink capacity, 3 rng buffer, "
                   "5 set table, 6 sample outside the geometry mask array, 12/13 eigen solver, 100 edge buffer too small)", worst);
@@ -889,6 +891,25 @@ extern "C" int octa_grow_run_packed(void* handle, const uint64_t* seeds, int n_g
     OCTA_ARG_CHECK(edge_offsets, "edge_offsets is null");
     return grow_run_impl(handle, seeds, n_graphs, edges7_out, cap_total_edges, n_art_edges, n_ven_edges, stats, trace, device_ms,
                          edge_offsets);
+}
+
+extern "C" int octa_grow_sinks(void* handle, int graph, int which, double* xyz_out, int64_t cap, int64_t* n) {
+    GrowCtx* ctx = (GrowCtx*)handle;
+    OCTA_ARG_CHECK(ctx && n && (which == 0 || which == 1), "bad arguments");
+    OCTA_ARG_CHECK(graph >= 0 && graph < ctx->last_n, "graph index outside the context's last run");
+    const GrowDev& D = ctx->D;
+    int cnt = 0;
+    OCTA_CUDA_CHECK(cudaMemcpy(&cnt, D.n_s[which] + graph, sizeof(int), cudaMemcpyDeviceToHost));
+    *n = cnt;
+    if (!xyz_out || cap < cnt) { set_error("octa_grow_sinks: buffer holds %lld rows, %d needed", (long long)(xyz_out ? cap : 0), cnt); return OCTA_E_NOMEM; }
+    if (cnt == 0) return OCTA_OK;
+    std::vector<double> soa((size_t)3 * cnt);
+    const size_t o = (size_t)graph * ctx->S.capS;
+    OCTA_CUDA_CHECK(cudaMemcpy(soa.data(), D.sx[which] + o, 8 * (size_t)cnt, cudaMemcpyDeviceToHost));
+    OCTA_CUDA_CHECK(cudaMemcpy(soa.data() + cnt, D.sy[which] + o, 8 * (size_t)cnt, cudaMemcpyDeviceToHost));
+    OCTA_CUDA_CHECK(cudaMemcpy(soa.data() + 2 * (size_t)cnt, D.sz[which] + o, 8 * (size_t)cnt, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < cnt; ++i) { xyz_out[3 * i] = soa[i]; xyz_out[3 * i + 1] = soa[cnt + i]; xyz_out[3 * i + 2] = soa[2 * (size_t)cnt + i]; }
+    return OCTA_OK;
 }
 
 extern "C" int octa_grow_batch_host(const OctaGrowConfig* cfg, const uint64_t* seeds, int n_graphs, double* edges7_out,

@@ -45,10 +45,9 @@ def volume_dimension(config: dict):
     return [int(d) for d in growth.simspace_shape(config) * config["output"]["image_scale_factor"]]
 
 
-def write_sample(config: dict, csv_bytes, image, volume) -> str:
-    """Files of one grown sample (generate_vessel_graph.py:28-30,59-86); csv_bytes / image / volume may be None."""
-    from PIL import Image
-
+def write_sample(config: dict, csv_bytes, image, volume, stats=None) -> str:
+    """Files of one grown sample (generate_vessel_graph.py:28-30,59-89); csv_bytes / image / volume / stats may be None.
+    stats = (oxygen sinks, CO2 sources, per_step [iterations, 4], seconds per iteration, radius_list): output.save_stats."""
     out_cfg = config["output"]
     out_dir = prepare_output_dir(out_cfg)
     with open(os.path.join(out_dir, "config.yml"), "w") as f:
@@ -68,7 +67,23 @@ def write_sample(config: dict, csv_bytes, image, volume) -> str:
             nib.save(nib.Nifti1Image(vol, np.eye(4)), f"{out_dir}/art_ven_img_gray.nii.gz")
     if image is not None:
         graph_io.save_png(f"{out_dir}/art_ven_img_gray.png", image.astype(np.uint8))
+    if stats is not None:
+        from . import stats_plots
+        oxys, co2s, per_step, seconds, radius_list = stats
+        stats_plots.save_stats(out_dir, oxys, co2s, per_step, seconds)               # generate_vessel_graph.py:40-41
+        stats_plots.plot_vessel_radii(out_dir, radius_list)                           # :88-89
     return out_dir
+
+
+def stats_radius_list(out_cfg: dict, edges7: np.ndarray) -> np.ndarray:
+    """The radius_list generate_vessel_graph.py:88-89 hands to plot_vessel_radii: rasterize_forest's 1.3 x radius of every edge
+    (tree2img.py:82-83; arterial rows, then venous) when save_2D_image is on -- the list is reset before the rasters
+    (:78-79) --, else voxelize_forest's plain radii (tree2img.py:196-238) when only volumes are written, else empty."""
+    if out_cfg["save_2D_image"]:
+        return edges7[:, 6] * 1.3
+    if out_cfg.get("save_3D_volumes"):
+        return edges7[:, 6].copy()
+    return np.zeros(0)
 
 
 def generate(config: dict, seeds, batch: int = 32, in_flight: int = 8, writer_threads: int = 4, device=None, gather: bool = False,
@@ -79,8 +94,9 @@ def generate(config: dict, seeds, batch: int = 32, in_flight: int = 8, writer_th
     image_res = [*dims]
     del image_res[out_cfg["proj_axis"]]
     save3d = bool(out_cfg.get("save_3D_volumes"))
+    save_stats = bool(out_cfg.get("save_stats"))
     pipe = Pipeline(config, device=device, volume_dims=dims, label_res=None, image_res=image_res, mip_axis=out_cfg["proj_axis"],
-                    voxelize=save3d)
+                    voxelize=save3d, growth_stats=save_stats)
     if save3d:
         in_flight = min(in_flight, 2)               # every buffer set holds a pinned copy of the batch's volumes
     batches = [list(seeds[k:k + batch]) for k in range(0, len(seeds), batch)]
@@ -93,7 +109,14 @@ def generate(config: dict, seeds, batch: int = 32, in_flight: int = 8, writer_th
             for i in range(n):
                 img = np.array(out["image_host"][i]) if out_cfg["save_2D_image"] else None        # copies: the pinned buffers are recycled
                 vol = np.array(out["volume_host"][i]) if save3d else None
-                futs.append(writers.submit(write_sample, config, bytes(out["csv"][i]) if write_csv else None, img, vol))      # (copy: may be a view of a pinned buffer)
+                st = None
+                if save_stats:
+                    gs = out["growth_stats"]
+                    # the loop grows the whole batch together: its device time, spread evenly over iterations and samples
+                    sec = np.full(gs["iterations"], gs["loop_seconds"] / max(1, gs["iterations"] * n))
+                    st = (gs["sinks"][i][0], gs["sinks"][i][1], gs["per_step"][i], sec,
+                          stats_radius_list(out_cfg, np.concatenate(out["graphs"][i])))
+                futs.append(writers.submit(write_sample, config, bytes(out["csv"][i]) if write_csv else None, img, vol, st))      # (copy: may be a view of a pinned buffer)
                 if gather:
                     tables[batches[bi][i]] = np.concatenate(out["graphs"][i]).copy()
             if save3d:                                 # 157 MB per sample: let the files land before the next batch's copies
@@ -123,8 +146,6 @@ def main(argv=None):
     apply_cli_overrides_from_unknown_args(config, unknown)
     assert config["output"].get("save_3D_volumes") in [None, "npy", "nifti"], \
         f"Your provided option {config['output'].get('save_3D_volumes')} for 'save_3D_volumes' does not exist. Choose one of 'null', 'npy' or 'nifti'."
-    if config["output"].get("save_stats"):
-        warnings.warn("output.save_stats (matplotlib statistic plots) is not produced by the GPU path")
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     import torch
     local = int(os.environ.get("LOCAL_RANK", "0"))

@@ -106,6 +106,8 @@ def _bind():
     L.octa_grow_run_packed.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.POINTER(ctypes.c_double)]
+    L.octa_grow_sinks.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
+                                  ctypes.POINTER(ctypes.c_int64)]
     L.octa_grow_destroy.argtypes = [ctypes.c_void_p]
     L.octa_grow_destroy.restype = None
     return L
@@ -134,9 +136,10 @@ class GrowContext:
         except Exception:
             pass
 
-    def run_packed(self, seeds: Sequence[int], out: np.ndarray):
+    def run_packed(self, seeds: Sequence[int], out: np.ndarray, trace: np.ndarray = None):
         """Rows of all graphs packed back to back into `out` (float64 [cap, 7], e.g. a view of pinned memory).
-        Returns (offsets int64 [n+1], n_art int64 [n], stats, device_ms)."""
+        Returns (offsets int64 [n+1], n_art int64 [n], stats, device_ms).  `trace` (optional, int32 [n, 4096, 4], C order)
+        receives the per-iteration counts (arterial nodes, O2 sinks, venous nodes, CO2 sources)."""
         n = len(seeds)
         if n > self.max_graphs:
             raise ValueError("batch larger than the context")
@@ -147,14 +150,29 @@ class GrowContext:
         st = (OctaGrowStats * n)()
         ms = ctypes.c_double(0)
         rc = self.L.octa_grow_run_packed(self._h, sd.ctypes.data, n, out.ctypes.data, out.shape[0], offs.ctypes.data,
-                                         na.ctypes.data, nv.ctypes.data, ctypes.cast(st, ctypes.c_void_p), None,
-                                         ctypes.byref(ms))
+                                         na.ctypes.data, nv.ctypes.data, ctypes.cast(st, ctypes.c_void_p),
+                                         trace.ctypes.data if trace is not None else None, ctypes.byref(ms))
         stats = [{k: (list(getattr(st[i], k)) if k in ('commit_cycles', 'replay_detail') else getattr(st[i], k)) for k, _ in OctaGrowStats._fields_} for i in range(n)]
         if rc != 0:
             err = _lib.OctaError(rc, self.L.octa_last_error().decode(errors="replace"))
             err.stats = stats
             raise err
         return offs, na, stats, ms.value
+
+    def sinks(self, graph: int):
+        """(oxygen sinks [n, 3], CO2 sources [m, 3]) graph `graph` of the LAST run ended with, in list order: what
+        Greenhouse.save_stats scatters (greenhouse.py:403,412; octa_grow_sinks)."""
+        out = []
+        for which in (0, 1):
+            n = ctypes.c_int64(0)
+            rc = self.L.octa_grow_sinks(self._h, int(graph), which, None, 0, ctypes.byref(n))
+            if rc not in (0, _lib.OCTA_E_NOMEM):
+                _lib.check(rc)
+            a = np.empty((n.value, 3))
+            if n.value:
+                _lib.check(self.L.octa_grow_sinks(self._h, int(graph), which, a.ctypes.data, n.value, ctypes.byref(n)))
+            out.append(a)
+        return tuple(out)
 
     def run(self, seeds: Sequence[int], trace: bool = False, copy: bool = True):
         n = len(seeds)

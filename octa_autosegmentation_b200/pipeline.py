@@ -22,7 +22,7 @@ from . import graph_io, growth, tree2img
 class Pipeline:
     def __init__(self, config: dict, device=None, volume_dims: Sequence[int] = (1216, 1216, 16),
                  label_res: Sequence[int] = (1216, 1216), image_res: Sequence[int] = (304, 304), mip_axis: int = 2,
-                 voxelize: bool = True, host_threads: int = 0):
+                 voxelize: bool = True, host_threads: int = 0, growth_stats: bool = False):
         import torch
 
         self.torch = torch
@@ -33,6 +33,9 @@ class Pipeline:
         self.image_res = [int(d) for d in image_res]
         self.mip_axis = int(mip_axis)
         self.voxelize = bool(voxelize)
+        # output.save_stats (greenhouse.py:401-441): every result also carries out["growth_stats"] = {"per_step": int32
+        # [n, iterations, 4], "sinks": [(oxygen sinks [k, 3], CO2 sources [m, 3]) per sample], "iterations", "loop_seconds"}
+        self.growth_stats = bool(growth_stats)
         ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 2)     # (ranks are pinned to core slices)
         self.host_threads = host_threads or max(1, ncores - 1)
         self._buf = {}
@@ -92,7 +95,13 @@ class Pipeline:
             # resident results are handed out before that stream has run.  Waiting here, after ~0.4 s of growth, never blocks in
             # practice; the same wait before the loop delayed every start by the post stream's lag (482 -> 450 graphs/s).
             ctx_edges = self._tensor("edges_ctx%d" % ctx, (cap, 7), torch.float64, pinned=True)
-            offs, n_art, stats, grow_ms = g.run_packed(seeds, ctx_edges.numpy())
+            tr = np.zeros((n, 4096, 4), dtype=np.int32) if self.growth_stats else None
+            offs, n_art, stats, grow_ms = g.run_packed(seeds, ctx_edges.numpy(), trace=tr)
+            gstats = None
+            if self.growth_stats:       # the context keeps the final sink lists until its next run: fetched under its lock
+                n_it = int(stats[0]["n_iters"]) if n else 0
+                gstats = {"per_step": tr[:, :n_it].copy(), "sinks": [g.sinks(i) for i in range(n)], "iterations": n_it,
+                          "loop_seconds": grow_ms * 1e-3}
             ev = self._h2d_done.get(slot)
             if ev is not None:
                 ev.synchronize()
@@ -101,6 +110,7 @@ class Pipeline:
             # grower thread at once, next to the CSV pool
             ctypes.memmove(host_edges.data_ptr(), ctx_edges.data_ptr(), E * 56)
             return {"n": n, "cap": cap, "host_edges": host_edges, "offs": offs, "n_art": n_art, "stats": stats, "grow_ms": grow_ms,
+                    "growth_stats": gstats,
                     "trace": {"ctx": ctx, "slot": slot, "t_submit": t_sub, "t_grow0": t_g0, "t_grow1": time.perf_counter()}}
 
     def _post_stage(self, g: dict, slot: int, d2h: bool, csv: bool, stream=None, d2h_volume: bool = False,
@@ -129,6 +139,8 @@ class Pipeline:
                 graphs = [(he[offs[i]:offs[i] + n_art[i]], he[offs[i] + n_art[i]:offs[i + 1]]) for i in range(n)]   # views
                 out = {"graphs": graphs, "stats": g["stats"], "offsets": offs, "n_art": n_art, "grow_device_ms": g["grow_ms"],
                        "edges_host": he[:E], "h2d_bytes": int(E * 56), "d2h_bytes": 0}
+                if g.get("growth_stats") is not None:
+                    out["growth_stats"] = g["growth_stats"]
                 from . import _lib
                 L = _lib.lib()
                 if self.voxelize:

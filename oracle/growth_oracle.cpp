@@ -1162,6 +1162,16 @@ extern "C" {
 
 /* Runs one seeded sample.  edges7_out receives arterial rows then venous rows (cap rows available).
  * Returns total rows (may exceed cap -> call again with a larger buffer), or <0 on error. */
+/* final sink lists of the calling thread's last run: what Greenhouse.save_stats scatters (greenhouse.py:401-418) */
+static thread_local std::vector<double> g_last_sinks[2];
+
+long og_last_sinks(int which, double* xyz_out, long cap) {
+    if (which < 0 || which > 1) return -1;
+    const long n = (long)g_last_sinks[which].size() / 3;
+    if (xyz_out && cap >= n) memcpy(xyz_out, g_last_sinks[which].data(), sizeof(double) * 3 * (size_t)n);
+    return n;
+}
+
 long growth_oracle_run(const OGConfig* cfg, uint64_t seed, double* edges7_out, long cap, long* n_art_edges,
                        long* n_ven_edges, OGStats* stats, og_eig_hook eig, og_trace_hook trace) {
     if (!cfg || cfg->n_modes < 1 || cfg->n_modes > 8 || cfg->n_walls < 0 || cfg->n_walls > 6) return -1;
@@ -1186,6 +1196,8 @@ long growth_oracle_run(const OGConfig* cfg, uint64_t seed, double* edges7_out, l
     s->st.n_co2_left = s->co2.size();
     s->st.np_u32 = s->np.g.drawn;
     if (stats) *stats = s->st;
+    g_last_sinks[0] = s->oxy.xyz;
+    g_last_sinks[1] = s->co2.xyz;
     delete s;
     return na + nv;
 }

@@ -64,6 +64,8 @@ def lib():
         L.growth_oracle_run.argtypes = [ctypes.POINTER(OGConfig), ctypes.c_uint64, ctypes.c_void_p, ctypes.c_long,
                                         ctypes.POINTER(ctypes.c_long), ctypes.POINTER(ctypes.c_long),
                                         ctypes.POINTER(OGStats), ctypes.c_void_p, ctypes.c_void_p]
+        L.og_last_sinks.restype = ctypes.c_long
+        L.og_last_sinks.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_long]
         L.og_hash_tuple3.restype = ctypes.c_int64
         L.og_hash_tuple3.argtypes = [ctypes.c_void_p]
         L.og_set_order.restype = ctypes.c_long
@@ -156,6 +158,17 @@ def run(config: dict, seed: int, ball_order: int = 0, use_numpy_eig: bool = True
         cap = int(n)
     stats = {k: getattr(st, k) for k, _ in OGStats._fields_}
     return out[:na.value].copy(), out[na.value:n].copy(), stats
+
+
+def last_sinks():
+    """(oxygen sinks [n, 3], CO2 sources [m, 3]) of this thread's last run(), in list order (greenhouse.py:403,412)."""
+    out = []
+    for which in (0, 1):
+        n = lib().og_last_sinks(which, None, 0)
+        a = np.empty((n, 3))
+        lib().og_last_sinks(which, a.ctypes.data, n)
+        out.append(a)
+    return tuple(out)
 
 
 def csv_bytes(edges7: np.ndarray) -> bytes:

@@ -7,6 +7,8 @@
   graph_geom_s{0,1}.csv       the same with SimulationSpace.oxygen_sample_geometry_path = tests/golden/geometry_mask.npy
                               (a synthetic 76x76x1 mask written by geometry_mask(); fixed-geometry branch of
                               simulation_space.py:26-34,69-76,95-96)
+  stats_small_s0.npz          the data Greenhouse.save_stats plots for graph_small_s0: oxy_mesh / co2_mesh .get_all_elements()
+                              and the *_per_step lists (incl. their leading 0 entry)
   graph_geom3d_s{0,1}.csv     a 3-D mask (tests/golden/geometry_mask_3d.npy, [40, 84, 8]) with source walls x0, y0, y1, z0, z1
                               (geometry_mask_3d(), geom3d_config(): 3-D argwhere sampling, z walls of forest.py:152-176)
   vox_small_s0_*.npz          tree2img.voxelize_forest of graph_small_s0.csv for several requests
@@ -114,6 +116,11 @@ def main():
         art, ven, _ = rh.run_growth(rh.small_config(), seed)
         with open(os.path.join(GOLD, "graph_small_s%d.csv" % seed), "wb") as f:
             f.write(rh.csv_bytes(art, ven))
+    # what Greenhouse.save_stats plots (greenhouse.py:401-441) for graph_small_s0: final sink lists, per-iteration counts
+    _, _, gh = rh.run_growth(rh.small_config(), 0)
+    np.savez_compressed(os.path.join(GOLD, "stats_small_s0.npz"), oxys=np.array(gh.oxy_mesh.get_all_elements()),
+                        co2s=np.array(gh.co2_mesh.get_all_elements()),
+                        per_step=np.stack([gh.art_nodes_per_step, gh.oxys_per_step, gh.ven_nodes_per_step, gh.co2_per_step], 1))
     mask_path = os.path.join(GOLD, "geometry_mask.npy")
     np.save(mask_path, geometry_mask())
     for seed in (0, 1):

@@ -126,3 +126,26 @@ def test_generate_cli_writes_reference_files(tmp_path):
         vol = np.load(os.path.join(d, "art_ven_img_gray.npy"))
         want = np.maximum(vox_oracle.voxelize_edges(oa, dims), vox_oracle.voxelize_edges(ov, dims)).astype(np.uint8)
         assert vol.dtype == np.uint8 and np.array_equal(vol, want)
+
+
+def test_generate_cli_save_stats(tmp_path):
+    """output.save_stats (on in the reference's main config, configs/dataset_18_June_2023.yml:57): every sample folder also gets
+    the five statistic plots of generate_vessel_graph.py:40-41,88-89 -- and the data behind them is the reference's (the sink
+    lists and per-iteration counts of graph_small_s0 as the unmodified reference held them, tests/golden/stats_small_s0.npz)."""
+    from PIL import Image
+    from octa_autosegmentation_b200 import generate_vessel_graph as cli
+    from octa_autosegmentation_b200.pipeline import Pipeline
+    cfg, yml = small_cfg(tmp_path, save_stats=True, image_scale_factor=152)
+    assert cli.main(["--config_file", str(yml), "--num_samples", "2", "--seed", "0", "--batch", "2", "--in_flight", "1"]) == 0
+    dirs = sorted(glob.glob(os.path.join(cfg["output"]["directory"], "*")))
+    assert len(dirs) == 2
+    for d in dirs:
+        for name, size in (("oxy_distribution", (600, 600)), ("co2_distribution", (600, 600)), ("time_per_step", (600, 600)),
+                           ("growth_over_time", (600, 600)), ("hist", (640, 480))):
+            im = Image.open(os.path.join(d, name + ".png"))
+            assert im.size == size and len(im.getcolors(1 << 16)) > 2, name
+    pipe = Pipeline(cfg, volume_dims=[152, 152, 1], label_res=None, image_res=[152, 152], voxelize=False, growth_stats=True)
+    gs = pipe.run([0, 1], d2h=True, csv=False)["growth_stats"]
+    gold = np.load(os.path.join(GOLDEN, "stats_small_s0.npz"))
+    assert gs["iterations"] == 24 and np.array_equal(gs["per_step"][0], gold["per_step"][1:])
+    assert np.array_equal(gs["sinks"][0][0], gold["oxys"]) and np.array_equal(gs["sinks"][0][1], gold["co2s"])

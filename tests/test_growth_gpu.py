@@ -182,6 +182,32 @@ def test_3d_geometry_and_z_walls_vs_reference_csv(growth, tmp_path):
     compare_with_oracle(growth, cfg, [0, 1, 2])
 
 
+def test_final_sink_lists_and_trace_vs_oracle(growth):
+    """octa_grow_sinks + trace: what Greenhouse.save_stats plots (greenhouse.py:401-441).  The oracle's lists equal the
+    reference's (tests/test_oracle_growth.py::test_save_stats_data_vs_reference); here the GPU against the oracle, list order
+    included, for the small config and a longer run inside the fixed sampling geometry."""
+    from oracle import growth_oracle as go
+    geom = small_config()
+    geom["Greenhouse"]["SimulationSpace"]["oxygen_sample_geometry_path"] = os.path.join(GOLDEN, "geometry_mask.npy")
+    for m, i in zip(geom["Greenhouse"]["modes"], (30, 25)):
+        m["I"], m["N"] = i, 600
+    for cfg in (small_config(), geom):
+        ctx = growth.GrowContext(cfg, 3)
+        try:
+            _, stats, extra = ctx.run([0, 1, 2], trace=True)
+            for i, seed in enumerate((0, 1, 2)):
+                tr = []
+                go.run(cfg, seed, trace=lambda t, a, o, v, c, pd, nd: tr.append((a, o, v, c)))
+                oxy, co2 = go.last_sinks()
+                got_oxy, got_co2 = ctx.sinks(i)
+                assert np.array_equal(got_oxy, oxy) and np.array_equal(got_co2, co2), seed
+                assert np.array_equal(extra["trace"][i], np.array(tr)), seed
+            with pytest.raises(Exception):
+                ctx.sinks(3)
+        finally:
+            ctx.close()
+
+
 def test_docker_config_24_seeds_vs_oracle(growth):
     """the GPU equals the exact-order oracle on docker-config seeds 0-23 (the oracle is byte-identical to the
     reference on the committed goldens).  Runs with the default on-demand cKDTree order (OCTA_BALL_ORDER unset)."""

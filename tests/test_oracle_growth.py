@@ -132,6 +132,17 @@ def test_3d_geometry_and_z_walls_byte_exact(seed):
     assert got == open(os.path.join(GOLDEN, "graph_geom3d_s%d.csv" % seed), "rb").read()
 
 
+def test_save_stats_data_vs_reference():
+    """The data Greenhouse.save_stats plots (greenhouse.py:401-441), as the unmodified reference held it after growing
+    graph_small_s0 (oracle/make_golden.py): final oxygen-sink / CO2-source lists in list order and the per-iteration counts."""
+    tr = []
+    go.run(small_config(), 0, trace=lambda t, a, o, v, c, pd, nd: tr.append((a, o, v, c)))
+    oxy, co2 = go.last_sinks()
+    gold = np.load(os.path.join(GOLDEN, "stats_small_s0.npz"))
+    assert np.array_equal(oxy, gold["oxys"]) and np.array_equal(co2, gold["co2s"])
+    assert not gold["per_step"][0].any() and np.array_equal(np.array(tr), gold["per_step"][1:])
+
+
 @pytest.mark.parametrize("seed", [0, 1, 2, 3])
 def test_docker_config_byte_exact(seed):
     """BASELINE config #1: docker/vessel_graph_gen_docker_config.yml, fixed seed."""
