@@ -8,7 +8,7 @@ growth loops in flight, post-processing and CSV text of finished batches beside 
 Per sample, as generate_vessel_graph.py:24-89:  <output.directory>/<YYYYmmdd_HHMMSS>_<uuid4>/
     config.yml                      resolved config (yaml.dump)
     <dirname>.csv                   node1,node2,radius rows (arterial trees first), CRLF          (save_trees)
-    art_ven_img_gray.npy            uint8 volume, np.maximum(arterial, venous)                    (save_3D_volumes: npy)
+    art_ven_img_gray.npy | .nii.gz  uint8 volume, np.maximum(arterial, venous)                    (save_3D_volumes: npy | nifti)
     art_ven_img_gray.png            uint8 gray image, np.maximum(arterial raster, venous raster)  (save_2D_image)
 New optional flags: --seed (sample i uses seed+i for BOTH generators; default: drawn from os.urandom, i.e. unseeded like the
 reference), --batch (samples per growth loop), --in_flight (growth loops in flight), --threads (file-writer threads).  Under
@@ -60,11 +60,7 @@ def write_sample(config: dict, csv_bytes, image, volume, stats=None) -> str:
         if out_cfg["save_3D_volumes"] == "npy":
             np.save(f"{out_dir}/art_ven_img_gray.npy", vol)
         else:
-            try:
-                import nibabel as nib
-            except ImportError as e:
-                raise RuntimeError("save_3D_volumes: nifti needs nibabel, which is not installed; use 'npy'") from e
-            nib.save(nib.Nifti1Image(vol, np.eye(4)), f"{out_dir}/art_ven_img_gray.nii.gz")
+            graph_io.save_nifti(f"{out_dir}/art_ven_img_gray.nii.gz", vol)          # nib.Nifti1Image(vol, np.eye(4)), :76-77
     if image is not None:
         graph_io.save_png(f"{out_dir}/art_ven_img_gray.png", image.astype(np.uint8))
     if stats is not None:

@@ -94,6 +94,70 @@ def save_png(path: str, image: np.ndarray) -> None:
         f.write(png_bytes(image))
 
 
+_NIFTI_CODES = {"uint8": (2, 8), "int16": (4, 16), "int32": (8, 32), "float32": (16, 32), "float64": (64, 64), "int8": (256, 8),
+                "uint16": (512, 16), "uint32": (768, 32), "int64": (1024, 64), "uint64": (1280, 64)}
+
+
+def nifti1_bytes(vol: np.ndarray) -> bytes:
+    """The single-file NIfTI-1 image `nib.Nifti1Image(vol, np.eye(4))` stands for (generate_vessel_graph.py:75-77,
+    visualize_vessel_graphs.py:85-87), uncompressed: the 348-byte header of the NIfTI-1 standard as nibabel fills it for an
+    array and an identity affine (dim = [ndim, *shape, 1...], pixdim = 1, sform 'aligned' = identity rows, qform 'unknown' with
+    qfac 1, scl_slope / scl_inter NaN = "no scaling", vox_offset 352, magic "n+1"), four zero bytes (no extensions), then the
+    voxels in Fortran order.  Written without nibabel (not part of this stack); parity with nibabel's bytes is NOT pinned -- no
+    nibabel here to compare with -- the fields follow the standard and tests/test_host_logic.py reads them back."""
+    import struct
+
+    a = np.asarray(vol)
+    if a.dtype.name not in _NIFTI_CODES:
+        raise ValueError('data dtype "%s" not supported' % a.dtype.name)      # nibabel: HeaderDataError with this text
+    if not 1 <= a.ndim <= 7:
+        raise ValueError("NIfTI-1 holds 1 to 7 dimensions")
+    code, bitpix = _NIFTI_CODES[a.dtype.name]
+    dim = [a.ndim] + list(a.shape) + [1] * (7 - a.ndim)
+    if max(dim) > 32767:
+        raise ValueError("NIfTI-1 dimensions are 16-bit")
+    nan = float("nan")
+    h = struct.pack("<i10s18sihcB", 348, b"", b"", 0, 0, b"\0", 0)                       # sizeof_hdr ... dim_info
+    h += struct.pack("<8h", *dim)
+    h += struct.pack("<3f4h", 0.0, 0.0, 0.0, 0, code, bitpix, 0)                           # intent_p1-3, intent_code, datatype, bitpix, slice_start
+    h += struct.pack("<8f", 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0)                        # pixdim (pixdim[0] = qfac)
+    h += struct.pack("<3fhBB", 352.0, nan, nan, 0, 0, 0)                                   # vox_offset, scl_slope, scl_inter, slice_end, slice_code, xyzt_units
+    h += struct.pack("<4f2i", 0.0, 0.0, 0.0, 0.0, 0, 0)                                    # cal_max, cal_min, slice_duration, toffset, glmax, glmin
+    h += struct.pack("<80s24s2h", b"", b"", 0, 2)                                          # descrip, aux_file, qform_code 0, sform_code 2 (aligned)
+    h += struct.pack("<6f", 0.0, 0.0, 0.0, 0.0, 0.0, 0.0)                                  # quatern_b/c/d, qoffset_x/y/z
+    h += struct.pack("<12f", 1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0)   # srow_x / y / z
+    h += struct.pack("<16s4s", b"", b"n+1\0")
+    assert len(h) == 348
+    return h + b"\0\0\0\0" + a.astype(a.dtype.newbyteorder("<"), copy=False).tobytes(order="F")
+
+
+def save_nifti(path: str, vol: np.ndarray) -> None:
+    """`nib.save(nib.Nifti1Image(vol, np.eye(4)), path)` for `.nii.gz` / `.nii` paths (gzip level 1, nibabel's default)."""
+    import gzip
+    data = nifti1_bytes(vol)
+    if path.endswith(".gz"):
+        with gzip.GzipFile(path, "wb", compresslevel=1) as f:
+            f.write(data)
+    else:
+        with open(path, "wb") as f:
+            f.write(data)
+
+
+def load_nifti(path: str) -> np.ndarray:
+    """Reads back what save_nifti (or any little-endian single-file NIfTI-1 writer) stored; used by the tests."""
+    import gzip
+    import struct
+    raw = gzip.open(path, "rb").read() if path.endswith(".gz") else open(path, "rb").read()
+    if struct.unpack_from("<i", raw, 0)[0] != 348 or raw[344:348] != b"n+1\0":
+        raise ValueError("not a little-endian single-file NIfTI-1 image")
+    dim = struct.unpack_from("<8h", raw, 40)
+    code = struct.unpack_from("<h", raw, 70)[0]
+    name = next(k for k, v in _NIFTI_CODES.items() if v[0] == code)
+    off = int(struct.unpack_from("<f", raw, 108)[0])
+    shape = dim[1:1 + dim[0]]
+    return np.frombuffer(raw, dtype=np.dtype(name).newbyteorder("<"), count=int(np.prod(shape)), offset=off).reshape(shape, order="F")
+
+
 def csv_batch_device(edges_dev, offsets, text_dev, text_offsets_dev, fallback_dev, workspace, stream=None):
     """Device writer (octa_format_csv_batch_dev): the CSV files of a batch, back to back, into `text_dev` (uint8 CUDA tensor);
     `text_offsets_dev` int64 [n+1], `fallback_dev` int32 [n] (!= 0: format that graph with csv_bytes).  Enqueued on `stream`."""

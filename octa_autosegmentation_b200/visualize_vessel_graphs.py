@@ -11,7 +11,7 @@ batches (one voxelize / raster launch per batch of files, file writers in a thre
 Mirrored quirks of the reference: `.npy` volumes are written as bool (:94); the 2-D image is rendered WITHOUT dropout (:95);
 with --save_3d the 2-D file names carry the 3-D suffix, because `name` is extended in place (:81-85,:99-101); the blackdict that
 is pickled next to the 2-D image is the 3-D one (:102-104; without --save_3d that line raises NameError in the reference's
-worker, which its pool swallows: no pickle is written).  NIfTI needs nibabel."""
+worker, which its pool swallows: no pickle is written).  NIfTI files are written by graph_io.save_nifti (no nibabel needed)."""
 from __future__ import annotations
 
 import argparse
@@ -45,11 +45,7 @@ def _write_outputs(args, name, vol, black_dict, img):
         else:
             name += "_3d"
         if args.save_3d_as == ".nii.gz":
-            try:
-                import nibabel as nib
-            except ImportError as e:
-                raise RuntimeError("--save_3d_as .nii.gz needs nibabel, which is not installed; use --save_3d_as .npy") from e
-            nib.save(nib.Nifti1Image(vol, np.eye(4)), os.path.join(args.out_dir, name + ".nii.gz"))
+            graph_io.save_nifti(os.path.join(args.out_dir, name + ".nii.gz"), vol)      # nib.Nifti1Image(vol, np.eye(4)), :85-87
         else:
             np.save(os.path.join(args.out_dir, name + ".npy"), vol.astype(np.bool_))
         if args.max_dropout_prob > 0:

@@ -83,6 +83,18 @@ def test_visualize_cli_gray_images_ignore_z_and_2d_only(source_dir, tmp_path):
     assert np.array_equal(np.array(Image.open(out3 / "1_label.png")), agg_oracle.to_label(ref.astype(np.uint8)))
     with pytest.raises(AssertionError):
         cli.main(["--source_dir", str(source_dir), "--out_dir", str(out3), "--no_save_2d"])
+    # the DEFAULT 3-D container is NIfTI (:39, :85-87): uint16 volume, binarised to 0 / 1 with --binarize, identity affine
+    from octa_autosegmentation_b200 import graph_io
+    out4 = tmp_path / "o4"
+    assert cli.main(["--source_dir", str(source_dir), "--out_dir", str(out4), "--resolution", "64,64,4", "--save_3d", "--no_save_2d",
+                     "--num_samples", "1"]) == 0
+    assert cli.main(["--source_dir", str(source_dir), "--out_dir", str(out4), "--resolution", "64,64,4", "--save_3d", "--no_save_2d",
+                     "--num_samples", "1", "--binarize"]) == 0
+    assert sorted(os.listdir(out4)) == ["1_3d.nii.gz", "1_3d_label.nii.gz"]
+    vol, _ = vox_oracle.voxelize_forest(rows, [64, 64, 4])
+    got = graph_io.load_nifti(str(out4 / "1_3d.nii.gz"))
+    assert got.dtype == np.uint16 and np.array_equal(got, vol)
+    assert np.array_equal(graph_io.load_nifti(str(out4 / "1_3d_label.nii.gz")), (vol >= 0.1).astype(np.uint16))
 
 
 def small_cfg(tmp_path, **out_kw):

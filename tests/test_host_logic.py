@@ -99,3 +99,36 @@ def test_bench_configs_module_and_buffer_sets():
     from octa_autosegmentation_b200.pipeline import Pipeline
     assert all(callable(getattr(bench_configs, "run_config%d" % k)) for k in (3, 4, 5))
     assert Pipeline.buffer_sets(7, True, 1) == 9 and Pipeline.buffer_sets(7, False) == 9 and Pipeline.buffer_sets(7, True) == 20
+
+
+def test_nifti1_writer_fields_and_roundtrip(tmp_path):
+    """graph_io.save_nifti stands in for nib.save(nib.Nifti1Image(vol, np.eye(4)), ...) (generate_vessel_graph.py:75-77,
+    visualize_vessel_graphs.py:85-87).  No nibabel here, so the check is the NIfTI-1 standard itself: field offsets and values of
+    the 348-byte header, Fortran voxel order, gzip container."""
+    import gzip
+    import struct
+    from octa_autosegmentation_b200 import graph_io
+    rng = np.random.default_rng(3)
+    vol = rng.integers(0, 65535, size=(7, 5, 3), dtype=np.uint16)
+    p = str(tmp_path / "v.nii.gz")
+    graph_io.save_nifti(p, vol)
+    raw = gzip.open(p, "rb").read()
+    assert len(raw) == 352 + vol.size * 2
+    assert struct.unpack_from("<i", raw, 0)[0] == 348                                  # sizeof_hdr
+    assert struct.unpack_from("<8h", raw, 40) == (3, 7, 5, 3, 1, 1, 1, 1)              # dim
+    assert struct.unpack_from("<hh", raw, 70) == (512, 16)                             # datatype uint16, bitpix
+    assert struct.unpack_from("<8f", raw, 76) == (1.0,) * 8                            # pixdim, qfac = 1
+    assert struct.unpack_from("<f", raw, 108)[0] == 352.0                              # vox_offset
+    assert all(np.isnan(struct.unpack_from("<2f", raw, 112)))                          # scl_slope / scl_inter: no scaling
+    assert struct.unpack_from("<2h", raw, 252) == (0, 2)                               # qform unknown, sform aligned
+    assert struct.unpack_from("<12f", raw, 280) == (1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0)  # srow_x/y/z = identity
+    assert raw[344:348] == b"n+1\0" and raw[348:352] == b"\0\0\0\0"
+    # Fortran order: the first axis runs fastest
+    assert np.array_equal(np.frombuffer(raw, dtype="<u2", offset=352, count=7), vol[:, 0, 0])
+    assert np.array_equal(graph_io.load_nifti(p), vol)
+    u8 = rng.integers(0, 255, size=(4, 6, 2), dtype=np.uint8)
+    graph_io.save_nifti(str(tmp_path / "u.nii"), u8)
+    raw = open(tmp_path / "u.nii", "rb").read()
+    assert struct.unpack_from("<hh", raw, 70) == (2, 8) and np.array_equal(graph_io.load_nifti(str(tmp_path / "u.nii")), u8)
+    with pytest.raises(ValueError):                # nibabel refuses bool arrays as well
+        graph_io.nifti1_bytes(np.zeros((2, 2, 2), dtype=bool))
