@@ -183,3 +183,37 @@ def test_mode_with_the_first_modes_name_keeps_previous_parameters_like_the_refer
     other = copy.deepcopy(cfg)
     other["Greenhouse"]["modes"][2]["name"] = "third"
     assert oracle_csv(other, 3)[0] != got
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/vessel_graph_generation"), reason="needs /root/reference (build container)")
+def test_random_3d_masks_and_wall_sets_vs_the_reference_itself(tmp_path):
+    """Random sampling geometries (flat, thick, longer than the default 76 voxels) with random source-wall sets, tree counts,
+    schedules and seeds: CSV bytes and final sink lists of the oracle against the unmodified reference run here."""
+    from oracle import ref_harness as rh
+    rng = np.random.default_rng(11)
+    for case in range(6):
+        shape = tuple(int(x) for x in rng.integers(3, 50, size=3))
+        if case % 3 == 0:
+            shape = (shape[0], shape[1], 1)
+        if case == 4:
+            shape = (int(rng.integers(80, 120)), shape[1], int(rng.integers(1, 6)))
+        g = rng.random(shape) > 0.25
+        g[0, :, :] |= rng.random(shape[1:]) > 0.5          # keep the wall planes populated (an empty plane raises in random.choice)
+        g[:, 0, :] |= rng.random((shape[0], shape[2])) > 0.5
+        g[:, :, 0] |= rng.random(shape[:2]) > 0.5
+        np.save(tmp_path / "mask.npy", g)
+        cfg = docker_config()
+        for m, i in zip(cfg["Greenhouse"]["modes"], (int(rng.integers(8, 16)), int(rng.integers(5, 12)))):
+            m["I"], m["N"] = i, int(rng.integers(200, 500))
+        cfg["Greenhouse"]["SimulationSpace"]["oxygen_sample_geometry_path"] = str(tmp_path / "mask.npy")
+        walls = {k: bool(rng.random() > 0.4) for k in ("x0", "x1", "y0", "y1", "z0", "z1")}
+        walls["x0"] = walls["x0"] or not any(walls.values())
+        cfg["Forest"]["source_walls"] = walls
+        cfg["Forest"]["N_trees"] = int(rng.integers(2, 9))
+        seed = int(rng.integers(0, 1000))
+        art, ven, gh = rh.run_growth(cfg, seed)
+        got, _ = oracle_csv(cfg, seed)
+        assert got == rh.csv_bytes(art, ven), (case, shape, walls)
+        oxy, co2 = go.last_sinks()
+        assert np.array_equal(oxy, np.array(gh.oxy_mesh.get_all_elements()).reshape(-1, 3)), (case, shape)
+        assert np.array_equal(co2, np.array(gh.co2_mesh.get_all_elements()).reshape(-1, 3)), (case, shape)
