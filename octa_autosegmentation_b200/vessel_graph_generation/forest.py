@@ -34,7 +34,8 @@ class Forest:
             key = row[3:6].tobytes()
             parent = nodes.get(key)
             if parent is None:
-                name = f'{"Arterial" if self.arterial else "Venous"}Tree{len(self.trees) + 1}'
+                # tree names count from 1 for 'stumps' (forest.py:87-88) and from 0 for 'nerve' (:49-50)
+                name = f'{"Arterial" if self.arterial else "Venous"}Tree{len(self.trees) + (0 if self.config["type"] == "nerve" else 1)}'
                 tree = ArterialTree(name, row[3:6].copy(), float(row[6]), self.size_x, self.size_y, self.size_z, self)
                 self.trees.append(tree)
                 nodes = {key: tree.root}

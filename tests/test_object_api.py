@@ -124,11 +124,12 @@ def test_unseeded_greenhouse_draws_its_seed_from_python_random(monkeypatch):
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/vessel_graph_generation"), reason="needs /root/reference (build container)")
-def test_object_api_against_the_reference_objects(monkeypatch):
+@pytest.mark.parametrize("kind", ["stumps", "nerve"])
+def test_object_api_against_the_reference_objects(monkeypatch, kind):
     """Attributes and iteration of the facade against the unmodified reference's own objects after the same seeded run."""
     from oracle import ref_harness as rh
     monkeypatch.setattr(growth, "GrowContext", OracleContext)
-    cfg = small_config()
+    cfg = small_config() if kind == "stumps" else rh.nerve_config(I=(30, 20), N=800)
     _, gh, art, ven, _, _ = reference_main_csv(cfg, 1)
     _, _, rgh = rh.run_growth(cfg, 1)
     # (the reference rescales its own .d while it grows, greenhouse.py:139-147; at construction both are config d / param_scale)
