@@ -59,3 +59,34 @@ def test_dropout_and_blackdict_semantics():
     assert (vol_a <= vol_c).all() and set(bd).issubset(bd_c)
     full, _ = vox_oracle.voxelize_forest(rows, [96, 96, 4])
     assert (vol_a <= full).all() and (vol_a < full).any()
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/vessel_graph_generation"), reason="needs /root/reference (build container)")
+def test_random_requests_vs_the_reference_itself():
+    """Random volume shapes (flat, tall, permuted axes), row ranges of three reference graphs, radius filters and ignore_z:
+    the oracle against `tree2img.voxelize_forest` of the unmodified reference run here."""
+    from oracle import ref_harness as rh
+    rng = np.random.default_rng(21)
+    graphs = [load_graph_rows(n) for n in ("graph_small_s0.csv", "graph_geom3d_s0.csv", "graph_docker_s0.csv.gz")]
+    filled = 0
+    for case in range(12):
+        rows = graphs[case % 3]
+        k = int(rng.integers(20, 400))
+        start = int(rng.integers(0, len(rows) - k))
+        dims = [int(rng.integers(8, 200)), int(rng.integers(8, 200)), int(rng.integers(1, 40))]
+        if case % 4 == 0:
+            dims[2] = 1
+        if case % 5 == 4:
+            dims = [dims[2] + 3, dims[0], dims[1]]
+        kw = {}
+        if rng.random() < 0.3:
+            kw["ignore_z"] = True
+        if rng.random() < 0.3:
+            kw["min_radius"] = float(rng.uniform(0.0005, 0.002))
+        if rng.random() < 0.3:
+            kw["max_radius"] = float(rng.uniform(0.002, 0.01))
+        ref, _ = rh.voxelize(rows[start:start + k], dims, **kw)
+        got, _ = vox_oracle.voxelize_forest(rows[start:start + k], dims, **kw)
+        assert ref.shape == got.shape and np.array_equal(ref, got), (case, dims, kw)
+        filled += int((ref > 0).any())
+    assert filled >= 8
