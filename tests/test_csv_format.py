@@ -149,3 +149,24 @@ def test_device_formatter_of_the_position_cells_equals_numpy_str():
     assert sum(g is None for g in got) == 0
     assert _fmt_many("octa_test_csvfmt_array3_many", np.array([3.0e9, 0.1, 0.2, np.inf, 0.0, 0.0]), 3) == [None, None]
     assert _fmt_many("octa_test_csvfmt_array3_many", np.array([3.0e7, 0.1, 0.2]), 3) == [str(np.array([3.0e7, 0.1, 0.2]))]
+
+
+def test_all_500_shipped_graphs_round_trip():
+    """Every graph the reference ships (datasets/vessel_graphs/*.csv, 6.8 M rows): parse -> format gives the file back byte for
+    byte.  The only exceptions are files with a row whose 8-decimal text changes numpy's layout decision when read back (one of
+    500: a cell -0.0005954 against 0.59540002 -- the printed values have max/min = 1000.00003 > 1000, so numpy itself switches
+    that row to exponent notation); there the writer must equal numpy's own formatting of the parsed values."""
+    import glob
+    import pytest
+    files = sorted(glob.glob("/root/reference/datasets/vessel_graphs/*.csv"))
+    if len(files) < 500:
+        pytest.skip("needs /root/reference (build container)")
+    differing = []
+    for p in files:
+        raw = open(p, "rb").read()
+        e = graph_io.parse_csv_bytes(raw)
+        out = graph_io.csv_bytes(e)
+        if out != raw:
+            differing.append(p)
+            assert out == python_csv(e), p
+    assert len(differing) <= 2, differing
