@@ -43,6 +43,17 @@ def write_csv(path: str, edges7: np.ndarray) -> None:
 
 def parse_csv_bytes(data: bytes) -> np.ndarray:
     L = _bind()
+    cap = data.count(b"\n") + 1               # a row ends with a newline: one pass instead of count + fill
+    out = np.empty((cap, 7), dtype=np.float64)
+    n = L.octa_parse_csv(data, len(data), out.ctypes.data, cap)
+    if n < 0:
+        _lib.check(int(n))
+    return out[:n] if n <= cap else parse_csv_bytes_two_pass(data)
+
+
+def parse_csv_bytes_two_pass(data: bytes) -> np.ndarray:
+    """Count, then fill (the sizing protocol of octa_parse_csv for callers that cannot bound the row count)."""
+    L = _bind()
     n = L.octa_parse_csv(data, len(data), None, 0)
     if n < 0:
         _lib.check(int(n))

@@ -62,12 +62,26 @@ def _write_outputs(args, name, vol, black_dict, img):
                 pickle.dump(black_dict, f)
 
 
+_READERS = None
+
+
+def _readers():
+    global _READERS
+    if _READERS is None:
+        ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 2)
+        _READERS = cf.ThreadPoolExecutor(max_workers=max(1, min(8, ncores)))
+    return _READERS
+
+
 def render_batch(files, args, resolution, img_res, writers):
     """One batch of csv files: parse, (3-D) host-side dropout exactly like voxelize_forest, ONE voxelize launch and ONE raster
     launch for the whole batch, file writes handed to `writers`."""
     import torch
 
     names, e3, e2, bds = [], [], [], []
+    # the C parser releases the GIL (7 ms per 13 k-row file): the files of the batch are read side by side
+    dropout3d = args.save_3d and args.max_dropout_prob > 0
+    parsed = dict(zip(files, _readers().map(graph_io.read_csv, files))) if (args.save_2d or not dropout3d) else {}
     for fp in files:
         names.append(fp.split("/")[-1].removesuffix(".csv"))
         if args.save_3d and args.max_dropout_prob > 0:
@@ -82,11 +96,11 @@ def render_batch(files, args, resolution, img_res, writers):
                 # the next file's dropout continues from there
                 for _ in range(1 + len(rows)):
                     random()
-                e2.append(graph_io.read_csv(fp))
+                e2.append(parsed[fp])
             else:
                 e2.append(None)
         else:
-            e = graph_io.read_csv(fp)            # C parser of the `[x y z]` cells (tree2img.py:73-76 semantics)
+            e = parsed[fp]                       # C parser of the `[x y z]` cells (tree2img.py:73-76 semantics)
             e3.append(e)
             e2.append(e)
             bds.append({})

@@ -170,3 +170,25 @@ def test_all_500_shipped_graphs_round_trip():
             differing.append(p)
             assert out == python_csv(e), p
     assert len(differing) <= 2, differing
+
+
+def test_parser_reads_cells_like_python_float():
+    """octa_parse_csv against `float(token)` for the `s[1:-1].split(" ")` tokens of the reference's readers (tree2img.py:73-76):
+    both notations numpy writes, repr radii, a leading '+', infinities / nan, values that overflow or underflow, and many random
+    doubles printed with repr (correct rounding of from_chars = strtod = Python)."""
+    rng = np.random.default_rng(8)
+    toks = ["0.", "1.", "-0.", "0.10898903", "-5.9540000e-04", "1.0898903e-01", "+1.5", "inf", "-inf", "nan", "1e400", "-1e400",
+            "1e-400", "4.9e-324", "2.2250738585072014e-308", "1.7976931348623157e+308", "0.1", "123456789.12345678",
+            "9007199254740993", "0.30000000000000004", "5e-324", "1E5", "1.e2", ".5"]
+    toks += [repr(float(x)) for x in rng.standard_normal(300) * 10.0 ** rng.integers(-12, 12, 300)]
+    toks += [repr(float(np.float64(x))) for x in rng.integers(0, 2 ** 63, 200).view(np.float64) if np.isfinite(x)]
+    while len(toks) % 7:
+        toks.append("1.")
+    rows = [toks[i:i + 7] for i in range(0, len(toks), 7)]
+    text = "node1,node2,radius\r\n" + "".join("[%s  %s %s],[ %s %s   %s ],%s\r\n" % tuple(r) for r in rows)
+    got = graph_io.parse_csv_bytes(text.encode())
+    want = np.array([[float(t) for t in r] for r in rows])
+    assert got.shape == want.shape and np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert np.array_equal(got[ok].view(np.uint64), want[ok].view(np.uint64))             # bit for bit, signed zeros included
+    assert np.array_equal(graph_io.parse_csv_bytes_two_pass(text.encode()).view(np.uint64), got.view(np.uint64))
